@@ -1,0 +1,18 @@
+# Builds libdgvit.so (sm_100a only) and nothing else.  `python -c "import __graft_entry__ as g; g.build()"` calls this.
+PKG   := dgvit-depth-goal-guided-vision-transformer-_b200
+CSRC  := $(PKG)/csrc
+NVCC  ?= /usr/local/cuda/bin/nvcc
+FLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall \
+         -Xcompiler -Wno-unused-function --expt-relaxed-constexpr
+LIB   := $(PKG)/libdgvit.so
+SRCS  := $(CSRC)/dgvit.cu $(CSRC)/depth.cu
+HDRS  := $(wildcard $(CSRC)/*.cuh) include/dgvit.h
+
+all: $(LIB)
+
+$(LIB): $(SRCS) $(HDRS)
+	$(NVCC) $(FLAGS) $(EXTRA) -shared -o $@ $(SRCS) -lcuda
+
+clean:
+	rm -f $(LIB)
+.PHONY: all clean

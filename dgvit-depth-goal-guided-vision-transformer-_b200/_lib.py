@@ -1,0 +1,163 @@
+"""ctypes binding of libdgvit.so (include/dgvit.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised.  PyTorch is used only to own device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdgvit.so")
+
+MAX_DEPTH = 16
+ACTOR, CRITIC = 0, 1
+FP32, BF16 = 0, 1
+DROP_NONE, DROP_MASK, DROP_RNG = 0, 1, 2
+
+c_f_p = C.c_void_p  # device pointers travel as integers
+
+
+class Cfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("kind", "img_h", "img_w", "patch_h", "patch_w", "dim", "depth", "heads", "dim_head",
+                 "mlp_dim", "n_act", "n_pstate")]
+
+
+class BlockLayout(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in
+                ("ln1_w", "ln1_b", "qkv_w", "out_w", "out_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class Layout(C.Structure):
+    _fields_ = ([("total", C.c_int64)] +
+                [(n, C.c_int64) for n in ("pos", "cls", "rms_g", "patch_w", "patch_b")] +
+                [("block", BlockLayout * MAX_DEPTH)] +
+                [(n, C.c_int64) for n in ("mlp_head_ln_w", "mlp_head_ln_b", "mlp_head_w", "mlp_head_b",
+                                          "embed_w", "embed_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+                                          "mean_w", "mean_b", "lstd_w", "lstd_b",
+                                          "conv1_w", "conv1_b", "conv2_w", "conv2_b", "conv3_w", "conv3_b",
+                                          "fc3_w", "fc3_b", "fc11_w", "fc11_b", "fc21_w", "fc21_b",
+                                          "fc31_w", "fc31_b")] +
+                [("n_skip", C.c_int32), ("skip_begin", C.c_int64 * 4), ("skip_end", C.c_int64 * 4),
+                 ("alpha_grad_slot", C.c_int64)])
+
+
+class Net(C.Structure):
+    _fields_ = [("cfg", Cfg), ("params", c_f_p), ("grads", c_f_p), ("shadow", c_f_p)]
+
+
+class Drop(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("p", C.c_float), ("keep_mask", c_f_p), ("rng_state", c_f_p),
+                ("stream_id", C.c_uint32)]
+
+
+class ActorIO(C.Structure):
+    _fields_ = [("img", c_f_p), ("pstate", c_f_p), ("eps", c_f_p), ("action_scale", c_f_p),
+                ("action_bias", c_f_p), ("drop", Drop), ("sample_offset", C.c_int32),
+                ("mean", c_f_p), ("log_std", c_f_p), ("action", c_f_p), ("log_prob", c_f_p),
+                ("mean_t", c_f_p), ("eps_out", c_f_p)]
+
+
+class ActorGrad(C.Structure):
+    _fields_ = [("d_mean", c_f_p), ("d_log_std", c_f_p), ("d_action", c_f_p), ("d_log_prob", c_f_p),
+                ("d_mean_t", c_f_p), ("d_log_prob_const", C.c_float)]
+
+
+class CriticIO(C.Structure):
+    _fields_ = [("img", c_f_p), ("pstate", c_f_p), ("action", c_f_p), ("drop", Drop), ("q1", c_f_p), ("q2", c_f_p)]
+
+
+class Adam(C.Structure):
+    _fields_ = [("m", c_f_p), ("v", c_f_p), ("step", c_f_p), ("lr", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("eps", C.c_float)]
+
+
+class Sac(C.Structure):
+    _fields_ = [("actor", Net), ("critic", Net), ("critic_target", Net), ("actor_opt", Adam), ("critic_opt", Adam),
+                ("log_alpha", c_f_p), ("alpha", c_f_p), ("alpha_m", c_f_p), ("alpha_v", c_f_p), ("alpha_step", c_f_p),
+                ("lr_alpha", C.c_float), ("auto_alpha", C.c_int32), ("target_entropy", C.c_float),
+                ("gamma", C.c_float), ("tau", C.c_float), ("do_polyak", C.c_int32), ("precision", C.c_int32),
+                ("global_batch", C.c_int32), ("sample_offset", C.c_int32), ("rng_state", c_f_p),
+                ("action_scale", c_f_p), ("action_bias", c_f_p)]
+
+
+class Batch(C.Structure):
+    _fields_ = [(n, c_f_p) for n in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done")]
+
+
+class Noise(C.Structure):
+    _fields_ = [(n, c_f_p) for n in ("eps_next", "eps_pi", "mask_a_next", "mask_ct", "mask_c", "mask_a", "mask_c_pi")] + \
+               [("drop_mode", C.c_int32)]
+
+
+class SacOut(C.Structure):
+    _fields_ = [("losses", c_f_p), ("debug", c_f_p)]
+
+
+class Replay(C.Structure):
+    _fields_ = [("obs", c_f_p), ("size", C.c_int64), ("frame", C.c_int64), ("pobs", c_f_p), ("next_pobs", c_f_p),
+                ("act", c_f_p), ("rew", c_f_p), ("done", c_f_p), ("n_pstate", C.c_int32), ("n_act", C.c_int32)]
+
+
+# every symbol include/dgvit.h declares: (name, restype, argtypes)
+P = C.POINTER
+SYMBOLS = {
+    "dgvit_version": (C.c_int, []),
+    "dgvit_last_error": (C.c_char_p, []),
+    "dgvit_param_layout": (C.c_int, [P(Cfg), P(Layout)]),
+    "dgvit_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
+    "dgvit_sac_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, P(C.c_size_t)]),
+    "dgvit_refresh_shadow": (C.c_int, [P(Net), C.c_void_p]),
+    "dgvit_actor_forward": (C.c_int, [P(Net), P(ActorIO), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_actor_backward": (C.c_int, [P(Net), P(ActorIO), P(ActorGrad), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_critic_forward": (C.c_int, [P(Net), P(CriticIO), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_critic_backward": (C.c_int, [P(Net), P(CriticIO), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_sac_phase1": (C.c_int, [P(Sac), P(Batch), P(Noise), P(SacOut), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_sac_phase2": (C.c_int, [P(Sac), P(Batch), P(Noise), P(SacOut), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_sac_phase3": (C.c_int, [P(Sac), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_sac_update": (C.c_int, [P(Sac), P(Batch), P(Noise), P(SacOut), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_adam_step": (C.c_int, [P(Net), P(Adam), P(Net), C.c_float, C.c_void_p]),
+    "dgvit_polyak": (C.c_int, [P(Net), P(Net), C.c_float, C.c_void_p]),
+    "dgvit_replay_gather": (C.c_int, [P(Replay), C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
+    "dgvit_depth_scratch_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
+    "dgvit_depth_augment": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libdgvit.so once; raise loudly if it is not built (no CPU / eager fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+                "dgvit_b200 has no fallback path.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().dgvit_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libdgvit {what} failed ({rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def layout_of(cfg: Cfg) -> Layout:
+    out = Layout()
+    check(lib().dgvit_param_layout(C.byref(cfg), C.byref(out)), "param_layout")
+    return out

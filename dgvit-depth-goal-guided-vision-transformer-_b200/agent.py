@@ -1,0 +1,310 @@
+"""SAC agent with the reference's method surface (vn/DRL.py:34-510), fused on the GPU.
+
+``SAC.learn`` runs the whole update (replay gather -> TD target -> critic fwd/bwd/Adam ->
+actor fwd + critic(s,pi) -> policy/alpha losses -> actor bwd/Adam -> alpha Adam -> Polyak)
+as hand-written CUDA kernels behind three C calls, optionally replayed from one CUDA graph.
+Data parallel: one process per GPU, gradient arenas all-reduced (NCCL) between the phases.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .modules import GoTPolicy, GoTQNetwork, set_seed, _stream
+
+
+# --------------------------------------------------------------------------- replay store
+class ReplayStore:
+    """Device-resident ring store with the fields and ``next_of="obs"`` aliasing of the
+    reference's cpprb buffer (vn/DRL.py:80-89).  Index *selection* stays on the host side of
+    the boundary (the reference never updates priorities, so PER sampling is uniform);
+    the row gather is a bit-exact CUDA kernel (``dgvit_replay_gather``)."""
+
+    def __init__(self, size: int, obs_shape=(128, 160), action_dim=2, pstate_dim=2, device="cuda", seed=0):
+        self.size = int(size)
+        self.obs_shape = tuple(obs_shape)
+        self.device = torch.device(device)
+        f = obs_shape[0] * obs_shape[1]
+        # one extra slot: next_obs of the newest transition lives at (idx+1) % (size+1) like cpprb's next_of
+        self.cap = self.size + 1
+        self.obs = torch.zeros(self.cap, f, dtype=torch.float32, device=self.device)
+        self.pobs = torch.zeros(self.cap, pstate_dim, dtype=torch.float32, device=self.device)
+        self.next_pobs = torch.zeros(self.cap, pstate_dim, dtype=torch.float32, device=self.device)
+        self.act = torch.zeros(self.cap, action_dim, dtype=torch.float32, device=self.device)
+        self.rew = torch.zeros(self.cap, 1, dtype=torch.float32, device=self.device)
+        self.done = torch.zeros(self.cap, 1, dtype=torch.float32, device=self.device)
+        self.engage = torch.zeros(self.cap, 1, dtype=torch.float32, device=self.device)
+        self.stored = 0
+        self.head = 0
+        self.action_dim, self.pstate_dim = action_dim, pstate_dim
+        self._gen = torch.Generator().manual_seed(seed)
+
+    def get_stored_size(self):
+        return self.stored
+
+    def add(self, obs, act, pobs, next_pobs, rew, next_obs, engage=0.0, done=0.0):
+        i = self.head
+        j = (i + 1) % self.cap
+        dev = self.device
+        self.obs[i] = torch.as_tensor(np.asarray(obs, dtype=np.float32).reshape(-1)).to(dev)
+        self.obs[j] = torch.as_tensor(np.asarray(next_obs, dtype=np.float32).reshape(-1)).to(dev)
+        self.act[i] = torch.as_tensor(np.asarray(act, dtype=np.float32).reshape(-1)).to(dev)
+        self.pobs[i] = torch.as_tensor(np.asarray(pobs, dtype=np.float32).reshape(-1)).to(dev)
+        self.next_pobs[i] = torch.as_tensor(np.asarray(next_pobs, dtype=np.float32).reshape(-1)).to(dev)
+        self.rew[i] = float(rew)
+        self.done[i] = float(done)
+        self.engage[i] = float(engage)
+        self.head = j if j < self.size else 0
+        self.stored = min(self.stored + 1, self.size)
+
+    def fill_synthetic(self, n: int, seed: int = 3407):
+        """Synthetic transitions written straight on the device."""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        n = min(n, self.size)
+        self.obs[: n + 1] = torch.rand(n + 1, self.obs.shape[1], device=self.device, generator=g)
+        self.pobs[:n, 0] = torch.rand(n, device=self.device, generator=g)
+        self.pobs[:n, 1] = torch.rand(n, device=self.device, generator=g) * 2 - 1
+        self.next_pobs[:n, 0] = torch.rand(n, device=self.device, generator=g)
+        self.next_pobs[:n, 1] = torch.rand(n, device=self.device, generator=g) * 2 - 1
+        self.act[:n] = torch.rand(n, self.action_dim, device=self.device, generator=g) * 2 - 1
+        self.rew[:n] = (torch.randn(n, 1, device=self.device, generator=g) * 20).clamp(-200, 500)
+        self.done[:n] = (torch.rand(n, 1, device=self.device, generator=g) < 0.01).float()
+        self.stored, self.head = n, n % self.size
+
+    def sample_indexes(self, batch_size: int) -> torch.Tensor:
+        return torch.randint(0, max(self.stored, 1), (batch_size,), generator=self._gen, dtype=torch.int64)
+
+    def gather(self, idx: torch.Tensor, out: Dict[str, torch.Tensor]):
+        """out: dict of preallocated device tensors obs,next_obs,pobs,next_pobs,act,rew,done."""
+        B = idx.numel()
+        st = L.Replay(obs=self.obs.data_ptr(), size=self.cap, frame=self.obs.shape[1], pobs=self.pobs.data_ptr(),
+                      next_pobs=self.next_pobs.data_ptr(), act=self.act.data_ptr(), rew=self.rew.data_ptr(),
+                      done=self.done.data_ptr(), n_pstate=self.pstate_dim, n_act=self.action_dim)
+        L.check(L.lib().dgvit_replay_gather(C.byref(st), idx.data_ptr(), B, out["obs"].data_ptr(),
+                                            out["next_obs"].data_ptr(), out["pobs"].data_ptr(),
+                                            out["next_pobs"].data_ptr(), out["act"].data_ptr(), out["rew"].data_ptr(),
+                                            out["done"].data_ptr(), _stream(self.device)), "replay_gather")
+
+
+# --------------------------------------------------------------------------- agent
+class SAC(object):
+    """Reference-compatible constructor (vn/DRL.py:35-39) plus keyword-only backend options."""
+
+    def __init__(self, action_dim, pstate_dim, policy_type, critic_type, policy_attention_fix,
+                 critic_attention_fix, pre_buffer, seed, LR_C=1e-3, LR_A=1e-3, LR_ALPHA=1e-4,
+                 BUFFER_SIZE=int(2e5), TAU=5e-3, POLICY_FREQ=2, GAMMA=0.99, ALPHA=0.05, block=2, head=4,
+                 l_f_size=32, buffer_size_expert=10816, automatic_entropy_tuning=True, *,
+                 precision="bf16", device=None, image_size=(128, 160), mlp_dim=2048,
+                 distributed=False, use_cuda_graph=False):
+        if policy_type != "GaussianTransformer":
+            raise NotImplementedError(f"policy_type={policy_type!r}: only the DGViT actor ('GaussianTransformer') "
+                                      "is on the accelerated path")
+        if critic_type != "Transformer":
+            raise NotImplementedError("critic_type='CNN' (QNetwork) is a 'next' row (SURVEY.md §8 f1); "
+                                      "use critic_type='Transformer'")
+        if policy_attention_fix or critic_attention_fix:
+            raise NotImplementedError("attention_fix (frozen trunk) variants are not on the accelerated path")
+        if not torch.cuda.is_available():
+            raise RuntimeError("dgvit_b200.SAC needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda")
+        self.gamma, self.tau, self.alpha = GAMMA, TAU, ALPHA
+        self.pstate_dim, self.action_dim = pstate_dim, action_dim
+        self.itera = 0
+        self.policy_type, self.critic_type = policy_type, critic_type
+        self.policy_freq = POLICY_FREQ
+        self.automatic_entropy_tuning = automatic_entropy_tuning
+        self.pre_buffer = pre_buffer
+        self.seed = int(seed)
+        self.block, self.head, self.l_f_size = block, head, l_f_size
+        self.precision = precision
+        self.lr_a, self.lr_c, self.lr_alpha = LR_A, LR_C, LR_ALPHA
+        self.distributed = bool(distributed)
+        self.use_cuda_graph = bool(use_cuda_graph)
+
+        torch.manual_seed(self.seed)
+        torch.cuda.manual_seed(self.seed)
+        np.random.seed(self.seed)
+        set_seed(self.seed)
+
+        self.replay_buffer = ReplayStore(BUFFER_SIZE, image_size, action_dim, pstate_dim, self.device, self.seed)
+
+        # construction order == reference (critic, critic_target, policy): same seed -> same weights
+        kw = dict(image_size=image_size, mlp_dim=mlp_dim)
+        self.critic = GoTQNetwork(action_dim, pstate_dim, block, head, l_f_size, **kw).to(self.device)
+        self.critic_target = GoTQNetwork(action_dim, pstate_dim, block, head, l_f_size, **kw).to(self.device)
+        self.target_entropy = -float(action_dim)
+        self.policy = GoTPolicy(action_dim, pstate_dim, block, head, l_f_size, **kw).to(self.device)
+        for m in (self.critic, self.critic_target, self.policy):
+            m.precision = precision
+            m.bind()
+        self.critic_target._arena.copy_(self.critic._arena)          # hard_update (vn/DRL.py:123)
+        self.target_policy = copy.deepcopy(self.policy)               # vn/DRL.py:169 (unused afterwards)
+
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.log_alpha = torch.zeros(1, **f32)
+        self._alpha = torch.full((1,), float(ALPHA), **f32)
+        self._alpha_m = torch.zeros(1, **f32)
+        self._alpha_v = torch.zeros(1, **f32)
+        self._alpha_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._opt = {}
+        for name, mod in (("actor", self.policy), ("critic", self.critic)):
+            n = mod.layout().total
+            self._opt[name] = dict(m=torch.zeros(n, **f32), v=torch.zeros(n, **f32),
+                                   step=torch.zeros(1, dtype=torch.int64, device=dev))
+        self._rng = torch.tensor([self.seed, 0], dtype=torch.int64, device=dev)
+        na = action_dim
+        self._scale = self.policy.action_scale.to(dev, torch.float32).expand(na).contiguous()
+        self._bias = self.policy.action_bias.to(dev, torch.float32).expand(na).contiguous()
+        self._losses = torch.zeros(4, **f32)
+        self._ws = None
+        self._batch = None
+        self._graphs = {}
+        for m in (self.critic, self.critic_target, self.policy):
+            m.refresh_shadow()
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def world(self):
+        return torch.distributed.get_world_size() if self.distributed else 1
+
+    @property
+    def rank(self):
+        return torch.distributed.get_rank() if self.distributed else 0
+
+    def _sac_struct(self, B_local: int, B_global: int, offset: int) -> L.Sac:
+        def adam(name, lr):
+            o = self._opt[name]
+            return L.Adam(m=o["m"].data_ptr(), v=o["v"].data_ptr(), step=o["step"].data_ptr(), lr=lr, beta1=0.9,
+                          beta2=0.999, eps=1e-8)
+        return L.Sac(actor=self.policy.net_struct(), critic=self.critic.net_struct(),
+                     critic_target=self.critic_target.net_struct(), actor_opt=adam("actor", self.lr_a),
+                     critic_opt=adam("critic", self.lr_c), log_alpha=self.log_alpha.data_ptr(),
+                     alpha=self._alpha.data_ptr(), alpha_m=self._alpha_m.data_ptr(), alpha_v=self._alpha_v.data_ptr(),
+                     alpha_step=self._alpha_step.data_ptr(), lr_alpha=self.lr_alpha,
+                     auto_alpha=int(self.automatic_entropy_tuning), target_entropy=self.target_entropy,
+                     gamma=self.gamma, tau=self.tau, do_polyak=int(self.itera % self.policy_freq == 0),
+                     precision={"fp32": L.FP32, "bf16": L.BF16}[self.precision], global_batch=B_global,
+                     sample_offset=offset, rng_state=self._rng.data_ptr(), action_scale=self._scale.data_ptr(),
+                     action_bias=self._bias.data_ptr())
+
+    def _workspace(self, B: int) -> torch.Tensor:
+        n = C.c_size_t()
+        prec = {"fp32": L.FP32, "bf16": L.BF16}[self.precision]
+        L.check(L.lib().dgvit_sac_workspace_bytes(C.byref(self.policy._cfg), B, prec, C.byref(n)), "sac_workspace")
+        if self._ws is None or self._ws.numel() < n.value:
+            self._ws = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _batch_buffers(self, B: int) -> Dict[str, torch.Tensor]:
+        if self._batch is None or self._batch["obs"].shape[0] != B:
+            f = self.replay_buffer.obs.shape[1]
+            z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
+            self._batch = dict(obs=z(B, f), next_obs=z(B, f), pobs=z(B, self.pstate_dim), next_pobs=z(B, self.pstate_dim),
+                               act=z(B, self.action_dim), rew=z(B, 1), done=z(B, 1))
+        return self._batch
+
+    # ------------------------------------------------------------------ the update
+    def update_from_batch(self, batch: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None,
+                          debug: Optional[torch.Tensor] = None, global_batch: Optional[int] = None,
+                          sample_offset: int = 0) -> torch.Tensor:
+        """One SAC update on device tensors (no host sync).  ``noise`` injects the stochastic
+        inputs (parity tests): eps_next, eps_pi [B,na] and keep-masks mask_* [B,N,D] uint8.
+        Returns the device tensor [qf1_loss, policy_loss, qf2_loss, alpha_loss]."""
+        B = batch["obs"].shape[0]
+        Bg = global_batch if global_batch is not None else B * self.world
+        ws = self._workspace(B)
+        s = self._sac_struct(B, Bg, sample_offset)
+        bt = L.Batch(**{k: batch[k].data_ptr() for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew")},
+                     done=batch["done"].data_ptr() if "done" in batch else None)
+        nz = None
+        if noise is not None:
+            nz = L.Noise(**{k: L.ptr(noise.get(k)) for k in ("eps_next", "eps_pi", "mask_a_next", "mask_ct", "mask_c",
+                                                              "mask_a", "mask_c_pi")},
+                         drop_mode=L.DROP_MASK if noise.get("mask_c") is not None else
+                         (L.DROP_NONE if noise.get("no_dropout") else L.DROP_RNG))
+        out = L.SacOut(losses=self._losses.data_ptr(), debug=L.ptr(debug))
+        st = _stream(self.device)
+        lib = L.lib()
+        nzp = C.byref(nz) if nz is not None else None
+        if not self.distributed or self.world == 1:
+            L.check(lib.dgvit_sac_update(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
+                    "sac_update")
+        else:
+            dist = torch.distributed
+            L.check(lib.dgvit_sac_phase1(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
+                    "sac_phase1")
+            dist.all_reduce(self.critic._garena)
+            L.check(lib.dgvit_sac_phase2(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
+                    "sac_phase2")
+            dist.all_reduce(self.policy._garena)
+            L.check(lib.dgvit_sac_phase3(C.byref(s), B, ws.data_ptr(), ws.numel(), st), "sac_phase3")
+            dist.all_reduce(self._losses)
+        self.itera += 1
+        return self._losses
+
+    def learn(self, batch_size=64):
+        """vn/DRL.py:373-437 — returns (qf1_loss, policy_loss) python floats (one D2H read)."""
+        losses = self.learn_async(batch_size)
+        l = losses.tolist()
+        self.alpha = float(self._alpha.item()) if self.automatic_entropy_tuning else self.alpha
+        return l[0], l[1]
+
+    def learn_async(self, batch_size=64) -> torch.Tensor:
+        """Same update without the host read-back (losses stay on the device)."""
+        B = int(batch_size)
+        idx = self.replay_buffer.sample_indexes(B).to(self.device, non_blocking=True)
+        batch = self._batch_buffers(B)
+        self.replay_buffer.gather(idx, batch)
+        return self.update_from_batch(batch)
+
+    # ------------------------------------------------------------------ act
+    def choose_action(self, istate, pstate, evaluate=False):
+        """vn/DRL.py:170-185."""
+        return self.policy.choose_action(istate, pstate, evaluate)
+
+    # ------------------------------------------------------------------ replay write path
+    def store_transition(self, s, a, ps, ps_, r, s_, engage, a_exp, d=0):
+        """vn/DRL.py:449-467."""
+        self.replay_buffer.add(obs=s, act=a if a is not None else a_exp, pobs=ps, next_pobs=ps_, rew=r, next_obs=s_,
+                               engage=engage, done=d)
+
+    # ------------------------------------------------------------------ checkpoints (vn/DRL.py:480-503)
+    def load_model(self, output):
+        if output is None:
+            return
+        self.policy.load_state_dict(torch.load("{}/actor.pkl".format(output)))
+        self.critic.load_state_dict(torch.load("{}/critic.pkl".format(output)))
+        self._after_load()
+
+    def save_model(self, output):
+        torch.save(self.policy.state_dict(), "{}/actor.pkl".format(output))
+        torch.save(self.critic.state_dict(), "{}/critic.pkl".format(output))
+
+    def save(self, filename, directory, reward, seed, nb_col=100):
+        torch.save(self.policy.state_dict(), "%s/%s_reward_%s_nbCol_%s_seed_%s_actor.pth" % (directory, filename, reward, nb_col, seed))
+        torch.save(self.critic.state_dict(), "%s/%s_reward_%s_nbCol_%s_seed_%s_critic.pth" % (directory, filename, reward, nb_col, seed))
+
+    def load(self, filename, directory):
+        self.policy.load_state_dict(torch.load("%s/%s_actor.pth" % (directory, filename)))
+        self.critic.load_state_dict(torch.load("%s/%s_critic.pth" % (directory, filename)))
+        self._after_load()
+
+    def load_target(self):
+        self.critic_target.bind()
+        self.critic_target._arena.copy_(self.critic._arena)
+        self.critic_target.refresh_shadow()
+
+    def load_actor(self, filename, directory):
+        self.policy.load_state_dict(torch.load("%s/%s_actor.pth" % (directory, filename)))
+        self._after_load()
+
+    def _after_load(self):
+        for m in (self.critic, self.critic_target, self.policy):
+            m.bind()
+            m.refresh_shadow()

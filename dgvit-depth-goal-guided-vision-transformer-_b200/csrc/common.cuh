@@ -1,0 +1,160 @@
+// common.cuh — shared host/device helpers of libdgvit (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/dgvit.h"
+
+namespace dgvit {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- error plumbing
+inline std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+struct Fail {
+  int code;
+};
+inline void fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+inline void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  throw Fail{code};
+}
+#define DG_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      ::dgvit::fail(DGVIT_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,                 \
+                    cudaGetErrorString(e__));                                                  \
+  } while (0)
+#define DG_LAUNCH_CHECK() DG_CUDA(cudaGetLastError())
+#define DG_REQUIRE(cond, ...)                                  \
+  do {                                                         \
+    if (!(cond)) ::dgvit::fail(DGVIT_ERR_ARG, __VA_ARGS__);    \
+  } while (0)
+
+// exceptions never cross the C ABI
+template <typename F>
+static inline int guarded(F&& f) {
+  try {
+    f();
+    return DGVIT_OK;
+  } catch (const Fail& e) {
+    return e.code;
+  } catch (const std::exception& e) {
+    last_error() = e.what();
+    return DGVIT_ERR_ARG;
+  } catch (...) {
+    last_error() = "unknown C++ exception";
+    return DGVIT_ERR_ARG;
+  }
+}
+
+// ---------------------------------------------------------------- workspace carving
+struct Carver {
+  char* base;
+  size_t off, cap;
+  bool dry;  // only measure
+  Carver(void* p, size_t cap_, bool dry_ = false) : base((char*)p), off(0), cap(cap_), dry(dry_) {}
+  template <typename T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    size_t o = off;
+    off += bytes;
+    if (dry) return nullptr;
+    if (off > cap) fail(DGVIT_ERR_WORKSPACE, "workspace too small: need >= %zu, have %zu", off, cap);
+    return (T*)(base + o);
+  }
+};
+
+__host__ __device__ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// exact-erf GELU and its derivative (nn.GELU default, vn/GoalFormer.py:44)
+__device__ __forceinline__ float gelu_f(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// ---------------------------------------------------------------- counter-based RNG
+// Philox4x32-10; key = seed, counter = (index, stream_id, update counter).
+struct Philox {
+  uint32_t c[4];
+  uint32_t k[2];
+};
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+  const uint32_t n1 = (uint32_t)p1;
+  const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+  const uint32_t n3 = (uint32_t)p0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__host__ __device__ __forceinline__ void philox4x32(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi,
+                                                    uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)ctr_lo, (uint32_t)(ctr_lo >> 32), (uint32_t)ctr_hi, (uint32_t)(ctr_hi >> 32)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+__host__ __device__ __forceinline__ float u01(uint32_t x) {  // (0,1]
+  return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+// Dropout keep decision shared by forward and backward.
+struct DropDev {
+  int mode;
+  float p, scale;
+  const uint8_t* mask;
+  const uint64_t* rng;
+  uint32_t stream_id;
+  int64_t elem_offset;  // global element index of local element 0 (data-parallel slicing)
+};
+__device__ __forceinline__ float drop_factor(const DropDev& d, int64_t i) {
+  if (d.mode == DGVIT_DROP_NONE) return 1.0f;
+  if (d.mode == DGVIT_DROP_MASK) return d.mask[i] ? d.scale : 0.0f;
+  uint32_t o[4];
+  const uint64_t gi = (uint64_t)(i + d.elem_offset);
+  philox4x32(d.rng[0], gi >> 2, ((uint64_t)d.stream_id << 32) | (d.rng[1] & 0xffffffffu), o);
+  return u01(o[gi & 3]) > d.p ? d.scale : 0.0f;
+}
+
+}  // namespace dgvit

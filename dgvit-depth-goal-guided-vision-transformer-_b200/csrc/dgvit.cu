@@ -1,0 +1,989 @@
+// dgvit.cu — host orchestration + C ABI of libdgvit.so (see include/dgvit.h).
+//
+// Data layout in HBM (per network): one flat fp32 parameter arena in the reference's
+// registration order (+ grads, Adam m/v, bf16 shadow arenas of the same geometry);
+// activations live in a caller-provided workspace carved deterministically from
+// (cfg, B, precision), so a backward call finds what its forward saved.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+#ifdef DGVIT_WITH_TC
+#include "gemm_tc.cuh"
+#endif
+
+namespace dgvit {
+
+// ------------------------------------------------------------------ layout
+static void make_layout(const dgvit_cfg& c, dgvit_layout& L) {
+  DG_REQUIRE(c.depth >= 1 && c.depth <= DGVIT_MAX_DEPTH, "depth %d out of range", c.depth);
+  DG_REQUIRE(c.dim % 32 == 0 && c.dim >= 32 && c.dim <= 256, "dim %d must be a multiple of 32 in [32,256]", c.dim);
+  DG_REQUIRE(c.img_h % c.patch_h == 0 && c.img_w % c.patch_w == 0, "image not divisible by patch");
+  DG_REQUIRE(c.heads >= 1 && c.dim_head >= 1 && c.mlp_dim >= 1 && c.n_act >= 1 && c.n_pstate >= 1, "bad cfg");
+  memset(&L, 0, sizeof(L));
+  int64_t off = 0;
+  auto take = [&](int64_t n) {
+    int64_t o = off;
+    off += (n + DGVIT_ALIGN_FLOATS - 1) / DGVIT_ALIGN_FLOATS * DGVIT_ALIGN_FLOATS;
+    return o;
+  };
+  const int64_t D = c.dim, P = (c.img_h / c.patch_h) * (c.img_w / c.patch_w), pd = c.patch_h * c.patch_w;
+  const int64_t inner = (int64_t)c.heads * c.dim_head, M = c.mlp_dim;
+  L.pos = take((P + 1) * D);
+  L.cls = take(D);
+  L.rms_g = take(D);
+  L.patch_w = take(D * pd);
+  L.patch_b = take(D);
+  for (int l = 0; l < c.depth; ++l) {
+    dgvit_block_layout& b = L.block[l];
+    b.ln1_w = take(D); b.ln1_b = take(D);
+    b.qkv_w = take(3 * inner * D);
+    b.out_w = take(D * inner); b.out_b = take(D);
+    b.ln2_w = take(D); b.ln2_b = take(D);
+    b.fc1_w = take(M * D); b.fc1_b = take(M);
+    b.fc2_w = take(D * M); b.fc2_b = take(D);
+  }
+  L.mlp_head_ln_w = take(D); L.mlp_head_ln_b = take(D);
+  L.mlp_head_w = take(2 * D); L.mlp_head_b = take(2);
+  const int64_t mlp_head_end = off;
+  L.n_skip = 0;
+  L.skip_begin[L.n_skip] = L.cls; L.skip_end[L.n_skip++] = L.rms_g;
+  L.skip_begin[L.n_skip] = L.mlp_head_ln_w; L.skip_end[L.n_skip++] = mlp_head_end;
+  if (c.kind == DGVIT_ACTOR) {
+    L.embed_w = take(D * c.n_pstate); L.embed_b = take(D);
+    L.fc1_w = take(128 * D); L.fc1_b = take(128);
+    L.fc2_w = take(128 * 128); L.fc2_b = take(128);
+    L.mean_w = take(c.n_act * 128); L.mean_b = take(c.n_act);
+    L.lstd_w = take(c.n_act * 128); L.lstd_b = take(c.n_act);
+    L.alpha_grad_slot = take(1);
+    L.skip_begin[L.n_skip] = L.alpha_grad_slot; L.skip_end[L.n_skip++] = off;
+  } else {
+    L.conv1_w = take(16 * 4 * 25); L.conv1_b = take(16);
+    L.conv2_w = take(64 * 16 * 25); L.conv2_b = take(64);
+    L.conv3_w = take(256 * 64 * 25); L.conv3_b = take(256);
+    L.skip_begin[L.n_skip] = L.conv1_w; L.skip_end[L.n_skip++] = off;
+    L.fc1_w = take(128 * (D + c.n_act)); L.fc1_b = take(128);
+    L.fc2_w = take(32 * 128); L.fc2_b = take(32);
+    L.fc3_w = take(c.n_act * 32); L.fc3_b = take(c.n_act);
+    L.embed_w = take(D * c.n_pstate); L.embed_b = take(D);
+    L.fc11_w = take(128 * (D + c.n_act)); L.fc11_b = take(128);
+    L.fc21_w = take(32 * 128); L.fc21_b = take(32);
+    L.fc31_w = take(c.n_act * 32); L.fc31_b = take(c.n_act);
+  }
+  L.total = off;
+}
+
+struct Dims {
+  int B, N, P, D, H, dh, inner, M, pd, L, na, nps;
+  int64_t T;
+  Dims(const dgvit_cfg& c, int B_) {
+    B = B_; P = (c.img_h / c.patch_h) * (c.img_w / c.patch_w); N = P + 1; D = c.dim; H = c.heads;
+    dh = c.dim_head; inner = H * dh; M = c.mlp_dim; pd = c.patch_h * c.patch_w; L = c.depth;
+    na = c.n_act; nps = c.n_pstate; T = (int64_t)B * N;
+  }
+};
+
+// weights in the arithmetic dtype of the contractions
+template <typename A> struct WSel;
+template <> struct WSel<float> {
+  static const float* w(const dgvit_net& n, int64_t off) { return n.params + off; }
+};
+template <> struct WSel<bf16> {
+  static const bf16* w(const dgvit_net& n, int64_t off) { return (const bf16*)n.shadow + off; }
+};
+
+// ------------------------------------------------------------------ GEMM dispatch
+template <typename TA, typename TB, typename TC>
+static void gemm(const GemmArgs& g, cudaStream_t st) {
+#ifdef DGVIT_WITH_TC
+  if (gemm_tc_try<TA, TB, TC>(g, st)) return;
+#endif
+  gemm_simt<TA, TB, TC>(g, st);
+}
+
+// y[R,N] = x[R,K] W[N,K]^T (+epilogue)
+template <typename TA, typename TB, typename TC>
+static void linear_fwd(const TA* x, const TB* W, TC* y, int64_t R, int N, int K, int epi, const float* bias,
+                       cudaStream_t st, const float* resid = nullptr, void* C2 = nullptr, int64_t ldc = -1) {
+  GemmArgs g;
+  g.M = (int)R; g.N = N; g.K = K;
+  g.A = x; g.a_sm = K; g.a_sk = 1;
+  g.B = W; g.b_sk = 1; g.b_sn = K;
+  g.C = y; g.ldc = ldc < 0 ? N : ldc;
+  g.epi = epi; g.bias = bias; g.resid = resid; g.ldr = g.ldc; g.C2 = C2;
+  gemm<TA, TB, TC>(g, st);
+}
+// dx[R,K] = dy[R,N] W[N,K]  (+epilogue)
+template <typename TA, typename TB, typename TC>
+static void linear_bwd_x(const TA* dy, const TB* W, TC* dx, int64_t R, int N, int K, int epi, const void* aux,
+                         int64_t ldaux, cudaStream_t st, int64_t ldy = -1, const float* resid = nullptr) {
+  GemmArgs g;
+  g.M = (int)R; g.N = K; g.K = N;
+  g.A = dy; g.a_sm = ldy < 0 ? N : ldy; g.a_sk = 1;
+  g.B = W; g.b_sk = K; g.b_sn = 1;
+  g.C = dx; g.ldc = K;
+  g.epi = epi; g.aux = aux; g.ldaux = ldaux; g.resid = resid; g.ldr = K;
+  gemm<TA, TB, TC>(g, st);
+}
+// dW[N,K] = dy[R,N]^T x[R,K]   (split-K over R, deterministic) ; db[N] = colsum(dy)
+template <typename TA, typename TB>
+static void linear_bwd_w(const TA* dy, const TB* x, float* dW, float* db, int64_t R, int N, int K,
+                         float* partial, cudaStream_t st, int64_t ldy = -1, int64_t ldx = -1) {
+  if (ldy < 0) ldy = N;
+  if (ldx < 0) ldx = K;
+  GemmArgs g;
+  g.M = N; g.N = K; g.K = (int)R;
+  g.A = dy; g.a_sm = 1; g.a_sk = ldy;
+  g.B = x; g.b_sk = ldx; g.b_sn = 1;
+  g.C = dW; g.ldc = K;
+  g.splitk = pick_splitk(R); g.partial = partial;
+  gemm<TA, TB, float>(g, st);
+  if (db) {
+    const int S = pick_splitk(R);
+    const int64_t rpb = cdiv(R, S);
+    dim3 grid((unsigned)cdiv(N, 128), (unsigned)S);
+    colsum_partial_kernel<TA><<<grid, 128, 0, st>>>(dy, ldy, partial, R, N, rpb);
+    DG_LAUNCH_CHECK();
+    reduce_partials_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(partial, db, S, N);
+    DG_LAUNCH_CHECK();
+  }
+}
+
+static unsigned grid1d(int64_t n, int bs = 256) {
+  int64_t g = cdiv(n, bs);
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+// ------------------------------------------------------------------ trunk context
+template <typename A>
+struct LayerBuf {
+  float *Xa, *Xm, *mean1, *rstd1, *mean2, *rstd2;
+  A *Xn1, *QKV, *O, *Xn2, *Hpre, *Hact;
+};
+template <typename A>
+struct TrunkCtx {
+  A* Pm; float* Xp; float* tok; float* Xout; float* z;
+  LayerBuf<A> L[DGVIT_MAX_DEPTH];
+  // backward scratch (only when saved)
+  float *dX, *dXn, *dtok, *dz, *dg_rows, *partial;
+  A *dH, *dO, *dQKV, *dXp;
+  bf16* dXh;  // bf16 copy of dX (operand of the tensor-core GEMMs); null in the fp32 path
+  size_t partial_floats;
+  // residual-stream gradient in the operand dtype
+  const A* dx_op() const {
+    if constexpr (std::is_same<A, float>::value) return dX; else return dXh;
+  }
+};
+
+template <typename A>
+static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
+  c.Pm = cv.take<A>((int64_t)d.B * d.P * d.pd);
+  c.Xp = cv.take<float>((int64_t)d.B * d.P * d.D);
+  c.tok = cv.take<float>((int64_t)d.B * d.D);
+  c.z = cv.take<float>((int64_t)d.B * d.D);
+  const int nl = save ? d.L : 1;
+  for (int l = 0; l < nl; ++l) {
+    LayerBuf<A>& b = c.L[l];
+    b.Xa = cv.take<float>(d.T * d.D);
+    b.Xm = cv.take<float>(d.T * d.D);
+    b.mean1 = cv.take<float>(d.T); b.rstd1 = cv.take<float>(d.T);
+    b.mean2 = cv.take<float>(d.T); b.rstd2 = cv.take<float>(d.T);
+    b.Xn1 = cv.take<A>(d.T * d.D);
+    b.QKV = cv.take<A>(d.T * 3 * d.inner);
+    b.O = cv.take<A>(d.T * d.inner);
+    b.Xn2 = cv.take<A>(d.T * d.D);
+    b.Hpre = cv.take<A>(d.T * d.M);
+    b.Hact = cv.take<A>(d.T * d.M);
+  }
+  if (save) {
+    c.Xout = cv.take<float>(d.T * d.D);
+  } else {
+    for (int l = 1; l < d.L; ++l) c.L[l] = c.L[0];
+    c.Xout = c.L[0].Xa;  // ping-pong: Xa -> Xm -> Xa
+  }
+  c.dX = nullptr; c.dXn = nullptr; c.dtok = nullptr; c.dz = nullptr; c.dg_rows = nullptr; c.partial = nullptr;
+  c.dH = nullptr; c.dO = nullptr; c.dQKV = nullptr; c.dXp = nullptr; c.dXh = nullptr; c.partial_floats = 0;
+  if (save) {
+    c.dX = cv.take<float>(d.T * d.D);
+    c.dXn = cv.take<float>(d.T * d.D);
+    c.dtok = cv.take<float>((int64_t)d.B * d.D);
+    c.dz = cv.take<float>((int64_t)d.B * d.D);
+    c.dg_rows = cv.take<float>((int64_t)d.B * d.D);
+    c.dH = cv.take<A>(d.T * d.M);
+    c.dO = cv.take<A>(d.T * d.inner);
+    c.dQKV = cv.take<A>(d.T * 3 * d.inner);
+    c.dXp = cv.take<A>((int64_t)d.B * d.P * d.D);
+    c.dXh = std::is_same<A, float>::value ? nullptr : cv.take<bf16>(d.T * d.D);
+    int64_t mx = (int64_t)d.D * d.M;
+    mx = std::max<int64_t>(mx, (int64_t)3 * d.inner * d.D);
+    mx = std::max<int64_t>(mx, (int64_t)d.D * d.pd);
+    mx = std::max<int64_t>(mx, (int64_t)128 * 128);
+    mx = std::max<int64_t>(mx, (int64_t)2 * d.D * 148 * 4 / 32 + 2 * d.D);
+    c.partial_floats = (size_t)mx * 32;
+    c.partial = cv.take<float>(c.partial_floats);
+  }
+}
+
+static DropDev make_drop(const dgvit_drop& d, const Dims& dm, int64_t sample_offset) {
+  DropDev r;
+  r.mode = d.mode;
+  r.p = d.p;
+  r.scale = 1.0f / (float)(1.0 - (double)d.p);
+  r.mask = d.keep_mask;
+  r.rng = d.rng_state;
+  r.stream_id = d.stream_id;
+  r.elem_offset = sample_offset * dm.N * dm.D;
+  if (d.mode == DGVIT_DROP_MASK) DG_REQUIRE(d.keep_mask != nullptr, "DROP_MASK without keep_mask");
+  if (d.mode == DGVIT_DROP_RNG) DG_REQUIRE(d.rng_state != nullptr, "DROP_RNG without rng_state");
+  return r;
+}
+
+template <typename A>
+static void launch_ln_fwd(const float* X, const float* g, const float* b, A* Y, float* mean, float* rstd,
+                          int64_t T, int D, cudaStream_t st) {
+  const int wpb = 8;
+  const unsigned grid = (unsigned)cdiv(T, wpb);
+  switch (D / 32) {
+#define LNF(V) case V: layernorm_fwd_kernel<A, V><<<grid, wpb * 32, 0, st>>>(X, g, b, Y, mean, rstd, T); break;
+    LNF(1) LNF(2) LNF(3) LNF(4) LNF(5) LNF(6) LNF(7) LNF(8)
+#undef LNF
+    default: fail(DGVIT_ERR_ARG, "unsupported dim %d", D);
+  }
+  DG_LAUNCH_CHECK();
+}
+static void launch_ln_bwd(const float* dY, const float* X, const float* mean, const float* rstd,
+                          const float* gamma, float* dX_io, bf16* dX_lp, float* dgamma, float* dbeta,
+                          float* partial, int64_t T, int D, cudaStream_t st) {
+  const int wpb = 8;
+  int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 4);
+  const size_t smem = (size_t)wpb * 2 * D * sizeof(float);
+  switch (D / 32) {
+#define LNB(V) case V: layernorm_bwd_kernel<V><<<nblocks, wpb * 32, smem, st>>>(dY, X, mean, rstd, gamma, dX_io, dX_lp, partial, T); break;
+    LNB(1) LNB(2) LNB(3) LNB(4) LNB(5) LNB(6) LNB(7) LNB(8)
+#undef LNB
+    default: fail(DGVIT_ERR_ARG, "unsupported dim %d", D);
+  }
+  DG_LAUNCH_CHECK();
+  ln_param_reduce_kernel<<<(unsigned)cdiv(2 * D, 128), 128, 0, st>>>(partial, dgamma, dbeta, nblocks, D);
+  DG_LAUNCH_CHECK();
+}
+
+template <typename A>
+static void launch_attention_fwd(const A* QKV, A* O, const Dims& d, cudaStream_t st) {
+  const int threads = 256, nw = threads / 32;
+  const size_t smem = ((size_t)d.N * (d.dh + 1) + (size_t)d.N * d.dh + (size_t)nw * d.N + (size_t)nw * d.dh) * sizeof(float);
+  DG_REQUIRE(smem <= 227 * 1024, "attention_fwd: N=%d dh=%d needs %zu B smem", d.N, d.dh, smem);
+  static bool attr_done = false;  // attribute is per-function; set once per dtype instantiation
+  if (!attr_done) {
+    DG_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  attention_fwd_kernel<A><<<d.B * d.H, threads, smem, st>>>(QKV, O, d.N, d.H, d.dh, 1.0f / sqrtf((float)d.dh));
+  DG_LAUNCH_CHECK();
+}
+template <typename A>
+static void launch_attention_bwd(const A* QKV, const A* O, const A* dO, A* dQKV, const Dims& d, cudaStream_t st) {
+  const int threads = 256, nw = threads / 32;
+  const size_t smem = ((size_t)4 * d.N * (d.dh + 1) + 2 * (size_t)d.N + 2 * (size_t)nw * d.N) * sizeof(float);
+  DG_REQUIRE(smem <= 227 * 1024, "attention_bwd: N=%d dh=%d needs %zu B smem (unsupported in this build)", d.N, d.dh, smem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    DG_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  attention_bwd_kernel<A><<<d.B * d.H, threads, smem, st>>>(QKV, O, dO, dQKV, d.N, d.H, d.dh, 1.0f / sqrtf((float)d.dh));
+  DG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ trunk forward
+// GoT.forward (vn/GoalFormer.py:156-171) given the goal token tok[B,D]; writes c.z.
+template <typename A>
+static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const float* img,
+                          const DropDev& drop, TrunkCtx<A>& c, cudaStream_t st) {
+  const dgvit_cfg& cfg = net.cfg;
+  const float* P = net.params;
+  // K1: patch embedding
+  {
+    const int64_t total = (int64_t)d.B * d.P * d.pd;
+    patchify_kernel<A><<<grid1d(total), 256, 0, st>>>(img, c.Pm, total, cfg.img_h, cfg.img_w, cfg.patch_h, cfg.patch_w);
+    DG_LAUNCH_CHECK();
+    linear_fwd<A, A, float>(c.Pm, WSel<A>::w(net, L.patch_w), c.Xp, (int64_t)d.B * d.P, d.D, d.pd, EPI_BIAS,
+                            P + L.patch_b, st);
+    const int64_t tot2 = d.T * d.D;
+    embed_assemble_kernel<<<grid1d(tot2), 256, 0, st>>>(c.tok, c.Xp, P + L.pos, c.L[0].Xa, drop, tot2, d.N, d.D);
+    DG_LAUNCH_CHECK();
+  }
+  for (int l = 0; l < d.L; ++l) {
+    const dgvit_block_layout& b = L.block[l];
+    LayerBuf<A>& B_ = c.L[l];
+    float* Xnext = (l + 1 < d.L) ? c.L[l + 1].Xa : c.Xout;
+    // attention block: x = attn(LN(x)) + x
+    launch_ln_fwd<A>(B_.Xa, P + b.ln1_w, P + b.ln1_b, B_.Xn1, B_.mean1, B_.rstd1, d.T, d.D, st);
+    linear_fwd<A, A, A>(B_.Xn1, WSel<A>::w(net, b.qkv_w), B_.QKV, d.T, 3 * d.inner, d.D, EPI_NONE, nullptr, st);
+    launch_attention_fwd<A>(B_.QKV, B_.O, d, st);
+    linear_fwd<A, A, float>(B_.O, WSel<A>::w(net, b.out_w), B_.Xm, d.T, d.D, d.inner, EPI_BIAS_RESID, P + b.out_b, st,
+                            B_.Xa);
+    // MLP block: x = ff(LN(x)) + x
+    launch_ln_fwd<A>(B_.Xm, P + b.ln2_w, P + b.ln2_b, B_.Xn2, B_.mean2, B_.rstd2, d.T, d.D, st);
+    linear_fwd<A, A, A>(B_.Xn2, WSel<A>::w(net, b.fc1_w), B_.Hpre, d.T, d.M, d.D, EPI_BIAS_GELU2, P + b.fc1_b, st,
+                        nullptr, B_.Hact);
+    linear_fwd<A, A, float>(B_.Hact, WSel<A>::w(net, b.fc2_w), Xnext, d.T, d.D, d.M, EPI_BIAS_RESID, P + b.fc2_b, st,
+                            B_.Xm);
+  }
+  pool_rmsnorm_fwd_kernel<<<(unsigned)cdiv(d.B, 8), 256, 0, st>>>(c.Xout, P + L.rms_g, c.z, d.B, d.N, d.D,
+                                                                   sqrtf((float)d.D));
+  DG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ trunk backward
+// in: c.dz [B,D]; out: grads of every trunk parameter, c.dtok [B,D]
+template <typename A>
+static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const DropDev& drop,
+                           TrunkCtx<A>& c, int relu_tok, cudaStream_t st) {
+  const float* P = net.params;
+  float* G = net.grads;
+  pool_rmsnorm_bwd_kernel<<<d.B, 128, 0, st>>>(c.Xout, P + L.rms_g, c.dz, c.dX, c.dXh, c.dg_rows, d.B, d.N, d.D,
+                                                sqrtf((float)d.D));
+  DG_LAUNCH_CHECK();
+  {  // dg = sum_b dg_rows
+    const int S = pick_splitk(d.B);
+    dim3 grid((unsigned)cdiv(d.D, 128), (unsigned)S);
+    colsum_partial_kernel<float><<<grid, 128, 0, st>>>(c.dg_rows, d.D, c.partial, d.B, d.D, cdiv(d.B, S));
+    DG_LAUNCH_CHECK();
+    reduce_partials_kernel<<<1, 256, 0, st>>>(c.partial, G + L.rms_g, S, d.D);
+    DG_LAUNCH_CHECK();
+  }
+  for (int l = d.L - 1; l >= 0; --l) {
+    const dgvit_block_layout& b = L.block[l];
+    LayerBuf<A>& B_ = c.L[l];
+    // ---- MLP block.  c.dX = dL/dX_out (fp32 residual-stream gradient; dx_op() = operand copy)
+    linear_bwd_w<A, A>(c.dx_op(), B_.Hact, G + b.fc2_w, G + b.fc2_b, d.T, d.D, d.M, c.partial, st);
+    linear_bwd_x<A, A, A>(c.dx_op(), WSel<A>::w(net, b.fc2_w), c.dH, d.T, d.D, d.M, EPI_GELU_BWD, B_.Hpre, d.M, st);
+    linear_bwd_w<A, A>(c.dH, B_.Xn2, G + b.fc1_w, G + b.fc1_b, d.T, d.M, d.D, c.partial, st);
+    linear_bwd_x<A, A, float>(c.dH, WSel<A>::w(net, b.fc1_w), c.dXn, d.T, d.M, d.D, EPI_NONE, nullptr, 0, st);
+    launch_ln_bwd(c.dXn, B_.Xm, B_.mean2, B_.rstd2, P + b.ln2_w, c.dX, c.dXh, G + b.ln2_w, G + b.ln2_b, c.partial,
+                  d.T, d.D, st);
+    // ---- attention block.  c.dX = dL/dX_m
+    linear_bwd_w<A, A>(c.dx_op(), B_.O, G + b.out_w, G + b.out_b, d.T, d.D, d.inner, c.partial, st);
+    linear_bwd_x<A, A, A>(c.dx_op(), WSel<A>::w(net, b.out_w), c.dO, d.T, d.D, d.inner, EPI_NONE, nullptr, 0, st);
+    launch_attention_bwd<A>(B_.QKV, B_.O, c.dO, c.dQKV, d, st);
+    linear_bwd_w<A, A>(c.dQKV, B_.Xn1, G + b.qkv_w, nullptr, d.T, 3 * d.inner, d.D, c.partial, st);
+    linear_bwd_x<A, A, float>(c.dQKV, WSel<A>::w(net, b.qkv_w), c.dXn, d.T, 3 * d.inner, d.D, EPI_NONE, nullptr, 0, st);
+    launch_ln_bwd(c.dXn, B_.Xa, B_.mean1, B_.rstd1, P + b.ln1_w, c.dX, c.dXh, G + b.ln1_w, G + b.ln1_b, c.partial,
+                  d.T, d.D, st);
+  }
+  // ---- embedding.  c.dX = dL/dX0 (post-dropout)
+  const int64_t tot = d.T * d.D;
+  embed_bwd_kernel<A><<<grid1d(tot), 256, 0, st>>>(c.dX, c.tok, c.dXp, c.dtok, drop, tot, d.N, d.D, relu_tok);
+  DG_LAUNCH_CHECK();
+  dpos_kernel<<<d.N, 128, 0, st>>>(c.dX, G + L.pos, drop, d.B, d.N, d.D);
+  DG_LAUNCH_CHECK();
+  linear_bwd_w<A, A>(c.dXp, c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st);
+}
+
+// zero the gradient ranges the reference leaves as None (so the arena is fully defined)
+static void zero_unused_grads(const dgvit_net& net, const dgvit_layout& L, cudaStream_t st) {
+  for (int k = 0; k < L.n_skip; ++k)
+    DG_CUDA(cudaMemsetAsync(net.grads + L.skip_begin[k], 0, (L.skip_end[k] - L.skip_begin[k]) * sizeof(float), st));
+}
+
+// ------------------------------------------------------------------ actor
+template <typename A>
+struct ActorCtx {
+  TrunkCtx<A> t;
+  float *h1, *h2, *mean_raw, *lstd_raw;  // [B,128] [B,128] [B,na] [B,na]
+  float *eps;                            // [B,na]
+  float *dmean, *dlstd, *dh2, *dh1;
+};
+template <typename A>
+static void carve_actor(Carver& cv, const Dims& d, bool save, ActorCtx<A>& c) {
+  carve_trunk<A>(cv, d, save, c.t);
+  c.h1 = cv.take<float>((int64_t)d.B * 128);
+  c.h2 = cv.take<float>((int64_t)d.B * 128);
+  c.mean_raw = cv.take<float>((int64_t)d.B * d.na);
+  c.lstd_raw = cv.take<float>((int64_t)d.B * d.na);
+  c.eps = cv.take<float>((int64_t)d.B * d.na);
+  c.dmean = c.dlstd = c.dh2 = c.dh1 = nullptr;
+  if (save) {
+    c.dmean = cv.take<float>((int64_t)d.B * d.na);
+    c.dlstd = cv.take<float>((int64_t)d.B * d.na);
+    c.dh2 = cv.take<float>((int64_t)d.B * 128);
+    c.dh1 = cv.take<float>((int64_t)d.B * 128);
+  }
+}
+
+// GoTPolicy.forward + .sample (vn/got_sac_network.py:221-251)
+template <typename A>
+static void actor_forward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const dgvit_actor_io& io,
+                          ActorCtx<A>& c, cudaStream_t st) {
+  const float* P = net.params;
+  DG_REQUIRE(io.img && io.pstate && io.action_scale && io.action_bias, "actor_forward: null input");
+  DG_REQUIRE(io.eps || io.drop.rng_state, "actor_forward: provide eps or drop.rng_state");
+  goal_embed_kernel<<<(unsigned)cdiv((int64_t)d.B * d.D, 256), 256, 0, st>>>(io.pstate, P + L.embed_w, P + L.embed_b,
+                                                                             c.t.tok, d.B, d.D, d.nps, 0);
+  DG_LAUNCH_CHECK();
+  const DropDev drop = make_drop(io.drop, d, io.sample_offset);
+  trunk_forward<A>(net, L, d, io.img, drop, c.t, st);
+  linear_fwd<float, float, float>(c.t.z, P + L.fc1_w, c.h1, d.B, 128, d.D, EPI_BIAS_RELU, P + L.fc1_b, st);
+  linear_fwd<float, float, float>(c.h1, P + L.fc2_w, c.h2, d.B, 128, 128, EPI_BIAS_RELU, P + L.fc2_b, st);
+  linear_fwd<float, float, float>(c.h2, P + L.mean_w, c.mean_raw, d.B, d.na, 128, EPI_BIAS, P + L.mean_b, st);
+  linear_fwd<float, float, float>(c.h2, P + L.lstd_w, c.lstd_raw, d.B, d.na, 128, EPI_BIAS, P + L.lstd_b, st);
+  SampleArgs s;
+  s.B = d.B; s.na = d.na;
+  s.mean = c.mean_raw; s.lstd_raw = c.lstd_raw;
+  s.scale = io.action_scale; s.bias = io.action_bias;
+  s.eps = io.eps; s.rng = io.drop.rng_state; s.stream_id = io.drop.stream_id ^ 0x5a5a0000u;
+  s.sample_offset = io.sample_offset;
+  s.mean_out = io.mean; s.log_std = io.log_std; s.action = io.action; s.log_prob = io.log_prob; s.mean_t = io.mean_t;
+  s.eps_out = c.eps;
+  actor_sample_kernel<<<(unsigned)cdiv(d.B, 128), 128, 0, st>>>(s);
+  DG_LAUNCH_CHECK();
+  if (io.eps_out)
+    DG_CUDA(cudaMemcpyAsync(io.eps_out, c.eps, (size_t)d.B * d.na * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+
+template <typename A>
+static void actor_backward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const dgvit_actor_io& io,
+                           const dgvit_actor_grad& g, const float* alpha_dev, float alpha_scale, ActorCtx<A>& c,
+                           cudaStream_t st) {
+  const float* P = net.params;
+  float* G = net.grads;
+  zero_unused_grads(net, L, st);
+  SampleBwdArgs s;
+  s.B = d.B; s.na = d.na;
+  s.mean = c.mean_raw; s.lstd_raw = c.lstd_raw; s.eps = c.eps; s.scale = io.action_scale;
+  s.d_mean = g.d_mean; s.d_log_std = g.d_log_std; s.d_action = g.d_action; s.d_log_prob = g.d_log_prob;
+  s.d_mean_t = g.d_mean_t; s.d_log_prob_const = g.d_log_prob_const;
+  s.d_log_prob_dev = alpha_dev; s.d_log_prob_dev_scale = alpha_scale;
+  s.d_mean_out = c.dmean; s.d_lstd_out = c.dlstd;
+  actor_sample_bwd_kernel<<<(unsigned)cdiv((int64_t)d.B * d.na, 128), 128, 0, st>>>(s);
+  DG_LAUNCH_CHECK();
+  float* part = c.t.partial;
+  linear_bwd_w<float, float>(c.dmean, c.h2, G + L.mean_w, G + L.mean_b, d.B, d.na, 128, part, st);
+  linear_bwd_w<float, float>(c.dlstd, c.h2, G + L.lstd_w, G + L.lstd_b, d.B, d.na, 128, part, st);
+  linear_bwd_x<float, float, float>(c.dmean, P + L.mean_w, c.dh2, d.B, d.na, 128, EPI_NONE, nullptr, 0, st);
+  linear_bwd_x<float, float, float>(c.dlstd, P + L.lstd_w, c.dh2, d.B, d.na, 128, EPI_BIAS_RESID, nullptr, 0, st, -1,
+                                    c.dh2);
+  {
+    const int64_t n = (int64_t)d.B * 128;
+    relu_mask_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(c.dh2, c.h2, n);
+    DG_LAUNCH_CHECK();
+  }
+  linear_bwd_w<float, float>(c.dh2, c.h1, G + L.fc2_w, G + L.fc2_b, d.B, 128, 128, part, st);
+  linear_bwd_x<float, float, float>(c.dh2, P + L.fc2_w, c.dh1, d.B, 128, 128, EPI_RELU_BWD, c.h1, 128, st);
+  linear_bwd_w<float, float>(c.dh1, c.t.z, G + L.fc1_w, G + L.fc1_b, d.B, 128, d.D, part, st);
+  linear_bwd_x<float, float, float>(c.dh1, P + L.fc1_w, c.t.dz, d.B, 128, d.D, EPI_NONE, nullptr, 0, st);
+  const DropDev drop = make_drop(io.drop, d, io.sample_offset);
+  trunk_backward<A>(net, L, d, drop, c.t, /*relu_tok=*/0, st);
+  // fc_embed: dW[D,nps] = dtok^T pstate ; db = colsum(dtok)
+  linear_bwd_w<float, float>(c.t.dtok, io.pstate, G + L.embed_w, G + L.embed_b, d.B, d.D, d.nps, part, st);
+}
+
+// ------------------------------------------------------------------ critic
+template <typename A>
+struct CriticCtx {
+  TrunkCtx<A> t;
+  float *xcat, *h1a, *h2a, *h1b, *h2b;  // [B,D+na] [B,128] [B,32] x2
+  float *dh2, *dh1, *dxa, *dxb;
+};
+template <typename A>
+static void carve_critic(Carver& cv, const Dims& d, bool save, CriticCtx<A>& c) {
+  carve_trunk<A>(cv, d, save, c.t);
+  c.xcat = cv.take<float>((int64_t)d.B * (d.D + d.na));
+  c.h1a = cv.take<float>((int64_t)d.B * 128);
+  c.h2a = cv.take<float>((int64_t)d.B * 32);
+  c.h1b = cv.take<float>((int64_t)d.B * 128);
+  c.h2b = cv.take<float>((int64_t)d.B * 32);
+  c.dh2 = cv.take<float>((int64_t)d.B * 32);
+  c.dh1 = cv.take<float>((int64_t)d.B * 128);
+  c.dxa = cv.take<float>((int64_t)d.B * (d.D + d.na));
+  c.dxb = cv.take<float>((int64_t)d.B * (d.D + d.na));
+}
+
+static void critic_heads_forward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const float* z,
+                                 const float* action, float* xcat, float* h1a, float* h2a, float* h1b, float* h2b,
+                                 float* q1, float* q2, cudaStream_t st) {
+  const float* P = net.params;
+  const int W = d.D + d.na;
+  concat_za_kernel<<<(unsigned)cdiv((int64_t)d.B * W, 256), 256, 0, st>>>(z, action, xcat, d.B, d.D, d.na);
+  DG_LAUNCH_CHECK();
+  linear_fwd<float, float, float>(xcat, P + L.fc1_w, h1a, d.B, 128, W, EPI_BIAS_RELU, P + L.fc1_b, st);
+  linear_fwd<float, float, float>(h1a, P + L.fc2_w, h2a, d.B, 32, 128, EPI_BIAS_RELU, P + L.fc2_b, st);
+  linear_fwd<float, float, float>(h2a, P + L.fc3_w, q1, d.B, d.na, 32, EPI_BIAS, P + L.fc3_b, st);
+  linear_fwd<float, float, float>(xcat, P + L.fc11_w, h1b, d.B, 128, W, EPI_BIAS_RELU, P + L.fc11_b, st);
+  linear_fwd<float, float, float>(h1b, P + L.fc21_w, h2b, d.B, 32, 128, EPI_BIAS_RELU, P + L.fc21_b, st);
+  linear_fwd<float, float, float>(h2b, P + L.fc31_w, q2, d.B, d.na, 32, EPI_BIAS, P + L.fc31_b, st);
+}
+
+template <typename A>
+static void critic_forward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const dgvit_critic_io& io,
+                           int64_t sample_offset, CriticCtx<A>& c, cudaStream_t st) {
+  const float* P = net.params;
+  DG_REQUIRE(io.img && io.pstate && io.action && io.q1 && io.q2, "critic_forward: null input/output");
+  goal_embed_kernel<<<(unsigned)cdiv((int64_t)d.B * d.D, 256), 256, 0, st>>>(io.pstate, P + L.embed_w, P + L.embed_b,
+                                                                             c.t.tok, d.B, d.D, d.nps, 1);
+  DG_LAUNCH_CHECK();
+  const DropDev drop = make_drop(io.drop, d, sample_offset);
+  trunk_forward<A>(net, L, d, io.img, drop, c.t, st);
+  critic_heads_forward(net, L, d, c.t.z, io.action, c.xcat, c.h1a, c.h2a, c.h1b, c.h2b, io.q1, io.q2, st);
+}
+
+// one Q head backward; dq [B,na] -> dx [B,W]; optionally parameter grads
+static void critic_head_backward(const dgvit_net& net, const Dims& d, const float* dq, const float* xcat,
+                                 const float* h1, const float* h2, int64_t w1, int64_t b1, int64_t w2, int64_t b2,
+                                 int64_t w3, int64_t b3, float* dh2, float* dh1, float* dx, bool param_grads,
+                                 float* part, cudaStream_t st) {
+  const float* P = net.params;
+  float* G = net.grads;
+  const int W = d.D + d.na;
+  if (param_grads) linear_bwd_w<float, float>(dq, h2, G + w3, G + b3, d.B, d.na, 32, part, st);
+  linear_bwd_x<float, float, float>(dq, P + w3, dh2, d.B, d.na, 32, EPI_RELU_BWD, h2, 32, st);
+  if (param_grads) linear_bwd_w<float, float>(dh2, h1, G + w2, G + b2, d.B, 32, 128, part, st);
+  linear_bwd_x<float, float, float>(dh2, P + w2, dh1, d.B, 32, 128, EPI_RELU_BWD, h1, 128, st);
+  if (param_grads) linear_bwd_w<float, float>(dh1, xcat, G + w1, G + b1, d.B, 128, W, part, st);
+  linear_bwd_x<float, float, float>(dh1, P + w1, dx, d.B, 128, W, EPI_NONE, nullptr, 0, st);
+}
+
+template <typename A>
+static void critic_backward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const dgvit_critic_io& io,
+                            int64_t sample_offset, const float* dq1, const float* dq2, float* d_action,
+                            bool param_grads, CriticCtx<A>& c, float* part_fallback, cudaStream_t st) {
+  float* part = c.t.partial ? c.t.partial : part_fallback;
+  if (param_grads) zero_unused_grads(net, L, st);
+  critic_head_backward(net, d, dq1, c.xcat, c.h1a, c.h2a, L.fc1_w, L.fc1_b, L.fc2_w, L.fc2_b, L.fc3_w, L.fc3_b, c.dh2,
+                       c.dh1, c.dxa, param_grads, part, st);
+  critic_head_backward(net, d, dq2, c.xcat, c.h1b, c.h2b, L.fc11_w, L.fc11_b, L.fc21_w, L.fc21_b, L.fc31_w, L.fc31_b,
+                       c.dh2, c.dh1, c.dxb, param_grads, part, st);
+  const int W = d.D + d.na;
+  split_dza_kernel<<<(unsigned)cdiv((int64_t)d.B * W, 256), 256, 0, st>>>(c.dxa, c.dxb, param_grads ? c.t.dz : nullptr,
+                                                                          d_action, d.B, d.D, d.na);
+  DG_LAUNCH_CHECK();
+  if (param_grads) {
+    const DropDev drop = make_drop(io.drop, d, sample_offset);
+    trunk_backward<A>(net, L, d, drop, c.t, /*relu_tok=*/1, st);
+    linear_bwd_w<float, float>(c.t.dtok, io.pstate, net.grads + L.embed_w, net.grads + L.embed_b, d.B, d.D, d.nps, part,
+                               st);
+  }
+}
+
+// ------------------------------------------------------------------ optimizer
+static void adam_step(const dgvit_net& net, const dgvit_layout& L, const dgvit_adam& o, const dgvit_net* tgt,
+                      float tau, bool want_shadow, cudaStream_t st) {
+  DG_REQUIRE(o.m && o.v && o.step, "adam: null state");
+  step_bump_kernel<<<1, 32, 0, st>>>(o.step);
+  DG_LAUNCH_CHECK();
+  AdamArgs a;
+  a.p = net.params; a.g = net.grads; a.m = o.m; a.v = o.v;
+  a.shadow = (want_shadow && net.shadow) ? (bf16*)net.shadow : nullptr;
+  a.tgt = tgt ? tgt->params : nullptr;
+  a.tgt_shadow = (tgt && want_shadow && tgt->shadow) ? (bf16*)tgt->shadow : nullptr;
+  a.tau = tau;
+  a.n = L.total; a.step = o.step;
+  a.lr = o.lr; a.b1 = o.beta1; a.b2 = o.beta2; a.eps = o.eps;
+  a.omb1 = (float)(1.0 - (double)o.beta1);
+  a.omb2 = (float)(1.0 - (double)o.beta2);
+  a.n_skip = L.n_skip;
+  for (int k = 0; k < 4; ++k) { a.skip_b[k] = L.skip_begin[k]; a.skip_e[k] = L.skip_end[k]; }
+  adam_polyak_kernel<<<148 * 4, 256, 0, st>>>(a);
+  DG_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ SAC.learn
+template <typename A>
+struct SacWs {
+  ActorCtx<A> actor_s;      // saved: policy.sample(s)
+  CriticCtx<A> critic_s;    // saved: critic(s, a)
+  ActorCtx<A> actor_tmp;    // unsaved: policy.sample(s')
+  CriticCtx<A> critic_tmp;  // unsaved: critic_target(s', a') and critic(s, pi)
+  float *a2, *logp2, *mean_tmp, *lstd_tmp, *q1t, *q2t, *q1, *q2, *dq1, *dq2, *nq;
+  float *pi, *logpi, *mean_pi, *lstd_pi, *q1p, *q2p, *dpi;
+};
+template <typename A>
+static void carve_sac(Carver& cv, const Dims& d, SacWs<A>& w) {
+  carve_actor<A>(cv, d, true, w.actor_s);
+  carve_critic<A>(cv, d, true, w.critic_s);
+  carve_actor<A>(cv, d, false, w.actor_tmp);
+  carve_critic<A>(cv, d, false, w.critic_tmp);
+  const int64_t bn = (int64_t)d.B * d.na;
+  w.a2 = cv.take<float>(bn); w.logp2 = cv.take<float>(d.B);
+  w.mean_tmp = cv.take<float>(bn); w.lstd_tmp = cv.take<float>(bn);
+  w.q1t = cv.take<float>(bn); w.q2t = cv.take<float>(bn);
+  w.q1 = cv.take<float>(bn); w.q2 = cv.take<float>(bn);
+  w.dq1 = cv.take<float>(bn); w.dq2 = cv.take<float>(bn); w.nq = cv.take<float>(bn);
+  w.pi = cv.take<float>(bn); w.logpi = cv.take<float>(d.B);
+  w.mean_pi = cv.take<float>(bn); w.lstd_pi = cv.take<float>(bn);
+  w.q1p = cv.take<float>(bn); w.q2p = cv.take<float>(bn); w.dpi = cv.take<float>(bn);
+}
+
+static dgvit_drop sac_drop(const dgvit_sac& s, const dgvit_noise* nz, const uint8_t* mask, uint32_t id) {
+  dgvit_drop dr;
+  dr.mode = nz ? nz->drop_mode : DGVIT_DROP_RNG;
+  dr.p = 0.1f;
+  dr.keep_mask = mask;
+  dr.rng_state = s.rng_state;
+  dr.stream_id = id;
+  return dr;
+}
+
+template <typename A>
+static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noise* nz, const dgvit_sac_out& out,
+                       const Dims& d, SacWs<A>& w, cudaStream_t st) {
+  dgvit_layout La, Lc;
+  make_layout(s.actor.cfg, La);
+  make_layout(s.critic.cfg, Lc);
+  // ---- no-grad: a', log pi' = policy.sample(s') ; q_t = critic_target(s', a')   (DRL.py:388-393)
+  dgvit_actor_io ai; memset(&ai, 0, sizeof(ai));
+  ai.img = b.next_obs; ai.pstate = b.next_pobs; ai.eps = nz ? nz->eps_next : nullptr;
+  ai.action_scale = s.action_scale; ai.action_bias = s.action_bias;
+  ai.drop = sac_drop(s, nz, nz ? nz->mask_a_next : nullptr, 1);
+  ai.sample_offset = s.sample_offset;
+  ai.mean = w.mean_tmp; ai.log_std = w.lstd_tmp; ai.action = w.a2; ai.log_prob = w.logp2;
+  actor_forward<A>(s.actor, La, d, ai, w.actor_tmp, st);
+  dgvit_critic_io ci; memset(&ci, 0, sizeof(ci));
+  ci.img = b.next_obs; ci.pstate = b.next_pobs; ci.action = w.a2;
+  ci.drop = sac_drop(s, nz, nz ? nz->mask_ct : nullptr, 2);
+  ci.q1 = w.q1t; ci.q2 = w.q2t;
+  critic_forward<A>(s.critic_target, Lc, d, ci, s.sample_offset, w.critic_tmp, st);
+  // ---- critic(s, a), losses, backward                                          (DRL.py:395-401)
+  dgvit_critic_io cs; memset(&cs, 0, sizeof(cs));
+  cs.img = b.obs; cs.pstate = b.pobs; cs.action = b.act;
+  cs.drop = sac_drop(s, nz, nz ? nz->mask_c : nullptr, 3);
+  cs.q1 = w.q1; cs.q2 = w.q2;
+  critic_forward<A>(s.critic, Lc, d, cs, s.sample_offset, w.critic_s, st);
+  critic_loss_kernel<<<1, 1024, 0, st>>>(w.q1, w.q2, w.q1t, w.q2t, w.logp2, b.rew, s.alpha, s.gamma, d.B, d.na,
+                                         s.global_batch, w.nq, w.dq1, w.dq2, out.losses);
+  DG_LAUNCH_CHECK();
+  critic_backward<A>(s.critic, Lc, d, cs, s.sample_offset, w.dq1, w.dq2, nullptr, true, w.critic_s, nullptr, st);
+  if (out.debug) {
+    const size_t bn = (size_t)d.B * d.na * sizeof(float);
+    DG_CUDA(cudaMemcpyAsync(out.debug, w.nq, bn, cudaMemcpyDeviceToDevice, st));
+    DG_CUDA(cudaMemcpyAsync(out.debug + d.B * d.na, w.q1, bn, cudaMemcpyDeviceToDevice, st));
+    DG_CUDA(cudaMemcpyAsync(out.debug + 2 * d.B * d.na, w.q2, bn, cudaMemcpyDeviceToDevice, st));
+  }
+}
+
+template <typename A>
+static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noise* nz, const dgvit_sac_out& out,
+                       const Dims& d, SacWs<A>& w, cudaStream_t st) {
+  dgvit_layout La, Lc;
+  make_layout(s.actor.cfg, La);
+  make_layout(s.critic.cfg, Lc);
+  const bool shadow = s.precision == DGVIT_BF16;
+  adam_step(s.critic, Lc, s.critic_opt, nullptr, 0.f, shadow, st);               // DRL.py:402
+  // ---- pi, log_pi = policy.sample(s) ; q_pi = critic(s, pi)                    (DRL.py:404-407)
+  dgvit_actor_io ai; memset(&ai, 0, sizeof(ai));
+  ai.img = b.obs; ai.pstate = b.pobs; ai.eps = nz ? nz->eps_pi : nullptr;
+  ai.action_scale = s.action_scale; ai.action_bias = s.action_bias;
+  ai.drop = sac_drop(s, nz, nz ? nz->mask_a : nullptr, 4);
+  ai.sample_offset = s.sample_offset;
+  ai.mean = w.mean_pi; ai.log_std = w.lstd_pi; ai.action = w.pi; ai.log_prob = w.logpi;
+  actor_forward<A>(s.actor, La, d, ai, w.actor_s, st);
+  dgvit_critic_io ci; memset(&ci, 0, sizeof(ci));
+  ci.img = b.obs; ci.pstate = b.pobs; ci.action = w.pi;
+  ci.drop = sac_drop(s, nz, nz ? nz->mask_c_pi : nullptr, 5);
+  ci.q1 = w.q1p; ci.q2 = w.q2p;
+  critic_forward<A>(s.critic, Lc, d, ci, s.sample_offset, w.critic_tmp, st);
+  policy_loss_kernel<<<1, 1024, 0, st>>>(w.q1p, w.q2p, w.logpi, s.alpha, s.log_alpha, s.target_entropy, d.B, d.na,
+                                         s.global_batch, w.dq1, w.dq2, out.losses, s.actor.grads + La.alpha_grad_slot);
+  DG_LAUNCH_CHECK();
+  // d policy_loss / d pi through the critic heads only (the critic's own parameter gradients
+  // of this backward are discarded by the reference's next zero_grad, DRL.py:399)
+  critic_backward<A>(s.critic, Lc, d, ci, s.sample_offset, w.dq1, w.dq2, w.dpi, false, w.critic_tmp,
+                     w.actor_s.t.partial, st);
+  dgvit_actor_grad ag; memset(&ag, 0, sizeof(ag));
+  ag.d_action = w.dpi;
+  actor_backward<A>(s.actor, La, d, ai, ag, s.alpha, 1.0f / (float)s.global_batch, w.actor_s, st);
+  if (out.debug) {
+    const size_t bn = (size_t)d.B * d.na * sizeof(float);
+    DG_CUDA(cudaMemcpyAsync(out.debug + 3 * d.B * d.na, w.pi, bn, cudaMemcpyDeviceToDevice, st));
+    DG_CUDA(cudaMemcpyAsync(out.debug + 4 * d.B * d.na, w.q1p, bn, cudaMemcpyDeviceToDevice, st));
+    DG_CUDA(cudaMemcpyAsync(out.debug + 5 * d.B * d.na, w.logpi, (size_t)d.B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+}
+
+
+template <typename A>
+static void sac_phase3(const dgvit_sac& s, cudaStream_t st) {
+  dgvit_layout La, Lc;
+  make_layout(s.actor.cfg, La);
+  make_layout(s.critic.cfg, Lc);
+  const bool shadow = s.precision == DGVIT_BF16;
+  adam_step(s.actor, La, s.actor_opt, nullptr, 0.f, shadow, st);                 // DRL.py:413
+  if (s.auto_alpha) {                                                            // DRL.py:416-423
+    alpha_step_kernel<<<1, 32, 0, st>>>(s.log_alpha, s.alpha, s.alpha_m, s.alpha_v, s.alpha_step,
+                                        s.actor.grads + La.alpha_grad_slot, s.lr_alpha, 0.9f, 0.999f,
+                                        (float)(1.0 - 0.9), (float)(1.0 - 0.999), 1e-8f);
+    DG_LAUNCH_CHECK();
+  }
+  if (s.do_polyak) {                                                             // DRL.py:430-431
+    polyak_kernel<<<148 * 4, 256, 0, st>>>(s.critic_target.params, s.critic.params,
+                                           shadow ? (bf16*)s.critic_target.shadow : nullptr, s.tau, Lc.total);
+    DG_LAUNCH_CHECK();
+  }
+  if (s.rng_state) {
+    rng_advance_kernel<<<1, 32, 0, st>>>(s.rng_state);
+    DG_LAUNCH_CHECK();
+  }
+}
+
+static void check_sac(const dgvit_sac& s, int B) {
+  DG_REQUIRE(B >= 1, "B must be >= 1");
+  DG_REQUIRE(s.actor.cfg.kind == DGVIT_ACTOR && s.critic.cfg.kind == DGVIT_CRITIC &&
+             s.critic_target.cfg.kind == DGVIT_CRITIC, "sac: wrong network kinds");
+  DG_REQUIRE(s.actor.params && s.actor.grads && s.critic.params && s.critic.grads && s.critic_target.params,
+             "sac: null arena");
+  DG_REQUIRE(s.alpha && s.log_alpha, "sac: null alpha");
+  DG_REQUIRE(s.global_batch >= B, "sac: global_batch < B");
+  DG_REQUIRE(s.action_scale && s.action_bias, "sac: null action scale/bias");
+  if (s.precision == DGVIT_BF16)
+    DG_REQUIRE(s.actor.shadow && s.critic.shadow && s.critic_target.shadow, "sac: bf16 needs shadow arenas");
+}
+
+template <typename A>
+static size_t sac_ws_bytes(const dgvit_cfg& acfg, int B) {
+  Dims d(acfg, B);
+  Carver cv(nullptr, 0, true);
+  SacWs<A> w;
+  carve_sac<A>(cv, d, w);
+  return cv.off;
+}
+
+template <typename F32, typename BF>
+static void by_precision(int precision, F32&& f32, BF&& bf) {
+  if (precision == DGVIT_FP32) f32();
+  else if (precision == DGVIT_BF16) bf();
+  else fail(DGVIT_ERR_ARG, "unknown precision %d", precision);
+}
+
+}  // namespace dgvit
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+using namespace dgvit;
+
+extern "C" {
+
+int dgvit_version(void) { return 100; }
+const char* dgvit_last_error(void) { return last_error().c_str(); }
+
+int dgvit_param_layout(const dgvit_cfg* cfg, dgvit_layout* out) {
+  return guarded([&] {
+    DG_REQUIRE(cfg && out, "null argument");
+    make_layout(*cfg, *out);
+  });
+}
+
+int dgvit_workspace_bytes(const dgvit_cfg* cfg, int B, int precision, int save, size_t* bytes) {
+  return guarded([&] {
+    DG_REQUIRE(cfg && bytes && B >= 1, "bad argument");
+    Dims d(*cfg, B);
+    Carver cv(nullptr, 0, true);
+    auto run = [&](auto tag) {
+      using A = decltype(tag);
+      if (cfg->kind == DGVIT_ACTOR) { ActorCtx<A> c; carve_actor<A>(cv, d, save != 0, c); }
+      else { CriticCtx<A> c; carve_critic<A>(cv, d, save != 0, c); }
+    };
+    by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
+    *bytes = cv.off;
+  });
+}
+
+int dgvit_sac_workspace_bytes(const dgvit_cfg* acfg, int B, int precision, size_t* bytes) {
+  return guarded([&] {
+    DG_REQUIRE(acfg && bytes && B >= 1, "bad argument");
+    by_precision(precision, [&] { *bytes = sac_ws_bytes<float>(*acfg, B); },
+                 [&] { *bytes = sac_ws_bytes<bf16>(*acfg, B); });
+  });
+}
+
+int dgvit_refresh_shadow(const dgvit_net* net, void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(net && net->params && net->shadow, "null argument");
+    dgvit_layout L;
+    make_layout(net->cfg, L);
+    shadow_refresh_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(net->params, (bf16*)net->shadow, L.total);
+    DG_LAUNCH_CHECK();
+  });
+}
+
+int dgvit_actor_forward(const dgvit_net* net, const dgvit_actor_io* io, int B, int precision, int save,
+                        void* ws, size_t ws_bytes, void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(net && io && ws && B >= 1 && net->cfg.kind == DGVIT_ACTOR && net->params, "bad argument");
+    dgvit_layout L;
+    make_layout(net->cfg, L);
+    Dims d(net->cfg, B);
+    auto run = [&](auto tag) {
+      using A = decltype(tag);
+      Carver cv(ws, ws_bytes);
+      ActorCtx<A> c;
+      carve_actor<A>(cv, d, save != 0, c);
+      actor_forward<A>(*net, L, d, *io, c, (cudaStream_t)stream);
+    };
+    if (precision == DGVIT_BF16) DG_REQUIRE(net->shadow, "bf16 needs a shadow arena");
+    by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
+  });
+}
+
+int dgvit_actor_backward(const dgvit_net* net, const dgvit_actor_io* io, const dgvit_actor_grad* g, int B,
+                         int precision, void* ws, size_t ws_bytes, void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(net && io && g && ws && B >= 1 && net->cfg.kind == DGVIT_ACTOR && net->params && net->grads,
+               "bad argument");
+    dgvit_layout L;
+    make_layout(net->cfg, L);
+    Dims d(net->cfg, B);
+    auto run = [&](auto tag) {
+      using A = decltype(tag);
+      Carver cv(ws, ws_bytes);
+      ActorCtx<A> c;
+      carve_actor<A>(cv, d, true, c);
+      actor_backward<A>(*net, L, d, *io, *g, nullptr, 0.f, c, (cudaStream_t)stream);
+    };
+    by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
+  });
+}
+
+int dgvit_critic_forward(const dgvit_net* net, const dgvit_critic_io* io, int B, int precision, int save,
+                         void* ws, size_t ws_bytes, void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(net && io && ws && B >= 1 && net->cfg.kind == DGVIT_CRITIC && net->params, "bad argument");
+    dgvit_layout L;
+    make_layout(net->cfg, L);
+    Dims d(net->cfg, B);
+    auto run = [&](auto tag) {
+      using A = decltype(tag);
+      Carver cv(ws, ws_bytes);
+      CriticCtx<A> c;
+      carve_critic<A>(cv, d, save != 0, c);
+      critic_forward<A>(*net, L, d, *io, 0, c, (cudaStream_t)stream);
+    };
+    if (precision == DGVIT_BF16) DG_REQUIRE(net->shadow, "bf16 needs a shadow arena");
+    by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
+  });
+}
+
+int dgvit_critic_backward(const dgvit_net* net, const dgvit_critic_io* io, const float* d_q1, const float* d_q2,
+                          float* d_action, int param_grads, int B, int precision, void* ws, size_t ws_bytes,
+                          void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(net && io && d_q1 && d_q2 && ws && B >= 1 && net->cfg.kind == DGVIT_CRITIC && net->params,
+               "bad argument");
+    if (param_grads) DG_REQUIRE(net->grads, "null grads");
+    dgvit_layout L;
+    make_layout(net->cfg, L);
+    Dims d(net->cfg, B);
+    auto run = [&](auto tag) {
+      using A = decltype(tag);
+      Carver cv(ws, ws_bytes);
+      CriticCtx<A> c;
+      carve_critic<A>(cv, d, true, c);
+      critic_backward<A>(*net, L, d, *io, 0, d_q1, d_q2, d_action, param_grads != 0, c, nullptr,
+                         (cudaStream_t)stream);
+    };
+    by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
+  });
+}
+
+static int sac_run(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* nz, const dgvit_sac_out* out, int B,
+                   void* ws, size_t ws_bytes, void* stream, int phases) {
+  return guarded([&] {
+    DG_REQUIRE(s && ws, "null argument");
+    check_sac(*s, B);
+    if (phases & 3) {
+      DG_REQUIRE(b && out && out->losses, "null batch/out");
+      DG_REQUIRE(b->obs && b->next_obs && b->pobs && b->next_pobs && b->act && b->rew, "null batch tensor");
+      if (nz && nz->drop_mode == DGVIT_DROP_MASK)
+        DG_REQUIRE(nz->mask_a_next && nz->mask_ct && nz->mask_c && nz->mask_a && nz->mask_c_pi, "null mask");
+      if (!nz || !nz->eps_next || !nz->eps_pi || nz->drop_mode == DGVIT_DROP_RNG)
+        DG_REQUIRE(s->rng_state, "rng_state required when noise is not injected");
+    }
+    Dims d(s->actor.cfg, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto run = [&](auto tag) {
+      using A = decltype(tag);
+      Carver cv(ws, ws_bytes);
+      SacWs<A> w;
+      carve_sac<A>(cv, d, w);
+      if (phases & 1) sac_phase1<A>(*s, *b, nz, *out, d, w, st);
+      if (phases & 2) sac_phase2<A>(*s, *b, nz, *out, d, w, st);
+      if (phases & 4) sac_phase3<A>(*s, st);
+    };
+    by_precision(s->precision, [&] { run(float()); }, [&] { run(bf16()); });
+  });
+}
+
+int dgvit_sac_phase1(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* nz, const dgvit_sac_out* out,
+                     int B, void* ws, size_t ws_bytes, void* stream) {
+  return sac_run(s, b, nz, out, B, ws, ws_bytes, stream, 1);
+}
+int dgvit_sac_phase2(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* nz, const dgvit_sac_out* out,
+                     int B, void* ws, size_t ws_bytes, void* stream) {
+  return sac_run(s, b, nz, out, B, ws, ws_bytes, stream, 2);
+}
+int dgvit_sac_phase3(const dgvit_sac* s, int B, void* ws, size_t ws_bytes, void* stream) {
+  return sac_run(s, nullptr, nullptr, nullptr, B, ws, ws_bytes, stream, 4);
+}
+int dgvit_sac_update(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* nz, const dgvit_sac_out* out,
+                     int B, void* ws, size_t ws_bytes, void* stream) {
+  return sac_run(s, b, nz, out, B, ws, ws_bytes, stream, 7);
+}
+
+int dgvit_adam_step(const dgvit_net* net, const dgvit_adam* opt, const dgvit_net* tgt, float tau, void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(net && opt && net->params && net->grads, "null argument");
+    dgvit_layout L;
+    make_layout(net->cfg, L);
+    adam_step(*net, L, *opt, tgt, tau, net->shadow != nullptr, (cudaStream_t)stream);
+  });
+}
+
+int dgvit_polyak(const dgvit_net* target, const dgvit_net* source, float tau, void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(target && source && target->params && source->params, "null argument");
+    dgvit_layout L, Ls;
+    make_layout(target->cfg, L);
+    make_layout(source->cfg, Ls);
+    DG_REQUIRE(L.total == Ls.total, "polyak: layouts differ");
+    polyak_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(target->params, source->params, (bf16*)target->shadow, tau,
+                                                             L.total);
+    DG_LAUNCH_CHECK();
+  });
+}
+
+int dgvit_replay_gather(const dgvit_replay* s, const int64_t* idx, int B, float* obs, float* next_obs, float* pobs,
+                        float* next_pobs, float* act, float* rew, float* done, void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(s && idx && B >= 0 && s->obs && s->size > 0, "bad argument");
+    DG_REQUIRE(s->frame % 4 == 0, "frame size must be a multiple of 4 floats");
+    DG_REQUIRE(((uintptr_t)s->obs % 16) == 0 && ((uintptr_t)obs % 16) == 0 && ((uintptr_t)next_obs % 16) == 0,
+               "frame buffers must be 16-byte aligned");
+    if (B == 0) return;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t frame4 = s->frame / 4;
+    const int chunks = (int)std::min<int64_t>(cdiv(frame4, 256), 8);
+    dim3 grid((unsigned)chunks, (unsigned)B, 2);
+    replay_gather_frames_kernel<<<grid, 256, 0, st>>>((const float4*)s->obs, idx, s->size, frame4, (float4*)obs,
+                                                      (float4*)next_obs);
+    DG_LAUNCH_CHECK();
+    SmallGather g;
+    g.n = 5;
+    g.src[0] = s->pobs; g.dst[0] = pobs; g.width[0] = s->n_pstate;
+    g.src[1] = s->next_pobs; g.dst[1] = next_pobs; g.width[1] = s->n_pstate;
+    g.src[2] = s->act; g.dst[2] = act; g.width[2] = s->n_act;
+    g.src[3] = s->rew; g.dst[3] = rew; g.width[3] = 1;
+    g.src[4] = s->done; g.dst[4] = done; g.width[4] = 1;
+    replay_gather_small_kernel<<<(unsigned)cdiv(B, 128), 128, 0, st>>>(g, idx, B);
+    DG_LAUNCH_CHECK();
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// gemm_simt.cuh — strided CUDA-core GEMM with fused epilogues.
+//
+// This is the fp32 arithmetic path (parity mode: the reference computes every
+// contraction in true fp32, SURVEY.md §7 "hard parts") and the path of the tiny head
+// GEMMs.  C[m,n] = sum_k A(m,k) * B(k,n) with arbitrary element strides, so the same
+// kernel serves y = x W^T (NT), dx = dy W (NN) and dW = dy^T x (TN, split-K).
+#pragma once
+#include "common.cuh"
+
+namespace dgvit {
+
+enum {
+  EPI_NONE = 0,
+  EPI_BIAS,        // C = acc + bias[n]
+  EPI_BIAS_RELU,   // C = relu(acc + bias[n])
+  EPI_BIAS_GELU2,  // C = acc + bias[n] ; C2 = gelu(C)
+  EPI_BIAS_RESID,  // C(f32) = acc + (bias ? bias[n] : 0) + resid[m,n]   (resid may alias C)
+  EPI_GELU_BWD,    // C = acc * gelu'(aux[m,n])
+  EPI_RELU_BWD     // C = acc * (auxf[m,n] > 0)
+};
+
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const void* A = nullptr;
+  int64_t a_sm = 0, a_sk = 0;
+  const void* B = nullptr;
+  int64_t b_sk = 0, b_sn = 0;
+  void* C = nullptr;
+  int64_t ldc = 0;
+  int epi = EPI_NONE;
+  const float* bias = nullptr;
+  const float* resid = nullptr;
+  int64_t ldr = 0;
+  void* C2 = nullptr;
+  const void* aux = nullptr;  // typed like C for EPI_GELU_BWD, float for EPI_RELU_BWD
+  int64_t ldaux = 0;
+  int splitk = 1;
+  float* partial = nullptr;  // [splitk, M, N]
+};
+
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_PAD = 4;
+
+template <typename TA, typename TB, typename TC>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[SG_BK][SG_BM + SG_PAD];
+  __shared__ __align__(16) float Bs[SG_BK][SG_BN + SG_PAD];
+  const TA* __restrict__ A = (const TA*)g.A;
+  const TB* __restrict__ B = (const TB*)g.B;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  // split-K range
+  const int kchunk = (int)cdiv(cdiv(g.K, g.splitk), SG_BK) * SG_BK;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(g.K, kbeg + kchunk);
+  const bool a_kc = (g.a_sk == 1);
+  const bool b_nc = (g.b_sn == 1);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += SG_BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      int m, k;
+      if (a_kc) { m = idx >> 4; k = idx & 15; } else { k = idx >> 6; m = idx & 63; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < g.M && gk < kend) v = ldf(A + (int64_t)gm * g.a_sm + (int64_t)gk * g.a_sk);
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      int n, k;
+      if (b_nc) { k = idx >> 6; n = idx & 63; } else { n = idx >> 4; k = idx & 15; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < g.N && gk < kend) v = ldf(B + (int64_t)gk * g.b_sk + (int64_t)gn * g.b_sn);
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  if (g.splitk > 1) {
+    float* P = g.partial + (int64_t)blockIdx.z * g.M * g.N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m >= g.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (n < g.N) P[(int64_t)m * g.N + n] = acc[i][j];
+      }
+    }
+    return;
+  }
+  TC* C = (TC*)g.C;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      switch (g.epi) {
+        case EPI_NONE: break;
+        case EPI_BIAS: v += g.bias[n]; break;
+        case EPI_BIAS_RELU: v = fmaxf(v + g.bias[n], 0.f); break;
+        case EPI_BIAS_GELU2:
+          v += g.bias[n];
+          stf((TC*)g.C2 + (int64_t)m * g.ldc + n, gelu_f(v));
+          break;
+        case EPI_BIAS_RESID: v += (g.bias ? g.bias[n] : 0.f) + g.resid[(int64_t)m * g.ldr + n]; break;
+        case EPI_GELU_BWD: v *= gelu_grad_f(ldf((const TC*)g.aux + (int64_t)m * g.ldaux + n)); break;
+        case EPI_RELU_BWD: v = ((const float*)g.aux)[(int64_t)m * g.ldaux + n] > 0.f ? v : 0.f; break;
+      }
+      stf(C + (int64_t)m * g.ldc + n, v);
+    }
+  }
+}
+
+// out[i] = sum_s partial[s, i]   (fixed order: deterministic)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                       int S, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += partial[(int64_t)k * n + i];
+  out[i] = s;
+}
+
+template <typename TA, typename TB, typename TC>
+static void gemm_simt(const GemmArgs& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return;
+  DG_REQUIRE(g.splitk >= 1 && (g.splitk == 1 || (g.partial && g.epi == EPI_NONE)),
+             "gemm_simt: split-K needs a partial buffer and EPI_NONE");
+  dim3 grid((unsigned)cdiv(g.N, SG_BN), (unsigned)cdiv(g.M, SG_BM), (unsigned)g.splitk);
+  gemm_simt_kernel<TA, TB, TC><<<grid, 256, 0, st>>>(g);
+  DG_LAUNCH_CHECK();
+  if (g.splitk > 1) {
+    DG_REQUIRE(g.ldc == g.N, "gemm_simt: split-K output must be dense");
+    const int64_t n = (int64_t)g.M * g.N;
+    reduce_partials_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(g.partial, (float*)g.C, g.splitk, n);
+    DG_LAUNCH_CHECK();
+  }
+}
+
+// split-K factor for the weight-gradient GEMMs (contraction over tokens)
+static inline int pick_splitk(int64_t K) {
+  int64_t s = K / 1024;
+  if (s < 1) s = 1;
+  if (s > 32) s = 32;
+  return (int)s;
+}
+
+}  // namespace dgvit

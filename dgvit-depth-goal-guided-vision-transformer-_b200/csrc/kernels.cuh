@@ -1,0 +1,690 @@
+// kernels.cuh — non-GEMM kernels of the DGViT hot path (embedding, LayerNorm, attention,
+// RMSNorm pooling, tanh-Gaussian head, SAC losses, Adam/Polyak, replay gather).
+// Reference lines are cited per kernel; "vn/" = src/vis_nav/vis_nav/.
+#pragma once
+#include "common.cuh"
+
+namespace dgvit {
+
+// =====================================================================================
+// Embedding  (vn/GoalFormer.py:137-139,156-163 ; vn/got_sac_network.py:111,226)
+// =====================================================================================
+
+// Rearrange 'b (h p1) (w p2) -> b (h w) (p1 p2)' materialised once per forward in the
+// activation dtype (the fp32->bf16 cast of the frame is fused here).
+template <typename A>
+__global__ void patchify_kernel(const float* __restrict__ img, A* __restrict__ out, int64_t total,
+                                int img_h, int img_w, int ph, int pw) {
+  const int gw = img_w / pw, gh = img_h / ph;
+  const int pd = ph * pw, P = gh * gw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % pd);
+    const int64_t bp = i / pd;
+    const int p = (int)(bp % P);
+    const int64_t b = bp / P;
+    const int p1 = k / pw, p2 = k % pw;
+    const int y = (p / gw) * ph + p1, x = (p % gw) * pw + p2;
+    stf(out + i, img[(b * img_h + y) * img_w + x]);
+  }
+}
+
+// goal token: tok[b,:] = act(W_e pstate[b] + b_e); ReLU only in the critic
+__global__ void goal_embed_kernel(const float* __restrict__ ps, const float* __restrict__ W,
+                                  const float* __restrict__ bias, float* __restrict__ tok, int B, int D,
+                                  int npst, int relu) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int b = i / D, d = i % D;
+  float v = bias[d];
+  for (int j = 0; j < npst; ++j) v = fmaf(W[d * npst + j], ps[b * npst + j], v);
+  tok[i] = relu ? fmaxf(v, 0.f) : v;
+}
+
+// x = cat(tok, patches) + pos ; x = dropout(x)     (GoalFormer.py:160-163)
+__global__ void embed_assemble_kernel(const float* __restrict__ tok, const float* __restrict__ Xp,
+                                      const float* __restrict__ pos, float* __restrict__ X0, DropDev drop,
+                                      int64_t total, int N, int D) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const int64_t bn = i / D;
+    const int n = (int)(bn % N);
+    const int64_t b = bn / N;
+    const float v = (n == 0 ? tok[b * D + d] : Xp[(b * (N - 1) + (n - 1)) * D + d]) + pos[n * D + d];
+    X0[i] = v * drop_factor(drop, i);
+  }
+}
+
+// backward of the above: dXp (compact, activation dtype), dtok (through the optional ReLU)
+template <typename A>
+__global__ void embed_bwd_kernel(const float* __restrict__ dX0, const float* __restrict__ tok,
+                                 A* __restrict__ dXp, float* __restrict__ dtok, DropDev drop, int64_t total,
+                                 int N, int D, int relu) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const int64_t bn = i / D;
+    const int n = (int)(bn % N);
+    const int64_t b = bn / N;
+    const float g = dX0[i] * drop_factor(drop, i);
+    if (n == 0) {
+      dtok[b * D + d] = (relu && !(tok[b * D + d] > 0.f)) ? 0.f : g;
+    } else {
+      stf(dXp + (b * (N - 1) + (n - 1)) * D + d, g);
+    }
+  }
+}
+
+// dpos[n,d] = sum_b dX0[b,n,d]*keep   — one block per token position, fixed order over b
+__global__ void dpos_kernel(const float* __restrict__ dX0, float* __restrict__ dpos, DropDev drop, int B,
+                            int N, int D) {
+  const int n = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const int64_t i = ((int64_t)b * N + n) * D + d;
+      s += dX0[i] * drop_factor(drop, i);
+    }
+    dpos[n * D + d] = s;
+  }
+}
+
+// =====================================================================================
+// LayerNorm (vn/GoalFormer.py:31-37; eps 1e-5, affine) — one warp per token row
+// =====================================================================================
+template <typename A, int VPL>  // D = 32*VPL
+__global__ void layernorm_fwd_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, A* __restrict__ Y,
+                                     float* __restrict__ mean, float* __restrict__ rstd, int64_t T) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= T) return;
+  constexpr int D = 32 * VPL;
+  float v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) { v[i] = X[row * D + lane + 32 * i]; s += v[i]; }
+  const float mu = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) { const float c = v[i] - mu; q = fmaf(c, c, q); }
+  const float var = warp_sum(q) * (1.0f / D);
+  const float rs = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int d = lane + 32 * i;
+    stf(Y + row * D + d, (v[i] - mu) * rs * gamma[d] + beta[d]);
+  }
+  if (lane == 0 && mean) { mean[row] = mu; rstd[row] = rs; }
+}
+
+// dX_io[row] += LN'(dY[row]); per-block partial sums of dgamma/dbeta -> part[block][2][D]
+template <int VPL>
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ X,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ gamma, float* __restrict__ dX_io,
+                                     bf16* __restrict__ dX_lp, float* __restrict__ part, int64_t T) {
+  constexpr int D = 32 * VPL;
+  extern __shared__ float sm[];  // [warps][2][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float dg[VPL], db[VPL], gm[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) { dg[i] = 0.f; db[i] = 0.f; gm[i] = gamma[lane + 32 * i]; }
+  for (int64_t row = (int64_t)blockIdx.x * nw + warp; row < T; row += (int64_t)gridDim.x * nw) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[VPL], dy[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int d = lane + 32 * i;
+      xh[i] = (X[row * D + d] - mu) * rs;
+      dy[i] = dY[row * D + d];
+      const float w = dy[i] * gm[i];
+      s1 += w;
+      s2 = fmaf(w, xh[i], s2);
+      dg[i] = fmaf(dy[i], xh[i], dg[i]);
+      db[i] += dy[i];
+    }
+    s1 = warp_sum(s1) * (1.0f / D);
+    s2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int d = lane + 32 * i;
+      const float nv = dX_io[row * D + d] + rs * (dy[i] * gm[i] - s1 - xh[i] * s2);
+      dX_io[row * D + d] = nv;
+      if (dX_lp) dX_lp[row * D + d] = __float2bfloat16_rn(nv);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    sm[(warp * 2 + 0) * D + lane + 32 * i] = dg[i];
+    sm[(warp * 2 + 1) * D + lane + 32 * i] = db[i];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * D; j += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += sm[w * 2 * D + j];
+    part[(int64_t)blockIdx.x * 2 * D + j] = s;
+  }
+}
+
+// out_g[d] = sum_blocks part[b][0][d], out_b[d] = sum_blocks part[b][1][d]
+__global__ void ln_param_reduce_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int nblocks, int D) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 2 * D) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * 2 * D + j];
+  if (j < D) dgamma[j] = s; else dbeta[j - D] = s;
+}
+
+// column sums (bias gradients): part[s][n] = sum over this block's row range
+template <typename T_>
+__global__ void colsum_partial_kernel(const T_* __restrict__ A, int64_t lda, float* __restrict__ part,
+                                      int64_t rows, int N, int64_t rows_per_block) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) s += ldf(A + r * lda + n);
+  part[(int64_t)blockIdx.y * N + n] = s;
+}
+
+// =====================================================================================
+// Attention (vn/GoalFormer.py:71-81): softmax(q k^T * dh^-0.5) v per (sample, head).
+// CUDA-core version: K,V (and Q,dO in backward) of one (b,h) staged in shared memory,
+// one warp per query row, warp-shuffle softmax.
+// QKV layout: [T, 3*inner], column = which*inner + h*dh + d  (chunk(3) then 'b n (h d)').
+// =====================================================================================
+template <typename A>
+__global__ void attention_fwd_kernel(const A* __restrict__ QKV, A* __restrict__ O, int N, int H, int dh,
+                                     float scale) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int inner = H * dh, ld = 3 * inner, kst = dh + 1;
+  float* Ks = sm;                 // [N][dh+1]
+  float* Vs = Ks + N * kst;       // [N][dh]
+  float* Ps = Vs + N * dh;        // [warps][N]
+  float* Qs = Ps + (blockDim.x >> 5) * N;  // [warps][dh]
+  const A* base = QKV + (int64_t)b * N * ld + h * dh;
+  for (int i = threadIdx.x; i < N * dh; i += blockDim.x) {
+    const int j = i / dh, d = i % dh;
+    Ks[j * kst + d] = ldf(base + (int64_t)j * ld + inner + d);
+    Vs[j * dh + d] = ldf(base + (int64_t)j * ld + 2 * inner + d);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* P = Ps + warp * N;
+  float* Q = Qs + warp * dh;
+  for (int i = warp; i < N; i += nw) {
+    for (int d = lane; d < dh; d += 32) Q[d] = ldf(base + (int64_t)i * ld + d);
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) {
+      float s = 0.f;
+      for (int d = 0; d < dh; ++d) s = fmaf(Q[d], Ks[j * kst + d], s);
+      s *= scale;
+      P[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) { const float e = expf(P[j] - mx); P[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    __syncwarp();
+    for (int d = lane; d < dh; d += 32) {
+      float o = 0.f;
+      for (int j = 0; j < N; ++j) o = fmaf(P[j], Vs[j * dh + d], o);
+      stf(O + ((int64_t)b * N + i) * inner + h * dh + d, o * inv);
+    }
+    __syncwarp();
+  }
+}
+
+// Backward: pass 1 (warp per query row) -> lse, delta, dQ ; pass 2 (warp per key row) -> dK, dV.
+template <typename A>
+__global__ void attention_bwd_kernel(const A* __restrict__ QKV, const A* __restrict__ O,
+                                     const A* __restrict__ dO, A* __restrict__ dQKV, int N, int H, int dh,
+                                     float scale) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int inner = H * dh, ld = 3 * inner, st = dh + 1, nw = blockDim.x >> 5;
+  float* Qs = sm;                  // [N][dh+1]
+  float* Ks = Qs + N * st;         // [N][dh+1]
+  float* Vs = Ks + N * st;         // [N][dh+1]
+  float* dOs = Vs + N * st;        // [N][dh+1]
+  float* lse = dOs + N * st;       // [N]
+  float* dlt = lse + N;            // [N]
+  float* W1 = dlt + N;             // [warps][N]
+  float* W2 = W1 + nw * N;         // [warps][N]
+  const A* base = QKV + (int64_t)b * N * ld + h * dh;
+  const int64_t obase = (int64_t)b * N * inner + h * dh;
+  for (int i = threadIdx.x; i < N * dh; i += blockDim.x) {
+    const int j = i / dh, d = i % dh;
+    Qs[j * st + d] = ldf(base + (int64_t)j * ld + d);
+    Ks[j * st + d] = ldf(base + (int64_t)j * ld + inner + d);
+    Vs[j * st + d] = ldf(base + (int64_t)j * ld + 2 * inner + d);
+    dOs[j * st + d] = ldf(dO + obase + (int64_t)j * inner + d);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* P = W1 + warp * N;
+  float* DS = W2 + warp * N;
+  // ---- pass 1: rows of the score matrix
+  for (int i = warp; i < N; i += nw) {
+    float dl = 0.f;
+    for (int d = lane; d < dh; d += 32) dl = fmaf(dOs[i * st + d], ldf(O + obase + (int64_t)i * inner + d), dl);
+    dl = warp_sum(dl);
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) {
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < dh; ++d) {
+        s = fmaf(Qs[i * st + d], Ks[j * st + d], s);
+        dp = fmaf(dOs[i * st + d], Vs[j * st + d], dp);
+      }
+      s *= scale;
+      P[j] = s;
+      DS[j] = dp;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) sum += expf(P[j] - mx);
+    sum = warp_sum(sum);
+    const float l = mx + logf(sum);
+    for (int j = lane; j < N; j += 32) {
+      const float p = expf(P[j] - l);
+      DS[j] = p * (DS[j] - dl) * scale;
+    }
+    if (lane == 0) { lse[i] = l; dlt[i] = dl; }
+    __syncwarp();
+    for (int d = lane; d < dh; d += 32) {
+      float a = 0.f;
+      for (int j = 0; j < N; ++j) a = fmaf(DS[j], Ks[j * st + d], a);
+      stf(dQKV + ((int64_t)b * N + i) * ld + h * dh + d, a);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- pass 2: columns of the score matrix
+  for (int j = warp; j < N; j += nw) {
+    for (int i = lane; i < N; i += 32) {
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < dh; ++d) {
+        s = fmaf(Qs[i * st + d], Ks[j * st + d], s);
+        dp = fmaf(dOs[i * st + d], Vs[j * st + d], dp);
+      }
+      const float p = expf(s * scale - lse[i]);
+      P[i] = p;
+      DS[i] = p * (dp - dlt[i]) * scale;
+    }
+    __syncwarp();
+    for (int d = lane; d < dh; d += 32) {
+      float dk = 0.f, dv = 0.f;
+      for (int i = 0; i < N; ++i) {
+        dk = fmaf(DS[i], Qs[i * st + d], dk);
+        dv = fmaf(P[i], dOs[i * st + d], dv);
+      }
+      stf(dQKV + ((int64_t)b * N + j) * ld + inner + h * dh + d, dk);
+      stf(dQKV + ((int64_t)b * N + j) * ld + 2 * inner + h * dh + d, dv);
+    }
+    __syncwarp();
+  }
+}
+
+// =====================================================================================
+// cls pooling + RMSNorm (vn/GoalFormer.py:167-170,120-122): z = x0/max(|x0|,1e-12)*sqrt(D)*g
+// =====================================================================================
+__global__ void pool_rmsnorm_fwd_kernel(const float* __restrict__ X, const float* __restrict__ g,
+                                        float* __restrict__ z, int B, int N, int D, float sqrtD) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* x = X + (int64_t)b * N * D;
+  float q = 0.f;
+  for (int d = lane; d < D; d += 32) q = fmaf(x[d], x[d], q);
+  const float nrm = fmaxf(sqrtf(warp_sum(q)), 1e-12f);
+  for (int d = lane; d < D; d += 32) z[b * D + d] = x[d] / nrm * sqrtD * g[d];
+}
+
+// dX (full [B,N,D], zero except token 0) and per-sample dg contributions
+__global__ void pool_rmsnorm_bwd_kernel(const float* __restrict__ X, const float* __restrict__ g,
+                                        const float* __restrict__ dz, float* __restrict__ dX,
+                                        bf16* __restrict__ dX_lp, float* __restrict__ dg_rows, int B, int N,
+                                        int D, float sqrtD) {
+  const int b = blockIdx.x;
+  const float* x = X + (int64_t)b * N * D;
+  float* dx = dX + (int64_t)b * N * D;
+  __shared__ float red[2];
+  // zero rows 1..N-1
+  bf16* dxl = dX_lp ? dX_lp + (int64_t)b * N * D : nullptr;
+  for (int i = D + threadIdx.x; i < N * D; i += blockDim.x) {
+    dx[i] = 0.f;
+    if (dxl) dxl[i] = __float2bfloat16_rn(0.f);
+  }
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    float q = 0.f, dot = 0.f;
+    for (int d = lane; d < D; d += 32) q = fmaf(x[d], x[d], q);
+    const float nr = sqrtf(warp_sum(q));
+    const float nrm = fmaxf(nr, 1e-12f);
+    for (int d = lane; d < D; d += 32) dot = fmaf(dz[b * D + d] * g[d], x[d], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) { red[0] = nrm; red[1] = (nr > 1e-12f) ? dot / (nrm * nrm) : 0.f; }
+  }
+  __syncthreads();
+  const float nrm = red[0], proj = red[1];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float w = dz[b * D + d] * g[d];
+    const float nv = sqrtD / nrm * (w - x[d] * proj);
+    dx[d] = nv;
+    if (dxl) dxl[d] = __float2bfloat16_rn(nv);
+    dg_rows[b * D + d] = dz[b * D + d] * x[d] / nrm * sqrtD;
+  }
+}
+
+// =====================================================================================
+// Actor head tail: tanh-Gaussian sample + log-prob (vn/got_sac_network.py:235,238-251)
+// =====================================================================================
+struct SampleArgs {
+  const float* mean;      // [B,na]
+  const float* lstd_raw;  // [B,na] unclamped
+  const float* eps;       // [B,na] or null
+  const float* scale;     // [na]
+  const float* bias;      // [na]
+  const uint64_t* rng;    // when eps == null
+  uint32_t stream_id;
+  int64_t sample_offset;
+  float *mean_out, *log_std, *action, *log_prob, *mean_t, *eps_out;
+  int B, na;
+};
+__global__ void actor_sample_kernel(SampleArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  float lp = 0.f;
+  for (int j = 0; j < a.na; ++j) {
+    const int i = b * a.na + j;
+    const float mu = a.mean[i];
+    const float ls = fminf(fmaxf(a.lstd_raw[i], -20.f), 2.f);
+    if (a.log_std) a.log_std[i] = ls;
+    if (a.mean_out) a.mean_out[i] = mu;
+    float e;
+    if (a.eps) {
+      e = a.eps[i];
+    } else {
+      uint32_t r[4];
+      const uint64_t gi = (uint64_t)(a.sample_offset + b) * a.na + j;
+      philox4x32(a.rng[0], gi, ((uint64_t)a.stream_id << 32) | (a.rng[1] & 0xffffffffu), r);
+      e = sqrtf(-2.0f * logf(u01(r[0]))) * cospif(2.0f * u01(r[1]));
+    }
+    if (a.eps_out) a.eps_out[i] = e;
+    const float sd = expf(ls);
+    const float x = mu + sd * e;
+    const float y = tanhf(x);
+    const float sc = a.scale[j];
+    if (a.action) a.action[i] = y * sc + a.bias[j];
+    if (a.mean_t) a.mean_t[i] = tanhf(mu) * sc + a.bias[j];
+    const float dx = x - mu;
+    lp += -(dx * dx) / (2.0f * sd * sd) - ls - 0.91893853320467274178f;
+    lp -= logf(sc * (1.0f - y * y) + 1e-6f);
+  }
+  if (a.log_prob) a.log_prob[b] = lp;
+}
+
+struct SampleBwdArgs {
+  const float *mean, *lstd_raw, *eps, *scale;
+  const float *d_mean, *d_log_std, *d_action, *d_log_prob, *d_mean_t;  // any may be null
+  float d_log_prob_const;          // host constant added to every d_log_prob
+  const float* d_log_prob_dev;     // optional device scalar (alpha) ...
+  float d_log_prob_dev_scale;      // ... times this (1/B_global)
+  float *d_mean_out, *d_lstd_out;  // [B,na] each: d/d mean, d/d raw log_std
+  int B, na;
+};
+__global__ void actor_sample_bwd_kernel(SampleBwdArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.B * a.na) return;
+  const int b = i / a.na, j = i % a.na;
+  const float mu = a.mean[i], raw = a.lstd_raw[i];
+  const float ls = fminf(fmaxf(raw, -20.f), 2.f);
+  const float sd = expf(ls), e = a.eps[i], sc = a.scale[j];
+  const float y = tanhf(mu + sd * e);
+  const float omy = 1.0f - y * y;
+  const float glp = (a.d_log_prob ? a.d_log_prob[b] : 0.f) + a.d_log_prob_const +
+                    (a.d_log_prob_dev ? (*a.d_log_prob_dev) * a.d_log_prob_dev_scale : 0.f);
+  // d/dx of  action (= y*sc+bias) and of  -log(sc*(1-y^2)+1e-6); the Normal.log_prob terms in
+  // mean cancel analytically (d/dmu = 0) and leave -1/sd in d/dsd.
+  float gx = glp * (2.0f * sc * y * omy / (sc * omy + 1e-6f));
+  if (a.d_action) gx += a.d_action[i] * sc * omy;
+  float gmu = gx;
+  float gsd = gx * e - glp / sd;
+  if (a.d_mean) gmu += a.d_mean[i];
+  if (a.d_mean_t) { const float t = tanhf(mu); gmu += a.d_mean_t[i] * sc * (1.0f - t * t); }
+  float gls = gsd * sd;
+  if (a.d_log_std) gls += a.d_log_std[i];
+  if (!(raw >= -20.f && raw <= 2.f)) gls = 0.f;  // clamp backward
+  a.d_mean_out[i] = gmu;
+  a.d_lstd_out[i] = gls;
+}
+
+// g *= (h > 0)
+__global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ h, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(h[i] > 0.f)) g[i] = 0.f;
+}
+
+// cat([z, a]) (vn/got_sac_network.py:114) and its inverse for gradients
+__global__ void concat_za_kernel(const float* __restrict__ z, const float* __restrict__ a,
+                                 float* __restrict__ out, int B, int D, int na) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = D + na;
+  if (i >= B * W) return;
+  const int b = i / W, c = i % W;
+  out[i] = c < D ? z[b * D + c] : a[b * na + (c - D)];
+}
+// dxcat = dx1 + dx2 ; split into dz and da
+__global__ void split_dza_kernel(const float* __restrict__ dx1, const float* __restrict__ dx2,
+                                 float* __restrict__ dz, float* __restrict__ da, int B, int D, int na) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = D + na;
+  if (i >= B * W) return;
+  const int b = i / W, c = i % W;
+  const float v = dx1[i] + dx2[i];
+  if (c < D) { if (dz) dz[b * D + c] = v; }
+  else if (da) da[b * na + (c - D)] = v;
+}
+
+// =====================================================================================
+// SAC losses (vn/DRL.py:388-399, 404-410, 416-424).  Single block, fixed-order reductions.
+// =====================================================================================
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.x == 0) { for (int w = 0; w < nw; ++w) s += red[w]; red[0] = s; }
+  __syncthreads();
+  s = red[0];
+  return s;
+}
+
+// next_q = r + gamma*(min(q1t,q2t) - alpha*logp')   [B,na]   (no (1-done), DRL.py:393)
+// then qf losses and their gradients wrt q1,q2 (mse mean over B_global*na elements).
+__global__ void critic_loss_kernel(const float* __restrict__ q1, const float* __restrict__ q2,
+                                   const float* __restrict__ q1t, const float* __restrict__ q2t,
+                                   const float* __restrict__ logp2, const float* __restrict__ rew,
+                                   const float* __restrict__ alpha, float gamma, int B, int na,
+                                   int Bglobal, float* __restrict__ nq_out, float* __restrict__ dq1,
+                                   float* __restrict__ dq2, float* __restrict__ losses) {
+  __shared__ float red[32];
+  const float al = *alpha;
+  const float inv = 1.0f / ((float)Bglobal * na);
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < B * na; i += blockDim.x) {
+    const int b = i / na;
+    const float nq = rew[b] + gamma * (fminf(q1t[i], q2t[i]) - al * logp2[b]);
+    if (nq_out) nq_out[i] = nq;
+    const float e1 = q1[i] - nq, e2 = q2[i] - nq;
+    s1 = fmaf(e1, e1, s1);
+    s2 = fmaf(e2, e2, s2);
+    dq1[i] = 2.0f * e1 * inv;
+    dq2[i] = 2.0f * e2 * inv;
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (threadIdx.x == 0) { losses[0] = s1 * inv; losses[2] = s2 * inv; }
+}
+
+// policy_loss = mean_{b,j}(alpha*log_pi[b] - min(q1pi,q2pi)[b,j]); alpha_loss and its gradient.
+// galpha[0] receives d alpha_loss / d log_alpha (local shard share, SUM-reducible).
+__global__ void policy_loss_kernel(const float* __restrict__ q1p, const float* __restrict__ q2p,
+                                   const float* __restrict__ logpi, const float* __restrict__ alpha,
+                                   const float* __restrict__ log_alpha, float target_entropy, int B, int na,
+                                   int Bglobal, float* __restrict__ dq1, float* __restrict__ dq2,
+                                   float* __restrict__ losses, float* __restrict__ galpha) {
+  __shared__ float red[32];
+  const float al = *alpha;
+  const float inv = 1.0f / ((float)Bglobal * na);
+  float sp = 0.f, sa = 0.f;
+  for (int i = threadIdx.x; i < B * na; i += blockDim.x) {
+    const int b = i / na;
+    const float a1 = q1p[i], a2 = q2p[i];
+    sp += al * logpi[b] - fminf(a1, a2);
+    // torch.min(a,b) backward: ties split the gradient equally
+    const float w1 = a1 < a2 ? 1.f : (a1 == a2 ? 0.5f : 0.f);
+    dq1[i] = -inv * w1;
+    dq2[i] = -inv * (1.f - w1);
+    if (i % na == 0) sa += logpi[b] + target_entropy;
+  }
+  sp = block_sum(sp, red);
+  sa = block_sum(sa, red);
+  if (threadIdx.x == 0) {
+    losses[1] = sp * inv;
+    const float g = -sa / (float)Bglobal;      // d/dlog_alpha of -(log_alpha*(log_pi+H)).mean()
+    losses[3] = (*log_alpha) * g;              // alpha_loss value (local share)
+    galpha[0] = g;
+  }
+}
+
+// Adam on the scalar log_alpha, then alpha = exp(log_alpha)  (DRL.py:419-423)
+__global__ void alpha_step_kernel(float* log_alpha, float* alpha, float* m, float* v, int64_t* step,
+                                  const float* g, float lr, float b1, float b2, float omb1, float omb2,
+                                  float eps) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int64_t t = ++(*step);
+  const float gr = *g;
+  *m = *m + omb1 * (gr - *m);
+  *v = *v * b2 + omb2 * gr * gr;
+  const double bc1 = 1.0 - pow((double)b1, (double)t);
+  const double bc2 = 1.0 - pow((double)b2, (double)t);
+  const float denom = sqrtf(*v) / (float)sqrt(bc2) + eps;
+  *log_alpha = *log_alpha - (float)((double)lr / bc1) * (*m / denom);
+  *alpha = expf(*log_alpha);
+}
+
+// =====================================================================================
+// Adam (torch.optim.Adam defaults; vn/DRL.py:113,150) fused with the Polyak target update
+// (vn/utils.py:31-33) and the bf16 shadow refresh.  One pass over the flat arenas.
+// =====================================================================================
+struct AdamArgs {
+  float* p; const float* g; float* m; float* v; bf16* shadow;
+  float* tgt; bf16* tgt_shadow; float tau;   // polyak target (may be null)
+  int64_t n; int64_t* step;                  // device step counter (incremented by the bump kernel)
+  float lr, b1, b2, eps;
+  float omb1, omb2;                          // (float)(1 - beta) computed in double like torch
+  int n_skip; int64_t skip_b[4], skip_e[4];
+};
+__global__ void step_bump_kernel(int64_t* step) { if (threadIdx.x == 0 && blockIdx.x == 0) ++(*step); }
+
+__global__ void adam_polyak_kernel(AdamArgs a) {
+  __shared__ float sh[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)(*a.step);
+    const double bc1 = 1.0 - pow((double)a.b1, t);
+    const double bc2 = 1.0 - pow((double)a.b2, t);
+    sh[0] = (float)((double)a.lr / bc1);
+    sh[1] = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = sh[0], bc2s = sh[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    bool skip = false;
+    for (int k = 0; k < a.n_skip; ++k) skip |= (i >= a.skip_b[k] && i < a.skip_e[k]);
+    float p = a.p[i];
+    if (!skip) {
+      const float g = a.g[i];
+      float m = a.m[i], v = a.v[i];
+      m = m + a.omb1 * (g - m);                        // exp_avg.lerp_(grad, 1-beta1)
+      v = v * a.b2 + a.omb2 * g * g;                   // mul_(beta2).addcmul_(g,g,1-beta2)
+      const float denom = sqrtf(v) / bc2s + a.eps;
+      p = p - step_size * (m / denom);
+      a.m[i] = m; a.v[i] = v; a.p[i] = p;
+    }
+    if (a.shadow) a.shadow[i] = __float2bfloat16_rn(p);
+    if (a.tgt) {
+      const float t = a.tgt[i] * (1.0f - a.tau) + p * a.tau;
+      a.tgt[i] = t;
+      if (a.tgt_shadow) a.tgt_shadow[i] = __float2bfloat16_rn(t);
+    }
+  }
+}
+
+__global__ void polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, bf16* tgt_shadow,
+                              float tau, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float t = (tau == 1.0f) ? src[i] : tgt[i] * (1.0f - tau) + src[i] * tau;
+    tgt[i] = t;
+    if (tgt_shadow) tgt_shadow[i] = __float2bfloat16_rn(t);
+  }
+}
+
+__global__ void shadow_refresh_kernel(const float* __restrict__ p, bf16* __restrict__ s, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    s[i] = __float2bfloat16_rn(p[i]);
+}
+
+__global__ void rng_advance_kernel(uint64_t* rng) { if (threadIdx.x == 0 && blockIdx.x == 0) rng[1] += 1; }
+
+// =====================================================================================
+// Replay gather (cpprb sample(); vn/DRL.py:375-386): bit-exact 16-byte vectorised row copies.
+// grid = (chunks, B, 2): z=0 -> obs[idx], z=1 -> obs[(idx+1)%size]
+// =====================================================================================
+__global__ void replay_gather_frames_kernel(const float4* __restrict__ store, const int64_t* __restrict__ idx,
+                                            int64_t size, int64_t frame4, float4* __restrict__ obs,
+                                            float4* __restrict__ next_obs) {
+  const int b = blockIdx.y;
+  int64_t r = idx[b];
+  float4* dst = obs;
+  if (blockIdx.z == 1) { r = (r + 1) % size; dst = next_obs; }
+  if (!dst) return;
+  const float4* src = store + r * frame4;
+  dst += (int64_t)b * frame4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < frame4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + i));
+    dst[i] = v;
+  }
+}
+struct SmallGather {
+  const float* src[5]; float* dst[5]; int width[5]; int n;
+};
+__global__ void replay_gather_small_kernel(SmallGather s, const int64_t* __restrict__ idx, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t r = idx[b];
+  for (int k = 0; k < s.n; ++k) {
+    if (!s.dst[k] || !s.src[k]) continue;
+    for (int j = 0; j < s.width[k]; ++j) s.dst[k][b * s.width[k] + j] = s.src[k][r * s.width[k] + j];
+  }
+}
+
+}  // namespace dgvit

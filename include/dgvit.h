@@ -1,0 +1,263 @@
+/*
+ * dgvit.h — C ABI of libdgvit.so, the B200 (sm_100a) implementation of the DGViT
+ * actor-critic hot path.
+ *
+ * The reference (REGRAGUIahmed/DGViT-…) is pure Python/PyTorch and has no FFI of its
+ * own; the boundary a maintainer would bind is the nn.Module / SAC method surface.
+ * Each entry point below names the reference interface it replaces
+ * (paths relative to src/vis_nav/vis_nav/ = "vn/").  The ctypes binding is shown in
+ * INTEGRATION.md and implemented in dgvit_b200/_lib.py.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - the library owns no memory: parameters, gradients, optimizer state, workspaces and
+ *     outputs are allocated by the caller (PyTorch on the Python side).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no
+ *     host synchronisation and is CUDA-graph capturable.
+ *   - return value: 0 = ok, negative = error; dgvit_last_error() returns a thread-local
+ *     message.  No exceptions cross the boundary.
+ */
+#ifndef DGVIT_H_
+#define DGVIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGVIT_MAX_DEPTH 16
+#define DGVIT_ALIGN_FLOATS 64 /* every tensor starts on a 256-byte boundary inside an arena */
+
+enum { DGVIT_ACTOR = 0, DGVIT_CRITIC = 1 };
+enum { DGVIT_FP32 = 0, DGVIT_BF16 = 1 };                 /* arithmetic of the contractions */
+enum { DGVIT_DROP_NONE = 0, DGVIT_DROP_MASK = 1, DGVIT_DROP_RNG = 2 };
+
+enum {
+  DGVIT_OK = 0,
+  DGVIT_ERR_ARG = -1,       /* bad argument / unsupported shape */
+  DGVIT_ERR_WORKSPACE = -2, /* workspace too small */
+  DGVIT_ERR_CUDA = -3       /* a CUDA call failed (message has the cudaError string) */
+};
+
+/* Shapes of one network: GoTPolicy(nb_actions, nb_pstate, block, head, l_f_size)
+ * vn/got_sac_network.py:173-185 / GoTQNetwork(...) :76-88; GoT(...) vn/GoalFormer.py:124. */
+typedef struct dgvit_cfg {
+  int32_t kind;     /* DGVIT_ACTOR | DGVIT_CRITIC */
+  int32_t img_h, img_w, patch_h, patch_w; /* 128,160,16,20 */
+  int32_t dim;      /* l_f_size */
+  int32_t depth;    /* block */
+  int32_t heads;    /* head */
+  int32_t dim_head; /* 64 */
+  int32_t mlp_dim;  /* 2048 */
+  int32_t n_act;    /* nb_actions (2) */
+  int32_t n_pstate; /* nb_pstate (2) */
+} dgvit_cfg;
+
+/* Offsets (in floats) of every parameter tensor inside the flat arena, in the reference's
+ * registration order (= module.parameters() order, which vn/utils.py:31-37 zips). */
+typedef struct dgvit_block_layout {
+  int64_t ln1_w, ln1_b, qkv_w, out_w, out_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b;
+} dgvit_block_layout;
+
+typedef struct dgvit_layout {
+  int64_t total; /* arena length in floats (padded) */
+  int64_t pos, cls, rms_g, patch_w, patch_b;
+  dgvit_block_layout block[DGVIT_MAX_DEPTH];
+  int64_t mlp_head_ln_w, mlp_head_ln_b, mlp_head_w, mlp_head_b; /* constructed, never used */
+  /* actor heads */
+  int64_t embed_w, embed_b, fc1_w, fc1_b, fc2_w, fc2_b, mean_w, mean_b, lstd_w, lstd_b;
+  /* critic heads (conv1-3 are constructed, never used) */
+  int64_t conv1_w, conv1_b, conv2_w, conv2_b, conv3_w, conv3_b;
+  int64_t fc3_w, fc3_b, fc11_w, fc11_b, fc21_w, fc21_b, fc31_w, fc31_b;
+  /* ranges Adam skips because the reference never produces a gradient for them
+   * (grad is None: cls_token, mlp_head.*, conv1-3) */
+  int32_t n_skip;
+  int64_t skip_begin[4], skip_end[4];
+  /* actor only: one extra float at the end of the arena that carries d(alpha_loss)/d(log_alpha)
+   * in the GRADIENT arena, so that a single all-reduce of actor.grads covers it (data parallel) */
+  int64_t alpha_grad_slot;
+} dgvit_layout;
+
+/* One network instance: caller-owned arenas, all `layout.total` elements long. */
+typedef struct dgvit_net {
+  dgvit_cfg cfg;
+  float* params;    /* fp32 master parameters */
+  float* grads;     /* fp32 gradients (written, not accumulated, by *_backward) */
+  uint16_t* shadow; /* bf16 copy of params for DGVIT_BF16 (may be NULL for DGVIT_FP32) */
+} dgvit_net;
+
+/* Stochastic inputs of one trunk call (vn/GoalFormer.py:163, emb dropout p=0.1). */
+typedef struct dgvit_drop {
+  int32_t mode;              /* DGVIT_DROP_* */
+  float p;                   /* 0.1 */
+  const uint8_t* keep_mask;  /* [B, N, D] {0,1}, DGVIT_DROP_MASK */
+  const uint64_t* rng_state; /* device {seed, counter}, DGVIT_DROP_RNG */
+  uint32_t stream_id;        /* distinguishes the calls inside one update */
+} dgvit_drop;
+
+/* ---- GoTPolicy.forward / .sample  (vn/got_sac_network.py:221-251) ------------------ */
+typedef struct dgvit_actor_io {
+  const float* img;    /* [B, img_h, img_w] */
+  const float* pstate; /* [B, n_pstate] */
+  const float* eps;    /* [B, n_act] N(0,1) draws of rsample, or NULL -> generated from rng */
+  const float* action_scale; /* [n_act] */
+  const float* action_bias;  /* [n_act] */
+  dgvit_drop drop;
+  int32_t sample_offset; /* global index of local sample 0 (data-parallel RNG slicing) */
+  /* outputs (any may be NULL except mean/log_std) */
+  float* mean;     /* [B, n_act]  pre-tanh mean */
+  float* log_std;  /* [B, n_act]  clamped to [-20, 2] */
+  float* action;   /* [B, n_act] */
+  float* log_prob; /* [B, 1] */
+  float* mean_t;   /* [B, n_act]  tanh(mean)*scale+bias */
+  float* eps_out;  /* [B, n_act]  the eps actually used (needed by backward) */
+} dgvit_actor_io;
+
+typedef struct dgvit_actor_grad {
+  const float* d_mean;     /* [B, n_act] or NULL */
+  const float* d_log_std;  /* [B, n_act] or NULL */
+  const float* d_action;   /* [B, n_act] or NULL */
+  const float* d_log_prob; /* [B, 1] or NULL */
+  const float* d_mean_t;   /* [B, n_act] or NULL */
+  float d_log_prob_const;  /* added to every d_log_prob element (alpha/B in SAC) */
+} dgvit_actor_grad;
+
+/* ---- GoTQNetwork.forward (vn/got_sac_network.py:107-123) ---------------------------- */
+typedef struct dgvit_critic_io {
+  const float* img;    /* [B, img_h, img_w] */
+  const float* pstate; /* [B, n_pstate] */
+  const float* action; /* [B, n_act] */
+  dgvit_drop drop;
+  float* q1; /* [B, n_act]  (the reference's Q heads emit nb_actions values, :97,:103) */
+  float* q2; /* [B, n_act] */
+} dgvit_critic_io;
+
+/* ---- SAC.learn (vn/DRL.py:373-437) -------------------------------------------------- */
+typedef struct dgvit_adam {
+  float* m;       /* [layout.total] exp_avg */
+  float* v;       /* [layout.total] exp_avg_sq */
+  int64_t* step;  /* device scalar, incremented by the kernel */
+  float lr, beta1, beta2, eps;
+} dgvit_adam;
+
+typedef struct dgvit_sac {
+  dgvit_net actor, critic, critic_target;
+  dgvit_adam actor_opt, critic_opt;
+  /* entropy temperature (vn/DRL.py:136-139,416-424); device scalars */
+  float* log_alpha; float* alpha; float* alpha_m; float* alpha_v; int64_t* alpha_step;
+  float lr_alpha; int32_t auto_alpha; float target_entropy;
+  float gamma, tau;
+  int32_t do_polyak;      /* itera % policy_freq == 0 (vn/DRL.py:430) */
+  int32_t precision;      /* DGVIT_FP32 | DGVIT_BF16 */
+  int32_t global_batch;   /* loss means are taken over this many samples (data parallel) */
+  int32_t sample_offset;  /* this rank's first sample inside the global batch */
+  uint64_t* rng_state;    /* device {seed, counter}; counter advanced once per update */
+  const float* action_scale; const float* action_bias;
+} dgvit_sac;
+
+typedef struct dgvit_batch {   /* one replay minibatch, already on the device */
+  const float *obs, *next_obs;   /* [B, img_h, img_w] */
+  const float *pobs, *next_pobs; /* [B, n_pstate] */
+  const float *act;              /* [B, n_act] */
+  const float *rew;              /* [B, 1] */
+  const float *done;             /* [B, 1]  read by the reference, unused (vn/DRL.py:393) */
+} dgvit_batch;
+
+typedef struct dgvit_noise {   /* parity mode: injected stochastic inputs; all NULL = RNG */
+  const float *eps_next, *eps_pi;                  /* [B, n_act] */
+  const uint8_t *mask_a_next, *mask_ct, *mask_c, *mask_a, *mask_c_pi; /* [B, N, D] */
+  int32_t drop_mode;                               /* DGVIT_DROP_* */
+} dgvit_noise;
+
+typedef struct dgvit_sac_out {
+  float* losses;   /* [4] qf1_loss, policy_loss, qf2_loss, alpha_loss (sums over the local
+                      shard already divided by global_batch; all-reduce SUM across ranks) */
+  float* debug;    /* optional [B*(5*n_act+1)]: nq, q1, q2, pi, (q1pi) , log_pi ; or NULL */
+} dgvit_sac_out;
+
+/* -------------------------------------------------------------------------------------- */
+int dgvit_version(void);
+const char* dgvit_last_error(void);
+
+/* parameter arena layout for `cfg` (mirrors module.parameters() order) */
+int dgvit_param_layout(const dgvit_cfg* cfg, dgvit_layout* out);
+
+/* bytes of workspace a forward (+ saved activations when save_for_backward) needs */
+int dgvit_workspace_bytes(const dgvit_cfg* cfg, int B, int precision, int save_for_backward,
+                          size_t* bytes);
+/* bytes of workspace dgvit_sac_* needs for a local batch of B */
+int dgvit_sac_workspace_bytes(const dgvit_cfg* actor_cfg, int B, int precision, size_t* bytes);
+
+/* refresh the bf16 shadow of a parameter arena (after load_state_dict etc.) */
+int dgvit_refresh_shadow(const dgvit_net* net, void* stream);
+
+/* GoTPolicy.forward/.sample — vn/got_sac_network.py:221-251 */
+int dgvit_actor_forward(const dgvit_net* net, const dgvit_actor_io* io, int B, int precision,
+                        int save_for_backward, void* workspace, size_t workspace_bytes,
+                        void* stream);
+/* backward of the above through the saved workspace; writes net->grads */
+int dgvit_actor_backward(const dgvit_net* net, const dgvit_actor_io* io,
+                         const dgvit_actor_grad* g, int B, int precision, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* GoTQNetwork.forward — vn/got_sac_network.py:107-123 */
+int dgvit_critic_forward(const dgvit_net* net, const dgvit_critic_io* io, int B, int precision,
+                         int save_for_backward, void* workspace, size_t workspace_bytes,
+                         void* stream);
+/* backward: d_q1,d_q2 [B,n_act]; writes net->grads when param_grads != 0 and
+ * d_action [B,n_act] when non-NULL */
+int dgvit_critic_backward(const dgvit_net* net, const dgvit_critic_io* io, const float* d_q1,
+                          const float* d_q2, float* d_action, int param_grads, int B,
+                          int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* SAC.learn in three phases so that a data-parallel caller can all-reduce the gradient
+ * arenas between them (vn/DRL.py:388-402 | :404-413 | :414-432):
+ *   phase 1: TD target + critic forward/backward        -> critic.grads
+ *   phase 2: critic Adam; actor forward; critic(s,pi); policy/alpha losses; backward
+ *                                                      -> actor.grads (+ alpha grad slot)
+ *   phase 3: actor Adam, alpha Adam, Polyak target update, RNG counter advance
+ * dgvit_sac_update = phases 1-3 back to back (single GPU). */
+int dgvit_sac_phase1(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* nz,
+                     const dgvit_sac_out* out, int B, void* workspace, size_t workspace_bytes,
+                     void* stream);
+int dgvit_sac_phase2(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* nz,
+                     const dgvit_sac_out* out, int B, void* workspace, size_t workspace_bytes,
+                     void* stream);
+int dgvit_sac_phase3(const dgvit_sac* s, int B, void* workspace, size_t workspace_bytes,
+                     void* stream);
+int dgvit_sac_update(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* nz,
+                     const dgvit_sac_out* out, int B, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* torch.optim.Adam.step (+ optional fused Polyak target update, vn/utils.py:31-33, and bf16
+ * shadow refresh) over a flat arena; skips layout.skip ranges */
+int dgvit_adam_step(const dgvit_net* net, const dgvit_adam* opt, const dgvit_net* polyak_target,
+                    float tau, void* stream);
+/* soft_update / hard_update (tau = 1) over all parameters — vn/utils.py:31-37 */
+int dgvit_polyak(const dgvit_net* target, const dgvit_net* source, float tau, void* stream);
+
+/* cpprb sample() row gather + staging — vn/DRL.py:375-386.  Bit-exact copies.
+ * store_obs [size, frame] with next_obs[i] = obs[(i+1)%size] (cpprb next_of="obs"). */
+typedef struct dgvit_replay {
+  const float* obs; int64_t size; int64_t frame; /* frame = img_h*img_w floats */
+  const float *pobs, *next_pobs, *act, *rew, *done; int32_t n_pstate, n_act;
+} dgvit_replay;
+int dgvit_replay_gather(const dgvit_replay* store, const int64_t* idx, int B, float* obs,
+                        float* next_obs, float* pobs, float* next_pobs, float* act, float* rew,
+                        float* done, void* stream);
+
+/* depth normalise + noise + blur + resize — vn/env_lab.py:420-434,78-90,69-76,295-299.
+ * raw [n, H, W] f32, noise [n, H, W] f32 (N(0,50) draws) or NULL (generated from rng),
+ * out [n, H/4, W/4] f32 in [0,1]; scratch >= dgvit_depth_scratch_bytes(n,H,W). */
+int dgvit_depth_scratch_bytes(int n, int H, int W, size_t* bytes);
+int dgvit_depth_augment(const float* raw, const float* noise, const uint64_t* rng_state, int n,
+                        int H, int W, float* out, void* scratch, size_t scratch_bytes,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGVIT_H_ */

@@ -1,0 +1,242 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded inputs, and against the committed golden vectors recorded from the live reference.
+
+Tolerances (BASELINE.json north_star): fp32 path <= 1e-4 relative; bf16 path <= 1e-2 relative on
+actions / Q; replay gather bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import dgvit_b200 as dg
+from dgvit_b200 import _lib as L
+from helpers import (O, SEED, golden, load_params, reference_init, reference_sac_init, relerr, synthetic_batch,
+                     synthetic_noise, unpack_mask)
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4
+BF16_TOL = 1e-2
+
+
+def _mk(kind, cfg, params, precision="fp32"):
+    cls = dg.GoTPolicy if kind == "actor" else dg.GoTQNetwork
+    m = cls(2, 2, cfg.depth, cfg.heads, cfg.dim, image_size=(cfg.img_h, cfg.img_w))
+    load_params(m, params)
+    m = m.to("cuda")
+    m.precision = precision
+    return m
+
+
+@pytest.mark.parametrize("tag,block,head,lfs,B", [("small", 2, 2, 32, 3), ("shipped", 4, 4, 64, 4)])
+def test_forward_matches_golden_reference_outputs(tag, block, head, lfs, B):
+    """Outputs recorded from the imported reference modules (eval mode and train mode with the
+    replayed dropout mask / rsample noise)."""
+    g = golden(f"modules_{tag}.npz")
+    cfg = O.Cfg(dim=lfs, depth=block, heads=head)
+    a = _mk("actor", cfg, reference_init("actor", cfg, SEED))
+    c = _mk("critic", cfg, reference_init("critic", cfg, SEED + 1))
+    batch = synthetic_batch(cfg, B, SEED + 2)
+    img, goal, act = (batch[k].cuda() for k in ("obs", "pobs", "act"))
+    a.eval(); c.eval()
+    with torch.no_grad():
+        mean, log_std = a([img, goal])
+        q1, q2 = c([img, goal, act])
+    for n, v in dict(mean=mean, log_std=log_std, q1=q1, q2=q2).items():
+        assert relerr(v, g["eval_" + n]) < FP32_TOL, n
+    a.train(); c.train()
+    shp = (B, cfg.n_tokens, cfg.dim)
+    a.inject_noise(mask=unpack_mask(g["train_mask_a"], shp), eps=torch.from_numpy(g["train_eps"]))
+    c.inject_noise(mask=unpack_mask(g["train_mask_c"], shp))
+    with torch.no_grad():
+        action, logp, mean_t = a.sample([img, goal])
+        q1, q2 = c([img, goal, action])
+    for n, v in dict(action=action, log_prob=logp, mean_t=mean_t, q1=q1, q2=q2).items():
+        assert relerr(v, g["train_" + n]) < FP32_TOL, n
+
+
+@pytest.mark.parametrize("block,head,lfs,B", [(2, 2, 32, 5), (4, 4, 64, 3), (1, 3, 96, 2)])
+def test_gradients_match_oracle_fp32(block, head, lfs, B):
+    """autograd through the nn.Module surface == oracle autograd, per parameter."""
+    cfg = O.Cfg(dim=lfs, depth=block, heads=head)
+    pa, pc = reference_init("actor", cfg, 11), reference_init("critic", cfg, 12)
+    a, c = _mk("actor", cfg, pa), _mk("critic", cfg, pc)
+    batch = synthetic_batch(cfg, B, 13)
+    nz = synthetic_noise(cfg, B, 14)
+    img, goal = batch["obs"], batch["pobs"]
+
+    def loss_fn(lp, q1, q2, mt):
+        return (lp.mean() * 0.3 - torch.min(q1, q2).mean()) + (q1 ** 2).mean() * 0.1 + (mt ** 2).sum() * 0.01
+
+    pa_g = {k: v.clone().requires_grad_(True) for k, v in pa.items()}
+    pc_g = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    oa, olp, omt = O.actor_sample(pa_g, img, goal, nz["eps_pi"], cfg, nz["mask_a"])
+    oq1, oq2 = O.critic_forward(pc_g, img, goal, oa, cfg, nz["mask_c"])
+    loss_fn(olp, oq1, oq2, omt).backward()
+
+    a.inject_noise(mask=nz["mask_a"], eps=nz["eps_pi"])
+    c.inject_noise(mask=nz["mask_c"])
+    act, lp, mt = a.sample([img.cuda(), goal.cuda()])
+    q1, q2 = c([img.cuda(), goal.cuda(), act])
+    for n, (x, y) in dict(action=(act, oa), logp=(lp, olp), q1=(q1, oq1), q2=(q2, oq2)).items():
+        assert relerr(x, y) < FP32_TOL, n
+    loss_fn(lp, q1, q2, mt).backward()
+    for mod, og in ((a, pa_g), (c, pc_g)):
+        for k, p in mod.named_parameters():
+            if og[k].grad is None:
+                assert p.grad is None, k            # Adam must skip exactly these (cls_token, mlp_head, conv)
+                continue
+            assert p.grad is not None, k
+            assert relerr(p.grad, og[k].grad) < 2e-4, (k, relerr(p.grad, og[k].grad))
+
+
+def _agent(cfg, precision, seed=SEED):
+    ag = dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, False, seed, LR_C=1e-3, LR_A=1e-3,
+                LR_ALPHA=1e-4, BUFFER_SIZE=64, TAU=5e-4, POLICY_FREQ=1, GAMMA=0.999, ALPHA=1.0, block=cfg.depth,
+                head=cfg.heads, l_f_size=cfg.dim, automatic_entropy_tuning=True, precision=precision)
+    return ag
+
+
+def _noise_cuda(noise):
+    out = {}
+    for k, v in noise.items():
+        if v is None:
+            continue
+        out[k] = v.cuda().to(torch.uint8).contiguous() if k.startswith("mask") else v.cuda().contiguous()
+    return out
+
+
+@pytest.mark.parametrize("tag,block,head,lfs,B", [("small", 2, 2, 32, 4), ("shipped", 4, 4, 64, 4)])
+def test_learn_matches_golden_reference_run(tag, block, head, lfs, B):
+    """3 fused updates vs the recorded run of the UNMODIFIED reference SAC.learn (same seeds,
+    replayed noise) and vs the oracle stepping beside it."""
+    g = golden(f"learn_{tag}.npz")
+    cfg = O.Cfg(dim=lfs, depth=block, heads=head)
+    ag = _agent(cfg, "fp32")
+    actor0, critic0 = reference_sac_init(cfg, SEED)
+    for k, v in ag.policy.state_dict().items():      # same seed + same construction order => same weights
+        assert torch.equal(v.cpu(), actor0[k]), k
+    for k, v in ag.critic.state_dict().items():
+        assert torch.equal(v.cpu(), critic0[k]), k
+    orc = O.SACOracle(actor0, critic0, cfg)
+    shp = (B, cfg.n_tokens, cfg.dim)
+    n = int(np.prod(shp))
+    for s in range(int(g["cfg"][4])):
+        batch = synthetic_batch(cfg, B, SEED + 10 + s)
+        bits = np.unpackbits(g[f"step{s}_noise_bits"])
+        noise = {k: torch.from_numpy(bits[i * n:][:n].reshape(shp).astype(np.float32))
+                 for i, k in enumerate(("mask_a_next", "mask_ct", "mask_c", "mask_a", "mask_c_pi"))}
+        noise["eps_next"], noise["eps_pi"] = (torch.from_numpy(x) for x in g[f"step{s}_eps"])
+        orc.learn(batch, noise)
+        cb = {k: v.reshape(B, -1).cuda().contiguous() for k, v in batch.items()}
+        losses = ag.update_from_batch(cb, _noise_cuda(noise)).cpu().numpy()
+        ref = g[f"step{s}_losses"]
+        assert abs(losses[0] - ref[0]) <= FP32_TOL * max(1.0, abs(ref[0])), (s, losses, ref)
+        assert abs(losses[1] - ref[1]) <= FP32_TOL * max(1.0, abs(ref[1])), (s, losses, ref)
+        assert abs(float(ag.log_alpha) - float(g[f"step{s}_log_alpha"])) < 1e-6
+        for nm, mod, od in (("actor", ag.policy, orc.actor), ("critic", ag.critic, orc.critic),
+                            ("target", ag.critic_target, orc.critic_target)):
+            worst = 0.0
+            for k, p in mod.named_parameters():
+                d = (p.detach().cpu() - od[k]).abs()
+                worst = max(worst, float(d.max()))
+                # Adam's g/(|g|+eps) amplifies rounding where |g| ~ 1e-8: demand the bulk to be tight
+                assert float((d > 2e-5 * (s + 1)).float().mean()) < 2e-3, (s, nm, k)
+            assert worst < 2.5e-3 * (s + 1), (s, nm, worst)
+            ab = np.array([float(p.detach().double().abs().sum()) for p in mod.parameters()])
+            np.testing.assert_allclose(ab, g[f"step{s}_{nm}_abssum"], rtol=2e-4, atol=2e-3)
+
+
+def test_learn_gradients_match_oracle_fp32():
+    """Per-parameter gradient parity of one fused update at the shipped preset."""
+    cfg = O.Cfg()
+    B = 6
+    ag = _agent(cfg, "fp32", seed=77)
+    actor0 = {k: v.detach().cpu().clone() for k, v in ag.policy.named_parameters()}
+    critic0 = {k: v.detach().cpu().clone() for k, v in ag.critic.named_parameters()}
+    orc = O.SACOracle(actor0, critic0, cfg)
+    batch = synthetic_batch(cfg, B, 5)
+    noise = synthetic_noise(cfg, B, 6)
+    orc.learn(batch, noise)
+    cb = {k: v.reshape(B, -1).cuda().contiguous() for k, v in batch.items()}
+    dbg = torch.zeros(B * (5 * 2 + 1), device="cuda")
+    ag.update_from_batch(cb, _noise_cuda(noise), debug=dbg)
+    d = dbg.cpu()
+    for i, k in enumerate(("nq", "q1", "q2", "pi", "q1p")):
+        assert relerr(d[i * B * 2:(i + 1) * B * 2].reshape(B, 2), orc.last[k]) < FP32_TOL, k
+    assert relerr(d[5 * B * 2:5 * B * 2 + B].reshape(B, 1), orc.last["log_pi"]) < FP32_TOL
+    for mod, og in ((ag.critic, orc.last_critic_grads), (ag.policy, orc.last_actor_grads)):
+        for (k, off), p in zip(mod._named_offsets(), mod.parameters()):
+            gr = mod._garena[off:off + p.numel()].view(p.shape).cpu()
+            if og[k] is None:
+                assert float(gr.abs().max()) == 0.0, k
+                continue
+            assert relerr(gr, og[k]) < 2e-4, (k, relerr(gr, og[k]))
+
+
+def test_replay_gather_bit_exact():
+    torch.manual_seed(0)
+    st = dg.ReplayStore(50, (128, 160), 2, 2, "cuda", seed=1)
+    st.fill_synthetic(50, seed=9)
+    rng = np.random.RandomState(3)
+    for B in (1, 7, 64):
+        idx = torch.from_numpy(rng.randint(0, 50, size=B)).cuda()
+        idx[0] = 49                                        # next_obs wraps into the extra slot
+        out = {k: torch.full((B, w), -1.0, device="cuda") for k, w in
+               dict(obs=20480, next_obs=20480, pobs=2, next_pobs=2, act=2, rew=1, done=1).items()}
+        st.gather(idx, out)
+        store = {k: getattr(st, k).cpu().numpy() for k in ("obs", "pobs", "next_pobs", "act", "rew", "done")}
+        ref = O.replay_gather(store, idx.cpu().numpy(), st.cap)
+        for k in out:
+            assert np.array_equal(out[k].cpu().numpy().view(np.uint32), ref[k].view(np.uint32)), k
+
+
+def test_depth_augment_matches_golden_and_oracle():
+    g = golden("depth_aug.npz")
+    for i in range(2):
+        H, W, k = (int(x) for x in g[f"raw_{i}_params"])
+        yy, xx = np.mgrid[0:H, 0:W]
+        raw = (0.03 + 7.97 * (0.5 + 0.5 * np.sin(xx / 37.0 + k) * np.cos(yy / 53.0))).astype(np.float32)
+        raw[H // 3: H // 3 + 40, W // 4: W // 4 + 90] = 1.25
+        np.random.seed(int(g[f"noise_seed_{i}"]))
+        noise = np.random.normal(0, 50, raw.shape).astype(np.float32)
+        got = dg.depth_augment(torch.from_numpy(raw).cuda(), torch.from_numpy(noise).cuda())[0].cpu().numpy()
+        want = O.depth_augment(raw, noise.astype(np.float64), out_hw=(H // 4, W // 4))
+        assert np.abs(got - want).max() < 1e-5
+        # the golden frame used float64 noise; float32 rounding of N(0,50) moves pixels by < 1e-5*255
+        assert np.abs(got - g[f"state_{i}"]).max() < 1e-4
+
+
+def test_soft_and_hard_update():
+    cfg = O.Cfg(dim=32, depth=1, heads=2)
+    a = _mk("critic", cfg, reference_init("critic", cfg, 1))
+    b = _mk("critic", cfg, reference_init("critic", cfg, 2))
+    pa = {k: v.detach().cpu().clone() for k, v in a.named_parameters()}
+    pb = {k: v.detach().cpu().clone() for k, v in b.named_parameters()}
+    dg.soft_update(a, b, 5e-4)
+    O.soft_update(pa, pb, pa.keys(), 5e-4)
+    for k, p in a.named_parameters():
+        assert relerr(p, pa[k]) < 1e-6, k
+    dg.hard_update(a, b)
+    for (k, p), q in zip(a.named_parameters(), b.parameters()):
+        assert torch.equal(p, q), k
+
+
+def test_bf16_path_within_tolerance():
+    """bf16 contractions (tensor-core path): actions / Q within 1e-2 relative of the fp32 oracle."""
+    cfg = O.Cfg()
+    B = 8
+    pa, pc = reference_init("actor", cfg, 21), reference_init("critic", cfg, 22)
+    a, c = _mk("actor", cfg, pa, "bf16"), _mk("critic", cfg, pc, "bf16")
+    batch = synthetic_batch(cfg, B, 23)
+    nz = synthetic_noise(cfg, B, 24)
+    img, goal = batch["obs"], batch["pobs"]
+    with torch.no_grad():
+        oa, olp, omt = O.actor_sample(pa, img, goal, nz["eps_pi"], cfg, nz["mask_a"])
+        oq1, oq2 = O.critic_forward(pc, img, goal, oa, cfg, nz["mask_c"])
+        a.inject_noise(mask=nz["mask_a"], eps=nz["eps_pi"])
+        c.inject_noise(mask=nz["mask_c"])
+        act, lp, mt = a.sample([img.cuda(), goal.cuda()])
+        q1, q2 = c([img.cuda(), goal.cuda(), oa.cuda()])
+    assert relerr(act, oa) < BF16_TOL and relerr(mt, omt) < BF16_TOL
+    assert relerr(q1, oq1) < BF16_TOL and relerr(q2, oq2) < BF16_TOL

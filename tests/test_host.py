@@ -1,0 +1,107 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dgvit.h declares, the
+parameter layout mirrors the reference registration order, and the module surface
+(state_dict keys, seeded init, deepcopy, loud failure without CUDA) matches the reference."""
+import copy
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import dgvit_b200 as dg
+from dgvit_b200 import _lib as L
+from helpers import O, SEED, golden, reference_init, reference_sac_init
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dgvit.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(dgvit_\w+)\s*\(", hdr, flags=re.M))
+    assert declared, "no declarations parsed"
+    lib = C.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"libdgvit.so does not export {name}"
+    assert declared == set(L.SYMBOLS), (declared ^ set(L.SYMBOLS))
+    assert L.lib().dgvit_version() >= 100
+
+
+def test_errors_are_codes_not_exceptions():
+    cfg = L.Cfg(kind=L.ACTOR, img_h=128, img_w=160, patch_h=16, patch_w=20, dim=48, depth=4, heads=4,
+                dim_head=64, mlp_dim=2048, n_act=2, n_pstate=2)       # dim not a multiple of 32
+    out = L.Layout()
+    rc = L.lib().dgvit_param_layout(C.byref(cfg), C.byref(out))
+    assert rc == -1 and b"dim" in L.lib().dgvit_last_error()
+    with pytest.raises(RuntimeError):
+        L.check(rc, "param_layout")
+
+
+@pytest.mark.parametrize("block,head,lfs", [(4, 4, 64), (2, 2, 32), (6, 6, 128)])
+def test_layout_matches_registration_order(block, head, lfs):
+    for cls in (dg.GoTPolicy, dg.GoTQNetwork):
+        m = cls(2, 2, block, head, lfs)
+        offs = m._named_offsets()
+        names = [n for n, _ in m.named_parameters()]
+        assert [n for n, _ in offs] == names
+        lay = m.layout()
+        end = 0
+        for (n, off), p in zip(offs, m.parameters()):
+            assert off % 64 == 0 and off >= end, n      # aligned, increasing, non-overlapping
+            end = off + p.numel()
+        assert end <= lay.total
+        m.bind()
+        assert m._bound()
+        # views really alias the arena
+        p0 = next(m.parameters())
+        p0.data.fill_(3.0)
+        assert float(m._arena[offs[0][1]]) == 3.0
+
+
+def test_seeded_init_equals_reference():
+    g = golden("modules_shipped.npz")
+    torch.manual_seed(SEED)
+    a = dg.GoTPolicy(2, 2, 4, 4, 64)
+    torch.manual_seed(SEED + 1)
+    c = dg.GoTQNetwork(2, 2, 4, 4, 64)
+    cfg = O.Cfg()
+    ra, rc = reference_init("actor", cfg, SEED), reference_init("critic", cfg, SEED + 1)
+    for mod, ref, nm in ((a, ra, "actor"), (c, rc, "critic")):
+        sd = mod.state_dict()
+        assert list(sd.keys()) == list(ref.keys()) == [str(s) for s in g[f"{nm}_names"]]
+        for k in ref:
+            assert torch.equal(sd[k], ref[k]), k
+        s = np.array([float(v.double().sum()) for v in sd.values()])
+        np.testing.assert_allclose(s, g[f"{nm}_sum"], rtol=0, atol=1e-9)
+
+
+def test_state_dict_roundtrip_and_deepcopy(tmp_path):
+    torch.manual_seed(1)
+    a = dg.GoTPolicy(2, 2, 2, 2, 32)
+    a.bind()
+    f = tmp_path / "a.pth"
+    torch.save(a.state_dict(), f)
+    b = dg.GoTPolicy(2, 2, 2, 2, 32)
+    b.bind()
+    b.load_state_dict(torch.load(f))
+    assert b._bound()                      # load_state_dict copies in place: aliasing survives
+    for (k, x), (_, y) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(x, y), k
+    c = copy.deepcopy(a)
+    c.bind()
+    for x, y in zip(a.parameters(), c.parameters()):
+        assert torch.equal(x, y) and x.data_ptr() != y.data_ptr()
+    # torch.optim.Adam accepts the parameters (real leaf nn.Parameters)
+    torch.optim.Adam(a.parameters(), lr=1e-3)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    a = dg.GoTPolicy(2, 2, 2, 2, 32)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        a.sample([torch.zeros(1, 128, 160), torch.zeros(1, 2)])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, False, 0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dg.depth_augment(torch.zeros(8, 8))
