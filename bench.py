@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — DGViT actor-critic update throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA kernels via the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU PyTorch path
+                                                               # (oracle port, all host threads)
+
+A "step" is one full off-policy SAC update (vn/DRL.py:373-437): replay-index gather ->
+TD target -> critic fwd/bwd/Adam -> actor fwd + critic(s,pi) -> policy/alpha losses -> actor
+bwd/Adam -> alpha Adam -> Polyak, on one minibatch of 256 samples per GPU (BASELINE config[1];
+weak scaling: every rank runs 256 samples/step and gradients are all-reduced over NCCL).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "actor-critic update samples/sec"
+UNIT = "samples/s"
+PRESET = dict(block=4, head=4, l_f_size=64)      # vn/config.yaml:5,62-63
+HP = dict(LR_C=1e-3, LR_A=1e-3, LR_ALPHA=1e-4, TAU=5e-4, POLICY_FREQ=1, GAMMA=0.999, ALPHA=1.0)   # config.yaml:12-17,39-41
+SEED = 3407
+# algorithmic FLOPs of one update per sample: 4 F_a + 5 F_c
+F_A, F_C = 190_371_072, 190_371_328
+FLOP_PER_SAMPLE = 4 * F_A + 5 * F_C
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of SAC.learn on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_update_rate(budget_s: float, batch: int, max_steps: int, warmup: int = 1):
+    """Times oracle.SACOracle.learn (restatement of the reference's CPU PyTorch path, pinned
+    against the imported reference) with all host threads.  Returns (samples/s, cores, sample str, ms/step)."""
+    from oracle import dgvit_oracle as O
+    from oracle.init_params import reference_sac_init, synthetic_batch, synthetic_noise
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.Cfg(dim=PRESET["l_f_size"], depth=PRESET["block"], heads=PRESET["head"])
+    actor, critic = reference_sac_init(cfg, SEED)
+    orc = O.SACOracle(actor, critic, cfg, lr_a=HP["LR_A"], lr_c=HP["LR_C"], lr_alpha=HP["LR_ALPHA"], gamma=HP["GAMMA"],
+                      tau=HP["TAU"], alpha=HP["ALPHA"], policy_freq=HP["POLICY_FREQ"])
+    b = synthetic_batch(cfg, batch, SEED)
+    nz = synthetic_noise(cfg, batch, SEED + 1)
+    for _ in range(warmup):
+        orc.learn(b, nz)
+    t0 = time.perf_counter()
+    n = 0
+    while n < max_steps and (n == 0 or time.perf_counter() - t0 < budget_s):
+        orc.learn(b, nz)
+        n += 1
+    dt = time.perf_counter() - t0
+    return batch * n / dt, cores, f"{n} update step(s) of batch {batch} (+{warmup} warm-up), fp32, torch CPU {cores} threads", dt / n * 1e3
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    # bounded sample: shrink the per-step batch so (steps+warmup) steps end within a few minutes
+    t0 = time.perf_counter()
+    rate_probe, cores, _, ms = cpu_update_rate(0.0, 32, 1, warmup=1)
+    per_sample_s = 1.0 / rate_probe
+    batch = args.batch
+    while batch > 16 and per_sample_s * batch * (args.steps + args.warmup) > 200.0:
+        batch //= 2
+    rate, cores, sample, ms = cpu_update_rate(1e9, batch, args.steps, warmup=max(args.warmup, 1))
+    line = dict(impl="reference", metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=f"full SAC update (DGViT actor + Transformer critic, D=64 L=4 H=4), "
+                                     f"CPU oracle port of vn/DRL.py:373-437, batch {batch} per step"),
+                cpu_baseline=dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=rate, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import dgvit_b200 as dg
+    from dgvit_b200 import _lib as L
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    pk = peaks()
+
+    ag = dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, False, SEED, BUFFER_SIZE=args.replay,
+                precision=args.precision, device=dev, distributed=world > 1, **HP, **PRESET)
+    ag.replay_buffer.fill_synthetic(args.replay, seed=SEED + rank)
+    lib = L.lib()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        ag.learn_async(B)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.check(lib.dgvit_prof_begin(L.PROF_GEMM_MLP, args.steps * 160), "prof_begin")
+    n0 = lib.dgvit_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ag.learn_async(B)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    launches = lib.dgvit_launch_count() - n0
+    pms, pl, pfl, pby = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
+    L.check(lib.dgvit_prof_end(C.byref(pms), C.byref(pl), C.byref(pfl), C.byref(pby)), "prof_end")
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = B * world * args.steps / (ms / 1e3)
+    losses = ag._losses.tolist()
+
+    # ---------------- end to end: pinned HOST minibatches -> H2D -> update -> D2H losses
+    f = ag.replay_buffer.obs.shape[1]
+    nbuf = 2
+    shapes = dict(obs=(B, f), next_obs=(B, f), pobs=(B, 2), next_pobs=(B, 2), act=(B, 2), rew=(B, 1), done=(B, 1))
+    g = torch.Generator().manual_seed(SEED + 7 + rank)
+    host = [{k: torch.rand(*s, generator=g).pin_memory() for k, s in shapes.items()} for _ in range(4)]
+    devb = [{k: torch.empty(*s, device=dev) for k, s in shapes.items()} for _ in range(nbuf)]
+    h2d_bytes = sum(4 * s[0] * s[1] for s in shapes.values())
+    loss_host = torch.zeros(4).pin_memory()
+    copy_stream = torch.cuda.Stream(dev)
+    ready = [torch.cuda.Event() for _ in range(nbuf)]
+    freed = [torch.cuda.Event() for _ in range(nbuf)]
+    main = torch.cuda.current_stream(dev)
+
+    def e2e_steps(n):
+        for i in range(n):
+            j = i % nbuf
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[j])
+                for k in shapes:
+                    devb[j][k].copy_(host[i % len(host)][k], non_blocking=True)
+                ready[j].record(copy_stream)
+            main.wait_event(ready[j])
+            ls = ag.update_from_batch(devb[j])
+            freed[j].record(main)
+            loss_host.copy_(ls, non_blocking=True)         # D2H read of the step's result
+        torch.cuda.synchronize(dev)
+
+    for j in range(nbuf):
+        freed[j].record(main)
+    e2e_steps(max(args.warmup, 3))
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    t0.record()
+    e2e_steps(args.steps)
+    t1.record()
+    torch.cuda.synchronize(dev)
+    w1 = time.perf_counter()
+    e2e_ms = max(t0.elapsed_time(t1), (w1 - w0) * 1e3)     # host-inclusive: take the longer clock
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / (float(t.item()) / 1e3)
+    barrier()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (the MLP GEMM family), timed live above
+    ach = (pfl.value / 1e12) / (pms.value / 1e3) if pms.value > 0 else 0.0
+    roof = dict(bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s", frac=ach / pk["tf_sust"],
+                traffic=None, kernel="MLP GEMM family (fc1+GELU, fc2+residual, and their dX/dW)",
+                launches_timed=int(pl.value), kernel_ms_per_step=pms.value / args.steps,
+                share_of_step=(pms.value / ms) if ms > 0 else None, peak_source=pk["src"] + " (sustained bf16 cuBLAS)")
+    whole = dict(achieved_tflops=value * FLOP_PER_SAMPLE / 1e12, frac_of_peak=value * FLOP_PER_SAMPLE / 1e12 / pk["tf_sust"] / world)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cores, sample, _ = cpu_update_rate(12.0, B, 3, warmup=1)
+        cpu = dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample)
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
+                config=dict(workload="full off-policy actor-critic update step, batch 256 per GPU, DGViT actor + "
+                                     "Transformer critic (D=64, L=4, H=4, 65 tokens, MLP 2048), 1xB200 per rank",
+                            batch_per_gpu=B, global_batch=B * world, precision=args.precision,
+                            parallelism=f"dp{world}", replay_transitions=args.replay,
+                            l2="inputs gathered each step by random index from a %.2f GB device replay store (> 126 MB L2)"
+                               % (ag.replay_buffer.obs.numel() * 4 / 1e9)),
+                roofline=roof, whole_step=whole, cpu_baseline=cpu,
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=16),
+                gpu_launches=int(launches), clocks=clocks, losses=losses)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="minibatch per GPU")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--replay", type=int, default=30000, help="replay store transitions (vn/config.yaml:17)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,7 @@ MAX_DEPTH = 16
 ACTOR, CRITIC = 0, 1
 FP32, BF16 = 0, 1
 DROP_NONE, DROP_MASK, DROP_RNG = 0, 1, 2
+PROF_NONE, PROF_GEMM_MLP, PROF_GEMM_ALL, PROF_ATTENTION, PROF_GATHER, PROF_ADAM = range(6)
 
 c_f_p = C.c_void_p  # device pointers travel as integers
 
@@ -106,6 +107,9 @@ P = C.POINTER
 SYMBOLS = {
     "dgvit_version": (C.c_int, []),
     "dgvit_last_error": (C.c_char_p, []),
+    "dgvit_launch_count": (C.c_longlong, []),
+    "dgvit_prof_begin": (C.c_int, [C.c_int, C.c_int]),
+    "dgvit_prof_end": (C.c_int, [P(C.c_double), P(C.c_longlong), P(C.c_double), P(C.c_double)]),
     "dgvit_param_layout": (C.c_int, [P(Cfg), P(Layout)]),
     "dgvit_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
     "dgvit_sac_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, P(C.c_size_t)]),

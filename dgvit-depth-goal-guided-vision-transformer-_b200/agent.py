@@ -212,12 +212,14 @@ class SAC(object):
     # ------------------------------------------------------------------ the update
     def update_from_batch(self, batch: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None,
                           debug: Optional[torch.Tensor] = None, global_batch: Optional[int] = None,
-                          sample_offset: int = 0) -> torch.Tensor:
+                          sample_offset: Optional[int] = None) -> torch.Tensor:
         """One SAC update on device tensors (no host sync).  ``noise`` injects the stochastic
         inputs (parity tests): eps_next, eps_pi [B,na] and keep-masks mask_* [B,N,D] uint8.
         Returns the device tensor [qf1_loss, policy_loss, qf2_loss, alpha_loss]."""
         B = batch["obs"].shape[0]
         Bg = global_batch if global_batch is not None else B * self.world
+        if sample_offset is None:
+            sample_offset = self.rank * B
         ws = self._workspace(B)
         s = self._sac_struct(B, Bg, sample_offset)
         bt = L.Batch(**{k: batch[k].data_ptr() for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew")},

@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/dgvit.h"
 
@@ -39,7 +40,50 @@ inline void fail(int code, const char* fmt, ...) {
       ::dgvit::fail(DGVIT_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,                 \
                     cudaGetErrorString(e__));                                                  \
   } while (0)
-#define DG_LAUNCH_CHECK() DG_CUDA(cudaGetLastError())
+// every kernel launch of the library passes through here: error check + launch accounting
+// (bench.py reports the count as "gpu_launches")
+inline long long& launch_counter() {
+  static long long n = 0;
+  return n;
+}
+#define DG_LAUNCH_CHECK()          \
+  do {                             \
+    ++::dgvit::launch_counter();   \
+    DG_CUDA(cudaGetLastError());   \
+  } while (0)
+
+// optional per-kernel timing of the launches tagged as the dominant kernel (bench.py roofline):
+// events are recorded on the launching stream around each tagged launch.
+struct Prof {
+  bool on = false;
+  int tag = 0;               // which kernel family is being timed
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop)
+  size_t used = 0;
+  double flops = 0, bytes = 0;
+  long long launches = 0;
+};
+inline Prof& prof() {
+  static Prof p;
+  return p;
+}
+enum { PROF_NONE = 0, PROF_GEMM_MLP = 1, PROF_GEMM_ALL = 2, PROF_ATTENTION = 3, PROF_GATHER = 4, PROF_ADAM = 5 };
+struct ProfScope {
+  bool active = false;
+  cudaStream_t st;
+  ProfScope(int tag, double flops, double bytes, cudaStream_t s) : st(s) {
+    Prof& p = prof();
+    if (!p.on || p.tag != tag || p.used + 2 > p.ev.size()) return;
+    active = true;
+    p.flops += flops; p.bytes += bytes; p.launches++;
+    cudaEventRecord(p.ev[p.used], st);
+  }
+  ~ProfScope() {
+    if (!active) return;
+    Prof& p = prof();
+    cudaEventRecord(p.ev[p.used + 1], st);
+    p.used += 2;
+  }
+};
 #define DG_REQUIRE(cond, ...)                                  \
   do {                                                         \
     if (!(cond)) ::dgvit::fail(DGVIT_ERR_ARG, __VA_ARGS__);    \

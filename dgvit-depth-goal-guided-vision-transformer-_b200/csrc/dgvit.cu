@@ -98,8 +98,18 @@ template <> struct WSel<bf16> {
 };
 
 // ------------------------------------------------------------------ GEMM dispatch
+static thread_local int g_cur_tag = PROF_NONE;
+struct TagScope {
+  int prev;
+  explicit TagScope(int t) : prev(g_cur_tag) { g_cur_tag = t; }
+  ~TagScope() { g_cur_tag = prev; }
+};
+
 template <typename TA, typename TB, typename TC>
 static void gemm(const GemmArgs& g, cudaStream_t st) {
+  const double fl = 2.0 * g.M * g.N * g.K;
+  ProfScope ps(g_cur_tag, fl, 0.0, st);
+  ProfScope ps_all(PROF_GEMM_ALL, fl, 0.0, st);
 #ifdef DGVIT_WITH_TC
   if (gemm_tc_try<TA, TB, TC>(g, st)) return;
 #endif
@@ -332,6 +342,7 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
                             B_.Xa);
     // MLP block: x = ff(LN(x)) + x
     launch_ln_fwd<A>(B_.Xm, P + b.ln2_w, P + b.ln2_b, B_.Xn2, B_.mean2, B_.rstd2, d.T, d.D, st);
+    TagScope mlp_tag(PROF_GEMM_MLP);
     linear_fwd<A, A, A>(B_.Xn2, WSel<A>::w(net, b.fc1_w), B_.Hpre, d.T, d.M, d.D, EPI_BIAS_GELU2, P + b.fc1_b, st,
                         nullptr, B_.Hact);
     linear_fwd<A, A, float>(B_.Hact, WSel<A>::w(net, b.fc2_w), Xnext, d.T, d.D, d.M, EPI_BIAS_RESID, P + b.fc2_b, st,
@@ -364,10 +375,13 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     const dgvit_block_layout& b = L.block[l];
     LayerBuf<A>& B_ = c.L[l];
     // ---- MLP block.  c.dX = dL/dX_out (fp32 residual-stream gradient; dx_op() = operand copy)
+    {
+    TagScope mlp_tag(PROF_GEMM_MLP);
     linear_bwd_w<A, A>(c.dx_op(), B_.Hact, G + b.fc2_w, G + b.fc2_b, d.T, d.D, d.M, c.partial, st);
     linear_bwd_x<A, A, A>(c.dx_op(), WSel<A>::w(net, b.fc2_w), c.dH, d.T, d.D, d.M, EPI_GELU_BWD, B_.Hpre, d.M, st);
     linear_bwd_w<A, A>(c.dH, B_.Xn2, G + b.fc1_w, G + b.fc1_b, d.T, d.M, d.D, c.partial, st);
     linear_bwd_x<A, A, float>(c.dH, WSel<A>::w(net, b.fc1_w), c.dXn, d.T, d.M, d.D, EPI_NONE, nullptr, 0, st);
+    }
     launch_ln_bwd(c.dXn, B_.Xm, B_.mean2, B_.rstd2, P + b.ln2_w, c.dX, c.dXh, G + b.ln2_w, G + b.ln2_b, c.partial,
                   d.T, d.D, st);
     // ---- attention block.  c.dX = dL/dX_m
@@ -390,8 +404,11 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
 
 // zero the gradient ranges the reference leaves as None (so the arena is fully defined)
 static void zero_unused_grads(const dgvit_net& net, const dgvit_layout& L, cudaStream_t st) {
-  for (int k = 0; k < L.n_skip; ++k)
+  for (int k = 0; k < L.n_skip; ++k) {
+    // the alpha-gradient slot is written by the policy-loss kernel before the actor backward
+    if (net.cfg.kind == DGVIT_ACTOR && L.skip_begin[k] == L.alpha_grad_slot) continue;
     DG_CUDA(cudaMemsetAsync(net.grads + L.skip_begin[k], 0, (L.skip_end[k] - L.skip_begin[k]) * sizeof(float), st));
+  }
 }
 
 // ------------------------------------------------------------------ actor
@@ -772,6 +789,37 @@ using namespace dgvit;
 extern "C" {
 
 int dgvit_version(void) { return 100; }
+long long dgvit_launch_count(void) { return launch_counter(); }
+
+int dgvit_prof_begin(int tag, int max_launches) {
+  return guarded([&] {
+    Prof& p = prof();
+    DG_REQUIRE(max_launches > 0 && max_launches <= (1 << 20), "bad max_launches");
+    while (p.ev.size() < (size_t)2 * max_launches) {
+      cudaEvent_t e;
+      DG_CUDA(cudaEventCreate(&e));
+      p.ev.push_back(e);
+    }
+    p.used = 0; p.flops = 0; p.bytes = 0; p.launches = 0; p.tag = tag; p.on = true;
+  });
+}
+int dgvit_prof_end(double* ms_total, long long* launches, double* flops, double* bytes) {
+  return guarded([&] {
+    Prof& p = prof();
+    p.on = false;
+    double ms = 0;
+    for (size_t i = 0; i + 1 < p.used; i += 2) {
+      DG_CUDA(cudaEventSynchronize(p.ev[i + 1]));
+      float t = 0;
+      DG_CUDA(cudaEventElapsedTime(&t, p.ev[i], p.ev[i + 1]));
+      ms += t;
+    }
+    if (ms_total) *ms_total = ms;
+    if (launches) *launches = p.launches;
+    if (flops) *flops = p.flops;
+    if (bytes) *bytes = p.bytes;
+  });
+}
 const char* dgvit_last_error(void) { return last_error().c_str(); }
 
 int dgvit_param_layout(const dgvit_cfg* cfg, dgvit_layout* out) {

@@ -316,11 +316,10 @@ def _require_cuda(t: torch.Tensor):
 # --------------------------------------------------------------------------- actor
 class _ActorFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mod, img, pstate, eps, *params):
+    def forward(ctx, mod, need_grad, img, pstate, eps, *params):
         B = img.shape[0]
         dev = img.device
         na = mod._cfg.n_act
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         keep: List = []
         drop, inj_eps = mod._drop_struct(B, keep)
         if eps is None:
@@ -358,7 +357,7 @@ class _ActorFn(torch.autograd.Function):
         net = mod.net_struct()
         L.check(L.lib().dgvit_actor_backward(C.byref(net), C.byref(ctx.io), C.byref(g), B, mod._precision_code(),
                                              ctx.ws.data_ptr(), ctx.ws.numel(), _stream(dev)), "actor_backward")
-        return (None, None, None, None) + tuple(mod._grads_for_autograd(ctx.needs))
+        return (None, None, None, None, None) + tuple(mod._grads_for_autograd(ctx.needs))
 
 
 class GoTPolicy(_ArenaModule):
@@ -400,7 +399,9 @@ class GoTPolicy(_ArenaModule):
         _require_cuda(self._arena)
         img = self._check_img(istate)
         ps = pstate.to(img.device, torch.float32).contiguous()
-        return _ActorFn.apply(self, img, ps, eps, *self.parameters())
+        ps_ = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in ps_)
+        return _ActorFn.apply(self, need_grad, img, ps, eps, *ps_)
 
     def forward(self, inp):
         mean, log_std, _, _, _ = self._run(inp)
@@ -431,11 +432,10 @@ class GoTPolicy(_ArenaModule):
 # --------------------------------------------------------------------------- critic
 class _CriticFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mod, img, pstate, action, *params):
+    def forward(ctx, mod, need_grad, img, pstate, action, *params):
         B = img.shape[0]
         dev = img.device
         na = mod._cfg.n_act
-        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or action.requires_grad)
         keep: List = []
         drop, _ = mod._drop_struct(B, keep)
         q1 = torch.empty(B, na, device=dev)
@@ -469,7 +469,7 @@ class _CriticFn(torch.autograd.Function):
                                               L.ptr(d_act), int(pg), B, mod._precision_code(), ctx.ws.data_ptr(),
                                               ctx.ws.numel(), _stream(dev)), "critic_backward")
         grads = mod._grads_for_autograd(ctx.needs) if pg else [None] * len(ctx.needs)
-        return (None, None, None, d_act) + tuple(grads)
+        return (None, None, None, None, d_act) + tuple(grads)
 
 
 class GoTQNetwork(_ArenaModule):
@@ -514,4 +514,6 @@ class GoTQNetwork(_ArenaModule):
         img = self._check_img(istate)
         ps = pstate.to(img.device, torch.float32).contiguous()
         act = a.to(img.device, torch.float32)
-        return _CriticFn.apply(self, img, ps, act, *self.parameters())
+        ps_ = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in ps_) or act.requires_grad)
+        return _CriticFn.apply(self, need_grad, img, ps, act, *ps_)

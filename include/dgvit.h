@@ -182,6 +182,15 @@ typedef struct dgvit_sac_out {
 int dgvit_version(void);
 const char* dgvit_last_error(void);
 
+/* measurement hooks (bench.py): number of kernels this library has launched so far, and
+ * CUDA-event timing of the launches of one kernel family (DGVIT_PROF_*), recorded on the
+ * launching stream.  dgvit_prof_end synchronises on the recorded events. */
+enum { DGVIT_PROF_NONE = 0, DGVIT_PROF_GEMM_MLP = 1, DGVIT_PROF_GEMM_ALL = 2, DGVIT_PROF_ATTENTION = 3,
+       DGVIT_PROF_GATHER = 4, DGVIT_PROF_ADAM = 5 };
+long long dgvit_launch_count(void);
+int dgvit_prof_begin(int tag, int max_launches);
+int dgvit_prof_end(double* ms_total, long long* launches, double* flops, double* bytes);
+
 /* parameter arena layout for `cfg` (mirrors module.parameters() order) */
 int dgvit_param_layout(const dgvit_cfg* cfg, dgvit_layout* out);
 
