@@ -11,7 +11,7 @@ HDRS  := $(wildcard $(CSRC)/*.cuh) include/dgvit.h
 all: $(LIB)
 
 $(LIB): $(SRCS) $(HDRS)
-	$(NVCC) $(FLAGS) $(EXTRA) -shared -o $@ $(SRCS) -lcuda
+	$(NVCC) $(FLAGS) $(EXTRA) -DDGVIT_WITH_TC -shared -o $@ $(SRCS)
 
 clean:
 	rm -f $(LIB)

@@ -985,6 +985,29 @@ int dgvit_sac_update(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise
   return sac_run(s, b, nz, out, B, ws, ws_bytes, stream, 7);
 }
 
+int dgvit_gemm_bf16(int M, int N, int K, const void* A, int64_t a_sm, int64_t a_sk, const void* B, int64_t b_sk,
+                    int64_t b_sn, float* C, int64_t ldc, int splitk, float* partial, int use_tensor_cores,
+                    void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K;
+    g.A = A; g.a_sm = a_sm; g.a_sk = a_sk;
+    g.B = B; g.b_sk = b_sk; g.b_sn = b_sn;
+    g.C = C; g.ldc = ldc; g.splitk = splitk < 1 ? 1 : splitk; g.partial = partial;
+    if (use_tensor_cores) {
+#ifdef DGVIT_WITH_TC
+      if (!gemm_tc_try<bf16, bf16, float>(g, (cudaStream_t)stream))
+        fail(DGVIT_ERR_ARG, "gemm_bf16: shape/layout not eligible for the tensor-core kernel");
+#else
+      fail(DGVIT_ERR_ARG, "built without the tensor-core kernel");
+#endif
+    } else {
+      gemm_simt<bf16, bf16, float>(g, (cudaStream_t)stream);
+    }
+  });
+}
+
 int dgvit_adam_step(const dgvit_net* net, const dgvit_adam* opt, const dgvit_net* tgt, float tau, void* stream) {
   return guarded([&] {
     DG_REQUIRE(net && opt && net->params && net->grads, "null argument");

@@ -1,0 +1,503 @@
+// gemm_tc.cuh — bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled
+// shared memory -> tcgen05.mma (fp32 accumulators in TMEM) -> tcgen05.ld epilogue.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+// warps 2..9 = epilogue (two warps per TMEM lane quadrant, each owning half of the columns).
+// TMEM accumulators are double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// One kernel serves the three contractions of the hot path through the operand "major":
+//   y  = x W^T      A K-major,  B K-major      (forward linears)
+//   dx = dy W       A K-major,  B MN-major     (input gradients)
+//   dW = dy^T x     A MN-major, B MN-major     (weight gradients, split-K over tokens)
+#pragma once
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace dgvit {
+namespace tc {
+
+constexpr int BM = 128;   // UMMA M (cta_group::1)
+constexpr int BK = 64;    // 64 bf16 = one 128-byte swizzle span
+constexpr int UK = 16;    // UMMA K for 16-bit inputs
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread t gets row (lane base + t), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+      "[%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------ descriptors
+// shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::f16: D=f32, A=B=bf16
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ kernel
+struct TcArgs {
+  int M, N, K;          // problem (K = contraction)
+  int splitk;           // >1: partial[split][M][N] (or transposed) fp32
+  int trans_out;        // store C^T (element (m,n) at C[n*ldc + m])
+  int epi;
+  void* C; void* C2; int64_t ldc;
+  const float* bias; const float* resid; int64_t ldr;
+  const void* aux; int64_t ldaux;
+  float* partial;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 5 : 6);
+  static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = TILES_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+};
+
+template <typename TC>
+__device__ __forceinline__ void store_row32(TC* dst, const float (&v)[32], int nvalid);
+template <>
+__device__ __forceinline__ void store_row32<float>(float* dst, const float (&v)[32], int nvalid) {
+  if (nvalid == 32 && ((uintptr_t)dst & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    for (int i = 0; i < nvalid; ++i) dst[i] = v[i];
+  }
+}
+template <>
+__device__ __forceinline__ void store_row32<bf16>(bf16* dst, const float (&v)[32], int nvalid) {
+  if (nvalid == 32 && ((uintptr_t)dst & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+      __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+      u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+      reinterpret_cast<uint4*>(dst)[i] = u;
+    }
+  } else {
+    for (int i = 0; i < nvalid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, typename TC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
+  using SL = SmemLayout<BN>;
+  constexpr int STAGES = SL::STAGES;
+  constexpr int ACC_STAGES = 2;
+  constexpr uint32_t TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32 : (ACC_STAGES * BN <= 64) ? 64 : (ACC_STAGES * BN <= 128) ? 128
+                                 : (ACC_STAGES * BN <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-B alignment
+  uint64_t* full_bar = (uint64_t*)(smem + SL::TILES_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
+  const int kb_total = (g.K + BK - 1) / BK;
+  const int kb_per_split = (kb_total + g.splitk - 1) / g.splitk;
+  const int total_tiles = m_tiles * n_tiles * g.splitk;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NUM_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / (m_tiles * n_tiles);
+        const int rem = tile % (m_tiles * n_tiles);
+        const int mt = rem / n_tiles, nt = rem % n_tiles;
+        const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * SL::STAGE_BYTES;
+          uint8_t* sb = sa + SL::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, mt * BM);                 // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)                                           // boxes {64 m, 64 k}
+              tma_load_2d(sa + i * (64 * BK * 2), &tmA, &full_bar[stage], mt * BM + 64 * i, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, nt * BN);                 // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sb + i * (64 * BK * 2), &tmB, &full_bar[stage], nt * BN + 64 * i, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / (m_tiles * n_tiles);
+        const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * SL::STAGE_BYTES);
+          const uint32_t sb = sa + SL::A_BYTES;
+          // K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart; k-step = 32 B inside the span
+          // MN-major: k-rows of 128 B (64 MN elements), 64-wide MN blocks 8192 B apart; k-step = 16 rows
+          const uint64_t adesc = A_MN ? make_smem_desc(sa, 64 * BK * 2, 1024) : make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc(sb, 64 * BK * 2, 1024) : make_smem_desc(sb, 16, 1024);
+          constexpr uint32_t a_step = (A_MN ? UK * 128 : UK * 2) >> 4;
+          constexpr uint32_t b_step = (B_MN ? UK * 128 : UK * 2) >> 4;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            umma_bf16(tacc, adesc + (uint64_t)(k * a_step), bdesc + (uint64_t)(k * b_step), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);      // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);          // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (8 warps) =====================
+    const int ew = warp - 2;
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;                  // which half of the BN columns
+    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int CHUNKS = (COLS_PER_WARP + 31) / 32;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = tile / (m_tiles * n_tiles);
+      const int rem = tile % (m_tiles * n_tiles);
+      const int mt = rem / n_tiles, nt = rem % n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = mt * BM + quad * 32 + lane;
+      const bool row_ok = row < g.M;
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ++ch) {
+        const int c0 = half * COLS_PER_WARP + ch * 32;          // column inside the tile
+        if (c0 >= BN) break;
+        float v[32];
+        tmem_ld32(tmem_base + acc * BN + c0 + ((uint32_t)(quad * 32) << 16), v);
+        const int col = nt * BN + c0;
+        const int nvalid = min(32, g.N - col);
+        if (row_ok && nvalid > 0) {
+          if (g.splitk > 1 || g.trans_out) {
+            float* P = g.splitk > 1 ? g.partial + (int64_t)split * g.M * g.N : (float*)g.C;
+            if (g.trans_out) {
+              const int64_t ld = g.splitk > 1 ? g.M : g.ldc;
+              for (int i = 0; i < nvalid; ++i) P[(int64_t)(col + i) * ld + row] = v[i];
+            } else {
+              store_row32<float>(P + (int64_t)row * (g.splitk > 1 ? g.N : g.ldc) + col, v, nvalid);
+            }
+          } else {
+            TC* C = (TC*)g.C + (int64_t)row * g.ldc + col;
+            switch (g.epi) {
+              case EPI_NONE: break;
+              case EPI_BIAS:
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += __ldg(g.bias + col + i);
+                break;
+              case EPI_BIAS_RELU:
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] = fmaxf(v[i] + __ldg(g.bias + col + i), 0.f);
+                break;
+              case EPI_BIAS_GELU2: {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += __ldg(g.bias + col + i);
+                store_row32<TC>(C, v, nvalid);      // pre-activation (saved for backward)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+                C = (TC*)g.C2 + (int64_t)row * g.ldc + col;
+              } break;
+              case EPI_BIAS_RESID: {
+                const float* R = g.resid + (int64_t)row * g.ldr + col;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += (g.bias ? __ldg(g.bias + col + i) : 0.f) + R[i];
+              } break;
+              case EPI_GELU_BWD: {
+                const TC* X = (const TC*)g.aux + (int64_t)row * g.ldaux + col;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] *= gelu_grad_f(ldf(X + i));
+              } break;
+              case EPI_RELU_BWD: {
+                const float* X = (const float*)g.aux + (int64_t)row * g.ldaux + col;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] = X[i] > 0.f ? v[i] : 0.f;
+              } break;
+            }
+            store_row32<TC>(C, v, nvalid);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    DG_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled unavailable");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major matrix [outer, inner] with row pitch ld (elements); box {box_inner, box_outer}
+static CUtensorMap make_map(const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(DGVIT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%ld outer=%ld ld=%ld", (int)r,
+                              (long)inner, (long)outer, (long)ld);
+  return m;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    DG_CUDA(cudaGetDevice(&dev));
+    DG_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+template <int BN, bool A_MN, bool B_MN, typename TC>
+static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, cudaStream_t st) {
+  using SL = SmemLayout<BN>;
+  static bool attr = false;
+  if (!attr) {
+    DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL));
+    attr = true;
+  }
+  const int tiles = (int)(cdiv(a.M, BM) * cdiv(a.N, BN) * a.splitk);
+  const int grid = std::min(tiles, sm_count());
+  gemm_tc_kernel<BN, A_MN, B_MN, TC><<<grid, NUM_THREADS, SL::TOTAL, st>>>(ta, tb, a);
+  DG_LAUNCH_CHECK();
+}
+
+template <typename TC>
+static void dispatch(bool a_mn, bool b_mn, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a,
+                     cudaStream_t st) {
+#define DG_TC_CASE(BN_)                                                        \
+  if (bn == BN_) {                                                             \
+    if (!a_mn && !b_mn) return launch<BN_, false, false, TC>(ta, tb, a, st);   \
+    if (!a_mn && b_mn) return launch<BN_, false, true, TC>(ta, tb, a, st);     \
+    if (a_mn && b_mn) return launch<BN_, true, true, TC>(ta, tb, a, st);       \
+  }
+  DG_TC_CASE(64)
+  DG_TC_CASE(128)
+  DG_TC_CASE(256)
+#undef DG_TC_CASE
+  fail(DGVIT_ERR_ARG, "gemm_tc: unsupported operand layout (a_mn=%d b_mn=%d bn=%d)", (int)a_mn, (int)b_mn, bn);
+}
+
+static bool g_tc_enabled = true;
+
+}  // namespace tc
+
+// Returns false when the problem is not eligible (caller falls back to the CUDA-core kernel,
+// which only happens for the tiny head GEMMs and fp32 operands).
+template <typename TA, typename TB, typename TC>
+static bool gemm_tc_try(const GemmArgs& g0, cudaStream_t st) {
+  if constexpr (!(std::is_same<TA, bf16>::value && std::is_same<TB, bf16>::value)) {
+    return false;
+  } else {
+    using namespace tc;
+    if (!g_tc_enabled) return false;
+    GemmArgs g = g0;
+    int trans_out = 0;
+    // weight-gradient shapes with a narrow output (e.g. dW2 [64, 2048]): compute C^T so that the
+    // wide dimension rides on UMMA M = 128
+    if (g.M < 128 && g.N >= 128 && g.epi == EPI_NONE) {
+      std::swap(g.M, g.N);
+      const void* a = g.A; int64_t a_sm = g.a_sm, a_sk = g.a_sk;
+      g.A = g.B; g.a_sm = g.b_sn; g.a_sk = g.b_sk;
+      g.B = a; g.b_sk = a_sk; g.b_sn = a_sm;
+      trans_out = 1;
+    }
+    if (g.M < 128 || g.K < 16) return false;
+    const bool a_mn = (g.a_sm == 1 && g.a_sk != 1), b_mn = (g.b_sn == 1 && g.b_sk != 1);
+    const bool a_k = (g.a_sk == 1), b_k = (g.b_sk == 1);
+    if (!(a_mn || a_k) || !(b_mn || b_k)) return false;
+    if (a_mn && !b_mn) return false;                       // combination not used by the hot path
+    const int64_t lda = a_mn ? g.a_sk : g.a_sm, ldb = b_mn ? g.b_sk : g.b_sn;
+    if (lda % 8 || ldb % 8 || ((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15)) return false;   // TMA: 16-B strides
+    if (g.splitk > 1 && g.epi != EPI_NONE) return false;
+    if (trans_out && !std::is_same<TC, float>::value) return false;
+    int bn = g.N >= 256 ? 256 : (g.N >= 128 ? 128 : 64);
+    if (g.N % 8) return false;
+    // tensor maps: K-major operand = [rows, K] (inner K); MN-major operand = [K, MN] (inner MN)
+    CUtensorMap ta = a_mn ? make_map(g.A, g.M, g.K, lda, 64, BK) : make_map(g.A, g.K, g.M, lda, BK, BM);
+    CUtensorMap tb = b_mn ? make_map(g.B, g.N, g.K, ldb, 64, BK) : make_map(g.B, g.K, g.N, ldb, BK, bn);
+    TcArgs a;
+    a.M = g.M; a.N = g.N; a.K = g.K;
+    a.splitk = g.splitk; a.trans_out = trans_out; a.epi = g.epi;
+    a.C = g.C; a.C2 = g.C2; a.ldc = g.ldc; a.bias = g.bias; a.resid = g.resid; a.ldr = g.ldr;
+    a.aux = g.aux; a.ldaux = g.ldaux; a.partial = g.partial;
+    // split-K must not leave an empty split (its accumulator would be undefined)
+    const int kb_total = (int)cdiv(g.K, BK);
+    if (a.splitk > kb_total) a.splitk = kb_total;
+    {
+      const int per = (int)cdiv(kb_total, a.splitk);
+      a.splitk = (int)cdiv(kb_total, per);
+    }
+    if (g0.splitk > 1 && a.splitk == 1 && !trans_out) { /* direct store below */ }
+    dispatch<TC>(a_mn, b_mn, bn, ta, tb, a, st);
+    if (a.splitk > 1) {
+      const int64_t n = (int64_t)g0.M * g0.N;
+      DG_REQUIRE(g0.ldc == g0.N, "gemm_tc: split-K output must be dense");
+      reduce_partials_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(g.partial, (float*)g0.C, a.splitk, n);
+      DG_LAUNCH_CHECK();
+    }
+    return true;
+  }
+}
+
+}  // namespace dgvit

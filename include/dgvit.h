@@ -241,6 +241,14 @@ int dgvit_sac_update(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise
                      const dgvit_sac_out* out, int B, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* bf16 GEMM primitive behind every contraction of the bf16 path (nn.Linear forward / dX / dW,
+ * vn/GoalFormer.py:43,46,64,67,139): C[m,n] (fp32) = sum_k A(m,k) B(k,n) with element strides
+ * A(m,k)=A[m*a_sm+k*a_sk], B(k,n)=B[k*b_sk+n*b_sn].  use_tensor_cores=1 -> tcgen05/TMA kernel
+ * (fails if the shape is not eligible), 0 -> CUDA-core kernel (test cross-check). */
+int dgvit_gemm_bf16(int M, int N, int K, const void* A, int64_t a_sm, int64_t a_sk, const void* B,
+                    int64_t b_sk, int64_t b_sn, float* C, int64_t ldc, int splitk, float* partial,
+                    int use_tensor_cores, void* stream);
+
 /* torch.optim.Adam.step (+ optional fused Polyak target update, vn/utils.py:31-33, and bf16
  * shadow refresh) over a flat arena; skips layout.skip ranges */
 int dgvit_adam_step(const dgvit_net* net, const dgvit_adam* opt, const dgvit_net* polyak_target,
