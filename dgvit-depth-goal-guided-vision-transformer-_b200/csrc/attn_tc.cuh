@@ -1,0 +1,460 @@
+// attn_tc.cuh — fused multi-head attention for sm_100a (vn/GoalFormer.py:71-81), forward and
+// backward, one (sample, head) per work item: TMA-staged Q/K/V tiles (128B swizzle), tcgen05.mma
+// into TMEM, one thread per query row for the fp32 softmax (the 32x32b TMEM layout gives every
+// thread a whole score row, so no cross-lane reduction is needed), P / dS handed back to the
+// tensor core through shared memory.
+//
+//   forward : S = Q K^T ; P = softmax(S * dh^-0.5) ; O = P V
+//   backward: S, dP = dO V^T ; dS = P o (dP - rowsum(dO o O)) * scale ;
+//             dQ = dS K ; dK = dS^T Q ; dV = P^T dO
+//
+// The whole sequence (N <= 128 tokens, 65 in the shipped model) of one head fits a single
+// 128-row UMMA tile, so there is no online-softmax loop.  One smem image serves two operand
+// roles: a [rows][64] 128B-swizzled tile is K-major for (rows x 64) and MN-major for its
+// transpose, which is how K feeds both S (K-major) and dQ (MN-major), dS feeds dQ and dK, etc.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace dgvit {
+namespace attn {
+
+using namespace tc;
+
+constexpr int DH = 64;          // dim_head (reference default, vn/GoalFormer.py:124)
+constexpr int TILE = 16384;     // 128 rows x 128 B
+constexpr int FWD_STAGES = 2;
+constexpr int FWD_THREADS = 64 + 128;
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// byte offset of 16-byte chunk `chunk` (8 bf16) of row `r` inside a [128][64]-bf16 128B-swizzled tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int chunk) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  return u;
+}
+
+struct AttnArgs {
+  int B, N, H, KPAD;     // KPAD = N rounded up to 16 (keys / contraction rows actually multiplied)
+  float scale;
+  bf16* O;               // fwd: output [T, inner]
+  const bf16* Oin;       // bwd: forward output
+  const bf16* dO;        // bwd
+  bf16* dQKV;            // bwd: [T, 3*inner]
+};
+
+// =====================================================================================
+// forward
+// =====================================================================================
+// smem stage: Q [128x64] | K [128x64 (KPAD rows used)] | V | P block0 | P block1  = 5 tiles
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int STAGE_BYTES = 5 * TILE;
+  uint64_t* bars = (uint64_t*)(smem + FWD_STAGES * STAGE_BYTES);
+  uint64_t* qkv_full = bars;                    // [S] TMA landed
+  uint64_t* qkv_empty = qkv_full + FWD_STAGES;  // [S] O-MMA retired: smem stage reusable
+  uint64_t* s_full = qkv_empty + FWD_STAGES;    // [S] S in TMEM
+  uint64_t* p_ready = s_full + FWD_STAGES;      // [S] P written to smem (4 warps)
+  uint64_t* o_full = p_ready + FWD_STAGES;      // [S] O in TMEM
+  uint64_t* t_free = o_full + FWD_STAGES;       // [S] TMEM stage drained (4 warps)
+  uint32_t* tmem_slot = (uint32_t*)(t_free + FWD_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int inner = a.H * DH;
+  const int items = a.B * a.H;
+  constexpr uint32_t TCOLS_STAGE = 256;   // S: cols [0,128), O: cols [128,192)
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
+    for (int i = 0; i < FWD_STAGES; ++i) {
+      mbar_init(&qkv_full[i], 1); mbar_init(&qkv_empty[i], 1); mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); mbar_init(&t_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int b = it / a.H, h = it % a.H;
+        mbar_wait(&qkv_empty[st], ph ^ 1);
+        uint8_t* base = smem + st * STAGE_BYTES;
+        mbar_expect_tx(&qkv_full[st], TILE + 2 * a.KPAD * 128);
+        tma_load_2d(base, &tmQ, &qkv_full[st], h * DH, b * a.N);
+        tma_load_2d(base + TILE, &tmKV, &qkv_full[st], inner + h * DH, b * a.N);
+        tma_load_2d(base + 2 * TILE, &tmKV, &qkv_full[st], 2 * inner + h * DH, b * a.N);
+        if (++st == FWD_STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(128, a.KPAD, false, false);
+      const uint32_t idesc_o = make_idesc(128, DH, false, true);
+      const int ksteps = a.KPAD / 16;
+      int st = 0; uint32_t ph = 0;          // issue side (S)
+      int st2 = 0; uint32_t ph2 = 0;        // O side (one item behind)
+      int n_mine = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) ++n_mine;
+      for (int i = 0; i <= n_mine; ++i) {
+        if (i < n_mine) {
+          mbar_wait(&t_free[st], ph ^ 1);
+          mbar_wait(&qkv_full[st], ph);
+          tc_fence_after();
+          const uint32_t sq = smem_u32(smem + st * STAGE_BYTES), sk = sq + TILE;
+          const uint64_t qd = make_smem_desc(sq, 16, 1024), kd = make_smem_desc(sk, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_bf16(tmem_base + st * TCOLS_STAGE, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_s, k > 0);
+          umma_commit(&s_full[st]);
+          if (++st == FWD_STAGES) { st = 0; ph ^= 1; }
+        }
+        if (i >= 1) {
+          mbar_wait(&p_ready[st2], ph2);
+          tc_fence_after();
+          const uint32_t sv = smem_u32(smem + st2 * STAGE_BYTES) + 2 * TILE, sp = sv + TILE;
+          for (int k = 0; k < ksteps; ++k) {
+            // A = P (K-major, 64-key blocks one tile apart); B = V as MN-major (16 key rows per step)
+            const uint64_t pd = make_smem_desc(sp + (k >> 2) * TILE + (k & 3) * 32, 16, 1024);
+            const uint64_t vd = make_smem_desc(sv + k * 2048, 8192, 1024);
+            umma_bf16(tmem_base + st2 * TCOLS_STAGE + 128, pd, vd, idesc_o, k > 0);
+          }
+          umma_commit(&o_full[st2]);
+          umma_commit(&qkv_empty[st2]);
+          if (++st2 == FWD_STAGES) { st2 = 0; ph2 ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ---- softmax + output: thread = query row
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const float sl2 = a.scale * 1.44269504088896f;
+    int st = 0; uint32_t ph = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int b = it / a.H, h = it % a.H;
+      uint8_t* P = smem + st * STAGE_BYTES + 3 * TILE;
+      mbar_wait(&s_full[st], ph);
+      tc_fence_after();
+      const uint32_t ts = tmem_base + st * TCOLS_STAGE + lane_off;
+      float mx = -INFINITY;
+      for (int c = 0; c < a.KPAD; c += 16) {
+        float v[16];
+        tmem_ld16(ts + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (c + i < a.N) mx = fmaxf(mx, v[i]);
+      }
+      float sum = 0.f;
+      for (int c = 0; c < a.KPAD; c += 16) {
+        float v[16];
+        tmem_ld16(ts + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e = (c + i < a.N) ? exp2f((v[i] - mx) * sl2) : 0.f;
+          // the tensor core sees the bf16-rounded value: sum what it sees
+          v[i] = __bfloat162float(__float2bfloat16_rn(e));
+          sum += v[i];
+        }
+        uint8_t* blk = P + (c >> 6) * TILE;
+        const int ch = (c & 63) >> 3;
+        *reinterpret_cast<uint4*>(blk + sw128_off(r, ch)) = pack8(v);
+        *reinterpret_cast<uint4*>(blk + sw128_off(r, ch + 1)) = pack8(v + 8);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[st]);
+      mbar_wait(&o_full[st], ph);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      {
+        // tcgen05.ld is warp-aligned: every lane loads, only rows inside the sequence store
+        bf16* dst = a.O + ((int64_t)b * a.N + r) * inner + h * DH;
+#pragma unroll
+        for (int c = 0; c < DH; c += 16) {
+          float v[16];
+          tmem_ld16(ts + 128 + c, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= inv;
+          if (r < a.N) {
+            reinterpret_cast<uint4*>(dst + c)[0] = pack8(v);
+            reinterpret_cast<uint4*>(dst + c)[1] = pack8(v + 8);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_free[st]);
+      if (++st == FWD_STAGES) { st = 0; ph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// =====================================================================================
+// backward
+// =====================================================================================
+// smem: 2 load stages x (Q | K | V | dO) + P block0,1 + dS block0,1
+constexpr int BWD_LOAD_STAGES = 2;
+constexpr int BWD_THREADS = 64 + 128;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   const __grid_constant__ CUtensorMap tmdO, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int LOAD_BYTES = 4 * TILE;
+  uint8_t* Pt = smem + BWD_LOAD_STAGES * LOAD_BYTES;   // 2 tiles
+  uint8_t* dSt = Pt + 2 * TILE;                        // 2 tiles
+  uint64_t* bars = (uint64_t*)(dSt + 2 * TILE);
+  uint64_t* ld_full = bars;                       // [2]
+  uint64_t* ld_empty = ld_full + BWD_LOAD_STAGES; // [2]
+  uint64_t* sdp_full = ld_empty + BWD_LOAD_STAGES;   // S and dP in TMEM
+  uint64_t* pds_ready = sdp_full + 1;                // P, dS in smem (4 warps)
+  uint64_t* out_full = pds_ready + 1;                // dQ, dK, dV in TMEM
+  uint64_t* t_free = out_full + 1;                   // TMEM drained (4 warps)
+  uint32_t* tmem_slot = (uint32_t*)(t_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int inner = a.H * DH;
+  const int items = a.B * a.H;
+  // TMEM columns: S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448)
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmdO);
+    for (int i = 0; i < BWD_LOAD_STAGES; ++i) { mbar_init(&ld_full[i], 1); mbar_init(&ld_empty[i], 1); }
+    mbar_init(sdp_full, 1); mbar_init(pds_ready, 4); mbar_init(out_full, 1); mbar_init(t_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int b = it / a.H, h = it % a.H;
+        mbar_wait(&ld_empty[st], ph ^ 1);
+        uint8_t* base = smem + st * LOAD_BYTES;
+        mbar_expect_tx(&ld_full[st], 2 * TILE + 2 * a.KPAD * 128);
+        tma_load_2d(base, &tmQ, &ld_full[st], h * DH, b * a.N);
+        tma_load_2d(base + TILE, &tmKV, &ld_full[st], inner + h * DH, b * a.N);
+        tma_load_2d(base + 2 * TILE, &tmKV, &ld_full[st], 2 * inner + h * DH, b * a.N);
+        tma_load_2d(base + 3 * TILE, &tmdO, &ld_full[st], h * DH, b * a.N);
+        if (++st == BWD_LOAD_STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(128, a.KPAD, false, false);    // S, dP
+      const uint32_t idesc_q = make_idesc(128, DH, false, true);         // dQ = dS K      (A K-major, B MN-major)
+      const uint32_t idesc_t = make_idesc(128, DH, true, true);          // dK, dV         (A MN-major, B MN-major)
+      const int ksteps = a.KPAD / 16;
+      int st = 0; uint32_t ph = 0; uint32_t iph = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        mbar_wait(t_free, iph ^ 1);
+        mbar_wait(&ld_full[st], ph);
+        tc_fence_after();
+        const uint32_t sq = smem_u32(smem + st * LOAD_BYTES), sk = sq + TILE, sv = sk + TILE, sdo = sv + TILE;
+        const uint32_t sp = smem_u32(Pt), sds = smem_u32(dSt);
+        {
+          const uint64_t qd = make_smem_desc(sq, 16, 1024), kd = make_smem_desc(sk, 16, 1024);
+          const uint64_t dod = make_smem_desc(sdo, 16, 1024), vd = make_smem_desc(sv, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_s, k > 0);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base + 128, dod + (uint64_t)(k * 2), vd + (uint64_t)(k * 2), idesc_s, k > 0);
+        }
+        umma_commit(sdp_full);
+        mbar_wait(pds_ready, iph);
+        tc_fence_after();
+        for (int k = 0; k < ksteps; ++k) {
+          // dQ[128 x 64] += dS[:, 16k:16k+16] K[16k:16k+16, :]
+          const uint64_t ad = make_smem_desc(sds + (k >> 2) * TILE + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(sk + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base + 256, ad, bd, idesc_q, k > 0);
+        }
+        for (int k = 0; k < ksteps; ++k) {
+          // dK[keys x 64] += dS^T[:, 16k rows of queries] Q[16k.., :]   (A = dS tile read MN-major)
+          const uint64_t ad = make_smem_desc(sds + k * 2048, TILE, 1024);
+          const uint64_t bd = make_smem_desc(sq + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base + 320, ad, bd, idesc_t, k > 0);
+        }
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = make_smem_desc(sp + k * 2048, TILE, 1024);
+          const uint64_t bd = make_smem_desc(sdo + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base + 384, ad, bd, idesc_t, k > 0);
+        }
+        umma_commit(out_full);
+        umma_commit(&ld_empty[st]);
+        iph ^= 1;
+        if (++st == BWD_LOAD_STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const float sl2 = a.scale * 1.44269504088896f;
+    uint32_t iph = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int b = it / a.H, h = it % a.H;
+      const bool valid = r < a.N;
+      // delta = rowsum(dO o O) straight from global (bf16, 128 B per row each)
+      float delta = 0.f;
+      if (valid) {
+        const uint4* po = reinterpret_cast<const uint4*>(a.Oin + ((int64_t)b * a.N + r) * inner + h * DH);
+        const uint4* pd = reinterpret_cast<const uint4*>(a.dO + ((int64_t)b * a.N + r) * inner + h * DH);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 x = po[i], y = pd[i];
+          const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            delta = fmaf(__uint_as_float(xs[j] << 16), __uint_as_float(ys[j] << 16), delta);
+            delta = fmaf(__uint_as_float(xs[j] & 0xffff0000u), __uint_as_float(ys[j] & 0xffff0000u), delta);
+          }
+        }
+      }
+      mbar_wait(sdp_full, iph);
+      tc_fence_after();
+      const uint32_t ts = tmem_base + lane_off;
+      float mx = -INFINITY;
+      for (int c = 0; c < a.KPAD; c += 16) {
+        float v[16];
+        tmem_ld16(ts + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (c + i < a.N) mx = fmaxf(mx, v[i]);
+      }
+      float sum = 0.f;
+      for (int c = 0; c < a.KPAD; c += 16) {
+        float v[16];
+        tmem_ld16(ts + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (c + i < a.N) sum += exp2f((v[i] - mx) * sl2);
+      }
+      const float inv = 1.0f / sum;
+      for (int c = 0; c < a.KPAD; c += 16) {
+        float s[16], dp[16], p[16], ds[16];
+        tmem_ld16(ts + c, s);
+        tmem_ld16(ts + 128 + c, dp);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const bool ok = valid && (c + i < a.N);
+          p[i] = ok ? exp2f((s[i] - mx) * sl2) * inv : 0.f;
+          ds[i] = ok ? p[i] * (dp[i] - delta) * a.scale : 0.f;
+        }
+        const int ch = (c & 63) >> 3;
+        uint8_t* pb = Pt + (c >> 6) * TILE;
+        uint8_t* db = dSt + (c >> 6) * TILE;
+        *reinterpret_cast<uint4*>(pb + sw128_off(r, ch)) = pack8(p);
+        *reinterpret_cast<uint4*>(pb + sw128_off(r, ch + 1)) = pack8(p + 8);
+        *reinterpret_cast<uint4*>(db + sw128_off(r, ch)) = pack8(ds);
+        *reinterpret_cast<uint4*>(db + sw128_off(r, ch + 1)) = pack8(ds + 8);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_ready);
+      mbar_wait(out_full, iph);
+      tc_fence_after();
+      bf16* dst = a.dQKV + ((int64_t)b * a.N + r) * (3 * inner) + h * DH;
+#pragma unroll 1
+      for (int w = 0; w < 3; ++w) {          // dQ, dK, dV rows (query r / key r)
+#pragma unroll
+        for (int c = 0; c < DH; c += 16) {
+          float v[16];
+          tmem_ld16(ts + 256 + w * 64 + c, v);
+          if (valid) {
+            reinterpret_cast<uint4*>(dst + w * inner + c)[0] = pack8(v);
+            reinterpret_cast<uint4*>(dst + w * inner + c)[1] = pack8(v + 8);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_free);
+      iph ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------ host
+static bool eligible(int N, int dh, const void* p0, int64_t ld) {
+  return tc::g_tc_enabled && dh == DH && N <= 128 && (ld % 8) == 0 && (((uintptr_t)p0) & 15) == 0;
+}
+
+static void fwd(const bf16* QKV, bf16* O, int B, int N, int H, cudaStream_t st) {
+  const int inner = H * DH;
+  const int64_t T = (int64_t)B * N;
+  AttnArgs a;
+  a.B = B; a.N = N; a.H = H; a.KPAD = (N + 15) / 16 * 16;
+  a.scale = 1.0f / sqrtf((float)DH);
+  a.O = O; a.Oin = nullptr; a.dO = nullptr; a.dQKV = nullptr;
+  CUtensorMap tq = make_map(QKV, 3 * inner, T, 3 * inner, 64, 128);
+  CUtensorMap tkv = make_map(QKV, 3 * inner, T, 3 * inner, 64, a.KPAD);
+  const int smem = FWD_STAGES * 5 * TILE + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    DG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int grid = std::min(B * H, sm_count());
+  attn_fwd_tc_kernel<<<grid, FWD_THREADS, smem, st>>>(tq, tkv, a);
+  DG_LAUNCH_CHECK();
+}
+
+static void bwd(const bf16* QKV, const bf16* O, const bf16* dO, bf16* dQKV, int B, int N, int H, cudaStream_t st) {
+  const int inner = H * DH;
+  const int64_t T = (int64_t)B * N;
+  AttnArgs a;
+  a.B = B; a.N = N; a.H = H; a.KPAD = (N + 15) / 16 * 16;
+  a.scale = 1.0f / sqrtf((float)DH);
+  a.O = nullptr; a.Oin = O; a.dO = dO; a.dQKV = dQKV;
+  CUtensorMap tq = make_map(QKV, 3 * inner, T, 3 * inner, 64, 128);
+  CUtensorMap tkv = make_map(QKV, 3 * inner, T, 3 * inner, 64, a.KPAD);
+  CUtensorMap tdo = make_map(dO, inner, T, inner, 64, 128);
+  const int smem = (BWD_LOAD_STAGES * 4 + 4) * TILE + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    DG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int grid = std::min(B * H, sm_count());
+  attn_bwd_tc_kernel<<<grid, BWD_THREADS, smem, st>>>(tq, tkv, tdo, a);
+  DG_LAUNCH_CHECK();
+}
+
+}  // namespace attn
+}  // namespace dgvit

@@ -152,6 +152,22 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
+// Branch-free GELU for the bf16 tensor-core epilogues (Abramowitz-Stegun 7.1.26 erf, |err| <= 1.5e-7,
+// two MUFU ops: rcp + ex2).  exp(-x^2/2) is shared between erf and the Gaussian pdf of the derivative.
+__device__ __forceinline__ void gelu_fast(float x, float& y, float& dy) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.23164189f, ax, 1.0f));        // p/sqrt(2) = 0.3275911/1.41421356
+  const float e = exp2f(-0.72134752f * x * x);                          // exp(-x^2/2)
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float erfa = fmaf(-poly * t, e, 1.0f);                          // erf(|x|/sqrt2)
+  const float cdf = fmaf(0.5f, copysignf(erfa, x), 0.5f);
+  y = x * cdf;
+  dy = fmaf(x * 0.39894228f, e, cdf);
+}
+
 // ---------------------------------------------------------------- counter-based RNG
 // Philox4x32-10; key = seed, counter = (index, stream_id, update counter).
 struct Philox {

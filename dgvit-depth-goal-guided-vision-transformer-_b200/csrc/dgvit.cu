@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #ifdef DGVIT_WITH_TC
 #include "gemm_tc.cuh"
+#include "attn_tc.cuh"
 #endif
 
 namespace dgvit {
@@ -154,7 +155,7 @@ static void linear_bwd_w(const TA* dy, const TB* x, float* dW, float* db, int64_
   g.splitk = pick_splitk(R); g.partial = partial;
   gemm<TA, TB, float>(g, st);
   if (db) {
-    const int S = pick_splitk(R);
+    const int S = (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 512);   // many short row ranges: HBM-bound read
     const int64_t rpb = cdiv(R, S);
     dim3 grid((unsigned)cdiv(N, 128), (unsigned)S);
     colsum_partial_kernel<TA><<<grid, 128, 0, st>>>(dy, ldy, partial, R, N, rpb);
@@ -272,7 +273,7 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
                           const float* gamma, float* dX_io, bf16* dX_lp, float* dgamma, float* dbeta,
                           float* partial, int64_t T, int D, cudaStream_t st) {
   const int wpb = 8;
-  int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 4);
+  int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148);
   const size_t smem = (size_t)wpb * 2 * D * sizeof(float);
   switch (D / 32) {
 #define LNB(V) case V: layernorm_bwd_kernel<V><<<nblocks, wpb * 32, smem, st>>>(dY, X, mean, rstd, gamma, dX_io, dX_lp, partial, T); break;
@@ -287,6 +288,12 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
 
 template <typename A>
 static void launch_attention_fwd(const A* QKV, A* O, const Dims& d, cudaStream_t st) {
+  ProfScope ps(PROF_ATTENTION, 4.0 * d.B * d.H * (double)d.N * d.N * d.dh, 0.0, st);
+#ifdef DGVIT_WITH_TC
+  if constexpr (std::is_same<A, bf16>::value) {
+    if (attn::eligible(d.N, d.dh, QKV, 3 * d.inner)) return attn::fwd(QKV, O, d.B, d.N, d.H, st);
+  }
+#endif
   const int threads = 256, nw = threads / 32;
   const size_t smem = ((size_t)d.N * (d.dh + 1) + (size_t)d.N * d.dh + (size_t)nw * d.N + (size_t)nw * d.dh) * sizeof(float);
   DG_REQUIRE(smem <= 227 * 1024, "attention_fwd: N=%d dh=%d needs %zu B smem", d.N, d.dh, smem);
@@ -300,6 +307,12 @@ static void launch_attention_fwd(const A* QKV, A* O, const Dims& d, cudaStream_t
 }
 template <typename A>
 static void launch_attention_bwd(const A* QKV, const A* O, const A* dO, A* dQKV, const Dims& d, cudaStream_t st) {
+  ProfScope ps(PROF_ATTENTION, 10.0 * d.B * d.H * (double)d.N * d.N * d.dh, 0.0, st);
+#ifdef DGVIT_WITH_TC
+  if constexpr (std::is_same<A, bf16>::value) {
+    if (attn::eligible(d.N, d.dh, QKV, 3 * d.inner)) return attn::bwd(QKV, O, dO, dQKV, d.B, d.N, d.H, st);
+  }
+#endif
   const int threads = 256, nw = threads / 32;
   const size_t smem = ((size_t)4 * d.N * (d.dh + 1) + 2 * (size_t)d.N + 2 * (size_t)nw * d.N) * sizeof(float);
   DG_REQUIRE(smem <= 227 * 1024, "attention_bwd: N=%d dh=%d needs %zu B smem (unsupported in this build)", d.N, d.dh, smem);
@@ -397,8 +410,14 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
   const int64_t tot = d.T * d.D;
   embed_bwd_kernel<A><<<grid1d(tot), 256, 0, st>>>(c.dX, c.tok, c.dXp, c.dtok, drop, tot, d.N, d.D, relu_tok);
   DG_LAUNCH_CHECK();
-  dpos_kernel<<<d.N, 128, 0, st>>>(c.dX, G + L.pos, drop, d.B, d.N, d.D);
-  DG_LAUNCH_CHECK();
+  {
+    const int S = std::max(1, std::min(32, d.B / 8));
+    dpos_kernel<<<dim3(d.N, S), 128, 0, st>>>(c.dX, c.partial, drop, d.B, d.N, d.D);
+    DG_LAUNCH_CHECK();
+    const int64_t n = (int64_t)d.N * d.D;
+    reduce_partials_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(c.partial, G + L.pos, S, n);
+    DG_LAUNCH_CHECK();
+  }
   linear_bwd_w<A, A>(c.dXp, c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st);
 }
 
@@ -1005,6 +1024,42 @@ int dgvit_gemm_bf16(int M, int N, int K, const void* A, int64_t a_sm, int64_t a_
     } else {
       gemm_simt<bf16, bf16, float>(g, (cudaStream_t)stream);
     }
+  });
+}
+
+int dgvit_attention_bf16(const void* qkv, void* o, const void* d_o, void* d_qkv, int B, int N, int H, int dim_head,
+                         int use_tensor_cores, void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(qkv && o && B >= 1 && N >= 1 && H >= 1, "bad argument");
+    dgvit_cfg c;
+    memset(&c, 0, sizeof(c));
+    c.img_h = 16; c.img_w = 20 * (N - 1); c.patch_h = 16; c.patch_w = 20; c.heads = H; c.dim_head = dim_head;
+    c.dim = 64; c.depth = 1; c.mlp_dim = 64; c.n_act = 2; c.n_pstate = 2;
+    Dims d(c, B);
+    DG_REQUIRE(d.N == N, "internal: N");
+    cudaStream_t st = (cudaStream_t)stream;
+#ifdef DGVIT_WITH_TC
+    const bool prev = tc::g_tc_enabled;
+    tc::g_tc_enabled = use_tensor_cores != 0;
+    if (use_tensor_cores) DG_REQUIRE(attn::eligible(N, dim_head, qkv, 3 * d.inner), "attention: shape not eligible for the tensor-core kernel");
+#else
+    DG_REQUIRE(!use_tensor_cores, "built without the tensor-core kernels");
+#endif
+    try {
+      if (!d_o) launch_attention_fwd<bf16>((const bf16*)qkv, (bf16*)o, d, st);
+      else {
+        DG_REQUIRE(d_qkv, "null d_qkv");
+        launch_attention_bwd<bf16>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, (bf16*)d_qkv, d, st);
+      }
+    } catch (...) {
+#ifdef DGVIT_WITH_TC
+      tc::g_tc_enabled = prev;
+#endif
+      throw;
+    }
+#ifdef DGVIT_WITH_TC
+    tc::g_tc_enabled = prev;
+#endif
   });
 }
 

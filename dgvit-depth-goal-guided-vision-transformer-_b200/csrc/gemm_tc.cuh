@@ -24,8 +24,13 @@ namespace tc {
 constexpr int BM = 128;   // UMMA M (cta_group::1)
 constexpr int BK = 64;    // 64 bf16 = one 128-byte swizzle span
 constexpr int UK = 16;    // UMMA K for 16-bit inputs
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+// epilogue warps: 4 TMEM lane quadrants x (BN/32 column groups, at most 4)
+template <int BN> struct EpiCfg {
+  static constexpr int COL_GROUPS = (BN >= 128) ? 4 : 2;
+  static constexpr int WARPS = 4 * COL_GROUPS;
+  static constexpr int THREADS = 64 + WARPS * 32;
+  static constexpr int COLS_PER_WARP = BN / COL_GROUPS;
+};
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -179,8 +184,34 @@ __device__ __forceinline__ void store_row32<bf16>(bf16* dst, const float (&v)[32
   }
 }
 
+template <typename TC>
+__device__ __forceinline__ void load_row32(const TC* src, float (&v)[32], int nvalid);
+template <>
+__device__ __forceinline__ void load_row32<float>(const float* src, float (&v)[32], int nvalid) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = i < nvalid ? src[i] : 0.f;
+}
+template <>
+__device__ __forceinline__ void load_row32<bf16>(const bf16* src, float (&v)[32], int nvalid) {
+  if (nvalid == 32 && ((uintptr_t)src & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = reinterpret_cast<const uint4*>(src)[i];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
+        v[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = i < nvalid ? __bfloat162float(src[i]) : 0.f;
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, typename TC>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(EpiCfg<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
   using SL = SmemLayout<BN>;
   constexpr int STAGES = SL::STAGES;
@@ -205,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NUM_EPI_WARPS); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EpiCfg<BN>::WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -281,11 +312,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (8 warps) =====================
+    // ===================== epilogue =====================
     const int ew = warp - 2;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                  // which half of the BN columns
-    constexpr int COLS_PER_WARP = BN / 2;
+    const int half = ew >> 2;                  // which column group of the tile
+    constexpr int COLS_PER_WARP = EpiCfg<BN>::COLS_PER_WARP;
     constexpr int CHUNKS = (COLS_PER_WARP + 31) / 32;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -330,7 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += __ldg(g.bias + col + i);
                 store_row32<TC>(C, v, nvalid);      // pre-activation (saved for backward)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+                for (int i = 0; i < 32; ++i) { float dy; gelu_fast(v[i], v[i], dy); }
                 C = (TC*)g.C2 + (int64_t)row * g.ldc + col;
               } break;
               case EPI_BIAS_RESID: {
@@ -340,8 +371,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               } break;
               case EPI_GELU_BWD: {
                 const TC* X = (const TC*)g.aux + (int64_t)row * g.ldaux + col;
+                float xin[32];
+                load_row32<TC>(X, xin, nvalid);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] *= gelu_grad_f(ldf(X + i));
+                for (int i = 0; i < 32; ++i) { float y, dy; gelu_fast(xin[i], y, dy); v[i] *= dy; }
               } break;
               case EPI_RELU_BWD: {
                 const float* X = (const float*)g.aux + (int64_t)row * g.ldaux + col;
@@ -418,7 +451,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a
   }
   const int tiles = (int)(cdiv(a.M, BM) * cdiv(a.N, BN) * a.splitk);
   const int grid = std::min(tiles, sm_count());
-  gemm_tc_kernel<BN, A_MN, B_MN, TC><<<grid, NUM_THREADS, SL::TOTAL, st>>>(ta, tb, a);
+  gemm_tc_kernel<BN, A_MN, B_MN, TC><<<grid, EpiCfg<BN>::THREADS, SL::TOTAL, st>>>(ta, tb, a);
   DG_LAUNCH_CHECK();
 }
 

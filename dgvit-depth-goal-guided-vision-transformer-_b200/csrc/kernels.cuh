@@ -76,17 +76,20 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dX0, const float* __r
   }
 }
 
-// dpos[n,d] = sum_b dX0[b,n,d]*keep   — one block per token position, fixed order over b
-__global__ void dpos_kernel(const float* __restrict__ dX0, float* __restrict__ dpos, DropDev drop, int B,
+// dpos partials: part[s][n,d] = sum over the s-th batch chunk of dX0[b,n,d]*keep (fixed order);
+// grid (N, S); a reduce_partials pass finishes the sum deterministically.
+__global__ void dpos_kernel(const float* __restrict__ dX0, float* __restrict__ part, DropDev drop, int B,
                             int N, int D) {
-  const int n = blockIdx.x;
+  const int n = blockIdx.x, s = blockIdx.y, S = gridDim.y;
+  const int per = (B + S - 1) / S;
+  const int b0 = s * per, b1 = min(B, b0 + per);
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) {
+    float acc = 0.f;
+    for (int b = b0; b < b1; ++b) {
       const int64_t i = ((int64_t)b * N + n) * D + d;
-      s += dX0[i] * drop_factor(drop, i);
+      acc += dX0[i] * drop_factor(drop, i);
     }
-    dpos[n * D + d] = s;
+    part[((int64_t)s * N + n) * D + d] = acc;
   }
 }
 

@@ -249,6 +249,12 @@ int dgvit_gemm_bf16(int M, int N, int K, const void* A, int64_t a_sm, int64_t a_
                     int64_t b_sk, int64_t b_sn, float* C, int64_t ldc, int splitk, float* partial,
                     int use_tensor_cores, void* stream);
 
+/* Attention.forward core (vn/GoalFormer.py:75-81) on bf16 QKV [B*N, 3*H*dim_head] (column =
+ * which*inner + h*dim_head + d): forward when d_o == NULL (writes o [B*N, inner]), else backward
+ * (reads o, d_o; writes d_qkv).  use_tensor_cores=1 -> tcgen05/TMEM kernel, 0 -> CUDA-core kernel. */
+int dgvit_attention_bf16(const void* qkv, void* o, const void* d_o, void* d_qkv, int B, int N, int H,
+                         int dim_head, int use_tensor_cores, void* stream);
+
 /* torch.optim.Adam.step (+ optional fused Polyak target update, vn/utils.py:31-33, and bf16
  * shadow refresh) over a flat arena; skips layout.skip ranges */
 int dgvit_adam_step(const dgvit_net* net, const dgvit_adam* opt, const dgvit_net* polyak_target,
