@@ -147,10 +147,12 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 5 : 6);
+  static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 128 ? 5 : 6);
   static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = TILES_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+  // per-epilogue-warp staging tiles for coalesced bf16 stores
+  static constexpr int STAGING_BYTES = EpiCfg<BN>::WARPS * 32 * (EpiCfg<BN>::COLS_PER_WARP * 2 + 16);
+  static constexpr int TOTAL = TILES_BYTES + BAR_BYTES + STAGING_BYTES + 1024;  // +1024 for manual alignment
 };
 
 template <typename TC>
@@ -182,6 +184,15 @@ __device__ __forceinline__ void store_row32<bf16>(bf16* dst, const float (&v)[32
   } else {
     for (int i = 0; i < nvalid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
   }
+}
+
+__device__ __forceinline__ uint4 attn_pack8(const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  return u;
 }
 
 template <typename TC>
@@ -315,9 +326,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue =====================
     const int ew = warp - 2;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                  // which column group of the tile
+    const int grp = ew >> 2;                   // which column group of the tile
     constexpr int COLS_PER_WARP = EpiCfg<BN>::COLS_PER_WARP;
-    constexpr int CHUNKS = (COLS_PER_WARP + 31) / 32;
+    constexpr int CHUNKS = COLS_PER_WARP / 32;
+    // per-warp staging tile (bf16 outputs): rows of COLS_PER_WARP*2 bytes + 16 B pad -> conflict-free
+    constexpr int ROW_BYTES = COLS_PER_WARP * 2;
+    constexpr int ROW_PITCH = ROW_BYTES + 16;
+    uint8_t* stage_buf = smem + SL::TILES_BYTES + SL::BAR_BYTES + ew * (32 * ROW_PITCH);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = tile / (m_tiles * n_tiles);
@@ -325,64 +340,100 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mt = rem / n_tiles, nt = rem % n_tiles;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = mt * BM + quad * 32 + lane;
+      const int row0 = mt * BM + quad * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < g.M;
-#pragma unroll 1
-      for (int ch = 0; ch < CHUNKS; ++ch) {
-        const int c0 = half * COLS_PER_WARP + ch * 32;          // column inside the tile
-        if (c0 >= BN) break;
-        float v[32];
-        tmem_ld32(tmem_base + acc * BN + c0 + ((uint32_t)(quad * 32) << 16), v);
-        const int col = nt * BN + c0;
+      const int colw = nt * BN + grp * COLS_PER_WARP;            // first column of this warp
+      const uint32_t tbase = tmem_base + acc * BN + grp * COLS_PER_WARP + ((uint32_t)(quad * 32) << 16);
+      const bool partial_out = (g.splitk > 1 || g.trans_out);
+      // epilogue math of one 32-column chunk (pass 1 of EPI_BIAS_GELU2 = the GELU output)
+      auto chunk_math = [&](int ch, float (&v)[32], int pass) {
+        tmem_ld32(tbase + ch * 32, v);
+        const int col = colw + ch * 32;
         const int nvalid = min(32, g.N - col);
-        if (row_ok && nvalid > 0) {
-          if (g.splitk > 1 || g.trans_out) {
-            float* P = g.splitk > 1 ? g.partial + (int64_t)split * g.M * g.N : (float*)g.C;
-            if (g.trans_out) {
-              const int64_t ld = g.splitk > 1 ? g.M : g.ldc;
-              for (int i = 0; i < nvalid; ++i) P[(int64_t)(col + i) * ld + row] = v[i];
+        if (partial_out || !row_ok || nvalid <= 0) return;
+        switch (g.epi) {
+          case EPI_NONE: break;
+          case EPI_BIAS:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += __ldg(g.bias + col + i);
+            break;
+          case EPI_BIAS_RELU:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] = fmaxf(v[i] + __ldg(g.bias + col + i), 0.f);
+            break;
+          case EPI_BIAS_GELU2:
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += __ldg(g.bias + col + i);
+            if (pass == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { float dy; gelu_fast(v[i], v[i], dy); }
+            }
+            break;
+          case EPI_BIAS_RESID: {
+            const float* R = g.resid + (int64_t)row * g.ldr + col;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += (g.bias ? __ldg(g.bias + col + i) : 0.f) + R[i];
+          } break;
+          case EPI_GELU_BWD: {
+            const TC* X = (const TC*)g.aux + (int64_t)row * g.ldaux + col;
+            float xin[32];
+            load_row32<TC>(X, xin, nvalid);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { float y, dy; gelu_fast(xin[i], y, dy); v[i] *= dy; }
+          } break;
+          case EPI_RELU_BWD: {
+            const float* X = (const float*)g.aux + (int64_t)row * g.ldaux + col;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] = X[i] > 0.f ? v[i] : 0.f;
+          } break;
+        }
+      };
+      const int passes = (!partial_out && g.epi == EPI_BIAS_GELU2) ? 2 : 1;
+      // coalesced path: bf16 output, the warp's whole column span inside N, 16-byte aligned rows
+      const bool staged = std::is_same<TC, bf16>::value && !partial_out && (colw + COLS_PER_WARP <= g.N) &&
+                          (g.ldc % 8 == 0) && (((uintptr_t)g.C & 15) == 0) && (passes == 1 || ((uintptr_t)g.C2 & 15) == 0);
+      for (int pass = 0; pass < passes; ++pass) {
+        TC* Cbase = (TC*)((passes == 2 && pass == 1) ? g.C2 : g.C);
+        if (staged) {
+#pragma unroll 1
+          for (int ch = 0; ch < CHUNKS; ++ch) {
+            float v[32];
+            chunk_math(ch, v, pass);
+            uint8_t* dst = stage_buf + lane * ROW_PITCH + ch * 64;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + i * 16) = attn_pack8(v + 8 * i);
+          }
+          __syncwarp();
+          constexpr int LPR = ROW_BYTES / 16;        // lanes per row
+          constexpr int RPI = 32 / LPR;              // rows per iteration
+#pragma unroll
+          for (int it = 0; it < 32 / RPI; ++it) {
+            const int rr = it * RPI + lane / LPR, c16 = lane % LPR;
+            const uint4 u = *reinterpret_cast<const uint4*>(stage_buf + rr * ROW_PITCH + c16 * 16);
+            if (row0 + rr < g.M)
+              *reinterpret_cast<uint4*>((bf16*)Cbase + (int64_t)(row0 + rr) * g.ldc + colw + c16 * 8) = u;
+          }
+          __syncwarp();
+        } else {
+#pragma unroll 1
+          for (int ch = 0; ch < CHUNKS; ++ch) {
+            float v[32];
+            chunk_math(ch, v, pass);
+            const int col = colw + ch * 32;
+            const int nvalid = min(32, g.N - col);
+            if (!row_ok || nvalid <= 0) continue;
+            if (partial_out) {
+              float* P = g.splitk > 1 ? g.partial + (int64_t)split * g.M * g.N : (float*)g.C;
+              if (g.trans_out) {
+                const int64_t ld = g.splitk > 1 ? g.M : g.ldc;
+                for (int i = 0; i < nvalid; ++i) P[(int64_t)(col + i) * ld + row] = v[i];
+              } else {
+                store_row32<float>(P + (int64_t)row * (g.splitk > 1 ? g.N : g.ldc) + col, v, nvalid);
+              }
             } else {
-              store_row32<float>(P + (int64_t)row * (g.splitk > 1 ? g.N : g.ldc) + col, v, nvalid);
+              store_row32<TC>(Cbase + (int64_t)row * g.ldc + col, v, nvalid);
             }
-          } else {
-            TC* C = (TC*)g.C + (int64_t)row * g.ldc + col;
-            switch (g.epi) {
-              case EPI_NONE: break;
-              case EPI_BIAS:
-#pragma unroll
-                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += __ldg(g.bias + col + i);
-                break;
-              case EPI_BIAS_RELU:
-#pragma unroll
-                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] = fmaxf(v[i] + __ldg(g.bias + col + i), 0.f);
-                break;
-              case EPI_BIAS_GELU2: {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += __ldg(g.bias + col + i);
-                store_row32<TC>(C, v, nvalid);      // pre-activation (saved for backward)
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { float dy; gelu_fast(v[i], v[i], dy); }
-                C = (TC*)g.C2 + (int64_t)row * g.ldc + col;
-              } break;
-              case EPI_BIAS_RESID: {
-                const float* R = g.resid + (int64_t)row * g.ldr + col;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += (g.bias ? __ldg(g.bias + col + i) : 0.f) + R[i];
-              } break;
-              case EPI_GELU_BWD: {
-                const TC* X = (const TC*)g.aux + (int64_t)row * g.ldaux + col;
-                float xin[32];
-                load_row32<TC>(X, xin, nvalid);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { float y, dy; gelu_fast(xin[i], y, dy); v[i] *= dy; }
-              } break;
-              case EPI_RELU_BWD: {
-                const float* X = (const float*)g.aux + (int64_t)row * g.ldaux + col;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] = X[i] > 0.f ? v[i] : 0.f;
-              } break;
-            }
-            store_row32<TC>(C, v, nvalid);
           }
         }
       }
