@@ -154,10 +154,19 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 
 // Branch-free GELU for the bf16 tensor-core epilogues (Abramowitz-Stegun 7.1.26 erf, |err| <= 1.5e-7,
 // two MUFU ops: rcp + ex2).  exp(-x^2/2) is shared between erf and the Gaussian pdf of the derivative.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void gelu_fast(float x, float& y, float& dy) {
-  const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.23164189f, ax, 1.0f));        // p/sqrt(2) = 0.3275911/1.41421356
-  const float e = exp2f(-0.72134752f * x * x);                          // exp(-x^2/2)
+  const float t = rcp_approx(fmaf(0.23164189f, fabsf(x), 1.0f));        // p/sqrt(2) = 0.3275911/1.41421356
+  const float e = ex2_approx(-0.72134752f * x * x);                     // exp(-x^2/2)
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
   poly = fmaf(t, poly, -0.284496736f);

@@ -148,10 +148,11 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 128 ? 5 : 6);
+  static_assert(STAGES * STAGE_BYTES + 256 + EpiCfg<BN>::WARPS * 32 * 80 + 1024 <= 232448, "smem budget");
   static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
   // per-epilogue-warp staging tiles for coalesced bf16 stores
-  static constexpr int STAGING_BYTES = EpiCfg<BN>::WARPS * 32 * (EpiCfg<BN>::COLS_PER_WARP * 2 + 16);
+  static constexpr int STAGING_BYTES = EpiCfg<BN>::WARPS * 32 * (64 + 16);
   static constexpr int TOTAL = TILES_BYTES + BAR_BYTES + STAGING_BYTES + 1024;  // +1024 for manual alignment
 };
 
@@ -164,7 +165,8 @@ __device__ __forceinline__ void store_row32<float>(float* dst, const float (&v)[
     for (int i = 0; i < 8; ++i)
       reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   } else {
-    for (int i = 0; i < nvalid; ++i) dst[i] = v[i];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) if (i < nvalid) dst[i] = v[i];
   }
 }
 template <>
@@ -182,7 +184,8 @@ __device__ __forceinline__ void store_row32<bf16>(bf16* dst, const float (&v)[32
       reinterpret_cast<uint4*>(dst)[i] = u;
     }
   } else {
-    for (int i = 0; i < nvalid; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) if (i < nvalid) dst[i] = __float2bfloat16_rn(v[i]);
   }
 }
 
@@ -329,9 +332,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int grp = ew >> 2;                   // which column group of the tile
     constexpr int COLS_PER_WARP = EpiCfg<BN>::COLS_PER_WARP;
     constexpr int CHUNKS = COLS_PER_WARP / 32;
-    // per-warp staging tile (bf16 outputs): rows of COLS_PER_WARP*2 bytes + 16 B pad -> conflict-free
-    constexpr int ROW_BYTES = COLS_PER_WARP * 2;
-    constexpr int ROW_PITCH = ROW_BYTES + 16;
+    // per-warp staging tile: 32 rows x 64 B (one 32-column bf16 chunk) + 16 B pad -> conflict-free,
+    // used to turn row-per-lane register tiles into coalesced 64-byte row segments (and back)
+    constexpr int ROW_PITCH = 64 + 16;
     uint8_t* stage_buf = smem + SL::TILES_BYTES + SL::BAR_BYTES + ew * (32 * ROW_PITCH);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -343,98 +346,146 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row0 = mt * BM + quad * 32;
       const int row = row0 + lane;
       const bool row_ok = row < g.M;
+      const bool rows_full = row0 + 32 <= g.M;
       const int colw = nt * BN + grp * COLS_PER_WARP;            // first column of this warp
       const uint32_t tbase = tmem_base + acc * BN + grp * COLS_PER_WARP + ((uint32_t)(quad * 32) << 16);
       const bool partial_out = (g.splitk > 1 || g.trans_out);
-      // epilogue math of one 32-column chunk (pass 1 of EPI_BIAS_GELU2 = the GELU output)
-      auto chunk_math = [&](int ch, float (&v)[32], int pass) {
+      // coalesced path: bf16 output, 16-byte aligned rows
+      const bool can_stage = std::is_same<TC, bf16>::value && !partial_out && (g.ldc % 8 == 0) &&
+                             (((uintptr_t)g.C & 15) == 0) && (g.epi != EPI_BIAS_GELU2 || ((uintptr_t)g.C2 & 15) == 0) &&
+                             (g.epi != EPI_GELU_BWD || ((g.ldaux % 8 == 0) && (((uintptr_t)g.aux & 15) == 0)));
+      // lane <-> (row, 16-byte piece) mapping of the coalesced phase: 4 lanes per 64-byte row segment
+      const int rr0 = lane >> 2, c16 = lane & 3;
+      auto stage_store = [&](const float (&v)[32], bf16* Cb, int col) {
+        uint8_t* dst = stage_buf + lane * ROW_PITCH;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + i * 16) = attn_pack8(v + 8 * i);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + rr0;
+          const uint4 u = *reinterpret_cast<const uint4*>(stage_buf + rr * ROW_PITCH + c16 * 16);
+          if (rows_full || row0 + rr < g.M)
+            *reinterpret_cast<uint4*>(Cb + (int64_t)(row0 + rr) * g.ldc + col + c16 * 8) = u;
+        }
+        __syncwarp();
+      };
+      auto stage_load = [&](float (&x)[32], const bf16* Xb, int64_t ldx, int col) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + rr0;
+          uint4 u = make_uint4(0, 0, 0, 0);
+          if (rows_full || row0 + rr < g.M)
+            u = *reinterpret_cast<const uint4*>(Xb + (int64_t)(row0 + rr) * ldx + col + c16 * 8);
+          *reinterpret_cast<uint4*>(stage_buf + rr * ROW_PITCH + c16 * 16) = u;
+        }
+        __syncwarp();
+        const uint8_t* src = stage_buf + lane * ROW_PITCH;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 u = *reinterpret_cast<const uint4*>(src + i * 16);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            x[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
+            x[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+          }
+        }
+        __syncwarp();
+      };
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ++ch) {
+        float v[32];
         tmem_ld32(tbase + ch * 32, v);
         const int col = colw + ch * 32;
         const int nvalid = min(32, g.N - col);
-        if (partial_out || !row_ok || nvalid <= 0) return;
-        switch (g.epi) {
-          case EPI_NONE: break;
-          case EPI_BIAS:
+        if (nvalid <= 0) continue;                                  // warp-uniform
+        if (partial_out) {
+          if (!row_ok) continue;
+          float* P = g.splitk > 1 ? g.partial + (int64_t)split * g.M * g.N : (float*)g.C;
+          if (g.trans_out) {
+            const int64_t ld = g.splitk > 1 ? g.M : g.ldc;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < nvalid) P[(int64_t)(col + i) * ld + row] = v[i];
+          } else {
+            store_row32<float>(P + (int64_t)row * (g.splitk > 1 ? g.N : g.ldc) + col, v, nvalid);
+          }
+          continue;
+        }
+        const bool full = (nvalid == 32);                           // warp-uniform
+        const bool staged = can_stage && full;
+        // ---- bias (all epilogues that have one)
+        if (g.bias && (g.epi == EPI_BIAS || g.epi == EPI_BIAS_RELU || g.epi == EPI_BIAS_GELU2 || g.epi == EPI_BIAS_RESID)) {
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col) + i);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
+          } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += __ldg(g.bias + col + i);
-            break;
+          }
+        }
+        TC* Cb = (TC*)g.C;
+        switch (g.epi) {
           case EPI_BIAS_RELU:
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] = fmaxf(v[i] + __ldg(g.bias + col + i), 0.f);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             break;
           case EPI_BIAS_GELU2:
+            // first output: the pre-activation (saved for backward); then GELU in place
+            if (staged) {
+              if constexpr (std::is_same<TC, bf16>::value) stage_store(v, (bf16*)g.C, col);
+            } else if (row_ok) {
+              store_row32<TC>((TC*)g.C + (int64_t)row * g.ldc + col, v, nvalid);
+            }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += __ldg(g.bias + col + i);
-            if (pass == 1) {
+            for (int i = 0; i < 32; ++i) { float dy; gelu_fast(v[i], v[i], dy); }
+            Cb = (TC*)g.C2;
+            break;
+          case EPI_BIAS_RESID:
+            if (row_ok) {
+              const float* R = g.resid + (int64_t)row * g.ldr + col;
+              if (full && ((((uintptr_t)R) & 15) == 0)) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) { float dy; gelu_fast(v[i], v[i], dy); }
+                for (int i = 0; i < 8; ++i) {
+                  const float4 r4 = reinterpret_cast<const float4*>(R)[i];
+                  v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += R[i];
+              }
             }
             break;
-          case EPI_BIAS_RESID: {
-            const float* R = g.resid + (int64_t)row * g.ldr + col;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += (g.bias ? __ldg(g.bias + col + i) : 0.f) + R[i];
-          } break;
           case EPI_GELU_BWD: {
-            const TC* X = (const TC*)g.aux + (int64_t)row * g.ldaux + col;
             float xin[32];
-            load_row32<TC>(X, xin, nvalid);
+            if (staged) {
+              if constexpr (std::is_same<TC, bf16>::value) stage_load(xin, (const bf16*)g.aux, g.ldaux, col);
+            } else {
+              if (row_ok) load_row32<TC>((const TC*)g.aux + (int64_t)row * g.ldaux + col, xin, nvalid);
+              else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xin[i] = 0.f;
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) { float y, dy; gelu_fast(xin[i], y, dy); v[i] *= dy; }
           } break;
-          case EPI_RELU_BWD: {
-            const float* X = (const float*)g.aux + (int64_t)row * g.ldaux + col;
+          case EPI_RELU_BWD:
+            if (row_ok) {
+              const float* X = (const float*)g.aux + (int64_t)row * g.ldaux + col;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] = X[i] > 0.f ? v[i] : 0.f;
-          } break;
-        }
-      };
-      const int passes = (!partial_out && g.epi == EPI_BIAS_GELU2) ? 2 : 1;
-      // coalesced path: bf16 output, the warp's whole column span inside N, 16-byte aligned rows
-      const bool staged = std::is_same<TC, bf16>::value && !partial_out && (colw + COLS_PER_WARP <= g.N) &&
-                          (g.ldc % 8 == 0) && (((uintptr_t)g.C & 15) == 0) && (passes == 1 || ((uintptr_t)g.C2 & 15) == 0);
-      for (int pass = 0; pass < passes; ++pass) {
-        TC* Cbase = (TC*)((passes == 2 && pass == 1) ? g.C2 : g.C);
-        if (staged) {
-#pragma unroll 1
-          for (int ch = 0; ch < CHUNKS; ++ch) {
-            float v[32];
-            chunk_math(ch, v, pass);
-            uint8_t* dst = stage_buf + lane * ROW_PITCH + ch * 64;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + i * 16) = attn_pack8(v + 8 * i);
-          }
-          __syncwarp();
-          constexpr int LPR = ROW_BYTES / 16;        // lanes per row
-          constexpr int RPI = 32 / LPR;              // rows per iteration
-#pragma unroll
-          for (int it = 0; it < 32 / RPI; ++it) {
-            const int rr = it * RPI + lane / LPR, c16 = lane % LPR;
-            const uint4 u = *reinterpret_cast<const uint4*>(stage_buf + rr * ROW_PITCH + c16 * 16);
-            if (row0 + rr < g.M)
-              *reinterpret_cast<uint4*>((bf16*)Cbase + (int64_t)(row0 + rr) * g.ldc + colw + c16 * 8) = u;
-          }
-          __syncwarp();
-        } else {
-#pragma unroll 1
-          for (int ch = 0; ch < CHUNKS; ++ch) {
-            float v[32];
-            chunk_math(ch, v, pass);
-            const int col = colw + ch * 32;
-            const int nvalid = min(32, g.N - col);
-            if (!row_ok || nvalid <= 0) continue;
-            if (partial_out) {
-              float* P = g.splitk > 1 ? g.partial + (int64_t)split * g.M * g.N : (float*)g.C;
-              if (g.trans_out) {
-                const int64_t ld = g.splitk > 1 ? g.M : g.ldc;
-                for (int i = 0; i < nvalid; ++i) P[(int64_t)(col + i) * ld + row] = v[i];
-              } else {
-                store_row32<float>(P + (int64_t)row * (g.splitk > 1 ? g.N : g.ldc) + col, v, nvalid);
-              }
-            } else {
-              store_row32<TC>(Cbase + (int64_t)row * g.ldc + col, v, nvalid);
+              for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] = X[i] > 0.f ? v[i] : 0.f;
             }
-          }
+            break;
+          default: break;
+        }
+        if (staged) {
+          if constexpr (std::is_same<TC, bf16>::value) stage_store(v, (bf16*)Cb, col);
+        } else if (row_ok) {
+          store_row32<TC>(Cb + (int64_t)row * g.ldc + col, v, nvalid);
         }
       }
       tc_fence_before();
