@@ -167,7 +167,8 @@ def run_ours(args):
     pk = peaks()
 
     ag = dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, False, SEED, BUFFER_SIZE=args.replay,
-                precision=args.precision, device=dev, distributed=world > 1, **HP, **PRESET)
+                precision=args.precision, device=dev, distributed=world > 1, use_cuda_graph=not args.no_graph,
+                **HP, **PRESET)
     ag.replay_buffer.fill_synthetic(args.replay, seed=SEED + rank)
     lib = L.lib()
 
@@ -183,8 +184,6 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    L.check(lib.dgvit_prof_begin(L.PROF_GEMM_MLP, args.steps * 160), "prof_begin")
-    n0 = lib.dgvit_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -192,11 +191,26 @@ def run_ours(args):
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
-    launches = lib.dgvit_launch_count() - n0
-    pms, pl, pfl, pby = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
-    L.check(lib.dgvit_prof_end(C.byref(pms), C.byref(pl), C.byref(pfl), C.byref(pby)), "prof_end")
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    # per-kernel timing of the dominant kernel family + launch count: the same steps launched eagerly
+    # (CUDA events around individual launches cannot be recorded inside a replayed graph)
+    graph_flag, ag.use_cuda_graph = ag.use_cuda_graph, False
+    psteps = min(args.steps, 5)
+    L.check(lib.dgvit_prof_begin(L.PROF_GEMM_MLP, psteps * 160), "prof_begin")
+    n0 = lib.dgvit_launch_count()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(psteps):
+        ag.learn_async(B)
+    p1.record()
+    torch.cuda.synchronize(dev)
+    launches = (lib.dgvit_launch_count() - n0) * args.steps // psteps
+    pms, pl, pfl, pby = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
+    L.check(lib.dgvit_prof_end(C.byref(pms), C.byref(pl), C.byref(pfl), C.byref(pby)), "prof_end")
+    eager_ms_per_step = p0.elapsed_time(p1) / psteps
+    ag.use_cuda_graph = graph_flag
+    barrier()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -227,7 +241,7 @@ def run_ours(args):
                     devb[j][k].copy_(host[i % len(host)][k], non_blocking=True)
                 ready[j].record(copy_stream)
             main.wait_event(ready[j])
-            ls = ag.update_from_batch(devb[j])
+            ls = ag.update_from_batch_graphed(devb[j], j)
             freed[j].record(main)
             loss_host.copy_(ls, non_blocking=True)         # D2H read of the step's result
         torch.cuda.synchronize(dev)
@@ -259,8 +273,9 @@ def run_ours(args):
     ach = (pfl.value / 1e12) / (pms.value / 1e3) if pms.value > 0 else 0.0
     roof = dict(bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s", frac=ach / pk["tf_sust"],
                 traffic=None, kernel="MLP GEMM family (fc1+GELU, fc2+residual, and their dX/dW)",
-                launches_timed=int(pl.value), kernel_ms_per_step=pms.value / args.steps,
-                share_of_step=(pms.value / ms) if ms > 0 else None, peak_source=pk["src"] + " (sustained bf16 cuBLAS)")
+                launches_timed=int(pl.value), kernel_ms_per_step=pms.value / psteps,
+                share_of_step=(pms.value / psteps) / (ms / args.steps) if ms > 0 else None,
+                eager_ms_per_step=eager_ms_per_step, peak_source=pk["src"] + " (sustained bf16 cuBLAS)")
     whole = dict(achieved_tflops=value * FLOP_PER_SAMPLE / 1e12, frac_of_peak=value * FLOP_PER_SAMPLE / 1e12 / pk["tf_sust"] / world)
 
     cpu = None
@@ -274,7 +289,7 @@ def run_ours(args):
                 config=dict(workload="full off-policy actor-critic update step, batch 256 per GPU, DGViT actor + "
                                      "Transformer critic (D=64, L=4, H=4, 65 tokens, MLP 2048), 1xB200 per rank",
                             batch_per_gpu=B, global_batch=B * world, precision=args.precision,
-                            parallelism=f"dp{world}", replay_transitions=args.replay,
+                            parallelism=f"dp{world}", replay_transitions=args.replay, cuda_graph=not args.no_graph,
                             l2="inputs gathered each step by random index from a %.2f GB device replay store (> 126 MB L2)"
                                % (ag.replay_buffer.obs.numel() * 4 / 1e9)),
                 roofline=roof, whole_step=whole, cpu_baseline=cpu,
@@ -295,6 +310,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--replay", type=int, default=30000, help="replay store transitions (vn/config.yaml:17)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

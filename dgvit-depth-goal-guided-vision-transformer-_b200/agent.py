@@ -164,6 +164,7 @@ class SAC(object):
         self._losses = torch.zeros(4, **f32)
         self._ws = None
         self._batch = None
+        self._idx = None
         self._graphs = {}
         for m in (self.critic, self.critic_target, self.policy):
             m.refresh_shadow()
@@ -260,10 +261,48 @@ class SAC(object):
     def learn_async(self, batch_size=64) -> torch.Tensor:
         """Same update without the host read-back (losses stay on the device)."""
         B = int(batch_size)
-        idx = self.replay_buffer.sample_indexes(B).to(self.device, non_blocking=True)
+        idx_host = self.replay_buffer.sample_indexes(B)
+        if self._idx is None or self._idx.numel() != B:
+            self._idx = torch.zeros(B, dtype=torch.int64, device=self.device)
+            self._idx_pin = torch.zeros(B, dtype=torch.int64).pin_memory()
+        self._idx_pin.copy_(idx_host)
+        self._idx.copy_(self._idx_pin, non_blocking=True)
         batch = self._batch_buffers(B)
-        self.replay_buffer.gather(idx, batch)
-        return self.update_from_batch(batch)
+        if not self.use_cuda_graph:
+            self.replay_buffer.gather(self._idx, batch)
+            return self.update_from_batch(batch)
+        return self._graphed(("learn", B), lambda: (self.replay_buffer.gather(self._idx, batch),
+                                                    self.update_from_batch(batch))[1])
+
+    def update_from_batch_graphed(self, batch: Dict[str, torch.Tensor], key) -> torch.Tensor:
+        """``update_from_batch`` replayed from a CUDA graph keyed by ``key`` (the batch tensors must be
+        the same device buffers on every call with that key)."""
+        if not self.use_cuda_graph:
+            return self.update_from_batch(batch)
+        return self._graphed(("batch", key, batch["obs"].data_ptr()), lambda: self.update_from_batch(batch))
+
+    def _graphed(self, key, fn):
+        """Eager on the first call (warms lazily initialised state), captured on the second,
+        replayed afterwards.  One graph per (key, polyak flag): every launch, tensor map and
+        device pointer of the update is frozen in the graph; per-step state (Adam step counts,
+        alpha, RNG counter, sampled indexes) lives in device memory."""
+        key = key + (int(self.itera % self.policy_freq == 0),)
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs[key] = "warm"
+            return fn()
+        if ent == "warm":
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            itera = self.itera
+            with torch.cuda.graph(g):
+                fn()
+            self.itera = itera            # capture does not execute: undo the host-side counter
+            self._graphs[key] = g
+            ent = g
+        ent.replay()
+        self.itera += 1
+        return self._losses
 
     # ------------------------------------------------------------------ act
     def choose_action(self, istate, pstate, evaluate=False):

@@ -155,7 +155,7 @@ static void linear_bwd_w(const TA* dy, const TB* x, float* dW, float* db, int64_
   g.splitk = pick_splitk(R); g.partial = partial;
   gemm<TA, TB, float>(g, st);
   if (db) {
-    const int S = (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 512);   // many short row ranges: HBM-bound read
+    const int S = (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 64);    // row ranges per column block
     const int64_t rpb = cdiv(R, S);
     dim3 grid((unsigned)cdiv(N, 128), (unsigned)S);
     colsum_partial_kernel<TA><<<grid, 128, 0, st>>>(dy, ldy, partial, R, N, rpb);
@@ -273,7 +273,7 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
                           const float* gamma, float* dX_io, bf16* dX_lp, float* dgamma, float* dbeta,
                           float* partial, int64_t T, int D, cudaStream_t st) {
   const int wpb = 8;
-  int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148);
+  int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 8);
   const size_t smem = (size_t)wpb * 2 * D * sizeof(float);
   switch (D / 32) {
 #define LNB(V) case V: layernorm_bwd_kernel<V><<<nblocks, wpb * 32, smem, st>>>(dY, X, mean, rstd, gamma, dX_io, dX_lp, partial, T); break;
@@ -282,7 +282,7 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
     default: fail(DGVIT_ERR_ARG, "unsupported dim %d", D);
   }
   DG_LAUNCH_CHECK();
-  ln_param_reduce_kernel<<<(unsigned)cdiv(2 * D, 128), 128, 0, st>>>(partial, dgamma, dbeta, nblocks, D);
+  ln_param_reduce_kernel<<<(unsigned)cdiv(2 * D, 32), 256, 0, st>>>(partial, dgamma, dbeta, nblocks, D);
   DG_LAUNCH_CHECK();
 }
 
@@ -334,8 +334,9 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
   const float* P = net.params;
   // K1: patch embedding
   {
-    const int64_t total = (int64_t)d.B * d.P * d.pd;
-    patchify_kernel<A><<<grid1d(total), 256, 0, st>>>(img, c.Pm, total, cfg.img_h, cfg.img_w, cfg.patch_h, cfg.patch_w);
+    const int64_t total4 = (int64_t)d.B * d.P * d.pd / 4;
+    DG_REQUIRE(cfg.patch_w % 4 == 0 && (((uintptr_t)img) & 15) == 0, "patchify: patch_w %% 4 and 16-byte aligned frames required");
+    patchify_kernel<A><<<grid1d(total4), 256, 0, st>>>(img, c.Pm, total4, cfg.img_h, cfg.img_w, cfg.patch_h, cfg.patch_w);
     DG_LAUNCH_CHECK();
     linear_fwd<A, A, float>(c.Pm, WSel<A>::w(net, L.patch_w), c.Xp, (int64_t)d.B * d.P, d.D, d.pd, EPI_BIAS,
                             P + L.patch_b, st);

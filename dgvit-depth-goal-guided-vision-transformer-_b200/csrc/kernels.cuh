@@ -13,19 +13,22 @@ namespace dgvit {
 // Rearrange 'b (h p1) (w p2) -> b (h w) (p1 p2)' materialised once per forward in the
 // activation dtype (the fp32->bf16 cast of the frame is fused here).
 template <typename A>
-__global__ void patchify_kernel(const float* __restrict__ img, A* __restrict__ out, int64_t total,
+__global__ void patchify_kernel(const float* __restrict__ img, A* __restrict__ out, int64_t total4,
                                 int img_h, int img_w, int ph, int pw) {
+  // one thread = 4 consecutive pixels of one patch row (pw % 4 == 0, img_w % 4 == 0)
   const int gw = img_w / pw, gh = img_h / ph;
-  const int pd = ph * pw, P = gh * gw;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+  const int q4 = pw / 4, pd4 = ph * q4, P = gh * gw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % pd);
-    const int64_t bp = i / pd;
+    const int k4 = (int)(i % pd4);
+    const int64_t bp = i / pd4;
     const int p = (int)(bp % P);
     const int64_t b = bp / P;
-    const int p1 = k / pw, p2 = k % pw;
-    const int y = (p / gw) * ph + p1, x = (p % gw) * pw + p2;
-    stf(out + i, img[(b * img_h + y) * img_w + x]);
+    const int p1 = k4 / q4, q = k4 % q4;
+    const int y = (p / gw) * ph + p1, x = (p % gw) * pw + 4 * q;
+    const float4 v = *reinterpret_cast<const float4*>(img + (b * img_h + y) * img_w + x);
+    A* o = out + i * 4;
+    stf(o, v.x); stf(o + 1, v.y); stf(o + 2, v.z); stf(o + 3, v.w);
   }
 }
 
@@ -172,14 +175,24 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dY, const float* 
   }
 }
 
-// out_g[d] = sum_blocks part[b][0][d], out_b[d] = sum_blocks part[b][1][d]
+// dgamma[d] = sum_blocks part[b][0][d], dbeta[d] = sum_blocks part[b][1][d]
+// block = 32 columns x 8 row-groups; fixed summation order (deterministic)
 __global__ void ln_param_reduce_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int nblocks, int D) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= 2 * D) return;
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * 2 * D + j];
-  if (j < D) dgamma[j] = s; else dbeta[j - D] = s;
+  if (j < 2 * D)
+    for (int b = gy; b < nblocks; b += 8) s += part[(int64_t)b * 2 * D + j];
+  sm[gy][cx] = s;
+  __syncthreads();
+  if (gy == 0 && j < 2 * D) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += sm[g][cx];
+    if (j < D) dgamma[j] = t; else dbeta[j - D] = t;
+  }
 }
 
 // column sums (bias gradients): part[s][n] = sum over this block's row range
