@@ -248,7 +248,7 @@ def run_ours(args):
 
     for j in range(nbuf):
         freed[j].record(main)
-    e2e_steps(max(args.warmup, 3))
+    e2e_steps(max(args.warmup, 3) * nbuf)      # each device buffer: eager warm-up, graph capture, replay
     barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()

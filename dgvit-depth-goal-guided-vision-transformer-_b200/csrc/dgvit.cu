@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
+#include "heads.cuh"
 #ifdef DGVIT_WITH_TC
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
@@ -120,24 +121,26 @@ static void gemm(const GemmArgs& g, cudaStream_t st) {
 // y[R,N] = x[R,K] W[N,K]^T (+epilogue)
 template <typename TA, typename TB, typename TC>
 static void linear_fwd(const TA* x, const TB* W, TC* y, int64_t R, int N, int K, int epi, const float* bias,
-                       cudaStream_t st, const float* resid = nullptr, void* C2 = nullptr, int64_t ldc = -1) {
+                       cudaStream_t st, const float* resid = nullptr, void* C2 = nullptr, int64_t ldc = -1,
+                       int64_t ldx = -1, int64_t ldr = -1) {
   GemmArgs g;
   g.M = (int)R; g.N = N; g.K = K;
-  g.A = x; g.a_sm = K; g.a_sk = 1;
+  g.A = x; g.a_sm = ldx < 0 ? K : ldx; g.a_sk = 1;
   g.B = W; g.b_sk = 1; g.b_sn = K;
   g.C = y; g.ldc = ldc < 0 ? N : ldc;
-  g.epi = epi; g.bias = bias; g.resid = resid; g.ldr = g.ldc; g.C2 = C2;
+  g.epi = epi; g.bias = bias; g.resid = resid; g.ldr = ldr < 0 ? g.ldc : ldr; g.C2 = C2;
   gemm<TA, TB, TC>(g, st);
 }
 // dx[R,K] = dy[R,N] W[N,K]  (+epilogue)
 template <typename TA, typename TB, typename TC>
 static void linear_bwd_x(const TA* dy, const TB* W, TC* dx, int64_t R, int N, int K, int epi, const void* aux,
-                         int64_t ldaux, cudaStream_t st, int64_t ldy = -1, const float* resid = nullptr) {
+                         int64_t ldaux, cudaStream_t st, int64_t ldy = -1, const float* resid = nullptr,
+                         int64_t ldc = -1) {
   GemmArgs g;
   g.M = (int)R; g.N = K; g.K = N;
   g.A = dy; g.a_sm = ldy < 0 ? N : ldy; g.a_sk = 1;
   g.B = W; g.b_sk = K; g.b_sn = 1;
-  g.C = dx; g.ldc = K;
+  g.C = dx; g.ldc = ldc < 0 ? K : ldc;
   g.epi = epi; g.aux = aux; g.ldaux = ldaux; g.resid = resid; g.ldr = K;
   gemm<TA, TB, TC>(g, st);
 }
@@ -186,10 +189,14 @@ struct TrunkCtx {
   float *dX, *dXn, *dtok, *dz, *dg_rows, *partial;
   A *dH, *dO, *dQKV, *dXp;
   bf16* dXh;  // bf16 copy of dX (operand of the tensor-core GEMMs); null in the fp32 path
+  float* dXc; bf16* dXch;   // last block: compact [B, D] residual gradient of the token-0 rows
   size_t partial_floats;
   // residual-stream gradient in the operand dtype
   const A* dx_op() const {
     if constexpr (std::is_same<A, float>::value) return dX; else return dXh;
+  }
+  const A* dxc_op() const {
+    if constexpr (std::is_same<A, float>::value) return dXc; else return dXch;
   }
 };
 
@@ -221,6 +228,7 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
   }
   c.dX = nullptr; c.dXn = nullptr; c.dtok = nullptr; c.dz = nullptr; c.dg_rows = nullptr; c.partial = nullptr;
   c.dH = nullptr; c.dO = nullptr; c.dQKV = nullptr; c.dXp = nullptr; c.dXh = nullptr; c.partial_floats = 0;
+  c.dXc = nullptr; c.dXch = nullptr;
   if (save) {
     c.dX = cv.take<float>(d.T * d.D);
     c.dXn = cv.take<float>(d.T * d.D);
@@ -232,6 +240,8 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
     c.dQKV = cv.take<A>(d.T * 3 * d.inner);
     c.dXp = cv.take<A>((int64_t)d.B * d.P * d.D);
     c.dXh = std::is_same<A, float>::value ? nullptr : cv.take<bf16>(d.T * d.D);
+    c.dXc = cv.take<float>((int64_t)d.B * d.D);
+    c.dXch = std::is_same<A, float>::value ? nullptr : cv.take<bf16>((int64_t)d.B * d.D);
     int64_t mx = (int64_t)d.D * d.M;
     mx = std::max<int64_t>(mx, (int64_t)3 * d.inner * d.D);
     mx = std::max<int64_t>(mx, (int64_t)d.D * d.pd);
@@ -352,17 +362,25 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
     launch_ln_fwd<A>(B_.Xa, P + b.ln1_w, P + b.ln1_b, B_.Xn1, B_.mean1, B_.rstd1, d.T, d.D, st);
     linear_fwd<A, A, A>(B_.Xn1, WSel<A>::w(net, b.qkv_w), B_.QKV, d.T, 3 * d.inner, d.D, EPI_NONE, nullptr, st);
     launch_attention_fwd<A>(B_.QKV, B_.O, d, st);
-    linear_fwd<A, A, float>(B_.O, WSel<A>::w(net, b.out_w), B_.Xm, d.T, d.D, d.inner, EPI_BIAS_RESID, P + b.out_b, st,
-                            B_.Xa);
+    // Only token 0 of the last block's output is consumed (x[:, 0], vn/GoalFormer.py:167): there the
+    // out-projection, LayerNorm, MLP and residuals run on the B token-0 rows only (compact [B, D]
+    // buffers).  Exact: the pruned rows never reach z, so outputs and every gradient are unchanged.
+    const bool last = (l == d.L - 1);
+    const int64_t R = last ? d.B : d.T;
+    const int64_t ostride = last ? (int64_t)d.N * d.inner : d.inner;
+    const int64_t xstride = last ? (int64_t)d.N * d.D : d.D;
+    linear_fwd<A, A, float>(B_.O, WSel<A>::w(net, b.out_w), B_.Xm, R, d.D, d.inner, EPI_BIAS_RESID, P + b.out_b, st,
+                            B_.Xa, nullptr, -1, ostride, xstride);
     // MLP block: x = ff(LN(x)) + x
-    launch_ln_fwd<A>(B_.Xm, P + b.ln2_w, P + b.ln2_b, B_.Xn2, B_.mean2, B_.rstd2, d.T, d.D, st);
+    launch_ln_fwd<A>(B_.Xm, P + b.ln2_w, P + b.ln2_b, B_.Xn2, B_.mean2, B_.rstd2, R, d.D, st);
     TagScope mlp_tag(PROF_GEMM_MLP);
-    linear_fwd<A, A, A>(B_.Xn2, WSel<A>::w(net, b.fc1_w), B_.Hpre, d.T, d.M, d.D, EPI_BIAS_GELU2, P + b.fc1_b, st,
+    linear_fwd<A, A, A>(B_.Xn2, WSel<A>::w(net, b.fc1_w), B_.Hpre, R, d.M, d.D, EPI_BIAS_GELU2, P + b.fc1_b, st,
                         nullptr, B_.Hact);
-    linear_fwd<A, A, float>(B_.Hact, WSel<A>::w(net, b.fc2_w), Xnext, d.T, d.D, d.M, EPI_BIAS_RESID, P + b.fc2_b, st,
+    linear_fwd<A, A, float>(B_.Hact, WSel<A>::w(net, b.fc2_w), Xnext, R, d.D, d.M, EPI_BIAS_RESID, P + b.fc2_b, st,
                             B_.Xm);
   }
-  pool_rmsnorm_fwd_kernel<<<(unsigned)cdiv(d.B, 8), 256, 0, st>>>(c.Xout, P + L.rms_g, c.z, d.B, d.N, d.D,
+  // c.Xout is compact [B, D] (token-0 rows of the last block)
+  pool_rmsnorm_fwd_kernel<<<(unsigned)cdiv(d.B, 8), 256, 0, st>>>(c.Xout, P + L.rms_g, c.z, d.B, 1, d.D,
                                                                    sqrtf((float)d.D));
   DG_LAUNCH_CHECK();
 }
@@ -374,7 +392,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
                            TrunkCtx<A>& c, int relu_tok, cudaStream_t st) {
   const float* P = net.params;
   float* G = net.grads;
-  pool_rmsnorm_bwd_kernel<<<d.B, 128, 0, st>>>(c.Xout, P + L.rms_g, c.dz, c.dX, c.dXh, c.dg_rows, d.B, d.N, d.D,
+  pool_rmsnorm_bwd_kernel<<<d.B, 128, 0, st>>>(c.Xout, P + L.rms_g, c.dz, c.dXc, c.dXch, c.dg_rows, d.B, 1, d.D,
                                                 sqrtf((float)d.D));
   DG_LAUNCH_CHECK();
   {  // dg = sum_b dg_rows
@@ -388,19 +406,38 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
   for (int l = d.L - 1; l >= 0; --l) {
     const dgvit_block_layout& b = L.block[l];
     LayerBuf<A>& B_ = c.L[l];
-    // ---- MLP block.  c.dX = dL/dX_out (fp32 residual-stream gradient; dx_op() = operand copy)
+    // the last block carries only the token-0 rows (compact [B, D]) down to its attention output
+    const bool last = (l == d.L - 1);
+    const int64_t R = last ? d.B : d.T;
+    float* dXr = last ? c.dXc : c.dX;                  // fp32 residual-stream gradient of these rows
+    bf16* dXr_lp = last ? c.dXch : c.dXh;
+    const A* dxop = last ? c.dxc_op() : c.dx_op();
+    // ---- MLP block.  dXr = dL/dX_out
     {
     TagScope mlp_tag(PROF_GEMM_MLP);
-    linear_bwd_w<A, A>(c.dx_op(), B_.Hact, G + b.fc2_w, G + b.fc2_b, d.T, d.D, d.M, c.partial, st);
-    linear_bwd_x<A, A, A>(c.dx_op(), WSel<A>::w(net, b.fc2_w), c.dH, d.T, d.D, d.M, EPI_GELU_BWD, B_.Hpre, d.M, st);
-    linear_bwd_w<A, A>(c.dH, B_.Xn2, G + b.fc1_w, G + b.fc1_b, d.T, d.M, d.D, c.partial, st);
-    linear_bwd_x<A, A, float>(c.dH, WSel<A>::w(net, b.fc1_w), c.dXn, d.T, d.M, d.D, EPI_NONE, nullptr, 0, st);
+    linear_bwd_w<A, A>(dxop, B_.Hact, G + b.fc2_w, G + b.fc2_b, R, d.D, d.M, c.partial, st);
+    linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.fc2_w), c.dH, R, d.D, d.M, EPI_GELU_BWD, B_.Hpre, d.M, st);
+    linear_bwd_w<A, A>(c.dH, B_.Xn2, G + b.fc1_w, G + b.fc1_b, R, d.M, d.D, c.partial, st);
+    linear_bwd_x<A, A, float>(c.dH, WSel<A>::w(net, b.fc1_w), c.dXn, R, d.M, d.D, EPI_NONE, nullptr, 0, st);
     }
-    launch_ln_bwd(c.dXn, B_.Xm, B_.mean2, B_.rstd2, P + b.ln2_w, c.dX, c.dXh, G + b.ln2_w, G + b.ln2_b, c.partial,
-                  d.T, d.D, st);
-    // ---- attention block.  c.dX = dL/dX_m
-    linear_bwd_w<A, A>(c.dx_op(), B_.O, G + b.out_w, G + b.out_b, d.T, d.D, d.inner, c.partial, st);
-    linear_bwd_x<A, A, A>(c.dx_op(), WSel<A>::w(net, b.out_w), c.dO, d.T, d.D, d.inner, EPI_NONE, nullptr, 0, st);
+    launch_ln_bwd(c.dXn, B_.Xm, B_.mean2, B_.rstd2, P + b.ln2_w, dXr, dXr_lp, G + b.ln2_w, G + b.ln2_b, c.partial, R,
+                  d.D, st);
+    // ---- attention block.  dXr = dL/dX_m
+    if (!last) {
+      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, G + b.out_b, d.T, d.D, d.inner, c.partial, st);
+      linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.out_w), c.dO, d.T, d.D, d.inner, EPI_NONE, nullptr, 0, st);
+    } else {
+      const int64_t ostride = (int64_t)d.N * d.inner;
+      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, G + b.out_b, d.B, d.D, d.inner, c.partial, st, -1, ostride);
+      // dO is zero except on the token-0 rows
+      DG_CUDA(cudaMemsetAsync(c.dO, 0, (size_t)d.T * d.inner * sizeof(A), st));
+      linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.out_w), c.dO, d.B, d.D, d.inner, EPI_NONE, nullptr, 0, st, -1,
+                            nullptr, ostride);
+      // expand the compact residual gradient to [T, D] (zero off token 0) for the LayerNorm-1 backward
+      const int64_t tot = d.T * d.D;
+      scatter_row0_kernel<<<grid1d(tot), 256, 0, st>>>(c.dXc, c.dX, tot, d.N, d.D);
+      DG_LAUNCH_CHECK();
+    }
     launch_attention_bwd<A>(B_.QKV, B_.O, c.dO, c.dQKV, d, st);
     linear_bwd_w<A, A>(c.dQKV, B_.Xn1, G + b.qkv_w, nullptr, d.T, 3 * d.inner, d.D, c.partial, st);
     linear_bwd_x<A, A, float>(c.dQKV, WSel<A>::w(net, b.qkv_w), c.dXn, d.T, 3 * d.inner, d.D, EPI_NONE, nullptr, 0, st);
@@ -468,10 +505,15 @@ static void actor_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
   DG_LAUNCH_CHECK();
   const DropDev drop = make_drop(io.drop, d, io.sample_offset);
   trunk_forward<A>(net, L, d, io.img, drop, c.t, st);
-  linear_fwd<float, float, float>(c.t.z, P + L.fc1_w, c.h1, d.B, 128, d.D, EPI_BIAS_RELU, P + L.fc1_b, st);
-  linear_fwd<float, float, float>(c.h1, P + L.fc2_w, c.h2, d.B, 128, 128, EPI_BIAS_RELU, P + L.fc2_b, st);
-  linear_fwd<float, float, float>(c.h2, P + L.mean_w, c.mean_raw, d.B, d.na, 128, EPI_BIAS, P + L.mean_b, st);
-  linear_fwd<float, float, float>(c.h2, P + L.lstd_w, c.lstd_raw, d.B, d.na, 128, EPI_BIAS, P + L.lstd_b, st);
+  {  // fc1 -> relu -> fc2 -> relu -> (mean_linear | log_std_linear), one launch
+    heads::FwdArgs h;
+    memset(&h, 0, sizeof(h));
+    h.nheads = 1; h.B = d.B; h.K1 = d.D; h.K2 = 0; h.H2 = 128; h.NOa = d.na; h.NOb = d.na;
+    h.x1 = c.t.z;
+    h.w[0] = heads::HeadW{P + L.fc1_w, P + L.fc1_b, P + L.fc2_w, P + L.fc2_b, P + L.mean_w, P + L.mean_b,
+                          P + L.lstd_w, P + L.lstd_b, c.h1, c.h2, c.mean_raw, c.lstd_raw};
+    heads::launch_fwd(h, st);
+  }
   SampleArgs s;
   s.B = d.B; s.na = d.na;
   s.mean = c.mean_raw; s.lstd_raw = c.lstd_raw;
@@ -502,25 +544,27 @@ static void actor_backward(const dgvit_net& net, const dgvit_layout& L, const Di
   s.d_mean_out = c.dmean; s.d_lstd_out = c.dlstd;
   actor_sample_bwd_kernel<<<(unsigned)cdiv((int64_t)d.B * d.na, 128), 128, 0, st>>>(s);
   DG_LAUNCH_CHECK();
-  float* part = c.t.partial;
-  linear_bwd_w<float, float>(c.dmean, c.h2, G + L.mean_w, G + L.mean_b, d.B, d.na, 128, part, st);
-  linear_bwd_w<float, float>(c.dlstd, c.h2, G + L.lstd_w, G + L.lstd_b, d.B, d.na, 128, part, st);
-  linear_bwd_x<float, float, float>(c.dmean, P + L.mean_w, c.dh2, d.B, d.na, 128, EPI_NONE, nullptr, 0, st);
-  linear_bwd_x<float, float, float>(c.dlstd, P + L.lstd_w, c.dh2, d.B, d.na, 128, EPI_BIAS_RESID, nullptr, 0, st, -1,
-                                    c.dh2);
   {
-    const int64_t n = (int64_t)d.B * 128;
-    relu_mask_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(c.dh2, c.h2, n);
-    DG_LAUNCH_CHECK();
+    heads::BwdArgs h;
+    memset(&h, 0, sizeof(h));
+    h.nheads = 1; h.B = d.B; h.K0 = d.D; h.H2 = 128; h.NOa = d.na; h.NOb = d.na;
+    h.h[0] = heads::BwdHead{P + L.fc1_w, P + L.fc2_w, P + L.mean_w, P + L.lstd_w, c.h1, c.h2, c.dmean, c.dlstd,
+                            c.dh1, c.dh2, c.t.dz};
+    heads::launch_bwd_dx(h, st);
+    heads::DwList dw(d.B);
+    dw.add(c.dmean, d.na, c.h2, G + L.mean_w, G + L.mean_b, d.na, 128);
+    dw.add(c.dlstd, d.na, c.h2, G + L.lstd_w, G + L.lstd_b, d.na, 128);
+    dw.add(c.dh2, 128, c.h1, G + L.fc2_w, G + L.fc2_b, 128, 128);
+    dw.add(c.dh1, 128, c.t.z, G + L.fc1_w, G + L.fc1_b, 128, d.D);
+    dw.launch(st);
   }
-  linear_bwd_w<float, float>(c.dh2, c.h1, G + L.fc2_w, G + L.fc2_b, d.B, 128, 128, part, st);
-  linear_bwd_x<float, float, float>(c.dh2, P + L.fc2_w, c.dh1, d.B, 128, 128, EPI_RELU_BWD, c.h1, 128, st);
-  linear_bwd_w<float, float>(c.dh1, c.t.z, G + L.fc1_w, G + L.fc1_b, d.B, 128, d.D, part, st);
-  linear_bwd_x<float, float, float>(c.dh1, P + L.fc1_w, c.t.dz, d.B, 128, d.D, EPI_NONE, nullptr, 0, st);
   const DropDev drop = make_drop(io.drop, d, io.sample_offset);
   trunk_backward<A>(net, L, d, drop, c.t, /*relu_tok=*/0, st);
-  // fc_embed: dW[D,nps] = dtok^T pstate ; db = colsum(dtok)
-  linear_bwd_w<float, float>(c.t.dtok, io.pstate, G + L.embed_w, G + L.embed_b, d.B, d.D, d.nps, part, st);
+  {  // fc_embed: dW[D,nps] = dtok^T pstate ; db = colsum(dtok)
+    heads::DwList dw(d.B);
+    dw.add(c.t.dtok, d.D, io.pstate, G + L.embed_w, G + L.embed_b, d.D, d.nps);
+    dw.launch(st);
+  }
 }
 
 // ------------------------------------------------------------------ critic
@@ -528,7 +572,7 @@ template <typename A>
 struct CriticCtx {
   TrunkCtx<A> t;
   float *xcat, *h1a, *h2a, *h1b, *h2b;  // [B,D+na] [B,128] [B,32] x2
-  float *dh2, *dh1, *dxa, *dxb;
+  float *dh2, *dh1, *dh2b, *dh1b, *dxa, *dxb;
 };
 template <typename A>
 static void carve_critic(Carver& cv, const Dims& d, bool save, CriticCtx<A>& c) {
@@ -540,6 +584,8 @@ static void carve_critic(Carver& cv, const Dims& d, bool save, CriticCtx<A>& c) 
   c.h2b = cv.take<float>((int64_t)d.B * 32);
   c.dh2 = cv.take<float>((int64_t)d.B * 32);
   c.dh1 = cv.take<float>((int64_t)d.B * 128);
+  c.dh2b = cv.take<float>((int64_t)d.B * 32);
+  c.dh1b = cv.take<float>((int64_t)d.B * 128);
   c.dxa = cv.take<float>((int64_t)d.B * (d.D + d.na));
   c.dxb = cv.take<float>((int64_t)d.B * (d.D + d.na));
 }
@@ -548,15 +594,15 @@ static void critic_heads_forward(const dgvit_net& net, const dgvit_layout& L, co
                                  const float* action, float* xcat, float* h1a, float* h2a, float* h1b, float* h2b,
                                  float* q1, float* q2, cudaStream_t st) {
   const float* P = net.params;
-  const int W = d.D + d.na;
-  concat_za_kernel<<<(unsigned)cdiv((int64_t)d.B * W, 256), 256, 0, st>>>(z, action, xcat, d.B, d.D, d.na);
-  DG_LAUNCH_CHECK();
-  linear_fwd<float, float, float>(xcat, P + L.fc1_w, h1a, d.B, 128, W, EPI_BIAS_RELU, P + L.fc1_b, st);
-  linear_fwd<float, float, float>(h1a, P + L.fc2_w, h2a, d.B, 32, 128, EPI_BIAS_RELU, P + L.fc2_b, st);
-  linear_fwd<float, float, float>(h2a, P + L.fc3_w, q1, d.B, d.na, 32, EPI_BIAS, P + L.fc3_b, st);
-  linear_fwd<float, float, float>(xcat, P + L.fc11_w, h1b, d.B, 128, W, EPI_BIAS_RELU, P + L.fc11_b, st);
-  linear_fwd<float, float, float>(h1b, P + L.fc21_w, h2b, d.B, 32, 128, EPI_BIAS_RELU, P + L.fc21_b, st);
-  linear_fwd<float, float, float>(h2b, P + L.fc31_w, q2, d.B, d.na, 32, EPI_BIAS, P + L.fc31_b, st);
+  heads::FwdArgs h;
+  memset(&h, 0, sizeof(h));
+  h.nheads = 2; h.B = d.B; h.K1 = d.D; h.K2 = d.na; h.H2 = 32; h.NOa = d.na; h.NOb = 0;
+  h.x1 = z; h.x2 = action; h.xcat = xcat;
+  h.w[0] = heads::HeadW{P + L.fc1_w, P + L.fc1_b, P + L.fc2_w, P + L.fc2_b, P + L.fc3_w, P + L.fc3_b, nullptr, nullptr,
+                        h1a, h2a, q1, nullptr};
+  h.w[1] = heads::HeadW{P + L.fc11_w, P + L.fc11_b, P + L.fc21_w, P + L.fc21_b, P + L.fc31_w, P + L.fc31_b, nullptr,
+                        nullptr, h1b, h2b, q2, nullptr};
+  heads::launch_fwd(h, st);
 }
 
 template <typename A>
@@ -572,32 +618,34 @@ static void critic_forward(const dgvit_net& net, const dgvit_layout& L, const Di
   critic_heads_forward(net, L, d, c.t.z, io.action, c.xcat, c.h1a, c.h2a, c.h1b, c.h2b, io.q1, io.q2, st);
 }
 
-// one Q head backward; dq [B,na] -> dx [B,W]; optionally parameter grads
-static void critic_head_backward(const dgvit_net& net, const Dims& d, const float* dq, const float* xcat,
-                                 const float* h1, const float* h2, int64_t w1, int64_t b1, int64_t w2, int64_t b2,
-                                 int64_t w3, int64_t b3, float* dh2, float* dh1, float* dx, bool param_grads,
-                                 float* part, cudaStream_t st) {
-  const float* P = net.params;
-  float* G = net.grads;
-  const int W = d.D + d.na;
-  if (param_grads) linear_bwd_w<float, float>(dq, h2, G + w3, G + b3, d.B, d.na, 32, part, st);
-  linear_bwd_x<float, float, float>(dq, P + w3, dh2, d.B, d.na, 32, EPI_RELU_BWD, h2, 32, st);
-  if (param_grads) linear_bwd_w<float, float>(dh2, h1, G + w2, G + b2, d.B, 32, 128, part, st);
-  linear_bwd_x<float, float, float>(dh2, P + w2, dh1, d.B, 32, 128, EPI_RELU_BWD, h1, 128, st);
-  if (param_grads) linear_bwd_w<float, float>(dh1, xcat, G + w1, G + b1, d.B, 128, W, part, st);
-  linear_bwd_x<float, float, float>(dh1, P + w1, dx, d.B, 128, W, EPI_NONE, nullptr, 0, st);
-}
-
 template <typename A>
 static void critic_backward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const dgvit_critic_io& io,
                             int64_t sample_offset, const float* dq1, const float* dq2, float* d_action,
                             bool param_grads, CriticCtx<A>& c, float* part_fallback, cudaStream_t st) {
-  float* part = c.t.partial ? c.t.partial : part_fallback;
+  const float* P = net.params;
+  float* G = net.grads;
+  (void)part_fallback;
   if (param_grads) zero_unused_grads(net, L, st);
-  critic_head_backward(net, d, dq1, c.xcat, c.h1a, c.h2a, L.fc1_w, L.fc1_b, L.fc2_w, L.fc2_b, L.fc3_w, L.fc3_b, c.dh2,
-                       c.dh1, c.dxa, param_grads, part, st);
-  critic_head_backward(net, d, dq2, c.xcat, c.h1b, c.h2b, L.fc11_w, L.fc11_b, L.fc21_w, L.fc21_b, L.fc31_w, L.fc31_b,
-                       c.dh2, c.dh1, c.dxb, param_grads, part, st);
+  {
+    heads::BwdArgs h;
+    memset(&h, 0, sizeof(h));
+    h.nheads = 2; h.B = d.B; h.K0 = d.D + d.na; h.H2 = 32; h.NOa = d.na; h.NOb = 0;
+    h.h[0] = heads::BwdHead{P + L.fc1_w, P + L.fc2_w, P + L.fc3_w, nullptr, c.h1a, c.h2a, dq1, nullptr, c.dh1, c.dh2, c.dxa};
+    h.h[1] = heads::BwdHead{P + L.fc11_w, P + L.fc21_w, P + L.fc31_w, nullptr, c.h1b, c.h2b, dq2, nullptr, c.dh1b, c.dh2b,
+                            c.dxb};
+    heads::launch_bwd_dx(h, st);
+    if (param_grads) {
+      const int W = d.D + d.na;
+      heads::DwList dw(d.B);
+      dw.add(dq1, d.na, c.h2a, G + L.fc3_w, G + L.fc3_b, d.na, 32);
+      dw.add(c.dh2, 32, c.h1a, G + L.fc2_w, G + L.fc2_b, 32, 128);
+      dw.add(c.dh1, 128, c.xcat, G + L.fc1_w, G + L.fc1_b, 128, W);
+      dw.add(dq2, d.na, c.h2b, G + L.fc31_w, G + L.fc31_b, d.na, 32);
+      dw.add(c.dh2b, 32, c.h1b, G + L.fc21_w, G + L.fc21_b, 32, 128);
+      dw.add(c.dh1b, 128, c.xcat, G + L.fc11_w, G + L.fc11_b, 128, W);
+      dw.launch(st);
+    }
+  }
   const int W = d.D + d.na;
   split_dza_kernel<<<(unsigned)cdiv((int64_t)d.B * W, 256), 256, 0, st>>>(c.dxa, c.dxb, param_grads ? c.t.dz : nullptr,
                                                                           d_action, d.B, d.D, d.na);
@@ -605,8 +653,9 @@ static void critic_backward(const dgvit_net& net, const dgvit_layout& L, const D
   if (param_grads) {
     const DropDev drop = make_drop(io.drop, d, sample_offset);
     trunk_backward<A>(net, L, d, drop, c.t, /*relu_tok=*/1, st);
-    linear_bwd_w<float, float>(c.t.dtok, io.pstate, net.grads + L.embed_w, net.grads + L.embed_b, d.B, d.D, d.nps, part,
-                               st);
+    heads::DwList dw(d.B);
+    dw.add(c.t.dtok, d.D, io.pstate, G + L.embed_w, G + L.embed_b, d.D, d.nps);
+    dw.launch(st);
   }
 }
 

@@ -402,6 +402,17 @@ __global__ void pool_rmsnorm_bwd_kernel(const float* __restrict__ X, const float
   }
 }
 
+// dX[b, n, :] = (n == 0) ? dXc[b, :] : 0     (last block: only token 0 carries gradient)
+__global__ void scatter_row0_kernel(const float* __restrict__ dXc, float* __restrict__ dX, int64_t total, int N,
+                                    int D) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const int64_t bn = i / D;
+    dX[i] = (bn % N == 0) ? dXc[(bn / N) * D + d] : 0.f;
+  }
+}
+
 // =====================================================================================
 // Actor head tail: tanh-Gaussian sample + log-prob (vn/got_sac_network.py:235,238-251)
 // =====================================================================================
