@@ -158,9 +158,9 @@ static void linear_bwd_w(const TA* dy, const TB* x, float* dW, float* db, int64_
   g.splitk = pick_splitk(R); g.partial = partial;
   gemm<TA, TB, float>(g, st);
   if (db) {
-    const int S = (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 64);    // row ranges per column block
+    const int S = (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 128);   // row ranges per column block
     const int64_t rpb = cdiv(R, S);
-    dim3 grid((unsigned)cdiv(N, 128), (unsigned)S);
+    dim3 grid((unsigned)cdiv(N, 256), (unsigned)S);
     colsum_partial_kernel<TA><<<grid, 128, 0, st>>>(dy, ldy, partial, R, N, rpb);
     DG_LAUNCH_CHECK();
     reduce_partials_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(partial, db, S, N);
@@ -283,7 +283,7 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
                           const float* gamma, float* dX_io, bf16* dX_lp, float* dgamma, float* dbeta,
                           float* partial, int64_t T, int D, cudaStream_t st) {
   const int wpb = 8;
-  int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 8);
+  int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 4);
   const size_t smem = (size_t)wpb * 2 * D * sizeof(float);
   switch (D / 32) {
 #define LNB(V) case V: layernorm_bwd_kernel<V><<<nblocks, wpb * 32, smem, st>>>(dY, X, mean, rstd, gamma, dX_io, dX_lp, partial, T); break;
@@ -292,7 +292,7 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
     default: fail(DGVIT_ERR_ARG, "unsupported dim %d", D);
   }
   DG_LAUNCH_CHECK();
-  ln_param_reduce_kernel<<<(unsigned)cdiv(2 * D, 32), 256, 0, st>>>(partial, dgamma, dbeta, nblocks, D);
+  ln_param_reduce_kernel<<<(unsigned)cdiv(2 * D, 32), 1024, 0, st>>>(partial, dgamma, dbeta, nblocks, D);
   DG_LAUNCH_CHECK();
 }
 
@@ -397,7 +397,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
   DG_LAUNCH_CHECK();
   {  // dg = sum_b dg_rows
     const int S = pick_splitk(d.B);
-    dim3 grid((unsigned)cdiv(d.D, 128), (unsigned)S);
+    dim3 grid((unsigned)cdiv(d.D, 256), (unsigned)S);
     colsum_partial_kernel<float><<<grid, 128, 0, st>>>(c.dg_rows, d.D, c.partial, d.B, d.D, cdiv(d.B, S));
     DG_LAUNCH_CHECK();
     reduce_partials_kernel<<<1, 256, 0, st>>>(c.partial, G + L.rms_g, S, d.D);

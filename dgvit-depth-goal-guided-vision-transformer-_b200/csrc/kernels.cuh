@@ -176,36 +176,66 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dY, const float* 
 }
 
 // dgamma[d] = sum_blocks part[b][0][d], dbeta[d] = sum_blocks part[b][1][d]
-// block = 32 columns x 8 row-groups; fixed summation order (deterministic)
-__global__ void ln_param_reduce_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int nblocks, int D) {
-  __shared__ float sm[8][33];
+// block = 32 columns x 32 row-groups (1024 threads); fixed summation order (deterministic)
+__global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* __restrict__ part,
+                                                               float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, int nblocks, int D) {
+  __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + cx;
-  float s = 0.f;
-  if (j < 2 * D)
-    for (int b = gy; b < nblocks; b += 8) s += part[(int64_t)b * 2 * D + j];
-  sm[gy][cx] = s;
+  float s0 = 0.f, s1 = 0.f;
+  if (j < 2 * D) {
+    int b = gy;
+    for (; b + 32 < nblocks; b += 64) {
+      s0 += part[(int64_t)b * 2 * D + j];
+      s1 += part[(int64_t)(b + 32) * 2 * D + j];
+    }
+    if (b < nblocks) s0 += part[(int64_t)b * 2 * D + j];
+  }
+  sm[gy][cx] = s0 + s1;
   __syncthreads();
   if (gy == 0 && j < 2 * D) {
     float t = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) t += sm[g][cx];
+    for (int g = 0; g < 32; ++g) t += sm[g][cx];
     if (j < D) dgamma[j] = t; else dbeta[j - D] = t;
   }
 }
 
-// column sums (bias gradients): part[s][n] = sum over this block's row range
+// column sums (bias gradients): part[s][n] = sum over this block's row range.
+// thread = 2 adjacent columns (4-byte bf16x2 / 8-byte float2 loads), 4 row-interleaved accumulators.
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld2(const bf16* p) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
 template <typename T_>
 __global__ void colsum_partial_kernel(const T_* __restrict__ A, int64_t lda, float* __restrict__ part,
                                       int64_t rows, int N, int64_t rows_per_block) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (n >= N) return;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
-  float s = 0.f;
-  for (int64_t r = r0; r < r1; ++r) s += ldf(A + r * lda + n);
-  part[(int64_t)blockIdx.y * N + n] = s;
+  const bool pair = (n + 1 < N) && ((lda & 1) == 0) && ((((uintptr_t)A) & 7) == 0);
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;
+  if (pair) {
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {
+      const float2 x0 = ld2(A + r * lda + n), x1 = ld2(A + (r + 1) * lda + n);
+      const float2 x2 = ld2(A + (r + 2) * lda + n), x3 = ld2(A + (r + 3) * lda + n);
+      a0 += x0.x; a1 += x0.y; b0 += x1.x; b1 += x1.y; c0 += x2.x; c1 += x2.y; d0 += x3.x; d1 += x3.y;
+    }
+    for (; r < r1; ++r) { const float2 x = ld2(A + r * lda + n); a0 += x.x; a1 += x.y; }
+    part[(int64_t)blockIdx.y * N + n] = (a0 + b0) + (c0 + d0);
+    part[(int64_t)blockIdx.y * N + n + 1] = (a1 + b1) + (c1 + d1);
+  } else {
+    for (int64_t r = r0; r < r1; ++r) {
+      a0 += ldf(A + r * lda + n);
+      if (n + 1 < N) a1 += ldf(A + r * lda + n + 1);
+    }
+    part[(int64_t)blockIdx.y * N + n] = a0;
+    if (n + 1 < N) part[(int64_t)blockIdx.y * N + n + 1] = a1;
+  }
 }
 
 // =====================================================================================
