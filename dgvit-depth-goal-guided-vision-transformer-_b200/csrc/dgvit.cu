@@ -17,6 +17,7 @@
 #ifdef DGVIT_WITH_TC
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
+#include "mlp_tc.cuh"
 #endif
 
 namespace dgvit {
@@ -191,6 +192,7 @@ struct TrunkCtx {
   bf16* dXh;  // bf16 copy of dX (operand of the tensor-core GEMMs); null in the fp32 path
   float* dXc; bf16* dXch;   // last block: compact [B, D] residual gradient of the token-0 rows
   size_t partial_floats;
+  bool save;   // activations kept for a backward pass
   // residual-stream gradient in the operand dtype
   const A* dx_op() const {
     if constexpr (std::is_same<A, float>::value) return dX; else return dXh;
@@ -202,6 +204,7 @@ struct TrunkCtx {
 
 template <typename A>
 static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
+  c.save = save;
   c.Pm = cv.take<A>((int64_t)d.B * d.P * d.pd);
   c.Xp = cv.take<float>((int64_t)d.B * d.P * d.D);
   c.tok = cv.take<float>((int64_t)d.B * d.D);
@@ -335,6 +338,17 @@ static void launch_attention_bwd(const A* QKV, const A* O, const A* dO, A* dQKV,
   DG_LAUNCH_CHECK();
 }
 
+// the fused tcgen05 MLP (mlp_tc.cuh) replaces fc1 -> GELU -> fc2 (+residual) when eligible;
+// forward and backward must take the same decision (the fused forward saves only the pre-activation)
+template <typename A>
+static bool mlp_fused(const Dims& d, int64_t R, const void* xn2, const void* w1, const void* w2, const float* resid,
+                      const float* out) {
+#ifdef DGVIT_WITH_TC
+  if constexpr (std::is_same<A, bf16>::value) return mlp::eligible(d.D, d.M, R, xn2, w1, w2, resid, d.D, out, d.D);
+#endif
+  return false;
+}
+
 // ------------------------------------------------------------------ trunk forward
 // GoT.forward (vn/GoalFormer.py:156-171) given the goal token tok[B,D]; writes c.z.
 template <typename A>
@@ -374,10 +388,20 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
     // MLP block: x = ff(LN(x)) + x
     launch_ln_fwd<A>(B_.Xm, P + b.ln2_w, P + b.ln2_b, B_.Xn2, B_.mean2, B_.rstd2, R, d.D, st);
     TagScope mlp_tag(PROF_GEMM_MLP);
-    linear_fwd<A, A, A>(B_.Xn2, WSel<A>::w(net, b.fc1_w), B_.Hpre, R, d.M, d.D, EPI_BIAS_GELU2, P + b.fc1_b, st,
-                        nullptr, B_.Hact);
-    linear_fwd<A, A, float>(B_.Hact, WSel<A>::w(net, b.fc2_w), Xnext, R, d.D, d.M, EPI_BIAS_RESID, P + b.fc2_b, st,
-                            B_.Xm);
+    if (mlp_fused<A>(d, R, B_.Xn2, WSel<A>::w(net, b.fc1_w), WSel<A>::w(net, b.fc2_w), B_.Xm, Xnext)) {
+#ifdef DGVIT_WITH_TC
+      if constexpr (std::is_same<A, bf16>::value) {
+        ProfScope ps(PROF_GEMM_MLP, 4.0 * R * d.D * d.M, 0.0, st);
+        mlp::fwd(B_.Xn2, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), P + b.fc2_b, B_.Xm, d.D, Xnext,
+                 d.D, c.save ? B_.Hpre : nullptr, R, d.M, st);
+      }
+#endif
+    } else {
+      linear_fwd<A, A, A>(B_.Xn2, WSel<A>::w(net, b.fc1_w), B_.Hpre, R, d.M, d.D, EPI_BIAS_GELU2, P + b.fc1_b, st,
+                          nullptr, B_.Hact);
+      linear_fwd<A, A, float>(B_.Hact, WSel<A>::w(net, b.fc2_w), Xnext, R, d.D, d.M, EPI_BIAS_RESID, P + b.fc2_b, st,
+                              B_.Xm);
+    }
   }
   // c.Xout is compact [B, D] (token-0 rows of the last block)
   pool_rmsnorm_fwd_kernel<<<(unsigned)cdiv(d.B, 8), 256, 0, st>>>(c.Xout, P + L.rms_g, c.z, d.B, 1, d.D,
@@ -415,8 +439,19 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     // ---- MLP block.  dXr = dL/dX_out
     {
     TagScope mlp_tag(PROF_GEMM_MLP);
+    {
+      // the fused forward kept only the pre-activation: the dH epilogue re-materialises gelu(Hpre) for dW2
+      float* Xn_out = (l + 1 < d.L) ? c.L[l + 1].Xa : c.Xout;
+      const bool fused = mlp_fused<A>(d, R, B_.Xn2, WSel<A>::w(net, b.fc1_w), WSel<A>::w(net, b.fc2_w), B_.Xm, Xn_out);
+      GemmArgs g;
+      g.M = (int)R; g.N = d.M; g.K = d.D;
+      g.A = dxop; g.a_sm = d.D; g.a_sk = 1;
+      g.B = WSel<A>::w(net, b.fc2_w); g.b_sk = d.M; g.b_sn = 1;
+      g.C = c.dH; g.ldc = d.M;
+      g.epi = fused ? EPI_GELU_BWD2 : EPI_GELU_BWD; g.aux = B_.Hpre; g.ldaux = d.M; g.C2 = B_.Hact;
+      gemm<A, A, A>(g, st);
+    }
     linear_bwd_w<A, A>(dxop, B_.Hact, G + b.fc2_w, G + b.fc2_b, R, d.D, d.M, c.partial, st);
-    linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.fc2_w), c.dH, R, d.D, d.M, EPI_GELU_BWD, B_.Hpre, d.M, st);
     linear_bwd_w<A, A>(c.dH, B_.Xn2, G + b.fc1_w, G + b.fc1_b, R, d.M, d.D, c.partial, st);
     linear_bwd_x<A, A, float>(c.dH, WSel<A>::w(net, b.fc1_w), c.dXn, R, d.M, d.D, EPI_NONE, nullptr, 0, st);
     }

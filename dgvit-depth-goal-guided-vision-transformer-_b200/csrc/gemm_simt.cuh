@@ -16,7 +16,8 @@ enum {
   EPI_BIAS_GELU2,  // C = acc + bias[n] ; C2 = gelu(C)
   EPI_BIAS_RESID,  // C(f32) = acc + (bias ? bias[n] : 0) + resid[m,n]   (resid may alias C)
   EPI_GELU_BWD,    // C = acc * gelu'(aux[m,n])
-  EPI_RELU_BWD     // C = acc * (auxf[m,n] > 0)
+  EPI_RELU_BWD,    // C = acc * (auxf[m,n] > 0)
+  EPI_GELU_BWD2    // C = acc * gelu'(aux[m,n]) ; C2 = gelu(aux[m,n])   (recomputes the activation for dW)
 };
 
 struct GemmArgs {
@@ -133,6 +134,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
         case EPI_BIAS_RESID: v += (g.bias ? g.bias[n] : 0.f) + g.resid[(int64_t)m * g.ldr + n]; break;
         case EPI_GELU_BWD: v *= gelu_grad_f(ldf((const TC*)g.aux + (int64_t)m * g.ldaux + n)); break;
         case EPI_RELU_BWD: v = ((const float*)g.aux)[(int64_t)m * g.ldaux + n] > 0.f ? v : 0.f; break;
+        case EPI_GELU_BWD2: {
+          const float x = ldf((const TC*)g.aux + (int64_t)m * g.ldaux + n);
+          v *= gelu_grad_f(x);
+          stf((TC*)g.C2 + (int64_t)m * g.ldc + n, gelu_f(x));
+        } break;
       }
       stf(C + (int64_t)m * g.ldc + n, v);
     }

@@ -353,7 +353,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // coalesced path: bf16 output, 16-byte aligned rows
       const bool can_stage = std::is_same<TC, bf16>::value && !partial_out && (g.ldc % 8 == 0) &&
                              (((uintptr_t)g.C & 15) == 0) && (g.epi != EPI_BIAS_GELU2 || ((uintptr_t)g.C2 & 15) == 0) &&
-                             (g.epi != EPI_GELU_BWD || ((g.ldaux % 8 == 0) && (((uintptr_t)g.aux & 15) == 0)));
+                             ((g.epi != EPI_GELU_BWD && g.epi != EPI_GELU_BWD2) ||
+                              ((g.ldaux % 8 == 0) && (((uintptr_t)g.aux & 15) == 0))) &&
+                             (g.epi != EPI_GELU_BWD2 || ((uintptr_t)g.C2 & 15) == 0);
       // lane <-> (row, 16-byte piece) mapping of the coalesced phase: 4 lanes per 64-byte row segment
       const int rr0 = lane >> 2, c16 = lane & 3;
       auto stage_store = [&](const float (&v)[32], bf16* Cb, int col) {
@@ -459,6 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             break;
+          case EPI_GELU_BWD2:
           case EPI_GELU_BWD: {
             float xin[32];
             if (staged) {
@@ -471,7 +474,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { float y, dy; gelu_fast(xin[i], y, dy); v[i] *= dy; }
+            for (int i = 0; i < 32; ++i) { float y, dy; gelu_fast(xin[i], y, dy); v[i] *= dy; xin[i] = y; }
+            if (g.epi == EPI_GELU_BWD2) {       // second output: the recomputed activation gelu(x)
+              if (staged) {
+                if constexpr (std::is_same<TC, bf16>::value) stage_store(xin, (bf16*)g.C2, col);
+              } else if (row_ok) {
+                store_row32<TC>((TC*)g.C2 + (int64_t)row * g.ldc + col, xin, nvalid);
+              }
+            }
           } break;
           case EPI_RELU_BWD:
             if (row_ok) {
