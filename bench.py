@@ -126,6 +126,25 @@ def cpu_update_rate(budget_s: float, batch: int, max_steps: int, warmup: int = 1
     return batch * n / dt, cores, f"{n} update step(s) of batch {batch} (+{warmup} warm-up), fp32, torch CPU {cores} threads", dt / n * 1e3
 
 
+def cpu_act_latency(calls: int = 60):
+    """p50 of the oracle's batch-1 actor sample on the host cores (reference GoTPolicy.choose_action path)."""
+    from oracle import dgvit_oracle as O
+    from oracle.init_params import reference_init
+    cfg = O.Cfg(dim=PRESET["l_f_size"], depth=PRESET["block"], heads=PRESET["head"])
+    p = reference_init("actor", cfg, SEED)
+    img, goal, eps = torch.rand(1, 128, 160), torch.rand(1, 2), torch.randn(1, 2)
+    mask = torch.ones(1, cfg.n_tokens, cfg.dim)
+    ts = []
+    with torch.no_grad():
+        for i in range(calls + 10):
+            t0 = time.perf_counter()
+            O.actor_sample(p, img, goal, eps, cfg, mask)
+            if i >= 10:
+                ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return ts[len(ts) // 2] * 1e3
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -264,6 +283,28 @@ def run_ours(args):
     e2e_value = B * world * args.steps / (float(t.item()) / 1e3)
     barrier()
 
+    # ---------------- batch-1 act latency (BASELINE metric, second half): numpy in -> numpy out
+    act = None
+    if rank == 0:
+        import numpy as np
+        rs = np.random.RandomState(SEED)
+        frame = rs.rand(128, 160, 1).astype(np.float32)
+        goal = np.array([0.4, -0.3], dtype=np.float32)
+        act = {}
+        for name, ev in (("evaluate", True), ("sample", False)):
+            for _ in range(100):
+                ag.choose_action(frame, goal, ev)
+            ts = []
+            for _ in range(1000):
+                t0 = time.perf_counter()
+                ag.choose_action(frame, goal, ev)
+                ts.append(time.perf_counter() - t0)
+            ts.sort()
+            act[name] = dict(p50_ms=ts[500] * 1e3, p99_ms=ts[990] * 1e3)
+        act["calls"] = 1000
+        act["path"] = "SAC.choose_action: pinned host frame -> CUDA graph (H2D, actor forward, D2H) -> sync"
+    barrier()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -281,7 +322,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, sample, _ = cpu_update_rate(12.0, B, 3, warmup=1)
-        cpu = dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample)
+        cpu = dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample, act_p50_ms=cpu_act_latency())
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -294,7 +335,7 @@ def run_ours(args):
                                % (ag.replay_buffer.obs.numel() * 4 / 1e9)),
                 roofline=roof, whole_step=whole, cpu_baseline=cpu,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=16),
-                gpu_launches=int(launches), clocks=clocks, losses=losses)
+                act_latency=act, gpu_launches=int(launches), clocks=clocks, losses=losses)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -12,6 +12,7 @@ Public surface (mirrors the reference):
 from .modules import GoT, GoTPolicy, GoTQNetwork, set_seed, weights_init_   # noqa: F401
 from .agent import SAC, ReplayStore                                        # noqa: F401
 from .ops import soft_update, hard_update, depth_augment                   # noqa: F401
+from . import parallel                                                     # noqa: F401
 from . import _lib                                                         # noqa: F401
 
 __all__ = ["GoT", "GoTPolicy", "GoTQNetwork", "SAC", "ReplayStore", "soft_update", "hard_update",

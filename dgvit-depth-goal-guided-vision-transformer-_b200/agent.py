@@ -16,6 +16,7 @@ import torch
 
 from . import _lib as L
 from .modules import GoTPolicy, GoTQNetwork, set_seed, _stream
+from .parallel import allreduce_sum_
 
 
 # --------------------------------------------------------------------------- replay store
@@ -239,15 +240,14 @@ class SAC(object):
             L.check(lib.dgvit_sac_update(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
                     "sac_update")
         else:
-            dist = torch.distributed
             L.check(lib.dgvit_sac_phase1(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
                     "sac_phase1")
-            dist.all_reduce(self.critic._garena)
+            allreduce_sum_(self.critic._garena)
             L.check(lib.dgvit_sac_phase2(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
                     "sac_phase2")
-            dist.all_reduce(self.policy._garena)
+            allreduce_sum_(self.policy._garena)
             L.check(lib.dgvit_sac_phase3(C.byref(s), B, ws.data_ptr(), ws.numel(), st), "sac_phase3")
-            dist.all_reduce(self._losses)
+            allreduce_sum_(self._losses)
         self.itera += 1
         return self._losses
 

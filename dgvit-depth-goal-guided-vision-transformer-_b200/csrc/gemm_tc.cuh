@@ -607,7 +607,7 @@ static bool gemm_tc_try(const GemmArgs& g0, cudaStream_t st) {
       g.B = a; g.b_sk = a_sk; g.b_sn = a_sm;
       trans_out = 1;
     }
-    if (g.M < 128 || g.K < 16) return false;
+    if (g.M < 32 || g.K < 16) return false;                // tiny head-sized problems stay on CUDA cores
     const bool a_mn = (g.a_sm == 1 && g.a_sk != 1), b_mn = (g.b_sn == 1 && g.b_sk != 1);
     const bool a_k = (g.a_sk == 1), b_k = (g.b_sk == 1);
     if (!(a_mn || a_k) || !(b_mn || b_k)) return false;

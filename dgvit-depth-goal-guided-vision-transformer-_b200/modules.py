@@ -174,6 +174,7 @@ class _ArenaModule(nn.Module):
         self._ws_cache: Dict = {}
         self._noise_fifo: List[dict] = []
         self._rng_state = None
+        self._act_state = None
         self.precision = "fp32"  # "fp32" | "bf16"
 
     # ---- layout
@@ -221,6 +222,7 @@ class _ArenaModule(nn.Module):
         self._shadow = torch.zeros(lay.total, dtype=torch.bfloat16, device=dev)
         self._ws_cache = {}
         self._rng_state = None
+        self._act_state = None
         return self
 
     def net_struct(self) -> L.Net:
@@ -284,6 +286,17 @@ class _ArenaModule(nn.Module):
         if istate.dim() != 3 or istate.shape[1] != c.img_h or istate.shape[2] != c.img_w:
             raise ValueError(f"istate must be [B,{c.img_h},{c.img_w}], got {tuple(istate.shape)}")
         return istate.to(self._arena.device, torch.float32).contiguous()
+
+    def __deepcopy__(self, memo):
+        # CUDA graphs / events / cached workspaces are per-instance runtime state, not model state
+        import copy as _copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        skip = {"_act_state": None, "_ws_cache": {}, "_noise_fifo": [], "_rng_state": None}
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = skip[k] if k in skip else _copy.deepcopy(v, memo)
+        return new
 
     # nn.Module plumbing: .to()/.cuda()/.float() replace p.data -> arenas are re-bound lazily
     def _apply(self, fn, *a, **k):
@@ -412,16 +425,74 @@ class GoTPolicy(_ArenaModule):
         return action, log_prob, mean_t
 
     def choose_action(self, istate, pstate, evaluate=False):
-        """numpy (H,W,1) frame + (2,) goal -> numpy action (vn/got_sac_network.py:205-220)."""
-        if istate.ndim < 4:
-            istate = torch.as_tensor(np.asarray(istate), dtype=torch.float32).permute(2, 0, 1)
-            pstate = torch.as_tensor(np.asarray(pstate), dtype=torch.float32).unsqueeze(0)
-        else:
+        """numpy (H,W,1) frame + (2,) goal -> numpy action (vn/got_sac_network.py:205-220).
+
+        Batch-1 control-loop path: pinned host staging -> one CUDA graph (H2D, the whole actor
+        forward, D2H) -> one stream synchronise.  ``evaluate=True`` returns tanh(mean)."""
+        istate = np.asarray(istate)
+        if istate.ndim >= 4:
             raise ValueError("4-D (frame-stacked) observations are a legacy path the DGViT trunk rejects")
-        with torch.no_grad():
-            action, _, mean_t = self.sample([istate, pstate])
-        out = mean_t if evaluate else action
-        return out.detach().squeeze(0).cpu().numpy()
+        self.bind()
+        _require_cuda(self._arena)
+        c = self._cfg
+        st = self._act_state
+        key = (self._arena.data_ptr(), self.training, self.precision)
+        if st is None or st["key"] != key:
+            st = self._build_act_graph(key)
+        st["img_host"].numpy()[...] = istate.reshape(1, c.img_h, c.img_w)
+        st["ps_host"].numpy()[...] = np.asarray(pstate, dtype=np.float32).reshape(1, c.n_pstate)
+        st["graph"].replay()
+        st["done"].record()
+        st["done"].synchronize()
+        out = st["mean_t_host"] if evaluate else st["action_host"]
+        return out.numpy()[0].copy()
+
+    def _build_act_graph(self, key):
+        c = self._cfg
+        dev = self._arena.device
+        na = c.n_act
+        f32 = dict(dtype=torch.float32)
+        st = dict(key=key,
+                  img_host=torch.zeros(1, c.img_h, c.img_w, **f32).pin_memory(),
+                  ps_host=torch.zeros(1, c.n_pstate, **f32).pin_memory(),
+                  action_host=torch.zeros(1, na, **f32).pin_memory(), mean_t_host=torch.zeros(1, na, **f32).pin_memory(),
+                  img=torch.zeros(1, c.img_h, c.img_w, device=dev, **f32), ps=torch.zeros(1, c.n_pstate, device=dev, **f32),
+                  mean=torch.zeros(1, na, device=dev, **f32), log_std=torch.zeros(1, na, device=dev, **f32),
+                  action=torch.zeros(1, na, device=dev, **f32), log_prob=torch.zeros(1, 1, device=dev, **f32),
+                  mean_t=torch.zeros(1, na, device=dev, **f32),
+                  scale=self.action_scale.to(dev, torch.float32).expand(na).contiguous(),
+                  bias=self.action_bias.to(dev, torch.float32).expand(na).contiguous(),
+                  ws=self._workspace(1, False), done=torch.cuda.Event())
+        if self._rng_state is None:
+            self._rng_state = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
+        drop = L.Drop(mode=L.DROP_RNG if (self.training and self.trans.emb_dropout > 0) else L.DROP_NONE,
+                      p=float(self.trans.emb_dropout), keep_mask=None, rng_state=self._rng_state.data_ptr(), stream_id=7)
+        io = L.ActorIO(img=st["img"].data_ptr(), pstate=st["ps"].data_ptr(), eps=None, action_scale=st["scale"].data_ptr(),
+                       action_bias=st["bias"].data_ptr(), drop=drop, sample_offset=0, mean=st["mean"].data_ptr(),
+                       log_std=st["log_std"].data_ptr(), action=st["action"].data_ptr(), log_prob=st["log_prob"].data_ptr(),
+                       mean_t=st["mean_t"].data_ptr(), eps_out=None)
+        net = self.net_struct()
+
+        def run():
+            st["img"].copy_(st["img_host"], non_blocking=True)
+            st["ps"].copy_(st["ps_host"], non_blocking=True)
+            self._rng_state[1] += 1            # fresh rsample / dropout stream per call
+            if self.precision == "bf16":
+                self.refresh_shadow()
+            L.check(L.lib().dgvit_actor_forward(C.byref(net), C.byref(io), 1, self._precision_code(), 0,
+                                                st["ws"].data_ptr(), st["ws"].numel(), _stream(dev)), "actor_forward")
+            st["action_host"].copy_(st["action"], non_blocking=True)
+            st["mean_t_host"].copy_(st["mean_t"], non_blocking=True)
+
+        run()                                   # eager warm-up (lazy kernel attributes, tensor-map entry point)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            run()
+        st["graph"] = g
+        st["io"] = io
+        self._act_state = st
+        return st
 
     def to(self, device):
         self.action_scale = self.action_scale.to(device)

@@ -273,3 +273,26 @@ def test_bf16_update_gradients_close_to_fp32_oracle():
             cos = float((gr @ rf) / (gr.norm() * rf.norm() + 1e-300))
             ratio = float(gr.norm() / rf.norm())
             assert cos > 0.99 and 0.95 < ratio < 1.05, (k, cos, ratio)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_choose_action_batch1(precision, tol):
+    """Batch-1 act (vn/DRL.py:170-185): numpy frame (H,W,1) + goal (2,) -> numpy action, graph-replayed."""
+    cfg = O.Cfg()
+    pa = reference_init("actor", cfg, 41)
+    a = _mk("actor", cfg, pa, precision)
+    a.eval()                                   # deterministic: no dropout, evaluate=True -> tanh(mean)
+    rs = np.random.RandomState(1)
+    for i in range(3):                         # repeated calls replay the captured graph with new inputs
+        frame = rs.rand(128, 160, 1).astype(np.float32)
+        goal = rs.rand(2).astype(np.float32)
+        got = a.choose_action(frame, goal, evaluate=True)
+        with torch.no_grad():
+            _, _, want = O.actor_sample(pa, torch.from_numpy(frame).permute(2, 0, 1), torch.from_numpy(goal)[None],
+                                        torch.zeros(1, 2), cfg, None)
+        assert got.shape == (2,) and got.dtype == np.float32
+        assert relerr(got, want[0]) < tol, (i, got, want)
+    a.train()                                  # stochastic path: bounded actions, changes call to call
+    x = a.choose_action(frame, goal)
+    y = a.choose_action(frame, goal)
+    assert np.all(np.abs(x) <= 1) and not np.array_equal(x, y)
