@@ -214,7 +214,7 @@ class SAC(object):
     # ------------------------------------------------------------------ the update
     def update_from_batch(self, batch: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None,
                           debug: Optional[torch.Tensor] = None, global_batch: Optional[int] = None,
-                          sample_offset: Optional[int] = None) -> torch.Tensor:
+                          sample_offset: Optional[int] = None, _phases=None) -> torch.Tensor:
         """One SAC update on device tensors (no host sync).  ``noise`` injects the stochastic
         inputs (parity tests): eps_next, eps_pi [B,na] and keep-masks mask_* [B,N,D] uint8.
         Returns the device tensor [qf1_loss, policy_loss, qf2_loss, alpha_loss]."""
@@ -233,20 +233,35 @@ class SAC(object):
                          drop_mode=L.DROP_MASK if noise.get("mask_c") is not None else
                          (L.DROP_NONE if noise.get("no_dropout") else L.DROP_RNG))
         out = L.SacOut(losses=self._losses.data_ptr(), debug=L.ptr(debug))
-        st = _stream(self.device)
         lib = L.lib()
         nzp = C.byref(nz) if nz is not None else None
+        keep = (s, bt, nz, out, ws, batch, noise, debug)      # ctypes structs must outlive the calls
+
+        def phase(which):
+            st = _stream(self.device)
+            if which == 0:
+                L.check(lib.dgvit_sac_update(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
+                        "sac_update")
+            elif which == 1:
+                L.check(lib.dgvit_sac_phase1(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
+                        "sac_phase1")
+            elif which == 2:
+                L.check(lib.dgvit_sac_phase2(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
+                        "sac_phase2")
+            else:
+                L.check(lib.dgvit_sac_phase3(C.byref(s), B, ws.data_ptr(), ws.numel(), st), "sac_phase3")
+            return keep
+
+        if _phases is not None:          # caller (graph capture of the data-parallel path) drives the phases itself
+            return phase
         if not self.distributed or self.world == 1:
-            L.check(lib.dgvit_sac_update(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
-                    "sac_update")
+            phase(0)
         else:
-            L.check(lib.dgvit_sac_phase1(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
-                    "sac_phase1")
+            phase(1)
             allreduce_sum_(self.critic._garena)
-            L.check(lib.dgvit_sac_phase2(C.byref(s), C.byref(bt), nzp, C.byref(out), B, ws.data_ptr(), ws.numel(), st),
-                    "sac_phase2")
+            phase(2)
             allreduce_sum_(self.policy._garena)
-            L.check(lib.dgvit_sac_phase3(C.byref(s), B, ws.data_ptr(), ws.numel(), st), "sac_phase3")
+            phase(3)
             allreduce_sum_(self._losses)
         self.itera += 1
         return self._losses
@@ -268,39 +283,53 @@ class SAC(object):
         self._idx_pin.copy_(idx_host)
         self._idx.copy_(self._idx_pin, non_blocking=True)
         batch = self._batch_buffers(B)
-        if not self.use_cuda_graph:
-            self.replay_buffer.gather(self._idx, batch)
-            return self.update_from_batch(batch)
-        return self._graphed(("learn", B), lambda: (self.replay_buffer.gather(self._idx, batch),
-                                                    self.update_from_batch(batch))[1])
+        return self._run(("learn", B), batch, gather=True)
 
     def update_from_batch_graphed(self, batch: Dict[str, torch.Tensor], key) -> torch.Tensor:
-        """``update_from_batch`` replayed from a CUDA graph keyed by ``key`` (the batch tensors must be
+        """``update_from_batch`` replayed from CUDA graph(s) keyed by ``key`` (the batch tensors must be
         the same device buffers on every call with that key)."""
-        if not self.use_cuda_graph:
-            return self.update_from_batch(batch)
-        return self._graphed(("batch", key, batch["obs"].data_ptr()), lambda: self.update_from_batch(batch))
+        return self._run(("batch", key, batch["obs"].data_ptr()), batch, gather=False)
 
-    def _graphed(self, key, fn):
-        """Eager on the first call (warms lazily initialised state), captured on the second,
-        replayed afterwards.  One graph per (key, polyak flag): every launch, tensor map and
-        device pointer of the update is frozen in the graph; per-step state (Adam step counts,
-        alpha, RNG counter, sampled indexes) lives in device memory."""
+    def _run(self, key, batch, gather: bool) -> torch.Tensor:
+        """Eager on the first call with a key (warms lazily initialised state), captured on the second,
+        replayed afterwards.  Every launch, tensor map and device pointer of the update is frozen in the
+        graph; per-step state (Adam step counts, alpha, RNG counter, sampled indexes) lives in device
+        memory.  Single GPU: one graph for gather + update.  Data parallel: one graph per phase with the
+        two NCCL gradient all-reduces issued between them."""
+        dp = self.distributed and self.world > 1
+        if not self.use_cuda_graph:
+            if gather:
+                self.replay_buffer.gather(self._idx, batch)
+            return self.update_from_batch(batch)
         key = key + (int(self.itera % self.policy_freq == 0),)
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = "warm"
-            return fn()
+            if gather:
+                self.replay_buffer.gather(self._idx, batch)
+            return self.update_from_batch(batch)
         if ent == "warm":
             torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
-            itera = self.itera
-            with torch.cuda.graph(g):
-                fn()
-            self.itera = itera            # capture does not execute: undo the host-side counter
-            self._graphs[key] = g
-            ent = g
-        ent.replay()
+            phase = self.update_from_batch(batch, _phases=True)
+            graphs = []
+            for i, which in enumerate((1, 2, 3) if dp else (0,)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    if gather and i == 0:
+                        self.replay_buffer.gather(self._idx, batch)
+                    keep = phase(which)
+                graphs.append(g)
+            ent = self._graphs[key] = (graphs, keep)
+        graphs = ent[0]
+        if dp:
+            graphs[0].replay()
+            allreduce_sum_(self.critic._garena)
+            graphs[1].replay()
+            allreduce_sum_(self.policy._garena)
+            graphs[2].replay()
+            allreduce_sum_(self._losses)
+        else:
+            graphs[0].replay()
         self.itera += 1
         return self._losses
 
