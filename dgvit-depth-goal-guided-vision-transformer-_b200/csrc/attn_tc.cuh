@@ -23,7 +23,7 @@ using namespace tc;
 constexpr int DH = 64;          // dim_head (reference default, vn/GoalFormer.py:124)
 constexpr int TILE = 16384;     // 128 rows x 128 B
 constexpr int FWD_STAGES = 2;
-constexpr int FWD_THREADS = 64 + 128;
+constexpr int FWD_THREADS = 64 + 256;   // TMA warp, MMA warp, two softmax warpgroups (one per TMEM/smem stage)
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -151,13 +151,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    // ---- softmax + output: thread = query row
+    // ---- softmax + output: thread = query row.  Warpgroup wg owns pipeline stage wg, i.e. every
+    //      second work item of this CTA, so two softmaxes are in flight while the tensor core runs.
     const int quad = warp & 3;
+    const int wg = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const float sl2 = a.scale * 1.44269504088896f;
-    int st = 0; uint32_t ph = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int st = wg; uint32_t ph = 0;
+    for (int it = blockIdx.x + wg * gridDim.x; it < items; it += FWD_STAGES * gridDim.x) {
       const int b = it / a.H, h = it % a.H;
       uint8_t* P = smem + st * STAGE_BYTES + 3 * TILE;
       mbar_wait(&s_full[st], ph);
@@ -210,7 +212,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_free[st]);
-      if (++st == FWD_STAGES) { st = 0; ph ^= 1; }
+      ph ^= 1;
     }
   }
   tc_fence_before();

@@ -753,13 +753,39 @@ static dgvit_drop sac_drop(const dgvit_sac& s, const dgvit_noise* nz, const uint
   return dr;
 }
 
+// The three forward passes of the first half of the update are independent of one another
+// (vn/DRL.py:388-395,404): [policy.sample(s') -> critic_target(s',a')], critic(s,a) and
+// policy.sample(s).  They are issued on three streams (fork/join with events: capturable into
+// one CUDA graph) so that their many small, latency-bound kernels fill each other's gaps.
+struct ForkState {
+  cudaStream_t aux[2];
+  cudaEvent_t fork, join[2];
+};
+static ForkState& fork_state() {
+  static ForkState f;
+  static bool init = false;
+  if (!init) {
+    for (int i = 0; i < 2; ++i) {
+      DG_CUDA(cudaStreamCreateWithFlags(&f.aux[i], cudaStreamNonBlocking));
+      DG_CUDA(cudaEventCreateWithFlags(&f.join[i], cudaEventDisableTiming));
+    }
+    DG_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
+    init = true;
+  }
+  return f;
+}
+
 template <typename A>
 static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noise* nz, const dgvit_sac_out& out,
                        const Dims& d, SacWs<A>& w, cudaStream_t st) {
   dgvit_layout La, Lc;
   make_layout(s.actor.cfg, La);
   make_layout(s.critic.cfg, Lc);
-  // ---- no-grad: a', log pi' = policy.sample(s') ; q_t = critic_target(s', a')   (DRL.py:388-393)
+  ForkState& f = fork_state();
+  DG_CUDA(cudaEventRecord(f.fork, st));
+  DG_CUDA(cudaStreamWaitEvent(f.aux[0], f.fork, 0));
+  DG_CUDA(cudaStreamWaitEvent(f.aux[1], f.fork, 0));
+  // ---- stream 0 (caller's): a', log pi' = policy.sample(s') ; q_t = critic_target(s', a')   (DRL.py:388-393)
   dgvit_actor_io ai; memset(&ai, 0, sizeof(ai));
   ai.img = b.next_obs; ai.pstate = b.next_pobs; ai.eps = nz ? nz->eps_next : nullptr;
   ai.action_scale = s.action_scale; ai.action_bias = s.action_bias;
@@ -772,12 +798,25 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   ci.drop = sac_drop(s, nz, nz ? nz->mask_ct : nullptr, 2);
   ci.q1 = w.q1t; ci.q2 = w.q2t;
   critic_forward<A>(s.critic_target, Lc, d, ci, s.sample_offset, w.critic_tmp, st);
-  // ---- critic(s, a), losses, backward                                          (DRL.py:395-401)
+  // ---- stream 1: critic(s, a)                                                   (DRL.py:395)
   dgvit_critic_io cs; memset(&cs, 0, sizeof(cs));
   cs.img = b.obs; cs.pstate = b.pobs; cs.action = b.act;
   cs.drop = sac_drop(s, nz, nz ? nz->mask_c : nullptr, 3);
   cs.q1 = w.q1; cs.q2 = w.q2;
-  critic_forward<A>(s.critic, Lc, d, cs, s.sample_offset, w.critic_s, st);
+  critic_forward<A>(s.critic, Lc, d, cs, s.sample_offset, w.critic_s, f.aux[0]);
+  DG_CUDA(cudaEventRecord(f.join[0], f.aux[0]));
+  // ---- stream 2: pi, log_pi = policy.sample(s)  (DRL.py:404; the actor is not touched before :413,
+  //      so this forward can run beside the whole critic update)
+  dgvit_actor_io ap; memset(&ap, 0, sizeof(ap));
+  ap.img = b.obs; ap.pstate = b.pobs; ap.eps = nz ? nz->eps_pi : nullptr;
+  ap.action_scale = s.action_scale; ap.action_bias = s.action_bias;
+  ap.drop = sac_drop(s, nz, nz ? nz->mask_a : nullptr, 4);
+  ap.sample_offset = s.sample_offset;
+  ap.mean = w.mean_pi; ap.log_std = w.lstd_pi; ap.action = w.pi; ap.log_prob = w.logpi;
+  actor_forward<A>(s.actor, La, d, ap, w.actor_s, f.aux[1]);
+  DG_CUDA(cudaEventRecord(f.join[1], f.aux[1]));
+  // ---- losses + critic backward                                                 (DRL.py:396-401)
+  DG_CUDA(cudaStreamWaitEvent(st, f.join[0], 0));
   critic_loss_kernel<<<1, 1024, 0, st>>>(w.q1, w.q2, w.q1t, w.q2t, w.logp2, b.rew, s.alpha, s.gamma, d.B, d.na,
                                          s.global_batch, w.nq, w.dq1, w.dq2, out.losses);
   DG_LAUNCH_CHECK();
@@ -788,6 +827,7 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
     DG_CUDA(cudaMemcpyAsync(out.debug + d.B * d.na, w.q1, bn, cudaMemcpyDeviceToDevice, st));
     DG_CUDA(cudaMemcpyAsync(out.debug + 2 * d.B * d.na, w.q2, bn, cudaMemcpyDeviceToDevice, st));
   }
+  DG_CUDA(cudaStreamWaitEvent(st, f.join[1], 0));      // join the actor forward before the phase ends
 }
 
 template <typename A>
@@ -798,14 +838,13 @@ static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   make_layout(s.critic.cfg, Lc);
   const bool shadow = s.precision == DGVIT_BF16;
   adam_step(s.critic, Lc, s.critic_opt, nullptr, 0.f, shadow, st);               // DRL.py:402
-  // ---- pi, log_pi = policy.sample(s) ; q_pi = critic(s, pi)                    (DRL.py:404-407)
+  // ---- q_pi = critic(s, pi) with the UPDATED critic (pi, log_pi come from phase 1)   (DRL.py:406-407)
   dgvit_actor_io ai; memset(&ai, 0, sizeof(ai));
   ai.img = b.obs; ai.pstate = b.pobs; ai.eps = nz ? nz->eps_pi : nullptr;
   ai.action_scale = s.action_scale; ai.action_bias = s.action_bias;
   ai.drop = sac_drop(s, nz, nz ? nz->mask_a : nullptr, 4);
   ai.sample_offset = s.sample_offset;
   ai.mean = w.mean_pi; ai.log_std = w.lstd_pi; ai.action = w.pi; ai.log_prob = w.logpi;
-  actor_forward<A>(s.actor, La, d, ai, w.actor_s, st);
   dgvit_critic_io ci; memset(&ci, 0, sizeof(ci));
   ci.img = b.obs; ci.pstate = b.pobs; ci.action = w.pi;
   ci.drop = sac_drop(s, nz, nz ? nz->mask_c_pi : nullptr, 5);
@@ -828,7 +867,6 @@ static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
     DG_CUDA(cudaMemcpyAsync(out.debug + 5 * d.B * d.na, w.logpi, (size_t)d.B * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
 }
-
 
 template <typename A>
 static void sac_phase3(const dgvit_sac& s, cudaStream_t st) {
