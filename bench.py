@@ -36,6 +36,9 @@ SEED = 3407
 # algorithmic FLOPs of one update per sample: 4 F_a + 5 F_c
 F_A, F_C = 190_371_072, 190_371_328
 FLOP_PER_SAMPLE = 4 * F_A + 5 * F_C
+# dram__bytes_read.sum + dram__bytes_write.sum of one mlp_fwd_tc_kernel launch (16640 rows, no pre-activation
+# store) from the `ncu --set full` capture summarised in profiles/ (None until captured)
+NCU_TRAFFIC_BYTES = None
 
 
 def peaks():
@@ -145,6 +148,29 @@ def cpu_act_latency(calls: int = 60):
     return ts[len(ts) // 2] * 1e3
 
 
+def gpu_eager_rate(batch: int, dev):
+    """Informational: the same oracle (= the reference's ATen/cuBLAS library path, fp32 eager) on the GPU."""
+    from oracle import dgvit_oracle as O
+    from oracle.init_params import reference_sac_init, synthetic_batch, synthetic_noise
+    cfg = O.Cfg(dim=PRESET["l_f_size"], depth=PRESET["block"], heads=PRESET["head"])
+    actor, critic = reference_sac_init(cfg, SEED)
+    b = {k: v.to(dev) for k, v in synthetic_batch(cfg, batch, SEED).items()}
+    nz = {k: v.to(dev) for k, v in synthetic_noise(cfg, batch, SEED + 1).items()}
+    with torch.device(dev):
+        orc = O.SACOracle({k: v.to(dev) for k, v in actor.items()}, {k: v.to(dev) for k, v in critic.items()}, cfg,
+                          gamma=HP["GAMMA"], tau=HP["TAU"], alpha=HP["ALPHA"], policy_freq=HP["POLICY_FREQ"])
+        orc.log_alpha = orc.log_alpha.to(dev)
+        for _ in range(3):
+            orc.learn(b, nz)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        n = 10
+        for _ in range(n):
+            orc.learn(b, nz)
+        torch.cuda.synchronize(dev)
+    return dict(value=batch * n / (time.perf_counter() - t0), unit=UNIT, what="oracle restatement in eager PyTorch fp32 on the same GPU")
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -215,19 +241,27 @@ def run_ours(args):
     # per-kernel timing of the dominant kernel family + launch count: the same steps launched eagerly
     # (CUDA events around individual launches cannot be recorded inside a replayed graph)
     graph_flag, ag.use_cuda_graph = ag.use_cuda_graph, False
-    psteps = min(args.steps, 5)
-    L.check(lib.dgvit_prof_begin(L.PROF_GEMM_MLP, psteps * 160), "prof_begin")
+    L.check(lib.dgvit_set_option(b"fork_streams", 0), "set_option")     # one stream: clean per-kernel durations
+    psteps = min(args.steps, 3)
+    prof = {}
     n0 = lib.dgvit_launch_count()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
-    for _ in range(psteps):
-        ag.learn_async(B)
+    for tag_name, tag in (("mlp_fused", L.PROF_MLP_FUSED), ("gemm_all", L.PROF_GEMM_ALL), ("attention", L.PROF_ATTENTION)):
+        L.check(lib.dgvit_prof_begin(tag, psteps * 400), "prof_begin")
+        for _ in range(psteps):
+            ag.learn_async(B)
+        torch.cuda.synchronize(dev)
+        pms, pl, pfl, pby = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
+        L.check(lib.dgvit_prof_end(C.byref(pms), C.byref(pl), C.byref(pfl), C.byref(pby)), "prof_end")
+        prof[tag_name] = dict(ms_per_step=pms.value / psteps, launches_per_step=pl.value / psteps,
+                              tflops=(pfl.value / 1e12) / (pms.value / 1e3) if pms.value > 0 else 0.0,
+                              flop_per_step=pfl.value / psteps)
     p1.record()
     torch.cuda.synchronize(dev)
-    launches = (lib.dgvit_launch_count() - n0) * args.steps // psteps
-    pms, pl, pfl, pby = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
-    L.check(lib.dgvit_prof_end(C.byref(pms), C.byref(pl), C.byref(pfl), C.byref(pby)), "prof_end")
-    eager_ms_per_step = p0.elapsed_time(p1) / psteps
+    launches = (lib.dgvit_launch_count() - n0) * args.steps // (3 * psteps)
+    eager_ms_per_step = p0.elapsed_time(p1) / (3 * psteps)
+    L.check(lib.dgvit_set_option(b"fork_streams", 1), "set_option")
     ag.use_cuda_graph = graph_flag
     barrier()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -311,18 +345,22 @@ def run_ours(args):
         return
 
     # ---------------- roofline of the dominant kernel (the MLP GEMM family), timed live above
-    ach = (pfl.value / 1e12) / (pms.value / 1e3) if pms.value > 0 else 0.0
+    dom = prof["mlp_fused"]
+    ach = dom["tflops"]
     roof = dict(bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s", frac=ach / pk["tf_sust"],
-                traffic=None, kernel="MLP GEMM family (fc1+GELU, fc2+residual, and their dX/dW)",
-                launches_timed=int(pl.value), kernel_ms_per_step=pms.value / psteps,
-                share_of_step=(pms.value / psteps) / (ms / args.steps) if ms > 0 else None,
-                eager_ms_per_step=eager_ms_per_step, peak_source=pk["src"] + " (sustained bf16 cuBLAS)")
+                traffic=NCU_TRAFFIC_BYTES, kernel="mlp::mlp_fwd_tc_kernel (fused fc1 + GELU + fc2 + residual, tcgen05/TMEM)",
+                algorithmic_flop_per_launch="4*rows*64*2048 (8.72 GFLOP at 16640 token rows)",
+                launches_per_step=dom["launches_per_step"], kernel_ms_per_step=dom["ms_per_step"],
+                share_of_step=dom["ms_per_step"] / (ms / args.steps) if ms > 0 else None,
+                eager_ms_per_step=eager_ms_per_step, peak_source=pk["src"] + " (sustained bf16 cuBLAS)",
+                other_kernels={k: v for k, v in prof.items() if k != "mlp_fused"})
     whole = dict(achieved_tflops=value * FLOP_PER_SAMPLE / 1e12, frac_of_peak=value * FLOP_PER_SAMPLE / 1e12 / pk["tf_sust"] / world)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, sample, _ = cpu_update_rate(12.0, B, 3, warmup=1)
-        cpu = dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample, act_p50_ms=cpu_act_latency())
+        cpu = dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample, act_p50_ms=cpu_act_latency(),
+                   torch_eager_on_gpu=gpu_eager_rate(B, dev))
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,

@@ -15,7 +15,7 @@ MAX_DEPTH = 16
 ACTOR, CRITIC = 0, 1
 FP32, BF16 = 0, 1
 DROP_NONE, DROP_MASK, DROP_RNG = 0, 1, 2
-PROF_NONE, PROF_GEMM_MLP, PROF_GEMM_ALL, PROF_ATTENTION, PROF_GATHER, PROF_ADAM = range(6)
+PROF_NONE, PROF_GEMM_MLP, PROF_GEMM_ALL, PROF_ATTENTION, PROF_GATHER, PROF_ADAM, PROF_MLP_FUSED = range(7)
 
 c_f_p = C.c_void_p  # device pointers travel as integers
 
@@ -108,6 +108,7 @@ SYMBOLS = {
     "dgvit_version": (C.c_int, []),
     "dgvit_last_error": (C.c_char_p, []),
     "dgvit_launch_count": (C.c_longlong, []),
+    "dgvit_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "dgvit_prof_begin": (C.c_int, [C.c_int, C.c_int]),
     "dgvit_prof_end": (C.c_int, [P(C.c_double), P(C.c_longlong), P(C.c_double), P(C.c_double)]),
     "dgvit_param_layout": (C.c_int, [P(Cfg), P(Layout)]),
@@ -125,6 +126,8 @@ SYMBOLS = {
     "dgvit_sac_update": (C.c_int, [P(Sac), P(Batch), P(Noise), P(SacOut), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dgvit_gemm_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "dgvit_linear_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "dgvit_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_void_p]),
     "dgvit_adam_step": (C.c_int, [P(Net), P(Adam), P(Net), C.c_float, C.c_void_p]),

@@ -66,7 +66,8 @@ inline Prof& prof() {
   static Prof p;
   return p;
 }
-enum { PROF_NONE = 0, PROF_GEMM_MLP = 1, PROF_GEMM_ALL = 2, PROF_ATTENTION = 3, PROF_GATHER = 4, PROF_ADAM = 5 };
+enum { PROF_NONE = 0, PROF_GEMM_MLP = 1, PROF_GEMM_ALL = 2, PROF_ATTENTION = 3, PROF_GATHER = 4, PROF_ADAM = 5,
+       PROF_MLP_FUSED = 6 };
 struct ProfScope {
   bool active = false;
   cudaStream_t st;

@@ -392,6 +392,7 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
 #ifdef DGVIT_WITH_TC
       if constexpr (std::is_same<A, bf16>::value) {
         ProfScope ps(PROF_GEMM_MLP, 4.0 * R * d.D * d.M, 0.0, st);
+        ProfScope ps2(PROF_MLP_FUSED, 4.0 * R * d.D * d.M, 0.0, st);
         mlp::fwd(B_.Xn2, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), P + b.fc2_b, B_.Xm, d.D, Xnext,
                  d.D, c.save ? B_.Hpre : nullptr, R, d.M, st);
       }
@@ -761,6 +762,7 @@ struct ForkState {
   cudaStream_t aux[2];
   cudaEvent_t fork, join[2];
 };
+static bool g_fork_enabled = true;
 static ForkState& fork_state() {
   static ForkState f;
   static bool init = false;
@@ -781,7 +783,9 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   dgvit_layout La, Lc;
   make_layout(s.actor.cfg, La);
   make_layout(s.critic.cfg, Lc);
-  ForkState& f = fork_state();
+  ForkState& f0 = fork_state();
+  ForkState f = f0;
+  if (!g_fork_enabled) { f.aux[0] = st; f.aux[1] = st; }      // single-stream mode (per-kernel timing)
   DG_CUDA(cudaEventRecord(f.fork, st));
   DG_CUDA(cudaStreamWaitEvent(f.aux[0], f.fork, 0));
   DG_CUDA(cudaStreamWaitEvent(f.aux[1], f.fork, 0));
@@ -932,6 +936,17 @@ extern "C" {
 
 int dgvit_version(void) { return 100; }
 long long dgvit_launch_count(void) { return launch_counter(); }
+
+int dgvit_set_option(const char* name, int value) {
+  return guarded([&] {
+    DG_REQUIRE(name != nullptr, "null option name");
+    if (!strcmp(name, "fork_streams")) g_fork_enabled = value != 0;
+#ifdef DGVIT_WITH_TC
+    else if (!strcmp(name, "tensor_cores")) tc::g_tc_enabled = value != 0;
+#endif
+    else fail(DGVIT_ERR_ARG, "unknown option %s", name);
+  });
+}
 
 int dgvit_prof_begin(int tag, int max_launches) {
   return guarded([&] {
@@ -1147,6 +1162,28 @@ int dgvit_gemm_bf16(int M, int N, int K, const void* A, int64_t a_sm, int64_t a_
     } else {
       gemm_simt<bf16, bf16, float>(g, (cudaStream_t)stream);
     }
+  });
+}
+
+int dgvit_linear_bf16(const void* x, const void* W, void* y, int64_t rows, int N, int K, int epilogue, const float* bias,
+                      const void* aux, void* y2, int weight_is_kn, void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(x && W && y && rows > 0 && N > 0 && K > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GemmArgs g;
+    g.M = (int)rows; g.N = N; g.K = K;
+    g.A = x; g.a_sm = K; g.a_sk = 1;
+    g.B = W;
+    if (weight_is_kn) { g.b_sk = N; g.b_sn = 1; } else { g.b_sk = 1; g.b_sn = K; }
+    g.C = y; g.ldc = N; g.C2 = y2; g.bias = bias; g.aux = aux; g.ldaux = N;
+    switch (epilogue) {
+      case 0: g.epi = EPI_NONE; break;
+      case 1: g.epi = EPI_BIAS_GELU2; DG_REQUIRE(bias && y2, "gelu2 needs bias and y2"); break;
+      case 2: g.epi = EPI_GELU_BWD; DG_REQUIRE(aux, "gelu_bwd needs aux"); break;
+      case 3: g.epi = EPI_GELU_BWD2; DG_REQUIRE(aux && y2, "gelu_bwd2 needs aux and y2"); break;
+      default: fail(DGVIT_ERR_ARG, "unknown epilogue %d", epilogue);
+    }
+    gemm<bf16, bf16, bf16>(g, st);
   });
 }
 

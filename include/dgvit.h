@@ -186,8 +186,12 @@ const char* dgvit_last_error(void);
  * CUDA-event timing of the launches of one kernel family (DGVIT_PROF_*), recorded on the
  * launching stream.  dgvit_prof_end synchronises on the recorded events. */
 enum { DGVIT_PROF_NONE = 0, DGVIT_PROF_GEMM_MLP = 1, DGVIT_PROF_GEMM_ALL = 2, DGVIT_PROF_ATTENTION = 3,
-       DGVIT_PROF_GATHER = 4, DGVIT_PROF_ADAM = 5 };
+       DGVIT_PROF_GATHER = 4, DGVIT_PROF_ADAM = 5, DGVIT_PROF_MLP_FUSED = 6 };
 long long dgvit_launch_count(void);
+/* runtime switches for measurement / A-B tests: "fork_streams" (1: the independent forward passes of
+ * the update run on library-owned side streams; 0: everything on the caller's stream),
+ * "tensor_cores" (0: route the bf16 contractions to the CUDA-core kernels) */
+int dgvit_set_option(const char* name, int value);
 int dgvit_prof_begin(int tag, int max_launches);
 int dgvit_prof_end(double* ms_total, long long* launches, double* flops, double* bytes);
 
@@ -248,6 +252,12 @@ int dgvit_sac_update(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise
 int dgvit_gemm_bf16(int M, int N, int K, const void* A, int64_t a_sm, int64_t a_sk, const void* B,
                     int64_t b_sk, int64_t b_sn, float* C, int64_t ldc, int splitk, float* partial,
                     int use_tensor_cores, void* stream);
+
+/* bf16 nn.Linear with the fused epilogues of the MLP path (vn/GoalFormer.py:43-46): y[rows,N] (bf16) =
+ * x[rows,K] W^T (W [N,K]; or x W with W [K,N] when weight_is_kn).  epilogue: 0 none; 1 y = acc+bias,
+ * y2 = gelu(y); 2 y = acc * gelu'(aux); 3 as 2 and y2 = gelu(aux).  (unit tests, micro-benchmarks) */
+int dgvit_linear_bf16(const void* x, const void* W, void* y, int64_t rows, int N, int K, int epilogue,
+                      const float* bias, const void* aux, void* y2, int weight_is_kn, void* stream);
 
 /* Attention.forward core (vn/GoalFormer.py:75-81) on bf16 QKV [B*N, 3*H*dim_head] (column =
  * which*inner + h*dim_head + d): forward when d_o == NULL (writes o [B*N, inner]), else backward

@@ -1,0 +1,67 @@
+"""Kernel micro-benchmarks through the C ABI (CUDA events, L2 flushed between iterations).
+usage: python profiles/microbench.py [B]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dgvit_b200 import _lib as L
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+T = B * 65
+dev = "cuda"
+lib = L.lib()
+st = torch.cuda.current_stream().cuda_stream
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=20):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def linear(rows, N, K, epi, kn=0):
+    x = torch.randn(rows, K, device=dev).bfloat16()
+    W = (torch.randn(K, N, device=dev) if kn else torch.randn(N, K, device=dev)).bfloat16()
+    y = torch.empty(rows, N, device=dev, dtype=torch.bfloat16)
+    y2 = torch.empty_like(y)
+    bias = torch.randn(N, device=dev)
+    aux = torch.randn(rows, N, device=dev).bfloat16()
+    def fn():
+        L.check(lib.dgvit_linear_bf16(x.data_ptr(), W.data_ptr(), y.data_ptr(), rows, N, K, epi, bias.data_ptr(),
+                                      aux.data_ptr(), y2.data_ptr(), kn, st))
+    return timeit(fn)
+
+
+def attention(bwd):
+    H = 4
+    qkv = torch.randn(T, 3 * H * 64, device=dev).bfloat16()
+    o = torch.empty(T, H * 64, device=dev, dtype=torch.bfloat16)
+    do = torch.randn(T, H * 64, device=dev).bfloat16()
+    dq = torch.empty_like(qkv)
+    def f():
+        L.check(lib.dgvit_attention_bf16(qkv.data_ptr(), o.data_ptr(), None, None, B, 65, H, 64, 1, st))
+    def b():
+        L.check(lib.dgvit_attention_bf16(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), dq.data_ptr(), B, 65, H, 64, 1, st))
+    f()
+    return timeit(b if bwd else f)
+
+
+print(f"B={B} T={T}")
+for name, args in [("QKV      x[T,64]  W[768,64]           none", (T, 768, 64, 0)),
+                   ("fc1      x[T,64]  W[2048,64]   bias+gelu2", (T, 2048, 64, 1)),
+                   ("dH       dy[T,64] W2[64,2048]    gelu_bwd", (T, 2048, 64, 2, 1)),
+                   ("dH+Hact  dy[T,64] W2[64,2048]   gelu_bwd2", (T, 2048, 64, 3, 1)),
+                   ("dO       dy[T,64] Wo[64,256]         none", (T, 256, 64, 0, 1))]:
+    us = linear(*args)
+    rows, N, K = args[:3]
+    print(f"{name}: {us:8.1f} us   {2 * rows * N * K / us / 1e6:7.1f} TFLOP/s   out {rows * N * 2 / us / 1e3:7.1f} GB/s")
+print(f"attention fwd: {attention(False):8.1f} us")
+print(f"attention bwd: {attention(True):8.1f} us")
