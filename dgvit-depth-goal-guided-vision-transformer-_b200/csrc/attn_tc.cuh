@@ -68,7 +68,7 @@ struct AttnArgs {
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int STAGE_BYTES = 5 * TILE;
   uint64_t* bars = (uint64_t*)(smem + FWD_STAGES * STAGE_BYTES);
   uint64_t* qkv_full = bars;                    // [S] TMA landed
@@ -97,6 +97,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmdO, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int LOAD_BYTES = 4 * TILE;
   uint8_t* Pt = smem + BWD_LOAD_STAGES * LOAD_BYTES;   // 2 tiles
   uint8_t* dSt = Pt + 2 * TILE;                        // 2 tiles
@@ -259,6 +262,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -433,7 +439,7 @@ static void fwd(const bf16* QKV, bf16* O, int B, int N, int H, cudaStream_t st) 
     attr = true;
   }
   const int grid = std::min(B * H, sm_count());
-  attn_fwd_tc_kernel<<<grid, FWD_THREADS, smem, st>>>(tq, tkv, a);
+  launch_k(attn_fwd_tc_kernel, grid, FWD_THREADS, smem, st, tq, tkv, a);
   DG_LAUNCH_CHECK();
 }
 
@@ -454,7 +460,7 @@ static void bwd(const bf16* QKV, const bf16* O, const bf16* dO, bf16* dQKV, int 
     attr = true;
   }
   const int grid = std::min(B * H, sm_count());
-  attn_bwd_tc_kernel<<<grid, BWD_THREADS, smem, st>>>(tq, tkv, tdo, a);
+  launch_k(attn_bwd_tc_kernel, grid, BWD_THREADS, smem, st, tq, tkv, tdo, a);
   DG_LAUNCH_CHECK();
 }
 

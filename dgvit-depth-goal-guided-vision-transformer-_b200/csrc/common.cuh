@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -51,6 +52,32 @@ inline long long& launch_counter() {
     ++::dgvit::launch_counter();   \
     DG_CUDA(cudaGetLastError());   \
   } while (0)
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may be
+// scheduled while the previous kernel of the stream is still draining, run their input-independent
+// prologue, and block in pdl_wait() until the previous grid has completed and flushed.  pdl_launch()
+// (issued right after the wait) lets the NEXT kernel do the same.  The ~370 kernels of one update are
+// mostly single-wave and latency-bound, so hiding launch + prologue latency matters.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool& pdl_enabled() {
+  static bool e = true;
+  return e;
+}
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  DG_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
 
 // optional per-kernel timing of the launches tagged as the dominant kernel (bench.py roofline):
 // events are recorded on the launching stream around each tagged launch.

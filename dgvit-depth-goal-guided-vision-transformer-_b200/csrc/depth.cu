@@ -16,6 +16,8 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 // pass 0: per-frame min/max partials  part[f][blk][2]
 __global__ void depth_minmax_kernel(const float* __restrict__ raw, float* __restrict__ part, int64_t hw) {
+  pdl_wait();
+  pdl_launch();
   const int f = blockIdx.y;
   const float* src = raw + (int64_t)f * hw;
   float mn = INFINITY, mx = -INFINITY;
@@ -59,6 +61,8 @@ __device__ __forceinline__ float noisy_px(const float* __restrict__ raw, const f
 __global__ void depth_noise_hblur_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
                                          const uint64_t* rng, const float* __restrict__ mmpart,
                                          float* __restrict__ S1, int H, int W) {
+  pdl_wait();
+  pdl_launch();
   const int f = blockIdx.z, y = blockIdx.y;
   __shared__ double sc[2];
   if (threadIdx.x == 0) {
@@ -87,6 +91,8 @@ __global__ void depth_noise_hblur_kernel(const float* __restrict__ raw, const fl
 
 // pass 2: vertical 5-tap
 __global__ void depth_vblur5_kernel(const float* __restrict__ S1, float* __restrict__ S2, int H, int W) {
+  pdl_wait();
+  pdl_launch();
   const int f = blockIdx.z, y = blockIdx.y;
   const float k[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
   for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
@@ -102,6 +108,8 @@ struct K11 { float k[11]; };
 // pass 3: horizontal 11-tap on the centre band rows (reflect in x)
 __global__ void depth_band_hblur_kernel(const float* __restrict__ S2, float* __restrict__ T1, K11 kk, int H, int W,
                                         int y1, int bh) {
+  pdl_wait();
+  pdl_launch();
   const int f = blockIdx.z, r = blockIdx.y;
   const float* src = S2 + ((int64_t)f * H + y1 + r) * W;
   for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
@@ -115,6 +123,8 @@ __global__ void depth_band_hblur_kernel(const float* __restrict__ S2, float* __r
 // pass 4: band vertical 11-tap (reflect inside the band) + bilinear downsample by `fac` + /255
 __global__ void depth_resize_kernel(const float* __restrict__ S2, const float* __restrict__ T1, K11 kk,
                                     float* __restrict__ out, int H, int W, int y1, int bh, int fac) {
+  pdl_wait();
+  pdl_launch();
   const int f = blockIdx.z, oy = blockIdx.y;
   const int oh = H / fac, ow = W / fac, o = fac / 2 - 1;
   for (int ox = blockIdx.x * blockDim.x + threadIdx.x; ox < ow; ox += gridDim.x * blockDim.x) {
@@ -179,17 +189,17 @@ int dgvit_depth_augment(const float* raw, const float* noise, const uint64_t* rn
       for (int i = 0; i < 11; ++i) { const double x = i - 5.0; k[i] = exp(-(x * x) / (2 * sigma * sigma)); sum += k[i]; }
       for (int i = 0; i < 11; ++i) kk.k[i] = (float)(k[i] / sum);
     }
-    depth_minmax_kernel<<<dim3(MM_BLOCKS, n), 256, 0, st>>>(raw, mm, (int64_t)H * W);
+    launch_k(depth_minmax_kernel, dim3(MM_BLOCKS, n), 256, 0, st, raw, mm, (int64_t)H * W);
     DG_LAUNCH_CHECK();
     const int xb = (int)cdiv(W, 256);
-    depth_noise_hblur_kernel<<<dim3(xb, H, n), 256, 0, st>>>(raw, noise, rng_state, mm, S1, H, W);
+    launch_k(depth_noise_hblur_kernel, dim3(xb, H, n), 256, 0, st, raw, noise, rng_state, mm, S1, H, W);
     DG_LAUNCH_CHECK();
-    depth_vblur5_kernel<<<dim3(xb, H, n), 256, 0, st>>>(S1, S2, H, W);
+    launch_k(depth_vblur5_kernel, dim3(xb, H, n), 256, 0, st, S1, S2, H, W);
     DG_LAUNCH_CHECK();
-    depth_band_hblur_kernel<<<dim3(xb, bh, n), 256, 0, st>>>(S2, T1, kk, H, W, y1, bh);
+    launch_k(depth_band_hblur_kernel, dim3(xb, bh, n), 256, 0, st, S2, T1, kk, H, W, y1, bh);
     DG_LAUNCH_CHECK();
     const int fac = 4;
-    depth_resize_kernel<<<dim3((unsigned)cdiv(W / fac, 128), H / fac, n), 128, 0, st>>>(S2, T1, kk, out, H, W, y1, bh, fac);
+    launch_k(depth_resize_kernel, dim3((unsigned)cdiv(W / fac, 128), H / fac, n), 128, 0, st, S2, T1, kk, out, H, W, y1, bh, fac);
     DG_LAUNCH_CHECK();
   });
 }

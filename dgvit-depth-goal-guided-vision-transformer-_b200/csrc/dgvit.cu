@@ -162,9 +162,9 @@ static void linear_bwd_w(const TA* dy, const TB* x, float* dW, float* db, int64_
     const int S = (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 128);   // row ranges per column block
     const int64_t rpb = cdiv(R, S);
     dim3 grid((unsigned)cdiv(N, 256), (unsigned)S);
-    colsum_partial_kernel<TA><<<grid, 128, 0, st>>>(dy, ldy, partial, R, N, rpb);
+    launch_k(colsum_partial_kernel<TA>, grid, 128, 0, st, dy, ldy, partial, R, N, rpb);
     DG_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(unsigned)cdiv(N, 256), 256, 0, st>>>(partial, db, S, N);
+    launch_k(reduce_partials_kernel, (unsigned)cdiv(N, 256), 256, 0, st, partial, db, S, N);
     DG_LAUNCH_CHECK();
   }
 }
@@ -275,7 +275,7 @@ static void launch_ln_fwd(const float* X, const float* g, const float* b, A* Y, 
   const int wpb = 8;
   const unsigned grid = (unsigned)cdiv(T, wpb);
   switch (D / 32) {
-#define LNF(V) case V: layernorm_fwd_kernel<A, V><<<grid, wpb * 32, 0, st>>>(X, g, b, Y, mean, rstd, T); break;
+#define LNF(V) case V: launch_k(layernorm_fwd_kernel<A, V>, grid, wpb * 32, 0, st, X, g, b, Y, mean, rstd, T); break;
     LNF(1) LNF(2) LNF(3) LNF(4) LNF(5) LNF(6) LNF(7) LNF(8)
 #undef LNF
     default: fail(DGVIT_ERR_ARG, "unsupported dim %d", D);
@@ -289,13 +289,13 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
   int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 4);
   const size_t smem = (size_t)wpb * 2 * D * sizeof(float);
   switch (D / 32) {
-#define LNB(V) case V: layernorm_bwd_kernel<V><<<nblocks, wpb * 32, smem, st>>>(dY, X, mean, rstd, gamma, dX_io, dX_lp, partial, T); break;
+#define LNB(V) case V: launch_k(layernorm_bwd_kernel<V>, nblocks, wpb * 32, smem, st, dY, X, mean, rstd, gamma, dX_io, dX_lp, partial, T); break;
     LNB(1) LNB(2) LNB(3) LNB(4) LNB(5) LNB(6) LNB(7) LNB(8)
 #undef LNB
     default: fail(DGVIT_ERR_ARG, "unsupported dim %d", D);
   }
   DG_LAUNCH_CHECK();
-  ln_param_reduce_kernel<<<(unsigned)cdiv(2 * D, 32), 1024, 0, st>>>(partial, dgamma, dbeta, nblocks, D);
+  launch_k(ln_param_reduce_kernel, (unsigned)cdiv(2 * D, 32), 1024, 0, st, partial, dgamma, dbeta, nblocks, D);
   DG_LAUNCH_CHECK();
 }
 
@@ -315,7 +315,7 @@ static void launch_attention_fwd(const A* QKV, A* O, const Dims& d, cudaStream_t
     DG_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  attention_fwd_kernel<A><<<d.B * d.H, threads, smem, st>>>(QKV, O, d.N, d.H, d.dh, 1.0f / sqrtf((float)d.dh));
+  launch_k(attention_fwd_kernel<A>, d.B * d.H, threads, smem, st, QKV, O, d.N, d.H, d.dh, 1.0f / sqrtf((float)d.dh));
   DG_LAUNCH_CHECK();
 }
 template <typename A>
@@ -334,7 +334,7 @@ static void launch_attention_bwd(const A* QKV, const A* O, const A* dO, A* dQKV,
     DG_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  attention_bwd_kernel<A><<<d.B * d.H, threads, smem, st>>>(QKV, O, dO, dQKV, d.N, d.H, d.dh, 1.0f / sqrtf((float)d.dh));
+  launch_k(attention_bwd_kernel<A>, d.B * d.H, threads, smem, st, QKV, O, dO, dQKV, d.N, d.H, d.dh, 1.0f / sqrtf((float)d.dh));
   DG_LAUNCH_CHECK();
 }
 
@@ -360,12 +360,12 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
   {
     const int64_t total4 = (int64_t)d.B * d.P * d.pd / 4;
     DG_REQUIRE(cfg.patch_w % 4 == 0 && (((uintptr_t)img) & 15) == 0, "patchify: patch_w %% 4 and 16-byte aligned frames required");
-    patchify_kernel<A><<<grid1d(total4), 256, 0, st>>>(img, c.Pm, total4, cfg.img_h, cfg.img_w, cfg.patch_h, cfg.patch_w);
+    launch_k(patchify_kernel<A>, grid1d(total4), 256, 0, st, img, c.Pm, total4, cfg.img_h, cfg.img_w, cfg.patch_h, cfg.patch_w);
     DG_LAUNCH_CHECK();
     linear_fwd<A, A, float>(c.Pm, WSel<A>::w(net, L.patch_w), c.Xp, (int64_t)d.B * d.P, d.D, d.pd, EPI_BIAS,
                             P + L.patch_b, st);
     const int64_t tot2 = d.T * d.D;
-    embed_assemble_kernel<<<grid1d(tot2), 256, 0, st>>>(c.tok, c.Xp, P + L.pos, c.L[0].Xa, drop, tot2, d.N, d.D);
+    launch_k(embed_assemble_kernel, grid1d(tot2), 256, 0, st, c.tok, c.Xp, P + L.pos, c.L[0].Xa, drop, tot2, d.N, d.D);
     DG_LAUNCH_CHECK();
   }
   for (int l = 0; l < d.L; ++l) {
@@ -405,7 +405,7 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
     }
   }
   // c.Xout is compact [B, D] (token-0 rows of the last block)
-  pool_rmsnorm_fwd_kernel<<<(unsigned)cdiv(d.B, 8), 256, 0, st>>>(c.Xout, P + L.rms_g, c.z, d.B, 1, d.D,
+  launch_k(pool_rmsnorm_fwd_kernel, (unsigned)cdiv(d.B, 8), 256, 0, st, c.Xout, P + L.rms_g, c.z, d.B, 1, d.D,
                                                                    sqrtf((float)d.D));
   DG_LAUNCH_CHECK();
 }
@@ -417,15 +417,15 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
                            TrunkCtx<A>& c, int relu_tok, cudaStream_t st) {
   const float* P = net.params;
   float* G = net.grads;
-  pool_rmsnorm_bwd_kernel<<<d.B, 128, 0, st>>>(c.Xout, P + L.rms_g, c.dz, c.dXc, c.dXch, c.dg_rows, d.B, 1, d.D,
+  launch_k(pool_rmsnorm_bwd_kernel, d.B, 128, 0, st, c.Xout, P + L.rms_g, c.dz, c.dXc, c.dXch, c.dg_rows, d.B, 1, d.D,
                                                 sqrtf((float)d.D));
   DG_LAUNCH_CHECK();
   {  // dg = sum_b dg_rows
     const int S = pick_splitk(d.B);
     dim3 grid((unsigned)cdiv(d.D, 256), (unsigned)S);
-    colsum_partial_kernel<float><<<grid, 128, 0, st>>>(c.dg_rows, d.D, c.partial, d.B, d.D, cdiv(d.B, S));
+    launch_k(colsum_partial_kernel<float>, grid, 128, 0, st, c.dg_rows, d.D, c.partial, d.B, d.D, cdiv(d.B, S));
     DG_LAUNCH_CHECK();
-    reduce_partials_kernel<<<1, 256, 0, st>>>(c.partial, G + L.rms_g, S, d.D);
+    launch_k(reduce_partials_kernel, 1, 256, 0, st, c.partial, G + L.rms_g, S, d.D);
     DG_LAUNCH_CHECK();
   }
   for (int l = d.L - 1; l >= 0; --l) {
@@ -471,7 +471,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
                             nullptr, ostride);
       // expand the compact residual gradient to [T, D] (zero off token 0) for the LayerNorm-1 backward
       const int64_t tot = d.T * d.D;
-      scatter_row0_kernel<<<grid1d(tot), 256, 0, st>>>(c.dXc, c.dX, tot, d.N, d.D);
+      launch_k(scatter_row0_kernel, grid1d(tot), 256, 0, st, c.dXc, c.dX, tot, d.N, d.D);
       DG_LAUNCH_CHECK();
     }
     launch_attention_bwd<A>(B_.QKV, B_.O, c.dO, c.dQKV, d, st);
@@ -482,14 +482,14 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
   }
   // ---- embedding.  c.dX = dL/dX0 (post-dropout)
   const int64_t tot = d.T * d.D;
-  embed_bwd_kernel<A><<<grid1d(tot), 256, 0, st>>>(c.dX, c.tok, c.dXp, c.dtok, drop, tot, d.N, d.D, relu_tok);
+  launch_k(embed_bwd_kernel<A>, grid1d(tot), 256, 0, st, c.dX, c.tok, c.dXp, c.dtok, drop, tot, d.N, d.D, relu_tok);
   DG_LAUNCH_CHECK();
   {
     const int S = std::max(1, std::min(32, d.B / 8));
-    dpos_kernel<<<dim3(d.N, S), 128, 0, st>>>(c.dX, c.partial, drop, d.B, d.N, d.D);
+    launch_k(dpos_kernel, dim3(d.N, S), 128, 0, st, c.dX, c.partial, drop, d.B, d.N, d.D);
     DG_LAUNCH_CHECK();
     const int64_t n = (int64_t)d.N * d.D;
-    reduce_partials_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(c.partial, G + L.pos, S, n);
+    launch_k(reduce_partials_kernel, (unsigned)cdiv(n, 256), 256, 0, st, c.partial, G + L.pos, S, n);
     DG_LAUNCH_CHECK();
   }
   linear_bwd_w<A, A>(c.dXp, c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st);
@@ -536,7 +536,7 @@ static void actor_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
   const float* P = net.params;
   DG_REQUIRE(io.img && io.pstate && io.action_scale && io.action_bias, "actor_forward: null input");
   DG_REQUIRE(io.eps || io.drop.rng_state, "actor_forward: provide eps or drop.rng_state");
-  goal_embed_kernel<<<(unsigned)cdiv((int64_t)d.B * d.D, 256), 256, 0, st>>>(io.pstate, P + L.embed_w, P + L.embed_b,
+  launch_k(goal_embed_kernel, (unsigned)cdiv((int64_t)d.B * d.D, 256), 256, 0, st, io.pstate, P + L.embed_w, P + L.embed_b,
                                                                              c.t.tok, d.B, d.D, d.nps, 0);
   DG_LAUNCH_CHECK();
   const DropDev drop = make_drop(io.drop, d, io.sample_offset);
@@ -558,7 +558,7 @@ static void actor_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
   s.sample_offset = io.sample_offset;
   s.mean_out = io.mean; s.log_std = io.log_std; s.action = io.action; s.log_prob = io.log_prob; s.mean_t = io.mean_t;
   s.eps_out = c.eps;
-  actor_sample_kernel<<<(unsigned)cdiv(d.B, 128), 128, 0, st>>>(s);
+  launch_k(actor_sample_kernel, (unsigned)cdiv(d.B, 128), 128, 0, st, s);
   DG_LAUNCH_CHECK();
   if (io.eps_out)
     DG_CUDA(cudaMemcpyAsync(io.eps_out, c.eps, (size_t)d.B * d.na * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -578,7 +578,7 @@ static void actor_backward(const dgvit_net& net, const dgvit_layout& L, const Di
   s.d_mean_t = g.d_mean_t; s.d_log_prob_const = g.d_log_prob_const;
   s.d_log_prob_dev = alpha_dev; s.d_log_prob_dev_scale = alpha_scale;
   s.d_mean_out = c.dmean; s.d_lstd_out = c.dlstd;
-  actor_sample_bwd_kernel<<<(unsigned)cdiv((int64_t)d.B * d.na, 128), 128, 0, st>>>(s);
+  launch_k(actor_sample_bwd_kernel, (unsigned)cdiv((int64_t)d.B * d.na, 128), 128, 0, st, s);
   DG_LAUNCH_CHECK();
   {
     heads::BwdArgs h;
@@ -646,7 +646,7 @@ static void critic_forward(const dgvit_net& net, const dgvit_layout& L, const Di
                            int64_t sample_offset, CriticCtx<A>& c, cudaStream_t st) {
   const float* P = net.params;
   DG_REQUIRE(io.img && io.pstate && io.action && io.q1 && io.q2, "critic_forward: null input/output");
-  goal_embed_kernel<<<(unsigned)cdiv((int64_t)d.B * d.D, 256), 256, 0, st>>>(io.pstate, P + L.embed_w, P + L.embed_b,
+  launch_k(goal_embed_kernel, (unsigned)cdiv((int64_t)d.B * d.D, 256), 256, 0, st, io.pstate, P + L.embed_w, P + L.embed_b,
                                                                              c.t.tok, d.B, d.D, d.nps, 1);
   DG_LAUNCH_CHECK();
   const DropDev drop = make_drop(io.drop, d, sample_offset);
@@ -683,7 +683,7 @@ static void critic_backward(const dgvit_net& net, const dgvit_layout& L, const D
     }
   }
   const int W = d.D + d.na;
-  split_dza_kernel<<<(unsigned)cdiv((int64_t)d.B * W, 256), 256, 0, st>>>(c.dxa, c.dxb, param_grads ? c.t.dz : nullptr,
+  launch_k(split_dza_kernel, (unsigned)cdiv((int64_t)d.B * W, 256), 256, 0, st, c.dxa, c.dxb, param_grads ? c.t.dz : nullptr,
                                                                           d_action, d.B, d.D, d.na);
   DG_LAUNCH_CHECK();
   if (param_grads) {
@@ -699,7 +699,7 @@ static void critic_backward(const dgvit_net& net, const dgvit_layout& L, const D
 static void adam_step(const dgvit_net& net, const dgvit_layout& L, const dgvit_adam& o, const dgvit_net* tgt,
                       float tau, bool want_shadow, cudaStream_t st) {
   DG_REQUIRE(o.m && o.v && o.step, "adam: null state");
-  step_bump_kernel<<<1, 32, 0, st>>>(o.step);
+  launch_k(step_bump_kernel, 1, 32, 0, st, o.step);
   DG_LAUNCH_CHECK();
   AdamArgs a;
   a.p = net.params; a.g = net.grads; a.m = o.m; a.v = o.v;
@@ -713,7 +713,7 @@ static void adam_step(const dgvit_net& net, const dgvit_layout& L, const dgvit_a
   a.omb2 = (float)(1.0 - (double)o.beta2);
   a.n_skip = L.n_skip;
   for (int k = 0; k < 4; ++k) { a.skip_b[k] = L.skip_begin[k]; a.skip_e[k] = L.skip_end[k]; }
-  adam_polyak_kernel<<<148 * 4, 256, 0, st>>>(a);
+  launch_k(adam_polyak_kernel, 148 * 4, 256, 0, st, a);
   DG_LAUNCH_CHECK();
 }
 
@@ -821,7 +821,7 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   DG_CUDA(cudaEventRecord(f.join[1], f.aux[1]));
   // ---- losses + critic backward                                                 (DRL.py:396-401)
   DG_CUDA(cudaStreamWaitEvent(st, f.join[0], 0));
-  critic_loss_kernel<<<1, 1024, 0, st>>>(w.q1, w.q2, w.q1t, w.q2t, w.logp2, b.rew, s.alpha, s.gamma, d.B, d.na,
+  launch_k(critic_loss_kernel, 1, 1024, 0, st, w.q1, w.q2, w.q1t, w.q2t, w.logp2, b.rew, s.alpha, s.gamma, d.B, d.na,
                                          s.global_batch, w.nq, w.dq1, w.dq2, out.losses);
   DG_LAUNCH_CHECK();
   critic_backward<A>(s.critic, Lc, d, cs, s.sample_offset, w.dq1, w.dq2, nullptr, true, w.critic_s, nullptr, st);
@@ -854,7 +854,7 @@ static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   ci.drop = sac_drop(s, nz, nz ? nz->mask_c_pi : nullptr, 5);
   ci.q1 = w.q1p; ci.q2 = w.q2p;
   critic_forward<A>(s.critic, Lc, d, ci, s.sample_offset, w.critic_tmp, st);
-  policy_loss_kernel<<<1, 1024, 0, st>>>(w.q1p, w.q2p, w.logpi, s.alpha, s.log_alpha, s.target_entropy, d.B, d.na,
+  launch_k(policy_loss_kernel, 1, 1024, 0, st, w.q1p, w.q2p, w.logpi, s.alpha, s.log_alpha, s.target_entropy, d.B, d.na,
                                          s.global_batch, w.dq1, w.dq2, out.losses, s.actor.grads + La.alpha_grad_slot);
   DG_LAUNCH_CHECK();
   // d policy_loss / d pi through the critic heads only (the critic's own parameter gradients
@@ -880,18 +880,18 @@ static void sac_phase3(const dgvit_sac& s, cudaStream_t st) {
   const bool shadow = s.precision == DGVIT_BF16;
   adam_step(s.actor, La, s.actor_opt, nullptr, 0.f, shadow, st);                 // DRL.py:413
   if (s.auto_alpha) {                                                            // DRL.py:416-423
-    alpha_step_kernel<<<1, 32, 0, st>>>(s.log_alpha, s.alpha, s.alpha_m, s.alpha_v, s.alpha_step,
+    launch_k(alpha_step_kernel, 1, 32, 0, st, s.log_alpha, s.alpha, s.alpha_m, s.alpha_v, s.alpha_step,
                                         s.actor.grads + La.alpha_grad_slot, s.lr_alpha, 0.9f, 0.999f,
                                         (float)(1.0 - 0.9), (float)(1.0 - 0.999), 1e-8f);
     DG_LAUNCH_CHECK();
   }
   if (s.do_polyak) {                                                             // DRL.py:430-431
-    polyak_kernel<<<148 * 4, 256, 0, st>>>(s.critic_target.params, s.critic.params,
+    launch_k(polyak_kernel, 148 * 4, 256, 0, st, s.critic_target.params, s.critic.params,
                                            shadow ? (bf16*)s.critic_target.shadow : nullptr, s.tau, Lc.total);
     DG_LAUNCH_CHECK();
   }
   if (s.rng_state) {
-    rng_advance_kernel<<<1, 32, 0, st>>>(s.rng_state);
+    launch_k(rng_advance_kernel, 1, 32, 0, st, s.rng_state);
     DG_LAUNCH_CHECK();
   }
 }
@@ -941,6 +941,7 @@ int dgvit_set_option(const char* name, int value) {
   return guarded([&] {
     DG_REQUIRE(name != nullptr, "null option name");
     if (!strcmp(name, "fork_streams")) g_fork_enabled = value != 0;
+    else if (!strcmp(name, "pdl")) pdl_enabled() = value != 0;
 #ifdef DGVIT_WITH_TC
     else if (!strcmp(name, "tensor_cores")) tc::g_tc_enabled = value != 0;
 #endif
@@ -1014,7 +1015,7 @@ int dgvit_refresh_shadow(const dgvit_net* net, void* stream) {
     DG_REQUIRE(net && net->params && net->shadow, "null argument");
     dgvit_layout L;
     make_layout(net->cfg, L);
-    shadow_refresh_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(net->params, (bf16*)net->shadow, L.total);
+    launch_k(shadow_refresh_kernel, 148 * 4, 256, 0, (cudaStream_t)stream, net->params, (bf16*)net->shadow, L.total);
     DG_LAUNCH_CHECK();
   });
 }
@@ -1239,7 +1240,7 @@ int dgvit_polyak(const dgvit_net* target, const dgvit_net* source, float tau, vo
     make_layout(target->cfg, L);
     make_layout(source->cfg, Ls);
     DG_REQUIRE(L.total == Ls.total, "polyak: layouts differ");
-    polyak_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(target->params, source->params, (bf16*)target->shadow, tau,
+    launch_k(polyak_kernel, 148 * 4, 256, 0, (cudaStream_t)stream, target->params, source->params, (bf16*)target->shadow, tau,
                                                              L.total);
     DG_LAUNCH_CHECK();
   });
@@ -1257,7 +1258,7 @@ int dgvit_replay_gather(const dgvit_replay* s, const int64_t* idx, int B, float*
     const int64_t frame4 = s->frame / 4;
     const int chunks = (int)std::min<int64_t>(cdiv(frame4, 256), 8);
     dim3 grid((unsigned)chunks, (unsigned)B, 2);
-    replay_gather_frames_kernel<<<grid, 256, 0, st>>>((const float4*)s->obs, idx, s->size, frame4, (float4*)obs,
+    launch_k(replay_gather_frames_kernel, grid, 256, 0, st, (const float4*)s->obs, idx, s->size, frame4, (float4*)obs,
                                                       (float4*)next_obs);
     DG_LAUNCH_CHECK();
     SmallGather g;
@@ -1267,7 +1268,7 @@ int dgvit_replay_gather(const dgvit_replay* s, const int64_t* idx, int B, float*
     g.src[2] = s->act; g.dst[2] = act; g.width[2] = s->n_act;
     g.src[3] = s->rew; g.dst[3] = rew; g.width[3] = 1;
     g.src[4] = s->done; g.dst[4] = done; g.width[4] = 1;
-    replay_gather_small_kernel<<<(unsigned)cdiv(B, 128), 128, 0, st>>>(g, idx, B);
+    launch_k(replay_gather_small_kernel, (unsigned)cdiv(B, 128), 128, 0, st, g, idx, B);
     DG_LAUNCH_CHECK();
   });
 }

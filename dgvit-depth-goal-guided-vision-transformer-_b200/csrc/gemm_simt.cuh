@@ -43,6 +43,8 @@ constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_PAD = 4;
 
 template <typename TA, typename TB, typename TC>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
+  pdl_wait();
+  pdl_launch();
   __shared__ __align__(16) float As[SG_BK][SG_BM + SG_PAD];
   __shared__ __align__(16) float Bs[SG_BK][SG_BN + SG_PAD];
   const TA* __restrict__ A = (const TA*)g.A;
@@ -148,6 +150,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
 // out[i] = sum_s partial[s, i]   (fixed order: deterministic)
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                        int S, int64_t n) {
+  pdl_wait();
+  pdl_launch();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;
@@ -161,12 +165,12 @@ static void gemm_simt(const GemmArgs& g, cudaStream_t st) {
   DG_REQUIRE(g.splitk >= 1 && (g.splitk == 1 || (g.partial && g.epi == EPI_NONE)),
              "gemm_simt: split-K needs a partial buffer and EPI_NONE");
   dim3 grid((unsigned)cdiv(g.N, SG_BN), (unsigned)cdiv(g.M, SG_BM), (unsigned)g.splitk);
-  gemm_simt_kernel<TA, TB, TC><<<grid, 256, 0, st>>>(g);
+  launch_k(gemm_simt_kernel<TA, TB, TC>, grid, 256, 0, st, g);
   DG_LAUNCH_CHECK();
   if (g.splitk > 1) {
     DG_REQUIRE(g.ldc == g.N, "gemm_simt: split-K output must be dense");
     const int64_t n = (int64_t)g.M * g.N;
-    reduce_partials_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(g.partial, (float*)g.C, g.splitk, n);
+    launch_k(reduce_partials_kernel, (unsigned)cdiv(n, 256), 256, 0, st, g.partial, (float*)g.C, g.splitk, n);
     DG_LAUNCH_CHECK();
   }
 }

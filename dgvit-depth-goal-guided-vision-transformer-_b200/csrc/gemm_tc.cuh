@@ -233,7 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32 : (ACC_STAGES * BN <= 64) ? 64 : (ACC_STAGES * BN <= 128) ? 128
                                  : (ACC_STAGES * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-B alignment
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B needs 1024-B alignment
   uint64_t* full_bar = (uint64_t*)(smem + SL::TILES_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -258,6 +258,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -563,7 +566,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a
   }
   const int tiles = (int)(cdiv(a.M, BM) * cdiv(a.N, BN) * a.splitk);
   const int grid = std::min(tiles, sm_count());
-  gemm_tc_kernel<BN, A_MN, B_MN, TC><<<grid, EpiCfg<BN>::THREADS, SL::TOTAL, st>>>(ta, tb, a);
+  launch_k(gemm_tc_kernel<BN, A_MN, B_MN, TC>, grid, EpiCfg<BN>::THREADS, SL::TOTAL, st, ta, tb, a);
   DG_LAUNCH_CHECK();
 }
 
@@ -638,7 +641,7 @@ static bool gemm_tc_try(const GemmArgs& g0, cudaStream_t st) {
     if (a.splitk > 1) {
       const int64_t n = (int64_t)g0.M * g0.N;
       DG_REQUIRE(g0.ldc == g0.N, "gemm_tc: split-K output must be dense");
-      reduce_partials_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(g.partial, (float*)g0.C, a.splitk, n);
+      launch_k(reduce_partials_kernel, (unsigned)cdiv(n, 256), 256, 0, st, g.partial, (float*)g0.C, a.splitk, n);
       DG_LAUNCH_CHECK();
     }
     return true;

@@ -32,6 +32,8 @@ __host__ __device__ __forceinline__ int odd_pitch(int k) { return k | 1; }
 __host__ __device__ __forceinline__ int al4(int n) { return (n + 3) & ~3; }
 
 __global__ void __launch_bounds__(128) head_fwd_kernel(FwdArgs a) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ __align__(16) float sm[];
   const HeadW& w = a.w[blockIdx.y];
   const int K0 = a.K1 + a.K2, H2 = a.H2, NO = a.NOa + a.NOb;
@@ -127,6 +129,8 @@ struct BwdArgs {
 };
 
 __global__ void __launch_bounds__(256) head_bwd_dx_kernel(BwdArgs a) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];
   const BwdHead& h = a.h[blockIdx.y];
   const int K0 = a.K0, H2 = a.H2, NO = a.NOa + a.NOb;
@@ -191,6 +195,8 @@ struct DwArgs {
   int njobs, B, total_tiles;
 };
 __global__ void __launch_bounds__(256) head_dw_kernel(DwArgs a) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float dys[32][33];
   __shared__ float xs[32][33];
   int ji = 0;
@@ -248,7 +254,7 @@ static void launch_fwd(const FwdArgs& a, cudaStream_t st) {
     attr = 227 * 1024;
   }
   dim3 grid((unsigned)std::min<int64_t>(cdiv(a.B, S), 148), (unsigned)a.nheads);
-  head_fwd_kernel<<<grid, 128, smem, st>>>(a);
+  launch_k(head_fwd_kernel, grid, 128, smem, st, a);
   DG_LAUNCH_CHECK();
 }
 static void launch_bwd_dx(const BwdArgs& a, cudaStream_t st) {
@@ -261,7 +267,7 @@ static void launch_bwd_dx(const BwdArgs& a, cudaStream_t st) {
     attr = 227 * 1024;
   }
   dim3 grid((unsigned)std::min<int64_t>(cdiv(a.B, S), 148), (unsigned)a.nheads);
-  head_bwd_dx_kernel<<<grid, 256, smem, st>>>(a);
+  launch_k(head_bwd_dx_kernel, grid, 256, smem, st, a);
   DG_LAUNCH_CHECK();
 }
 struct DwList {
@@ -274,7 +280,7 @@ struct DwList {
     a.total_tiles += (int)(cdiv(N, 32) * cdiv(K, 32));
   }
   void launch(cudaStream_t st) {
-    head_dw_kernel<<<a.total_tiles, 256, 0, st>>>(a);
+    launch_k(head_dw_kernel, a.total_tiles, 256, 0, st, a);
     DG_LAUNCH_CHECK();
   }
 };

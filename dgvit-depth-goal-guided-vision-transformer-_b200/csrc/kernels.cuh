@@ -15,6 +15,8 @@ namespace dgvit {
 template <typename A>
 __global__ void patchify_kernel(const float* __restrict__ img, A* __restrict__ out, int64_t total4,
                                 int img_h, int img_w, int ph, int pw) {
+  pdl_wait();
+  pdl_launch();
   // one thread = 4 consecutive pixels of one patch row (pw % 4 == 0, img_w % 4 == 0)
   const int gw = img_w / pw, gh = img_h / ph;
   const int q4 = pw / 4, pd4 = ph * q4, P = gh * gw;
@@ -36,6 +38,8 @@ __global__ void patchify_kernel(const float* __restrict__ img, A* __restrict__ o
 __global__ void goal_embed_kernel(const float* __restrict__ ps, const float* __restrict__ W,
                                   const float* __restrict__ bias, float* __restrict__ tok, int B, int D,
                                   int npst, int relu) {
+  pdl_wait();
+  pdl_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i % D;
@@ -48,6 +52,8 @@ __global__ void goal_embed_kernel(const float* __restrict__ ps, const float* __r
 __global__ void embed_assemble_kernel(const float* __restrict__ tok, const float* __restrict__ Xp,
                                       const float* __restrict__ pos, float* __restrict__ X0, DropDev drop,
                                       int64_t total, int N, int D) {
+  pdl_wait();
+  pdl_launch();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int d = (int)(i % D);
@@ -64,6 +70,8 @@ template <typename A>
 __global__ void embed_bwd_kernel(const float* __restrict__ dX0, const float* __restrict__ tok,
                                  A* __restrict__ dXp, float* __restrict__ dtok, DropDev drop, int64_t total,
                                  int N, int D, int relu) {
+  pdl_wait();
+  pdl_launch();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int d = (int)(i % D);
@@ -83,6 +91,8 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dX0, const float* __r
 // grid (N, S); a reduce_partials pass finishes the sum deterministically.
 __global__ void dpos_kernel(const float* __restrict__ dX0, float* __restrict__ part, DropDev drop, int B,
                             int N, int D) {
+  pdl_wait();
+  pdl_launch();
   const int n = blockIdx.x, s = blockIdx.y, S = gridDim.y;
   const int per = (B + S - 1) / S;
   const int b0 = s * per, b1 = min(B, b0 + per);
@@ -103,6 +113,8 @@ template <typename A, int VPL>  // D = 32*VPL
 __global__ void layernorm_fwd_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, A* __restrict__ Y,
                                      float* __restrict__ mean, float* __restrict__ rstd, int64_t T) {
+  pdl_wait();
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= T) return;
@@ -131,6 +143,8 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dY, const float* 
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const float* __restrict__ gamma, float* __restrict__ dX_io,
                                      bf16* __restrict__ dX_lp, float* __restrict__ part, int64_t T) {
+  pdl_wait();
+  pdl_launch();
   constexpr int D = 32 * VPL;
   extern __shared__ float sm[];  // [warps][2][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -180,6 +194,8 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dY, const float* 
 __global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* __restrict__ part,
                                                                float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, int nblocks, int D) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + cx;
@@ -212,6 +228,8 @@ __device__ __forceinline__ float2 ld2(const bf16* p) {
 template <typename T_>
 __global__ void colsum_partial_kernel(const T_* __restrict__ A, int64_t lda, float* __restrict__ part,
                                       int64_t rows, int N, int64_t rows_per_block) {
+  pdl_wait();
+  pdl_launch();
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (n >= N) return;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
@@ -247,6 +265,8 @@ __global__ void colsum_partial_kernel(const T_* __restrict__ A, int64_t lda, flo
 template <typename A>
 __global__ void attention_fwd_kernel(const A* __restrict__ QKV, A* __restrict__ O, int N, int H, int dh,
                                      float scale) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int inner = H * dh, ld = 3 * inner, kst = dh + 1;
@@ -295,6 +315,8 @@ template <typename A>
 __global__ void attention_bwd_kernel(const A* __restrict__ QKV, const A* __restrict__ O,
                                      const A* __restrict__ dO, A* __restrict__ dQKV, int N, int H, int dh,
                                      float scale) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ float sm[];
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int inner = H * dh, ld = 3 * inner, st = dh + 1, nw = blockDim.x >> 5;
@@ -386,6 +408,8 @@ __global__ void attention_bwd_kernel(const A* __restrict__ QKV, const A* __restr
 // =====================================================================================
 __global__ void pool_rmsnorm_fwd_kernel(const float* __restrict__ X, const float* __restrict__ g,
                                         float* __restrict__ z, int B, int N, int D, float sqrtD) {
+  pdl_wait();
+  pdl_launch();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -401,6 +425,8 @@ __global__ void pool_rmsnorm_bwd_kernel(const float* __restrict__ X, const float
                                         const float* __restrict__ dz, float* __restrict__ dX,
                                         bf16* __restrict__ dX_lp, float* __restrict__ dg_rows, int B, int N,
                                         int D, float sqrtD) {
+  pdl_wait();
+  pdl_launch();
   const int b = blockIdx.x;
   const float* x = X + (int64_t)b * N * D;
   float* dx = dX + (int64_t)b * N * D;
@@ -435,6 +461,8 @@ __global__ void pool_rmsnorm_bwd_kernel(const float* __restrict__ X, const float
 // dX[b, n, :] = (n == 0) ? dXc[b, :] : 0     (last block: only token 0 carries gradient)
 __global__ void scatter_row0_kernel(const float* __restrict__ dXc, float* __restrict__ dX, int64_t total, int N,
                                     int D) {
+  pdl_wait();
+  pdl_launch();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int d = (int)(i % D);
@@ -459,6 +487,8 @@ struct SampleArgs {
   int B, na;
 };
 __global__ void actor_sample_kernel(SampleArgs a) {
+  pdl_wait();
+  pdl_launch();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
   float lp = 0.f;
@@ -501,6 +531,8 @@ struct SampleBwdArgs {
   int B, na;
 };
 __global__ void actor_sample_bwd_kernel(SampleBwdArgs a) {
+  pdl_wait();
+  pdl_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.B * a.na) return;
   const int b = i / a.na, j = i % a.na;
@@ -528,6 +560,8 @@ __global__ void actor_sample_bwd_kernel(SampleBwdArgs a) {
 
 // g *= (h > 0)
 __global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ h, int64_t n) {
+  pdl_wait();
+  pdl_launch();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && !(h[i] > 0.f)) g[i] = 0.f;
 }
@@ -535,6 +569,8 @@ __global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict_
 // cat([z, a]) (vn/got_sac_network.py:114) and its inverse for gradients
 __global__ void concat_za_kernel(const float* __restrict__ z, const float* __restrict__ a,
                                  float* __restrict__ out, int B, int D, int na) {
+  pdl_wait();
+  pdl_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int W = D + na;
   if (i >= B * W) return;
@@ -544,6 +580,8 @@ __global__ void concat_za_kernel(const float* __restrict__ z, const float* __res
 // dxcat = dx1 + dx2 ; split into dz and da
 __global__ void split_dza_kernel(const float* __restrict__ dx1, const float* __restrict__ dx2,
                                  float* __restrict__ dz, float* __restrict__ da, int B, int D, int na) {
+  pdl_wait();
+  pdl_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int W = D + na;
   if (i >= B * W) return;
@@ -577,6 +615,8 @@ __global__ void critic_loss_kernel(const float* __restrict__ q1, const float* __
                                    const float* __restrict__ alpha, float gamma, int B, int na,
                                    int Bglobal, float* __restrict__ nq_out, float* __restrict__ dq1,
                                    float* __restrict__ dq2, float* __restrict__ losses) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   const float al = *alpha;
   const float inv = 1.0f / ((float)Bglobal * na);
@@ -603,6 +643,8 @@ __global__ void policy_loss_kernel(const float* __restrict__ q1p, const float* _
                                    const float* __restrict__ log_alpha, float target_entropy, int B, int na,
                                    int Bglobal, float* __restrict__ dq1, float* __restrict__ dq2,
                                    float* __restrict__ losses, float* __restrict__ galpha) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   const float al = *alpha;
   const float inv = 1.0f / ((float)Bglobal * na);
@@ -631,6 +673,8 @@ __global__ void policy_loss_kernel(const float* __restrict__ q1p, const float* _
 __global__ void alpha_step_kernel(float* log_alpha, float* alpha, float* m, float* v, int64_t* step,
                                   const float* g, float lr, float b1, float b2, float omb1, float omb2,
                                   float eps) {
+  pdl_wait();
+  pdl_launch();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int64_t t = ++(*step);
   const float gr = *g;
@@ -655,9 +699,13 @@ struct AdamArgs {
   float omb1, omb2;                          // (float)(1 - beta) computed in double like torch
   int n_skip; int64_t skip_b[4], skip_e[4];
 };
-__global__ void step_bump_kernel(int64_t* step) { if (threadIdx.x == 0 && blockIdx.x == 0) ++(*step); }
+__global__ void step_bump_kernel(int64_t* step) {
+  pdl_wait();
+  pdl_launch(); if (threadIdx.x == 0 && blockIdx.x == 0) ++(*step); }
 
 __global__ void adam_polyak_kernel(AdamArgs a) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float sh[2];
   if (threadIdx.x == 0) {
     const double t = (double)(*a.step);
@@ -693,6 +741,8 @@ __global__ void adam_polyak_kernel(AdamArgs a) {
 
 __global__ void polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, bf16* tgt_shadow,
                               float tau, int64_t n) {
+  pdl_wait();
+  pdl_launch();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const float t = (tau == 1.0f) ? src[i] : tgt[i] * (1.0f - tau) + src[i] * tau;
@@ -702,12 +752,16 @@ __global__ void polyak_kernel(float* __restrict__ tgt, const float* __restrict__
 }
 
 __global__ void shadow_refresh_kernel(const float* __restrict__ p, bf16* __restrict__ s, int64_t n) {
+  pdl_wait();
+  pdl_launch();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     s[i] = __float2bfloat16_rn(p[i]);
 }
 
-__global__ void rng_advance_kernel(uint64_t* rng) { if (threadIdx.x == 0 && blockIdx.x == 0) rng[1] += 1; }
+__global__ void rng_advance_kernel(uint64_t* rng) {
+  pdl_wait();
+  pdl_launch(); if (threadIdx.x == 0 && blockIdx.x == 0) rng[1] += 1; }
 
 // =====================================================================================
 // Replay gather (cpprb sample(); vn/DRL.py:375-386): bit-exact 16-byte vectorised row copies.
@@ -716,6 +770,8 @@ __global__ void rng_advance_kernel(uint64_t* rng) { if (threadIdx.x == 0 && bloc
 __global__ void replay_gather_frames_kernel(const float4* __restrict__ store, const int64_t* __restrict__ idx,
                                             int64_t size, int64_t frame4, float4* __restrict__ obs,
                                             float4* __restrict__ next_obs) {
+  pdl_wait();
+  pdl_launch();
   const int b = blockIdx.y;
   int64_t r = idx[b];
   float4* dst = obs;
@@ -735,6 +791,8 @@ struct SmallGather {
   const float* src[5]; float* dst[5]; int width[5]; int n;
 };
 __global__ void replay_gather_small_kernel(SmallGather s, const int64_t* __restrict__ idx, int B) {
+  pdl_wait();
+  pdl_launch();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int64_t r = idx[b];

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const MlpArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
   uint64_t* x_full = bars;                 // 1
   uint64_t* w1_full = x_full + 1;          // NST
@@ -101,6 +101,9 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;     // acc1: cols [0,256) ; Y: cols [256,320)
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -249,8 +252,8 @@ static void fwd(const bf16* x, const bf16* W1, const float* b1, const bf16* W2, 
     attr = true;
   }
   const int grid = (int)cdiv(M, 128);
-  if (hpre) mlp_fwd_tc_kernel<true><<<grid, THREADS, SMEM_TOTAL, st>>>(tx, tw1, tw2, a);
-  else mlp_fwd_tc_kernel<false><<<grid, THREADS, SMEM_TOTAL, st>>>(tx, tw1, tw2, a);
+  if (hpre) launch_k(mlp_fwd_tc_kernel<true>, grid, THREADS, SMEM_TOTAL, st, tx, tw1, tw2, a);
+  else launch_k(mlp_fwd_tc_kernel<false>, grid, THREADS, SMEM_TOTAL, st, tx, tw1, tw2, a);
   DG_LAUNCH_CHECK();
 }
 
