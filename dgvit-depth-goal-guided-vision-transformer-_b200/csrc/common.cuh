@@ -205,6 +205,26 @@ __device__ __forceinline__ void gelu_fast(float x, float& y, float& dy) {
   dy = fmaf(x * 0.39894228f, e, cdf);
 }
 
+// 3-term Abramowitz-Stegun erf (7.1.25, |err| <= 2.5e-5: far below bf16 resolution of the outputs)
+__device__ __forceinline__ float gelu3(float x) {
+  const float t = rcp_approx(fmaf(0.33267264f, fabsf(x), 1.0f));
+  const float e = ex2_approx(-0.72134752f * x * x);
+  float poly = fmaf(t, 0.7478556f, -0.0958798f);
+  poly = fmaf(t, poly, 0.3480242f);
+  const float erfa = fmaf(-poly * t, e, 1.0f);
+  return x * fmaf(0.5f, copysignf(erfa, x), 0.5f);
+}
+__device__ __forceinline__ void gelu3_grad(float x, float& y, float& dy) {
+  const float t = rcp_approx(fmaf(0.33267264f, fabsf(x), 1.0f));
+  const float e = ex2_approx(-0.72134752f * x * x);
+  float poly = fmaf(t, 0.7478556f, -0.0958798f);
+  poly = fmaf(t, poly, 0.3480242f);
+  const float erfa = fmaf(-poly * t, e, 1.0f);
+  const float cdf = fmaf(0.5f, copysignf(erfa, x), 0.5f);
+  y = x * cdf;
+  dy = fmaf(x * 0.39894228f, e, cdf);
+}
+
 // ---------------------------------------------------------------- counter-based RNG
 // Philox4x32-10; key = seed, counter = (index, stream_id, update counter).
 struct Philox {

@@ -944,6 +944,7 @@ int dgvit_set_option(const char* name, int value) {
     else if (!strcmp(name, "pdl")) pdl_enabled() = value != 0;
 #ifdef DGVIT_WITH_TC
     else if (!strcmp(name, "tensor_cores")) tc::g_tc_enabled = value != 0;
+    else if (!strcmp(name, "debug_epilogue")) tc::g_debug = value;
 #endif
     else fail(DGVIT_ERR_ARG, "unknown option %s", name);
   });

@@ -54,7 +54,9 @@ def attention(bwd):
     return timeit(b if bwd else f)
 
 
-print(f"B={B} T={T}")
+import os
+if os.environ.get("DBG"): L.check(lib.dgvit_set_option(b"debug_epilogue", int(os.environ["DBG"])))
+print(f"B={B} T={T} DBG={os.environ.get('DBG')}")
 for name, args in [("QKV      x[T,64]  W[768,64]           none", (T, 768, 64, 0)),
                    ("fc1      x[T,64]  W[2048,64]   bias+gelu2", (T, 2048, 64, 1)),
                    ("dH       dy[T,64] W2[64,2048]    gelu_bwd", (T, 2048, 64, 2, 1)),
