@@ -38,7 +38,7 @@ F_A, F_C = 190_371_072, 190_371_328
 FLOP_PER_SAMPLE = 4 * F_A + 5 * F_C
 # dram__bytes_read.sum + dram__bytes_write.sum of one mlp_fwd_tc_kernel launch (16640 rows, no pre-activation
 # store) from the `ncu --set full` capture summarised in profiles/ (None until captured)
-NCU_TRAFFIC_BYTES = None
+NCU_TRAFFIC_BYTES = 6951936   # profiles/r1_07_kernel_metrics.md (mlp_fwd_tc_kernel<0>, 16640 rows)
 
 
 def peaks():

@@ -67,3 +67,22 @@ for name, args in [("QKV      x[T,64]  W[768,64]           none", (T, 768, 64, 0
     print(f"{name}: {us:8.1f} us   {2 * rows * N * K / us / 1e6:7.1f} TFLOP/s   out {rows * N * 2 / us / 1e3:7.1f} GB/s")
 print(f"attention fwd: {attention(False):8.1f} us")
 print(f"attention bwd: {attention(True):8.1f} us")
+
+# ---- HBM-bound kernels: achieved bandwidth on ALGORITHMIC bytes
+import ctypes as C
+import dgvit_b200 as dg
+store = dg.ReplayStore(30000, (128, 160), 2, 2, dev, seed=1)
+store.fill_synthetic(30000, seed=2)
+for Bg in (256, 4096):
+    idx = torch.randint(0, 30000, (Bg,), device=dev)
+    out = {k: torch.empty(Bg, w, device=dev) for k, w in dict(obs=20480, next_obs=20480, pobs=2, next_pobs=2, act=2, rew=1, done=1).items()}
+    us = timeit(lambda: store.gather(idx, out))
+    print(f"replay gather B={Bg}: {us:8.1f} us   {Bg * 327752 / us / 1e3:7.1f} GB/s (algorithmic 327,752 B/sample)")
+for n in (1, 64):
+    raw = torch.rand(n, 512, 640, device=dev) * 8
+    noise = torch.randn(n, 512, 640, device=dev) * 50
+    us = timeit(lambda: dg.depth_augment(raw, noise))
+    print(f"depth augment n={n}: {us:8.1f} us   {n * (1392640 + 1310720) / us / 1e3:7.1f} GB/s (algorithmic 2,703,360 B/frame with injected noise)")
+    rng = torch.tensor([1, 2], dtype=torch.int64, device=dev)
+    us = timeit(lambda: dg.depth_augment(raw, None, rng))
+    print(f"depth augment n={n} (in-kernel noise): {us:8.1f} us   {n * 1392640 / us / 1e3:7.1f} GB/s (algorithmic 1,392,640 B/frame)")
