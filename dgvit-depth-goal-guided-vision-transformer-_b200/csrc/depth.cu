@@ -41,19 +41,22 @@ __global__ void depth_minmax_kernel(const float* __restrict__ raw, float* __rest
   }
 }
 
+// N(0,1) draw of pixel gi: one Philox4x32 call serves the 4 pixels of an aligned group (two Box-Muller pairs)
+__device__ __forceinline__ float normal_at(const uint64_t* rng, int64_t gi) {
+  uint32_t r[4];
+  philox4x32(rng[0], (uint64_t)(gi >> 2), 0x6465707468000000ull | (rng[1] & 0xffffffffu), r);
+  const int q = (int)(gi & 3);
+  const float rad = sqrtf(-2.0f * __logf(u01(r[q & 2])));
+  float sn, cs;
+  __sincosf(6.283185307179586f * u01(r[(q & 2) + 1]), &sn, &cs);
+  return rad * ((q & 1) ? sn : cs);
+}
 __device__ __forceinline__ float noisy_px(const float* __restrict__ raw, const float* __restrict__ noise,
                                           const uint64_t* rng, int64_t gi, double scale, double shift) {
   // cv2.normalize(NORM_MINMAX, 0..255) then .astype(uint8) (truncation)
   const float nrm = (float)((double)raw[gi] * scale + shift);
   const float u8 = (float)(int)fminf(fmaxf(nrm, 0.f), 255.f);
-  float nz;
-  if (noise) {
-    nz = noise[gi];
-  } else {
-    uint32_t r[4];
-    philox4x32(rng[0], (uint64_t)gi, 0x6465707468000000ull | (rng[1] & 0xffffffffu), r);
-    nz = 50.0f * sqrtf(-2.0f * logf(u01(r[0]))) * cospif(2.0f * u01(r[1]));
-  }
+  const float nz = noise ? noise[gi] : 50.0f * normal_at(rng, gi);
   return fminf(fmaxf(u8 + nz, 0.f), 255.f);
 }
 
@@ -151,6 +154,140 @@ __global__ void depth_resize_kernel(const float* __restrict__ S2, const float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused pass: noise + 5x5 blur + centre-band 11x11 blur + 4x bilinear resize + /255 in one kernel.
+// One CTA = an 8 x 32 tile of OUTPUT pixels (32 x 128 input pixels + halo) staged in shared memory:
+//   A  = clip(u8(normalised) + noise)      halo 7 (band tiles) / 2 (other tiles)
+//   Bh = horizontal 5-tap of A, S2 = vertical 5-tap of Bh  (the GaussianBlur(5,5) image)
+//   T1 = horizontal 11-tap of S2 at the sampled columns (band tiles), vertical 11-tap at the
+//        sampled rows with BORDER_REFLECT_101 inside the band, then the 2x2 average = cv2.resize.
+// Out-of-image halo positions are filled by mirrored coordinates, which is exact for symmetric
+// kernels.  HBM traffic: raw (+noise) once; neighbouring tiles' halos hit L2.
+constexpr int TOH = 8, TOW = 32;                 // output tile
+constexpr int CORE_R = TOH * 4 - 2, CORE_C = TOW * 4 - 2;   // span of sampled rows / cols (30, 126)
+constexpr int A_R = CORE_R + 14, A_C = CORE_C + 14;         // 44 x 140 (halo 7)
+constexpr int S_R = CORE_R + 10, S_C = CORE_C + 10;         // 40 x 136 (halo 5)
+constexpr int A_P = A_C + 1, S_P = S_C + 1;                 // padded pitches
+constexpr int FUSED_SMEM = (A_R * A_P + A_R * S_P) * 4 + 32;   // S2 reuses A, T1 reuses Bh
+
+__global__ void __launch_bounds__(256) depth_fused_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
+                                                          const uint64_t* rng, const float* __restrict__ mmpart,
+                                                          K11 kk, float* __restrict__ out, int H, int W, int y1, int bh) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ __align__(16) float smf[];
+  float* A = smf;                       // [A_R][A_P]
+  float* Bh = A + A_R * A_P;            // [A_R][S_P]
+  float* S2 = A;                        // [S_R][S_P]     (A is dead once Bh exists)
+  float* T1 = Bh;                       // [S_R][2*TOW]   (Bh is dead once S2 exists)
+  double* sc = reinterpret_cast<double*>(Bh + A_R * S_P);
+  const int f = blockIdx.z, oy0 = blockIdx.y * TOH, ox0 = blockIdx.x * TOW;
+  const int oh = H / 4, ow = W / 4;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (int b = 0; b < MM_BLOCKS; ++b) {
+      mn = fminf(mn, mmpart[((int64_t)f * MM_BLOCKS + b) * 2]);
+      mx = fmaxf(mx, mmpart[((int64_t)f * MM_BLOCKS + b) * 2 + 1]);
+    }
+    const double rg = (double)mx - (double)mn;
+    const double s = rg > 2.220446049250313e-16 ? 255.0 / rg : 0.0;
+    sc[0] = s;
+    sc[1] = 0.0 - (double)mn * s;
+  }
+  const int ys0 = oy0 * 4 + 1, xs0 = ox0 * 4 + 1;           // first sampled row / col of the tile
+  const int y2 = y1 + bh;
+  const bool band = (ys0 + CORE_R - 1 >= y1) && (ys0 < y2);  // some sampled row lies in the centre band
+  const int hs = band ? 5 : 0;                                // halo of S2, A needs hs + 2
+  const int ar = CORE_R + 2 * (hs + 2), ac = CORE_C + 2 * (hs + 2);
+  const int sr = CORE_R + 2 * hs, scn = CORE_C + 2 * hs;
+  __syncthreads();
+  const double scale = sc[0], shift = sc[1];
+  const float k5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+  const int64_t fbase = (int64_t)f * H * W;
+  {  // stage A: warp per window row, lanes over columns; all loads of a row issued before any use
+    const int lane = tid & 31, wrp = tid >> 5;
+    for (int r = wrp; r < ar; r += 8) {
+      const int gy = reflect101(ys0 - hs - 2 + r, H);
+      const int64_t rb = fbase + (int64_t)gy * W;
+      float rv[5], nv[5];
+      int gxs[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int c = lane + 32 * k;
+        gxs[k] = reflect101(xs0 - hs - 2 + min(c, ac - 1), W);
+        rv[k] = raw[rb + gxs[k]];
+        nv[k] = noise ? noise[rb + gxs[k]] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int c = lane + 32 * k;
+        if (c < ac) {
+          const float nrm = (float)((double)rv[k] * scale + shift);
+          const float u8 = (float)(int)fminf(fmaxf(nrm, 0.f), 255.f);
+          const float nz = noise ? nv[k] : 50.0f * normal_at(rng, rb + gxs[k]);
+          A[r * A_P + c] = fminf(fmaxf(u8 + nz, 0.f), 255.f);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < ar * scn; i += blockDim.x) {          // horizontal 5-tap
+    const int r = i / scn, c = i % scn;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) s = fmaf(k5[t], A[r * A_P + c + t], s);
+    Bh[r * S_P + c] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < sr * scn; i += blockDim.x) {          // vertical 5-tap -> GaussianBlur(5,5)
+    const int r = i / scn, c = i % scn;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) s = fmaf(k5[t], Bh[(r + t) * S_P + c], s);
+    S2[r * S_P + c] = s;
+  }
+  __syncthreads();
+  if (band) {                                                  // horizontal 11-tap at the sampled columns
+    for (int i = tid; i < sr * 2 * TOW; i += blockDim.x) {
+      const int r = i / (2 * TOW), j = i % (2 * TOW);
+      const int c = (j >> 1) * 4 + (j & 1);                    // sampled col relative to xs0
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < 11; ++t) s = fmaf(kk.k[t], S2[r * S_P + c + t], s);   // S2 col index = c + hs - 5 + t, hs = 5
+      T1[r * 2 * TOW + j] = s;
+    }
+    __syncthreads();
+  }
+  {
+    const int oy = oy0 + tid / TOW, ox = ox0 + tid % TOW;
+    if (oy < oh && ox < ow) {
+      float acc = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int y = oy * 4 + 1 + dy;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int j = (tid % TOW) * 2 + dx;
+          float v;
+          if (y >= y1 && y < y2) {
+            v = 0.f;
+#pragma unroll
+            for (int t = 0; t < 11; ++t) {
+              const int yy = y1 + reflect101(y - y1 + t - 5, bh);          // reflect inside the band
+              v = fmaf(kk.k[t], T1[(yy - (ys0 - hs)) * 2 * TOW + j], v);
+            }
+          } else {
+            v = S2[(y - (ys0 - hs)) * S_P + (j >> 1) * 4 + (j & 1) + hs];
+          }
+          acc += 0.25f * v;
+        }
+      }
+      out[((int64_t)f * oh + oy) * ow + ox] = acc / 255.0f;
+    }
+  }
+}
+
 }  // namespace dgvit
 
 using namespace dgvit;
@@ -191,15 +328,14 @@ int dgvit_depth_augment(const float* raw, const float* noise, const uint64_t* rn
     }
     launch_k(depth_minmax_kernel, dim3(MM_BLOCKS, n), 256, 0, st, raw, mm, (int64_t)H * W);
     DG_LAUNCH_CHECK();
-    const int xb = (int)cdiv(W, 256);
-    launch_k(depth_noise_hblur_kernel, dim3(xb, H, n), 256, 0, st, raw, noise, rng_state, mm, S1, H, W);
-    DG_LAUNCH_CHECK();
-    launch_k(depth_vblur5_kernel, dim3(xb, H, n), 256, 0, st, S1, S2, H, W);
-    DG_LAUNCH_CHECK();
-    launch_k(depth_band_hblur_kernel, dim3(xb, bh, n), 256, 0, st, S2, T1, kk, H, W, y1, bh);
-    DG_LAUNCH_CHECK();
-    const int fac = 4;
-    launch_k(depth_resize_kernel, dim3((unsigned)cdiv(W / fac, 128), H / fac, n), 128, 0, st, S2, T1, kk, out, H, W, y1, bh, fac);
+    static bool attr = false;
+    if (!attr) {
+      DG_CUDA(cudaFuncSetAttribute(depth_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
+      attr = true;
+    }
+    (void)S1; (void)S2; (void)T1;
+    launch_k(depth_fused_kernel, dim3((unsigned)cdiv(W / 4, TOW), (unsigned)cdiv(H / 4, TOH), n), 256, FUSED_SMEM, st, raw,
+             noise, rng_state, mm, kk, out, H, W, y1, bh);
     DG_LAUNCH_CHECK();
   });
 }

@@ -1257,7 +1257,8 @@ int dgvit_replay_gather(const dgvit_replay* s, const int64_t* idx, int B, float*
     if (B == 0) return;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t frame4 = s->frame / 4;
-    const int chunks = (int)std::min<int64_t>(cdiv(frame4, 256), 8);
+    // small batches: one float4 per thread (more CTAs in flight); large batches: 8 chunks per frame
+    const int chunks = (int)std::min<int64_t>(cdiv(frame4, 256), B <= 1024 ? 32 : 8);
     dim3 grid((unsigned)chunks, (unsigned)B, 2);
     launch_k(replay_gather_frames_kernel, grid, 256, 0, st, (const float4*)s->obs, idx, s->size, frame4, (float4*)obs,
                                                       (float4*)next_obs);

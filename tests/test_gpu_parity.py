@@ -296,3 +296,23 @@ def test_choose_action_batch1(precision, tol):
     x = a.choose_action(frame, goal)
     y = a.choose_action(frame, goal)
     assert np.all(np.abs(x) <= 1) and not np.array_equal(x, y)
+
+
+def test_depth_augment_in_kernel_noise_statistics():
+    """Generated noise (Philox + Box-Muller, sigma 50 on the 0..255 scale): same statistics as the
+    injected-noise path, deterministic for a given rng state, different across frames / counters."""
+    H, W, n = 512, 640, 4
+    raw = (torch.rand(n, H, W, generator=torch.Generator().manual_seed(3)) * 6 + 1).cuda()
+    rng = torch.tensor([1234, 0], dtype=torch.int64, device="cuda")
+    a = dg.depth_augment(raw, None, rng)
+    b = dg.depth_augment(raw, None, rng)
+    assert torch.equal(a, b)
+    rng2 = torch.tensor([1234, 1], dtype=torch.int64, device="cuda")
+    c = dg.depth_augment(raw, None, rng2)
+    assert not torch.equal(a, c) and not torch.equal(a[0], a[1])
+    noise = torch.randn(n, H, W, generator=torch.Generator().manual_seed(4)).cuda() * 50
+    ref = dg.depth_augment(raw, noise)
+    assert a.shape == ref.shape == (n, H // 4, W // 4)
+    assert float(a.min()) >= 0 and float(a.max()) <= 1
+    assert abs(float(a.mean()) - float(ref.mean())) < 5e-3
+    assert abs(float(a.std()) - float(ref.std())) < 5e-3
