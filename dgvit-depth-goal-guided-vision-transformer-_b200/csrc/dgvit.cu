@@ -327,14 +327,20 @@ static void launch_attention_bwd(const A* QKV, const A* O, const A* dO, A* dQKV,
   }
 #endif
   const int threads = 256, nw = threads / 32;
-  const size_t smem = ((size_t)4 * d.N * (d.dh + 1) + 2 * (size_t)d.N + 2 * (size_t)nw * d.N) * sizeof(float);
+  const size_t small = ((size_t)2 * d.N * (d.dh + 1) + 2 * (size_t)d.N + 2 * (size_t)nw * d.N + 2 * (size_t)nw * d.dh) * sizeof(float);
+  const size_t full = small + (size_t)2 * d.N * (d.dh + 1) * sizeof(float);
+  const bool qdo_smem = full <= 227 * 1024;
+  const size_t smem = qdo_smem ? full : small;
   DG_REQUIRE(smem <= 227 * 1024, "attention_bwd: N=%d dh=%d needs %zu B smem (unsupported in this build)", d.N, d.dh, smem);
   static bool attr_done = false;
   if (!attr_done) {
-    DG_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DG_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DG_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  launch_k(attention_bwd_kernel<A>, d.B * d.H, threads, smem, st, QKV, O, dO, dQKV, d.N, d.H, d.dh, 1.0f / sqrtf((float)d.dh));
+  const float scale = 1.0f / sqrtf((float)d.dh);
+  if (qdo_smem) launch_k(attention_bwd_kernel<A, true>, d.B * d.H, threads, smem, st, QKV, O, dO, dQKV, d.N, d.H, d.dh, scale);
+  else launch_k(attention_bwd_kernel<A, false>, d.B * d.H, threads, smem, st, QKV, O, dO, dQKV, d.N, d.H, d.dh, scale);
   DG_LAUNCH_CHECK();
 }
 

@@ -311,7 +311,9 @@ __global__ void attention_fwd_kernel(const A* __restrict__ QKV, A* __restrict__ 
 }
 
 // Backward: pass 1 (warp per query row) -> lse, delta, dQ ; pass 2 (warp per key row) -> dK, dV.
-template <typename A>
+// K and V always live in shared memory; Q and dO too when they fit (QDO_SMEM), otherwise (long
+// sequences, e.g. 257 tokens at 2x resolution) they are read through L1/L2.
+template <typename A, bool QDO_SMEM>
 __global__ void attention_bwd_kernel(const A* __restrict__ QKV, const A* __restrict__ O,
                                      const A* __restrict__ dO, A* __restrict__ dQKV, int N, int H, int dh,
                                      float scale) {
@@ -320,38 +322,49 @@ __global__ void attention_bwd_kernel(const A* __restrict__ QKV, const A* __restr
   extern __shared__ float sm[];
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int inner = H * dh, ld = 3 * inner, st = dh + 1, nw = blockDim.x >> 5;
-  float* Qs = sm;                  // [N][dh+1]
-  float* Ks = Qs + N * st;         // [N][dh+1]
+  float* Ks = sm;                  // [N][dh+1]
   float* Vs = Ks + N * st;         // [N][dh+1]
-  float* dOs = Vs + N * st;        // [N][dh+1]
-  float* lse = dOs + N * st;       // [N]
+  float* lse = Vs + N * st;        // [N]
   float* dlt = lse + N;            // [N]
   float* W1 = dlt + N;             // [warps][N]
   float* W2 = W1 + nw * N;         // [warps][N]
+  float* Qw = W2 + nw * N;         // [warps][dh]   (pass 1: this warp's query row)
+  float* dOw = Qw + nw * dh;       // [warps][dh]
+  float* Qs = dOw + nw * dh;       // [N][dh+1]     (QDO_SMEM only)
+  float* dOs = Qs + N * st;        // [N][dh+1]     (QDO_SMEM only)
   const A* base = QKV + (int64_t)b * N * ld + h * dh;
   const int64_t obase = (int64_t)b * N * inner + h * dh;
   for (int i = threadIdx.x; i < N * dh; i += blockDim.x) {
     const int j = i / dh, d = i % dh;
-    Qs[j * st + d] = ldf(base + (int64_t)j * ld + d);
     Ks[j * st + d] = ldf(base + (int64_t)j * ld + inner + d);
     Vs[j * st + d] = ldf(base + (int64_t)j * ld + 2 * inner + d);
-    dOs[j * st + d] = ldf(dO + obase + (int64_t)j * inner + d);
+    if (QDO_SMEM) {
+      Qs[j * st + d] = ldf(base + (int64_t)j * ld + d);
+      dOs[j * st + d] = ldf(dO + obase + (int64_t)j * inner + d);
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* P = W1 + warp * N;
   float* DS = W2 + warp * N;
+  float* q = Qw + warp * dh;
+  float* go = dOw + warp * dh;
   // ---- pass 1: rows of the score matrix
   for (int i = warp; i < N; i += nw) {
     float dl = 0.f;
-    for (int d = lane; d < dh; d += 32) dl = fmaf(dOs[i * st + d], ldf(O + obase + (int64_t)i * inner + d), dl);
+    for (int d = lane; d < dh; d += 32) {
+      q[d] = ldf(base + (int64_t)i * ld + d);
+      go[d] = ldf(dO + obase + (int64_t)i * inner + d);
+      dl = fmaf(go[d], ldf(O + obase + (int64_t)i * inner + d), dl);
+    }
     dl = warp_sum(dl);
+    __syncwarp();
     float mx = -INFINITY;
     for (int j = lane; j < N; j += 32) {
       float s = 0.f, dp = 0.f;
       for (int d = 0; d < dh; ++d) {
-        s = fmaf(Qs[i * st + d], Ks[j * st + d], s);
-        dp = fmaf(dOs[i * st + d], Vs[j * st + d], dp);
+        s = fmaf(q[d], Ks[j * st + d], s);
+        dp = fmaf(go[d], Vs[j * st + d], dp);
       }
       s *= scale;
       P[j] = s;
@@ -382,8 +395,10 @@ __global__ void attention_bwd_kernel(const A* __restrict__ QKV, const A* __restr
     for (int i = lane; i < N; i += 32) {
       float s = 0.f, dp = 0.f;
       for (int d = 0; d < dh; ++d) {
-        s = fmaf(Qs[i * st + d], Ks[j * st + d], s);
-        dp = fmaf(dOs[i * st + d], Vs[j * st + d], dp);
+        const float qv = QDO_SMEM ? Qs[i * st + d] : ldf(base + (int64_t)i * ld + d);
+        const float gv = QDO_SMEM ? dOs[i * st + d] : ldf(dO + obase + (int64_t)i * inner + d);
+        s = fmaf(qv, Ks[j * st + d], s);
+        dp = fmaf(gv, Vs[j * st + d], dp);
       }
       const float p = expf(s * scale - lse[i]);
       P[i] = p;
@@ -393,8 +408,10 @@ __global__ void attention_bwd_kernel(const A* __restrict__ QKV, const A* __restr
     for (int d = lane; d < dh; d += 32) {
       float dk = 0.f, dv = 0.f;
       for (int i = 0; i < N; ++i) {
-        dk = fmaf(DS[i], Qs[i * st + d], dk);
-        dv = fmaf(P[i], dOs[i * st + d], dv);
+        const float qv = QDO_SMEM ? Qs[i * st + d] : ldf(base + (int64_t)i * ld + d);
+        const float gv = QDO_SMEM ? dOs[i * st + d] : ldf(dO + obase + (int64_t)i * inner + d);
+        dk = fmaf(DS[i], qv, dk);
+        dv = fmaf(P[i], gv, dv);
       }
       stf(dQKV + ((int64_t)b * N + j) * ld + inner + h * dh + d, dk);
       stf(dQKV + ((int64_t)b * N + j) * ld + 2 * inner + h * dh + d, dv);

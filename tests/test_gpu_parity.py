@@ -316,3 +316,62 @@ def test_depth_augment_in_kernel_noise_statistics():
     assert float(a.min()) >= 0 and float(a.max()) <= 1
     assert abs(float(a.mean()) - float(ref.mean())) < 5e-3
     assert abs(float(a.std()) - float(ref.std())) < 5e-3
+
+
+def test_wide_deep_variant_at_2x_resolution():
+    """BASELINE config 5 shape family: 256x320 frames (257 tokens), D=128, 6 heads, fp32
+    forward + every parameter gradient vs the oracle, bf16 forward within tolerance."""
+    cfg = O.Cfg(dim=128, depth=2, heads=6, img_h=256, img_w=320)
+    B = 2
+    pa, pc = reference_init("actor", cfg, 51), reference_init("critic", cfg, 52)
+    batch, nz = synthetic_batch(cfg, B, 53), synthetic_noise(cfg, B, 54)
+    img, goal = batch["obs"], batch["pobs"]
+    pa_g = {k: v.clone().requires_grad_(True) for k, v in pa.items()}
+    pc_g = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    oa, olp, omt = O.actor_sample(pa_g, img, goal, nz["eps_pi"], cfg, nz["mask_a"])
+    oq1, oq2 = O.critic_forward(pc_g, img, goal, oa, cfg, nz["mask_c"])
+    (olp.mean() * 0.3 - torch.min(oq1, oq2).mean() + (oq1 ** 2).mean() * 0.1).backward()
+    a, c = _mk("actor", cfg, pa), _mk("critic", cfg, pc)
+    a.inject_noise(mask=nz["mask_a"], eps=nz["eps_pi"])
+    c.inject_noise(mask=nz["mask_c"])
+    act, lp, mt = a.sample([img.cuda(), goal.cuda()])
+    q1, q2 = c([img.cuda(), goal.cuda(), act])
+    for n, (x, y) in dict(action=(act, oa), logp=(lp, olp), q1=(q1, oq1), q2=(q2, oq2)).items():
+        assert relerr(x, y) < FP32_TOL, n
+    (lp.mean() * 0.3 - torch.min(q1, q2).mean() + (q1 ** 2).mean() * 0.1).backward()
+    for mod, og in ((a, pa_g), (c, pc_g)):
+        for k, p in mod.named_parameters():
+            if og[k].grad is None:
+                assert p.grad is None, k
+                continue
+            assert relerr(p.grad, og[k].grad) < 3e-4, (k, relerr(p.grad, og[k].grad))
+    ab, cb = _mk("actor", cfg, pa, "bf16"), _mk("critic", cfg, pc, "bf16")
+    with torch.no_grad():
+        ab.inject_noise(mask=nz["mask_a"], eps=nz["eps_pi"])
+        cb.inject_noise(mask=nz["mask_c"])
+        act_b, _, _ = ab.sample([img.cuda(), goal.cuda()])
+        q1_b, _ = cb([img.cuda(), goal.cuda(), oa.detach().cuda()])
+    assert relerr(act_b, oa) < BF16_TOL and relerr(q1_b, oq1) < BF16_TOL
+
+
+@pytest.mark.parametrize("B,precision", [(1, "fp32"), (3, "fp32"), (130, "bf16"), (1, "bf16")])
+def test_update_ragged_batches(B, precision):
+    """Batch sizes that do not fill a 128-row tile / a warp: one fused update vs the oracle."""
+    cfg = O.Cfg(dim=64, depth=2, heads=4)
+    ag = _agent(cfg, precision, seed=9)
+    actor0 = {k: v.detach().cpu().clone() for k, v in ag.policy.named_parameters()}
+    critic0 = {k: v.detach().cpu().clone() for k, v in ag.critic.named_parameters()}
+    orc = O.SACOracle(actor0, critic0, cfg)
+    batch, noise = synthetic_batch(cfg, B, 61), synthetic_noise(cfg, B, 62)
+    want = orc.learn(batch, noise)
+    cb = {k: v.reshape(B, -1).cuda().contiguous() for k, v in batch.items()}
+    got = ag.update_from_batch(cb, _noise_cuda(noise)).tolist()
+    tol = FP32_TOL if precision == "fp32" else 5e-2
+    assert abs(got[0] - want[0]) <= tol * max(1.0, abs(want[0])), (got, want)
+    assert abs(got[1] - want[1]) <= tol * max(1.0, abs(want[1])), (got, want)
+    for mod, od in ((ag.policy, orc.actor), (ag.critic, orc.critic)):
+        for k, p in mod.named_parameters():
+            d = (p.detach().cpu() - od[k]).abs()
+            assert torch.isfinite(p).all(), k
+            if precision == "fp32":
+                assert float((d > 2e-5).float().mean()) < 5e-3, k
