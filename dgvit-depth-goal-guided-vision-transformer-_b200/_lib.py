@@ -80,12 +80,13 @@ class Sac(C.Structure):
                 ("log_alpha", c_f_p), ("alpha", c_f_p), ("alpha_m", c_f_p), ("alpha_v", c_f_p), ("alpha_step", c_f_p),
                 ("lr_alpha", C.c_float), ("auto_alpha", C.c_int32), ("target_entropy", C.c_float),
                 ("gamma", C.c_float), ("tau", C.c_float), ("do_polyak", C.c_int32), ("precision", C.c_int32),
-                ("global_batch", C.c_int32), ("sample_offset", C.c_int32), ("rng_state", c_f_p),
+                ("global_batch", C.c_int32), ("n_extra", C.c_int32), ("sample_offset", C.c_int32), ("rng_state", c_f_p),
                 ("action_scale", c_f_p), ("action_bias", c_f_p)]
 
 
 class Batch(C.Structure):
-    _fields_ = [(n, c_f_p) for n in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done")]
+    _fields_ = [(n, c_f_p) for n in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done", "extra_target",
+                                     "extra_weight")]
 
 
 class Noise(C.Structure):
@@ -113,7 +114,7 @@ SYMBOLS = {
     "dgvit_prof_end": (C.c_int, [P(C.c_double), P(C.c_longlong), P(C.c_double), P(C.c_double)]),
     "dgvit_param_layout": (C.c_int, [P(Cfg), P(Layout)]),
     "dgvit_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
-    "dgvit_sac_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, P(C.c_size_t)]),
+    "dgvit_sac_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
     "dgvit_refresh_shadow": (C.c_int, [P(Net), C.c_void_p]),
     "dgvit_actor_forward": (C.c_int, [P(Net), P(ActorIO), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dgvit_actor_backward": (C.c_int, [P(Net), P(ActorIO), P(ActorGrad), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),

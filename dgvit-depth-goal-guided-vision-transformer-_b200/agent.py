@@ -40,6 +40,7 @@ class ReplayStore:
         self.rew = torch.zeros(self.cap, 1, dtype=torch.float32, device=self.device)
         self.done = torch.zeros(self.cap, 1, dtype=torch.float32, device=self.device)
         self.engage = torch.zeros(self.cap, 1, dtype=torch.float32, device=self.device)
+        self.engage_host = np.zeros(self.cap, dtype=np.float32)     # host mirror: engaged rows are selected on the host
         self.stored = 0
         self.head = 0
         self.action_dim, self.pstate_dim = action_dim, pstate_dim
@@ -60,6 +61,7 @@ class ReplayStore:
         self.rew[i] = float(rew)
         self.done[i] = float(done)
         self.engage[i] = float(engage)
+        self.engage_host[i] = float(engage)
         self.head = j if j < self.size else 0
         self.stored = min(self.stored + 1, self.size)
 
@@ -133,6 +135,11 @@ class SAC(object):
         set_seed(self.seed)
 
         self.replay_buffer = ReplayStore(BUFFER_SIZE, image_size, action_dim, pstate_dim, self.device, self.seed)
+        self.buffer_size_expert = buffer_size_expert + 1                    # vn/DRL.py:53
+        self.guidence_weight, self.engage_weight, self.batch_expert = 1.0, 1.0, 0          # vn/DRL.py:51-52,54
+        self.replay_buffer_expert = (ReplayStore(self.buffer_size_expert, image_size, action_dim, pstate_dim, self.device,
+                                                 self.seed + 1) if pre_buffer else None)    # vn/DRL.py:91-100
+        self._gbuf = {}
 
         # construction order == reference (critic, critic_target, policy): same seed -> same weights
         kw = dict(image_size=image_size, mlp_dim=mlp_dim)
@@ -179,7 +186,7 @@ class SAC(object):
     def rank(self):
         return torch.distributed.get_rank() if self.distributed else 0
 
-    def _sac_struct(self, B_local: int, B_global: int, offset: int) -> L.Sac:
+    def _sac_struct(self, B_local: int, B_global: int, offset: int, n_extra: int = 0) -> L.Sac:
         def adam(name, lr):
             o = self._opt[name]
             return L.Adam(m=o["m"].data_ptr(), v=o["v"].data_ptr(), step=o["step"].data_ptr(), lr=lr, beta1=0.9,
@@ -192,13 +199,13 @@ class SAC(object):
                      auto_alpha=int(self.automatic_entropy_tuning), target_entropy=self.target_entropy,
                      gamma=self.gamma, tau=self.tau, do_polyak=int(self.itera % self.policy_freq == 0),
                      precision={"fp32": L.FP32, "bf16": L.BF16}[self.precision], global_batch=B_global,
-                     sample_offset=offset, rng_state=self._rng.data_ptr(), action_scale=self._scale.data_ptr(),
+                     n_extra=n_extra, sample_offset=offset, rng_state=self._rng.data_ptr(), action_scale=self._scale.data_ptr(),
                      action_bias=self._bias.data_ptr())
 
-    def _workspace(self, B: int) -> torch.Tensor:
+    def _workspace(self, B: int, n_extra: int = 0) -> torch.Tensor:
         n = C.c_size_t()
         prec = {"fp32": L.FP32, "bf16": L.BF16}[self.precision]
-        L.check(L.lib().dgvit_sac_workspace_bytes(C.byref(self.policy._cfg), B, prec, C.byref(n)), "sac_workspace")
+        L.check(L.lib().dgvit_sac_workspace_bytes(C.byref(self.policy._cfg), B, n_extra, prec, C.byref(n)), "sac_workspace")
         if self._ws is None or self._ws.numel() < n.value:
             self._ws = torch.empty(n.value, dtype=torch.uint8, device=self.device)
         return self._ws
@@ -214,18 +221,25 @@ class SAC(object):
     # ------------------------------------------------------------------ the update
     def update_from_batch(self, batch: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None,
                           debug: Optional[torch.Tensor] = None, global_batch: Optional[int] = None,
-                          sample_offset: Optional[int] = None, _phases=None) -> torch.Tensor:
+                          sample_offset: Optional[int] = None, _phases=None,
+                          extra: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
         """One SAC update on device tensors (no host sync).  ``noise`` injects the stochastic
         inputs (parity tests): eps_next, eps_pi [B,na] and keep-masks mask_* [B,N,D] uint8.
+        ``extra`` (learn_guidence): dict(target [n,na], weight [n]); then batch["obs"] / ["pobs"] carry
+        B + n rows, the last n being imitation rows seen only by the actor.
         Returns the device tensor [qf1_loss, policy_loss, qf2_loss, alpha_loss]."""
-        B = batch["obs"].shape[0]
+        B = batch["next_obs"].shape[0]
+        n_extra = 0 if extra is None else int(extra["target"].shape[0])
+        assert batch["obs"].shape[0] == B + n_extra and batch["pobs"].shape[0] == B + n_extra
         Bg = global_batch if global_batch is not None else B * self.world
         if sample_offset is None:
             sample_offset = self.rank * B
-        ws = self._workspace(B)
-        s = self._sac_struct(B, Bg, sample_offset)
+        ws = self._workspace(B, n_extra)
+        s = self._sac_struct(B, Bg, sample_offset, n_extra)
         bt = L.Batch(**{k: batch[k].data_ptr() for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew")},
-                     done=batch["done"].data_ptr() if "done" in batch else None)
+                     done=batch["done"].data_ptr() if "done" in batch else None,
+                     extra_target=None if extra is None else extra["target"].data_ptr(),
+                     extra_weight=None if extra is None else extra["weight"].data_ptr())
         nz = None
         if noise is not None:
             nz = L.Noise(**{k: L.ptr(noise.get(k)) for k in ("eps_next", "eps_pi", "mask_a_next", "mask_ct", "mask_c",
@@ -235,7 +249,7 @@ class SAC(object):
         out = L.SacOut(losses=self._losses.data_ptr(), debug=L.ptr(debug))
         lib = L.lib()
         nzp = C.byref(nz) if nz is not None else None
-        keep = (s, bt, nz, out, ws, batch, noise, debug)      # ctypes structs must outlive the calls
+        keep = (s, bt, nz, out, ws, batch, noise, debug, extra)      # ctypes structs must outlive the calls
 
         def phase(which):
             st = _stream(self.device)
@@ -332,6 +346,55 @@ class SAC(object):
             graphs[0].replay()
         self.itera += 1
         return self._losses
+
+    def learn_guidence(self, engage, batch_size=64):
+        """vn/DRL.py:187-301 — the update the shipped config runs (PRE_BUFFER): agent + expert minibatch
+        for the critic / policy losses, plus the guidance (expert rows) and engage (rows with engage == 1)
+        imitation losses on the actor's tanh-mean.  All imitation rows ride in the same actor pass as
+        extra rows with per-row loss weights, so the update stays one fused call."""
+        B = int(batch_size)
+        rb, re = self.replay_buffer, (self.replay_buffer_expert if self.pre_buffer else None)
+        Be = 0
+        if re is not None and rb.get_stored_size() > 0:
+            Be = int(min(np.floor(re.get_stored_size() / rb.get_stored_size() * B), B))      # :193-196
+        idx_a = rb.sample_indexes(B)
+        eng_rows = np.nonzero(rb.engage_host[idx_a.numpy()] == 1)[0]                         # :266
+        Bc, n_extra = B + Be, Be + len(eng_rows)
+        f = rb.obs.shape[1]
+        dev = self.device
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        key = (Bc, n_extra)
+        buf = self._gbuf.get(key)
+        if buf is None:
+            buf = dict(obs=z(Bc + n_extra, f), next_obs=z(Bc, f), pobs=z(Bc + n_extra, self.pstate_dim),
+                       next_pobs=z(Bc, self.pstate_dim), act=z(Bc, self.action_dim), rew=z(Bc, 1), done=z(Bc, 1),
+                       target=z(max(n_extra, 1), self.action_dim), weight=z(max(n_extra, 1)))
+            self._gbuf = {key: buf}
+        rows = lambda t, a, b: t[a:b]
+        rb.gather(idx_a.to(dev), {k: rows(buf[k], 0, B) for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done")})
+        if Be > 0:
+            idx_e = re.sample_indexes(Be).to(dev)
+            re.gather(idx_e, {k: rows(buf[k], B, Bc) for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done")})
+            # guidance rows = the expert minibatch again (its own dropout / rsample draws), :259-263
+            buf["obs"][Bc:Bc + Be].copy_(buf["obs"][B:Bc])
+            buf["pobs"][Bc:Bc + Be].copy_(buf["pobs"][B:Bc])
+            buf["target"][:Be].copy_(buf["act"][B:Bc])
+            buf["weight"][:Be].fill_(self.guidence_weight / (Be * self.action_dim * self.world))
+        if len(eng_rows) > 0:                                                                # :267-273
+            er = torch.as_tensor(eng_rows, device=dev)
+            buf["obs"][Bc + Be:].copy_(buf["obs"][er])
+            buf["pobs"][Bc + Be:].copy_(buf["pobs"][er])
+            buf["target"][Be:n_extra].copy_(buf["act"][er])
+            buf["weight"][Be:n_extra].fill_(self.engage_weight / (len(eng_rows) * self.action_dim * self.world))
+        extra = None if n_extra == 0 else dict(target=buf["target"][:n_extra], weight=buf["weight"][:n_extra])
+        losses = self.update_from_batch({k: buf[k] for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done")},
+                                        extra=extra).tolist()
+        self.alpha = float(self._alpha.item()) if self.automatic_entropy_tuning else self.alpha
+        return losses[0], losses[1]
+
+    def initialize_expert_buffer(self, s, a_exp, ps, ps_, r, s_, d=0):
+        """vn/DRL.py:469-477."""
+        self.replay_buffer_expert.add(obs=s, act=a_exp, pobs=ps, next_pobs=ps_, rew=r, next_obs=s_, done=d)
 
     # ------------------------------------------------------------------ act
     def choose_action(self, istate, pstate, evaluate=False):

@@ -732,10 +732,11 @@ struct SacWs {
   CriticCtx<A> critic_tmp;  // unsaved: critic_target(s', a') and critic(s, pi)
   float *a2, *logp2, *mean_tmp, *lstd_tmp, *q1t, *q2t, *q1, *q2, *dq1, *dq2, *nq;
   float *pi, *logpi, *mean_pi, *lstd_pi, *q1p, *q2p, *dpi;
+  float *meant_pi, *dlogp, *dmeant;   // learn_guidence: per-row gradients of the actor's (B + n_extra)-row pass
 };
 template <typename A>
-static void carve_sac(Carver& cv, const Dims& d, SacWs<A>& w) {
-  carve_actor<A>(cv, d, true, w.actor_s);
+static void carve_sac(Carver& cv, const Dims& d, const Dims& da, SacWs<A>& w) {
+  carve_actor<A>(cv, da, true, w.actor_s);
   carve_critic<A>(cv, d, true, w.critic_s);
   carve_actor<A>(cv, d, false, w.actor_tmp);
   carve_critic<A>(cv, d, false, w.critic_tmp);
@@ -745,9 +746,11 @@ static void carve_sac(Carver& cv, const Dims& d, SacWs<A>& w) {
   w.q1t = cv.take<float>(bn); w.q2t = cv.take<float>(bn);
   w.q1 = cv.take<float>(bn); w.q2 = cv.take<float>(bn);
   w.dq1 = cv.take<float>(bn); w.dq2 = cv.take<float>(bn); w.nq = cv.take<float>(bn);
-  w.pi = cv.take<float>(bn); w.logpi = cv.take<float>(d.B);
-  w.mean_pi = cv.take<float>(bn); w.lstd_pi = cv.take<float>(bn);
-  w.q1p = cv.take<float>(bn); w.q2p = cv.take<float>(bn); w.dpi = cv.take<float>(bn);
+  const int64_t an = (int64_t)da.B * d.na;
+  w.pi = cv.take<float>(an); w.logpi = cv.take<float>(da.B);
+  w.mean_pi = cv.take<float>(an); w.lstd_pi = cv.take<float>(an);
+  w.q1p = cv.take<float>(bn); w.q2p = cv.take<float>(bn); w.dpi = cv.take<float>(an);
+  w.meant_pi = cv.take<float>(an); w.dlogp = cv.take<float>(da.B); w.dmeant = cv.take<float>(an);
 }
 
 static dgvit_drop sac_drop(const dgvit_sac& s, const dgvit_noise* nz, const uint8_t* mask, uint32_t id) {
@@ -785,7 +788,7 @@ static ForkState& fork_state() {
 
 template <typename A>
 static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noise* nz, const dgvit_sac_out& out,
-                       const Dims& d, SacWs<A>& w, cudaStream_t st) {
+                       const Dims& d, const Dims& da, SacWs<A>& w, cudaStream_t st) {
   dgvit_layout La, Lc;
   make_layout(s.actor.cfg, La);
   make_layout(s.critic.cfg, Lc);
@@ -822,8 +825,8 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   ap.action_scale = s.action_scale; ap.action_bias = s.action_bias;
   ap.drop = sac_drop(s, nz, nz ? nz->mask_a : nullptr, 4);
   ap.sample_offset = s.sample_offset;
-  ap.mean = w.mean_pi; ap.log_std = w.lstd_pi; ap.action = w.pi; ap.log_prob = w.logpi;
-  actor_forward<A>(s.actor, La, d, ap, w.actor_s, f.aux[1]);
+  ap.mean = w.mean_pi; ap.log_std = w.lstd_pi; ap.action = w.pi; ap.log_prob = w.logpi; ap.mean_t = w.meant_pi;
+  actor_forward<A>(s.actor, La, da, ap, w.actor_s, f.aux[1]);      // B rows (+ the imitation rows of learn_guidence)
   DG_CUDA(cudaEventRecord(f.join[1], f.aux[1]));
   // ---- losses + critic backward                                                 (DRL.py:396-401)
   DG_CUDA(cudaStreamWaitEvent(st, f.join[0], 0));
@@ -842,7 +845,7 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
 
 template <typename A>
 static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noise* nz, const dgvit_sac_out& out,
-                       const Dims& d, SacWs<A>& w, cudaStream_t st) {
+                       const Dims& d, const Dims& da, SacWs<A>& w, cudaStream_t st) {
   dgvit_layout La, Lc;
   make_layout(s.actor.cfg, La);
   make_layout(s.critic.cfg, Lc);
@@ -869,7 +872,18 @@ static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
                      w.actor_s.t.partial, st);
   dgvit_actor_grad ag; memset(&ag, 0, sizeof(ag));
   ag.d_action = w.dpi;
-  actor_backward<A>(s.actor, La, d, ai, ag, s.alpha, 1.0f / (float)s.global_batch, w.actor_s, st);
+  if (da.B == d.B) {
+    actor_backward<A>(s.actor, La, d, ai, ag, s.alpha, 1.0f / (float)s.global_batch, w.actor_s, st);
+  } else {
+    // learn_guidence: rows >= B carry only the imitation loss  weight_r * |tanh-mean_r - target_r|^2  (DRL.py:257-278)
+    DG_REQUIRE(b.extra_target && b.extra_weight, "n_extra > 0 needs extra_target / extra_weight");
+    launch_k(imitation_grad_kernel, 1, 1024, 0, st, (const float*)w.meant_pi, b.extra_target, b.extra_weight, (const float*)s.alpha,
+             1.0f / (float)s.global_batch, d.B, da.B, d.na, w.dpi, w.dlogp, w.dmeant, out.losses);
+    DG_LAUNCH_CHECK();
+    ag.d_log_prob = w.dlogp;
+    ag.d_mean_t = w.dmeant;
+    actor_backward<A>(s.actor, La, da, ai, ag, nullptr, 0.f, w.actor_s, st);
+  }
   if (out.debug) {
     const size_t bn = (size_t)d.B * d.na * sizeof(float);
     DG_CUDA(cudaMemcpyAsync(out.debug + 3 * d.B * d.na, w.pi, bn, cudaMemcpyDeviceToDevice, st));
@@ -916,11 +930,11 @@ static void check_sac(const dgvit_sac& s, int B) {
 }
 
 template <typename A>
-static size_t sac_ws_bytes(const dgvit_cfg& acfg, int B) {
-  Dims d(acfg, B);
+static size_t sac_ws_bytes(const dgvit_cfg& acfg, int B, int n_extra) {
+  Dims d(acfg, B), da(acfg, B + n_extra);
   Carver cv(nullptr, 0, true);
   SacWs<A> w;
-  carve_sac<A>(cv, d, w);
+  carve_sac<A>(cv, d, da, w);
   return cv.off;
 }
 
@@ -1009,11 +1023,11 @@ int dgvit_workspace_bytes(const dgvit_cfg* cfg, int B, int precision, int save, 
   });
 }
 
-int dgvit_sac_workspace_bytes(const dgvit_cfg* acfg, int B, int precision, size_t* bytes) {
+int dgvit_sac_workspace_bytes(const dgvit_cfg* acfg, int B, int n_extra, int precision, size_t* bytes) {
   return guarded([&] {
-    DG_REQUIRE(acfg && bytes && B >= 1, "bad argument");
-    by_precision(precision, [&] { *bytes = sac_ws_bytes<float>(*acfg, B); },
-                 [&] { *bytes = sac_ws_bytes<bf16>(*acfg, B); });
+    DG_REQUIRE(acfg && bytes && B >= 1 && n_extra >= 0, "bad argument");
+    by_precision(precision, [&] { *bytes = sac_ws_bytes<float>(*acfg, B, n_extra); },
+                 [&] { *bytes = sac_ws_bytes<bf16>(*acfg, B, n_extra); });
   });
 }
 
@@ -1119,15 +1133,16 @@ static int sac_run(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* 
       if (!nz || !nz->eps_next || !nz->eps_pi || nz->drop_mode == DGVIT_DROP_RNG)
         DG_REQUIRE(s->rng_state, "rng_state required when noise is not injected");
     }
-    Dims d(s->actor.cfg, B);
+    DG_REQUIRE(s->n_extra >= 0, "n_extra < 0");
+    Dims d(s->actor.cfg, B), da(s->actor.cfg, B + s->n_extra);
     cudaStream_t st = (cudaStream_t)stream;
     auto run = [&](auto tag) {
       using A = decltype(tag);
       Carver cv(ws, ws_bytes);
       SacWs<A> w;
-      carve_sac<A>(cv, d, w);
-      if (phases & 1) sac_phase1<A>(*s, *b, nz, *out, d, w, st);
-      if (phases & 2) sac_phase2<A>(*s, *b, nz, *out, d, w, st);
+      carve_sac<A>(cv, d, da, w);
+      if (phases & 1) sac_phase1<A>(*s, *b, nz, *out, d, da, w, st);
+      if (phases & 2) sac_phase2<A>(*s, *b, nz, *out, d, da, w, st);
       if (phases & 4) sac_phase3<A>(*s, st);
     };
     by_precision(s->precision, [&] { run(float()); }, [&] { run(bf16()); });

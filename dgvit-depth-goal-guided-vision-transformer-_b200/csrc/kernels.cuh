@@ -686,6 +686,37 @@ __global__ void policy_loss_kernel(const float* __restrict__ q1p, const float* _
   }
 }
 
+// learn_guidence (vn/DRL.py:257-278): per-row gradients of the actor pass over B policy rows followed by
+// imitation rows.  rows < B: d log_pi = alpha / B_global, d mean_t = 0 (d action comes from the critic heads);
+// rows >= B: d action = d log_pi = 0, d mean_t = 2 w_r (mean_t - target).  The imitation loss is added to losses[1].
+__global__ void imitation_grad_kernel(const float* __restrict__ mean_t, const float* __restrict__ target,
+                                      const float* __restrict__ weight, const float* __restrict__ alpha,
+                                      float inv_bglobal, int B, int Ba, int na, float* __restrict__ dpi,
+                                      float* __restrict__ dlogp, float* __restrict__ dmeant,
+                                      float* __restrict__ losses) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float red[32];
+  const float al = *alpha;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < Ba * na; i += blockDim.x) {
+    const int r = i / na;
+    if (r < B) {
+      dmeant[i] = 0.f;
+      if (i % na == 0) dlogp[r] = al * inv_bglobal;
+    } else {
+      const float w = weight[r - B];
+      const float e = mean_t[i] - target[(r - B) * na + i % na];
+      acc = fmaf(w * e, e, acc);
+      dmeant[i] = 2.0f * w * e;
+      dpi[i] = 0.f;
+      if (i % na == 0) dlogp[r] = 0.f;
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) losses[1] += acc;
+}
+
 // Adam on the scalar log_alpha, then alpha = exp(log_alpha)  (DRL.py:419-423)
 __global__ void alpha_step_kernel(float* log_alpha, float* alpha, float* m, float* v, int64_t* step,
                                   const float* g, float lr, float b1, float b2, float omb1, float omb2,

@@ -153,22 +153,28 @@ typedef struct dgvit_sac {
   int32_t do_polyak;      /* itera % policy_freq == 0 (vn/DRL.py:430) */
   int32_t precision;      /* DGVIT_FP32 | DGVIT_BF16 */
   int32_t global_batch;   /* loss means are taken over this many samples (data parallel) */
+  int32_t n_extra;        /* learn_guidence: imitation rows appended to the actor's batch (0 for learn) */
   int32_t sample_offset;  /* this rank's first sample inside the global batch */
   uint64_t* rng_state;    /* device {seed, counter}; counter advanced once per update */
   const float* action_scale; const float* action_bias;
 } dgvit_sac;
 
 typedef struct dgvit_batch {   /* one replay minibatch, already on the device */
-  const float *obs, *next_obs;   /* [B, img_h, img_w] */
-  const float *pobs, *next_pobs; /* [B, n_pstate] */
+  const float *obs, *next_obs;   /* [B (+ n_extra for obs), img_h, img_w] */
+  const float *pobs, *next_pobs; /* [B (+ n_extra for pobs), n_pstate] */
   const float *act;              /* [B, n_act] */
   const float *rew;              /* [B, 1] */
   const float *done;             /* [B, 1]  read by the reference, unused (vn/DRL.py:393) */
+  /* SAC.learn_guidence (vn/DRL.py:257-278): rows B .. B+n_extra-1 of obs/pobs are imitation rows (expert
+   * minibatch / engaged rows) seen only by the actor; they add  sum_r weight[r] * |tanh-mean_r - target_r|^2
+   * to the policy loss (weight = guidence_weight / (rows * n_act), resp. engage_weight / ...). */
+  const float *extra_target;     /* [n_extra, n_act] or NULL */
+  const float *extra_weight;     /* [n_extra] or NULL */
 } dgvit_batch;
 
 typedef struct dgvit_noise {   /* parity mode: injected stochastic inputs; all NULL = RNG */
-  const float *eps_next, *eps_pi;                  /* [B, n_act] */
-  const uint8_t *mask_a_next, *mask_ct, *mask_c, *mask_a, *mask_c_pi; /* [B, N, D] */
+  const float *eps_next, *eps_pi;                  /* [B, n_act] (eps_pi: B + n_extra rows) */
+  const uint8_t *mask_a_next, *mask_ct, *mask_c, *mask_a, *mask_c_pi; /* [B, N, D] (mask_a: B + n_extra rows) */
   int32_t drop_mode;                               /* DGVIT_DROP_* */
 } dgvit_noise;
 
@@ -202,7 +208,7 @@ int dgvit_param_layout(const dgvit_cfg* cfg, dgvit_layout* out);
 int dgvit_workspace_bytes(const dgvit_cfg* cfg, int B, int precision, int save_for_backward,
                           size_t* bytes);
 /* bytes of workspace dgvit_sac_* needs for a local batch of B */
-int dgvit_sac_workspace_bytes(const dgvit_cfg* actor_cfg, int B, int precision, size_t* bytes);
+int dgvit_sac_workspace_bytes(const dgvit_cfg* actor_cfg, int B, int n_extra, int precision, size_t* bytes);
 
 /* refresh the bf16 shadow of a parameter arena (after load_state_dict etc.) */
 int dgvit_refresh_shadow(const dgvit_net* net, void* stream);

@@ -308,6 +308,60 @@ class SACOracle:
         return float(qf1_loss.detach()), float(policy_loss.detach())                 # :437
 
 
+    def learn_guidence(self, batch, noise, expert=None, engage_rows=None,
+                       guidence_weight=1.0, engage_weight=1.0):
+        """``SAC.learn_guidence`` on tensors — vn/DRL.py:187-301.
+
+        ``batch``: the minibatch the reference builds at :199-226 (agent rows, then expert rows when
+        ``expert`` is given).  ``expert``: dict obs,pobs,act of the expert rows (:259-263), ``engage_rows``:
+        index tensor of the rows with engage == 1 (:266-273).  Extra ``noise`` keys: mask_g/eps_g (the
+        policy.sample on the expert rows) and mask_e/eps_e (the one on the engaged rows), drawn by the
+        reference right after mask_c_pi."""
+        cfg = self.cfg
+        s, ps, a = batch["obs"], batch["pobs"], batch["act"]
+        r, s2, ps2 = batch["rew"], batch["next_obs"], batch["next_pobs"]
+        alpha = self.alpha
+        with torch.no_grad():                                       # :238-242
+            a2, logp2, _ = actor_sample(self.actor, s2, ps2, noise["eps_next"], cfg, noise.get("mask_a_next"))
+            q1t, q2t = critic_forward(self.critic_target, s2, ps2, a2, cfg, noise.get("mask_ct"))
+            nq = r + self.gamma * (torch.min(q1t, q2t) - alpha * logp2)
+        cp = {k: v.clone().requires_grad_(True) for k, v in self.critic.items()}
+        q1, q2 = critic_forward(cp, s, ps, a, cfg, noise.get("mask_c"))      # :244
+        qf1_loss = F.mse_loss(q1, nq)
+        qf2_loss = F.mse_loss(q2, nq)
+        (qf1_loss + qf2_loss).backward()                            # :249-251
+        cgrads = {k: v.grad for k, v in cp.items()}
+        self.critic_opt.step(self.critic, cgrads)
+        self.last_critic_grads = cgrads
+        ap = {k: v.clone().requires_grad_(True) for k, v in self.actor.items()}
+        pi, log_pi, _ = actor_sample(ap, s, ps, noise["eps_pi"], cfg, noise.get("mask_a"))   # :253
+        q1p, q2p = critic_forward(self.critic, s, ps, pi, cfg, noise.get("mask_c_pi"))       # :255
+        min_qp = torch.min(q1p, q2p)
+        guidence_loss = 0.0
+        if expert is not None:                                      # :259-265
+            _, _, pred = actor_sample(ap, expert["obs"], expert["pobs"], noise["eps_g"], cfg, noise.get("mask_g"))
+            guidence_loss = guidence_weight * F.mse_loss(pred, expert["act"]).mean()
+        engage_loss = 0.0
+        if engage_rows is not None and engage_rows.numel() > 0:     # :268-276
+            _, _, pred = actor_sample(ap, s[engage_rows], ps[engage_rows], noise["eps_e"], cfg, noise.get("mask_e"))
+            engage_loss = engage_weight * F.mse_loss(pred, a[engage_rows]).mean()
+        policy_loss = ((alpha * log_pi) - min_qp).mean() + guidence_loss + engage_loss       # :278
+        policy_loss.backward()
+        agrads = {k: v.grad for k, v in ap.items()}
+        self.actor_opt.step(self.actor, agrads)
+        self.last_actor_grads = agrads
+        if self.auto:                                               # :285-293
+            la = self.log_alpha.clone().requires_grad_(True)
+            alpha_loss = -(la * (log_pi + self.target_entropy).detach()).mean()
+            alpha_loss.backward()
+            self.alpha_opt.step({"log_alpha": self.log_alpha}, {"log_alpha": la.grad})
+            self.alpha = float(self.log_alpha.exp())
+        if self.itera % self.policy_freq == 0:                      # :294-295
+            soft_update(self.critic_target, self.critic, self.critic.keys(), self.tau)
+        self.itera += 1
+        return float(qf1_loss.detach()), float(policy_loss.detach())            # :299
+
+
 # --------------------------------------------------------------------------
 # Replay gather (cpprb semantics; vn/DRL.py:80-89,375-386)
 # --------------------------------------------------------------------------

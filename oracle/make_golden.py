@@ -244,6 +244,75 @@ def case_learn(G, D, tag, block, head, lfs, B, steps=3):
     print(f"[golden] learn_{tag}: ok")
 
 
+def case_guidence(G, D, tag, block, head, lfs, B, Be, steps=2):
+    """Unmodified reference SAC.learn_guidence (expert buffer + engage rows) vs SACOracle.learn_guidence."""
+    cfg = O.Cfg(dim=lfs, depth=block, heads=head)
+    agent = D.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, True, SEED,
+                  LR_C=1e-3, LR_A=1e-3, LR_ALPHA=1e-4, BUFFER_SIZE=64, TAU=5e-4, POLICY_FREQ=1,
+                  GAMMA=0.999, ALPHA=1.0, block=block, head=head, l_f_size=lfs, buffer_size_expert=63,
+                  automatic_entropy_tuning=True)
+    orc = O.SACOracle(params_of(agent.policy), params_of(agent.critic), cfg)
+    out = {}
+    # get_stored_size(): agent 64, expert 64 -> batch_expert = min(floor(64/64*B), B) = B  (vn/DRL.py:193-196);
+    # the stub returns Be expert rows whatever is asked: plant Be = B
+    assert Be == B
+    for s in range(steps):
+        ba = synthetic_batch(cfg, B, SEED + 30 + s)
+        be = synthetic_batch(cfg, Be, SEED + 40 + s)
+        engage = np.zeros((B, 1), np.float32)
+        engage[[1, B - 1], 0] = 1.0
+        agent_dict = {k: v.numpy() for k, v in ba.items()}
+        agent_dict["engage"] = engage
+        expert_dict = {k: v.numpy() for k, v in be.items()}
+        expert_dict["act_exp"] = expert_dict.pop("act")
+        planted = [agent_dict, expert_dict]
+
+        class _Seq:
+            i = 0
+        def sample_seq(self_, n, _p=planted, _c=_Seq):
+            d = _p[_c.i % 2]
+            _c.i += 1
+            return {k: v.copy() for k, v in d.items()}
+        _StubPER.sample = sample_seq
+        torch.manual_seed(SEED + 300 + s)
+        l_ref = agent.learn_guidence(False, B)
+        torch.manual_seed(SEED + 300 + s)
+        Bc = B + Be
+        shp = lambda n: (n, cfg.n_tokens, cfg.dim)
+        noise = {}
+        noise["mask_a_next"] = torch.empty(shp(Bc)).bernoulli_(0.9)
+        noise["eps_next"] = torch.empty(Bc, 2).normal_()
+        noise["mask_ct"] = torch.empty(shp(Bc)).bernoulli_(0.9)
+        noise["mask_c"] = torch.empty(shp(Bc)).bernoulli_(0.9)
+        noise["mask_a"] = torch.empty(shp(Bc)).bernoulli_(0.9)
+        noise["eps_pi"] = torch.empty(Bc, 2).normal_()
+        noise["mask_c_pi"] = torch.empty(shp(Bc)).bernoulli_(0.9)
+        noise["mask_g"] = torch.empty(shp(Be)).bernoulli_(0.9)
+        noise["eps_g"] = torch.empty(Be, 2).normal_()
+        noise["mask_e"] = torch.empty(shp(2)).bernoulli_(0.9)
+        noise["eps_e"] = torch.empty(2, 2).normal_()
+        cat = {k: torch.cat([ba[k], be[k]], 0) for k in ba}
+        l_orc = orc.learn_guidence(cat, noise, expert=dict(obs=be["obs"], pobs=be["pobs"], act=be["act"]),
+                                   engage_rows=torch.tensor([1, B - 1]))
+        for a_, b_ in zip(l_ref, l_orc):
+            assert abs(a_ - b_) <= 1e-5 * max(1.0, abs(a_)), (tag, s, l_ref, l_orc)
+        for nm, mod, od in (("actor", agent.policy, orc.actor), ("critic", agent.critic, orc.critic)):
+            worst = max(float((p.detach() - od[k]).abs().max()) for k, p in mod.named_parameters())
+            assert worst < 2e-3 * (s + 1), (tag, s, nm, worst)
+            names, sm, ab = checksum(params_of(mod))
+            out[f"step{s}_{nm}_abssum"] = ab
+        out[f"step{s}_losses"] = np.array(l_ref)
+        out[f"step{s}_log_alpha"] = np.array(float(agent.log_alpha.detach()))
+        out[f"step{s}_noise_bits"] = np.concatenate([np.packbits(noise[k].numpy().astype(np.uint8)) for k in
+                                                     ("mask_a_next", "mask_ct", "mask_c", "mask_a", "mask_c_pi", "mask_g", "mask_e")])
+        out[f"step{s}_eps"] = np.concatenate([noise[k].numpy().reshape(-1) for k in ("eps_next", "eps_pi", "eps_g", "eps_e")])
+    del _StubPER.sample
+    _StubPER.sample = lambda self, n: {k: v.copy() for k, v in _StubPER.planted.items()}
+    out["cfg"] = np.array([lfs, block, head, B, Be, steps])
+    np.savez_compressed(os.path.join(GOLD, f"guidence_{tag}.npz"), **out)
+    print(f"[golden] guidence_{tag}: ok")
+
+
 def case_depth():
     """vn/env_lab.py source slices executed with this image's cv2."""
     import cv2
@@ -285,6 +354,7 @@ def main():
     case_modules(G, "shipped", block=4, head=4, lfs=64, B=4)
     case_learn(G, D, "small", block=2, head=2, lfs=32, B=4)
     case_learn(G, D, "shipped", block=4, head=4, lfs=64, B=4)
+    case_guidence(G, D, "small", block=2, head=2, lfs=32, B=4, Be=4)
     case_depth()
 
 

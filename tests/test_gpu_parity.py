@@ -375,3 +375,56 @@ def test_update_ragged_batches(B, precision):
             assert torch.isfinite(p).all(), k
             if precision == "fp32":
                 assert float((d > 2e-5).float().mean()) < 5e-3, k
+
+
+def test_learn_guidence_matches_golden_reference_run():
+    """SAC.learn_guidence semantics (vn/DRL.py:187-301): agent + expert minibatch, guidance rows and engaged
+    rows as extra actor rows of ONE fused update, vs the recorded unmodified-reference run and the oracle."""
+    from test_oracle_golden import _guidence_inputs
+    g = golden("guidence_small.npz")
+    lfs, block, head, B, Be, steps = (int(x) for x in g["cfg"])
+    cfg = O.Cfg(dim=lfs, depth=block, heads=head)
+    ag = _agent(cfg, "fp32")
+    actor0, critic0 = reference_sac_init(cfg, SEED)
+    orc = O.SACOracle(actor0, critic0, cfg)
+    for s in range(steps):
+        ba, be, cat, noise = _guidence_inputs(g, cfg, B, Be, s)
+        eng = torch.tensor([1, B - 1])
+        orc.learn_guidence(cat, noise, expert=dict(obs=be["obs"], pobs=be["pobs"], act=be["act"]), engage_rows=eng)
+        Bc, ne = B + Be, 2
+        flat = lambda t: t.reshape(t.shape[0], -1)
+        batch = dict(obs=torch.cat([flat(cat["obs"]), flat(be["obs"]), flat(cat["obs"][eng])]),
+                     pobs=torch.cat([cat["pobs"], be["pobs"], cat["pobs"][eng]]),
+                     next_obs=flat(cat["next_obs"]), next_pobs=cat["next_pobs"], act=cat["act"], rew=cat["rew"], done=cat["done"])
+        extra = dict(target=torch.cat([be["act"], cat["act"][eng]]),
+                     weight=torch.cat([torch.full((Be,), 1.0 / (Be * 2)), torch.full((ne,), 1.0 / (ne * 2))]))
+        nz = dict(noise)
+        nz["mask_a"] = torch.cat([noise["mask_a"], noise["mask_g"], noise["mask_e"]])
+        nz["eps_pi"] = torch.cat([noise["eps_pi"], noise["eps_g"], noise["eps_e"]])
+        for k in ("mask_g", "mask_e", "eps_g", "eps_e"):
+            nz.pop(k)
+        losses = ag.update_from_batch({k: v.cuda().contiguous() for k, v in batch.items()}, _noise_cuda(nz),
+                                      extra={k: v.cuda().contiguous() for k, v in extra.items()}).cpu().numpy()
+        ref = g[f"step{s}_losses"]
+        assert abs(losses[0] - ref[0]) <= FP32_TOL * max(1.0, abs(ref[0])), (s, losses, ref)
+        assert abs(losses[1] - ref[1]) <= FP32_TOL * max(1.0, abs(ref[1])), (s, losses, ref)
+        assert abs(float(ag.log_alpha) - float(g[f"step{s}_log_alpha"])) < 1e-6
+        for nm, mod, od in (("actor", ag.policy, orc.actor), ("critic", ag.critic, orc.critic)):
+            for k, p in mod.named_parameters():
+                d = (p.detach().cpu() - od[k]).abs()
+                assert float((d > 2e-5 * (s + 1)).float().mean()) < 2e-3, (s, nm, k)
+
+
+def test_learn_guidence_agent_api():
+    """The agent-level call: expert buffer fill, engaged transitions, graph-free fused update, finite losses."""
+    cfg = O.Cfg(dim=32, depth=1, heads=2)
+    ag = dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, True, 5, BUFFER_SIZE=32, TAU=5e-4, POLICY_FREQ=1,
+                GAMMA=0.999, ALPHA=1.0, block=1, head=2, l_f_size=32, buffer_size_expert=15, precision="bf16")
+    rs = np.random.RandomState(0)
+    for i in range(12):
+        s, s2 = rs.rand(128, 160).astype(np.float32), rs.rand(128, 160).astype(np.float32)
+        ag.store_transition(s, rs.rand(2) * 2 - 1, rs.rand(2), rs.rand(2), float(rs.randn()), s2, float(i % 5 == 0), None, 0)
+        ag.initialize_expert_buffer(s, rs.rand(2) * 2 - 1, rs.rand(2), rs.rand(2), 1.0, s2, 0)
+    for _ in range(3):
+        q, p = ag.learn_guidence(False, 8)
+        assert np.isfinite(q) and np.isfinite(p)

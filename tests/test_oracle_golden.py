@@ -94,3 +94,41 @@ def test_replay_gather_semantics():
     out = O.replay_gather(store, idx, size)
     assert np.array_equal(out["obs"], store["obs"][idx])
     assert np.array_equal(out["next_obs"], store["obs"][[1, 0, 6, 6]])
+
+
+def _guidence_inputs(g, cfg, B, Be, s):
+    """Rebuild the planted minibatches / replayed noise of oracle/make_golden.py:case_guidence."""
+    ba, be = synthetic_batch(cfg, B, SEED + 30 + s), synthetic_batch(cfg, Be, SEED + 40 + s)
+    Bc = B + Be
+    sizes = dict(mask_a_next=Bc, mask_ct=Bc, mask_c=Bc, mask_a=Bc, mask_c_pi=Bc, mask_g=Be, mask_e=2)
+    bits = np.unpackbits(g[f"step{s}_noise_bits"])
+    noise, off = {}, 0
+    for k, n in sizes.items():
+        cnt = n * cfg.n_tokens * cfg.dim
+        noise[k] = torch.from_numpy(bits[off:off + cnt].reshape(n, cfg.n_tokens, cfg.dim).astype(np.float32))
+        off += (cnt + 7) // 8 * 8
+    eps, off = g[f"step{s}_eps"], 0
+    for k, n in dict(eps_next=Bc, eps_pi=Bc, eps_g=Be, eps_e=2).items():
+        noise[k] = torch.from_numpy(eps[off:off + 2 * n].reshape(n, 2).copy())
+        off += 2 * n
+    cat = {k: torch.cat([ba[k], be[k]], 0) for k in ba}
+    return ba, be, cat, noise
+
+
+def test_learn_guidence_against_golden():
+    """SACOracle.learn_guidence vs the recorded run of the UNMODIFIED reference SAC.learn_guidence
+    (expert minibatch + two engaged rows)."""
+    g = golden("guidence_small.npz")
+    lfs, block, head, B, Be, steps = (int(x) for x in g["cfg"])
+    cfg = O.Cfg(dim=lfs, depth=block, heads=head)
+    actor, critic = reference_sac_init(cfg, SEED)
+    orc = O.SACOracle(actor, critic, cfg)
+    for s in range(steps):
+        ba, be, cat, noise = _guidence_inputs(g, cfg, B, Be, s)
+        l = orc.learn_guidence(cat, noise, expert=dict(obs=be["obs"], pobs=be["pobs"], act=be["act"]),
+                               engage_rows=torch.tensor([1, B - 1]))
+        np.testing.assert_allclose(np.array(l), g[f"step{s}_losses"], rtol=1e-5, atol=1e-6)
+        assert abs(float(orc.log_alpha) - float(g[f"step{s}_log_alpha"])) < 1e-7
+        for nm, d in (("actor", orc.actor), ("critic", orc.critic)):
+            a = np.array([float(v.double().abs().sum()) for v in d.values()])
+            np.testing.assert_allclose(a, g[f"step{s}_{nm}_abssum"], rtol=2e-4, atol=1e-3)
