@@ -428,3 +428,39 @@ def test_learn_guidence_agent_api():
     for _ in range(3):
         q, p = ag.learn_guidence(False, 8)
         assert np.isfinite(q) and np.isfinite(p)
+
+
+def test_behaviour_cloning_step_through_module_surface():
+    """vn/attention_imitating.py:45-67 unchanged on top of the drop-in module: policy.sample -> RMSE on the
+    clipped tanh-mean -> backward -> clip_grad_norm_(10) -> torch.optim.Adam(policy.parameters()).  Two steps
+    against the same code running on the oracle's parameters (autograd on CPU)."""
+    cfg = O.Cfg(dim=32, depth=2, heads=2)
+    B = 6
+    pa = reference_init("actor", cfg, 71)
+    a = _mk("actor", cfg, pa)
+    opt = torch.optim.Adam(a.parameters(), lr=1e-3)
+    ref = {k: v.clone().requires_grad_(True) for k, v in pa.items()}
+    ropt = torch.optim.Adam(list(ref.values()), lr=1e-3)
+    for s in range(2):
+        batch, nz = synthetic_batch(cfg, B, 80 + s), synthetic_noise(cfg, B, 90 + s)
+        img, goal, act = batch["obs"], batch["pobs"], batch["act"]
+        # reference-side (oracle) step
+        _, _, mean = O.actor_sample(ref, img, goal, nz["eps_pi"], cfg, nz["mask_a"])
+        rloss = torch.sqrt(torch.pow(mean.clip(-1, 1) - act, 2).mean())
+        ropt.zero_grad()
+        rloss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in ref.values() if p.grad is not None], 10)
+        ropt.step()
+        # drop-in module
+        a.inject_noise(mask=nz["mask_a"], eps=nz["eps_pi"])
+        _, _, m = a.sample([img.cuda(), goal.cuda()])
+        loss = torch.sqrt(torch.pow(m.clip(-1, 1) - act.cuda(), 2).mean())
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(a.parameters(), 10)
+        opt.step()
+        assert abs(float(loss) - float(rloss)) < FP32_TOL * max(1.0, abs(float(rloss)))
+        for k, p in a.named_parameters():
+            d = (p.detach().cpu() - ref[k].detach()).abs()
+            assert float((d > 2e-5 * (s + 1)).float().mean()) < 5e-3, (s, k)
+    assert a._bound()          # torch.optim updated the flat arena in place through the parameter views
