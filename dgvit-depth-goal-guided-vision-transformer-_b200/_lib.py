@@ -131,6 +131,8 @@ SYMBOLS = {
                                     C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "dgvit_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_void_p]),
+    "dgvit_mlp_bf16": (C.c_int, [C.c_void_p] * 12 + [C.c_int64, C.c_int, C.c_void_p]),
+    "dgvit_mlp_partial_floats": (C.c_int64, [C.c_int64, C.c_int]),
     "dgvit_adam_step": (C.c_int, [P(Net), P(Adam), P(Net), C.c_float, C.c_void_p]),
     "dgvit_polyak": (C.c_int, [P(Net), P(Net), C.c_float, C.c_void_p]),
     "dgvit_replay_gather": (C.c_int, [P(Replay), C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),

@@ -400,7 +400,7 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
         ProfScope ps(PROF_GEMM_MLP, 4.0 * R * d.D * d.M, 0.0, st);
         ProfScope ps2(PROF_MLP_FUSED, 4.0 * R * d.D * d.M, 0.0, st);
         mlp::fwd(B_.Xn2, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), P + b.fc2_b, B_.Xm, d.D, Xnext,
-                 d.D, c.save ? B_.Hpre : nullptr, R, d.M, st);
+                 d.D, R, d.M, st);
       }
 #endif
     } else {
@@ -446,21 +446,33 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     // ---- MLP block.  dXr = dL/dX_out
     {
     TagScope mlp_tag(PROF_GEMM_MLP);
-    {
-      // the fused forward kept only the pre-activation: the dH epilogue re-materialises gelu(Hpre) for dW2
-      float* Xn_out = (l + 1 < d.L) ? c.L[l + 1].Xa : c.Xout;
-      const bool fused = mlp_fused<A>(d, R, B_.Xn2, WSel<A>::w(net, b.fc1_w), WSel<A>::w(net, b.fc2_w), B_.Xm, Xn_out);
+    float* Xn_out = (l + 1 < d.L) ? c.L[l + 1].Xa : c.Xout;
+    bool fused = mlp_fused<A>(d, R, B_.Xn2, WSel<A>::w(net, b.fc1_w), WSel<A>::w(net, b.fc2_w), B_.Xm, Xn_out);
+#ifdef DGVIT_WITH_TC
+    if constexpr (std::is_same<A, bf16>::value) {
+      if (fused) {
+        // the fused forward saved nothing: both backward launches recompute the pre-activation on chip
+        DG_REQUIRE(mlp::bwd_partial_floats(R, d.M) <= c.partial_floats, "mlp::bwd partial buffer too small");
+        ProfScope ps(PROF_GEMM_MLP, 8.0 * R * d.D * d.M, 0.0, st);
+        mlp::bwd(B_.Xn2, dxop, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), c.dXn, G + b.fc1_w,
+                 G + b.fc1_b, G + b.fc2_w, G + b.fc2_b, c.partial, R, d.M, st);
+      }
+    }
+#else
+    fused = false;
+#endif
+    if (!fused) {
       GemmArgs g;
       g.M = (int)R; g.N = d.M; g.K = d.D;
       g.A = dxop; g.a_sm = d.D; g.a_sk = 1;
       g.B = WSel<A>::w(net, b.fc2_w); g.b_sk = d.M; g.b_sn = 1;
       g.C = c.dH; g.ldc = d.M;
-      g.epi = fused ? EPI_GELU_BWD2 : EPI_GELU_BWD; g.aux = B_.Hpre; g.ldaux = d.M; g.C2 = B_.Hact;
+      g.epi = EPI_GELU_BWD; g.aux = B_.Hpre; g.ldaux = d.M;
       gemm<A, A, A>(g, st);
+      linear_bwd_w<A, A>(dxop, B_.Hact, G + b.fc2_w, G + b.fc2_b, R, d.D, d.M, c.partial, st);
+      linear_bwd_w<A, A>(c.dH, B_.Xn2, G + b.fc1_w, G + b.fc1_b, R, d.M, d.D, c.partial, st);
+      linear_bwd_x<A, A, float>(c.dH, WSel<A>::w(net, b.fc1_w), c.dXn, R, d.M, d.D, EPI_NONE, nullptr, 0, st);
     }
-    linear_bwd_w<A, A>(dxop, B_.Hact, G + b.fc2_w, G + b.fc2_b, R, d.D, d.M, c.partial, st);
-    linear_bwd_w<A, A>(c.dH, B_.Xn2, G + b.fc1_w, G + b.fc1_b, R, d.M, d.D, c.partial, st);
-    linear_bwd_x<A, A, float>(c.dH, WSel<A>::w(net, b.fc1_w), c.dXn, R, d.M, d.D, EPI_NONE, nullptr, 0, st);
     }
     launch_ln_bwd(c.dXn, B_.Xm, B_.mean2, B_.rstd2, P + b.ln2_w, dXr, dXr_lp, G + b.ln2_w, G + b.ln2_b, c.partial, R,
                   d.D, st);
@@ -1207,6 +1219,37 @@ int dgvit_linear_bf16(const void* x, const void* W, void* y, int64_t rows, int N
       default: fail(DGVIT_ERR_ARG, "unknown epilogue %d", epilogue);
     }
     gemm<bf16, bf16, bf16>(g, st);
+  });
+}
+
+int64_t dgvit_mlp_partial_floats(int64_t rows, int hid) {
+#ifdef DGVIT_WITH_TC
+  if (rows >= 1 && hid >= mlp::HC && hid % mlp::HC == 0) return (int64_t)mlp::bwd_partial_floats(rows, hid);
+#endif
+  return -1;
+}
+
+int dgvit_mlp_bf16(const void* x, const void* W1, const float* b1, const void* W2, const float* b2, const float* resid,
+                   float* out, const void* d_y, float* d_x, float* d_w, float* d_b2, float* partial, int64_t rows, int hid,
+                   void* stream) {
+  return guarded([&] {
+#ifdef DGVIT_WITH_TC
+    DG_REQUIRE(x && W1 && b1 && W2 && rows > 0 && hid > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_y) {
+      DG_REQUIRE(b2 && resid && out, "forward needs b2, resid, out");
+      DG_REQUIRE(mlp::eligible(64, hid, rows, x, W1, W2, resid, 64, out, 64), "mlp: shape not eligible for the fused kernel");
+      mlp::fwd((const bf16*)x, (const bf16*)W1, b1, (const bf16*)W2, b2, resid, 64, out, 64, rows, hid, st);
+    } else {
+      DG_REQUIRE(d_x && d_w && d_b2 && partial, "backward needs d_x, d_w, d_b2, partial");
+      DG_REQUIRE(mlp::eligible(64, hid, rows, x, W1, W2, d_x, 64, d_x, 64) && ((uintptr_t)d_y & 15) == 0,
+                 "mlp: shape not eligible for the fused kernel");
+      mlp::bwd((const bf16*)x, (const bf16*)d_y, (const bf16*)W1, b1, (const bf16*)W2, d_x, d_w, d_w + (int64_t)hid * 64,
+               d_w + (int64_t)hid * 65, d_b2, partial, rows, hid, st);
+    }
+#else
+    fail(DGVIT_ERR_ARG, "built without the tensor-core kernels");
+#endif
   });
 }
 

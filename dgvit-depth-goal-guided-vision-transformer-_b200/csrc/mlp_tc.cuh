@@ -1,18 +1,34 @@
-// mlp_tc.cuh — fused GELU-MLP forward for sm_100a (FeedForward.forward + residual,
+// mlp_tc.cuh — fused GELU-MLP for sm_100a, forward and backward (FeedForward.forward + residual,
 // vn/GoalFormer.py:39-50,104):
 //
 //     out = x + W2 gelu(W1 LN(x) + b1) + b2        (LN applied by the preceding kernel)
 //
-// One CTA per 128-token tile.  The 2048-wide hidden activation never leaves the SM: for each
-// 128-column hidden chunk, GEMM1 (tcgen05, K = 64) lands in TMEM, 16 epilogue warps add the bias,
-// apply GELU in fp32 and write the bf16 chunk straight into a 128B-swizzled shared-memory tile that
-// is the A operand of GEMM2, whose [128 x 64] fp32 accumulator stays in TMEM across all chunks.
-// Weight chunks stream through TMA rings (they are L2 resident: 512 KB per layer).  In training
-// passes the pre-activation is additionally written out (bf16, coalesced) for the backward.
+// The 2048-wide hidden activation never leaves the SM in either direction.
 //
-//   HBM traffic per token: read 128 B (bf16 LN output) + 256 B (fp32 residual), write 256 B
-//   (+ 4 KB pre-activation when saved) instead of 8-12 KB for the unfused pair of GEMMs.
+// forward (mlp_fwd_tc_kernel): one CTA per 128-token tile.  For each 128-column hidden chunk GEMM1
+// (tcgen05, K = 64) lands in TMEM, 16 epilogue warps add the bias, apply GELU and write the chunk
+// straight into a 128B-swizzled shared-memory tile that is the A operand of GEMM2, whose [128 x 64]
+// fp32 accumulator stays in TMEM across all chunks.  Weight chunks stream through TMA rings (L2
+// resident: 512 KB per layer).  Nothing but x and the output touches HBM: the backward recomputes
+// the pre-activation instead of reading a saved copy (a K = 64 GEMM is cheaper than 4 KB/token).
+//
+// backward (mlp_bwd_tc_kernel<MODE>): two launches of one kernel over (token tile, hidden chunk) pairs.
+// Per pair, from the smem images of X (LN output), dY, W1[chunk], W2[:, chunk]:
+//     Hpre = X W1c^T (+b1)        dG = dY W2c           (both into TMEM)
+//     G = gelu(Hpre)              dH = dG * gelu'(Hpre) (epilogue warps -> swizzled smem tiles)
+//   MODE 0 (CTA = token tile, loops over chunks):  dX += dH W1c          (+ colsum(dY) for db2)
+//   MODE 1 (CTA = hidden chunk x token range):     dW1c += dH^T X ; dW2c^T += G^T dY ; db1c += dH^T 1
+// so neither dX nor dW needs a cross-CTA reduction beyond the few token ranges of MODE 1, and the
+// [tokens x 2048] tensors G / dH never exist in HBM.  One smem image serves as K-major operand of
+// one GEMM and MN-major operand of another (same trick as attn_tc.cuh).
+//
+// The GELU epilogue is the bound of all three kernels (issue slots + MUFU), so it runs in packed
+// f16x2: x(a + b x^2) -> MUFU.TANH -> 0.5x(1+t), constants fitted to the exact erf GELU
+// (|err| <= 2.7e-4; the f16 pipeline's rms error is 4x below that of rounding the exact GELU to bf16).
+// tcgen05 kind::f16 rejects mixed f16 / bf16 operands (illegal instruction), so the result is re-packed to bf16.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "attn_tc.cuh"
 
 namespace dgvit {
@@ -24,31 +40,101 @@ using attn::sw128_off;
 using attn::tmem_ld16;
 
 constexpr int HC = 128;            // hidden chunk (columns of GEMM1 / K of GEMM2)
-constexpr int NST = 3;             // weight ring depth
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
-constexpr int X_BYTES = 16384, W_BYTES = 16384, H_BYTES = 32768;
-constexpr int STAGE_PITCH = 80;
+constexpr int TILE16 = 16384;      // [128 rows][64 x 16-bit] swizzled tile
+constexpr int MAX_HID = 4096;      // f16 bias copy in smem
+
+constexpr float GELU_A = 0.80015708f, GELU_B = 0.03470089f;
+
+// kind::f16 instruction descriptor with explicit operand formats (0 = f16, 1 = bf16), D = f32
+__host__ __device__ constexpr uint32_t make_idesc_fmt(int M, int N, bool a_mn, bool b_mn, uint32_t afmt, uint32_t bfmt) {
+  return (1u << 4) | (afmt << 7) | (bfmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ __half2 h2_tanh(__half2 x) {
+  uint32_t r;
+  const uint32_t a = *reinterpret_cast<const uint32_t*>(&x);
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a));
+  return *reinterpret_cast<__half2*>(&r);
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 x) { return *reinterpret_cast<const uint32_t*>(&x); }
+__device__ __forceinline__ uint32_t h2_to_bf2_bits(__half2 x) {
+  const float2 f = __half22float2(x);
+  const __nv_bfloat162 p = __floats2bfloat162_rn(f.x, f.y);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+
+__device__ __forceinline__ __half2 gelu_h2(__half2 x) {
+  const __half2 A = __float2half2_rn(GELU_A), B = __float2half2_rn(GELU_B), hf = __float2half2_rn(0.5f);
+  const __half2 x2 = __hmul2(x, x);
+  const __half2 t = h2_tanh(__hmul2(x, __hfma2(x2, B, A)));
+  const __half2 hx = __hmul2(x, hf);
+  return __hfma2(hx, t, hx);
+}
+// g = gelu(x), d = d gelu / dx of the same approximant
+__device__ __forceinline__ void gelu_grad_h2(__half2 x, __half2& g, __half2& d) {
+  const __half2 A = __float2half2_rn(GELU_A), B = __float2half2_rn(GELU_B), hf = __float2half2_rn(0.5f);
+  const __half2 B3 = __float2half2_rn(3.0f * GELU_B), one = __float2half2_rn(1.0f);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(60000.0f));   // keeps (1 - t^2) * q finite
+  const __half2 t = h2_tanh(__hmul2(x, __hfma2(x2, B, A)));
+  const __half2 hx = __hmul2(x, hf);
+  g = __hfma2(hx, t, hx);
+  const __half2 q = __hfma2(x2, B3, A);
+  const __half2 s = __hfma2(__hneg2(t), t, one);
+  d = __hfma2(__hmul2(hx, s), q, __hfma2(t, hf, hf));
+}
+
+// 32 lanes x 32 columns, no wait (pair with tmem_wait_ld)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+      "[%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+
+// fp32 bias -> f16 copy in shared memory (epilogue threads only), then a barrier among them
+__device__ __forceinline__ void stage_bias_f16(const float* b, __half* dst, int n, int tid) {
+  for (int i = tid * 2; i < n; i += EPI_WARPS * 32 * 2)
+    *reinterpret_cast<__half2*>(dst + i) = __floats2half2_rn(__ldg(b + i), __ldg(b + i + 1));
+  epi_bar_sync();
+}
+
+// =====================================================================================
+// forward
+// =====================================================================================
+namespace f {
+constexpr int NST = 3;             // weight ring depth
+constexpr int X_BYTES = TILE16, W_BYTES = TILE16, H_BYTES = 2 * TILE16;
 constexpr int OFF_W1 = X_BYTES;
 constexpr int OFF_W2 = OFF_W1 + NST * W_BYTES;
 constexpr int OFF_H = OFF_W2 + NST * W_BYTES;
-constexpr int OFF_BAR = OFF_H + 2 * H_BYTES;
-constexpr int OFF_STG = OFF_BAR + 256;
-constexpr int SMEM_TOTAL = OFF_STG + EPI_WARPS * 32 * STAGE_PITCH + 1024;
+constexpr int OFF_BIAS = OFF_H + 2 * H_BYTES;
+constexpr int OFF_BAR = OFF_BIAS + MAX_HID * 2;
+constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
 static_assert(SMEM_TOTAL <= 232448, "smem budget");
+}  // namespace f
 
 struct MlpArgs {
   int M, HID;                 // token rows, hidden width
   const float* b1; const float* b2;
   const float* resid; int64_t ldr;
   float* out; int64_t ldc;
-  bf16* hpre;                 // [M, HID] or null
 };
 
-template <bool SAVE_PRE>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const MlpArgs a) {
+  using namespace f;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
@@ -63,6 +149,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* h_free = h_ready + 2;          // 2
   uint64_t* y_full = h_free + 2;           // 1
   uint32_t* tmem_slot = (uint32_t*)(y_full + 1);
+  __half* bias_h = (__half*)(smem + OFF_BIAS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x;
@@ -144,46 +231,37 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int quad = warp & 3, grp = ew >> 2;            // rows quad*32.., hidden columns grp*32.. of the chunk
     const int r = quad * 32 + lane;
     const int row0 = mt * 128 + quad * 32;
-    const bool rows_full = row0 + 32 <= a.M;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    uint8_t* stage_buf = smem + OFF_STG + ew * (32 * STAGE_PITCH);
-    const int rr0 = lane >> 2, c16 = lane & 3;
+    stage_bias_f16(a.b1, bias_h, a.HID, threadIdx.x - 64);
     for (int c = 0; c < NC; ++c) {
       const int ab = c & 1; const uint32_t aph = (c >> 1) & 1;
       mbar_wait(&acc_full[ab], aph);
       tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem_base + ab * HC + grp * 32 + lane_off, v);
+      uint32_t v[32];
+      tmem_ld32_nowait(tmem_base + ab * HC + grp * 32 + lane_off, v);
+      tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_free[ab]);          // TMEM chunk drained: GEMM1(c+2) may start
-      const int col = c * HC + grp * 32;
+      const uint4* bsm = reinterpret_cast<const uint4*>(bias_h + c * HC + grp * 32);
+      uint4 o[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b1 + col) + i);
-        v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-      }
-      if constexpr (SAVE_PRE) {
-        uint8_t* dst = stage_buf + lane * STAGE_PITCH;
+      for (int i = 0; i < 4; ++i) {
+        const uint4 b4 = bsm[i];
+        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+        uint32_t ow[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + i * 16) = attn_pack8(v + 8 * i);
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rr = it * 8 + rr0;
-          const uint4 u = *reinterpret_cast<const uint4*>(stage_buf + rr * STAGE_PITCH + c16 * 16);
-          if (rows_full || row0 + rr < a.M)
-            *reinterpret_cast<uint4*>(a.hpre + (int64_t)(row0 + rr) * a.HID + col + c16 * 8) = u;
+        for (int j = 0; j < 4; ++j) {
+          __half2 x = __floats2half2_rn(__uint_as_float(v[8 * i + 2 * j]), __uint_as_float(v[8 * i + 2 * j + 1]));
+          x = __hadd2(x, *reinterpret_cast<const __half2*>(&bw[j]));
+          ow[j] = h2_to_bf2_bits(gelu_h2(x));
         }
-        __syncwarp();
+        o[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu3(v[i]);
       mbar_wait(&h_free[ab], aph ^ 1);                   // GEMM2(c-2) has consumed this buffer
       uint8_t* hb = smem + OFF_H + ab * H_BYTES + (grp >> 1) * 16384;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<uint4*>(hb + sw128_off(r, (grp & 1) * 4 + i)) = attn_pack8(v + 8 * i);
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(hb + sw128_off(r, (grp & 1) * 4 + i)) = o[i];
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&h_ready[ab]);
@@ -211,29 +289,341 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// =====================================================================================
+// backward
+// =====================================================================================
+namespace b {
+constexpr int NST = 3;                       // ring depth of the streamed operand pair
+constexpr int OFF_FIX = 0;                   // fixed pair:    MODE 0: X | dY      MODE 1: W1c | W2c
+constexpr int OFF_RING = 2 * TILE16;         // streamed pair: MODE 0: W1c | W2c   MODE 1: X | dY
+// 4 KB of bf16 1.0 (operand of the column-sum MMAs).  As a 128-row A operand only its first 8-row
+// group is ones; the other rows alias the dH tile that follows and produce accumulator rows nobody reads.
+constexpr int OFF_ONES = OFF_RING + NST * 2 * TILE16;
+constexpr int OFF_DH = OFF_ONES + 4096;               // dH tile [128 tok][128 hid] bf16 (two 64-column blocks)
+constexpr int OFF_G = OFF_DH + 2 * TILE16;            // G tile (MODE 1)
+constexpr int OFF_BIAS = OFF_G + 2 * TILE16;
+constexpr int OFF_BAR = OFF_BIAS + MAX_HID * 2;
+constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
+static_assert(SMEM_TOTAL <= 232448, "smem budget");
+static_assert(OFF_DH % 1024 == 0 && OFF_ONES % 1024 == 0, "swizzle atoms are 1024-byte aligned");
+// TMEM columns
+constexpr uint32_t T_HPRE = 0, T_DG = 128, T_ACC0 = 256, T_ACC1 = 320, T_ACC2 = 384;
+}  // namespace b
+
+struct MlpBwdArgs {
+  int M, HID;                 // token rows, hidden width
+  int tiles_per_split;        // MODE 1: token tiles per CTA
+  const float* b1;
+  float* dX; int64_t lddx;    // MODE 0: [M, 64] fp32
+  float* db2_part;            // MODE 0: [tiles][64] column sums of dY (or null)
+  float* dW1_part;            // MODE 1: [split][HID][64]
+  float* db1_part;            // MODE 1: [split][HID]
+  float* dW2_part;            // MODE 1: [split][64][HID]
+  int64_t split_stride;       // floats between consecutive splits (same for the three partials)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1)
+mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const MlpBwdArgs a) {
+  using namespace b;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
+  uint64_t* fix_full = bars;                // 1
+  uint64_t* ring_full = fix_full + 1;       // NST
+  uint64_t* ring_empty = ring_full + NST;   // NST
+  uint64_t* acc_full = ring_empty + NST;    // 1: Hpre and dG of this step are in TMEM
+  uint64_t* acc_free = acc_full + 1;        // 1 (16 warps): both drained into registers
+  uint64_t* h_ready = acc_free + 1;         // 1 (16 warps): dH (and G) tiles written
+  uint64_t* h_free = h_ready + 1;           // 1: the MMAs reading the tiles have retired
+  uint64_t* out_full = h_free + 1;          // 1
+  uint32_t* tmem_slot = (uint32_t*)(out_full + 1);
+  __half* bias_h = (__half*)(smem + OFF_BIAS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NC = a.HID / HC;
+  const int tiles = (a.M + 127) / 128;
+  // step i of this CTA = (token tile t_of(i), hidden chunk c_of(i))
+  int nsteps, t0, c0;
+  if (MODE == 0) { t0 = blockIdx.x; c0 = 0; nsteps = NC; }
+  else {
+    c0 = blockIdx.x % NC;
+    t0 = (blockIdx.x / NC) * a.tiles_per_split;
+    nsteps = min(a.tiles_per_split, tiles - t0);
+  }
+  const int split = (MODE == 0) ? 0 : blockIdx.x / NC;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDY); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+    mbar_init(fix_full, 1);
+    for (int i = 0; i < NST; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    mbar_init(acc_full, 1); mbar_init(acc_free, EPI_WARPS); mbar_init(h_ready, EPI_WARPS); mbar_init(h_free, 1);
+    mbar_init(out_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  // constant ones tile (generic-proxy writes, made visible to the tensor core by the fence below)
+  for (int i = threadIdx.x; i < 4096 / 4; i += THREADS) reinterpret_cast<uint32_t*>(smem + OFF_ONES)[i] = 0x3F803F80u;
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch();
+
+  // smem images
+  uint8_t* sX = smem + (MODE == 0 ? OFF_FIX : OFF_RING);
+  uint8_t* sW = smem + (MODE == 0 ? OFF_RING : OFF_FIX);
+  // (X, dY) and (W1c, W2c) are adjacent 16 KB tiles; the streamed pair advances by 2*TILE16 per stage
+
+  if (warp == 0) {
+    if (lane == 0) {
+      auto load_tok = [&](uint8_t* dst, uint64_t* bar, int t) {   // X tile | dY tile, rows t*128..
+        tma_load_2d(dst, &tmX, bar, 0, t * 128);
+        tma_load_2d(dst + TILE16, &tmDY, bar, 0, t * 128);
+      };
+      auto load_w = [&](uint8_t* dst, uint64_t* bar, int c) {     // W1[c*128.., :] | W2[:, c*128..] (two 64-col blocks)
+        tma_load_2d(dst, &tmW1, bar, 0, c * HC);
+        tma_load_2d(dst + TILE16, &tmW2, bar, c * HC, 0);
+        tma_load_2d(dst + TILE16 + 8192, &tmW2, bar, c * HC + 64, 0);
+      };
+      mbar_expect_tx(fix_full, 2 * TILE16);
+      if (MODE == 0) load_tok(sX, fix_full, t0); else load_w(sW, fix_full, c0);
+      for (int i = 0; i < nsteps; ++i) {
+        const int s = i % NST; const uint32_t ph = (i / NST) & 1;
+        mbar_wait(&ring_empty[s], ph ^ 1);
+        mbar_expect_tx(&ring_full[s], 2 * TILE16);
+        if (MODE == 0) load_w(sW + s * 2 * TILE16, &ring_full[s], c0 + i);
+        else load_tok(sX + s * 2 * TILE16, &ring_full[s], t0 + i);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_hpre = make_idesc(128, HC, false, false);                       // X (K) x W1c (K)
+      constexpr uint32_t id_dg = make_idesc(128, HC, false, true);                          // dY (K) x W2c (MN)
+      constexpr uint32_t id_dx = make_idesc(128, 64, false, true);                          // dH (K) x W1c (MN)
+      constexpr uint32_t id_dw1 = make_idesc(128, 64, true, true);                          // dH^T (MN) x X (MN)
+      constexpr uint32_t id_dw2 = make_idesc(128, 64, true, true);                          // G^T (MN) x dY (MN)
+      constexpr uint32_t id_db1 = make_idesc(128, 16, true, false);                         // dH^T (MN) x ones
+      constexpr uint32_t id_db2 = make_idesc(128, 64, false, true);                         // ones (K) x dY (MN)
+      const uint32_t s_dh = smem_u32(smem + OFF_DH), s_g = smem_u32(smem + OFF_G), s_one = smem_u32(smem + OFF_ONES);
+      auto stage_x = [&](int i) { return smem_u32(sX) + (MODE == 0 ? 0 : (i % NST) * 2 * TILE16); };
+      auto stage_w = [&](int i) { return smem_u32(sW) + (MODE == 0 ? (i % NST) * 2 * TILE16 : 0); };
+      auto issue_ab = [&](int i) {
+        const int s = i % NST; const uint32_t ph = (i / NST) & 1;
+        if (i > 0) mbar_wait(acc_free, (uint32_t)((i - 1) & 1));
+        mbar_wait(&ring_full[s], ph);
+        tc_fence_after();
+        const uint32_t x = stage_x(i), dy = x + TILE16, w1 = stage_w(i), w2 = w1 + TILE16;
+        const uint64_t xd = make_smem_desc(x, 16, 1024), w1d = make_smem_desc(w1, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_HPRE, xd + (uint64_t)(k * 2), w1d + (uint64_t)(k * 2), id_hpre, k > 0);
+        const uint64_t dyd = make_smem_desc(dy, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // W2c image: rows = 64 out (K), two 64-hid blocks 8192 B apart
+          umma_bf16(tmem_base + T_DG, dyd + (uint64_t)(k * 2), make_smem_desc(w2 + k * 2048, 8192, 1024), id_dg, k > 0);
+        umma_commit(acc_full);
+      };
+      mbar_wait(fix_full, 0);
+      issue_ab(0);
+      for (int i = 0; i < nsteps; ++i) {
+        if (i + 1 < nsteps) issue_ab(i + 1);
+        const int s = i % NST;
+        mbar_wait(h_ready, (uint32_t)(i & 1));
+        tc_fence_after();
+        const uint32_t x = stage_x(i), dy = x + TILE16, w1 = stage_w(i);
+        if (MODE == 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dX[tok, in] += dH[tok, hid] W1c[hid, in]
+            umma_bf16(tmem_base + T_ACC0, make_smem_desc(s_dh + (k >> 2) * TILE16 + (k & 3) * 32, 16, 1024),
+                      make_smem_desc(w1 + k * 2048, TILE16, 1024), id_dx, (i > 0 || k > 0) ? 1u : 0u);
+          if (i == 0 && a.db2_part) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)   // every row of the result = column sums of the dY tile
+              umma_bf16(tmem_base + T_ACC1, make_smem_desc(s_one, 16, 1024), make_smem_desc(dy + k * 2048, TILE16, 1024),
+                        id_db2, k > 0);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // K = 16 tokens per step = 16 rows of 128 B
+            const uint64_t dhd = make_smem_desc(s_dh + k * 2048, TILE16, 1024);
+            const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(tmem_base + T_ACC0, dhd, make_smem_desc(x + k * 2048, TILE16, 1024), id_dw1, acc);
+            umma_bf16(tmem_base + T_ACC1, make_smem_desc(s_g + k * 2048, TILE16, 1024),
+                      make_smem_desc(dy + k * 2048, TILE16, 1024), id_dw2, acc);
+            umma_bf16(tmem_base + T_ACC2, dhd, make_smem_desc(s_one, 16, 1024), id_db1, acc);
+          }
+        }
+        umma_commit(&ring_empty[s]);
+        umma_commit(h_free);
+      }
+      umma_commit(out_full);
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quad = warp & 3, grp = ew >> 2;            // rows quad*32.., hidden columns grp*32.. of the chunk
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    stage_bias_f16(a.b1, bias_h, a.HID, threadIdx.x - 64);
+    for (int i = 0; i < nsteps; ++i) {
+      const int c = (MODE == 0) ? c0 + i : c0;
+      mbar_wait(acc_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      uint32_t hv[32], gv[32];
+      tmem_ld32_nowait(tmem_base + T_HPRE + grp * 32 + lane_off, hv);
+      tmem_ld32_nowait(tmem_base + T_DG + grp * 32 + lane_off, gv);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);               // TMEM drained: the next step's Hpre / dG MMAs may start
+      const uint4* bsm = reinterpret_cast<const uint4*>(bias_h + c * HC + grp * 32);
+      uint4 odh[4], og[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 b4 = bsm[q];
+        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+        uint32_t wd[4], wg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = 8 * q + 2 * j;
+          __half2 x = __floats2half2_rn(__uint_as_float(hv[e]), __uint_as_float(hv[e + 1]));
+          x = __hadd2(x, *reinterpret_cast<const __half2*>(&bw[j]));
+          __half2 g, d;
+          gelu_grad_h2(x, g, d);
+          const float2 df = __half22float2(d);
+          const __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(gv[e]) * df.x, __uint_as_float(gv[e + 1]) * df.y);
+          wd[j] = *reinterpret_cast<const uint32_t*>(&p);
+          wg[j] = h2_to_bf2_bits(g);
+        }
+        odh[q] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        og[q] = make_uint4(wg[0], wg[1], wg[2], wg[3]);
+      }
+      if (i > 0) mbar_wait(h_free, (uint32_t)((i - 1) & 1));   // the previous step's MMAs have consumed the tiles
+      uint8_t* tdh = smem + OFF_DH + (grp >> 1) * TILE16;
+      uint8_t* tg = smem + OFF_G + (grp >> 1) * TILE16;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t off = sw128_off(r, (grp & 1) * 4 + q);
+        *reinterpret_cast<uint4*>(tdh + off) = odh[q];
+        if (MODE == 1) *reinterpret_cast<uint4*>(tg + off) = og[q];
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h_ready);
+    }
+    // ---- outputs (16 columns per warp)
+    mbar_wait(out_full, 0);
+    tc_fence_after();
+    float y[16];
+    if (MODE == 0) {
+      tmem_ld16(tmem_base + T_ACC0 + grp * 16 + lane_off, y);
+      const int row = t0 * 128 + r;
+      if (row < a.M) {
+        float* O = a.dX + (int64_t)row * a.lddx + grp * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(O)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+      }
+      if (a.db2_part && quad == 0) {                      // row 0 of the ones x dY product
+        tmem_ld16(tmem_base + T_ACC1 + grp * 16 + lane_off, y);
+        if (lane == 0) {
+          float* O = a.db2_part + (int64_t)t0 * 64 + grp * 16;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) O[q] = y[q];
+        }
+      }
+    } else {
+      const int h = c0 * HC + r;                          // hidden unit of this thread's accumulator row
+      const int64_t so = (int64_t)split * a.split_stride;
+      tmem_ld16(tmem_base + T_ACC0 + grp * 16 + lane_off, y);
+      {
+        float* O = a.dW1_part + so + (int64_t)h * 64 + grp * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(O)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+      }
+      tmem_ld16(tmem_base + T_ACC1 + grp * 16 + lane_off, y);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) a.dW2_part[so + (int64_t)(grp * 16 + q) * a.HID + h] = y[q];   // lanes = consecutive h
+      if (grp == 0) {
+        tmem_ld16(tmem_base + T_ACC2 + lane_off, y);
+        a.db1_part[so + h] = y[0];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ------------------------------------------------------------------ host
 static bool eligible(int D, int HID, int64_t M, const void* x, const void* w1, const void* w2, const float* resid,
                      int64_t ldr, const float* out, int64_t ldc) {
-  return tc::g_tc_enabled && D == 64 && HID % HC == 0 && M >= 1 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w1 & 15) == 0 &&
-         ((uintptr_t)w2 & 15) == 0 && ((uintptr_t)resid & 15) == 0 && ((uintptr_t)out & 15) == 0 && ldr % 4 == 0 && ldc % 4 == 0;
+  return tc::g_tc_enabled && D == 64 && HID % HC == 0 && HID <= MAX_HID && M >= 1 && ((uintptr_t)x & 15) == 0 &&
+         ((uintptr_t)w1 & 15) == 0 && ((uintptr_t)w2 & 15) == 0 && ((uintptr_t)resid & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+         ldr % 4 == 0 && ldc % 4 == 0;
 }
 
 static void fwd(const bf16* x, const bf16* W1, const float* b1, const bf16* W2, const float* b2, const float* resid,
-                int64_t ldr, float* out, int64_t ldc, bf16* hpre, int64_t M, int HID, cudaStream_t st) {
+                int64_t ldr, float* out, int64_t ldc, int64_t M, int HID, cudaStream_t st) {
   MlpArgs a;
-  a.M = (int)M; a.HID = HID; a.b1 = b1; a.b2 = b2; a.resid = resid; a.ldr = ldr; a.out = out; a.ldc = ldc; a.hpre = hpre;
+  a.M = (int)M; a.HID = HID; a.b1 = b1; a.b2 = b2; a.resid = resid; a.ldr = ldr; a.out = out; a.ldc = ldc;
   CUtensorMap tx = make_map(x, 64, M, 64, 64, 128);
   CUtensorMap tw1 = make_map(W1, 64, HID, 64, 64, 128);
   CUtensorMap tw2 = make_map(W2, HID, 64, HID, 64, 64);
   static bool attr = false;
   if (!attr) {
-    DG_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    DG_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    DG_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
     attr = true;
   }
   const int grid = (int)cdiv(M, 128);
-  if (hpre) launch_k(mlp_fwd_tc_kernel<true>, grid, THREADS, SMEM_TOTAL, st, tx, tw1, tw2, a);
-  else launch_k(mlp_fwd_tc_kernel<false>, grid, THREADS, SMEM_TOTAL, st, tx, tw1, tw2, a);
+  launch_k(mlp_fwd_tc_kernel, grid, THREADS, f::SMEM_TOTAL, st, tx, tw1, tw2, a);
+  DG_LAUNCH_CHECK();
+}
+
+// number of token ranges of the weight-gradient launch (grid = HID/128 x splits ~ one wave)
+static int bwd_splits(int64_t M, int HID) {
+  const int tiles = (int)cdiv(M, 128), NC = HID / HC;
+  int S = std::max(1, std::min(tiles, sm_count() / NC));
+  const int per = (int)cdiv(tiles, S);
+  return (int)cdiv(tiles, per);          // no empty range
+}
+// floats of partial storage needed by bwd()
+static size_t bwd_partial_floats(int64_t M, int HID) {
+  return (size_t)bwd_splits(M, HID) * ((size_t)HID * 64 * 2 + HID) + (size_t)cdiv(M, 128) * 64;
+}
+
+// dXn[M,64] = d/dx ; dW1 [HID,64], db1 [HID], dW2 [64,HID], db2 [64] (fp32, overwritten).
+// dW1 / db1 / dW2 must be adjacent in that order (the parameter arena's order) so that one pass reduces all three.
+static void bwd(const bf16* x, const bf16* dy, const bf16* W1, const float* b1, const bf16* W2, float* dXn, float* dW1,
+                float* db1, float* dW2, float* db2, float* partial, int64_t M, int HID, cudaStream_t st) {
+  DG_REQUIRE(db1 == dW1 + (int64_t)HID * 64 && dW2 == db1 + HID, "mlp::bwd: dW1 | db1 | dW2 must be contiguous");
+  const int tiles = (int)cdiv(M, 128), NC = HID / HC;
+  const int S = bwd_splits(M, HID);
+  const int64_t per_split = (int64_t)HID * 64 * 2 + HID;
+  MlpBwdArgs a;
+  a.M = (int)M; a.HID = HID; a.tiles_per_split = (int)cdiv(tiles, S); a.b1 = b1;
+  a.dX = dXn; a.lddx = 64;
+  a.dW1_part = partial; a.db1_part = partial + (int64_t)HID * 64; a.dW2_part = a.db1_part + HID;
+  a.split_stride = per_split;
+  a.db2_part = partial + (int64_t)S * per_split;
+  CUtensorMap tx = make_map(x, 64, M, 64, 64, 128);
+  CUtensorMap tdy = make_map(dy, 64, M, 64, 64, 128);
+  CUtensorMap tw1 = make_map(W1, 64, HID, 64, 64, 128);
+  CUtensorMap tw2 = make_map(W2, HID, 64, HID, 64, 64);
+  static bool attr = false;
+  if (!attr) {
+    DG_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b::SMEM_TOTAL));
+    DG_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b::SMEM_TOTAL));
+    attr = true;
+  }
+  launch_k(mlp_bwd_tc_kernel<0>, tiles, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
+  DG_LAUNCH_CHECK();
+  launch_k(mlp_bwd_tc_kernel<1>, NC * S, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
+  DG_LAUNCH_CHECK();
+  launch_k(reduce_partials_kernel, (unsigned)cdiv(per_split, 256), 256, 0, st, (const float*)partial, dW1, S, per_split);
+  DG_LAUNCH_CHECK();
+  launch_k(reduce_partials_kernel, 1, 64, 0, st, (const float*)a.db2_part, db2, tiles, (int64_t)64);
   DG_LAUNCH_CHECK();
 }
 

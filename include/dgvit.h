@@ -271,6 +271,17 @@ int dgvit_linear_bf16(const void* x, const void* W, void* y, int64_t rows, int N
 int dgvit_attention_bf16(const void* qkv, void* o, const void* d_o, void* d_qkv, int B, int N, int H,
                          int dim_head, int use_tensor_cores, void* stream);
 
+/* FeedForward.forward + residual (vn/GoalFormer.py:39-50,104) on bf16 operands, fused tcgen05 kernels, D = 64:
+ * forward  (d_y == NULL): out[rows,64] (fp32) = resid + W2 gelu(W1 x + b1) + b2, x [rows,64] bf16 (the LayerNorm output),
+ *                         W1 [hid,64], W2 [64,hid] bf16.
+ * backward (d_y != NULL): d_x[rows,64] (fp32) = gradient w.r.t. x; d_w = [dW1 (hid*64) | db1 (hid) | dW2 (64*hid)] fp32,
+ *                         d_b2 [64] fp32; partial = scratch of dgvit_mlp_partial_floats(rows, hid) floats.
+ * (unit tests, micro-benchmarks; the update calls the same kernels internally) */
+int dgvit_mlp_bf16(const void* x, const void* W1, const float* b1, const void* W2, const float* b2,
+                   const float* resid, float* out, const void* d_y, float* d_x, float* d_w, float* d_b2,
+                   float* partial, int64_t rows, int hid, void* stream);
+int64_t dgvit_mlp_partial_floats(int64_t rows, int hid);
+
 /* torch.optim.Adam.step (+ optional fused Polyak target update, vn/utils.py:31-33, and bf16
  * shadow refresh) over a flat arena; skips layout.skip ranges */
 int dgvit_adam_step(const dgvit_net* net, const dgvit_adam* opt, const dgvit_net* polyak_target,

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "dgvit.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|long long|const char\*)\s+(dgvit_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|int64_t|long long|const char\*)\s+(dgvit_\w+)\s*\(", hdr, flags=re.M))
     assert declared, "no declarations parsed"
     lib = C.CDLL(L.LIB_PATH)
     for name in declared:
