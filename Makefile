@@ -13,6 +13,10 @@ all: $(LIB)
 $(LIB): $(SRCS) $(HDRS)
 	$(NVCC) $(FLAGS) $(EXTRA) -DDGVIT_WITH_TC -shared -o $@ $(SRCS)
 
+# instrumented build for profiles/mlp_trace.py (never loaded by the package)
+trace: $(SRCS) $(HDRS)
+	$(NVCC) $(FLAGS) -DDGVIT_WITH_TC -DDGVIT_MLP_TRACE -shared -o $(PKG)/libdgvit_trace.so $(SRCS)
+
 clean:
 	rm -f $(LIB)
-.PHONY: all clean
+.PHONY: all clean trace

@@ -102,7 +102,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   pdl_launch();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int st = 0; uint32_t ph = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int b = it / a.H, h = it % a.H;
@@ -116,7 +116,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc_s = make_idesc(128, a.KPAD, false, false);
       const uint32_t idesc_o = make_idesc(128, DH, false, true);
       const int ksteps = a.KPAD / 16;
@@ -267,7 +267,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   pdl_launch();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int st = 0; uint32_t ph = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int b = it / a.H, h = it % a.H;
@@ -282,7 +282,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc_s = make_idesc(128, a.KPAD, false, false);    // S, dP
       const uint32_t idesc_q = make_idesc(128, DH, false, true);         // dQ = dS K      (A K-major, B MN-major)
       const uint32_t idesc_t = make_idesc(128, DH, true, true);          // dK, dV         (A MN-major, B MN-major)

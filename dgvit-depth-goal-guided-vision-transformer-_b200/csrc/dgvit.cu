@@ -982,6 +982,11 @@ int dgvit_set_option(const char* name, int value) {
   });
 }
 
+#if defined(DGVIT_MLP_TRACE) && defined(DGVIT_WITH_TC)
+// trace builds only (make trace -> libdgvit_trace.so): device buffer receiving the pipeline timeline of CTA 0
+int dgvit_debug_set_trace(void* p) { mlp::g_trace = (long long*)p; return 0; }
+#endif
+
 int dgvit_prof_begin(int tag, int max_launches) {
   return guarded([&] {
     Prof& p = prof();

@@ -4,7 +4,8 @@
 //
 // The heads are ~50 kFLOP per sample (0.03 % of a network pass) and purely latency-bound when run
 // as separate tiny GEMMs, so each direction is one launch: weights staged once per CTA in shared
-// memory (odd row pitch -> conflict-free), 8 samples per pass, fp32 throughout.
+// memory with float4 loads (the staging round trips, not the arithmetic, set the duration), 8 samples
+// per pass, fp32 throughout.
 // Twin critic heads (fc1/fc2/fc3 and fc11/fc21/fc31) run as blockIdx.y = 0/1 of one launch; the
 // actor's two output layers (mean_linear, log_std_linear) are the "a" and "b" outputs of one head.
 #pragma once
@@ -31,7 +32,32 @@ struct FwdArgs {
 __host__ __device__ __forceinline__ int odd_pitch(int k) { return k | 1; }
 __host__ __device__ __forceinline__ int al4(int n) { return (n + 3) & ~3; }
 
-__global__ void __launch_bounds__(128) head_fwd_kernel(FwdArgs a) {
+constexpr int FWD_THREADS = 512;   // 4 K-quarters x 128 output units
+constexpr int BWD_THREADS = 512;
+
+// global [rows][cols] (dense, 16-byte aligned, rows*cols % 4 == 0 not required) -> smem [rows][pitch], float4 loads
+__device__ __forceinline__ void stage_matrix(float* dst, int pitch, const float* __restrict__ src, int rows, int cols,
+                                             int tid, int nthreads) {
+  const int n = rows * cols, n4 = n >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  for (int i = tid; i < n4; i += nthreads) {
+    const float4 v = __ldg(s4 + i);
+    const int e = i * 4;
+    int r = e / cols, c = e - r * cols;
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      dst[r * pitch + c] = vv[q];
+      if (++c == cols) { c = 0; ++r; }
+    }
+  }
+  for (int e = n4 * 4 + tid; e < n; e += nthreads) dst[(e / cols) * pitch + e % cols] = __ldg(src + e);
+}
+
+// One pass = S samples.  Layers 1 and 2: thread (j = tid & 127, q = tid >> 7) accumulates output unit j over the
+// q-th quarter of the contraction for all S samples (weights conflict-free through the odd row pitch, inputs
+// broadcast as float4); the four quarters are summed in a fixed order through shared memory.
+__global__ void __launch_bounds__(FWD_THREADS) head_fwd_kernel(FwdArgs a) {
   pdl_wait();
   pdl_launch();
   extern __shared__ __align__(16) float sm[];
@@ -45,19 +71,21 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(FwdArgs a) {
   float* b2s = b1s + H1;                 // [H2]
   float* b3s = b2s + al4(H2);            // [NO]
   float* xs = b3s + MAX_NO;              // [K0][S]
-  float* h1s = xs + K0 * S;              // [H1][S]
+  float* h1s = xs + al4(K0) * S;         // [H1][S]
   float* h2s = h1s + H1 * S;             // [H2][S]
+  float* red = h2s + H1 * S;             // [4][S][H1]
   const int tid = threadIdx.x;
-  for (int i = tid; i < H1 * K0; i += blockDim.x) W1s[(i / K0) * p1 + i % K0] = w.W1[i];
-  for (int i = tid; i < H2 * H1; i += blockDim.x) W2s[(i / H1) * p2 + i % H1] = w.W2[i];
-  for (int i = tid; i < a.NOa * H2; i += blockDim.x) W3s[(i / H2) * p3 + i % H2] = w.W3a[i];
-  for (int i = tid; i < a.NOb * H2; i += blockDim.x) W3s[(a.NOa + i / H2) * p3 + i % H2] = w.W3b[i];
-  for (int i = tid; i < H1; i += blockDim.x) b1s[i] = w.b1[i];
-  for (int i = tid; i < H2; i += blockDim.x) b2s[i] = w.b2[i];
-  for (int i = tid; i < NO; i += blockDim.x) b3s[i] = i < a.NOa ? w.b3a[i] : w.b3b[i - a.NOa];
+  stage_matrix(W1s, p1, w.W1, H1, K0, tid, FWD_THREADS);
+  stage_matrix(W2s, p2, w.W2, H2, H1, tid, FWD_THREADS);
+  stage_matrix(W3s, p3, w.W3a, a.NOa, H2, tid, FWD_THREADS);
+  if (a.NOb) stage_matrix(W3s + a.NOa * p3, p3, w.W3b, a.NOb, H2, tid, FWD_THREADS);
+  for (int i = tid; i < H1; i += FWD_THREADS) b1s[i] = w.b1[i];
+  for (int i = tid; i < H2; i += FWD_THREADS) b2s[i] = w.b2[i];
+  for (int i = tid; i < NO; i += FWD_THREADS) b3s[i] = i < a.NOa ? w.b3a[i] : w.b3b[i - a.NOa];
+  const int j = tid & (H1 - 1), q = tid >> 7;
   for (int s0 = blockIdx.x * S; s0 < a.B; s0 += gridDim.x * S) {
     __syncthreads();
-    for (int i = tid; i < K0 * S; i += blockDim.x) {
+    for (int i = tid; i < K0 * S; i += FWD_THREADS) {
       const int s = i / K0, k = i % K0, b = s0 + s;
       float v = 0.f;
       if (b < a.B) v = k < a.K1 ? a.x1[(int64_t)b * a.K1 + k] : a.x2[(int64_t)b * a.K2 + (k - a.K1)];
@@ -65,49 +93,51 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(FwdArgs a) {
       if (a.xcat && blockIdx.y == 0 && b < a.B) a.xcat[(int64_t)b * K0 + k] = v;
     }
     __syncthreads();
-    {  // layer 1: thread j < H1
-      const int j = tid;
-      float acc[S];
+    auto layer = [&](const float* Ws, int pitch, const float* in, int K, int nout) {
+      if (j < nout) {
+        const int kq = (K + 3) >> 2, k0 = q * kq, k1 = min(K, k0 + kq);
+        float acc[S];
 #pragma unroll
-      for (int s = 0; s < S; ++s) acc[s] = b1s[j];
-      for (int k = 0; k < K0; ++k) {
-        const float wv = W1s[j * p1 + k];
-        const float4 xa = *reinterpret_cast<const float4*>(xs + k * S), xb = *reinterpret_cast<const float4*>(xs + k * S + 4);
-        acc[0] = fmaf(wv, xa.x, acc[0]); acc[1] = fmaf(wv, xa.y, acc[1]); acc[2] = fmaf(wv, xa.z, acc[2]); acc[3] = fmaf(wv, xa.w, acc[3]);
-        acc[4] = fmaf(wv, xb.x, acc[4]); acc[5] = fmaf(wv, xb.y, acc[5]); acc[6] = fmaf(wv, xb.z, acc[6]); acc[7] = fmaf(wv, xb.w, acc[7]);
-      }
+        for (int s = 0; s < S; ++s) acc[s] = 0.f;
+#pragma unroll 4
+        for (int k = k0; k < k1; ++k) {
+          const float wv = Ws[j * pitch + k];
+          const float4 xa = *reinterpret_cast<const float4*>(in + k * S), xb = *reinterpret_cast<const float4*>(in + k * S + 4);
+          acc[0] = fmaf(wv, xa.x, acc[0]); acc[1] = fmaf(wv, xa.y, acc[1]); acc[2] = fmaf(wv, xa.z, acc[2]); acc[3] = fmaf(wv, xa.w, acc[3]);
+          acc[4] = fmaf(wv, xb.x, acc[4]); acc[5] = fmaf(wv, xb.y, acc[5]); acc[6] = fmaf(wv, xb.z, acc[6]); acc[7] = fmaf(wv, xb.w, acc[7]);
+        }
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        acc[s] = fmaxf(acc[s], 0.f);
-        h1s[j * S + s] = acc[s];
-        if (s0 + s < a.B) w.h1[(int64_t)(s0 + s) * H1 + j] = acc[s];
+        for (int s = 0; s < S; ++s) red[(q * S + s) * H1 + j] = acc[s];
       }
-    }
+    };
+    auto finish = [&](const float* bs, float* hs, float* hg, int nout) {   // relu(bias + quarters), fixed order
+      for (int i = tid; i < nout * S; i += FWD_THREADS) {
+        const int s = i / nout, u = i - s * nout;
+        float v = bs[u] + red[(0 * S + s) * H1 + u];
+        v += red[(1 * S + s) * H1 + u]; v += red[(2 * S + s) * H1 + u]; v += red[(3 * S + s) * H1 + u];
+        v = fmaxf(v, 0.f);
+        hs[u * S + s] = v;
+        if (s0 + s < a.B) hg[(int64_t)(s0 + s) * nout + u] = v;
+      }
+    };
+    layer(W1s, p1, xs, K0, H1);
     __syncthreads();
-    if (tid < H2) {  // layer 2
-      const int j = tid;
-      float acc[S];
-#pragma unroll
-      for (int s = 0; s < S; ++s) acc[s] = b2s[j];
-      for (int k = 0; k < H1; ++k) {
-        const float wv = W2s[j * p2 + k];
-        const float4 xa = *reinterpret_cast<const float4*>(h1s + k * S), xb = *reinterpret_cast<const float4*>(h1s + k * S + 4);
-        acc[0] = fmaf(wv, xa.x, acc[0]); acc[1] = fmaf(wv, xa.y, acc[1]); acc[2] = fmaf(wv, xa.z, acc[2]); acc[3] = fmaf(wv, xa.w, acc[3]);
-        acc[4] = fmaf(wv, xb.x, acc[4]); acc[5] = fmaf(wv, xb.y, acc[5]); acc[6] = fmaf(wv, xb.z, acc[6]); acc[7] = fmaf(wv, xb.w, acc[7]);
-      }
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        acc[s] = fmaxf(acc[s], 0.f);
-        h2s[j * S + s] = acc[s];
-        if (s0 + s < a.B) w.h2[(int64_t)(s0 + s) * H2 + j] = acc[s];
-      }
-    }
+    finish(b1s, h1s, w.h1, H1);
     __syncthreads();
-    if (tid < S * NO) {  // output layer(s): thread = (sample, output)
-      const int s = tid / NO, o = tid % NO;
-      float acc = b3s[o];
-      for (int k = 0; k < H2; ++k) acc = fmaf(W3s[o * p3 + k], h2s[k * S + s], acc);
-      if (s0 + s < a.B) {
+    layer(W2s, p2, h1s, H1, H2);
+    __syncthreads();
+    finish(b2s, h2s, w.h2, H2);
+    __syncthreads();
+    if (tid < S * NO * 4) {  // output layer(s): 4 lanes per (sample, output), quarter of H2 each
+      const int pr = tid >> 2, part = tid & 3;
+      const int s = pr / NO, o = pr % NO;
+      const int kq = (H2 + 3) >> 2, k0 = part * kq, k1 = min(H2, k0 + kq);
+      float acc = 0.f;
+      for (int k = k0; k < k1; ++k) acc = fmaf(W3s[o * p3 + k], h2s[k * S + s], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += b3s[o];
+      if (part == 0 && s0 + s < a.B) {
         if (o < a.NOa) w.outa[(int64_t)(s0 + s) * a.NOa + o] = acc;
         else w.outb[(int64_t)(s0 + s) * a.NOb + (o - a.NOa)] = acc;
       }
@@ -128,23 +158,23 @@ struct BwdArgs {
   int nheads, B, K0, H2, NOa, NOb;
 };
 
-__global__ void __launch_bounds__(256) head_bwd_dx_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(BWD_THREADS) head_bwd_dx_kernel(BwdArgs a) {
   pdl_wait();
   pdl_launch();
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const BwdHead& h = a.h[blockIdx.y];
   const int K0 = a.K0, H2 = a.H2, NO = a.NOa + a.NOb;
   float* W1s = sm;                       // [H1][K0]
-  float* W2s = W1s + H1 * K0;            // [H2][H1]
+  float* W2s = W1s + al4(H1 * K0);       // [H2][H1]
   float* W3s = W2s + H2 * H1;            // [NO][H2]
-  float* dos = W3s + NO * H2;            // [NO][S]
+  float* dos = W3s + al4(NO * H2);       // [NO][S]
   float* dh2s = dos + MAX_NO * S;        // [H2][S]
   float* dh1s = dh2s + H2 * S;           // [H1][S]
   const int tid = threadIdx.x;
-  for (int i = tid; i < H1 * K0; i += blockDim.x) W1s[i] = h.W1[i];
-  for (int i = tid; i < H2 * H1; i += blockDim.x) W2s[i] = h.W2[i];
-  for (int i = tid; i < a.NOa * H2; i += blockDim.x) W3s[i] = h.W3a[i];
-  for (int i = tid; i < a.NOb * H2; i += blockDim.x) W3s[a.NOa * H2 + i] = h.W3b[i];
+  stage_matrix(W1s, K0, h.W1, H1, K0, tid, BWD_THREADS);
+  stage_matrix(W2s, H1, h.W2, H2, H1, tid, BWD_THREADS);
+  stage_matrix(W3s, H2, h.W3a, a.NOa, H2, tid, BWD_THREADS);
+  if (a.NOb) stage_matrix(W3s + a.NOa * H2, H2, h.W3b, a.NOb, H2, tid, BWD_THREADS);
   for (int s0 = blockIdx.x * S; s0 < a.B; s0 += gridDim.x * S) {
     __syncthreads();
     if (tid < NO * S) {
@@ -154,8 +184,8 @@ __global__ void __launch_bounds__(256) head_bwd_dx_kernel(BwdArgs a) {
       dos[o * S + s] = v;
     }
     __syncthreads();
-    for (int i = tid; i < H2 * S; i += blockDim.x) {       // dh2[s][j]
-      const int j = i / S, s = i % S, b = s0 + s;
+    for (int i = tid; i < H2 * S; i += BWD_THREADS) {       // dh2[s][j]: consecutive threads -> consecutive j
+      const int j = i % H2, s = i / H2, b = s0 + s;
       float acc = 0.f;
       for (int o = 0; o < NO; ++o) acc = fmaf(dos[o * S + s], W3s[o * H2 + j], acc);
       const bool on = b < a.B && h.h2[(int64_t)b * H2 + j] > 0.f;
@@ -164,27 +194,42 @@ __global__ void __launch_bounds__(256) head_bwd_dx_kernel(BwdArgs a) {
       if (b < a.B) h.dh2[(int64_t)b * H2 + j] = acc;
     }
     __syncthreads();
-    for (int i = tid; i < H1 * S; i += blockDim.x) {       // dh1[s][k]: consecutive threads -> consecutive k
-      const int k = i % H1, s = i / H1, b = s0 + s;
-      float acc = 0.f;
-      for (int j = 0; j < H2; ++j) acc = fmaf(dh2s[j * S + s], W2s[j * H1 + k], acc);
-      const bool on = b < a.B && h.h1[(int64_t)b * H1 + k] > 0.f;
-      acc = on ? acc : 0.f;
-      dh1s[k * S + s] = acc;
-      if (b < a.B) h.dh1[(int64_t)b * H1 + k] = acc;
+    for (int i = tid; i < H1 * (S / 2); i += BWD_THREADS) { // dh1[s][k], two samples per thread
+      const int k = i % H1, s = (i / H1) * 2, b = s0 + s;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < H2; ++j) {
+        const float wv = W2s[j * H1 + k];
+        const float2 d = *reinterpret_cast<const float2*>(dh2s + j * S + s);
+        a0 = fmaf(d.x, wv, a0); a1 = fmaf(d.y, wv, a1);
+      }
+      a0 = (b < a.B && h.h1[(int64_t)b * H1 + k] > 0.f) ? a0 : 0.f;
+      a1 = (b + 1 < a.B && h.h1[(int64_t)(b + 1) * H1 + k] > 0.f) ? a1 : 0.f;
+      dh1s[k * S + s] = a0; dh1s[k * S + s + 1] = a1;
+      if (b < a.B) h.dh1[(int64_t)b * H1 + k] = a0;
+      if (b + 1 < a.B) h.dh1[(int64_t)(b + 1) * H1 + k] = a1;
     }
     __syncthreads();
-    for (int i = tid; i < K0 * S; i += blockDim.x) {       // dx[s][d]
-      const int d = i % K0, s = i / K0, b = s0 + s;
-      float acc = 0.f;
-      for (int k = 0; k < H1; ++k) acc = fmaf(dh1s[k * S + s], W1s[k * K0 + d], acc);
-      if (b < a.B) h.dx[(int64_t)b * K0 + d] = acc;
+    for (int i = tid; i < K0 * (S / 2); i += BWD_THREADS) { // dx[s][d], two samples per thread
+      const int d = i % K0, s = (i / K0) * 2, b = s0 + s;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < H1; ++k) {
+        const float wv = W1s[k * K0 + d];
+        const float2 g = *reinterpret_cast<const float2*>(dh1s + k * S + s);
+        a0 = fmaf(g.x, wv, a0); a1 = fmaf(g.y, wv, a1);
+      }
+      if (b < a.B) h.dx[(int64_t)b * K0 + d] = a0;
+      if (b + 1 < a.B) h.dx[(int64_t)(b + 1) * K0 + d] = a1;
     }
   }
 }
 
 // ---- backward, parameter gradients of up to 8 linear layers in one launch:
-//      dW[n][k] = sum_s dy[s][n] x[s][k] ; db[n] = sum_s dy[s][n]   (fixed order over s: deterministic)
+//      dW[n][k] = sum_s dy[s][n] x[s][k] ; db[n] = sum_s dy[s][n]
+// One CTA per 32x32 tile of dW.  Each of the 8 warps owns every 8th slab of 32 samples and accumulates the whole
+// tile for it in registers (lane = k, 32 n-accumulators; dy rows broadcast from a per-warp smem slab); the eight
+// per-warp tiles are then summed in a fixed order, so the result is deterministic.
 struct DwJob {
   const float *dy, *x;   // [B,N] (row pitch ldy), [B,K]
   float *dW, *db;        // [N,K], [N]
@@ -197,55 +242,74 @@ struct DwArgs {
 __global__ void __launch_bounds__(256) head_dw_kernel(DwArgs a) {
   pdl_wait();
   pdl_launch();
-  __shared__ float dys[32][33];
-  __shared__ float xs[32][33];
+  __shared__ __align__(16) float slab[8][32][32];   // per-warp dy slab [s][n]; reused for the cross-warp sum
+  __shared__ float bsum[8][32];
   int ji = 0;
   while (ji + 1 < a.njobs && (int)blockIdx.x >= a.job[ji + 1].tile0) ++ji;
   const DwJob& j = a.job[ji];
   const int t = blockIdx.x - j.tile0;
   const int kt = (j.K + 31) / 32;
   const int n0 = (t / kt) * 32, k0 = (t % kt) * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // thread: k = tx, n = ty + 8*i
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int s0 = 0; s0 < a.B; s0 += 32) {
-    __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool n_ok = n0 + lane < j.N, k_ok = k0 + lane < j.K;
+  float acc[32], accb = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int s = ty + 8 * i, b = s0 + s;
-      dys[s][tx] = (b < a.B && n0 + tx < j.N) ? j.dy[(int64_t)b * j.ldy + n0 + tx] : 0.f;
-      xs[s][tx] = (b < a.B && k0 + tx < j.K) ? j.x[(int64_t)b * j.K + k0 + tx] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 8
+  for (int n = 0; n < 32; ++n) acc[n] = 0.f;
+  for (int s0 = w * 32; s0 < a.B; s0 += 8 * 32) {
+    float xr[32];
+#pragma unroll
     for (int s = 0; s < 32; ++s) {
-      const float xv = xs[s][tx];
+      const int b = s0 + s;
+      const float d = (b < a.B && n_ok) ? j.dy[(int64_t)b * j.ldy + n0 + lane] : 0.f;
+      xr[s] = (b < a.B && k_ok) ? j.x[(int64_t)b * j.K + k0 + lane] : 0.f;
+      slab[w][s][lane] = d;
+      accb += d;
+    }
+    __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float d = dys[s][ty + 8 * i];
-        acc[i] = fmaf(d, xv, acc[i]);
-        accb[i] += d;
+    for (int s = 0; s < 32; ++s) {
+      const float xv = xr[s];
+#pragma unroll
+      for (int n4 = 0; n4 < 8; ++n4) {
+        const float4 d = *reinterpret_cast<const float4*>(&slab[w][s][4 * n4]);
+        acc[4 * n4] = fmaf(d.x, xv, acc[4 * n4]); acc[4 * n4 + 1] = fmaf(d.y, xv, acc[4 * n4 + 1]);
+        acc[4 * n4 + 2] = fmaf(d.z, xv, acc[4 * n4 + 2]); acc[4 * n4 + 3] = fmaf(d.w, xv, acc[4 * n4 + 3]);
       }
     }
+    __syncwarp();
   }
 #pragma unroll
+  for (int n = 0; n < 32; ++n) slab[w][n][lane] = acc[n];     // now [w][n][k]
+  bsum[w][lane] = accb;
+  __syncthreads();
+#pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int n = n0 + ty + 8 * i, k = k0 + tx;
-    if (n < j.N && k < j.K) j.dW[(int64_t)n * j.K + k] = acc[i];
-    if (j.db && k0 == 0 && tx == 0 && n < j.N) j.db[n] = accb[i];
+    const int n = w + 8 * i;
+    float v = slab[0][n][lane];
+#pragma unroll
+    for (int ww = 1; ww < 8; ++ww) v += slab[ww][n][lane];
+    if (n0 + n < j.N && k_ok) j.dW[(int64_t)(n0 + n) * j.K + k0 + lane] = v;
+  }
+  if (j.db && k0 == 0 && w == 0 && n_ok) {
+    float v = bsum[0][lane];
+#pragma unroll
+    for (int ww = 1; ww < 8; ++ww) v += bsum[ww][lane];
+    j.db[n0 + lane] = v;
   }
 }
 
 static size_t fwd_smem(int K0, int H2, int NO) {
   return sizeof(float) * ((size_t)al4(H1 * (K0 | 1)) + (size_t)al4(H2 * (H1 | 1)) + (size_t)al4(NO * (H2 | 1)) + H1 + al4(H2) +
-                          MAX_NO + (size_t)K0 * S + (size_t)H1 * S + (size_t)H2 * S);
+                          MAX_NO + (size_t)al4(K0) * S + (size_t)H1 * S + (size_t)H1 * S + (size_t)4 * S * H1);
 }
 static size_t bwd_smem(int K0, int H2, int NO) {
-  return sizeof(float) * ((size_t)H1 * K0 + (size_t)H2 * H1 + (size_t)NO * H2 + MAX_NO * S + (size_t)H2 * S + (size_t)H1 * S);
+  return sizeof(float) * ((size_t)al4(H1 * K0) + (size_t)H2 * H1 + (size_t)al4(NO * H2) + MAX_NO * S + (size_t)H2 * S +
+                          (size_t)H1 * S);
 }
 
 static void launch_fwd(const FwdArgs& a, cudaStream_t st) {
   const int K0 = a.K1 + a.K2, NO = a.NOa + a.NOb;
-  DG_REQUIRE(NO <= MAX_NO && a.H2 <= 128 && S * NO <= 128, "head_fwd: unsupported head shape");
+  DG_REQUIRE(NO <= MAX_NO && a.H2 <= 128 && S * NO * 4 <= FWD_THREADS, "head_fwd: unsupported head shape");
   const size_t smem = fwd_smem(K0, a.H2, NO);
   DG_REQUIRE(smem <= 227 * 1024, "head_fwd: K0=%d needs %zu B smem", K0, smem);
   static size_t attr = 0;
@@ -254,7 +318,7 @@ static void launch_fwd(const FwdArgs& a, cudaStream_t st) {
     attr = 227 * 1024;
   }
   dim3 grid((unsigned)std::min<int64_t>(cdiv(a.B, S), 148), (unsigned)a.nheads);
-  launch_k(head_fwd_kernel, grid, 128, smem, st, a);
+  launch_k(head_fwd_kernel, grid, FWD_THREADS, smem, st, a);
   DG_LAUNCH_CHECK();
 }
 static void launch_bwd_dx(const BwdArgs& a, cudaStream_t st) {
@@ -267,7 +331,7 @@ static void launch_bwd_dx(const BwdArgs& a, cudaStream_t st) {
     attr = 227 * 1024;
   }
   dim3 grid((unsigned)std::min<int64_t>(cdiv(a.B, S), 148), (unsigned)a.nheads);
-  launch_k(head_bwd_dx_kernel, grid, 256, smem, st, a);
+  launch_k(head_bwd_dx_kernel, grid, BWD_THREADS, smem, st, a);
   DG_LAUNCH_CHECK();
 }
 struct DwList {

@@ -124,7 +124,15 @@ constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
 static_assert(SMEM_TOTAL <= 232448, "smem budget");
 }  // namespace f
 
+// optional timeline instrumentation (DGVIT_MLP_TRACE builds only): CTA 0 records clock64() at pipeline events
+#ifdef DGVIT_MLP_TRACE
+#define MLP_TRACE(slot, idx) do { if (a.trace && blockIdx.x == 0 && (lane == 0 || warp < 2)) a.trace[(slot) * 64 + (idx)] = clock64(); } while (0)
+#else
+#define MLP_TRACE(slot, idx) do { } while (0)
+#endif
+
 struct MlpArgs {
+  long long* trace;           // [16 slots][64] (null unless tracing)
   int M, HID;                 // token rows, hidden width
   const float* b1; const float* b2;
   const float* resid; int64_t ldr;
@@ -144,8 +152,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* w2_full = w1_empty + NST;      // NST
   uint64_t* w2_empty = w2_full + NST;      // NST
   uint64_t* acc_full = w2_empty + NST;     // 2
-  uint64_t* acc_free = acc_full + 2;       // 2 (16 warps)
-  uint64_t* h_ready = acc_free + 2;        // 2 (16 warps)
+  uint64_t* acc_free = acc_full + 2;       // 2 (8 warps each)
+  uint64_t* h_ready = acc_free + 2;        // 2 (8 warps each)
   uint64_t* h_free = h_ready + 2;          // 2
   uint64_t* y_full = h_free + 2;           // 1
   uint32_t* tmem_slot = (uint32_t*)(y_full + 1);
@@ -154,12 +162,13 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x;
   const int NC = a.HID / HC;
+  if (warp == 2) MLP_TRACE(12, 0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     mbar_init(x_full, 1);
     for (int i = 0; i < NST; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], EPI_WARPS); mbar_init(&h_ready[i], EPI_WARPS); mbar_init(&h_free[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], EPI_WARPS / 2); mbar_init(&h_ready[i], EPI_WARPS / 2); mbar_init(&h_free[i], 1); }
     mbar_init(y_full, 1);
     fence_barrier_init();
   }
@@ -169,11 +178,13 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;     // acc1: cols [0,256) ; Y: cols [256,320)
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
+  if (warp == 2) MLP_TRACE(12, 1);
   pdl_wait();
   pdl_launch();
+  if (warp == 2) MLP_TRACE(12, 2);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(x_full, X_BYTES);
       tma_load_2d(smem, &tmX, x_full, 0, mt * 128);
       for (int c = 0; c < NC; ++c) {
@@ -188,7 +199,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc1 = make_idesc(128, HC, false, false);
       constexpr uint32_t idesc2 = make_idesc(128, 64, false, false);
       const uint32_t sx = smem_u32(smem);
@@ -206,13 +217,21 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         umma_commit(&acc_full[ab]);
       };
       mbar_wait(x_full, 0);
+      MLP_TRACE(12, 8);
       gemm1(0);
+      MLP_TRACE(12, 9);
+      if (NC > 1) gemm1(1);
       for (int c = 0; c < NC; ++c) {
-        if (c + 1 < NC) gemm1(c + 1);
+        // accumulator buffer c&1 is free as soon as the epilogue of chunk c has pulled it into registers, long before
+        // that epilogue finishes: GEMM1(c+2) is issued now so its result is waiting when the group comes back
+        if (c + 2 < NC) gemm1(c + 2);
         const int s = c % NST; const uint32_t ph = (c / NST) & 1;
         const int hb = c & 1; const uint32_t hph = (c >> 1) & 1;
+        MLP_TRACE(8, c);
         mbar_wait(&h_ready[hb], hph);
+        MLP_TRACE(9, c);
         mbar_wait(&w2_full[s], ph);
+        MLP_TRACE(10, c);
         tc_fence_after();
         const uint32_t sh = sx + OFF_H + hb * H_BYTES, sw = sx + OFF_W2 + s * W_BYTES;
 #pragma unroll
@@ -223,69 +242,90 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         umma_commit(&w2_empty[s]);
         umma_commit(&h_free[hb]);
+        MLP_TRACE(11, c);
       }
       umma_commit(y_full);
     }
   } else {
+    // Two ping-pong groups of 8 warps: group g owns the chunks c = g (mod 2), i.e. accumulator buffer g and H buffer g,
+    // so one group's TMEM-load / smem-store / barrier phases overlap the other group's MUFU + FMA phase.
     const int ew = warp - 2;
-    const int quad = warp & 3, grp = ew >> 2;            // rows quad*32.., hidden columns grp*32.. of the chunk
+    const int pg = ew >> 3, half = (ew >> 2) & 1;        // group ; 64-column half of the chunk
+    const int quad = warp & 3, grp = ew >> 2;            // TMEM lane quadrant ; 16-column group of the final output
     const int r = quad * 32 + lane;
     const int row0 = mt * 128 + quad * 32;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     stage_bias_f16(a.b1, bias_h, a.HID, threadIdx.x - 64);
-    for (int c = 0; c < NC; ++c) {
-      const int ab = c & 1; const uint32_t aph = (c >> 1) & 1;
+    if (warp == 2) MLP_TRACE(12, 3);
+    for (int c = pg; c < NC; c += 2) {
+      const int ab = pg; const uint32_t aph = (c >> 1) & 1;
+      if ((ew & 7) == 0) MLP_TRACE(0, c);
       mbar_wait(&acc_full[ab], aph);
+      if ((ew & 7) == 0) MLP_TRACE(1, c);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32_nowait(tmem_base + ab * HC + grp * 32 + lane_off, v);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_free[ab]);          // TMEM chunk drained: GEMM1(c+2) may start
-      const uint4* bsm = reinterpret_cast<const uint4*>(bias_h + c * HC + grp * 32);
-      uint4 o[4];
+      uint4 o[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 b4 = bsm[i];
-        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-        uint32_t ow[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __half2 x = __floats2half2_rn(__uint_as_float(v[8 * i + 2 * j]), __uint_as_float(v[8 * i + 2 * j + 1]));
-          x = __hadd2(x, *reinterpret_cast<const __half2*>(&bw[j]));
-          ow[j] = h2_to_bf2_bits(gelu_h2(x));
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32_nowait(tmem_base + ab * HC + half * 64 + hh * 32 + lane_off, v);
+        tmem_wait_ld();
+        if (hh == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_free[ab]);      // TMEM chunk drained: GEMM1(c+2) may start
         }
-        o[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      }
-      mbar_wait(&h_free[ab], aph ^ 1);                   // GEMM2(c-2) has consumed this buffer
-      uint8_t* hb = smem + OFF_H + ab * H_BYTES + (grp >> 1) * 16384;
+        const uint4* bsm = reinterpret_cast<const uint4*>(bias_h + c * HC + half * 64 + hh * 32);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(hb + sw128_off(r, (grp & 1) * 4 + i)) = o[i];
+        for (int i = 0; i < 4; ++i) {
+          const uint4 b4 = bsm[i];
+          const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __half2 x = __floats2half2_rn(__uint_as_float(v[8 * i + 2 * j]), __uint_as_float(v[8 * i + 2 * j + 1]));
+            x = __hadd2(x, *reinterpret_cast<const __half2*>(&bw[j]));
+            ow[j] = h2_to_bf2_bits(gelu_h2(x));
+          }
+          o[hh * 4 + i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+      }
+      if ((ew & 7) == 0) MLP_TRACE(2, c);
+      mbar_wait(&h_free[ab], aph ^ 1);                   // GEMM2(c-2) has consumed this buffer
+      if ((ew & 7) == 0) MLP_TRACE(3, c);
+      uint8_t* hb = smem + OFF_H + ab * H_BYTES + half * 16384;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(hb + sw128_off(r, i)) = o[i];
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&h_ready[ab]);
+      if ((ew & 7) == 0) MLP_TRACE(4, c);
     }
-    // ---- output: y + b2 + residual  (16 columns per warp)
+    // ---- output: y + b2 + residual  (16 columns per warp); the residual loads overlap the last GEMM2
+    const int row = row0 + lane;
+    float4 r4[4], b4[4];
+    if (row < a.M) {
+      const float* R = a.resid + (int64_t)row * a.ldr + grp * 16;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { r4[i] = reinterpret_cast<const float4*>(R)[i]; b4[i] = __ldg(reinterpret_cast<const float4*>(a.b2 + grp * 16) + i); }
+    }
+    if (warp == 2) MLP_TRACE(12, 4);
     mbar_wait(y_full, 0);
+    if (warp == 2) MLP_TRACE(12, 5);
     tc_fence_after();
     float y[16];
     tmem_ld16(tmem_base + 256 + grp * 16 + lane_off, y);
-    const int row = row0 + lane;
     if (row < a.M) {
-      const float* R = a.resid + (int64_t)row * a.ldr + grp * 16;
       float* O = a.out + (int64_t)row * a.ldc + grp * 16;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b2 + grp * 16) + i);
-        const float4 r4 = reinterpret_cast<const float4*>(R)[i];
-        reinterpret_cast<float4*>(O)[i] = make_float4(y[4 * i] + b4.x + r4.x, y[4 * i + 1] + b4.y + r4.y,
-                                                      y[4 * i + 2] + b4.z + r4.z, y[4 * i + 3] + b4.w + r4.w);
-      }
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<float4*>(O)[i] = make_float4(y[4 * i] + b4[i].x + r4[i].x, y[4 * i + 1] + b4[i].y + r4[i].y,
+                                                      y[4 * i + 2] + b4[i].z + r4[i].z, y[4 * i + 3] + b4[i].w + r4[i].w);
     }
   }
+  if (warp == 2) MLP_TRACE(12, 6);
   tc_fence_before();
   __syncthreads();
+  if (warp == 2) MLP_TRACE(12, 7);
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
@@ -379,7 +419,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   // (X, dY) and (W1c, W2c) are adjacent 16 KB tiles; the streamed pair advances by 2*TILE16 per stage
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       auto load_tok = [&](uint8_t* dst, uint64_t* bar, int t) {   // X tile | dY tile, rows t*128..
         tma_load_2d(dst, &tmX, bar, 0, t * 128);
         tma_load_2d(dst + TILE16, &tmDY, bar, 0, t * 128);
@@ -400,7 +440,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t id_hpre = make_idesc(128, HC, false, false);                       // X (K) x W1c (K)
       constexpr uint32_t id_dg = make_idesc(128, HC, false, true);                          // dY (K) x W2c (MN)
       constexpr uint32_t id_dx = make_idesc(128, 64, false, true);                          // dH (K) x W1c (MN)
@@ -557,6 +597,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 // ------------------------------------------------------------------ host
+static long long* g_trace = nullptr;   // device buffer for DGVIT_MLP_TRACE builds (dgvit_set_option_ptr)
 static bool eligible(int D, int HID, int64_t M, const void* x, const void* w1, const void* w2, const float* resid,
                      int64_t ldr, const float* out, int64_t ldc) {
   return tc::g_tc_enabled && D == 64 && HID % HC == 0 && HID <= MAX_HID && M >= 1 && ((uintptr_t)x & 15) == 0 &&
@@ -567,6 +608,7 @@ static bool eligible(int D, int HID, int64_t M, const void* x, const void* w1, c
 static void fwd(const bf16* x, const bf16* W1, const float* b1, const bf16* W2, const float* b2, const float* resid,
                 int64_t ldr, float* out, int64_t ldc, int64_t M, int HID, cudaStream_t st) {
   MlpArgs a;
+  a.trace = g_trace;
   a.M = (int)M; a.HID = HID; a.b1 = b1; a.b2 = b2; a.resid = resid; a.ldr = ldr; a.out = out; a.ldc = ldc;
   CUtensorMap tx = make_map(x, 64, M, 64, 64, 128);
   CUtensorMap tw1 = make_map(W1, 64, HID, 64, 64, 128);
