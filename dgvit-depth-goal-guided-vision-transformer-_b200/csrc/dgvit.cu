@@ -164,7 +164,7 @@ static void linear_bwd_w(const TA* dy, const TB* x, float* dW, float* db, int64_
     dim3 grid((unsigned)cdiv(N, 256), (unsigned)S);
     launch_k(colsum_partial_kernel<TA>, grid, 128, 0, st, dy, ldy, partial, R, N, rpb);
     DG_LAUNCH_CHECK();
-    launch_k(reduce_partials_kernel, (unsigned)cdiv(N, 256), 256, 0, st, partial, db, S, N);
+    launch_k(reduce_partials_kernel, reduce_grid(N), 256, 0, st, partial, db, S, N);
     DG_LAUNCH_CHECK();
   }
 }
@@ -249,7 +249,7 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
     mx = std::max<int64_t>(mx, (int64_t)3 * d.inner * d.D);
     mx = std::max<int64_t>(mx, (int64_t)d.D * d.pd);
     mx = std::max<int64_t>(mx, (int64_t)128 * 128);
-    mx = std::max<int64_t>(mx, (int64_t)2 * d.D * 148 * 4 / 32 + 2 * d.D);
+    mx = std::max<int64_t>(mx, (int64_t)3 * d.D * 148 * 4 / 32 + 3 * d.D);
     c.partial_floats = (size_t)mx * 32;
     c.partial = cv.take<float>(c.partial_floats);
   }
@@ -282,12 +282,13 @@ static void launch_ln_fwd(const float* X, const float* g, const float* b, A* Y, 
   }
   DG_LAUNCH_CHECK();
 }
+// dxsum (optional): receives colsum over rows of the updated dX_io (a bias gradient, see layernorm_bwd_kernel)
 static void launch_ln_bwd(const float* dY, const float* X, const float* mean, const float* rstd,
-                          const float* gamma, float* dX_io, bf16* dX_lp, float* dgamma, float* dbeta,
+                          const float* gamma, float* dX_io, bf16* dX_lp, float* dgamma, float* dbeta, float* dxsum,
                           float* partial, int64_t T, int D, cudaStream_t st) {
   const int wpb = 8;
   int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 4);
-  const size_t smem = (size_t)wpb * 2 * D * sizeof(float);
+  const size_t smem = (size_t)wpb * 3 * D * sizeof(float);
   switch (D / 32) {
 #define LNB(V) case V: launch_k(layernorm_bwd_kernel<V>, nblocks, wpb * 32, smem, st, dY, X, mean, rstd, gamma, dX_io, dX_lp, partial, T); break;
     LNB(1) LNB(2) LNB(3) LNB(4) LNB(5) LNB(6) LNB(7) LNB(8)
@@ -295,7 +296,7 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
     default: fail(DGVIT_ERR_ARG, "unsupported dim %d", D);
   }
   DG_LAUNCH_CHECK();
-  launch_k(ln_param_reduce_kernel, (unsigned)cdiv(2 * D, 32), 1024, 0, st, partial, dgamma, dbeta, nblocks, D);
+  launch_k(ln_param_reduce_kernel, (unsigned)cdiv(3 * D, 32), 1024, 0, st, partial, dgamma, dbeta, dxsum, nblocks, D);
   DG_LAUNCH_CHECK();
 }
 
@@ -454,8 +455,9 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
         // the fused forward saved nothing: both backward launches recompute the pre-activation on chip
         DG_REQUIRE(mlp::bwd_partial_floats(R, d.M) <= c.partial_floats, "mlp::bwd partial buffer too small");
         ProfScope ps(PROF_GEMM_MLP, 8.0 * R * d.D * d.M, 0.0, st);
+        // net.3.bias gradient = colsum(dL/dX_out): below the top block it falls out of the next block's LayerNorm-1 backward
         mlp::bwd(B_.Xn2, dxop, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), c.dXn, G + b.fc1_w,
-                 G + b.fc1_b, G + b.fc2_w, G + b.fc2_b, c.partial, R, d.M, st);
+                 G + b.fc1_b, G + b.fc2_w, last ? G + b.fc2_b : nullptr, c.partial, R, d.M, st);
       }
     }
 #else
@@ -469,20 +471,21 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
       g.C = c.dH; g.ldc = d.M;
       g.epi = EPI_GELU_BWD; g.aux = B_.Hpre; g.ldaux = d.M;
       gemm<A, A, A>(g, st);
-      linear_bwd_w<A, A>(dxop, B_.Hact, G + b.fc2_w, G + b.fc2_b, R, d.D, d.M, c.partial, st);
+      linear_bwd_w<A, A>(dxop, B_.Hact, G + b.fc2_w, last ? G + b.fc2_b : nullptr, R, d.D, d.M, c.partial, st);
       linear_bwd_w<A, A>(c.dH, B_.Xn2, G + b.fc1_w, G + b.fc1_b, R, d.M, d.D, c.partial, st);
       linear_bwd_x<A, A, float>(c.dH, WSel<A>::w(net, b.fc1_w), c.dXn, R, d.M, d.D, EPI_NONE, nullptr, 0, st);
     }
     }
-    launch_ln_bwd(c.dXn, B_.Xm, B_.mean2, B_.rstd2, P + b.ln2_w, dXr, dXr_lp, G + b.ln2_w, G + b.ln2_b, c.partial, R,
-                  d.D, st);
+    // dXr becomes dL/dX_m, whose column sums are the to_out.0.bias gradient
+    launch_ln_bwd(c.dXn, B_.Xm, B_.mean2, B_.rstd2, P + b.ln2_w, dXr, dXr_lp, G + b.ln2_w, G + b.ln2_b, G + b.out_b,
+                  c.partial, R, d.D, st);
     // ---- attention block.  dXr = dL/dX_m
     if (!last) {
-      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, G + b.out_b, d.T, d.D, d.inner, c.partial, st);
+      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, nullptr, d.T, d.D, d.inner, c.partial, st);
       linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.out_w), c.dO, d.T, d.D, d.inner, EPI_NONE, nullptr, 0, st);
     } else {
       const int64_t ostride = (int64_t)d.N * d.inner;
-      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, G + b.out_b, d.B, d.D, d.inner, c.partial, st, -1, ostride);
+      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, nullptr, d.B, d.D, d.inner, c.partial, st, -1, ostride);
       // dO is zero except on the token-0 rows
       DG_CUDA(cudaMemsetAsync(c.dO, 0, (size_t)d.T * d.inner * sizeof(A), st));
       linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.out_w), c.dO, d.B, d.D, d.inner, EPI_NONE, nullptr, 0, st, -1,
@@ -495,8 +498,9 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     launch_attention_bwd<A>(B_.QKV, B_.O, c.dO, c.dQKV, d, st);
     linear_bwd_w<A, A>(c.dQKV, B_.Xn1, G + b.qkv_w, nullptr, d.T, 3 * d.inner, d.D, c.partial, st);
     linear_bwd_x<A, A, float>(c.dQKV, WSel<A>::w(net, b.qkv_w), c.dXn, d.T, 3 * d.inner, d.D, EPI_NONE, nullptr, 0, st);
-    launch_ln_bwd(c.dXn, B_.Xa, B_.mean1, B_.rstd1, P + b.ln1_w, c.dX, c.dXh, G + b.ln1_w, G + b.ln1_b, c.partial,
-                  d.T, d.D, st);
+    // c.dX becomes dL/dX_a = gradient of the previous block's output: its column sums are that block's net.3.bias gradient
+    launch_ln_bwd(c.dXn, B_.Xa, B_.mean1, B_.rstd1, P + b.ln1_w, c.dX, c.dXh, G + b.ln1_w, G + b.ln1_b,
+                  l > 0 ? G + L.block[l - 1].fc2_b : nullptr, c.partial, d.T, d.D, st);
   }
   // ---- embedding.  c.dX = dL/dX0 (post-dropout)
   const int64_t tot = d.T * d.D;
@@ -507,7 +511,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     launch_k(dpos_kernel, dim3(d.N, S), 128, 0, st, c.dX, c.partial, drop, d.B, d.N, d.D);
     DG_LAUNCH_CHECK();
     const int64_t n = (int64_t)d.N * d.D;
-    launch_k(reduce_partials_kernel, (unsigned)cdiv(n, 256), 256, 0, st, c.partial, G + L.pos, S, n);
+    launch_k(reduce_partials_kernel, reduce_grid(n), 256, 0, st, c.partial, G + L.pos, S, n);
     DG_LAUNCH_CHECK();
   }
   linear_bwd_w<A, A>(c.dXp, c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st);

@@ -148,16 +148,38 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
 }
 
 // out[i] = sum_s partial[s, i]   (fixed order: deterministic)
+// out[i] = sum_k partial[k][i], k ascending (fixed order).  Four elements per thread, the split loop unrolled so
+// that eight independent 16-byte loads are in flight (the kernel is pure load latency otherwise).
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                        int S, int64_t n) {
   pdl_wait();
   pdl_launch();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
-  float s = 0.f;
-  for (int k = 0; k < S; ++k) s += partial[(int64_t)k * n + i];
-  out[i] = s;
+  if (i + 3 < n && (n & 3) == 0 && ((((uintptr_t)partial) | ((uintptr_t)out)) & 15) == 0) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = 0;
+    for (; k + 8 <= S; k += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(partial + (int64_t)(k + u) * n + i));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; k < S; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (int64_t)k * n + i));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + i) = s;
+  } else {
+    for (int64_t e = i; e < min(n, i + 4); ++e) {
+      float s = 0.f;
+      for (int k = 0; k < S; ++k) s += partial[(int64_t)k * n + e];
+      out[e] = s;
+    }
+  }
 }
+static inline unsigned reduce_grid(int64_t n) { return (unsigned)cdiv(cdiv(n, 4), 256); }
 
 template <typename TA, typename TB, typename TC>
 static void gemm_simt(const GemmArgs& g, cudaStream_t st) {
@@ -170,7 +192,7 @@ static void gemm_simt(const GemmArgs& g, cudaStream_t st) {
   if (g.splitk > 1) {
     DG_REQUIRE(g.ldc == g.N, "gemm_simt: split-K output must be dense");
     const int64_t n = (int64_t)g.M * g.N;
-    launch_k(reduce_partials_kernel, (unsigned)cdiv(n, 256), 256, 0, st, g.partial, (float*)g.C, g.splitk, n);
+    launch_k(reduce_partials_kernel, reduce_grid(n), 256, 0, st, g.partial, (float*)g.C, g.splitk, n);
     DG_LAUNCH_CHECK();
   }
 }

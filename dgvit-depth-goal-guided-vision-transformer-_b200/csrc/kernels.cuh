@@ -137,7 +137,9 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ X, const float* _
   if (lane == 0 && mean) { mean[row] = mu; rstd[row] = rs; }
 }
 
-// dX_io[row] += LN'(dY[row]); per-block partial sums of dgamma/dbeta -> part[block][2][D]
+// dX_io[row] += LN'(dY[row]); per-block partial sums of dgamma / dbeta / column sums of the updated dX_io
+// -> part[block][3][D].  The third vector is the bias gradient of the linear layer that produced this residual
+// stream (to_out.0.bias / net.3.bias): colsum(dL/dX) in fp32, for free instead of a separate pass over dX.
 template <int VPL>
 __global__ void layernorm_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ X,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -146,11 +148,11 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dY, const float* 
   pdl_wait();
   pdl_launch();
   constexpr int D = 32 * VPL;
-  extern __shared__ float sm[];  // [warps][2][D]
+  extern __shared__ float sm[];  // [warps][3][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float dg[VPL], db[VPL], gm[VPL];
+  float dg[VPL], db[VPL], dxs[VPL], gm[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) { dg[i] = 0.f; db[i] = 0.f; gm[i] = gamma[lane + 32 * i]; }
+  for (int i = 0; i < VPL; ++i) { dg[i] = 0.f; db[i] = 0.f; dxs[i] = 0.f; gm[i] = gamma[lane + 32 * i]; }
   for (int64_t row = (int64_t)blockIdx.x * nw + warp; row < T; row += (int64_t)gridDim.x * nw) {
     const float mu = mean[row], rs = rstd[row];
     float xh[VPL], dy[VPL];
@@ -173,48 +175,53 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dY, const float* 
       const int d = lane + 32 * i;
       const float nv = dX_io[row * D + d] + rs * (dy[i] * gm[i] - s1 - xh[i] * s2);
       dX_io[row * D + d] = nv;
+      dxs[i] += nv;
       if (dX_lp) dX_lp[row * D + d] = __float2bfloat16_rn(nv);
     }
   }
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    sm[(warp * 2 + 0) * D + lane + 32 * i] = dg[i];
-    sm[(warp * 2 + 1) * D + lane + 32 * i] = db[i];
+    sm[(warp * 3 + 0) * D + lane + 32 * i] = dg[i];
+    sm[(warp * 3 + 1) * D + lane + 32 * i] = db[i];
+    sm[(warp * 3 + 2) * D + lane + 32 * i] = dxs[i];
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < 2 * D; j += blockDim.x) {
+  for (int j = threadIdx.x; j < 3 * D; j += blockDim.x) {
     float s = 0.f;
-    for (int w = 0; w < nw; ++w) s += sm[w * 2 * D + j];
-    part[(int64_t)blockIdx.x * 2 * D + j] = s;
+    for (int w = 0; w < nw; ++w) s += sm[w * 3 * D + j];
+    part[(int64_t)blockIdx.x * 3 * D + j] = s;
   }
 }
 
-// dgamma[d] = sum_blocks part[b][0][d], dbeta[d] = sum_blocks part[b][1][d]
+// dgamma[d] = sum_blocks part[b][0][d], dbeta[d] = sum_blocks part[b][1][d], dxsum[d] = sum_blocks part[b][2][d]
 // block = 32 columns x 32 row-groups (1024 threads); fixed summation order (deterministic)
 __global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* __restrict__ part,
                                                                float* __restrict__ dgamma,
-                                                               float* __restrict__ dbeta, int nblocks, int D) {
+                                                               float* __restrict__ dbeta,
+                                                               float* __restrict__ dxsum, int nblocks, int D) {
   pdl_wait();
   pdl_launch();
   __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + cx;
   float s0 = 0.f, s1 = 0.f;
-  if (j < 2 * D) {
+  if (j < 3 * D) {
     int b = gy;
     for (; b + 32 < nblocks; b += 64) {
-      s0 += part[(int64_t)b * 2 * D + j];
-      s1 += part[(int64_t)(b + 32) * 2 * D + j];
+      s0 += part[(int64_t)b * 3 * D + j];
+      s1 += part[(int64_t)(b + 32) * 3 * D + j];
     }
-    if (b < nblocks) s0 += part[(int64_t)b * 2 * D + j];
+    if (b < nblocks) s0 += part[(int64_t)b * 3 * D + j];
   }
   sm[gy][cx] = s0 + s1;
   __syncthreads();
-  if (gy == 0 && j < 2 * D) {
+  if (gy == 0 && j < 3 * D) {
     float t = 0.f;
 #pragma unroll
     for (int g = 0; g < 32; ++g) t += sm[g][cx];
-    if (j < D) dgamma[j] = t; else dbeta[j - D] = t;
+    if (j < D) dgamma[j] = t;
+    else if (j < 2 * D) dbeta[j - D] = t;
+    else if (dxsum) dxsum[j - 2 * D] = t;
   }
 }
 

@@ -22,10 +22,13 @@
 // [tokens x 2048] tensors G / dH never exist in HBM.  One smem image serves as K-major operand of
 // one GEMM and MN-major operand of another (same trick as attn_tc.cuh).
 //
-// The GELU epilogue is the bound of all three kernels (issue slots + MUFU), so it runs in packed
-// f16x2: x(a + b x^2) -> MUFU.TANH -> 0.5x(1+t), constants fitted to the exact erf GELU
-// (|err| <= 2.7e-4; the f16 pipeline's rms error is 4x below that of rounding the exact GELU to bf16).
-// tcgen05 kind::f16 rejects mixed f16 / bf16 operands (illegal instruction), so the result is re-packed to bf16.
+// The GELU epilogue is the bound of all three kernels (MUFU + FMA pipe + issue slots), so it uses the cheapest
+// form that stays below bf16 resolution: 0.5x(1 + tanh(x(a + b x^2))) with one MUFU.TANH per element and a, b
+// fitted to the exact erf GELU (|err| <= 2.7e-4), evaluated in packed f16x2 (the f16 pipeline's rms error is 4x
+// below that of rounding the exact GELU to bf16).  Measured on B200: MUFU.TANH is 16 results/clk/SM in every
+// variant and HFMA2 issues at half the FFMA rate (profiles/micro/mufu_rate.cu), yet the same epilogue written in
+// fp32 runs 10-13 % slower end to end (general three-register FFMAs do not sustain the full rate), so f16x2 stays.
+// tcgen05 kind::f16 rejects mixed f16 / bf16 operands (illegal instruction): the result is re-packed to bf16.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -43,7 +46,7 @@ constexpr int HC = 128;            // hidden chunk (columns of GEMM1 / K of GEMM
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int TILE16 = 16384;      // [128 rows][64 x 16-bit] swizzled tile
-constexpr int MAX_HID = 4096;      // f16 bias copy in smem
+constexpr int MAX_HID = 4096;      // bias copy in smem
 
 constexpr float GELU_A = 0.80015708f, GELU_B = 0.03470089f;
 
@@ -59,13 +62,11 @@ __device__ __forceinline__ __half2 h2_tanh(__half2 x) {
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a));
   return *reinterpret_cast<__half2*>(&r);
 }
-__device__ __forceinline__ uint32_t h2_bits(__half2 x) { return *reinterpret_cast<const uint32_t*>(&x); }
 __device__ __forceinline__ uint32_t h2_to_bf2_bits(__half2 x) {
   const float2 f = __half22float2(x);
   const __nv_bfloat162 p = __floats2bfloat162_rn(f.x, f.y);
   return *reinterpret_cast<const uint32_t*>(&p);
 }
-
 __device__ __forceinline__ __half2 gelu_h2(__half2 x) {
   const __half2 A = __float2half2_rn(GELU_A), B = __float2half2_rn(GELU_B), hf = __float2half2_rn(0.5f);
   const __half2 x2 = __hmul2(x, x);
@@ -85,6 +86,10 @@ __device__ __forceinline__ void gelu_grad_h2(__half2 x, __half2& g, __half2& d) 
   const __half2 s = __hfma2(__hneg2(t), t, one);
   d = __hfma2(__hmul2(hx, s), q, __hfma2(t, hf, hf));
 }
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+  const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
 
 // 32 lanes x 32 columns, no wait (pair with tmem_wait_ld)
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
@@ -103,7 +108,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
 // fp32 bias -> f16 copy in shared memory (epilogue threads only), then a barrier among them
-__device__ __forceinline__ void stage_bias_f16(const float* b, __half* dst, int n, int tid) {
+__device__ __forceinline__ void stage_bias(const float* b, __half* dst, int n, int tid) {
   for (int i = tid * 2; i < n; i += EPI_WARPS * 32 * 2)
     *reinterpret_cast<__half2*>(dst + i) = __floats2half2_rn(__ldg(b + i), __ldg(b + i + 1));
   epi_bar_sync();
@@ -157,7 +162,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* h_free = h_ready + 2;          // 2
   uint64_t* y_full = h_free + 2;           // 1
   uint32_t* tmem_slot = (uint32_t*)(y_full + 1);
-  __half* bias_h = (__half*)(smem + OFF_BIAS);
+  __half* bias_s = (__half*)(smem + OFF_BIAS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x;
@@ -255,7 +260,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int r = quad * 32 + lane;
     const int row0 = mt * 128 + quad * 32;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    stage_bias_f16(a.b1, bias_h, a.HID, threadIdx.x - 64);
+    stage_bias(a.b1, bias_s, a.HID, threadIdx.x - 64);
     if (warp == 2) MLP_TRACE(12, 3);
     for (int c = pg; c < NC; c += 2) {
       const int ab = pg; const uint32_t aph = (c >> 1) & 1;
@@ -263,7 +268,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_wait(&acc_full[ab], aph);
       if ((ew & 7) == 0) MLP_TRACE(1, c);
       tc_fence_after();
-      uint4 o[8];
+      mbar_wait(&h_free[ab], aph ^ 1);                   // GEMM2(c-2) has consumed this H buffer (long ago)
+      uint8_t* hb = smem + OFF_H + ab * H_BYTES + half * 16384;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t v[32];
@@ -274,7 +280,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_free[ab]);      // TMEM chunk drained: GEMM1(c+2) may start
         }
-        const uint4* bsm = reinterpret_cast<const uint4*>(bias_h + c * HC + half * 64 + hh * 32);
+        const uint4* bsm = reinterpret_cast<const uint4*>(bias_s + c * HC + half * 64 + hh * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint4 b4 = bsm[i];
@@ -286,15 +292,10 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             x = __hadd2(x, *reinterpret_cast<const __half2*>(&bw[j]));
             ow[j] = h2_to_bf2_bits(gelu_h2(x));
           }
-          o[hh * 4 + i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          *reinterpret_cast<uint4*>(hb + sw128_off(r, hh * 4 + i)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
       if ((ew & 7) == 0) MLP_TRACE(2, c);
-      mbar_wait(&h_free[ab], aph ^ 1);                   // GEMM2(c-2) has consumed this buffer
-      if ((ew & 7) == 0) MLP_TRACE(3, c);
-      uint8_t* hb = smem + OFF_H + ab * H_BYTES + half * 16384;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(hb + sw128_off(r, i)) = o[i];
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&h_ready[ab]);
@@ -379,7 +380,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* h_free = h_ready + 1;           // 1: the MMAs reading the tiles have retired
   uint64_t* out_full = h_free + 1;          // 1
   uint32_t* tmem_slot = (uint32_t*)(out_full + 1);
-  __half* bias_h = (__half*)(smem + OFF_BIAS);
+  __half* bias_s = (__half*)(smem + OFF_BIAS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NC = a.HID / HC;
@@ -506,7 +507,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int quad = warp & 3, grp = ew >> 2;            // rows quad*32.., hidden columns grp*32.. of the chunk
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    stage_bias_f16(a.b1, bias_h, a.HID, threadIdx.x - 64);
+    stage_bias(a.b1, bias_s, a.HID, threadIdx.x - 64);
     for (int i = 0; i < nsteps; ++i) {
       const int c = (MODE == 0) ? c0 + i : c0;
       mbar_wait(acc_full, (uint32_t)(i & 1));
@@ -518,7 +519,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_free);               // TMEM drained: the next step's Hpre / dG MMAs may start
-      const uint4* bsm = reinterpret_cast<const uint4*>(bias_h + c * HC + grp * 32);
+      const uint4* bsm = reinterpret_cast<const uint4*>(bias_s + c * HC + grp * 32);
       uint4 odh[4], og[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -532,9 +533,8 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           x = __hadd2(x, *reinterpret_cast<const __half2*>(&bw[j]));
           __half2 g, d;
           gelu_grad_h2(x, g, d);
-          const float2 df = __half22float2(d);
-          const __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(gv[e]) * df.x, __uint_as_float(gv[e + 1]) * df.y);
-          wd[j] = *reinterpret_cast<const uint32_t*>(&p);
+          const float2 df = __half22float2(d);       // dG stays fp32: gradients underflow f16
+          wd[j] = pack_bf2(__uint_as_float(gv[e]) * df.x, __uint_as_float(gv[e + 1]) * df.y);
           wg[j] = h2_to_bf2_bits(g);
         }
         odh[q] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
@@ -635,7 +635,7 @@ static size_t bwd_partial_floats(int64_t M, int HID) {
   return (size_t)bwd_splits(M, HID) * ((size_t)HID * 64 * 2 + HID) + (size_t)cdiv(M, 128) * 64;
 }
 
-// dXn[M,64] = d/dx ; dW1 [HID,64], db1 [HID], dW2 [64,HID], db2 [64] (fp32, overwritten).
+// dXn[M,64] = d/dx ; dW1 [HID,64], db1 [HID], dW2 [64,HID], db2 [64] (fp32, overwritten; db2 may be null = not wanted).
 // dW1 / db1 / dW2 must be adjacent in that order (the parameter arena's order) so that one pass reduces all three.
 static void bwd(const bf16* x, const bf16* dy, const bf16* W1, const float* b1, const bf16* W2, float* dXn, float* dW1,
                 float* db1, float* dW2, float* db2, float* partial, int64_t M, int HID, cudaStream_t st) {
@@ -648,7 +648,7 @@ static void bwd(const bf16* x, const bf16* dy, const bf16* W1, const float* b1, 
   a.dX = dXn; a.lddx = 64;
   a.dW1_part = partial; a.db1_part = partial + (int64_t)HID * 64; a.dW2_part = a.db1_part + HID;
   a.split_stride = per_split;
-  a.db2_part = partial + (int64_t)S * per_split;
+  a.db2_part = db2 ? partial + (int64_t)S * per_split : nullptr;
   CUtensorMap tx = make_map(x, 64, M, 64, 64, 128);
   CUtensorMap tdy = make_map(dy, 64, M, 64, 64, 128);
   CUtensorMap tw1 = make_map(W1, 64, HID, 64, 64, 128);
@@ -663,10 +663,12 @@ static void bwd(const bf16* x, const bf16* dy, const bf16* W1, const float* b1, 
   DG_LAUNCH_CHECK();
   launch_k(mlp_bwd_tc_kernel<1>, NC * S, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
   DG_LAUNCH_CHECK();
-  launch_k(reduce_partials_kernel, (unsigned)cdiv(per_split, 256), 256, 0, st, (const float*)partial, dW1, S, per_split);
+  launch_k(reduce_partials_kernel, reduce_grid(per_split), 256, 0, st, (const float*)partial, dW1, S, per_split);
   DG_LAUNCH_CHECK();
-  launch_k(reduce_partials_kernel, 1, 64, 0, st, (const float*)a.db2_part, db2, tiles, (int64_t)64);
-  DG_LAUNCH_CHECK();
+  if (db2) {
+    launch_k(reduce_partials_kernel, 1, 64, 0, st, (const float*)a.db2_part, db2, tiles, (int64_t)64);
+    DG_LAUNCH_CHECK();
+  }
 }
 
 }  // namespace mlp
