@@ -37,6 +37,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // byte offset of 16-byte chunk `chunk` (8 bf16) of row `r` inside a [128][64]-bf16 128B-swizzled tile
@@ -65,6 +78,7 @@ struct AttnArgs {
 // forward
 // =====================================================================================
 // smem stage: Q [128x64] | K [128x64 (KPAD rows used)] | V | P block0 | P block1  = 5 tiles
+template <int NK>   // NK = KPAD / 16: key blocks held in registers by the softmax
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -168,28 +182,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&s_full[st], ph);
       tc_fence_after();
       const uint32_t ts = tmem_base + st * TCOLS_STAGE + lane_off;
+      // the whole score row in registers: one TMEM round trip, one exp per element
+      uint32_t sr[NK][16];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) tmem_ld16_nowait(ts + 16 * k, sr[k]);
+      tmem_ld_wait();
       float mx = -INFINITY;
-      for (int c = 0; c < a.KPAD; c += 16) {
-        float v[16];
-        tmem_ld16(ts + c, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (c + i < a.N) mx = fmaxf(mx, v[i]);
-      }
+      for (int k = 0; k < NK; ++k)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (16 * k + i < a.N) mx = fmaxf(mx, __uint_as_float(sr[k][i]));
+      const float mb = mx * sl2;
       float sum = 0.f;
-      for (int c = 0; c < a.KPAD; c += 16) {
-        float v[16];
-        tmem_ld16(ts + c, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float e = (c + i < a.N) ? exp2f((v[i] - mx) * sl2) : 0.f;
+      for (int k = 0; k < NK; ++k) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c0 = 16 * k + 2 * i;
+          const float e0 = (c0 < a.N) ? ex2_approx(fmaf(__uint_as_float(sr[k][2 * i]), sl2, -mb)) : 0.f;
+          const float e1 = (c0 + 1 < a.N) ? ex2_approx(fmaf(__uint_as_float(sr[k][2 * i + 1]), sl2, -mb)) : 0.f;
+          w[i] = pack2(e0, e1);
           // the tensor core sees the bf16-rounded value: sum what it sees
-          v[i] = __bfloat162float(__float2bfloat16_rn(e));
-          sum += v[i];
+          sum += __uint_as_float(w[i] << 16) + __uint_as_float(w[i] & 0xffff0000u);
         }
-        uint8_t* blk = P + (c >> 6) * TILE;
-        const int ch = (c & 63) >> 3;
-        *reinterpret_cast<uint4*>(blk + sw128_off(r, ch)) = pack8(v);
-        *reinterpret_cast<uint4*>(blk + sw128_off(r, ch + 1)) = pack8(v + 8);
+        uint8_t* blk = P + (k >> 2) * TILE;
+        const int ch = (k & 3) * 2;
+        *reinterpret_cast<uint4*>(blk + sw128_off(r, ch)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(blk + sw128_off(r, ch + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
       }
       fence_async_smem();
       __syncwarp();
@@ -200,15 +220,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       {
         // tcgen05.ld is warp-aligned: every lane loads, only rows inside the sequence store
         bf16* dst = a.O + ((int64_t)b * a.N + r) * inner + h * DH;
+        uint32_t orr[4][16];
 #pragma unroll
-        for (int c = 0; c < DH; c += 16) {
-          float v[16];
-          tmem_ld16(ts + 128 + c, v);
+        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(ts + 128 + 16 * c, orr[c]);
+        tmem_ld_wait();
+        if (r < a.N) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= inv;
-          if (r < a.N) {
-            reinterpret_cast<uint4*>(dst + c)[0] = pack8(v);
-            reinterpret_cast<uint4*>(dst + c)[1] = pack8(v + 8);
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = pack2(__uint_as_float(orr[c][2 * i]) * inv, __uint_as_float(orr[c][2 * i + 1]) * inv);
+            reinterpret_cast<uint4*>(dst + 16 * c)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4*>(dst + 16 * c)[1] = make_uint4(w[4], w[5], w[6], w[7]);
           }
         }
       }
@@ -230,6 +253,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 constexpr int BWD_LOAD_STAGES = 2;
 constexpr int BWD_THREADS = 64 + 128;
 
+template <int NK>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmdO, const AttnArgs a) {
@@ -356,38 +380,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(sdp_full, iph);
       tc_fence_after();
       const uint32_t ts = tmem_base + lane_off;
+      // S row in registers (one exp per element); dP streamed 16 columns at a time
+      uint32_t sr[NK][16];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) tmem_ld16_nowait(ts + 16 * k, sr[k]);
+      tmem_ld_wait();
       float mx = -INFINITY;
-      for (int c = 0; c < a.KPAD; c += 16) {
-        float v[16];
-        tmem_ld16(ts + c, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (c + i < a.N) mx = fmaxf(mx, v[i]);
-      }
+      for (int k = 0; k < NK; ++k)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (16 * k + i < a.N) mx = fmaxf(mx, __uint_as_float(sr[k][i]));
+      const float mb = mx * sl2;
       float sum = 0.f;
-      for (int c = 0; c < a.KPAD; c += 16) {
-        float v[16];
-        tmem_ld16(ts + c, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (c + i < a.N) sum += exp2f((v[i] - mx) * sl2);
-      }
-      const float inv = 1.0f / sum;
-      for (int c = 0; c < a.KPAD; c += 16) {
-        float s[16], dp[16], p[16], ds[16];
-        tmem_ld16(ts + c, s);
-        tmem_ld16(ts + 128 + c, dp);
+      for (int k = 0; k < NK; ++k)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const bool ok = valid && (c + i < a.N);
-          p[i] = ok ? exp2f((s[i] - mx) * sl2) * inv : 0.f;
-          ds[i] = ok ? p[i] * (dp[i] - delta) * a.scale : 0.f;
+          const float e = (valid && 16 * k + i < a.N) ? ex2_approx(fmaf(__uint_as_float(sr[k][i]), sl2, -mb)) : 0.f;
+          sr[k][i] = __float_as_uint(e);
+          sum += e;
         }
-        const int ch = (c & 63) >> 3;
-        uint8_t* pb = Pt + (c >> 6) * TILE;
-        uint8_t* db = dSt + (c >> 6) * TILE;
-        *reinterpret_cast<uint4*>(pb + sw128_off(r, ch)) = pack8(p);
-        *reinterpret_cast<uint4*>(pb + sw128_off(r, ch + 1)) = pack8(p + 8);
-        *reinterpret_cast<uint4*>(db + sw128_off(r, ch)) = pack8(ds);
-        *reinterpret_cast<uint4*>(db + sw128_off(r, ch + 1)) = pack8(ds + 8);
+      const float inv = valid ? 1.0f / sum : 0.f;
+      const float nds = -delta;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        uint32_t dpr[16];
+        tmem_ld16_nowait(ts + 128 + 16 * k, dpr);
+        tmem_ld_wait();
+        uint32_t wp[8], wd[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float p0 = __uint_as_float(sr[k][2 * i]) * inv, p1 = __uint_as_float(sr[k][2 * i + 1]) * inv;
+          const float d0 = p0 * (__uint_as_float(dpr[2 * i]) + nds) * a.scale, d1 = p1 * (__uint_as_float(dpr[2 * i + 1]) + nds) * a.scale;
+          wp[i] = pack2(p0, p1);
+          wd[i] = pack2(d0, d1);
+        }
+        const int ch = (k & 3) * 2;
+        uint8_t* pb = Pt + (k >> 2) * TILE;
+        uint8_t* db = dSt + (k >> 2) * TILE;
+        *reinterpret_cast<uint4*>(pb + sw128_off(r, ch)) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+        *reinterpret_cast<uint4*>(pb + sw128_off(r, ch + 1)) = make_uint4(wp[4], wp[5], wp[6], wp[7]);
+        *reinterpret_cast<uint4*>(db + sw128_off(r, ch)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        *reinterpret_cast<uint4*>(db + sw128_off(r, ch + 1)) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
       }
       fence_async_smem();
       __syncwarp();
@@ -397,13 +431,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       bf16* dst = a.dQKV + ((int64_t)b * a.N + r) * (3 * inner) + h * DH;
 #pragma unroll 1
       for (int w = 0; w < 3; ++w) {          // dQ, dK, dV rows (query r / key r)
+        uint32_t orr[4][16];
 #pragma unroll
-        for (int c = 0; c < DH; c += 16) {
-          float v[16];
-          tmem_ld16(ts + 256 + w * 64 + c, v);
-          if (valid) {
-            reinterpret_cast<uint4*>(dst + w * inner + c)[0] = pack8(v);
-            reinterpret_cast<uint4*>(dst + w * inner + c)[1] = pack8(v + 8);
+        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(ts + 256 + w * 64 + 16 * c, orr[c]);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t u[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] = pack2(__uint_as_float(orr[c][2 * i]), __uint_as_float(orr[c][2 * i + 1]));
+            reinterpret_cast<uint4*>(dst + w * inner + 16 * c)[0] = make_uint4(u[0], u[1], u[2], u[3]);
+            reinterpret_cast<uint4*>(dst + w * inner + 16 * c)[1] = make_uint4(u[4], u[5], u[6], u[7]);
           }
         }
       }
@@ -433,13 +472,21 @@ static void fwd(const bf16* QKV, bf16* O, int B, int N, int H, cudaStream_t st) 
   CUtensorMap tq = make_map(QKV, 3 * inner, T, 3 * inner, 64, 128);
   CUtensorMap tkv = make_map(QKV, 3 * inner, T, 3 * inner, 64, a.KPAD);
   const int smem = FWD_STAGES * 5 * TILE + 256 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    DG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
   const int grid = std::min(B * H, sm_count());
-  launch_k(attn_fwd_tc_kernel, grid, FWD_THREADS, smem, st, tq, tkv, a);
+  switch (a.KPAD / 16) {
+#define DG_ATTN_F(NK_)                                                                                              \
+    case NK_: {                                                                                                     \
+      static bool attr = false;                                                                                     \
+      if (!attr) {                                                                                                  \
+        DG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<NK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+        attr = true;                                                                                                \
+      }                                                                                                             \
+      launch_k(attn_fwd_tc_kernel<NK_>, grid, FWD_THREADS, smem, st, tq, tkv, a);                                   \
+    } break;
+    DG_ATTN_F(1) DG_ATTN_F(2) DG_ATTN_F(3) DG_ATTN_F(4) DG_ATTN_F(5) DG_ATTN_F(6) DG_ATTN_F(7) DG_ATTN_F(8)
+#undef DG_ATTN_F
+    default: fail(DGVIT_ERR_ARG, "attention: N=%d not supported by the tensor-core kernel", N);
+  }
   DG_LAUNCH_CHECK();
 }
 
@@ -454,13 +501,21 @@ static void bwd(const bf16* QKV, const bf16* O, const bf16* dO, bf16* dQKV, int 
   CUtensorMap tkv = make_map(QKV, 3 * inner, T, 3 * inner, 64, a.KPAD);
   CUtensorMap tdo = make_map(dO, inner, T, inner, 64, 128);
   const int smem = (BWD_LOAD_STAGES * 4 + 4) * TILE + 256 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    DG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
   const int grid = std::min(B * H, sm_count());
-  launch_k(attn_bwd_tc_kernel, grid, BWD_THREADS, smem, st, tq, tkv, tdo, a);
+  switch (a.KPAD / 16) {
+#define DG_ATTN_B(NK_)                                                                                              \
+    case NK_: {                                                                                                     \
+      static bool attr = false;                                                                                     \
+      if (!attr) {                                                                                                  \
+        DG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<NK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+        attr = true;                                                                                                \
+      }                                                                                                             \
+      launch_k(attn_bwd_tc_kernel<NK_>, grid, BWD_THREADS, smem, st, tq, tkv, tdo, a);                              \
+    } break;
+    DG_ATTN_B(1) DG_ATTN_B(2) DG_ATTN_B(3) DG_ATTN_B(4) DG_ATTN_B(5) DG_ATTN_B(6) DG_ATTN_B(7) DG_ATTN_B(8)
+#undef DG_ATTN_B
+    default: fail(DGVIT_ERR_ARG, "attention: N=%d not supported by the tensor-core kernel", N);
+  }
   DG_LAUNCH_CHECK();
 }
 
