@@ -77,20 +77,34 @@ struct AttnArgs {
 // =====================================================================================
 // forward
 // =====================================================================================
-// smem stage: Q [128x64] | K [128x64 (KPAD rows used)] | V | P block0 | P block1  = 5 tiles
+// smem: a ring of LS load stages (Q | K | V, KPAD rows of 128 B each) decoupled from the two compute stages
+// (P block0 | P block1 + one TMEM stage each), so the TMA producer runs LS items ahead of the softmax.
+// The S MMA reads 128 query rows from a KPAD-row Q tile: rows >= KPAD alias the following tiles and only produce
+// score rows that are never stored.
+template <int NK> struct FwdSmem {
+  static constexpr int LT = NK * 2048;                       // one Q / K / V tile
+  static constexpr int LS = (26 / NK) < 4 ? (26 / NK) : 4;   // load stages that fit beside the P buffers
+  static constexpr int LOAD_STAGE = 3 * LT;
+  static constexpr int OFF_P = LS * LOAD_STAGE;
+  static constexpr int OFF_BAR = OFF_P + FWD_STAGES * 2 * TILE;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static_assert(LS >= 2 && TOTAL <= 232448, "smem budget");
+};
+
 template <int NK>   // NK = KPAD / 16: key blocks held in registers by the softmax
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnArgs a) {
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const AttnArgs a) {
+  using SM = FwdSmem<NK>;
+  constexpr int LS = SM::LS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int STAGE_BYTES = 5 * TILE;
-  uint64_t* bars = (uint64_t*)(smem + FWD_STAGES * STAGE_BYTES);
-  uint64_t* qkv_full = bars;                    // [S] TMA landed
-  uint64_t* qkv_empty = qkv_full + FWD_STAGES;  // [S] O-MMA retired: smem stage reusable
-  uint64_t* s_full = qkv_empty + FWD_STAGES;    // [S] S in TMEM
-  uint64_t* p_ready = s_full + FWD_STAGES;      // [S] P written to smem (4 warps)
-  uint64_t* o_full = p_ready + FWD_STAGES;      // [S] O in TMEM
-  uint64_t* t_free = o_full + FWD_STAGES;       // [S] TMEM stage drained (4 warps)
+  uint64_t* bars = (uint64_t*)(smem + SM::OFF_BAR);
+  uint64_t* qkv_full = bars;                    // [LS] TMA landed
+  uint64_t* qkv_empty = qkv_full + LS;          // [LS] O-MMA retired: load stage reusable
+  uint64_t* s_full = qkv_empty + LS;            // [2] S in TMEM
+  uint64_t* p_ready = s_full + FWD_STAGES;      // [2] P written to smem (4 warps)
+  uint64_t* o_full = p_ready + FWD_STAGES;      // [2] O in TMEM
+  uint64_t* t_free = o_full + FWD_STAGES;       // [2] TMEM stage drained (4 warps)
   uint32_t* tmem_slot = (uint32_t*)(t_free + FWD_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,10 +113,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr uint32_t TCOLS_STAGE = 256;   // S: cols [0,128), O: cols [128,192)
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmKV);
+    for (int i = 0; i < LS; ++i) { mbar_init(&qkv_full[i], 1); mbar_init(&qkv_empty[i], 1); }
     for (int i = 0; i < FWD_STAGES; ++i) {
-      mbar_init(&qkv_full[i], 1); mbar_init(&qkv_empty[i], 1); mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); mbar_init(&t_free[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); mbar_init(&t_free[i], 4);
     }
     fence_barrier_init();
   }
@@ -117,53 +131,58 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0) {
     if (elect_one_sync()) {
-      int st = 0; uint32_t ph = 0;
+      int ls = 0; uint32_t ph = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int b = it / a.H, h = it % a.H;
-        mbar_wait(&qkv_empty[st], ph ^ 1);
-        uint8_t* base = smem + st * STAGE_BYTES;
-        mbar_expect_tx(&qkv_full[st], TILE + 2 * a.KPAD * 128);
-        tma_load_2d(base, &tmQ, &qkv_full[st], h * DH, b * a.N);
-        tma_load_2d(base + TILE, &tmKV, &qkv_full[st], inner + h * DH, b * a.N);
-        tma_load_2d(base + 2 * TILE, &tmKV, &qkv_full[st], 2 * inner + h * DH, b * a.N);
-        if (++st == FWD_STAGES) { st = 0; ph ^= 1; }
+        mbar_wait(&qkv_empty[ls], ph ^ 1);
+        uint8_t* base = smem + ls * SM::LOAD_STAGE;
+        mbar_expect_tx(&qkv_full[ls], 3 * SM::LT);
+        tma_load_2d(base, &tmKV, &qkv_full[ls], h * DH, b * a.N);
+        tma_load_2d(base + SM::LT, &tmKV, &qkv_full[ls], inner + h * DH, b * a.N);
+        tma_load_2d(base + 2 * SM::LT, &tmKV, &qkv_full[ls], 2 * inner + h * DH, b * a.N);
+        if (++ls == LS) { ls = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (elect_one_sync()) {
-      const uint32_t idesc_s = make_idesc(128, a.KPAD, false, false);
-      const uint32_t idesc_o = make_idesc(128, DH, false, true);
-      const int ksteps = a.KPAD / 16;
-      int st = 0; uint32_t ph = 0;          // issue side (S)
+      constexpr uint32_t idesc_s = make_idesc(128, NK * 16, false, false);
+      constexpr uint32_t idesc_o = make_idesc(128, DH, false, true);
+      int st = 0; uint32_t ph = 0;          // compute stage of the S issue
+      int ls = 0; uint32_t lph = 0;         // load stage of the S issue
       int st2 = 0; uint32_t ph2 = 0;        // O side (one item behind)
+      int ls2 = 0;
       int n_mine = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) ++n_mine;
       for (int i = 0; i <= n_mine; ++i) {
         if (i < n_mine) {
           mbar_wait(&t_free[st], ph ^ 1);
-          mbar_wait(&qkv_full[st], ph);
+          mbar_wait(&qkv_full[ls], lph);
           tc_fence_after();
-          const uint32_t sq = smem_u32(smem + st * STAGE_BYTES), sk = sq + TILE;
+          const uint32_t sq = smem_u32(smem + ls * SM::LOAD_STAGE), sk = sq + SM::LT;
           const uint64_t qd = make_smem_desc(sq, 16, 1024), kd = make_smem_desc(sk, 16, 1024);
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k)
             umma_bf16(tmem_base + st * TCOLS_STAGE, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_s, k > 0);
           umma_commit(&s_full[st]);
           if (++st == FWD_STAGES) { st = 0; ph ^= 1; }
+          if (++ls == LS) { ls = 0; lph ^= 1; }
         }
         if (i >= 1) {
           mbar_wait(&p_ready[st2], ph2);
           tc_fence_after();
-          const uint32_t sv = smem_u32(smem + st2 * STAGE_BYTES) + 2 * TILE, sp = sv + TILE;
-          for (int k = 0; k < ksteps; ++k) {
+          const uint32_t sv = smem_u32(smem + ls2 * SM::LOAD_STAGE) + 2 * SM::LT;
+          const uint32_t sp = smem_u32(smem + SM::OFF_P + st2 * 2 * TILE);
+#pragma unroll
+          for (int k = 0; k < NK; ++k) {
             // A = P (K-major, 64-key blocks one tile apart); B = V as MN-major (16 key rows per step)
             const uint64_t pd = make_smem_desc(sp + (k >> 2) * TILE + (k & 3) * 32, 16, 1024);
             const uint64_t vd = make_smem_desc(sv + k * 2048, 8192, 1024);
             umma_bf16(tmem_base + st2 * TCOLS_STAGE + 128, pd, vd, idesc_o, k > 0);
           }
           umma_commit(&o_full[st2]);
-          umma_commit(&qkv_empty[st2]);
+          umma_commit(&qkv_empty[ls2]);
           if (++st2 == FWD_STAGES) { st2 = 0; ph2 ^= 1; }
+          if (++ls2 == LS) ls2 = 0;
         }
       }
     }
@@ -178,7 +197,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int st = wg; uint32_t ph = 0;
     for (int it = blockIdx.x + wg * gridDim.x; it < items; it += FWD_STAGES * gridDim.x) {
       const int b = it / a.H, h = it % a.H;
-      uint8_t* P = smem + st * STAGE_BYTES + 3 * TILE;
+      uint8_t* P = smem + SM::OFF_P + st * 2 * TILE;
       mbar_wait(&s_full[st], ph);
       tc_fence_after();
       const uint32_t ts = tmem_base + st * TCOLS_STAGE + lane_off;
@@ -469,19 +488,18 @@ static void fwd(const bf16* QKV, bf16* O, int B, int N, int H, cudaStream_t st) 
   a.B = B; a.N = N; a.H = H; a.KPAD = (N + 15) / 16 * 16;
   a.scale = 1.0f / sqrtf((float)DH);
   a.O = O; a.Oin = nullptr; a.dO = nullptr; a.dQKV = nullptr;
-  CUtensorMap tq = make_map(QKV, 3 * inner, T, 3 * inner, 64, 128);
   CUtensorMap tkv = make_map(QKV, 3 * inner, T, 3 * inner, 64, a.KPAD);
-  const int smem = FWD_STAGES * 5 * TILE + 256 + 1024;
   const int grid = std::min(B * H, sm_count());
   switch (a.KPAD / 16) {
 #define DG_ATTN_F(NK_)                                                                                              \
     case NK_: {                                                                                                     \
+      constexpr int smem = FwdSmem<NK_>::TOTAL;                                                                     \
       static bool attr = false;                                                                                     \
       if (!attr) {                                                                                                  \
         DG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<NK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
         attr = true;                                                                                                \
       }                                                                                                             \
-      launch_k(attn_fwd_tc_kernel<NK_>, grid, FWD_THREADS, smem, st, tq, tkv, a);                                   \
+      launch_k(attn_fwd_tc_kernel<NK_>, grid, FWD_THREADS, smem, st, tkv, a);                                       \
     } break;
     DG_ATTN_F(1) DG_ATTN_F(2) DG_ATTN_F(3) DG_ATTN_F(4) DG_ATTN_F(5) DG_ATTN_F(6) DG_ATTN_F(7) DG_ATTN_F(8)
 #undef DG_ATTN_F

@@ -81,6 +81,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// shared -> global tile store (bulk async group); smem must stay untouched until wait_group.read
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -152,6 +163,7 @@ struct TcArgs {
   int splitk;           // >1: partial[split][M][N] (or transposed) fp32
   int trans_out;        // store C^T (element (m,n) at C[n*ldc + m])
   int epi;
+  int tma_store;        // bf16 output without epilogue math leaves through TMA tile stores (tmC)
   void* C; void* C2; int64_t ldc;
   const float* bias; const float* resid; int64_t ldr;
   const void* aux; int64_t ldaux;
@@ -164,11 +176,14 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 128 ? 5 : 6);
-  static_assert(STAGES * STAGE_BYTES + 256 + EpiCfg<BN>::WARPS * 32 * 80 + 1024 <= 232448, "smem budget");
+  static_assert(STAGES * STAGE_BYTES + 1024 + (BN / 64) * 16384 + 1024 <= 232448, "smem budget");
   static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 1024;       // keeps the staging area 1024-byte aligned (swizzled TMA-store tiles)
   // per-epilogue-warp staging tiles for coalesced bf16 stores
-  static constexpr int STAGING_BYTES = EpiCfg<BN>::WARPS * 32 * (64 + 16);
+  // ... or, for the TMA-store epilogue, one 128B-swizzled [128 rows][64 cols] bf16 tile per 64 output columns
+  static constexpr int WARP_STAGING = EpiCfg<BN>::WARPS * 32 * (64 + 16);
+  static constexpr int BLOCK_STAGING = (BN / 64) * 16384;
+  static constexpr int STAGING_BYTES = WARP_STAGING > BLOCK_STAGING ? WARP_STAGING : BLOCK_STAGING;
   static constexpr int TOTAL = TILES_BYTES + BAR_BYTES + STAGING_BYTES + 1024;  // +1024 for manual alignment
 };
 
@@ -242,7 +257,8 @@ __device__ __forceinline__ void load_row32<bf16>(const bf16* src, float (&v)[32]
 
 template <int BN, bool A_MN, bool B_MN, typename TC>
 __global__ void __launch_bounds__(EpiCfg<BN>::THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const TcArgs g) {
   using SL = SmemLayout<BN>;
   constexpr int STAGES = SL::STAGES;
   constexpr int ACC_STAGES = 2;
@@ -265,6 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.tma_store) tma_prefetch_desc(&tmC);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EpiCfg<BN>::WARPS); }
     fence_barrier_init();
@@ -414,6 +431,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       };
+      if constexpr (std::is_same<TC, bf16>::value) {
+        if (g.tma_store) {
+          // ---- plain bf16 output: registers -> swizzled smem tile -> one TMA store per 64-column block.
+          constexpr int WARPS_PER_BLK = 4 * (64 / COLS_PER_WARP);
+          const int blk = (grp * COLS_PER_WARP) / 64;                       // 64-column block of the tile
+          uint8_t* sblk = smem + SL::TILES_BYTES + SL::BAR_BYTES + blk * 16384;
+          const bool leader = (quad == 0) && ((grp * COLS_PER_WARP) % 64 == 0);
+          if (leader && elect_one_sync()) tma_store_wait_read();            // previous tile's store has drained the block
+          named_bar_sync(1 + blk, WARPS_PER_BLK * 32);
+          const int r = quad * 32 + lane;
+#pragma unroll
+          for (int ch = 0; ch < CHUNKS; ++ch) {
+            float v[32];
+            tmem_ld32(tbase + ch * 32, v);
+            const int c16 = ((grp * COLS_PER_WARP + ch * 32) % 64) / 8;     // first 16-byte chunk inside the 128-byte row
+            const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(sblk + rowoff + (((c16 + i) ^ (r & 7)) << 4)) = attn_pack8(v + 8 * i);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);                     // accumulator drained: next tile's MMAs may start
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          named_bar_sync(1 + blk, WARPS_PER_BLK * 32);
+          if (leader && elect_one_sync()) {
+            if (g.debug != 1) tma_store_2d(&tmC, sblk, nt * BN + blk * 64, mt * BM);
+            tma_store_commit();
+          }
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+      }
 #pragma unroll 1
       for (int ch = 0; ch < CHUNKS; ++ch) {
         if (g.debug == 2) break;
@@ -523,6 +573,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
+    if (g.tma_store) tma_store_wait_read();     // (no-op for threads that issued nothing)
   }
   tc_fence_before();
   __syncthreads();
@@ -574,7 +625,7 @@ static int sm_count() {
 }
 
 template <int BN, bool A_MN, bool B_MN, typename TC>
-static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, cudaStream_t st) {
+static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const TcArgs& a, cudaStream_t st) {
   using SL = SmemLayout<BN>;
   static bool attr = false;
   if (!attr) {
@@ -583,18 +634,18 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a
   }
   const int tiles = (int)(cdiv(a.M, BM) * cdiv(a.N, BN) * a.splitk);
   const int grid = std::min(tiles, sm_count());
-  launch_k(gemm_tc_kernel<BN, A_MN, B_MN, TC>, grid, EpiCfg<BN>::THREADS, SL::TOTAL, st, ta, tb, a);
+  launch_k(gemm_tc_kernel<BN, A_MN, B_MN, TC>, grid, EpiCfg<BN>::THREADS, SL::TOTAL, st, ta, tb, tc_, a);
   DG_LAUNCH_CHECK();
 }
 
 template <typename TC>
-static void dispatch(bool a_mn, bool b_mn, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a,
-                     cudaStream_t st) {
+static void dispatch(bool a_mn, bool b_mn, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_,
+                     const TcArgs& a, cudaStream_t st) {
 #define DG_TC_CASE(BN_)                                                        \
   if (bn == BN_) {                                                             \
-    if (!a_mn && !b_mn) return launch<BN_, false, false, TC>(ta, tb, a, st);   \
-    if (!a_mn && b_mn) return launch<BN_, false, true, TC>(ta, tb, a, st);     \
-    if (a_mn && b_mn) return launch<BN_, true, true, TC>(ta, tb, a, st);       \
+    if (!a_mn && !b_mn) return launch<BN_, false, false, TC>(ta, tb, tc_, a, st);   \
+    if (!a_mn && b_mn) return launch<BN_, false, true, TC>(ta, tb, tc_, a, st);     \
+    if (a_mn && b_mn) return launch<BN_, true, true, TC>(ta, tb, tc_, a, st);       \
   }
   DG_TC_CASE(64)
   DG_TC_CASE(128)
@@ -656,7 +707,11 @@ static bool gemm_tc_try(const GemmArgs& g0, cudaStream_t st) {
       a.splitk = (int)cdiv(kb_total, per);
     }
     if (g0.splitk > 1 && a.splitk == 1 && !trans_out) { /* direct store below */ }
-    dispatch<TC>(a_mn, b_mn, bn, ta, tb, a, st);
+    // plain bf16 outputs (QKV, dO) leave through TMA tile stores
+    a.tma_store = (std::is_same<TC, bf16>::value && g.epi == EPI_NONE && a.splitk == 1 && !trans_out && g.N % 64 == 0 &&
+                   g.ldc % 8 == 0 && (((uintptr_t)g.C) & 15) == 0) ? 1 : 0;
+    CUtensorMap tcm = a.tma_store ? make_map(g.C, g.N, g.M, g.ldc, 64, BM) : ta;
+    dispatch<TC>(a_mn, b_mn, bn, ta, tb, tcm, a, st);
     if (a.splitk > 1) {
       const int64_t n = (int64_t)g0.M * g0.N;
       DG_REQUIRE(g0.ldc == g0.N, "gemm_tc: split-K output must be dense");
