@@ -103,6 +103,12 @@ class Replay(C.Structure):
                 ("act", c_f_p), ("rew", c_f_p), ("done", c_f_p), ("n_pstate", C.c_int32), ("n_act", C.c_int32)]
 
 
+class QnetLayout(C.Structure):
+    _fields_ = [("conv_w", C.c_int64 * 3), ("conv_b", C.c_int64 * 3)] + [
+        (n, C.c_int64) for n in ("fc1_w", "fc1_b", "fc2_w", "fc2_b", "fc3_w", "fc3_b", "embed_w", "embed_b",
+                                 "fc11_w", "fc11_b", "fc21_w", "fc21_b", "fc31_w", "fc31_b", "total")]
+
+
 # every symbol include/dgvit.h declares: (name, restype, argtypes)
 P = C.POINTER
 SYMBOLS = {
@@ -133,8 +139,13 @@ SYMBOLS = {
                                        C.c_int, C.c_void_p]),
     "dgvit_mlp_bf16": (C.c_int, [C.c_void_p] * 12 + [C.c_int64, C.c_int, C.c_void_p]),
     "dgvit_mlp_partial_floats": (C.c_int64, [C.c_int64, C.c_int]),
+    "dgvit_qnet_param_layout": (C.c_int, [C.c_int, C.c_int, P(QnetLayout)]),
+    "dgvit_qnet_workspace_bytes": (C.c_int, [C.c_int] * 6 + [P(C.c_size_t)]),
+    "dgvit_qnet_forward": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_qnet_backward": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 7 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     "dgvit_adam_step": (C.c_int, [P(Net), P(Adam), P(Net), C.c_float, C.c_void_p]),
     "dgvit_polyak": (C.c_int, [P(Net), P(Net), C.c_float, C.c_void_p]),
+    "dgvit_polyak_flat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "dgvit_replay_gather": (C.c_int, [P(Replay), C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
     "dgvit_depth_scratch_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
     "dgvit_depth_augment": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -176,6 +176,10 @@ static unsigned grid1d(int64_t n, int bs = 256) {
   return (unsigned)g;
 }
 
+}  // namespace dgvit
+#include "qnet.cuh"
+namespace dgvit {
+
 // ------------------------------------------------------------------ trunk context
 template <typename A>
 struct LayerBuf {
@@ -1298,6 +1302,69 @@ int dgvit_attention_bf16(const void* qkv, void* o, const void* d_o, void* d_qkv,
   });
 }
 
+// ---- CNN twin-Q critic (vn/got_sac_network.py:125-170)
+int dgvit_qnet_param_layout(int n_act, int n_pstate, dgvit_qnet_layout* out) {
+  return guarded([&] {
+    DG_REQUIRE(out && n_act >= 1 && n_act <= 4 && n_pstate >= 1, "bad argument");
+    qnet::make_layout(n_act, n_pstate, *out);
+  });
+}
+static void qnet_check(int img_h, int img_w, int n_act, int n_pstate, int B) {
+  DG_REQUIRE(B >= 1 && n_act >= 1 && n_act <= 4 && n_pstate >= 1, "qnet: bad sizes");
+  qnet::Geo g(B, img_h, img_w, n_act, n_pstate);
+  DG_REQUIRE(g.H3 >= 1 && g.W3 >= 1, "qnet: image %dx%d too small for three 5x5 stride-2 convolutions", img_h, img_w);
+}
+int dgvit_qnet_workspace_bytes(int img_h, int img_w, int n_act, int n_pstate, int B, int precision, size_t* bytes) {
+  return guarded([&] {
+    DG_REQUIRE(bytes != nullptr, "null bytes");
+    qnet_check(img_h, img_w, n_act, n_pstate, B);
+    qnet::Geo g(B, img_h, img_w, n_act, n_pstate);
+    Carver cv(nullptr, 0, true);
+    by_precision(precision, [&] { qnet::Ws<float> w; qnet::carve(cv, g, w); }, [&] { qnet::Ws<bf16> w; qnet::carve(cv, g, w); });
+    *bytes = cv.off;
+  });
+}
+int dgvit_qnet_forward(const float* params, const float* img, const float* pstate, const float* action, float* q1, float* q2,
+                       int img_h, int img_w, int n_act, int n_pstate, int B, int precision, void* ws, size_t ws_bytes,
+                       void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(params && img && pstate && action && q1 && q2 && ws, "qnet_forward: null argument");
+    DG_REQUIRE((((uintptr_t)img) & 15) == 0 && (((uintptr_t)params) & 15) == 0, "qnet_forward: 16-byte alignment required");
+    qnet_check(img_h, img_w, n_act, n_pstate, B);
+    qnet::Geo g(B, img_h, img_w, n_act, n_pstate);
+    dgvit_qnet_layout L;
+    qnet::make_layout(n_act, n_pstate, L);
+    Carver cv(ws, ws_bytes);
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      qnet::Ws<T> w;
+      qnet::carve(cv, g, w);
+      qnet::forward<T>(params, L, g, img, pstate, action, q1, q2, w, (cudaStream_t)stream);
+    };
+    by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
+  });
+}
+int dgvit_qnet_backward(const float* params, float* grads, const float* img, const float* pstate, const float* d_q1,
+                        const float* d_q2, float* d_action, int param_grads, int img_h, int img_w, int n_act, int n_pstate,
+                        int B, int precision, void* ws, size_t ws_bytes, void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(params && img && pstate && d_q1 && d_q2 && ws, "qnet_backward: null argument");
+    DG_REQUIRE(!param_grads || grads, "qnet_backward: param_grads without a gradient arena");
+    qnet_check(img_h, img_w, n_act, n_pstate, B);
+    qnet::Geo g(B, img_h, img_w, n_act, n_pstate);
+    dgvit_qnet_layout L;
+    qnet::make_layout(n_act, n_pstate, L);
+    Carver cv(ws, ws_bytes);
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      qnet::Ws<T> w;
+      qnet::carve(cv, g, w);
+      qnet::backward<T>(params, grads, L, g, img, pstate, d_q1, d_q2, d_action, param_grads != 0, w, (cudaStream_t)stream);
+    };
+    by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
+  });
+}
+
 int dgvit_adam_step(const dgvit_net* net, const dgvit_adam* opt, const dgvit_net* tgt, float tau, void* stream) {
   return guarded([&] {
     DG_REQUIRE(net && opt && net->params && net->grads, "null argument");
@@ -1316,6 +1383,15 @@ int dgvit_polyak(const dgvit_net* target, const dgvit_net* source, float tau, vo
     DG_REQUIRE(L.total == Ls.total, "polyak: layouts differ");
     launch_k(polyak_kernel, 148 * 4, 256, 0, (cudaStream_t)stream, target->params, source->params, (bf16*)target->shadow, tau,
                                                              L.total);
+    DG_LAUNCH_CHECK();
+  });
+}
+
+int dgvit_polyak_flat(float* target, const float* source, int64_t n, float tau, void* stream) {
+  return guarded([&] {
+    DG_REQUIRE(target && source && n >= 0, "null argument");
+    if (n == 0) return;
+    launch_k(polyak_kernel, 148 * 4, 256, 0, (cudaStream_t)stream, target, source, (bf16*)nullptr, tau, n);
     DG_LAUNCH_CHECK();
   });
 }

@@ -588,3 +588,154 @@ class GoTQNetwork(_ArenaModule):
         ps_ = list(self.parameters())
         need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in ps_) or act.requires_grad)
         return _CriticFn.apply(self, need_grad, img, ps, act, *ps_)
+
+
+# --------------------------------------------------------------------------- CNN critic
+class _QnetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, need_grad, img, pstate, action, *params):
+        B, dev, na = img.shape[0], img.device, mod.nb_actions
+        q1 = torch.empty(B, na, device=dev)
+        q2 = torch.empty(B, na, device=dev)
+        act = action.detach().contiguous()
+        ws = mod._workspace(B, need_grad)
+        L.check(L.lib().dgvit_qnet_forward(mod._arena.data_ptr(), img.data_ptr(), pstate.data_ptr(), act.data_ptr(),
+                                           q1.data_ptr(), q2.data_ptr(), mod.image_size[0], mod.image_size[1], na,
+                                           mod.nb_pstate, B, mod._precision_code(), ws.data_ptr(), ws.numel(), _stream(dev)),
+                "qnet_forward")
+        ctx.mod, ctx.ws, ctx.B = mod, ws, B
+        ctx.keep = (img, pstate, act)
+        ctx.needs = [p.requires_grad for p in params]
+        ctx.act_grad = action.requires_grad
+        return q1, q2
+
+    @staticmethod
+    def backward(ctx, d_q1, d_q2):
+        mod, B = ctx.mod, ctx.B
+        img, pstate, _ = ctx.keep
+        dev, na = img.device, mod.nb_actions
+        d_q1 = torch.zeros(B, na, device=dev) if d_q1 is None else d_q1.contiguous().float()
+        d_q2 = torch.zeros(B, na, device=dev) if d_q2 is None else d_q2.contiguous().float()
+        d_act = torch.empty(B, na, device=dev) if ctx.act_grad else None
+        pg = any(ctx.needs)
+        L.check(L.lib().dgvit_qnet_backward(mod._arena.data_ptr(), mod._garena.data_ptr(), img.data_ptr(), pstate.data_ptr(),
+                                            d_q1.data_ptr(), d_q2.data_ptr(), L.ptr(d_act), int(pg), mod.image_size[0],
+                                            mod.image_size[1], na, mod.nb_pstate, B, mod._precision_code(),
+                                            ctx.ws.data_ptr(), ctx.ws.numel(), _stream(dev)), "qnet_backward")
+        grads = [None] * len(ctx.needs)
+        if pg:
+            ps = dict(mod.named_parameters())
+            grads = [mod._garena[off:off + ps[n].numel()].view(ps[n].shape).clone() if need else None
+                     for (n, off), need in zip(mod._named_offsets(), ctx.needs)]
+        return (None, None, None, None, d_act) + tuple(grads)
+
+
+class QNetwork(nn.Module):
+    """Drop-in for the reference CNN twin-Q critic ``QNetwork`` (vn/got_sac_network.py:125-170), the shipped
+    default ``critic_type`` (vn/config.yaml:61): same constructor, ``forward([istate, pstate, a]) -> (q1, q2)``,
+    attribute names and ``state_dict`` keys.  The parameters are views into one flat arena
+    (``dgvit_qnet_param_layout``); forward / backward run ``dgvit_qnet_forward`` / ``dgvit_qnet_backward``."""
+
+    def __init__(self, nb_actions, nb_pstate, *, image_size=(128, 160)):
+        super().__init__()
+        self.conv1 = nn.Conv2d(1, 16, 5, stride=2)
+        self.conv2 = nn.Conv2d(16, 64, 5, stride=2)
+        self.conv3 = nn.Conv2d(64, 256, 5, stride=2)
+        self.avg = nn.AdaptiveAvgPool2d(output_size=(1, 1))
+        self.fc1 = nn.Linear(256 + 32 + nb_actions, 128)
+        self.fc2 = nn.Linear(128, 32)
+        self.fc3 = nn.Linear(32, nb_actions)
+        self.fc_embed = nn.Linear(nb_pstate, 32)
+        self.fc11 = nn.Linear(256 + 32 + nb_actions, 128)
+        self.fc21 = nn.Linear(128, 32)
+        self.fc31 = nn.Linear(32, nb_actions)
+        self.apply(weights_init_)
+        self.nb_actions, self.nb_pstate, self.image_size = nb_actions, nb_pstate, tuple(image_size)
+        self.precision = "fp32"
+        self._arena = self._garena = None
+        self._ws_cache: Dict = {}
+        self._layout = None
+
+    def layout(self) -> L.QnetLayout:
+        if self._layout is None:
+            out = L.QnetLayout()
+            L.check(L.lib().dgvit_qnet_param_layout(self.nb_actions, self.nb_pstate, C.byref(out)), "qnet_param_layout")
+            self._layout = out
+        return self._layout
+
+    def _named_offsets(self) -> List[Tuple[str, int]]:
+        lay = self.layout()
+        out = []
+        for i in range(3):
+            out += [(f"conv{i + 1}.weight", lay.conv_w[i]), (f"conv{i + 1}.bias", lay.conv_b[i])]
+        for n, f in (("fc1", "fc1"), ("fc2", "fc2"), ("fc3", "fc3"), ("fc_embed", "embed"), ("fc11", "fc11"),
+                     ("fc21", "fc21"), ("fc31", "fc31")):
+            out += [(n + ".weight", getattr(lay, f + "_w")), (n + ".bias", getattr(lay, f + "_b"))]
+        return out
+
+    def _bound(self) -> bool:
+        if self._arena is None:
+            return False
+        ps = dict(self.named_parameters())
+        base = self._arena.data_ptr()
+        offs = self._named_offsets()
+        return all(ps[n].device == self._arena.device and ps[n].data_ptr() == base + 4 * off for n, off in (offs[0], offs[-1]))
+
+    def bind(self, force: bool = False):
+        if not force and self._bound():
+            return self
+        lay = self.layout()
+        ps = dict(self.named_parameters())
+        offs = self._named_offsets()
+        assert [n for n, _ in offs] == list(ps.keys()), "parameter registration order differs from the C layout"
+        dev = next(iter(ps.values())).device
+        arena = torch.zeros(lay.total, dtype=torch.float32, device=dev)
+        for name, off in offs:
+            p = ps[name]
+            arena[off:off + p.numel()].copy_(p.data.reshape(-1))
+            p.data = arena[off:off + p.numel()].view(p.shape)
+        self._arena, self._garena, self._ws_cache = arena, torch.zeros_like(arena), {}
+        return self
+
+    def _precision_code(self) -> int:
+        return {"fp32": L.FP32, "bf16": L.BF16}[self.precision]
+
+    def _workspace(self, B: int, save: bool) -> torch.Tensor:
+        nbytes = C.c_size_t()
+        L.check(L.lib().dgvit_qnet_workspace_bytes(self.image_size[0], self.image_size[1], self.nb_actions, self.nb_pstate, B,
+                                                   self._precision_code(), C.byref(nbytes)), "qnet_workspace_bytes")
+        dev = self._arena.device
+        if save:
+            return torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        key = (B, self.precision)
+        ws = self._ws_cache.get(key)
+        if ws is None or ws.numel() < nbytes.value:
+            ws = self._ws_cache[key] = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        return ws
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._arena = None
+        return r
+
+    def __deepcopy__(self, memo):
+        import copy as _copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_ws_cache" else _copy.deepcopy(v, memo)
+        return new
+
+    def forward(self, inp):
+        istate, pstate, a = inp
+        self.bind()
+        _require_cuda(self._arena)
+        h, w = self.image_size
+        if istate.dim() != 3 or istate.shape[1] != h or istate.shape[2] != w:
+            raise ValueError(f"istate must be [B,{h},{w}], got {tuple(istate.shape)}")
+        img = istate.to(self._arena.device, torch.float32).contiguous()
+        ps = pstate.to(img.device, torch.float32).contiguous()
+        act = a.to(img.device, torch.float32)
+        ps_ = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in ps_) or act.requires_grad)
+        return _QnetFn.apply(self, need_grad, img, ps, act, *ps_)

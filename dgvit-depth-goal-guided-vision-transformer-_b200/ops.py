@@ -7,11 +7,18 @@ from typing import Optional
 import torch
 
 from . import _lib as L
-from .modules import _ArenaModule, _stream
+from .modules import QNetwork, _ArenaModule, _stream
 
 
 def soft_update(target, source, tau):
     """vn/utils.py:31-33 over all parameters, one fused kernel over the flat arenas."""
+    if isinstance(target, QNetwork) and isinstance(source, QNetwork):
+        target.bind(); source.bind()
+        n = target.layout().total
+        assert n == source.layout().total
+        L.check(L.lib().dgvit_polyak_flat(target._arena.data_ptr(), source._arena.data_ptr(), n, float(tau),
+                                          _stream(target._arena.device)), "polyak_flat")
+        return
     if not (isinstance(target, _ArenaModule) and isinstance(source, _ArenaModule)):
         raise TypeError("soft_update expects dgvit_b200 modules")
     t, s = target.net_struct(), source.net_struct()

@@ -282,12 +282,37 @@ int dgvit_mlp_bf16(const void* x, const void* W1, const float* b1, const void* W
                    float* partial, int64_t rows, int hid, void* stream);
 int64_t dgvit_mlp_partial_floats(int64_t rows, int hid);
 
+/* ---- CNN twin-Q critic `QNetwork` (vn/got_sac_network.py:125-170; the reference's shipped default critic_type,
+ * vn/config.yaml:61, vn/DRL.py:118-121).  Parameters live in one flat fp32 arena in the reference's registration
+ * order (conv1-3, fc1, fc2, fc3, fc_embed, fc11, fc21, fc31; weight then bias), each tensor 256-byte aligned. */
+typedef struct dgvit_qnet_layout {
+  int64_t conv_w[3], conv_b[3];          /* [16,1,5,5] [64,16,5,5] [256,64,5,5] */
+  int64_t fc1_w, fc1_b, fc2_w, fc2_b, fc3_w, fc3_b;     /* [128, 256+32+n_act] [32,128] [n_act,32] */
+  int64_t embed_w, embed_b;              /* fc_embed [32, n_pstate] */
+  int64_t fc11_w, fc11_b, fc21_w, fc21_b, fc31_w, fc31_b;
+  int64_t total;                         /* floats */
+} dgvit_qnet_layout;
+int dgvit_qnet_param_layout(int n_act, int n_pstate, dgvit_qnet_layout* out);
+int dgvit_qnet_workspace_bytes(int img_h, int img_w, int n_act, int n_pstate, int B, int precision, size_t* bytes);
+/* QNetwork.forward([img, pstate, action]) -> (q1, q2), each [B, n_act].  img [B, img_h, img_w] fp32.  The workspace
+ * keeps the activations: pass the same one to dgvit_qnet_backward. */
+int dgvit_qnet_forward(const float* params, const float* img, const float* pstate, const float* action, float* q1,
+                       float* q2, int img_h, int img_w, int n_act, int n_pstate, int B, int precision,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of the forward that last ran on `workspace`: d_action [B, n_act] (optional) and, when param_grads != 0,
+ * every parameter gradient into `grads` (same layout as params, overwritten). */
+int dgvit_qnet_backward(const float* params, float* grads, const float* img, const float* pstate, const float* d_q1,
+                        const float* d_q2, float* d_action, int param_grads, int img_h, int img_w, int n_act,
+                        int n_pstate, int B, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
 /* torch.optim.Adam.step (+ optional fused Polyak target update, vn/utils.py:31-33, and bf16
  * shadow refresh) over a flat arena; skips layout.skip ranges */
 int dgvit_adam_step(const dgvit_net* net, const dgvit_adam* opt, const dgvit_net* polyak_target,
                     float tau, void* stream);
 /* soft_update / hard_update (tau = 1) over all parameters — vn/utils.py:31-37 */
 int dgvit_polyak(const dgvit_net* target, const dgvit_net* source, float tau, void* stream);
+/* the same over two flat fp32 arenas of n floats (modules without a dgvit_cfg: the CNN critic) */
+int dgvit_polyak_flat(float* target, const float* source, int64_t n, float tau, void* stream);
 
 /* cpprb sample() row gather + staging — vn/DRL.py:375-386.  Bit-exact copies.
  * store_obs [size, frame] with next_obs[i] = obs[(i+1)%size] (cpprb next_of="obs"). */

@@ -181,6 +181,25 @@ def critic_forward(p, img, pstate, a, cfg: Cfg, drop_mask=None):
     return q1, q2
 
 
+def qnet_forward(p, img, pstate, a):
+    """``QNetwork.forward`` (CNN twin-Q critic, the shipped default ``critic_type``) —
+    vn/got_sac_network.py:149-170; layers :129-144."""
+    x1 = img.unsqueeze(1)                                                       # :153
+    x1 = F.relu(F.conv2d(x1, p["conv1.weight"], p["conv1.bias"], stride=2))     # :154
+    x1 = F.relu(F.conv2d(x1, p["conv2.weight"], p["conv2.bias"], stride=2))     # :155
+    x1 = F.relu(F.conv2d(x1, p["conv3.weight"], p["conv3.bias"], stride=2))     # :156
+    x1 = x1.mean(dim=(2, 3))                                                    # :157-158 AdaptiveAvgPool2d((1,1)) + view
+    x2 = F.relu(pstate @ p["fc_embed.weight"].t() + p["fc_embed.bias"])         # :160-161
+    x = torch.cat([x1, x2, a], dim=1)                                           # :163
+    q1 = F.relu(x @ p["fc1.weight"].t() + p["fc1.bias"])
+    q1 = F.relu(q1 @ p["fc2.weight"].t() + p["fc2.bias"])
+    q1 = q1 @ p["fc3.weight"].t() + p["fc3.bias"]                               # :165-167
+    q2 = F.relu(x @ p["fc11.weight"].t() + p["fc11.bias"])
+    q2 = F.relu(q2 @ p["fc21.weight"].t() + p["fc21.bias"])
+    q2 = q2 @ p["fc31.weight"].t() + p["fc31.bias"]                             # :169-171
+    return q1, q2
+
+
 # --------------------------------------------------------------------------
 # Optimizer / target update
 # --------------------------------------------------------------------------

@@ -126,6 +126,30 @@ def reference_init(kind: str, cfg: Cfg, seed) -> "OrderedDict[str, torch.Tensor]
     return OrderedDict((k, v.detach().clone()) for k, v in out.items())
 
 
+def reference_qnet_init(seed, nb_actions: int = 2, nb_pstate: int = 2) -> "OrderedDict[str, torch.Tensor]":
+    """Parameters of the CNN critic as ``QNetwork.__init__`` creates them (vn/got_sac_network.py:126-147):
+    conv1-3 (default Conv2d init), fc1, fc2, fc3, fc_embed, fc11, fc21, fc31, then ``apply(weights_init_)``."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    m = OrderedDict()
+    m["conv1"] = nn.Conv2d(1, 16, 5, stride=2)
+    m["conv2"] = nn.Conv2d(16, 64, 5, stride=2)
+    m["conv3"] = nn.Conv2d(64, 256, 5, stride=2)
+    m["fc1"] = nn.Linear(256 + 32 + nb_actions, 128)
+    m["fc2"] = nn.Linear(128, 32)
+    m["fc3"] = nn.Linear(32, nb_actions)
+    m["fc_embed"] = nn.Linear(nb_pstate, 32)
+    m["fc11"] = nn.Linear(256 + 32 + nb_actions, 128)
+    m["fc21"] = nn.Linear(128, 32)
+    m["fc31"] = nn.Linear(32, nb_actions)
+    _xavier_linears(m)
+    out = OrderedDict()
+    for name, mod in m.items():
+        out[name + ".weight"] = mod.weight
+        out[name + ".bias"] = mod.bias
+    return OrderedDict((k, v.detach().clone()) for k, v in out.items())
+
+
 def reference_sac_init(cfg: Cfg, seed: int):
     """Weights as ``SAC.__init__`` creates them (vn/DRL.py:71-78 seeding, :105-106 critic,
     :115-116 critic_target (consumes the generator, then overwritten by hard_update :123),

@@ -171,6 +171,47 @@ def case_modules(G, tag, block, head, lfs, B):
     print(f"[golden] modules_{tag}: ok")
 
 
+def case_qnet(G, B):
+    """CNN twin-Q critic ``QNetwork`` (vn/got_sac_network.py:125-170): init, forward and gradients vs the oracle."""
+    from oracle.init_params import reference_qnet_init
+    cfg = O.Cfg()
+    torch.manual_seed(SEED + 7)
+    ref = G.QNetwork(2, 2)
+    pr = params_of(ref)
+    io = reference_qnet_init(SEED + 7)
+    assert list(io.keys()) == list(pr.keys()), "qnet param order"
+    for k in pr:
+        assert torch.equal(pr[k], io[k]), f"qnet init {k}"
+    batch = synthetic_batch(cfg, B, SEED + 8)
+    img, goal, act = batch["obs"], batch["pobs"], batch["act"]
+    q1, q2 = ref.forward([img, goal, act])
+    w = torch.linspace(0.5, 1.5, B).unsqueeze(1)
+    loss = ((q1 - 0.3) ** 2 * w).mean() + (torch.min(q1, q2) * w).mean()
+    ref.zero_grad()
+    loss.backward()
+    pg = {k: v.clone().requires_grad_(True) for k, v in pr.items()}
+    oq1, oq2 = O.qnet_forward(pg, img, goal, act)
+    oloss = ((oq1 - 0.3) ** 2 * w).mean() + (torch.min(oq1, oq2) * w).mean()
+    oloss.backward()
+    out = {}
+    for n, (r, o) in dict(q1=(q1, oq1), q2=(q2, oq2)).items():
+        e = maxrel(o, r)
+        assert e < 1e-5, ("qnet", n, e)
+        out[n] = r.detach().numpy()
+    for k, rp in ref.named_parameters():
+        e = maxrel(pg[k].grad, rp.grad)
+        assert e < 2e-4, ("qnet grad", k, e)
+    out["loss"] = np.array(float(loss.detach()))
+    out["grad_norms"] = np.array([float(p.grad.double().norm()) for _, p in ref.named_parameters()])
+    out["grad_fc1_bias"] = dict(ref.named_parameters())["fc1.bias"].grad.numpy()
+    out["grad_conv1_weight"] = dict(ref.named_parameters())["conv1.weight"].grad.numpy()
+    names, sm, ab = checksum(pr)
+    out["names"], out["sum"], out["abssum"] = np.array(names), sm, ab
+    out["cfg"] = np.array([B])
+    np.savez_compressed(os.path.join(GOLD, "qnet.npz"), **out)
+    print("[golden] qnet: ok")
+
+
 def case_learn(G, D, tag, block, head, lfs, B, steps=3):
     """Unmodified reference SAC.learn vs SACOracle.learn."""
     cfg = O.Cfg(dim=lfs, depth=block, heads=head)
@@ -348,6 +389,9 @@ def case_depth():
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "qnet":       # regenerate one fixture only
+        G, _ = import_reference()
+        return case_qnet(G, B=4)
     torch.set_num_threads(8)
     G, D = import_reference()
     case_modules(G, "small", block=2, head=2, lfs=32, B=3)
@@ -356,6 +400,7 @@ def main():
     case_learn(G, D, "shipped", block=4, head=4, lfs=64, B=4)
     case_guidence(G, D, "small", block=2, head=2, lfs=32, B=4, Be=4)
     case_depth()
+    case_qnet(G, B=4)
 
 
 if __name__ == "__main__":

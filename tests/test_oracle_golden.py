@@ -132,3 +132,22 @@ def test_learn_guidence_against_golden():
         for nm, d in (("actor", orc.actor), ("critic", orc.critic)):
             a = np.array([float(v.double().abs().sum()) for v in d.values()])
             np.testing.assert_allclose(a, g[f"step{s}_{nm}_abssum"], rtol=2e-4, atol=1e-3)
+
+
+def test_qnet_oracle_against_golden():
+    """CNN twin-Q critic: the oracle restatement vs the outputs recorded from the unmodified reference ``QNetwork``."""
+    from oracle.init_params import reference_qnet_init, synthetic_batch
+    G = golden("qnet.npz")
+    B = int(G["cfg"][0])
+    p = reference_qnet_init(SEED + 7)
+    assert [str(n) for n in G["names"]] == list(p.keys())
+    assert np.allclose([float(v.double().sum()) for v in p.values()], G["sum"], rtol=0, atol=1e-9)
+    batch = synthetic_batch(O.Cfg(), B, SEED + 8)
+    pg = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    q1, q2 = O.qnet_forward(pg, batch["obs"], batch["pobs"], batch["act"])
+    assert relerr(q1.detach(), torch.tensor(G["q1"])) < 1e-5 and relerr(q2.detach(), torch.tensor(G["q2"])) < 1e-5
+    w = torch.linspace(0.5, 1.5, B).unsqueeze(1)
+    loss = ((q1 - 0.3) ** 2 * w).mean() + (torch.min(q1, q2) * w).mean()
+    loss.backward()
+    norms = np.array([float(v.grad.double().norm()) for v in pg.values()])
+    assert np.allclose(norms, G["grad_norms"], rtol=2e-4, atol=1e-9)
