@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .modules import GoTPolicy, GoTQNetwork, set_seed, _stream
+from .modules import GoTPolicy, GoTQNetwork, QNetwork, set_seed, _stream
+from .ops import hard_update, soft_update
 from .parallel import allreduce_sum_
 
 
@@ -107,9 +108,8 @@ class SAC(object):
         if policy_type != "GaussianTransformer":
             raise NotImplementedError(f"policy_type={policy_type!r}: only the DGViT actor ('GaussianTransformer') "
                                       "is on the accelerated path")
-        if critic_type != "Transformer":
-            raise NotImplementedError("critic_type='CNN' (QNetwork) is a 'next' row (SURVEY.md §8 f1); "
-                                      "use critic_type='Transformer'")
+        # any other critic_type selects the CNN twin-Q critic, as in vn/DRL.py:118-121
+        self._cnn_critic = critic_type != "Transformer"
         if policy_attention_fix or critic_attention_fix:
             raise NotImplementedError("attention_fix (frozen trunk) variants are not on the accelerated path")
         if not torch.cuda.is_available():
@@ -141,6 +141,9 @@ class SAC(object):
                                                  self.seed + 1) if pre_buffer else None)    # vn/DRL.py:91-100
         self._gbuf = {}
 
+        if self._cnn_critic:
+            self._init_cnn_critic(action_dim, pstate_dim, block, head, l_f_size, image_size, mlp_dim, ALPHA)
+            return
         # construction order == reference (critic, critic_target, policy): same seed -> same weights
         kw = dict(image_size=image_size, mlp_dim=mlp_dim)
         self.critic = GoTQNetwork(action_dim, pstate_dim, block, head, l_f_size, **kw).to(self.device)
@@ -176,6 +179,73 @@ class SAC(object):
         self._graphs = {}
         for m in (self.critic, self.critic_target, self.policy):
             m.refresh_shadow()
+
+    # ------------------------------------------------------------------ CNN critic (vn/DRL.py:118-121)
+    def _init_cnn_critic(self, action_dim, pstate_dim, block, head, l_f_size, image_size, mlp_dim, ALPHA):
+        """critic_type != "Transformer": the reference's wiring (vn/DRL.py:118-150) on top of the drop-in modules —
+        ``QNetwork`` critic + target, DGViT actor, three ``torch.optim.Adam``.  The update is the reference's
+        ``learn`` statement by statement with autograd as the glue between the library's forward / backward calls
+        (the single-call fused update exists for the Transformer critic only)."""
+        if self.distributed:
+            raise NotImplementedError("data-parallel updates are implemented for critic_type='Transformer'")
+        dev = self.device
+        self.critic = QNetwork(action_dim, pstate_dim, image_size=image_size).to(dev)
+        self.critic_target = QNetwork(action_dim, pstate_dim, image_size=image_size).to(dev)
+        self.target_entropy = -float(action_dim)
+        self.policy = GoTPolicy(action_dim, pstate_dim, block, head, l_f_size, image_size=image_size, mlp_dim=mlp_dim).to(dev)
+        for m in (self.critic, self.critic_target, self.policy):
+            m.precision = self.precision
+            m.bind()
+        hard_update(self.critic_target, self.critic)                                   # vn/DRL.py:123
+        self.critic_optim = torch.optim.Adam(self.critic.parameters(), lr=self.lr_c)    # :113
+        self.policy_optim = torch.optim.Adam(self.policy.parameters(), lr=self.lr_a)    # :150
+        self.log_alpha = torch.zeros(1, requires_grad=True, device=dev)                 # :138
+        self.alpha_optim = torch.optim.Adam([self.log_alpha], lr=self.lr_alpha)         # :139
+        self.target_policy = copy.deepcopy(self.policy)
+        self._batch, self._idx = None, None
+
+    def _learn_cnn(self, batch: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None):
+        """vn/DRL.py:388-434 with the drop-in modules.  ``noise`` (tests): eps_next / eps_pi rsample draws and
+        mask_a_next / mask_a dropout keep-masks of the two actor passes."""
+        import torch.nn.functional as F
+        view = lambda t: t.view(t.shape[0], *self.replay_buffer.obs_shape) if t.dim() == 2 else t
+        s, s2 = view(batch["obs"]), view(batch["next_obs"])
+        ps, ps2, a, r = batch["pobs"], batch["next_pobs"], batch["act"], batch["rew"]
+        nz = noise or {}
+        with torch.no_grad():
+            if noise:
+                self.policy.inject_noise(mask=nz.get("mask_a_next"), eps=nz.get("eps_next"))
+            a2, logp2, _ = self.policy.sample([s2, ps2])
+            q1t, q2t = self.critic_target([s2, ps2, a2])
+            next_q = r + self.gamma * (torch.min(q1t, q2t) - self.alpha * logp2)
+        qf1, qf2 = self.critic([s, ps, a])
+        qf1_loss = F.mse_loss(qf1, next_q)
+        qf_loss = qf1_loss + F.mse_loss(qf2, next_q)
+        self.critic_optim.zero_grad()
+        qf_loss.backward()
+        self.critic_optim.step()
+        if noise:
+            self.policy.inject_noise(mask=nz.get("mask_a"), eps=nz.get("eps_pi"))
+        pi, log_pi, _ = self.policy.sample([s, ps])
+        for p in self.critic.parameters():          # the reference discards these gradients at the next zero_grad
+            p.requires_grad_(False)
+        qf1_pi, qf2_pi = self.critic([s, ps, pi])
+        for p in self.critic.parameters():
+            p.requires_grad_(True)
+        policy_loss = ((self.alpha * log_pi) - torch.min(qf1_pi, qf2_pi)).mean()
+        self.policy_optim.zero_grad()
+        policy_loss.backward()
+        self.policy_optim.step()
+        if self.automatic_entropy_tuning:
+            alpha_loss = -(self.log_alpha * (log_pi + self.target_entropy).detach()).mean()
+            self.alpha_optim.zero_grad()
+            alpha_loss.backward()
+            self.alpha_optim.step()
+            self.alpha = self.log_alpha.exp().detach()
+        if self.itera % self.policy_freq == 0:
+            soft_update(self.critic_target, self.critic, self.tau)
+        self.itera += 1
+        return qf1_loss.detach(), policy_loss.detach()
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -282,6 +352,13 @@ class SAC(object):
 
     def learn(self, batch_size=64):
         """vn/DRL.py:373-437 — returns (qf1_loss, policy_loss) python floats (one D2H read)."""
+        if self._cnn_critic:
+            B = int(batch_size)
+            idx = self.replay_buffer.sample_indexes(B).to(self.device)
+            batch = self._batch_buffers(B)
+            self.replay_buffer.gather(idx, batch)
+            q, p = self._learn_cnn(batch)
+            return float(q), float(p)
         losses = self.learn_async(batch_size)
         l = losses.tolist()
         self.alpha = float(self._alpha.item()) if self.automatic_entropy_tuning else self.alpha
@@ -352,6 +429,8 @@ class SAC(object):
         for the critic / policy losses, plus the guidance (expert rows) and engage (rows with engage == 1)
         imitation losses on the actor's tanh-mean.  All imitation rows ride in the same actor pass as
         extra rows with per-row loss weights, so the update stays one fused call."""
+        if self._cnn_critic:
+            raise NotImplementedError("learn_guidence with the CNN critic: use critic_type='Transformer' or learn()")
         B = int(batch_size)
         rb, re = self.replay_buffer, (self.replay_buffer_expert if self.pre_buffer else None)
         Be = 0
@@ -431,7 +510,8 @@ class SAC(object):
     def load_target(self):
         self.critic_target.bind()
         self.critic_target._arena.copy_(self.critic._arena)
-        self.critic_target.refresh_shadow()
+        if hasattr(self.critic_target, "refresh_shadow"):
+            self.critic_target.refresh_shadow()
 
     def load_actor(self, filename, directory):
         self.policy.load_state_dict(torch.load("%s/%s_actor.pth" % (directory, filename)))
@@ -440,4 +520,5 @@ class SAC(object):
     def _after_load(self):
         for m in (self.critic, self.critic_target, self.policy):
             m.bind()
-            m.refresh_shadow()
+            if hasattr(m, "refresh_shadow"):
+                m.refresh_shadow()

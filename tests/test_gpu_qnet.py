@@ -100,3 +100,64 @@ def test_qnet_module_protocol():
     assert not torch.equal(before, m.fc1.weight) and m._bound()
     dg.soft_update(t, m, 0.5)
     assert torch.allclose(t.fc1.weight, 0.5 * before + 0.5 * m.fc1.weight)
+
+
+def test_sac_learn_with_cnn_critic_matches_reference_style_update():
+    """critic_type != "Transformer" (vn/DRL.py:118-121): two ``learn`` updates of the agent (QNetwork critic + DGViT actor,
+    fp32) against the same statements (vn/DRL.py:388-434) run with autograd on the oracle's functions."""
+    import torch.nn.functional as F
+    from helpers import reference_init
+    from oracle.init_params import synthetic_noise
+    cfg = O.Cfg(dim=32, depth=2, heads=2)
+    B = 5
+    ag = dg.SAC(2, 2, "GaussianTransformer", "CNN", False, False, False, 11, LR_C=1e-3, LR_A=1e-3, LR_ALPHA=1e-4,
+                BUFFER_SIZE=64, TAU=5e-3, POLICY_FREQ=1, GAMMA=0.99, ALPHA=0.2, block=2, head=2, l_f_size=32,
+                precision="fp32")
+    pa, pc = reference_init("actor", cfg, 21), reference_qnet_init(22)
+    ag.policy.load_state_dict(pa); ag.critic.load_state_dict(pc); ag.critic_target.load_state_dict(pc)
+    ag._after_load()
+    ra = {k: v.clone().requires_grad_(True) for k, v in pa.items()}
+    rc = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    rt = {k: v.clone() for k, v in pc.items()}
+    log_alpha = torch.zeros(1, requires_grad=True)
+    opt_c, opt_a = torch.optim.Adam(list(rc.values()), lr=1e-3), torch.optim.Adam(list(ra.values()), lr=1e-3)
+    opt_al = torch.optim.Adam([log_alpha], lr=1e-4)
+    alpha = 0.2
+    for step in range(2):
+        batch, nz = synthetic_batch(cfg, B, 300 + step), synthetic_noise(cfg, B, 400 + step)
+        s, s2, ps, ps2, a, r = (batch[k] for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew"))
+        with torch.no_grad():
+            a2, lp2, _ = O.actor_sample(ra, s2, ps2, nz["eps_next"], cfg, nz["mask_a_next"])
+            q1t, q2t = O.qnet_forward(rt, s2, ps2, a2)
+            nq = r + 0.99 * (torch.min(q1t, q2t) - alpha * lp2)
+        q1, q2 = O.qnet_forward(rc, s, ps, a)
+        l1 = F.mse_loss(q1, nq)
+        lq = l1 + F.mse_loss(q2, nq)
+        opt_c.zero_grad(); lq.backward(); opt_c.step()
+        pi, lp, _ = O.actor_sample(ra, s, ps, nz["eps_pi"], cfg, nz["mask_a"])
+        q1p, q2p = O.qnet_forward(rc, s, ps, pi)
+        lpol = ((alpha * lp) - torch.min(q1p, q2p)).mean()
+        opt_a.zero_grad(); lpol.backward()
+        opt_a.step()
+        lal = -(log_alpha * (lp + (-2.0)).detach()).mean()
+        opt_al.zero_grad(); lal.backward(); opt_al.step()
+        alpha = float(log_alpha.exp())
+        with torch.no_grad():
+            for k in rt:
+                rt[k].mul_(1 - 5e-3).add_(rc[k].detach(), alpha=5e-3)
+        gb = {k: v.cuda() for k, v in batch.items()}
+        qg, pg = ag._learn_cnn(gb, {k: (v.cuda() if v is not None else None) for k, v in nz.items()})
+        assert abs(float(qg) - float(l1)) < 1e-4 * max(1.0, abs(float(l1))), (step, float(qg), float(l1))
+        assert abs(float(pg) - float(lpol)) < 1e-4 * max(1.0, abs(float(lpol))), (step, float(pg), float(lpol))
+        assert abs(float(ag.alpha) - alpha) < 1e-6
+        for k, p in ag.critic.named_parameters():
+            assert float((p.detach().cpu() - rc[k].detach()).abs().max()) < 3e-5 * (step + 1), ("critic", step, k)
+        for k, p in ag.critic_target.named_parameters():
+            assert float((p.detach().cpu() - rt[k]).abs().max()) < 1e-5, ("target", step, k)
+        for k, p in ag.policy.named_parameters():
+            d = (p.detach().cpu() - ra[k].detach()).abs()
+            assert float((d > 3e-5 * (step + 1)).float().mean()) < 5e-3, ("actor", step, k)
+    # the public entry point: replay store -> gather -> update
+    ag.replay_buffer.fill_synthetic(32)
+    q, p = ag.learn(4)
+    assert np.isfinite(q) and np.isfinite(p)
