@@ -379,12 +379,14 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
     launch_k(embed_assemble_kernel, grid1d(tot2), 256, 0, st, c.tok, c.Xp, P + L.pos, c.L[0].Xa, drop, tot2, d.N, d.D);
     DG_LAUNCH_CHECK();
   }
+  bool ln1_done = false;
   for (int l = 0; l < d.L; ++l) {
     const dgvit_block_layout& b = L.block[l];
     LayerBuf<A>& B_ = c.L[l];
     float* Xnext = (l + 1 < d.L) ? c.L[l + 1].Xa : c.Xout;
-    // attention block: x = attn(LN(x)) + x
-    launch_ln_fwd<A>(B_.Xa, P + b.ln1_w, P + b.ln1_b, B_.Xn1, B_.mean1, B_.rstd1, d.T, d.D, st);
+    // attention block: x = attn(LN(x)) + x   (LN already applied by the previous block's fused MLP kernel when ln1_done)
+    if (!ln1_done) launch_ln_fwd<A>(B_.Xa, P + b.ln1_w, P + b.ln1_b, B_.Xn1, B_.mean1, B_.rstd1, d.T, d.D, st);
+    ln1_done = false;
     linear_fwd<A, A, A>(B_.Xn1, WSel<A>::w(net, b.qkv_w), B_.QKV, d.T, 3 * d.inner, d.D, EPI_NONE, nullptr, st);
     launch_attention_fwd<A>(B_.QKV, B_.O, d, st);
     // Only token 0 of the last block's output is consumed (x[:, 0], vn/GoalFormer.py:167): there the
@@ -394,18 +396,43 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
     const int64_t R = last ? d.B : d.T;
     const int64_t ostride = last ? (int64_t)d.N * d.inner : d.inner;
     const int64_t xstride = last ? (int64_t)d.N * d.D : d.D;
-    linear_fwd<A, A, float>(B_.O, WSel<A>::w(net, b.out_w), B_.Xm, R, d.D, d.inner, EPI_BIAS_RESID, P + b.out_b, st,
-                            B_.Xa, nullptr, -1, ostride, xstride);
-    // MLP block: x = ff(LN(x)) + x
-    launch_ln_fwd<A>(B_.Xm, P + b.ln2_w, P + b.ln2_b, B_.Xn2, B_.mean2, B_.rstd2, R, d.D, st);
+    // out-projection + bias + residual, with the MLP block's LayerNorm-2 fused into the GEMM epilogue when the
+    // tensor-core kernel takes it (x = ff(LN(x)) + x, vn/GoalFormer.py:104)
+    bool ln2_done = false;
+#ifdef DGVIT_WITH_TC
+    if constexpr (std::is_same<A, bf16>::value) {
+      GemmArgs g;
+      g.M = (int)R; g.N = d.D; g.K = d.inner;
+      g.A = B_.O; g.a_sm = ostride; g.a_sk = 1;
+      g.B = WSel<A>::w(net, b.out_w); g.b_sk = 1; g.b_sn = d.inner;
+      g.C = B_.Xm; g.ldc = d.D;
+      g.epi = EPI_BIAS_RESID; g.bias = P + b.out_b; g.resid = B_.Xa; g.ldr = xstride;
+      g.ln_gamma = P + b.ln2_w; g.ln_beta = P + b.ln2_b; g.ln_out = B_.Xn2; g.ln_mean = B_.mean2; g.ln_rstd = B_.rstd2;
+      ProfScope ps_all(PROF_GEMM_ALL, 2.0 * g.M * g.N * g.K, 0.0, st);
+      ln2_done = gemm_tc_try<A, A, float>(g, st);
+    }
+#endif
+    if (!ln2_done) {
+      linear_fwd<A, A, float>(B_.O, WSel<A>::w(net, b.out_w), B_.Xm, R, d.D, d.inner, EPI_BIAS_RESID, P + b.out_b, st,
+                              B_.Xa, nullptr, -1, ostride, xstride);
+      // MLP block: x = ff(LN(x)) + x
+      launch_ln_fwd<A>(B_.Xm, P + b.ln2_w, P + b.ln2_b, B_.Xn2, B_.mean2, B_.rstd2, R, d.D, st);
+    }
     TagScope mlp_tag(PROF_GEMM_MLP);
     if (mlp_fused<A>(d, R, B_.Xn2, WSel<A>::w(net, b.fc1_w), WSel<A>::w(net, b.fc2_w), B_.Xm, Xnext)) {
 #ifdef DGVIT_WITH_TC
       if constexpr (std::is_same<A, bf16>::value) {
         ProfScope ps(PROF_GEMM_MLP, 4.0 * R * d.D * d.M, 0.0, st);
         ProfScope ps2(PROF_MLP_FUSED, 4.0 * R * d.D * d.M, 0.0, st);
+        mlp::LnFuse ln;
+        if (!last) {   // the next block's LayerNorm-1 rides in this kernel's output stage
+          const dgvit_block_layout& nb = L.block[l + 1];
+          LayerBuf<A>& N_ = c.L[l + 1];
+          ln.gamma = P + nb.ln1_w; ln.beta = P + nb.ln1_b; ln.out = (bf16*)N_.Xn1; ln.mean = N_.mean1; ln.rstd = N_.rstd1;
+          ln1_done = true;
+        }
         mlp::fwd(B_.Xn2, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), P + b.fc2_b, B_.Xm, d.D, Xnext,
-                 d.D, R, d.M, st);
+                 d.D, R, d.M, st, ln);
       }
 #endif
     } else {

@@ -37,6 +37,9 @@ struct GemmArgs {
   int64_t ldaux = 0;
   int splitk = 1;
   float* partial = nullptr;  // [splitk, M, N]
+  // optional LayerNorm of the output rows fused into the epilogue (tensor-core kernel only, N == 64, EPI_BIAS_RESID)
+  const float* ln_gamma = nullptr; const float* ln_beta = nullptr;
+  void* ln_out = nullptr; float* ln_mean = nullptr; float* ln_rstd = nullptr;
 };
 
 constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_PAD = 4;

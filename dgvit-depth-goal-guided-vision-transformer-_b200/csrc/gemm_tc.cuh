@@ -168,6 +168,7 @@ struct TcArgs {
   const float* bias; const float* resid; int64_t ldr;
   const void* aux; int64_t ldaux;
   float* partial;
+  const float* ln_gamma; const float* ln_beta; bf16* ln_out; float* ln_mean; float* ln_rstd;   // fused LayerNorm (BN == 64)
 };
 
 template <int BN>
@@ -567,6 +568,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else if (row_ok) {
           store_row32<TC>(Cb + (int64_t)row * g.ldc + col, v, nvalid);
         }
+        if constexpr (std::is_same<TC, float>::value && BN == 64) {
+          if (g.ln_gamma) {
+            // LayerNorm over the 64 output columns of a row (PreNorm of the following block, vn/GoalFormer.py:31-37):
+            // this warp holds 32 of them, the other column group's warp of the same lane quadrant the rest;
+            // two-pass statistics exchanged through shared memory
+            float* part = reinterpret_cast<float*>(smem + SL::TILES_BYTES + SL::BAR_BYTES);   // [128][2]
+            const int r = quad * 32 + lane;
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s += v[i];
+            part[r * 2 + grp] = s;
+            named_bar_sync(1 + quad, 64);
+            const float mu = (part[r * 2] + part[r * 2 + 1]) * (1.0f / 64.0f);
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float c = v[i] - mu; q = fmaf(c, c, q); }
+            named_bar_sync(1 + quad, 64);
+            part[r * 2 + grp] = q;
+            named_bar_sync(1 + quad, 64);
+            const float rs = 1.0f / sqrtf((part[r * 2] + part[r * 2 + 1]) * (1.0f / 64.0f) + 1e-5f);
+            named_bar_sync(1 + quad, 64);                 // table free for the next tile
+            if (row_ok) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(g.ln_gamma + col) + i);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.ln_beta + col) + i);
+                v[4 * i] = (v[4 * i] - mu) * rs * g4.x + b4.x; v[4 * i + 1] = (v[4 * i + 1] - mu) * rs * g4.y + b4.y;
+                v[4 * i + 2] = (v[4 * i + 2] - mu) * rs * g4.z + b4.z; v[4 * i + 3] = (v[4 * i + 3] - mu) * rs * g4.w + b4.w;
+              }
+              store_row32<bf16>(g.ln_out + (int64_t)row * 64 + col, v, 32);
+              if (grp == 0 && g.ln_mean) { g.ln_mean[row] = mu; g.ln_rstd[row] = rs; }
+            }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -687,6 +722,9 @@ static bool gemm_tc_try(const GemmArgs& g0, cudaStream_t st) {
     const int64_t lda = a_mn ? g.a_sk : g.a_sm, ldb = b_mn ? g.b_sk : g.b_sn;
     if (lda % 8 || ldb % 8 || ((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15)) return false;   // TMA: 16-B strides
     if (g.splitk > 1 && g.epi != EPI_NONE) return false;
+    if (g.ln_gamma && !(std::is_same<TC, float>::value && g.N == 64 && g.epi == EPI_BIAS_RESID && g.splitk == 1 && !trans_out &&
+                        g.ln_beta && g.ln_out && (((uintptr_t)g.ln_out) & 15) == 0))
+      return false;
     if (trans_out && !std::is_same<TC, float>::value) return false;
     int bn = g.N >= 256 ? 256 : (g.N >= 128 ? 128 : 64);
     if (g.N % 8) return false;
@@ -699,6 +737,7 @@ static bool gemm_tc_try(const GemmArgs& g0, cudaStream_t st) {
     a.splitk = g.splitk; a.trans_out = trans_out; a.epi = g.epi;
     a.C = g.C; a.C2 = g.C2; a.ldc = g.ldc; a.bias = g.bias; a.resid = g.resid; a.ldr = g.ldr;
     a.aux = g.aux; a.ldaux = g.ldaux; a.partial = g.partial;
+    a.ln_gamma = g.ln_gamma; a.ln_beta = g.ln_beta; a.ln_out = (bf16*)g.ln_out; a.ln_mean = g.ln_mean; a.ln_rstd = g.ln_rstd;
     // split-K must not leave an empty split (its accumulator would be undefined)
     const int kb_total = (int)cdiv(g.K, BK);
     if (a.splitk > kb_total) a.splitk = kb_total;

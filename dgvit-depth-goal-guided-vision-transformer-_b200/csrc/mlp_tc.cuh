@@ -125,7 +125,8 @@ constexpr int OFF_W2 = OFF_W1 + NST * W_BYTES;
 constexpr int OFF_H = OFF_W2 + NST * W_BYTES;
 constexpr int OFF_BIAS = OFF_H + 2 * H_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + MAX_HID * 2;
-constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
+constexpr int OFF_LN = OFF_BAR + 256;          // [128 rows][4 column groups] partial sums of the fused LayerNorm
+constexpr int SMEM_TOTAL = OFF_LN + 2048 + 1024;
 static_assert(SMEM_TOTAL <= 232448, "smem budget");
 }  // namespace f
 
@@ -142,6 +143,9 @@ struct MlpArgs {
   const float* b1; const float* b2;
   const float* resid; int64_t ldr;
   float* out; int64_t ldc;
+  // optional fused LayerNorm of the output rows (the next block's PreNorm, vn/GoalFormer.py:31-37,103):
+  const float* ln_gamma; const float* ln_beta;   // null = off
+  bf16* ln_out; float* ln_mean; float* ln_rstd;  // [M,64] bf16, [M], [M]
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -316,11 +320,47 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     float y[16];
     tmem_ld16(tmem_base + 256 + grp * 16 + lane_off, y);
     if (row < a.M) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        y[4 * i] += b4[i].x + r4[i].x; y[4 * i + 1] += b4[i].y + r4[i].y;
+        y[4 * i + 2] += b4[i].z + r4[i].z; y[4 * i + 3] += b4[i].w + r4[i].w;
+      }
       float* O = a.out + (int64_t)row * a.ldc + grp * 16;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        reinterpret_cast<float4*>(O)[i] = make_float4(y[4 * i] + b4[i].x + r4[i].x, y[4 * i + 1] + b4[i].y + r4[i].y,
-                                                      y[4 * i + 2] + b4[i].z + r4[i].z, y[4 * i + 3] + b4[i].w + r4[i].w);
+      for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(O)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    }
+    if (a.ln_gamma) {
+      // LayerNorm over the 64 columns of a row = this thread's 16 + three other warps' (same quadrant, other groups):
+      // two-pass statistics through a [128][4] table in shared memory
+      float* part = reinterpret_cast<float*>(smem + OFF_LN);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s += y[i];
+      part[r * 4 + grp] = s;
+      epi_bar_sync();
+      const float4 p4 = *reinterpret_cast<const float4*>(part + r * 4);
+      const float mu = ((p4.x + p4.y) + (p4.z + p4.w)) * (1.0f / 64.0f);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { const float c = y[i] - mu; q = fmaf(c, c, q); }
+      epi_bar_sync();                                   // everyone has read the sums
+      part[r * 4 + grp] = q;
+      epi_bar_sync();
+      const float4 q4 = *reinterpret_cast<const float4*>(part + r * 4);
+      const float rs = 1.0f / sqrtf(((q4.x + q4.y) + (q4.z + q4.w)) * (1.0f / 64.0f) + 1e-5f);
+      if (row < a.M) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = grp * 16 + 2 * i;
+          const float2 g2 = __ldg(reinterpret_cast<const float2*>(a.ln_gamma + c)), b2 = __ldg(reinterpret_cast<const float2*>(a.ln_beta + c));
+          w[i] = pack_bf2((y[2 * i] - mu) * rs * g2.x + b2.x, (y[2 * i + 1] - mu) * rs * g2.y + b2.y);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(a.ln_out + (int64_t)row * 64 + grp * 16);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        if (grp == 0 && a.ln_mean) { a.ln_mean[row] = mu; a.ln_rstd[row] = rs; }
+      }
     }
   }
   if (warp == 2) MLP_TRACE(12, 6);
@@ -605,9 +645,15 @@ static bool eligible(int D, int HID, int64_t M, const void* x, const void* w1, c
          ldr % 4 == 0 && ldc % 4 == 0;
 }
 
+struct LnFuse {   // LayerNorm of the output rows, fused into the forward's last stage (all null = off)
+  const float* gamma = nullptr; const float* beta = nullptr;
+  bf16* out = nullptr; float* mean = nullptr; float* rstd = nullptr;
+};
 static void fwd(const bf16* x, const bf16* W1, const float* b1, const bf16* W2, const float* b2, const float* resid,
-                int64_t ldr, float* out, int64_t ldc, int64_t M, int HID, cudaStream_t st) {
+                int64_t ldr, float* out, int64_t ldc, int64_t M, int HID, cudaStream_t st, const LnFuse& ln = LnFuse()) {
   MlpArgs a;
+  a.ln_gamma = ln.gamma; a.ln_beta = ln.beta; a.ln_out = ln.out; a.ln_mean = ln.mean; a.ln_rstd = ln.rstd;
+  DG_REQUIRE(!ln.gamma || (ln.beta && ln.out && (((uintptr_t)ln.out) & 15) == 0), "mlp::fwd: fused LayerNorm needs beta and an aligned output");
   a.trace = g_trace;
   a.M = (int)M; a.HID = HID; a.b1 = b1; a.b2 = b2; a.resid = resid; a.ldr = ldr; a.out = out; a.ldc = ldc;
   CUtensorMap tx = make_map(x, 64, M, 64, 64, 128);
