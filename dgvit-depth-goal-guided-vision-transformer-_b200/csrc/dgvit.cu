@@ -148,10 +148,12 @@ static void linear_bwd_x(const TA* dy, const TB* W, TC* dx, int64_t R, int N, in
 // dW[N,K] = dy[R,N]^T x[R,K]   (split-K over R, deterministic) ; db[N] = colsum(dy)
 template <typename TA, typename TB>
 static void linear_bwd_w(const TA* dy, const TB* x, float* dW, float* db, int64_t R, int N, int K,
-                         float* partial, cudaStream_t st, int64_t ldy = -1, int64_t ldx = -1) {
+                         float* partial, cudaStream_t st, int64_t ldy = -1, int64_t ldx = -1, ReduceList* defer = nullptr) {
   if (ldy < 0) ldy = N;
   if (ldx < 0) ldx = K;
+  if (defer) partial = defer->alloc((size_t)pick_splitk(R) * N * K);
   GemmArgs g;
+  g.defer = defer;
   g.M = N; g.N = K; g.K = (int)R;
   g.A = dy; g.a_sm = 1; g.a_sk = ldy;
   g.B = x; g.b_sk = ldx; g.b_sn = 1;
@@ -162,10 +164,15 @@ static void linear_bwd_w(const TA* dy, const TB* x, float* dW, float* db, int64_
     const int S = (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 128);   // row ranges per column block
     const int64_t rpb = cdiv(R, S);
     dim3 grid((unsigned)cdiv(N, 256), (unsigned)S);
+    if (defer) partial = defer->alloc((size_t)S * N);      // the GEMM's partials may still be queued
     launch_k(colsum_partial_kernel<TA>, grid, 128, 0, st, dy, ldy, partial, R, N, rpb);
     DG_LAUNCH_CHECK();
-    launch_k(reduce_partials_kernel, reduce_grid(N), 256, 0, st, partial, db, S, N);
-    DG_LAUNCH_CHECK();
+    if (defer && N % 4 == 0) {
+      defer->add(partial, db, S, N, N);
+    } else {
+      launch_k(reduce_partials_kernel, reduce_grid(N), 256, 0, st, partial, db, S, N);
+      DG_LAUNCH_CHECK();
+    }
   }
 }
 
@@ -254,7 +261,9 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
     mx = std::max<int64_t>(mx, (int64_t)d.D * d.pd);
     mx = std::max<int64_t>(mx, (int64_t)128 * 128);
     mx = std::max<int64_t>(mx, (int64_t)3 * d.D * 148 * 4 / 32 + 3 * d.D);
-    c.partial_floats = (size_t)mx * 32;
+    // one block's worth of queued reductions (split-K dW of qkv / out / both MLP matrices + LayerNorm partials)
+    const int64_t per_block = (int64_t)32 * (4 * d.inner * d.D + 2 * d.D * d.M) + (int64_t)8 * d.D * 148 * 4 + 4 * d.M + 4096;
+    c.partial_floats = (size_t)std::max<int64_t>(mx * 32, per_block);
     c.partial = cv.take<float>(c.partial_floats);
   }
 }
@@ -289,9 +298,10 @@ static void launch_ln_fwd(const float* X, const float* g, const float* b, A* Y, 
 // dxsum (optional): receives colsum over rows of the updated dX_io (a bias gradient, see layernorm_bwd_kernel)
 static void launch_ln_bwd(const float* dY, const float* X, const float* mean, const float* rstd,
                           const float* gamma, float* dX_io, bf16* dX_lp, float* dgamma, float* dbeta, float* dxsum,
-                          float* partial, int64_t T, int D, cudaStream_t st) {
+                          float* partial, int64_t T, int D, cudaStream_t st, ReduceList* defer = nullptr) {
   const int wpb = 8;
   int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 4);
+  if (defer && D % 4 == 0) partial = defer->alloc((size_t)nblocks * 3 * D); else defer = nullptr;
   const size_t smem = (size_t)wpb * 3 * D * sizeof(float);
   switch (D / 32) {
 #define LNB(V) case V: launch_k(layernorm_bwd_kernel<V>, nblocks, wpb * 32, smem, st, dY, X, mean, rstd, gamma, dX_io, dX_lp, partial, T); break;
@@ -300,6 +310,12 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
     default: fail(DGVIT_ERR_ARG, "unsupported dim %d", D);
   }
   DG_LAUNCH_CHECK();
+  if (defer) {
+    defer->add(partial, dgamma, nblocks, D, 3 * D);
+    defer->add(partial + D, dbeta, nblocks, D, 3 * D);
+    if (dxsum) defer->add(partial + 2 * D, dxsum, nblocks, D, 3 * D);
+    return;
+  }
   launch_k(ln_param_reduce_kernel, (unsigned)cdiv(3 * D, 32), 1024, 0, st, partial, dgamma, dbeta, dxsum, nblocks, D);
   DG_LAUNCH_CHECK();
 }
@@ -475,6 +491,8 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     float* dXr = last ? c.dXc : c.dX;                  // fp32 residual-stream gradient of these rows
     bf16* dXr_lp = last ? c.dXch : c.dXh;
     const A* dxop = last ? c.dxc_op() : c.dx_op();
+    // every partial-sum reduction of this block is queued here and done by one launch at the end of the block
+    ReduceList rl(c.partial, c.partial_floats);
     // ---- MLP block.  dXr = dL/dX_out
     {
     TagScope mlp_tag(PROF_GEMM_MLP);
@@ -488,7 +506,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
         ProfScope ps(PROF_GEMM_MLP, 8.0 * R * d.D * d.M, 0.0, st);
         // net.3.bias gradient = colsum(dL/dX_out): below the top block it falls out of the next block's LayerNorm-1 backward
         mlp::bwd(B_.Xn2, dxop, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), c.dXn, G + b.fc1_w,
-                 G + b.fc1_b, G + b.fc2_w, last ? G + b.fc2_b : nullptr, c.partial, R, d.M, st);
+                 G + b.fc1_b, G + b.fc2_w, last ? G + b.fc2_b : nullptr, c.partial, R, d.M, st, &rl);
       }
     }
 #else
@@ -509,14 +527,14 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     }
     // dXr becomes dL/dX_m, whose column sums are the to_out.0.bias gradient
     launch_ln_bwd(c.dXn, B_.Xm, B_.mean2, B_.rstd2, P + b.ln2_w, dXr, dXr_lp, G + b.ln2_w, G + b.ln2_b, G + b.out_b,
-                  c.partial, R, d.D, st);
+                  c.partial, R, d.D, st, &rl);
     // ---- attention block.  dXr = dL/dX_m
     if (!last) {
-      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, nullptr, d.T, d.D, d.inner, c.partial, st);
+      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, nullptr, d.T, d.D, d.inner, c.partial, st, -1, -1, &rl);
       linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.out_w), c.dO, d.T, d.D, d.inner, EPI_NONE, nullptr, 0, st);
     } else {
       const int64_t ostride = (int64_t)d.N * d.inner;
-      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, nullptr, d.B, d.D, d.inner, c.partial, st, -1, ostride);
+      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, nullptr, d.B, d.D, d.inner, c.partial, st, -1, ostride, &rl);
       // dO is zero except on the token-0 rows
       DG_CUDA(cudaMemsetAsync(c.dO, 0, (size_t)d.T * d.inner * sizeof(A), st));
       linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.out_w), c.dO, d.B, d.D, d.inner, EPI_NONE, nullptr, 0, st, -1,
@@ -527,11 +545,12 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
       DG_LAUNCH_CHECK();
     }
     launch_attention_bwd<A>(B_.QKV, B_.O, c.dO, c.dQKV, d, st);
-    linear_bwd_w<A, A>(c.dQKV, B_.Xn1, G + b.qkv_w, nullptr, d.T, 3 * d.inner, d.D, c.partial, st);
+    linear_bwd_w<A, A>(c.dQKV, B_.Xn1, G + b.qkv_w, nullptr, d.T, 3 * d.inner, d.D, c.partial, st, -1, -1, &rl);
     linear_bwd_x<A, A, float>(c.dQKV, WSel<A>::w(net, b.qkv_w), c.dXn, d.T, 3 * d.inner, d.D, EPI_NONE, nullptr, 0, st);
     // c.dX becomes dL/dX_a = gradient of the previous block's output: its column sums are that block's net.3.bias gradient
     launch_ln_bwd(c.dXn, B_.Xa, B_.mean1, B_.rstd1, P + b.ln1_w, c.dX, c.dXh, G + b.ln1_w, G + b.ln1_b,
-                  l > 0 ? G + L.block[l - 1].fc2_b : nullptr, c.partial, d.T, d.D, st);
+                  l > 0 ? G + L.block[l - 1].fc2_b : nullptr, c.partial, d.T, d.D, st, &rl);
+    rl.launch(st);
   }
   // ---- embedding.  c.dX = dL/dX0 (post-dropout)
   const int64_t tot = d.T * d.D;

@@ -40,6 +40,7 @@ struct GemmArgs {
   // optional LayerNorm of the output rows fused into the epilogue (tensor-core kernel only, N == 64, EPI_BIAS_RESID)
   const float* ln_gamma = nullptr; const float* ln_beta = nullptr;
   void* ln_out = nullptr; float* ln_mean = nullptr; float* ln_rstd = nullptr;
+  struct ReduceList* defer = nullptr;   // split-K: queue the reduction instead of launching it (tensor-core kernel)
 };
 
 constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_PAD = 4;
@@ -183,6 +184,82 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, float*
   }
 }
 static inline unsigned reduce_grid(int64_t n) { return (unsigned)cdiv(cdiv(n, 4), 256); }
+
+// Several partial-sum reductions in one launch: out_j[i] = sum_k part_j[k * stride_j + i].  The backward of a
+// transformer block produces five to ten of them (split-K weight gradients, LayerNorm parameter / bias partials);
+// each is a few microseconds of pure latency as its own kernel.  Block = 16 warps x 128 consecutive floats of one
+// job: warp w sums the partial rows k = w, w+16, ..., the 16 warp sums are added in a fixed order.
+struct ReduceJob {
+  const float* part; float* out;
+  int S, n; int64_t stride; int blk0;
+};
+struct ReduceJobs {
+  ReduceJob job[12];
+  int njobs;
+};
+constexpr int MR_WARPS = 16;
+__global__ void __launch_bounds__(MR_WARPS * 32) multi_reduce_kernel(ReduceJobs a) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float4 sm[MR_WARPS][32];
+  int ji = 0;
+  while (ji + 1 < a.njobs && (int)blockIdx.x >= a.job[ji + 1].blk0) ++ji;
+  const ReduceJob& j = a.job[ji];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t e = ((int64_t)((int)blockIdx.x - j.blk0) * 32 + lane) * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e < j.n) {
+    const float* p = j.part + e;
+    int k = w;
+    for (; k + 3 * MR_WARPS < j.S; k += 4 * MR_WARPS) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + (int64_t)k * j.stride));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(k + MR_WARPS) * j.stride));
+      const float4 v2 = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(k + 2 * MR_WARPS) * j.stride));
+      const float4 v3 = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(k + 3 * MR_WARPS) * j.stride));
+      s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y);
+      s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; k < j.S; k += MR_WARPS) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p + (int64_t)k * j.stride));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  sm[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && e < j.n) {
+    float4 t = sm[0][lane];
+#pragma unroll
+    for (int ww = 1; ww < MR_WARPS; ++ww) { const float4 v = sm[ww][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    *reinterpret_cast<float4*>(j.out + e) = t;
+  }
+}
+// host side: a bump allocator over the partial-sum workspace plus the job table
+struct ReduceList {
+  ReduceJobs a;
+  float* base; size_t cap, used; int blocks;
+  ReduceList(float* b, size_t cap_) : base(b), cap(cap_), used(0), blocks(0) { a.njobs = 0; }
+  float* alloc(size_t n) {
+    n = (n + 3) & ~size_t(3);
+    DG_REQUIRE(used + n <= cap, "reduction workspace too small: need %zu floats, have %zu", used + n, cap);
+    float* p = base + used;
+    used += n;
+    return p;
+  }
+  void add(const float* part, float* out, int S, int64_t n, int64_t stride) {
+    DG_REQUIRE(a.njobs < 12 && n % 4 == 0 && stride % 4 == 0 && ((((uintptr_t)part) | ((uintptr_t)out)) & 15) == 0,
+               "multi_reduce: job table full or unaligned job");
+    ReduceJob& j = a.job[a.njobs++];
+    j.part = part; j.out = out; j.S = S; j.n = (int)n; j.stride = stride; j.blk0 = blocks;
+    blocks += (int)cdiv(n, 128);
+  }
+  void launch(cudaStream_t st) {
+    if (a.njobs) {
+      launch_k(multi_reduce_kernel, blocks, MR_WARPS * 32, 0, st, a);
+      DG_LAUNCH_CHECK();
+    }
+    a.njobs = 0; blocks = 0; used = 0;
+  }
+};
 
 template <typename TA, typename TB, typename TC>
 static void gemm_simt(const GemmArgs& g, cudaStream_t st) {

@@ -754,8 +754,12 @@ static bool gemm_tc_try(const GemmArgs& g0, cudaStream_t st) {
     if (a.splitk > 1) {
       const int64_t n = (int64_t)g0.M * g0.N;
       DG_REQUIRE(g0.ldc == g0.N, "gemm_tc: split-K output must be dense");
-      launch_k(reduce_partials_kernel, reduce_grid(n), 256, 0, st, g.partial, (float*)g0.C, a.splitk, n);
-      DG_LAUNCH_CHECK();
+      if (g0.defer && n % 4 == 0) {
+        g0.defer->add(g.partial, (float*)g0.C, a.splitk, n, n);
+      } else {
+        launch_k(reduce_partials_kernel, reduce_grid(n), 256, 0, st, g.partial, (float*)g0.C, a.splitk, n);
+        DG_LAUNCH_CHECK();
+      }
     }
     return true;
   }

@@ -684,7 +684,9 @@ static size_t bwd_partial_floats(int64_t M, int HID) {
 // dXn[M,64] = d/dx ; dW1 [HID,64], db1 [HID], dW2 [64,HID], db2 [64] (fp32, overwritten; db2 may be null = not wanted).
 // dW1 / db1 / dW2 must be adjacent in that order (the parameter arena's order) so that one pass reduces all three.
 static void bwd(const bf16* x, const bf16* dy, const bf16* W1, const float* b1, const bf16* W2, float* dXn, float* dW1,
-                float* db1, float* dW2, float* db2, float* partial, int64_t M, int HID, cudaStream_t st) {
+                float* db1, float* dW2, float* db2, float* partial, int64_t M, int HID, cudaStream_t st,
+                ReduceList* defer = nullptr) {
+  if (defer) partial = defer->alloc(bwd_partial_floats(M, HID));
   DG_REQUIRE(db1 == dW1 + (int64_t)HID * 64 && dW2 == db1 + HID, "mlp::bwd: dW1 | db1 | dW2 must be contiguous");
   const int tiles = (int)cdiv(M, 128), NC = HID / HC;
   const int S = bwd_splits(M, HID);
@@ -709,6 +711,11 @@ static void bwd(const bf16* x, const bf16* dy, const bf16* W1, const float* b1, 
   DG_LAUNCH_CHECK();
   launch_k(mlp_bwd_tc_kernel<1>, NC * S, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
   DG_LAUNCH_CHECK();
+  if (defer) {       // the caller reduces these together with the block's other partial sums
+    defer->add(partial, dW1, S, per_split, per_split);
+    if (db2) defer->add(a.db2_part, db2, tiles, 64, 64);
+    return;
+  }
   launch_k(reduce_partials_kernel, reduce_grid(per_split), 256, 0, st, (const float*)partial, dW1, S, per_split);
   DG_LAUNCH_CHECK();
   if (db2) {
