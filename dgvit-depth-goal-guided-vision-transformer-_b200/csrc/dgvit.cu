@@ -1031,6 +1031,7 @@ int dgvit_set_option(const char* name, int value) {
 #ifdef DGVIT_WITH_TC
     else if (!strcmp(name, "tensor_cores")) tc::g_tc_enabled = value != 0;
     else if (!strcmp(name, "debug_epilogue")) tc::g_debug = value;
+    else if (!strcmp(name, "mlp_split")) mlp::g_split_enabled = value != 0;
 #endif
     else fail(DGVIT_ERR_ARG, "unknown option %s", name);
   });

@@ -707,14 +707,16 @@ static bool gemm_tc_try(const GemmArgs& g0, cudaStream_t st) {
     int trans_out = 0;
     // weight-gradient shapes with a narrow output (e.g. dW2 [64, 2048]): compute C^T so that the
     // wide dimension rides on UMMA M = 128
-    if (g.M < 128 && g.N >= 128 && g.epi == EPI_NONE) {
+    if (g.M < 128 && g.N >= 128 && g.epi == EPI_NONE && std::is_same<TC, float>::value) {
       std::swap(g.M, g.N);
       const void* a = g.A; int64_t a_sm = g.a_sm, a_sk = g.a_sk;
       g.A = g.B; g.a_sm = g.b_sn; g.a_sk = g.b_sk;
       g.B = a; g.b_sk = a_sk; g.b_sn = a_sm;
       trans_out = 1;
     }
-    if (g.M < 32 || g.K < 16) return false;                // tiny head-sized problems stay on CUDA cores
+    // tiny head-sized contractions stay on CUDA cores; a short M with a real K / N (batch-1 act, the pruned last
+    // block) is one mostly-empty UMMA tile, still several times faster than the serial CUDA-core K loop
+    if (g.K < 64 || g.N < 64 || g.M < 1) return false;
     const bool a_mn = (g.a_sm == 1 && g.a_sk != 1), b_mn = (g.b_sn == 1 && g.b_sk != 1);
     const bool a_k = (g.a_sk == 1), b_k = (g.b_sk == 1);
     if (!(a_mn || a_k) || !(b_mn || b_k)) return false;

@@ -105,25 +105,54 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+template <int NWARPS = EPI_WARPS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NWARPS * 32) : "memory"); }
 
 // fp32 bias -> f16 copy in shared memory (epilogue threads only), then a barrier among them
+template <int NWARPS = EPI_WARPS>
 __device__ __forceinline__ void stage_bias(const float* b, __half* dst, int n, int tid) {
-  for (int i = tid * 2; i < n; i += EPI_WARPS * 32 * 2)
+  for (int i = tid * 2; i < n; i += NWARPS * 32 * 2)
     *reinterpret_cast<__half2*>(dst + i) = __floats2half2_rn(__ldg(b + i), __ldg(b + i + 1));
-  epi_bar_sync();
+  epi_bar_sync<NWARPS>();
+}
+
+// thread-block-cluster helpers (split-hidden forward)
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, int cta_rank) {
+  uint32_t r;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t addr) {
+  float2 v;
+  asm("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  // not volatile / no memory clobber: the caller orders it after cluster_sync(), and independent loads must overlap
+  // (a distributed-shared-memory load is ~750 cycles)
+  asm("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 
 // =====================================================================================
 // forward
 // =====================================================================================
 namespace f {
+constexpr int NSPLIT = 8;          // CTAs per token tile in the split-hidden variant (one cluster)
 constexpr int NST = 3;             // weight ring depth
+constexpr int NG = 2;              // epilogue groups = accumulator / H buffers in flight (3 measured slower: 30.7 vs 28.7 us)
+constexpr int GW = 8;              // warps per group (2 per TMEM lane quadrant, 64 chunk columns each)
+constexpr int FWD_EPI_WARPS = NG * GW;
+constexpr int FWD_THREADS = 64 + FWD_EPI_WARPS * 32;
 constexpr int X_BYTES = TILE16, W_BYTES = TILE16, H_BYTES = 2 * TILE16;
 constexpr int OFF_W1 = X_BYTES;
 constexpr int OFF_W2 = OFF_W1 + NST * W_BYTES;
 constexpr int OFF_H = OFF_W2 + NST * W_BYTES;
-constexpr int OFF_BIAS = OFF_H + 2 * H_BYTES;
+constexpr int OFF_BIAS = OFF_H + NG * H_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + MAX_HID * 2;
 constexpr int OFF_LN = OFF_BAR + 256;          // [128 rows][4 column groups] partial sums of the fused LayerNorm
 constexpr int SMEM_TOTAL = OFF_LN + 2048 + 1024;
@@ -148,7 +177,10 @@ struct MlpArgs {
   bf16* ln_out; float* ln_mean; float* ln_rstd;  // [M,64] bf16, [M], [M]
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
+// SPLIT: few token tiles (the pruned last block, batch-1 act): a cluster of NSPLIT CTAs shares one tile, each taking
+// HID / NSPLIT hidden columns; the partial outputs meet in CTA 0 of the cluster through distributed shared memory.
+template <bool SPLIT>
+__global__ void __launch_bounds__(f::FWD_THREADS, 1)
 mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const MlpArgs a) {
   using namespace f;
@@ -160,24 +192,26 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* w1_empty = w1_full + NST;      // NST
   uint64_t* w2_full = w1_empty + NST;      // NST
   uint64_t* w2_empty = w2_full + NST;      // NST
-  uint64_t* acc_full = w2_empty + NST;     // 2
-  uint64_t* acc_free = acc_full + 2;       // 2 (8 warps each)
-  uint64_t* h_ready = acc_free + 2;        // 2 (8 warps each)
-  uint64_t* h_free = h_ready + 2;          // 2
-  uint64_t* y_full = h_free + 2;           // 1
+  uint64_t* acc_full = w2_empty + NST;     // NG
+  uint64_t* acc_free = acc_full + NG;      // NG (8 warps each)
+  uint64_t* h_ready = acc_free + NG;       // NG (8 warps each)
+  uint64_t* h_free = h_ready + NG;         // NG
+  uint64_t* y_full = h_free + NG;          // 1
   uint32_t* tmem_slot = (uint32_t*)(y_full + 1);
   __half* bias_s = (__half*)(smem + OFF_BIAS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x;
-  const int NC = a.HID / HC;
+  const int mt = SPLIT ? blockIdx.x / NSPLIT : blockIdx.x;
+  const int rank = SPLIT ? blockIdx.x % NSPLIT : 0;                 // == %cluster_ctarank (cluster = NSPLIT CTAs along x)
+  const int NC = SPLIT ? a.HID / HC / NSPLIT : a.HID / HC;          // chunks of this CTA
+  const int cbase = rank * NC;                                      // first hidden chunk of this CTA
   if (warp == 2) MLP_TRACE(12, 0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     mbar_init(x_full, 1);
     for (int i = 0; i < NST; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], EPI_WARPS / 2); mbar_init(&h_ready[i], EPI_WARPS / 2); mbar_init(&h_free[i], 1); }
+    for (int i = 0; i < NG; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], GW); mbar_init(&h_ready[i], GW); mbar_init(&h_free[i], 1); }
     mbar_init(y_full, 1);
     fence_barrier_init();
   }
@@ -185,7 +219,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;     // acc1: cols [0,256) ; Y: cols [256,320)
+  const uint32_t tmem_base = *tmem_slot;     // accumulators: cols [0, NG*128) ; Y: cols [NG*128, NG*128+64)
+  constexpr uint32_t T_Y = NG * HC;
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
   if (warp == 2) MLP_TRACE(12, 1);
   pdl_wait();
@@ -200,11 +235,11 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int s = c % NST; const uint32_t ph = (c / NST) & 1;
         mbar_wait(&w1_empty[s], ph ^ 1);
         mbar_expect_tx(&w1_full[s], W_BYTES);
-        tma_load_2d(smem + OFF_W1 + s * W_BYTES, &tmW1, &w1_full[s], 0, c * HC);          // [128 hidden rows][64 k]
+        tma_load_2d(smem + OFF_W1 + s * W_BYTES, &tmW1, &w1_full[s], 0, (cbase + c) * HC);          // [128 hidden rows][64 k]
         mbar_wait(&w2_empty[s], ph ^ 1);
         mbar_expect_tx(&w2_full[s], W_BYTES);
-        tma_load_2d(smem + OFF_W2 + s * W_BYTES, &tmW2, &w2_full[s], c * HC, 0);          // [64 d rows][64 k] k-block 0
-        tma_load_2d(smem + OFF_W2 + s * W_BYTES + 8192, &tmW2, &w2_full[s], c * HC + 64, 0);  // k-block 1
+        tma_load_2d(smem + OFF_W2 + s * W_BYTES, &tmW2, &w2_full[s], (cbase + c) * HC, 0);          // [64 d rows][64 k] k-block 0
+        tma_load_2d(smem + OFF_W2 + s * W_BYTES + 8192, &tmW2, &w2_full[s], (cbase + c) * HC + 64, 0);  // k-block 1
       }
     }
   } else if (warp == 1) {
@@ -214,7 +249,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t sx = smem_u32(smem);
       auto gemm1 = [&](int c) {
         const int s = c % NST; const uint32_t ph = (c / NST) & 1;
-        const int ab = c & 1; const uint32_t aph = (c >> 1) & 1;
+        const int ab = c % NG; const uint32_t aph = (c / NG) & 1;
         mbar_wait(&acc_free[ab], aph ^ 1);
         mbar_wait(&w1_full[s], ph);
         tc_fence_after();
@@ -229,13 +264,13 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       MLP_TRACE(12, 8);
       gemm1(0);
       MLP_TRACE(12, 9);
-      if (NC > 1) gemm1(1);
+      for (int c = 1; c < NG && c < NC; ++c) gemm1(c);
       for (int c = 0; c < NC; ++c) {
-        // accumulator buffer c&1 is free as soon as the epilogue of chunk c has pulled it into registers, long before
-        // that epilogue finishes: GEMM1(c+2) is issued now so its result is waiting when the group comes back
-        if (c + 2 < NC) gemm1(c + 2);
+        // accumulator buffer c % NG is free as soon as the epilogue of chunk c has pulled it into registers, long before
+        // that epilogue finishes: GEMM1(c+NG) is issued now so its result is waiting when the group comes back
+        if (c + NG < NC) gemm1(c + NG);
         const int s = c % NST; const uint32_t ph = (c / NST) & 1;
-        const int hb = c & 1; const uint32_t hph = (c >> 1) & 1;
+        const int hb = c % NG; const uint32_t hph = (c / NG) & 1;
         MLP_TRACE(8, c);
         mbar_wait(&h_ready[hb], hph);
         MLP_TRACE(9, c);
@@ -247,7 +282,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int k = 0; k < HC / 16; ++k) {
           const uint64_t hd = make_smem_desc(sh + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
           const uint64_t wd = make_smem_desc(sw + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024);
-          umma_bf16(tmem_base + 256, hd, wd, idesc2, (c > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base + T_Y, hd, wd, idesc2, (c > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&w2_empty[s]);
         umma_commit(&h_free[hb]);
@@ -256,18 +291,18 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       umma_commit(y_full);
     }
   } else {
-    // Two ping-pong groups of 8 warps: group g owns the chunks c = g (mod 2), i.e. accumulator buffer g and H buffer g,
-    // so one group's TMEM-load / smem-store / barrier phases overlap the other group's MUFU + FMA phase.
+    // NG groups of 8 warps: group g owns the chunks c = g (mod NG), i.e. accumulator buffer g and H buffer g, so one
+    // group's TMEM-load / smem-store / barrier phases overlap the other groups' MUFU + FMA phases (measured: a third group does not help, the MUFU / FMA / issue mix is the limit, not latency).
     const int ew = warp - 2;
-    const int pg = ew >> 3, half = (ew >> 2) & 1;        // group ; 64-column half of the chunk
-    const int quad = warp & 3, grp = ew >> 2;            // TMEM lane quadrant ; 16-column group of the final output
+    const int pg = ew / GW, half = (ew >> 2) & 1;        // group ; 64-column half of the chunk
+    const int quad = warp & 3, grp = ew >> 2;            // TMEM lane quadrant ; 16-column group of the final output (grp < 4)
     const int r = quad * 32 + lane;
     const int row0 = mt * 128 + quad * 32;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    stage_bias(a.b1, bias_s, a.HID, threadIdx.x - 64);
+    stage_bias<FWD_EPI_WARPS>(a.b1, bias_s, a.HID, threadIdx.x - 64);
     if (warp == 2) MLP_TRACE(12, 3);
-    for (int c = pg; c < NC; c += 2) {
-      const int ab = pg; const uint32_t aph = (c >> 1) & 1;
+    for (int c = pg; c < NC; c += NG) {
+      const int ab = pg; const uint32_t aph = (c / NG) & 1;
       if ((ew & 7) == 0) MLP_TRACE(0, c);
       mbar_wait(&acc_full[ab], aph);
       if ((ew & 7) == 0) MLP_TRACE(1, c);
@@ -284,7 +319,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_free[ab]);      // TMEM chunk drained: GEMM1(c+2) may start
         }
-        const uint4* bsm = reinterpret_cast<const uint4*>(bias_s + c * HC + half * 64 + hh * 32);
+        const uint4* bsm = reinterpret_cast<const uint4*>(bias_s + (cbase + c) * HC + half * 64 + hh * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint4 b4 = bsm[i];
@@ -305,7 +340,64 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (lane == 0) mbar_arrive(&h_ready[ab]);
       if ((ew & 7) == 0) MLP_TRACE(4, c);
     }
-    // ---- output: y + b2 + residual  (16 columns per warp); the residual loads overlap the last GEMM2
+    if (SPLIT) {   // partial Y of this CTA's hidden columns -> own shared memory (the H buffers are dead by now)
+      if (grp < 4) {
+        mbar_wait(y_full, 0);
+        tc_fence_after();
+        float y[16];
+        tmem_ld16(tmem_base + T_Y + grp * 16 + lane_off, y);
+        float4* yb = reinterpret_cast<float4*>(smem + OFF_H + (r * 64 + grp * 16) * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) yb[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      }
+    }
+  }
+  if (warp == 2) MLP_TRACE(12, 10);
+  if (SPLIT) {
+    // Reduce-scatter over distributed shared memory (a single CTA pulling all partials would be bound by the
+    // ~20 B/clk DSMEM port): CTA `rank` finishes rows [16 rank, 16 rank + 16) of the tile, one row per epilogue warp,
+    // two columns per lane, partials summed in rank order (deterministic); LayerNorm statistics by warp shuffle.
+    static_assert(FWD_EPI_WARPS * NSPLIT == 128, "one tile row per epilogue warp and cluster rank");
+    cluster_sync();                     // every CTA's partial is in place (all threads of all CTAs)
+    if (warp == 2) MLP_TRACE(12, 11);
+    if (warp >= 2) {
+      const int rt = rank * FWD_EPI_WARPS + (warp - 2);
+      const int row = mt * 128 + rt, col = lane * 2;
+      const uint32_t local = smem_u32(smem + OFF_H + (rt * 64 + col) * 4);
+      float2 v[NSPLIT];
+#pragma unroll
+      for (int cr = 0; cr < NSPLIT; ++cr) v[cr] = ld_dsmem_f2(mapa_shared(local, cr));
+      float y0 = v[0].x, y1 = v[0].y;
+#pragma unroll
+      for (int cr = 1; cr < NSPLIT; ++cr) { y0 += v[cr].x; y1 += v[cr].y; }
+      if (warp == 2) MLP_TRACE(12, 12);
+      const bool ok = row < a.M;
+      if (ok) {
+        const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.b2 + col));
+        const float2 rr = *reinterpret_cast<const float2*>(a.resid + (int64_t)row * a.ldr + col);
+        y0 += b2.x + rr.x; y1 += b2.y + rr.y;
+        *reinterpret_cast<float2*>(a.out + (int64_t)row * a.ldc + col) = make_float2(y0, y1);
+      }
+      if (a.ln_gamma) {
+        const float mu = warp_sum(y0 + y1) * (1.0f / 64.0f);
+        const float c0 = y0 - mu, c1 = y1 - mu;
+        const float rs = 1.0f / sqrtf(warp_sum(fmaf(c0, c0, c1 * c1)) * (1.0f / 64.0f) + 1e-5f);
+        if (ok) {
+          const float2 g2 = __ldg(reinterpret_cast<const float2*>(a.ln_gamma + col)), be = __ldg(reinterpret_cast<const float2*>(a.ln_beta + col));
+          *reinterpret_cast<uint32_t*>(a.ln_out + (int64_t)row * 64 + col) = pack_bf2(c0 * rs * g2.x + be.x, c1 * rs * g2.y + be.y);
+          if (lane == 0 && a.ln_mean) { a.ln_mean[row] = mu; a.ln_rstd[row] = rs; }
+        }
+      }
+    }
+  } else if (warp >= 2) {
+    const int ew = warp - 2;
+    const int quad = warp & 3, grp = ew >> 2;
+    const int r = quad * 32 + lane;
+    const int row0 = mt * 128 + quad * 32;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    // ---- output: y + b2 + residual  (16 columns per warp, the first 16 epilogue warps); the residual loads overlap
+    //      the last GEMM2
+    if (grp < 4) {
     const int row = row0 + lane;
     float4 r4[4], b4[4];
     if (row < a.M) {
@@ -313,12 +405,14 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
       for (int i = 0; i < 4; ++i) { r4[i] = reinterpret_cast<const float4*>(R)[i]; b4[i] = __ldg(reinterpret_cast<const float4*>(a.b2 + grp * 16) + i); }
     }
-    if (warp == 2) MLP_TRACE(12, 4);
-    mbar_wait(y_full, 0);
-    if (warp == 2) MLP_TRACE(12, 5);
-    tc_fence_after();
     float y[16];
-    tmem_ld16(tmem_base + 256 + grp * 16 + lane_off, y);
+    {
+      if (warp == 2) MLP_TRACE(12, 4);
+      mbar_wait(y_full, 0);
+      if (warp == 2) MLP_TRACE(12, 5);
+      tc_fence_after();
+      tmem_ld16(tmem_base + T_Y + grp * 16 + lane_off, y);
+    }
     if (row < a.M) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -337,15 +431,15 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
       for (int i = 0; i < 16; ++i) s += y[i];
       part[r * 4 + grp] = s;
-      epi_bar_sync();
+      epi_bar_sync<16>();
       const float4 p4 = *reinterpret_cast<const float4*>(part + r * 4);
       const float mu = ((p4.x + p4.y) + (p4.z + p4.w)) * (1.0f / 64.0f);
       float q = 0.f;
 #pragma unroll
       for (int i = 0; i < 16; ++i) { const float c = y[i] - mu; q = fmaf(c, c, q); }
-      epi_bar_sync();                                   // everyone has read the sums
+      epi_bar_sync<16>();                               // everyone has read the sums
       part[r * 4 + grp] = q;
-      epi_bar_sync();
+      epi_bar_sync<16>();
       const float4 q4 = *reinterpret_cast<const float4*>(part + r * 4);
       const float rs = 1.0f / sqrtf(((q4.x + q4.y) + (q4.z + q4.w)) * (1.0f / 64.0f) + 1e-5f);
       if (row < a.M) {
@@ -362,8 +456,10 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (grp == 0 && a.ln_mean) { a.ln_mean[row] = mu; a.ln_rstd[row] = rs; }
       }
     }
+    }
   }
   if (warp == 2) MLP_TRACE(12, 6);
+  if (SPLIT) cluster_sync();            // every CTA has read its slice of everyone's partial: shared memory may go away
   tc_fence_before();
   __syncthreads();
   if (warp == 2) MLP_TRACE(12, 7);
@@ -637,6 +733,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 // ------------------------------------------------------------------ host
+static bool g_split_enabled = true;     // split-hidden cluster variant of the forward (set_option "mlp_split")
 static long long* g_trace = nullptr;   // device buffer for DGVIT_MLP_TRACE builds (dgvit_set_option_ptr)
 static bool eligible(int D, int HID, int64_t M, const void* x, const void* w1, const void* w2, const float* resid,
                      int64_t ldr, const float* out, int64_t ldc) {
@@ -661,11 +758,16 @@ static void fwd(const bf16* x, const bf16* W1, const float* b1, const bf16* W2, 
   CUtensorMap tw2 = make_map(W2, HID, 64, HID, 64, 64);
   static bool attr = false;
   if (!attr) {
-    DG_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
+    DG_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
+    DG_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
     attr = true;
   }
   const int grid = (int)cdiv(M, 128);
-  launch_k(mlp_fwd_tc_kernel, grid, THREADS, f::SMEM_TOTAL, st, tx, tw1, tw2, a);
+  // few tiles (pruned last block, batch-1 act): one 16-chunk CTA per tile is pure latency, so a cluster of 8 CTAs
+  // shares each tile's hidden columns
+  const bool split = g_split_enabled && grid * f::NSPLIT <= sm_count() && (HID / HC) % f::NSPLIT == 0 && (HID / HC) / f::NSPLIT >= 1;
+  if (split) launch_k_cluster(mlp_fwd_tc_kernel<true>, grid * f::NSPLIT, f::FWD_THREADS, f::SMEM_TOTAL, st, f::NSPLIT, tx, tw1, tw2, a);
+  else launch_k(mlp_fwd_tc_kernel<false>, grid, f::FWD_THREADS, f::SMEM_TOTAL, st, tx, tw1, tw2, a);
   DG_LAUNCH_CHECK();
 }
 

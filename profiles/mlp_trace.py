@@ -29,5 +29,5 @@ names = {0: "epi wait", 1: "acc_full", 2: "computed", 3: "h_free", 4: "h_written
 print("chunk " + " ".join(f"{names[k]:>18s}" for k in names))
 for c in range(hid // 128):
     print(f"{c:5d} " + " ".join(f"{int(t[k, c]) - t0 if t[k, c] > 0 else -1:18d}" for k in names))
-ev = ["entry", "after tmem alloc+sync", "after pdl_wait", "bias staged", "loop done", "y_full", "stored", "final sync", "mma: x_full", "mma: gemm1(0) issued"]
+ev = ["entry", "after tmem alloc+sync", "after pdl_wait", "bias staged", "loop done", "y_full", "stored", "final sync", "mma: x_full", "mma: gemm1(0) issued", "before cluster sync", "after cluster sync", "dsmem reduced"]
 print("one-off events (clocks since first loop event): " + ", ".join(f"{n}={int(t[12, i]) - t0}" for i, n in enumerate(ev)))
