@@ -499,7 +499,9 @@ struct MlpBwdArgs {
   int64_t split_stride;       // floats between consecutive splits (same for the three partials)
 };
 
-template <int MODE>
+// SPLIT (MODE 0 only, few token tiles): a cluster of f::NSPLIT CTAs shares one tile, each taking HID / NSPLIT hidden
+// columns; the partial dX tiles are reduce-scattered over distributed shared memory as in the forward.
+template <int MODE, bool SPLIT = false>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const MlpBwdArgs a) {
@@ -523,7 +525,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int tiles = (a.M + 127) / 128;
   // step i of this CTA = (token tile t_of(i), hidden chunk c_of(i))
   int nsteps, t0, c0;
-  if (MODE == 0) { t0 = blockIdx.x; c0 = 0; nsteps = NC; }
+  const int rank = SPLIT ? blockIdx.x % f::NSPLIT : 0;
+  if (MODE == 0 && SPLIT) { t0 = blockIdx.x / f::NSPLIT; nsteps = NC / f::NSPLIT; c0 = rank * nsteps; }
+  else if (MODE == 0) { t0 = blockIdx.x; c0 = 0; nsteps = NC; }
   else {
     c0 = blockIdx.x % NC;
     t0 = (blockIdx.x / NC) * a.tiles_per_split;
@@ -616,7 +620,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int k = 0; k < 8; ++k)   // dX[tok, in] += dH[tok, hid] W1c[hid, in]
             umma_bf16(tmem_base + T_ACC0, make_smem_desc(s_dh + (k >> 2) * TILE16 + (k & 3) * 32, 16, 1024),
                       make_smem_desc(w1 + k * 2048, TILE16, 1024), id_dx, (i > 0 || k > 0) ? 1u : 0u);
-          if (i == 0 && a.db2_part) {
+          if (i == 0 && a.db2_part && rank == 0) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)   // every row of the result = column sums of the dY tile
               umma_bf16(tmem_base + T_ACC1, make_smem_desc(s_one, 16, 1024), make_smem_desc(dy + k * 2048, TILE16, 1024),
@@ -696,12 +700,16 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (MODE == 0) {
       tmem_ld16(tmem_base + T_ACC0 + grp * 16 + lane_off, y);
       const int row = t0 * 128 + r;
-      if (row < a.M) {
+      if (SPLIT) {        // partial dX of this CTA's hidden columns -> own shared memory (the dH tile is dead by now)
+        float4* yb = reinterpret_cast<float4*>(smem + OFF_DH + (r * 64 + grp * 16) * 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) yb[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+      } else if (row < a.M) {
         float* O = a.dX + (int64_t)row * a.lddx + grp * 16;
 #pragma unroll
         for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(O)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
       }
-      if (a.db2_part && quad == 0) {                      // row 0 of the ones x dY product
+      if (a.db2_part && quad == 0 && rank == 0) {         // row 0 of the ones x dY product
         tmem_ld16(tmem_base + T_ACC1 + grp * 16 + lane_off, y);
         if (lane == 0) {
           float* O = a.db2_part + (int64_t)t0 * 64 + grp * 16;
@@ -726,6 +734,23 @@ mlp_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         a.db1_part[so + h] = y[0];
       }
     }
+  }
+  if (MODE == 0 && SPLIT) {
+    static_assert(EPI_WARPS * f::NSPLIT == 128, "one tile row per epilogue warp and cluster rank");
+    cluster_sync();                     // every CTA's partial dX is in place
+    if (warp >= 2) {                    // rows [16 rank, 16 rank + 16): one per warp, two columns per lane, rank order
+      const int rt = rank * EPI_WARPS + (warp - 2);
+      const int row = t0 * 128 + rt, col = lane * 2;
+      const uint32_t local = smem_u32(smem + OFF_DH + (rt * 64 + col) * 4);
+      float2 v[f::NSPLIT];
+#pragma unroll
+      for (int cr = 0; cr < f::NSPLIT; ++cr) v[cr] = ld_dsmem_f2(mapa_shared(local, cr));
+      float y0 = v[0].x, y1 = v[0].y;
+#pragma unroll
+      for (int cr = 1; cr < f::NSPLIT; ++cr) { y0 += v[cr].x; y1 += v[cr].y; }
+      if (row < a.M) *reinterpret_cast<float2*>(a.dX + (int64_t)row * a.lddx + col) = make_float2(y0, y1);
+    }
+    cluster_sync();                     // everyone has read its slice: shared memory may go away
   }
   tc_fence_before();
   __syncthreads();
@@ -806,10 +831,13 @@ static void bwd(const bf16* x, const bf16* dy, const bf16* W1, const float* b1, 
   static bool attr = false;
   if (!attr) {
     DG_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b::SMEM_TOTAL));
+    DG_CUDA(cudaFuncSetAttribute((mlp_bwd_tc_kernel<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b::SMEM_TOTAL));
     DG_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b::SMEM_TOTAL));
     attr = true;
   }
-  launch_k(mlp_bwd_tc_kernel<0>, tiles, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
+  const bool split = g_split_enabled && tiles * f::NSPLIT <= sm_count() && NC % f::NSPLIT == 0;
+  if (split) launch_k_cluster((mlp_bwd_tc_kernel<0, true>), tiles * f::NSPLIT, THREADS, b::SMEM_TOTAL, st, f::NSPLIT, tx, tdy, tw1, tw2, a);
+  else launch_k(mlp_bwd_tc_kernel<0>, tiles, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
   DG_LAUNCH_CHECK();
   launch_k(mlp_bwd_tc_kernel<1>, NC * S, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
   DG_LAUNCH_CHECK();
