@@ -264,6 +264,171 @@ __global__ void colsum_partial_kernel(const T_* __restrict__ A, int64_t lda, flo
 }
 
 // =====================================================================================
+// Last-block attention.  Only token 0 of the last block's output is consumed (x[:, 0], vn/GoalFormer.py:167), so
+// there the attention needs a single query row per (sample, head): o0 = softmax(q0 K^T * dh^-0.5) V.  K and V
+// still come from every token, so gradients reach all of them; dQ is zero except on row 0.  Exact, not an
+// approximation.  One warp per (sample, head), dh = 64, up to 72 keys (the shipped model has 65):
+// lane = (g, c): key slot g of 8 per pass, quarter c of the 64 head dims -> every load is a 32-byte piece of a row and
+// all loads of a phase are independent (the kernel is a latency chain: q, K, softmax, V).
+// =====================================================================================
+constexpr int R0_DH = 64, R0_NP = 9, R0_MAXN = 8 * R0_NP;
+template <typename A> __device__ __forceinline__ void r0_ld16(const A* p, float (&v)[16]);
+template <> __device__ __forceinline__ void r0_ld16<float>(const float* p, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 f = reinterpret_cast<const float4*>(p)[i];
+    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+  }
+}
+template <> __device__ __forceinline__ void r0_ld16<bf16>(const bf16* p, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint4 u = reinterpret_cast<const uint4*>(p)[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[8 * i + 2 * j] = __uint_as_float(w[j] << 16); v[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+  }
+}
+template <typename A> __device__ __forceinline__ void r0_st16(A* p, const float (&v)[16]);
+template <> __device__ __forceinline__ void r0_st16<float>(float* p, const float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+template <> __device__ __forceinline__ void r0_st16<bf16>(bf16* p, const float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+      w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    reinterpret_cast<uint4*>(p)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+// x[t] = <vec quarter, row (8t+g) quarter> summed over the 4 quarter lanes (rows >= N give 0)
+template <typename A>
+__device__ __forceinline__ void r0_dots(const float (&vec)[16], const A* rows, int ld, int N, int g, float (&x)[R0_NP]) {
+#pragma unroll
+  for (int t = 0; t < R0_NP; ++t) {
+    const int j = 8 * t + g;
+    float s = 0.f;
+    if (j < N) {
+      float k[16];
+      r0_ld16<A>(rows + (int64_t)j * ld, k);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s = fmaf(vec[i], k[i], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    x[t] = s;
+  }
+}
+__device__ __forceinline__ float r0_groups_sum(float v) {   // over the 8 key slots (each value is replicated on 4 lanes)
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+// p[t] = softmax weight of key 8t+g (unnormalised exp; returns 1 / sum)
+__device__ __forceinline__ float r0_softmax(float (&p)[R0_NP], int N, int g, float scale) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < R0_NP; ++t) if (8 * t + g < N) mx = fmaxf(mx, p[t]);
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < R0_NP; ++t) {
+    p[t] = (8 * t + g < N) ? expf((p[t] - mx) * scale) : 0.f;
+    sum += p[t];
+  }
+  return 1.0f / r0_groups_sum(sum);
+}
+template <typename A>
+__global__ void __launch_bounds__(128) attention_row0_fwd_kernel(const A* __restrict__ QKV, A* __restrict__ O, int items, int N,
+                                                                 int H, float scale) {
+  pdl_wait();
+  pdl_launch();
+  const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  const int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (it >= items) return;
+  const int b = it / H, h = it % H, inner = H * R0_DH, ld = 3 * inner;
+  const A* base = QKV + (int64_t)b * N * ld + h * R0_DH;
+  float q[16], p[R0_NP];
+  r0_ld16<A>(base + 16 * c, q);
+  r0_dots<A>(q, base + inner + 16 * c, ld, N, g, p);
+  const float inv = r0_softmax(p, N, g, scale);
+  // o0[d] = sum_j p_j V[j][d]: each lane sums its own keys over its quarter of the head dims, then the 8 key slots meet
+  float o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int t = 0; t < R0_NP; ++t) {
+    const int j = 8 * t + g;
+    if (j < N) {
+      float v[16];
+      r0_ld16<A>(base + 2 * inner + (int64_t)j * ld + 16 * c, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = fmaf(p[t], v[i], o[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = r0_groups_sum(o[i]) * inv;
+  if (g == 0) r0_st16<A>(O + (int64_t)b * N * inner + h * R0_DH + 16 * c, o);
+}
+// dQKV of the (sample, head): dV[j] = p_j dO0, dK[j] = ds_j q0, dQ[0] = sum_j ds_j K[j], dQ[j>0] = 0
+template <typename A>
+__global__ void __launch_bounds__(128) attention_row0_bwd_kernel(const A* __restrict__ QKV, const A* __restrict__ dO,
+                                                                 A* __restrict__ dQKV, int items, int N, int H, float scale) {
+  pdl_wait();
+  pdl_launch();
+  const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  const int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (it >= items) return;
+  const int b = it / H, h = it % H, inner = H * R0_DH, ld = 3 * inner;
+  const A* base = QKV + (int64_t)b * N * ld + h * R0_DH;
+  A* obase = dQKV + (int64_t)b * N * ld + h * R0_DH;
+  float q[16], go[16], p[R0_NP], ds[R0_NP];
+  r0_ld16<A>(base + 16 * c, q);
+  r0_ld16<A>(dO + (int64_t)b * N * inner + h * R0_DH + 16 * c, go);
+  r0_dots<A>(q, base + inner + 16 * c, ld, N, g, p);
+  const float inv = r0_softmax(p, N, g, scale);
+  r0_dots<A>(go, base + 2 * inner + 16 * c, ld, N, g, ds);          // dp_j = <dO0, V[j]>
+  float delta = 0.f;
+#pragma unroll
+  for (int t = 0; t < R0_NP; ++t) { p[t] *= inv; delta = fmaf(p[t], ds[t], delta); }
+  delta = r0_groups_sum(delta);
+  float dq[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dq[i] = 0.f;
+#pragma unroll
+  for (int t = 0; t < R0_NP; ++t) {
+    const int j = 8 * t + g;
+    const float dsj = p[t] * (ds[t] - delta) * scale;
+    if (j < N) {
+      float k[16], w[16];
+      r0_ld16<A>(base + inner + (int64_t)j * ld + 16 * c, k);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { dq[i] = fmaf(dsj, k[i], dq[i]); w[i] = dsj * q[i]; }
+      r0_st16<A>(obase + inner + (int64_t)j * ld + 16 * c, w);       // dK[j]
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = p[t] * go[i];
+      r0_st16<A>(obase + 2 * inner + (int64_t)j * ld + 16 * c, w);   // dV[j]
+      if (j > 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = 0.f;
+        r0_st16<A>(obase + (int64_t)j * ld + 16 * c, w);             // dQ[j] = 0
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dq[i] = r0_groups_sum(dq[i]);
+  if (g == 0) r0_st16<A>(obase + 16 * c, dq);                        // dQ[0]
+}
+
+// =====================================================================================
 // Attention (vn/GoalFormer.py:71-81): softmax(q k^T * dh^-0.5) v per (sample, head).
 // CUDA-core version: K,V (and Q,dO in backward) of one (b,h) staged in shared memory,
 // one warp per query row, warp-shuffle softmax.
