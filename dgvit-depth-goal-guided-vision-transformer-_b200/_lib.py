@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdgvit.so")
+# DGVIT_LIB selects another build of the same library (A/B measurements); there is still no fallback
+LIB_PATH = os.environ.get("DGVIT_LIB") or os.path.join(_HERE, "libdgvit.so")
 
 MAX_DEPTH = 16
 ACTOR, CRITIC = 0, 1
@@ -167,6 +168,11 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
+        # DGVIT_OPTS="name=value,..." applies dgvit_set_option at load time (A/B measurements of kernel variants)
+        for kv in filter(None, os.environ.get("DGVIT_OPTS", "").split(",")):
+            k, v = kv.split("=")
+            if l.dgvit_set_option(k.strip().encode(), int(v)) != 0:
+                raise RuntimeError(f"DGVIT_OPTS: {l.dgvit_last_error().decode()}")
         _lib = l
     return _lib
 

@@ -492,7 +492,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
                                                 sqrtf((float)d.D));
   DG_LAUNCH_CHECK();
   {  // dg = sum_b dg_rows
-    const int S = pick_splitk(d.B);
+    const int S = std::max(1, std::min(64, d.B / 4));
     dim3 grid((unsigned)cdiv(d.D, 256), (unsigned)S);
     launch_k(colsum_partial_kernel<float>, grid, 128, 0, st, c.dg_rows, d.D, c.partial, d.B, d.D, cdiv(d.B, S));
     DG_LAUNCH_CHECK();

@@ -464,3 +464,35 @@ def test_behaviour_cloning_step_through_module_surface():
             d = (p.detach().cpu() - ref[k].detach()).abs()
             assert float((d > 2e-5 * (s + 1)).float().mean()) < 5e-3, (s, k)
     assert a._bound()          # torch.optim updated the flat arena in place through the parameter views
+
+
+def _one_update(cfg, precision, B, opts):
+    """losses + both gradient arenas of one fused update with library options `opts` set during the call"""
+    for k, v in opts.items():
+        L.check(L.lib().dgvit_set_option(k.encode(), v), "set_option")
+    try:
+        ag = _agent(cfg, precision, seed=9)
+        batch, noise = synthetic_batch(cfg, B, 51), synthetic_noise(cfg, B, 52)
+        cb = {k: v.reshape(B, -1).cuda().contiguous() for k, v in batch.items()}
+        losses = ag.update_from_batch(cb, _noise_cuda(noise)).cpu()
+        torch.cuda.synchronize()
+        return losses, ag.critic._garena.cpu().clone(), ag.policy._garena.cpu().clone()
+    finally:
+        for k, v in dict(mlp_split=1, attention_row0=2).items():
+            L.check(L.lib().dgvit_set_option(k.encode(), v), "set_option")
+
+
+@pytest.mark.parametrize("precision,B", [("bf16", 16), ("bf16", 3), ("fp32", 5)])
+def test_pruned_block_variants_are_equivalent(precision, B):
+    """The last-block shortcuts are exact rewrites, so switching them off must not change the update beyond summation
+    order: split-hidden cluster MLP kernels (few token tiles) vs one CTA per tile; single-query-row attention
+    (forward and backward) vs the full attention kernels."""
+    cfg = O.Cfg()
+    base = _one_update(cfg, precision, B, dict(mlp_split=0, attention_row0=0))
+    for opts in (dict(mlp_split=1, attention_row0=0), dict(mlp_split=0, attention_row0=2), dict(mlp_split=1, attention_row0=3)):
+        got = _one_update(cfg, precision, B, opts)
+        tol = 2e-5 if precision == "fp32" else 2e-2
+        assert torch.allclose(got[0], base[0], rtol=tol, atol=tol * 1e-2), (opts, got[0], base[0])
+        for g, b in zip(got[1:], base[1:]):
+            err = float((g - b).norm() / b.norm().clamp_min(1e-20))
+            assert err < tol, (opts, err)
