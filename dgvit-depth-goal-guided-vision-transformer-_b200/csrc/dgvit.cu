@@ -102,8 +102,9 @@ template <> struct WSel<bf16> {
 
 // ------------------------------------------------------------------ GEMM dispatch
 // single-query-row attention in the last block (set_option "attention_row0": bit 0 forward, bit 1 backward).  Measured
-// at B=256: backward 22 us vs 38 us for the full tcgen05 kernel; forward 16 us vs 13.5 us, so the forward stays on tcgen05.
-static int g_row0_mode = 2;
+// at B=256 (ncu, cold): backward 22 us vs 38 us for the full tcgen05 kernel, forward 16 us vs 13.5 us; inside the graph-replayed
+// step both help (same-box A/B: off 104.8 k, backward only 106.2 k, both 106.6 k samples/s).
+static int g_row0_mode = 3;
 static thread_local int g_cur_tag = PROF_NONE;
 struct TagScope {
   int prev;
