@@ -207,6 +207,9 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL writes its banner ("NCCL version ...") to stdout at NCCL_DEBUG=VERSION: stdout carries the JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     pk = peaks()
