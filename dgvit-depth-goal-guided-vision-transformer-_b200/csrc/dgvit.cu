@@ -430,23 +430,32 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
     const int64_t R = last ? d.B : d.T;
     const int64_t ostride = last ? (int64_t)d.N * d.inner : d.inner;
     const int64_t xstride = last ? (int64_t)d.N * d.D : d.D;
-    // out-projection + bias + residual, with the MLP block's LayerNorm-2 fused into the GEMM epilogue when the
-    // tensor-core kernel takes it (x = ff(LN(x)) + x, vn/GoalFormer.py:104)
-    bool ln2_done = false;
+    // out-projection + bias + residual + LayerNorm-2 (x = attn(LN x) + x ; ff input = LN(x), vn/GoalFormer.py:103-104):
+    //   (a) bf16 path, inner = 256: the prologue of the fused MLP kernel below (no launch of its own);
+    //   (b) else the tensor-core GEMM with LayerNorm-2 in its epilogue;  (c) else GEMM + LayerNorm kernels.
+    bool ln2_done = false, front_done = false;
 #ifdef DGVIT_WITH_TC
+    mlp::FrontFuse fr;
     if constexpr (std::is_same<A, bf16>::value) {
-      GemmArgs g;
-      g.M = (int)R; g.N = d.D; g.K = d.inner;
-      g.A = B_.O; g.a_sm = ostride; g.a_sk = 1;
-      g.B = WSel<A>::w(net, b.out_w); g.b_sk = 1; g.b_sn = d.inner;
-      g.C = B_.Xm; g.ldc = d.D;
-      g.epi = EPI_BIAS_RESID; g.bias = P + b.out_b; g.resid = B_.Xa; g.ldr = xstride;
-      g.ln_gamma = P + b.ln2_w; g.ln_beta = P + b.ln2_b; g.ln_out = B_.Xn2; g.ln_mean = B_.mean2; g.ln_rstd = B_.rstd2;
-      ProfScope ps_all(PROF_GEMM_ALL, 2.0 * g.M * g.N * g.K, 0.0, st);
-      ln2_done = gemm_tc_try<A, A, float>(g, st);
+      fr.o = (const bf16*)B_.O; fr.ldo = ostride; fr.Wo = (const bf16*)WSel<A>::w(net, b.out_w); fr.ob = P + b.out_b;
+      fr.xa = B_.Xa; fr.ldxa = xstride; fr.xm = B_.Xm; fr.gamma = P + b.ln2_w; fr.beta = P + b.ln2_b;
+      fr.xn2 = (bf16*)B_.Xn2; fr.mean = B_.mean2; fr.rstd = B_.rstd2;
+      front_done = mlp::front_eligible(d.inner, fr) &&
+                   mlp_fused<A>(d, R, B_.Xn2, WSel<A>::w(net, b.fc1_w), WSel<A>::w(net, b.fc2_w), B_.Xm, Xnext);
+      if (!front_done) {
+        GemmArgs g;
+        g.M = (int)R; g.N = d.D; g.K = d.inner;
+        g.A = B_.O; g.a_sm = ostride; g.a_sk = 1;
+        g.B = WSel<A>::w(net, b.out_w); g.b_sk = 1; g.b_sn = d.inner;
+        g.C = B_.Xm; g.ldc = d.D;
+        g.epi = EPI_BIAS_RESID; g.bias = P + b.out_b; g.resid = B_.Xa; g.ldr = xstride;
+        g.ln_gamma = P + b.ln2_w; g.ln_beta = P + b.ln2_b; g.ln_out = B_.Xn2; g.ln_mean = B_.mean2; g.ln_rstd = B_.rstd2;
+        ProfScope ps_all(PROF_GEMM_ALL, 2.0 * g.M * g.N * g.K, 0.0, st);
+        ln2_done = gemm_tc_try<A, A, float>(g, st);
+      }
     }
 #endif
-    if (!ln2_done) {
+    if (!ln2_done && !front_done) {
       linear_fwd<A, A, float>(B_.O, WSel<A>::w(net, b.out_w), B_.Xm, R, d.D, d.inner, EPI_BIAS_RESID, P + b.out_b, st,
                               B_.Xa, nullptr, -1, ostride, xstride);
       // MLP block: x = ff(LN(x)) + x
@@ -465,8 +474,9 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
           ln.gamma = P + nb.ln1_w; ln.beta = P + nb.ln1_b; ln.out = (bf16*)N_.Xn1; ln.mean = N_.mean1; ln.rstd = N_.rstd1;
           ln1_done = true;
         }
+        ProfScope ps3(PROF_GEMM_ALL, front_done ? 2.0 * R * d.D * d.inner : 0.0, 0.0, st);
         mlp::fwd(B_.Xn2, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), P + b.fc2_b, B_.Xm, d.D, Xnext,
-                 d.D, R, d.M, st, ln);
+                 d.D, R, d.M, st, ln, front_done ? fr : mlp::FrontFuse());
       }
 #endif
     } else {
@@ -1052,6 +1062,7 @@ int dgvit_set_option(const char* name, int value) {
     else if (!strcmp(name, "tensor_cores")) tc::g_tc_enabled = value != 0;
     else if (!strcmp(name, "debug_epilogue")) tc::g_debug = value;
     else if (!strcmp(name, "mlp_split")) mlp::g_split_enabled = value != 0;
+    else if (!strcmp(name, "mlp_front")) mlp::g_front_enabled = value != 0;
 #endif
     else fail(DGVIT_ERR_ARG, "unknown option %s", name);
   });

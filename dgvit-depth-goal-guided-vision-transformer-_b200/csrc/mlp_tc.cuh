@@ -155,7 +155,10 @@ constexpr int OFF_H = OFF_W2 + NST * W_BYTES;
 constexpr int OFF_BIAS = OFF_H + NG * H_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + MAX_HID * 2;
 constexpr int OFF_LN = OFF_BAR + 256;          // [128 rows][4 column groups] partial sums of the fused LayerNorm
+constexpr int OFF_WO = (OFF_LN + 2048 + 1023) / 1024 * 1024;   // FRONT: W_out [64][256] bf16 (4 k-blocks of 8 KB), then the x_m tile [128][64] fp32
 constexpr int SMEM_TOTAL = OFF_LN + 2048 + 1024;
+constexpr int SMEM_TOTAL_FRONT = OFF_WO + 32768 + 1024;
+static_assert(SMEM_TOTAL_FRONT <= 232448 && OFF_WO % 1024 == 0, "smem budget");
 static_assert(SMEM_TOTAL <= 232448, "smem budget");
 }  // namespace f
 
@@ -175,14 +178,23 @@ struct MlpArgs {
   // optional fused LayerNorm of the output rows (the next block's PreNorm, vn/GoalFormer.py:31-37,103):
   const float* ln_gamma; const float* ln_beta;   // null = off
   bf16* ln_out; float* ln_mean; float* ln_rstd;  // [M,64] bf16, [M], [M]
+  // FRONT: the attention out-projection + residual + this block's LayerNorm-2 run as the kernel's prologue
+  // (x = to_out(o) + x ; ff input = LN(x), vn/GoalFormer.py:81-82,103-104): the kernel reads the attention output o
+  // (tmO) instead of a ready-made LN(x) tile and also emits x_m, LN(x_m), mean, rstd for the backward.
+  const float* ob;                               // to_out.0.bias [64]
+  const float* xa; int64_t ldxa;                 // residual input rows (fp32)
+  float* xm;                                     // [M,64] fp32 out (= resid of the MLP)
+  const float* ln2_gamma; const float* ln2_beta;
+  bf16* xn2; float* mean2; float* rstd2;
 };
 
 // SPLIT: few token tiles (the pruned last block, batch-1 act): a cluster of NSPLIT CTAs shares one tile, each taking
 // HID / NSPLIT hidden columns; the partial outputs meet in CTA 0 of the cluster through distributed shared memory.
-template <bool SPLIT>
+// FRONT: see MlpArgs.  tmX then maps the attention output o ([M rows, 256] bf16) and tmWo the out-projection weight.
+template <bool SPLIT, bool FRONT>
 __global__ void __launch_bounds__(f::FWD_THREADS, 1)
 mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                  const __grid_constant__ CUtensorMap tmW2, const MlpArgs a) {
+                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmWo, const MlpArgs a) {
   using namespace f;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -197,7 +209,9 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* h_ready = acc_free + NG;       // NG (8 warps each)
   uint64_t* h_free = h_ready + NG;         // NG
   uint64_t* y_full = h_free + NG;          // 1
-  uint32_t* tmem_slot = (uint32_t*)(y_full + 1);
+  uint64_t* front_done = y_full + 1;       // 1: out-projection accumulator complete (FRONT)
+  uint64_t* x_ready = front_done + 1;      // 1 (16 warps): LN(x_m) tile written to smem (FRONT)
+  uint32_t* tmem_slot = (uint32_t*)(x_ready + 1);
   __half* bias_s = (__half*)(smem + OFF_BIAS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,6 +227,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int i = 0; i < NST; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
     for (int i = 0; i < NG; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], GW); mbar_init(&h_ready[i], GW); mbar_init(&h_free[i], 1); }
     mbar_init(y_full, 1);
+    mbar_init(front_done, 1); mbar_init(x_ready, FWD_EPI_WARPS);
+    if (FRONT) tma_prefetch_desc(&tmWo);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -229,8 +245,17 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   if (warp == 0) {
     if (elect_one_sync()) {
-      mbar_expect_tx(x_full, X_BYTES);
-      tma_load_2d(smem, &tmX, x_full, 0, mt * 128);
+      if (FRONT) {      // o tile: 4 k-blocks of [128 rows][64] into the (still unused) H buffers; W_out: 4 k-blocks of [64][64]
+        mbar_expect_tx(x_full, 4 * TILE16 + 4 * 8192);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          tma_load_2d(smem + OFF_H + k * TILE16, &tmX, x_full, k * 64, mt * 128);
+          tma_load_2d(smem + OFF_WO + k * 8192, &tmWo, x_full, k * 64, 0);
+        }
+      } else {
+        mbar_expect_tx(x_full, X_BYTES);
+        tma_load_2d(smem, &tmX, x_full, 0, mt * 128);
+      }
       for (int c = 0; c < NC; ++c) {
         const int s = c % NST; const uint32_t ph = (c / NST) & 1;
         mbar_wait(&w1_empty[s], ph ^ 1);
@@ -262,6 +287,18 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       };
       mbar_wait(x_full, 0);
       MLP_TRACE(12, 8);
+      if (FRONT) {      // x_m accumulator = o W_out^T  (K = 256) into the Y columns, then wait for the epilogue's LN(x_m) tile
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const uint64_t od = make_smem_desc(sx + OFF_H + (k >> 2) * TILE16 + (k & 3) * 32, 16, 1024);
+          const uint64_t wd = make_smem_desc(sx + OFF_WO + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024);
+          umma_bf16(tmem_base + T_Y, od, wd, idesc2, k > 0);
+        }
+        umma_commit(front_done);
+        mbar_wait(x_ready, 0);
+        tc_fence_after();
+      }
       gemm1(0);
       MLP_TRACE(12, 9);
       for (int c = 1; c < NG && c < NC; ++c) gemm1(c);
@@ -301,6 +338,73 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     stage_bias<FWD_EPI_WARPS>(a.b1, bias_s, a.HID, threadIdx.x - 64);
     if (warp == 2) MLP_TRACE(12, 3);
+    if (FRONT) {
+      static_assert(!FRONT || FWD_EPI_WARPS == 16, "front epilogue: 4 lane quadrants x 4 column groups");
+      // x_m = o W_out^T + b_out + x_a (fp32) ; LayerNorm-2 -> bf16 tile that is the A operand of every GEMM1.
+      // x_m also stays in shared memory (over the dead W_out tile) as the residual of the output stage.
+      mbar_wait(front_done, 0);
+      tc_fence_after();
+      float y[16];
+      tmem_ld16(tmem_base + T_Y + grp * 16 + lane_off, y);
+      const int row = row0 + lane;
+      const bool ok = row < a.M;
+      if (ok) {
+        const float* R = a.xa + (int64_t)row * a.ldxa + grp * 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 r4 = reinterpret_cast<const float4*>(R)[i];
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ob + grp * 16) + i);
+          y[4 * i] += b4.x + r4.x; y[4 * i + 1] += b4.y + r4.y; y[4 * i + 2] += b4.z + r4.z; y[4 * i + 3] += b4.w + r4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = 0.f;
+      }
+      float4* xs = reinterpret_cast<float4*>(smem + OFF_WO + (r * 64 + grp * 16) * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xs[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      const bool wr = ok && rank == 0;            // (SPLIT: every CTA of the cluster computes the same rows)
+      if (wr) {
+        float4* O = reinterpret_cast<float4*>(a.xm + (int64_t)row * 64 + grp * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) O[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      }
+      float* part = reinterpret_cast<float*>(smem + OFF_LN);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sum += y[i];
+      part[r * 4 + grp] = sum;
+      epi_bar_sync<16>();
+      const float4 p4 = *reinterpret_cast<const float4*>(part + r * 4);
+      const float mu = ((p4.x + p4.y) + (p4.z + p4.w)) * (1.0f / 64.0f);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { const float c = y[i] - mu; q = fmaf(c, c, q); }
+      epi_bar_sync<16>();
+      part[r * 4 + grp] = q;
+      epi_bar_sync<16>();
+      const float4 q4 = *reinterpret_cast<const float4*>(part + r * 4);
+      const float rs = 1.0f / sqrtf(((q4.x + q4.y) + (q4.z + q4.w)) * (1.0f / 64.0f) + 1e-5f);
+      epi_bar_sync<16>();                               // table free again (the output stage reuses it)
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = grp * 16 + 2 * i;
+        const float2 g2 = __ldg(reinterpret_cast<const float2*>(a.ln2_gamma + c)), b2 = __ldg(reinterpret_cast<const float2*>(a.ln2_beta + c));
+        w[i] = ok ? pack_bf2((y[2 * i] - mu) * rs * g2.x + b2.x, (y[2 * i + 1] - mu) * rs * g2.y + b2.y) : 0u;
+      }
+      *reinterpret_cast<uint4*>(smem + sw128_off(r, grp * 2)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(smem + sw128_off(r, grp * 2 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+      if (wr) {
+        uint4* dst = reinterpret_cast<uint4*>(a.xn2 + (int64_t)row * 64 + grp * 16);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        if (grp == 0 && a.mean2) { a.mean2[row] = mu; a.rstd2[row] = rs; }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_ready);
+    }
     for (int c = pg; c < NC; c += NG) {
       const int ab = pg; const uint32_t aph = (c / NG) & 1;
       if ((ew & 7) == 0) MLP_TRACE(0, c);
@@ -374,7 +478,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const bool ok = row < a.M;
       if (ok) {
         const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.b2 + col));
-        const float2 rr = *reinterpret_cast<const float2*>(a.resid + (int64_t)row * a.ldr + col);
+        const float2 rr = FRONT ? *reinterpret_cast<const float2*>(smem + OFF_WO + (rt * 64 + col) * 4)
+                                : *reinterpret_cast<const float2*>(a.resid + (int64_t)row * a.ldr + col);
         y0 += b2.x + rr.x; y1 += b2.y + rr.y;
         *reinterpret_cast<float2*>(a.out + (int64_t)row * a.ldc + col) = make_float2(y0, y1);
       }
@@ -401,7 +506,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int row = row0 + lane;
     float4 r4[4], b4[4];
     if (row < a.M) {
-      const float* R = a.resid + (int64_t)row * a.ldr + grp * 16;
+      const float* R = FRONT ? reinterpret_cast<const float*>(smem + OFF_WO) + r * 64 + grp * 16
+                             : a.resid + (int64_t)row * a.ldr + grp * 16;
 #pragma unroll
       for (int i = 0; i < 4; ++i) { r4[i] = reinterpret_cast<const float4*>(R)[i]; b4[i] = __ldg(reinterpret_cast<const float4*>(a.b2 + grp * 16) + i); }
     }
@@ -771,28 +877,56 @@ struct LnFuse {   // LayerNorm of the output rows, fused into the forward's last
   const float* gamma = nullptr; const float* beta = nullptr;
   bf16* out = nullptr; float* mean = nullptr; float* rstd = nullptr;
 };
+struct FrontFuse {   // out-projection + residual + LayerNorm-2 as the kernel's prologue (o == null: off)
+  const bf16* o = nullptr; int64_t ldo = 0;       // attention output rows [M, 256] (row pitch ldo elements)
+  const bf16* Wo = nullptr; const float* ob = nullptr;
+  const float* xa = nullptr; int64_t ldxa = 0;
+  float* xm = nullptr;
+  const float* gamma = nullptr; const float* beta = nullptr;
+  bf16* xn2 = nullptr; float* mean = nullptr; float* rstd = nullptr;
+};
+static bool g_front_enabled = true;     // set_option "mlp_front"
+static bool front_eligible(int inner, const FrontFuse& fr) {
+  return g_front_enabled && inner == 256 && fr.o && fr.Wo && fr.ob && fr.xa && fr.xm && fr.gamma && fr.beta && fr.xn2 &&
+         ((((uintptr_t)fr.o) | ((uintptr_t)fr.Wo) | ((uintptr_t)fr.xa) | ((uintptr_t)fr.xm) | ((uintptr_t)fr.xn2)) & 15) == 0 &&
+         fr.ldo % 8 == 0 && fr.ldxa % 4 == 0;
+}
 static void fwd(const bf16* x, const bf16* W1, const float* b1, const bf16* W2, const float* b2, const float* resid,
-                int64_t ldr, float* out, int64_t ldc, int64_t M, int HID, cudaStream_t st, const LnFuse& ln = LnFuse()) {
+                int64_t ldr, float* out, int64_t ldc, int64_t M, int HID, cudaStream_t st, const LnFuse& ln = LnFuse(),
+                const FrontFuse& fr = FrontFuse()) {
   MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  a.trace = g_trace;
   a.ln_gamma = ln.gamma; a.ln_beta = ln.beta; a.ln_out = ln.out; a.ln_mean = ln.mean; a.ln_rstd = ln.rstd;
   DG_REQUIRE(!ln.gamma || (ln.beta && ln.out && (((uintptr_t)ln.out) & 15) == 0), "mlp::fwd: fused LayerNorm needs beta and an aligned output");
-  a.trace = g_trace;
   a.M = (int)M; a.HID = HID; a.b1 = b1; a.b2 = b2; a.resid = resid; a.ldr = ldr; a.out = out; a.ldc = ldc;
-  CUtensorMap tx = make_map(x, 64, M, 64, 64, 128);
+  const bool front = fr.o != nullptr;
+  a.ob = fr.ob; a.xa = fr.xa; a.ldxa = fr.ldxa; a.xm = fr.xm; a.ln2_gamma = fr.gamma; a.ln2_beta = fr.beta;
+  a.xn2 = fr.xn2; a.mean2 = fr.mean; a.rstd2 = fr.rstd;
+  CUtensorMap tx = front ? make_map(fr.o, 256, M, fr.ldo, 64, 128) : make_map(x, 64, M, 64, 64, 128);
   CUtensorMap tw1 = make_map(W1, 64, HID, 64, 64, 128);
   CUtensorMap tw2 = make_map(W2, HID, 64, HID, 64, 64);
+  CUtensorMap two = front ? make_map(fr.Wo, 256, 64, 256, 64, 64) : tw1;
   static bool attr = false;
   if (!attr) {
-    DG_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
-    DG_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
+    DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
+    DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
+    DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL_FRONT));
+    DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL_FRONT));
     attr = true;
   }
   const int grid = (int)cdiv(M, 128);
   // few tiles (pruned last block, batch-1 act): one 16-chunk CTA per tile is pure latency, so a cluster of 8 CTAs
   // shares each tile's hidden columns
   const bool split = g_split_enabled && grid * f::NSPLIT <= sm_count() && (HID / HC) % f::NSPLIT == 0 && (HID / HC) / f::NSPLIT >= 1;
-  if (split) launch_k_cluster(mlp_fwd_tc_kernel<true>, grid * f::NSPLIT, f::FWD_THREADS, f::SMEM_TOTAL, st, f::NSPLIT, tx, tw1, tw2, a);
-  else launch_k(mlp_fwd_tc_kernel<false>, grid, f::FWD_THREADS, f::SMEM_TOTAL, st, tx, tw1, tw2, a);
+  const int smem = front ? f::SMEM_TOTAL_FRONT : f::SMEM_TOTAL;
+  if (split) {
+    if (front) launch_k_cluster((mlp_fwd_tc_kernel<true, true>), grid * f::NSPLIT, f::FWD_THREADS, smem, st, f::NSPLIT, tx, tw1, tw2, two, a);
+    else launch_k_cluster((mlp_fwd_tc_kernel<true, false>), grid * f::NSPLIT, f::FWD_THREADS, smem, st, f::NSPLIT, tx, tw1, tw2, two, a);
+  } else {
+    if (front) launch_k((mlp_fwd_tc_kernel<false, true>), grid, f::FWD_THREADS, smem, st, tx, tw1, tw2, two, a);
+    else launch_k((mlp_fwd_tc_kernel<false, false>), grid, f::FWD_THREADS, smem, st, tx, tw1, tw2, two, a);
+  }
   DG_LAUNCH_CHECK();
 }
 

@@ -478,7 +478,7 @@ def _one_update(cfg, precision, B, opts):
         torch.cuda.synchronize()
         return losses, ag.critic._garena.cpu().clone(), ag.policy._garena.cpu().clone()
     finally:
-        for k, v in dict(mlp_split=1, attention_row0=2).items():
+        for k, v in dict(mlp_split=1, attention_row0=3, mlp_front=1).items():
             L.check(L.lib().dgvit_set_option(k.encode(), v), "set_option")
 
 
@@ -486,10 +486,12 @@ def _one_update(cfg, precision, B, opts):
 def test_pruned_block_variants_are_equivalent(precision, B):
     """The last-block shortcuts are exact rewrites, so switching them off must not change the update beyond summation
     order: split-hidden cluster MLP kernels (few token tiles) vs one CTA per tile; single-query-row attention
-    (forward and backward) vs the full attention kernels."""
+    (forward and backward) vs the full attention kernels; out-projection + LayerNorm-2 as the MLP kernel's prologue vs
+    the separate GEMM."""
     cfg = O.Cfg()
-    base = _one_update(cfg, precision, B, dict(mlp_split=0, attention_row0=0))
-    for opts in (dict(mlp_split=1, attention_row0=0), dict(mlp_split=0, attention_row0=2), dict(mlp_split=1, attention_row0=3)):
+    base = _one_update(cfg, precision, B, dict(mlp_split=0, attention_row0=0, mlp_front=0))
+    for opts in (dict(mlp_split=1, attention_row0=0, mlp_front=0), dict(mlp_split=0, attention_row0=2, mlp_front=0),
+                 dict(mlp_split=0, attention_row0=0, mlp_front=1), dict(mlp_split=1, attention_row0=3, mlp_front=1)):
         got = _one_update(cfg, precision, B, opts)
         tol = 2e-5 if precision == "fp32" else 2e-2
         assert torch.allclose(got[0], base[0], rtol=tol, atol=tol * 1e-2), (opts, got[0], base[0])
