@@ -476,7 +476,253 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// =====================================================================================
+// backward, pipelined (KPAD <= 80): two softmax warpgroups alternate work items.  S / dP accumulators and the P / dS
+// shared-memory tiles are double-buffered (one set per warpgroup), the dQ / dK / dV accumulators are shared, the TMA
+// ring runs three items ahead, and every tile holds KPAD rows only (a 128-row A operand over-reads into the next tile:
+// those accumulator rows are never stored).  While one warpgroup drains and stores an item's gradients the other one is
+// in its softmax, and the tensor core works on whichever is ready.
+//   TMEM: stage g: S [160g, 160g+80)  dP [160g+80, 160g+160) ; dQ [320,384) dK [384,448) dV [448,512)
+// =====================================================================================
+constexpr int BWD2_THREADS = 64 + 256;
+template <int NK> struct Bwd2Smem {
+  static constexpr int BLK = NK * 2048;                 // one [KPAD rows][64 cols] bf16 tile
+  static constexpr int LS = 3;                          // load stages: Q | K | V | dO
+  static constexpr int OFF_PD = 0;                      // stage g: P block0, block1, dS block0, block1
+  static constexpr int OFF_LD = 2 * 4 * BLK;
+  static constexpr int OFF_BAR = OFF_LD + LS * 4 * BLK + 8192;    // 8 KB of slack behind the last tile (A-operand over-read)
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static_assert(NK <= 5 && TOTAL <= 232448, "smem budget");
+};
+
+template <int NK>
+__global__ void __launch_bounds__(BWD2_THREADS, 1)
+attn_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmdO, const AttnArgs a) {
+  using SM = Bwd2Smem<NK>;
+  constexpr int BLK = SM::BLK, LS = SM::LS, KPAD = NK * 16;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = (uint64_t*)(smem + SM::OFF_BAR);
+  uint64_t* ld_full = bars;                 // [LS]
+  uint64_t* ld_empty = ld_full + LS;        // [LS]
+  uint64_t* sdp_full = ld_empty + LS;       // [2] S and dP of the stage in TMEM
+  uint64_t* sdp_free = sdp_full + 2;        // [2] (4 warps) both pulled into registers
+  uint64_t* pds_ready = sdp_free + 2;       // [2] (4 warps) P, dS tiles written
+  uint64_t* out_full = pds_ready + 2;       // [2] dQ, dK, dV of the stage's item in TMEM
+  uint64_t* out_free = out_full + 2;        // [2] (4 warps) drained
+  uint32_t* tmem_slot = (uint32_t*)(out_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int inner = a.H * DH;
+  const int items = a.B * a.H;
+  int n_mine = 0;
+  for (int it = blockIdx.x; it < items; it += gridDim.x) ++n_mine;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmdO);
+    for (int i = 0; i < LS; ++i) { mbar_init(&ld_full[i], 1); mbar_init(&ld_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_free[i], 4); mbar_init(&pds_ready[i], 4);
+      mbar_init(&out_full[i], 1); mbar_init(&out_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch();
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      for (int i = 0; i < n_mine; ++i) {
+        const int it = blockIdx.x + i * gridDim.x;
+        const int b = it / a.H, h = it % a.H;
+        const int ls = i % LS; const uint32_t ph = (i / LS) & 1;
+        mbar_wait(&ld_empty[ls], ph ^ 1);
+        uint8_t* base = smem + SM::OFF_LD + ls * 4 * BLK;
+        mbar_expect_tx(&ld_full[ls], 4 * BLK);
+        tma_load_2d(base, &tmKV, &ld_full[ls], h * DH, b * a.N);
+        tma_load_2d(base + BLK, &tmKV, &ld_full[ls], inner + h * DH, b * a.N);
+        tma_load_2d(base + 2 * BLK, &tmKV, &ld_full[ls], 2 * inner + h * DH, b * a.N);
+        tma_load_2d(base + 3 * BLK, &tmdO, &ld_full[ls], h * DH, b * a.N);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc_s = make_idesc(128, KPAD, false, false);   // S, dP
+      constexpr uint32_t idesc_q = make_idesc(128, DH, false, true);      // dQ = dS K      (A K-major, B MN-major)
+      constexpr uint32_t idesc_t = make_idesc(128, DH, true, true);       // dK, dV         (A MN-major, B MN-major)
+      auto tiles = [&](int i) { return smem_u32(smem + SM::OFF_LD + (i % LS) * 4 * BLK); };
+      auto issue_sdp = [&](int i) {
+        const int g = i & 1, j = i >> 1;
+        if (j > 0) mbar_wait(&sdp_free[g], (uint32_t)((j - 1) & 1));
+        mbar_wait(&ld_full[i % LS], (uint32_t)((i / LS) & 1));
+        tc_fence_after();
+        const uint32_t sq = tiles(i), sk = sq + BLK, sv = sk + BLK, sdo = sv + BLK;
+        const uint64_t qd = make_smem_desc(sq, 16, 1024), kd = make_smem_desc(sk, 16, 1024);
+        const uint64_t dod = make_smem_desc(sdo, 16, 1024), vd = make_smem_desc(sv, 16, 1024);
+        const uint32_t ts = tmem_base + g * 160;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(ts, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(ts + 80, dod + (uint64_t)(k * 2), vd + (uint64_t)(k * 2), idesc_s, k > 0);
+        umma_commit(&sdp_full[g]);
+      };
+      if (n_mine > 0) issue_sdp(0);
+      for (int i = 0; i < n_mine; ++i) {
+        if (i + 1 < n_mine) issue_sdp(i + 1);
+        const int g = i & 1, j = i >> 1;
+        mbar_wait(&pds_ready[g], (uint32_t)(j & 1));
+        if (i > 0) mbar_wait(&out_free[g ^ 1], (uint32_t)(((i - 1) >> 1) & 1));   // the shared accumulators are drained
+        tc_fence_after();
+        const uint32_t sq = tiles(i), sk = sq + BLK, sdo = sk + 2 * BLK;
+        const uint32_t sp = smem_u32(smem + SM::OFF_PD + g * 4 * BLK), sds = sp + 2 * BLK;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          // dQ[128 x 64] += dS[:, 16k:16k+16] K[16k:16k+16, :]
+          const uint64_t ad = make_smem_desc(sds + (k >> 2) * BLK + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(sk + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base + 320, ad, bd, idesc_q, k > 0);
+        }
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          // dK[keys x 64] += dS^T[:, 16k rows of queries] Q[16k.., :]   (A = dS tile read MN-major, 64-key blocks BLK apart)
+          const uint64_t ad = make_smem_desc(sds + k * 2048, BLK, 1024);
+          const uint64_t bd = make_smem_desc(sq + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base + 384, ad, bd, idesc_t, k > 0);
+        }
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          const uint64_t ad = make_smem_desc(sp + k * 2048, BLK, 1024);
+          const uint64_t bd = make_smem_desc(sdo + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base + 448, ad, bd, idesc_t, k > 0);
+        }
+        umma_commit(&out_full[g]);
+        umma_commit(&ld_empty[i % LS]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int g = (warp - 2) >> 2;                     // warpgroup = pipeline stage
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const float sl2 = a.scale * 1.44269504088896f;
+    const bool valid = r < a.N;
+    uint8_t* Pt = smem + SM::OFF_PD + g * 4 * BLK;
+    uint8_t* dSt = Pt + 2 * BLK;
+    for (int i = g, j = 0; i < n_mine; i += 2, ++j) {
+      const int it = blockIdx.x + i * gridDim.x;
+      const int b = it / a.H, h = it % a.H;
+      // delta = rowsum(dO o O) straight from global (bf16, 128 B per row each)
+      float delta = 0.f;
+      if (valid) {
+        const uint4* po = reinterpret_cast<const uint4*>(a.Oin + ((int64_t)b * a.N + r) * inner + h * DH);
+        const uint4* pd = reinterpret_cast<const uint4*>(a.dO + ((int64_t)b * a.N + r) * inner + h * DH);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint4 x = po[q], y = pd[q];
+          const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            delta = fmaf(__uint_as_float(xs[t] << 16), __uint_as_float(ys[t] << 16), delta);
+            delta = fmaf(__uint_as_float(xs[t] & 0xffff0000u), __uint_as_float(ys[t] & 0xffff0000u), delta);
+          }
+        }
+      }
+      mbar_wait(&sdp_full[g], (uint32_t)(j & 1));
+      tc_fence_after();
+      const uint32_t ts = tmem_base + g * 160 + lane_off;
+      uint32_t sr[NK][16];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) tmem_ld16_nowait(ts + 16 * k, sr[k]);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) if (16 * k + q < a.N) mx = fmaxf(mx, __uint_as_float(sr[k][q]));
+      const float mb = mx * sl2;
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float e = (valid && 16 * k + q < a.N) ? ex2_approx(fmaf(__uint_as_float(sr[k][q]), sl2, -mb)) : 0.f;
+          sr[k][q] = __float_as_uint(e);
+          sum += e;
+        }
+      const float inv = valid ? 1.0f / sum : 0.f;
+      const float nds = -delta;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        uint32_t dpr[16];
+        tmem_ld16_nowait(ts + 80 + 16 * k, dpr);
+        tmem_ld_wait();
+        if (k == NK - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sdp_free[g]);     // S / dP of this stage may be overwritten (item i+2)
+        }
+        if (r < KPAD) {                                 // the tiles hold KPAD rows only
+          uint32_t wp[8], wd[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float p0 = __uint_as_float(sr[k][2 * q]) * inv, p1 = __uint_as_float(sr[k][2 * q + 1]) * inv;
+            const float d0 = p0 * (__uint_as_float(dpr[2 * q]) + nds) * a.scale;
+            const float d1 = p1 * (__uint_as_float(dpr[2 * q + 1]) + nds) * a.scale;
+            wp[q] = pack2(p0, p1);
+            wd[q] = pack2(d0, d1);
+          }
+          const int ch = (k & 3) * 2;
+          uint8_t* pb = Pt + (k >> 2) * BLK;
+          uint8_t* db = dSt + (k >> 2) * BLK;
+          *reinterpret_cast<uint4*>(pb + sw128_off(r, ch)) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+          *reinterpret_cast<uint4*>(pb + sw128_off(r, ch + 1)) = make_uint4(wp[4], wp[5], wp[6], wp[7]);
+          *reinterpret_cast<uint4*>(db + sw128_off(r, ch)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+          *reinterpret_cast<uint4*>(db + sw128_off(r, ch + 1)) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_ready[g]);
+      mbar_wait(&out_full[g], (uint32_t)(j & 1));
+      tc_fence_after();
+      bf16* dst = a.dQKV + ((int64_t)b * a.N + r) * (3 * inner) + h * DH;
+      const uint32_t to = tmem_base + 320 + lane_off;
+#pragma unroll 1
+      for (int w = 0; w < 3; ++w) {          // dQ, dK, dV rows (query r / key r)
+        uint32_t orr[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(to + w * 64 + 16 * c, orr[c]);
+        tmem_ld_wait();
+        if (w == 2) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&out_free[g]);     // the other warpgroup's item may now use dQ / dK / dV
+        }
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t u[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) u[q] = pack2(__uint_as_float(orr[c][2 * q]), __uint_as_float(orr[c][2 * q + 1]));
+            reinterpret_cast<uint4*>(dst + w * inner + 16 * c)[0] = make_uint4(u[0], u[1], u[2], u[3]);
+            reinterpret_cast<uint4*>(dst + w * inner + 16 * c)[1] = make_uint4(u[4], u[5], u[6], u[7]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ------------------------------------------------------------------ host
+static bool g_bwd2_enabled = true;      // set_option "attn_bwd2"
 static bool eligible(int N, int dh, const void* p0, int64_t ld) {
   return tc::g_tc_enabled && dh == DH && N <= 128 && (ld % 8) == 0 && (((uintptr_t)p0) & 15) == 0;
 }
@@ -490,6 +736,7 @@ static void fwd(const bf16* QKV, bf16* O, int B, int N, int H, cudaStream_t st) 
   a.O = O; a.Oin = nullptr; a.dO = nullptr; a.dQKV = nullptr;
   CUtensorMap tkv = make_map(QKV, 3 * inner, T, 3 * inner, 64, a.KPAD);
   const int grid = std::min(B * H, sm_count());
+  if (skip_mask() & SKIP_ATTN_FWD) return;
   switch (a.KPAD / 16) {
 #define DG_ATTN_F(NK_)                                                                                              \
     case NK_: {                                                                                                     \
@@ -520,6 +767,26 @@ static void bwd(const bf16* QKV, const bf16* O, const bf16* dO, bf16* dQKV, int 
   CUtensorMap tdo = make_map(dO, inner, T, inner, 64, 128);
   const int smem = (BWD_LOAD_STAGES * 4 + 4) * TILE + 256 + 1024;
   const int grid = std::min(B * H, sm_count());
+  if (skip_mask() & SKIP_ATTN_BWD) return;
+  if (g_bwd2_enabled && a.KPAD <= 80) {         // pipelined kernel (two softmax warpgroups)
+    CUtensorMap tdo2 = make_map(dO, inner, T, inner, 64, a.KPAD);
+    switch (a.KPAD / 16) {
+#define DG_ATTN_B2(NK_)                                                                                                    \
+      case NK_: {                                                                                                          \
+        constexpr int smem2 = Bwd2Smem<NK_>::TOTAL;                                                                        \
+        static bool attr2 = false;                                                                                         \
+        if (!attr2) {                                                                                                      \
+          DG_CUDA(cudaFuncSetAttribute(attn_bwd2_tc_kernel<NK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));     \
+          attr2 = true;                                                                                                    \
+        }                                                                                                                  \
+        launch_k(attn_bwd2_tc_kernel<NK_>, grid, BWD2_THREADS, smem2, st, tkv, tdo2, a);                                   \
+      } break;
+      DG_ATTN_B2(1) DG_ATTN_B2(2) DG_ATTN_B2(3) DG_ATTN_B2(4) DG_ATTN_B2(5)
+#undef DG_ATTN_B2
+    }
+    DG_LAUNCH_CHECK();
+    return;
+  }
   switch (a.KPAD / 16) {
 #define DG_ATTN_B(NK_)                                                                                              \
     case NK_: {                                                                                                     \

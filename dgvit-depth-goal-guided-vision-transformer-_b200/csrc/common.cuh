@@ -61,6 +61,14 @@ inline long long& launch_counter() {
 // mostly single-wave and latency-bound, so hiding launch + prologue latency matters.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// measurement knob (set_option "skip"): bit mask of kernel families whose launches are dropped, to read their marginal
+// cost inside the graph-replayed step off an A/B run (results are garbage with any bit set)
+enum { SKIP_MLP_FWD = 1, SKIP_MLP_BWD_X = 2, SKIP_MLP_BWD_W = 4, SKIP_ATTN_FWD = 8, SKIP_ATTN_BWD = 16, SKIP_GEMM_TC = 32,
+       SKIP_LN_BWD = 64, SKIP_REDUCE = 128, SKIP_HEADS = 256, SKIP_EMBED = 512 };
+inline int& skip_mask() {
+  static int m = 0;
+  return m;
+}
 inline bool& pdl_enabled() {
   static bool e = true;
   return e;

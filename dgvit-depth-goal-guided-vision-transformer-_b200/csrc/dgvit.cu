@@ -303,8 +303,10 @@ static void launch_ln_fwd(const float* X, const float* g, const float* b, A* Y, 
 static void launch_ln_bwd(const float* dY, const float* X, const float* mean, const float* rstd,
                           const float* gamma, float* dX_io, bf16* dX_lp, float* dgamma, float* dbeta, float* dxsum,
                           float* partial, int64_t T, int D, cudaStream_t st, ReduceList* defer = nullptr) {
-  const int wpb = 8;
-  int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 4);
+  // 16 warps per block and at most two blocks per SM: 296 partial rows for the reduction instead of 592
+  const int wpb = 16;
+  int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 2);
+  if (skip_mask() & SKIP_LN_BWD) return;
   if (defer && D % 4 == 0) partial = defer->alloc((size_t)nblocks * 3 * D); else defer = nullptr;
   const size_t smem = (size_t)wpb * 3 * D * sizeof(float);
   switch (D / 32) {
@@ -401,7 +403,7 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
   const dgvit_cfg& cfg = net.cfg;
   const float* P = net.params;
   // K1: patch embedding
-  {
+  if (!(skip_mask() & SKIP_EMBED)) {
     const int64_t total4 = (int64_t)d.B * d.P * d.pd / 4;
     DG_REQUIRE(cfg.patch_w % 4 == 0 && (((uintptr_t)img) & 15) == 0, "patchify: patch_w %% 4 and 16-byte aligned frames required");
     launch_k(patchify_kernel<A>, grid1d(total4), 256, 0, st, img, c.Pm, total4, cfg.img_h, cfg.img_w, cfg.patch_h, cfg.patch_w);
@@ -1057,10 +1059,12 @@ int dgvit_set_option(const char* name, int value) {
     DG_REQUIRE(name != nullptr, "null option name");
     if (!strcmp(name, "fork_streams")) g_fork_enabled = value != 0;
     else if (!strcmp(name, "pdl")) pdl_enabled() = value != 0;
+    else if (!strcmp(name, "skip")) skip_mask() = value;
     else if (!strcmp(name, "attention_row0")) g_row0_mode = value;
 #ifdef DGVIT_WITH_TC
     else if (!strcmp(name, "tensor_cores")) tc::g_tc_enabled = value != 0;
     else if (!strcmp(name, "debug_epilogue")) tc::g_debug = value;
+    else if (!strcmp(name, "attn_bwd2")) attn::g_bwd2_enabled = value != 0;
     else if (!strcmp(name, "mlp_split")) mlp::g_split_enabled = value != 0;
     else if (!strcmp(name, "mlp_front")) mlp::g_front_enabled = value != 0;
 #endif

@@ -253,7 +253,7 @@ struct ReduceList {
     blocks += (int)cdiv(n, 128);
   }
   void launch(cudaStream_t st) {
-    if (a.njobs) {
+    if (a.njobs && !(skip_mask() & SKIP_REDUCE)) {
       launch_k(multi_reduce_kernel, blocks, MR_WARPS * 32, 0, st, a);
       DG_LAUNCH_CHECK();
     }

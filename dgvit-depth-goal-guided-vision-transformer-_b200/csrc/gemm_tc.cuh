@@ -669,6 +669,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   }
   const int tiles = (int)(cdiv(a.M, BM) * cdiv(a.N, BN) * a.splitk);
   const int grid = std::min(tiles, sm_count());
+  if (skip_mask() & SKIP_GEMM_TC) return;
   launch_k(gemm_tc_kernel<BN, A_MN, B_MN, TC>, grid, EpiCfg<BN>::THREADS, SL::TOTAL, st, ta, tb, tc_, a);
   DG_LAUNCH_CHECK();
 }

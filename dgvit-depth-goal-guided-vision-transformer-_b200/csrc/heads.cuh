@@ -318,6 +318,7 @@ static void launch_fwd(const FwdArgs& a, cudaStream_t st) {
     attr = 227 * 1024;
   }
   dim3 grid((unsigned)std::min<int64_t>(cdiv(a.B, S), 148), (unsigned)a.nheads);
+  if (skip_mask() & SKIP_HEADS) return;
   launch_k(head_fwd_kernel, grid, FWD_THREADS, smem, st, a);
   DG_LAUNCH_CHECK();
 }
@@ -331,6 +332,7 @@ static void launch_bwd_dx(const BwdArgs& a, cudaStream_t st) {
     attr = 227 * 1024;
   }
   dim3 grid((unsigned)std::min<int64_t>(cdiv(a.B, S), 148), (unsigned)a.nheads);
+  if (skip_mask() & SKIP_HEADS) return;
   launch_k(head_bwd_dx_kernel, grid, BWD_THREADS, smem, st, a);
   DG_LAUNCH_CHECK();
 }
@@ -344,6 +346,7 @@ struct DwList {
     a.total_tiles += (int)(cdiv(N, 32) * cdiv(K, 32));
   }
   void launch(cudaStream_t st) {
+    if (skip_mask() & SKIP_HEADS) return;
     launch_k(head_dw_kernel, a.total_tiles, 256, 0, st, a);
     DG_LAUNCH_CHECK();
   }

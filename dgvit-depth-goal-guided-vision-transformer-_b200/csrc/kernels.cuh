@@ -141,42 +141,57 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ X, const float* _
 // -> part[block][3][D].  The third vector is the bias gradient of the linear layer that produced this residual
 // stream (to_out.0.bias / net.3.bias): colsum(dL/dX) in fp32, for free instead of a separate pass over dX.
 template <int VPL>
-__global__ void layernorm_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ X,
+__global__ void __launch_bounds__(512) layernorm_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ X,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const float* __restrict__ gamma, float* __restrict__ dX_io,
                                      bf16* __restrict__ dX_lp, float* __restrict__ part, int64_t T) {
   pdl_wait();
   pdl_launch();
   constexpr int D = 32 * VPL;
+  constexpr int RB = VPL <= 2 ? 4 : (VPL <= 4 ? 2 : 1);   // rows in flight per warp: the kernel is a chain of load latencies otherwise
   extern __shared__ float sm[];  // [warps][3][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float dg[VPL], db[VPL], dxs[VPL], gm[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) { dg[i] = 0.f; db[i] = 0.f; dxs[i] = 0.f; gm[i] = gamma[lane + 32 * i]; }
-  for (int64_t row = (int64_t)blockIdx.x * nw + warp; row < T; row += (int64_t)gridDim.x * nw) {
-    const float mu = mean[row], rs = rstd[row];
-    float xh[VPL], dy[VPL];
-    float s1 = 0.f, s2 = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * nw;
+  for (int64_t row0 = (int64_t)blockIdx.x * nw + warp; row0 < T; row0 += RB * stride) {
+    float mu[RB], rs[RB], xh[RB][VPL], dy[RB][VPL], dxin[RB][VPL];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int d = lane + 32 * i;
-      xh[i] = (X[row * D + d] - mu) * rs;
-      dy[i] = dY[row * D + d];
-      const float w = dy[i] * gm[i];
-      s1 += w;
-      s2 = fmaf(w, xh[i], s2);
-      dg[i] = fmaf(dy[i], xh[i], dg[i]);
-      db[i] += dy[i];
+    for (int b = 0; b < RB; ++b) {
+      const int64_t row = row0 + b * stride;
+      const bool ok = row < T;
+      mu[b] = ok ? mean[row] : 0.f; rs[b] = ok ? rstd[row] : 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int64_t e = row * D + lane + 32 * i;
+        xh[b][i] = ok ? X[e] : 0.f; dy[b][i] = ok ? dY[e] : 0.f; dxin[b][i] = ok ? dX_io[e] : 0.f;
+      }
     }
-    s1 = warp_sum(s1) * (1.0f / D);
-    s2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int d = lane + 32 * i;
-      const float nv = dX_io[row * D + d] + rs * (dy[i] * gm[i] - s1 - xh[i] * s2);
-      dX_io[row * D + d] = nv;
-      dxs[i] += nv;
-      if (dX_lp) dX_lp[row * D + d] = __float2bfloat16_rn(nv);
+    for (int b = 0; b < RB; ++b) {
+      const int64_t row = row0 + b * stride;
+      if (row >= T) break;                      // warp-uniform
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        xh[b][i] = (xh[b][i] - mu[b]) * rs[b];
+        const float w = dy[b][i] * gm[i];
+        s1 += w;
+        s2 = fmaf(w, xh[b][i], s2);
+        dg[i] = fmaf(dy[b][i], xh[b][i], dg[i]);
+        db[i] += dy[b][i];
+      }
+      s1 = warp_sum(s1) * (1.0f / D);
+      s2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int d = lane + 32 * i;
+        const float nv = dxin[b][i] + rs[b] * (dy[b][i] * gm[i] - s1 - xh[b][i] * s2);
+        dX_io[row * D + d] = nv;
+        dxs[i] += nv;
+        if (dX_lp) dX_lp[row * D + d] = __float2bfloat16_rn(nv);
+      }
     }
   }
 #pragma unroll

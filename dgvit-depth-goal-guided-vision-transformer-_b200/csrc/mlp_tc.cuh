@@ -915,6 +915,7 @@ static void fwd(const bf16* x, const bf16* W1, const float* b1, const bf16* W2, 
     DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL_FRONT));
     attr = true;
   }
+  if (skip_mask() & SKIP_MLP_FWD) return;
   const int grid = (int)cdiv(M, 128);
   // few tiles (pruned last block, batch-1 act): one 16-chunk CTA per tile is pure latency, so a cluster of 8 CTAs
   // shares each tile's hidden columns
@@ -970,10 +971,11 @@ static void bwd(const bf16* x, const bf16* dy, const bf16* W1, const float* b1, 
     attr = true;
   }
   const bool split = g_split_enabled && tiles * f::NSPLIT <= sm_count() && NC % f::NSPLIT == 0;
-  if (split) launch_k_cluster((mlp_bwd_tc_kernel<0, true>), tiles * f::NSPLIT, THREADS, b::SMEM_TOTAL, st, f::NSPLIT, tx, tdy, tw1, tw2, a);
+  if (skip_mask() & SKIP_MLP_BWD_X) {}
+  else if (split) launch_k_cluster((mlp_bwd_tc_kernel<0, true>), tiles * f::NSPLIT, THREADS, b::SMEM_TOTAL, st, f::NSPLIT, tx, tdy, tw1, tw2, a);
   else launch_k(mlp_bwd_tc_kernel<0>, tiles, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
   DG_LAUNCH_CHECK();
-  launch_k(mlp_bwd_tc_kernel<1>, NC * S, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
+  if (!(skip_mask() & SKIP_MLP_BWD_W)) launch_k(mlp_bwd_tc_kernel<1>, NC * S, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
   DG_LAUNCH_CHECK();
   if (defer) {       // the caller reduces these together with the block's other partial sums
     defer->add(partial, dW1, S, per_split, per_split);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Same-box A/B of library builds / kernel-variant options through bench.py (value is reproducible to ~0.1 % on one box).
 # usage: bash profiles/ab.sh "label1:ENV=..;ENV2=.." "label2:..." ...   e.g.  "row0fwd:DGVIT_OPTS=attention_row0=3"
-for rep in 1 2; do
+for rep in $(seq 1 ${REPS:-2}); do
 for spec in "$@"; do
   label=${spec%%:*}; envs=${spec#*:}
   ( IFS=';'; for e in $envs; do [ -n "$e" ] && export "$e"; done
