@@ -616,22 +616,6 @@ attn_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     for (int i = g, j = 0; i < n_mine; i += 2, ++j) {
       const int it = blockIdx.x + i * gridDim.x;
       const int b = it / a.H, h = it % a.H;
-      // delta = rowsum(dO o O) straight from global (bf16, 128 B per row each)
-      float delta = 0.f;
-      if (valid) {
-        const uint4* po = reinterpret_cast<const uint4*>(a.Oin + ((int64_t)b * a.N + r) * inner + h * DH);
-        const uint4* pd = reinterpret_cast<const uint4*>(a.dO + ((int64_t)b * a.N + r) * inner + h * DH);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const uint4 x = po[q], y = pd[q];
-          const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            delta = fmaf(__uint_as_float(xs[t] << 16), __uint_as_float(ys[t] << 16), delta);
-            delta = fmaf(__uint_as_float(xs[t] & 0xffff0000u), __uint_as_float(ys[t] & 0xffff0000u), delta);
-          }
-        }
-      }
       mbar_wait(&sdp_full[g], (uint32_t)(j & 1));
       tc_fence_after();
       const uint32_t ts = tmem_base + g * 160 + lane_off;
@@ -655,7 +639,17 @@ attn_bwd2_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           sum += e;
         }
       const float inv = valid ? 1.0f / sum : 0.f;
-      const float nds = -delta;
+      // delta = rowsum(dO o O) = sum_j P_j dP_j (O = P V): from the accumulators, no global read of O / dO
+      float delta = 0.f;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        uint32_t dpr[16];
+        tmem_ld16_nowait(ts + 80 + 16 * k, dpr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) delta = fmaf(__uint_as_float(sr[k][q]), __uint_as_float(dpr[q]), delta);
+      }
+      const float nds = -delta * inv;
 #pragma unroll
       for (int k = 0; k < NK; ++k) {
         uint32_t dpr[16];
