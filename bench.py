@@ -38,7 +38,7 @@ F_A, F_C = 190_371_072, 190_371_328
 FLOP_PER_SAMPLE = 4 * F_A + 5 * F_C
 # dram__bytes_read.sum + dram__bytes_write.sum of one mlp_fwd_tc_kernel launch (16640 rows, no pre-activation
 # store) from the `ncu --set full` capture summarised in profiles/ (None until captured)
-NCU_TRAFFIC_BYTES = 6957824   # profiles/r1_11_kernel_metrics_full.md (mlp_fwd_tc_kernel, 16640 rows: 6.96 MB read, 0 written)
+NCU_TRAFFIC_BYTES = 13400000  # profiles/r1_15_final_launches.md (mlp_fwd_tc_kernel<0,1>, 16640 rows: 13.4 MB read + written per launch)
 
 
 def peaks():
@@ -383,13 +383,13 @@ def run_ours(args):
     ach = dom["tflops"]
     roof = dict(bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s", frac=ach / pk["tf_sust"],
                 traffic=NCU_TRAFFIC_BYTES,
-                kernel="mlp::mlp_fwd_tc_kernel (fused fc1 + GELU + fc2 + residual + next LayerNorm, tcgen05/TMEM)",
+                kernel="mlp::mlp_fwd_tc_kernel (out-projection + LayerNorm-2 prologue, fused fc1 + GELU + fc2 + residual, next LayerNorm-1; tcgen05/TMEM)",
                 how="CUDA events around every launch of the kernel in an eager single-stream replica of the timed steps "
                     "(includes the per-launch event gap; ncu reports the same 27-28 us per cold launch)",
                 back_to_back=dict(us_per_launch=burst_us, tflops=4.0 * rows * 64 * 2048 / burst_us / 1e6,
                                   frac=4.0 * rows * 64 * 2048 / burst_us / 1e6 / pk["tf_burst"], peak=pk["tf_burst"],
                                   what="20 graph-replayed launches between one event pair, %d token rows, burst bf16 peak" % rows),
-                algorithmic_flop_per_launch="4*rows*64*2048 (8.72 GFLOP at 16640 token rows)",
+                algorithmic_flop_per_launch="4*rows*64*2048 + 2*rows*64*256 (8.72 + 0.55 GFLOP at 16640 token rows)",
                 launches_per_step=dom["launches_per_step"], kernel_ms_per_step=dom["ms_per_step"],
                 share_of_step=dom["ms_per_step"] / (ms / args.steps) if ms > 0 else None,
                 eager_ms_per_step=eager_ms_per_step, peak_source=pk["src"] + " (sustained bf16 cuBLAS)",

@@ -468,7 +468,7 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
 #ifdef DGVIT_WITH_TC
       if constexpr (std::is_same<A, bf16>::value) {
         ProfScope ps(PROF_GEMM_MLP, 4.0 * R * d.D * d.M, 0.0, st);
-        ProfScope ps2(PROF_MLP_FUSED, 4.0 * R * d.D * d.M, 0.0, st);
+        ProfScope ps2(PROF_MLP_FUSED, 4.0 * R * d.D * d.M + (front_done ? 2.0 * R * d.D * d.inner : 0.0), 0.0, st);
         mlp::LnFuse ln;
         if (!last) {   // the next block's LayerNorm-1 rides in this kernel's output stage
           const dgvit_block_layout& nb = L.block[l + 1];
@@ -565,8 +565,9 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     } else {
       const int64_t ostride = (int64_t)d.N * d.inner;
       linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, nullptr, d.B, d.D, d.inner, c.partial, st, -1, ostride, &rl);
-      // dO is zero except on the token-0 rows
-      DG_CUDA(cudaMemsetAsync(c.dO, 0, (size_t)d.T * d.inner * sizeof(A), st));
+      // dO is zero except on the token-0 rows (the single-query-row attention backward reads only those)
+      if (!(d.dh == R0_DH && d.N <= R0_MAXN && (g_row0_mode & 2) && ((((uintptr_t)B_.QKV) | ((uintptr_t)c.dO) | ((uintptr_t)c.dQKV)) & 15) == 0))
+        DG_CUDA(cudaMemsetAsync(c.dO, 0, (size_t)d.T * d.inner * sizeof(A), st));
       linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.out_w), c.dO, d.B, d.D, d.inner, EPI_NONE, nullptr, 0, st, -1,
                             nullptr, ostride);
       // expand the compact residual gradient to [T, D] (zero off token 0) for the LayerNorm-1 backward
