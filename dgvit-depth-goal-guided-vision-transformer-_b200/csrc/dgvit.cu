@@ -206,7 +206,7 @@ struct TrunkCtx {
   A *dH, *dO, *dQKV, *dXp;
   bf16* dXh;  // bf16 copy of dX (operand of the tensor-core GEMMs); null in the fp32 path
   float* dXc; bf16* dXch;   // last block: compact [B, D] residual gradient of the token-0 rows
-  size_t partial_floats;
+  size_t partial_floats, misc_floats;
   bool save;   // activations kept for a backward pass
   // residual-stream gradient in the operand dtype
   const A* dx_op() const {
@@ -245,7 +245,7 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
     c.Xout = c.L[0].Xa;  // ping-pong: Xa -> Xm -> Xa
   }
   c.dX = nullptr; c.dXn = nullptr; c.dtok = nullptr; c.dz = nullptr; c.dg_rows = nullptr; c.partial = nullptr;
-  c.dH = nullptr; c.dO = nullptr; c.dQKV = nullptr; c.dXp = nullptr; c.dXh = nullptr; c.partial_floats = 0;
+  c.dH = nullptr; c.dO = nullptr; c.dQKV = nullptr; c.dXp = nullptr; c.dXh = nullptr; c.partial_floats = 0; c.misc_floats = 0;
   c.dXc = nullptr; c.dXch = nullptr;
   if (save) {
     c.dX = cv.take<float>(d.T * d.D);
@@ -267,7 +267,9 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
     mx = std::max<int64_t>(mx, (int64_t)3 * d.D * 148 * 4 / 32 + 3 * d.D);
     // one block's worth of queued reductions (split-K dW of qkv / out / both MLP matrices + LayerNorm partials)
     const int64_t per_block = (int64_t)32 * (4 * d.inner * d.D + 2 * d.D * d.M) + (int64_t)8 * d.D * 148 * 4 + 4 * d.M + 4096;
-    c.partial_floats = (size_t)std::max<int64_t>(mx * 32, per_block);
+    // + the reductions outside the blocks (rms gain, pos embedding, patch dW split-K + bias)
+    c.misc_floats = (size_t)(64 * d.D + (int64_t)32 * d.N * d.D + (int64_t)32 * d.D * d.pd + 128 * d.D + 1024);
+    c.partial_floats = (size_t)std::max<int64_t>(mx * 32, per_block) + c.misc_floats;
     c.partial = cv.take<float>(c.partial_floats);
   }
 }
@@ -399,7 +401,7 @@ static bool mlp_fused(const Dims& d, int64_t R, const void* xn2, const void* w1,
 // GoT.forward (vn/GoalFormer.py:156-171) given the goal token tok[B,D]; writes c.z.
 template <typename A>
 static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const float* img,
-                          const DropDev& drop, TrunkCtx<A>& c, cudaStream_t st) {
+                          const DropDev& drop, TrunkCtx<A>& c, cudaStream_t st, const GoalTok& gt) {
   const dgvit_cfg& cfg = net.cfg;
   const float* P = net.params;
   // K1: patch embedding
@@ -410,11 +412,23 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
     DG_LAUNCH_CHECK();
     linear_fwd<A, A, float>(c.Pm, WSel<A>::w(net, L.patch_w), c.Xp, (int64_t)d.B * d.P, d.D, d.pd, EPI_BIAS,
                             P + L.patch_b, st);
-    const int64_t tot2 = d.T * d.D;
-    launch_k(embed_assemble_kernel, grid1d(tot2), 256, 0, st, c.tok, c.Xp, P + L.pos, c.L[0].Xa, drop, tot2, d.N, d.D);
-    DG_LAUNCH_CHECK();
+    // goal token (fc_embed) + cat + pos + dropout + the first block's LayerNorm-1 in one warp-per-row kernel
+    {
+      const dgvit_block_layout& b0 = L.block[0];
+      LayerBuf<A>& B0 = c.L[0];
+      const int wpb = 8;
+      const unsigned grid = (unsigned)cdiv(d.T, wpb);
+      switch (d.D / 32) {
+#define EMB(V) case V: launch_k(embed_ln_kernel<A, V>, grid, wpb * 32, 0, st, gt, c.tok, (const float*)c.Xp, P + L.pos, B0.Xa, drop, \
+                                P + b0.ln1_w, P + b0.ln1_b, B0.Xn1, B0.mean1, B0.rstd1, d.T, d.N); break;
+        EMB(1) EMB(2) EMB(3) EMB(4) EMB(5) EMB(6) EMB(7) EMB(8)
+#undef EMB
+        default: fail(DGVIT_ERR_ARG, "unsupported dim %d", d.D);
+      }
+      DG_LAUNCH_CHECK();
+    }
   }
-  bool ln1_done = false;
+  bool ln1_done = !(skip_mask() & SKIP_EMBED);      // block 0's LayerNorm-1 ran inside embed_ln_kernel
   for (int l = 0; l < d.L; ++l) {
     const dgvit_block_layout& b = L.block[l];
     LayerBuf<A>& B_ = c.L[l];
@@ -504,13 +518,21 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
   launch_k(pool_rmsnorm_bwd_kernel, d.B, 128, 0, st, c.Xout, P + L.rms_g, c.dz, c.dXc, c.dXch, c.dg_rows, d.B, 1, d.D,
                                                 sqrtf((float)d.D));
   DG_LAUNCH_CHECK();
+  // reductions outside the blocks (RMSNorm gain, position embedding, patch embedding) are queued in the tail of the
+  // partial-sum workspace and done by one launch at the end
+  ReduceList rl_misc(c.partial + c.partial_floats - c.misc_floats, c.misc_floats);
+  const size_t block_floats = c.partial_floats - c.misc_floats;
   {  // dg = sum_b dg_rows
     const int S = std::max(1, std::min(64, d.B / 4));
     dim3 grid((unsigned)cdiv(d.D, 256), (unsigned)S);
-    launch_k(colsum_partial_kernel<float>, grid, 128, 0, st, c.dg_rows, d.D, c.partial, d.B, d.D, cdiv(d.B, S));
+    float* part = rl_misc.alloc((size_t)S * d.D);
+    launch_k(colsum_partial_kernel<float>, grid, 128, 0, st, c.dg_rows, d.D, part, d.B, d.D, cdiv(d.B, S));
     DG_LAUNCH_CHECK();
-    launch_k(reduce_partials_kernel, 1, 256, 0, st, c.partial, G + L.rms_g, S, d.D);
-    DG_LAUNCH_CHECK();
+    if (d.D % 4 == 0) rl_misc.add(part, G + L.rms_g, S, d.D, d.D);
+    else {
+      launch_k(reduce_partials_kernel, 1, 256, 0, st, part, G + L.rms_g, S, d.D);
+      DG_LAUNCH_CHECK();
+    }
   }
   for (int l = d.L - 1; l >= 0; --l) {
     const dgvit_block_layout& b = L.block[l];
@@ -522,7 +544,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     bf16* dXr_lp = last ? c.dXch : c.dXh;
     const A* dxop = last ? c.dxc_op() : c.dx_op();
     // every partial-sum reduction of this block is queued here and done by one launch at the end of the block
-    ReduceList rl(c.partial, c.partial_floats);
+    ReduceList rl(c.partial, block_floats);
     // ---- MLP block.  dXr = dL/dX_out
     {
     TagScope mlp_tag(PROF_GEMM_MLP);
@@ -532,7 +554,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     if constexpr (std::is_same<A, bf16>::value) {
       if (fused) {
         // the fused forward saved nothing: both backward launches recompute the pre-activation on chip
-        DG_REQUIRE(mlp::bwd_partial_floats(R, d.M) <= c.partial_floats, "mlp::bwd partial buffer too small");
+        DG_REQUIRE(mlp::bwd_partial_floats(R, d.M) <= block_floats, "mlp::bwd partial buffer too small");
         ProfScope ps(PROF_GEMM_MLP, 8.0 * R * d.D * d.M, 0.0, st);
         // net.3.bias gradient = colsum(dL/dX_out): below the top block it falls out of the next block's LayerNorm-1 backward
         mlp::bwd(B_.Xn2, dxop, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), c.dXn, G + b.fc1_w,
@@ -590,13 +612,18 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
   DG_LAUNCH_CHECK();
   {
     const int S = std::max(1, std::min(32, d.B / 8));
-    launch_k(dpos_kernel, dim3(d.N, S), 128, 0, st, c.dX, c.partial, drop, d.B, d.N, d.D);
-    DG_LAUNCH_CHECK();
     const int64_t n = (int64_t)d.N * d.D;
-    launch_k(reduce_partials_kernel, reduce_grid(n), 256, 0, st, c.partial, G + L.pos, S, n);
+    float* part = rl_misc.alloc((size_t)S * n);
+    launch_k(dpos_kernel, dim3(d.N, S), 128, 0, st, c.dX, part, drop, d.B, d.N, d.D);
     DG_LAUNCH_CHECK();
+    if (n % 4 == 0) rl_misc.add(part, G + L.pos, S, n, n);
+    else {
+      launch_k(reduce_partials_kernel, reduce_grid(n), 256, 0, st, part, G + L.pos, S, n);
+      DG_LAUNCH_CHECK();
+    }
   }
-  linear_bwd_w<A, A>(c.dXp, c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st);
+  linear_bwd_w<A, A>(c.dXp, c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st, -1, -1, &rl_misc);
+  rl_misc.launch(st);
 }
 
 // zero the gradient ranges the reference leaves as None (so the arena is fully defined)
@@ -640,11 +667,9 @@ static void actor_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
   const float* P = net.params;
   DG_REQUIRE(io.img && io.pstate && io.action_scale && io.action_bias, "actor_forward: null input");
   DG_REQUIRE(io.eps || io.drop.rng_state, "actor_forward: provide eps or drop.rng_state");
-  launch_k(goal_embed_kernel, (unsigned)cdiv((int64_t)d.B * d.D, 256), 256, 0, st, io.pstate, P + L.embed_w, P + L.embed_b,
-                                                                             c.t.tok, d.B, d.D, d.nps, 0);
-  DG_LAUNCH_CHECK();
   const DropDev drop = make_drop(io.drop, d, io.sample_offset);
-  trunk_forward<A>(net, L, d, io.img, drop, c.t, st);
+  const GoalTok gt{io.pstate, P + L.embed_w, P + L.embed_b, d.nps, 0};      // fc_embed, no activation (got_sac_network.py:224)
+  trunk_forward<A>(net, L, d, io.img, drop, c.t, st, gt);
   {  // fc1 -> relu -> fc2 -> relu -> (mean_linear | log_std_linear), one launch
     heads::FwdArgs h;
     memset(&h, 0, sizeof(h));
@@ -750,11 +775,9 @@ static void critic_forward(const dgvit_net& net, const dgvit_layout& L, const Di
                            int64_t sample_offset, CriticCtx<A>& c, cudaStream_t st) {
   const float* P = net.params;
   DG_REQUIRE(io.img && io.pstate && io.action && io.q1 && io.q2, "critic_forward: null input/output");
-  launch_k(goal_embed_kernel, (unsigned)cdiv((int64_t)d.B * d.D, 256), 256, 0, st, io.pstate, P + L.embed_w, P + L.embed_b,
-                                                                             c.t.tok, d.B, d.D, d.nps, 1);
-  DG_LAUNCH_CHECK();
   const DropDev drop = make_drop(io.drop, d, sample_offset);
-  trunk_forward<A>(net, L, d, io.img, drop, c.t, st);
+  const GoalTok gt{io.pstate, P + L.embed_w, P + L.embed_b, d.nps, 1};      // relu(fc_embed) (got_sac_network.py:111)
+  trunk_forward<A>(net, L, d, io.img, drop, c.t, st, gt);
   critic_heads_forward(net, L, d, c.t.z, io.action, c.xcat, c.h1a, c.h2a, c.h1b, c.h2b, io.q1, io.q2, st);
 }
 

@@ -65,6 +65,58 @@ __global__ void embed_assemble_kernel(const float* __restrict__ tok, const float
   }
 }
 
+// The same fused with the goal-token embedding (fc_embed, optional ReLU; vn/got_sac_network.py:111,224) and the first
+// block's LayerNorm-1: one warp per token row (D = 32 * VPL).  Writes tok [B,D], X0 (fp32 residual stream), LN(X0) in the
+// operand dtype, mean, rstd.
+struct GoalTok {
+  const float* ps; const float* W; const float* b;   // pstate [B,nps], fc_embed.weight [D,nps], .bias [D]
+  int nps, relu;
+};
+template <typename A, int VPL>
+__global__ void embed_ln_kernel(GoalTok gt, float* __restrict__ tok, const float* __restrict__ Xp,
+                                const float* __restrict__ pos, float* __restrict__ X0, DropDev drop,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, A* __restrict__ Y,
+                                float* __restrict__ mean, float* __restrict__ rstd, int64_t T, int N) {
+  pdl_wait();
+  pdl_launch();
+  constexpr int D = 32 * VPL;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= T) return;
+  const int n = (int)(row % N);
+  const int64_t b = row / N;
+  float v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int d = lane + 32 * i;
+    float x;
+    if (n == 0) {
+      x = gt.b[d];
+      for (int j = 0; j < gt.nps; ++j) x = fmaf(gt.W[d * gt.nps + j], gt.ps[b * gt.nps + j], x);
+      if (gt.relu) x = fmaxf(x, 0.f);
+      tok[b * D + d] = x;
+    } else {
+      x = Xp[(b * (N - 1) + (n - 1)) * D + d];
+    }
+    x = (x + pos[n * D + d]) * drop_factor(drop, row * D + d);
+    X0[row * D + d] = x;
+    v[i] = x;
+    s += x;
+  }
+  const float mu = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) { const float c = v[i] - mu; q = fmaf(c, c, q); }
+  const float rs = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int d = lane + 32 * i;
+    stf(Y + row * D + d, (v[i] - mu) * rs * gamma[d] + beta[d]);
+  }
+  if (lane == 0 && mean) { mean[row] = mu; rstd[row] = rs; }
+}
+
 // backward of the above: dXp (compact, activation dtype), dtok (through the optional ReLU)
 template <typename A>
 __global__ void embed_bwd_kernel(const float* __restrict__ dX0, const float* __restrict__ tok,
