@@ -490,7 +490,7 @@ template <int NK> struct Bwd2Smem {
   static constexpr int LS = 3;                          // load stages: Q | K | V | dO
   static constexpr int OFF_PD = 0;                      // stage g: P block0, block1, dS block0, block1
   static constexpr int OFF_LD = 2 * 4 * BLK;
-  static constexpr int OFF_BAR = OFF_LD + LS * 4 * BLK + 8192;    // 8 KB of slack behind the last tile (A-operand over-read)
+  static constexpr int OFF_BAR = OFF_LD + LS * 4 * BLK + 16384;   // slack behind the last tile: a 128-row A operand over-reads up to 16 KB - BLK
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
   static_assert(NK <= 5 && TOTAL <= 232448, "smem budget");
 };

@@ -200,6 +200,7 @@ struct LayerBuf {
 template <typename A>
 struct TrunkCtx {
   A* Pm; float* Xp; float* tok; float* Xout; float* z;
+  const A* Pm_ext = nullptr;   // patch matrix computed elsewhere for the same frames (the update patchifies s and s' once)
   LayerBuf<A> L[DGVIT_MAX_DEPTH];
   // backward scratch (only when saved)
   float *dX, *dXn, *dtok, *dz, *dg_rows, *partial;
@@ -398,6 +399,14 @@ static bool mlp_fused(const Dims& d, int64_t R, const void* xn2, const void* w1,
 }
 
 // ------------------------------------------------------------------ trunk forward
+// Rearrange 'b (h p1) (w p2) -> b (h w) (p1 p2)' (vn/GoalFormer.py:138) + cast to the operand dtype: the A matrix of the patch GEMM
+template <typename A>
+static void launch_patchify(const float* img, A* Pm, int B, const Dims& d, const dgvit_cfg& cfg, cudaStream_t st) {
+  const int64_t total4 = (int64_t)B * d.P * d.pd / 4;
+  DG_REQUIRE(cfg.patch_w % 4 == 0 && (((uintptr_t)img) & 15) == 0, "patchify: patch_w %% 4 and 16-byte aligned frames required");
+  launch_k(patchify_kernel<A>, grid1d(total4), 256, 0, st, img, Pm, total4, cfg.img_h, cfg.img_w, cfg.patch_h, cfg.patch_w);
+  DG_LAUNCH_CHECK();
+}
 // GoT.forward (vn/GoalFormer.py:156-171) given the goal token tok[B,D]; writes c.z.
 template <typename A>
 static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const float* img,
@@ -406,11 +415,8 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
   const float* P = net.params;
   // K1: patch embedding
   if (!(skip_mask() & SKIP_EMBED)) {
-    const int64_t total4 = (int64_t)d.B * d.P * d.pd / 4;
-    DG_REQUIRE(cfg.patch_w % 4 == 0 && (((uintptr_t)img) & 15) == 0, "patchify: patch_w %% 4 and 16-byte aligned frames required");
-    launch_k(patchify_kernel<A>, grid1d(total4), 256, 0, st, img, c.Pm, total4, cfg.img_h, cfg.img_w, cfg.patch_h, cfg.patch_w);
-    DG_LAUNCH_CHECK();
-    linear_fwd<A, A, float>(c.Pm, WSel<A>::w(net, L.patch_w), c.Xp, (int64_t)d.B * d.P, d.D, d.pd, EPI_BIAS,
+    if (!c.Pm_ext) launch_patchify<A>(img, c.Pm, d.B, d, cfg, st);
+    linear_fwd<A, A, float>(c.Pm_ext ? c.Pm_ext : c.Pm, WSel<A>::w(net, L.patch_w), c.Xp, (int64_t)d.B * d.P, d.D, d.pd, EPI_BIAS,
                             P + L.patch_b, st);
     // goal token (fc_embed) + cat + pos + dropout + the first block's LayerNorm-1 in one warp-per-row kernel
     {
@@ -622,7 +628,8 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
       DG_LAUNCH_CHECK();
     }
   }
-  linear_bwd_w<A, A>(c.dXp, c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st, -1, -1, &rl_misc);
+  linear_bwd_w<A, A>(c.dXp, c.Pm_ext ? c.Pm_ext : c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st, -1,
+                     -1, &rl_misc);
   rl_misc.launch(st);
 }
 
@@ -916,6 +923,11 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   ForkState& f0 = fork_state();
   ForkState f = f0;
   if (!g_fork_enabled) { f.aux[0] = st; f.aux[1] = st; }      // single-stream mode (per-kernel timing)
+  // the five forward passes of an update see two distinct frame batches: patchify s and s' once, before the fork
+  launch_patchify<A>(b.obs, w.actor_s.t.Pm, da.B, da, s.actor.cfg, st);
+  launch_patchify<A>(b.next_obs, w.actor_tmp.t.Pm, d.B, d, s.actor.cfg, st);
+  w.actor_s.t.Pm_ext = w.actor_s.t.Pm; w.critic_s.t.Pm_ext = w.actor_s.t.Pm;
+  w.actor_tmp.t.Pm_ext = w.actor_tmp.t.Pm; w.critic_tmp.t.Pm_ext = w.actor_tmp.t.Pm;
   DG_CUDA(cudaEventRecord(f.fork, st));
   DG_CUDA(cudaStreamWaitEvent(f.aux[0], f.fork, 0));
   DG_CUDA(cudaStreamWaitEvent(f.aux[1], f.fork, 0));
@@ -972,6 +984,8 @@ static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   make_layout(s.critic.cfg, Lc);
   const bool shadow = s.precision == DGVIT_BF16;
   adam_step(s.critic, Lc, s.critic_opt, nullptr, 0.f, shadow, st);               // DRL.py:402
+  // the patch matrix of s was written by phase 1 (same workspace) into the saved actor context
+  w.critic_tmp.t.Pm_ext = w.actor_s.t.Pm; w.actor_s.t.Pm_ext = w.actor_s.t.Pm; w.critic_s.t.Pm_ext = w.actor_s.t.Pm;
   // ---- q_pi = critic(s, pi) with the UPDATED critic (pi, log_pi come from phase 1)   (DRL.py:406-407)
   dgvit_actor_io ai; memset(&ai, 0, sizeof(ai));
   ai.img = b.obs; ai.pstate = b.pobs; ai.eps = nz ? nz->eps_pi : nullptr;
