@@ -1,16 +1,20 @@
 // mlp_tc.cuh — fused GELU-MLP for sm_100a, forward and backward (FeedForward.forward + residual,
 // vn/GoalFormer.py:39-50,104):
 //
-//     out = x + W2 gelu(W1 LN(x) + b1) + b2        (LN applied by the preceding kernel)
+//     out = x + W2 gelu(W1 LN(x) + b1) + b2
 //
 // The 2048-wide hidden activation never leaves the SM in either direction.
 //
-// forward (mlp_fwd_tc_kernel): one CTA per 128-token tile.  For each 128-column hidden chunk GEMM1
-// (tcgen05, K = 64) lands in TMEM, 16 epilogue warps add the bias, apply GELU and write the chunk
-// straight into a 128B-swizzled shared-memory tile that is the A operand of GEMM2, whose [128 x 64]
+// forward (mlp_fwd_tc_kernel<SPLIT, FRONT>): one CTA per 128-token tile.  For each 128-column hidden chunk GEMM1
+// (tcgen05, K = 64) lands in TMEM, two ping-pong groups of 8 epilogue warps add the bias, apply GELU and write the
+// chunk straight into a 128B-swizzled shared-memory tile that is the A operand of GEMM2, whose [128 x 64]
 // fp32 accumulator stays in TMEM across all chunks.  Weight chunks stream through TMA rings (L2
 // resident: 512 KB per layer).  Nothing but x and the output touches HBM: the backward recomputes
 // the pre-activation instead of reading a saved copy (a K = 64 GEMM is cheaper than 4 KB/token).
+// The kernel also absorbs what surrounds the MLP in a transformer block (vn/GoalFormer.py:81-82,103-104):
+//   FRONT  prologue: x_m = to_out(o) + x_a ; LN2(x_m) written straight into GEMM1's A tile (no LN(x) input needed)
+//   output stage   : the next block's LayerNorm-1 of the result (fp32 x, bf16 LN(x), mean, rstd)
+//   SPLIT          : few token tiles -> a cluster of 8 CTAs shares a tile's hidden columns, reduce-scatter over DSMEM
 //
 // backward (mlp_bwd_tc_kernel<MODE>): two launches of one kernel over (token tile, hidden chunk) pairs.
 // Per pair, from the smem images of X (LN output), dY, W1[chunk], W2[:, chunk]:
@@ -164,9 +168,12 @@ static_assert(SMEM_TOTAL <= 232448, "smem budget");
 
 // optional timeline instrumentation (DGVIT_MLP_TRACE builds only): CTA 0 records clock64() at pipeline events
 #ifdef DGVIT_MLP_TRACE
+__device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define MLP_GT(idx) do { if (a.trace && threadIdx.x == 64) a.trace[2048 + (blockIdx.x & 255) * 4 + (idx)] = gtime_ns(); } while (0)
 #define MLP_TRACE(slot, idx) do { if (a.trace && blockIdx.x == 0 && (lane == 0 || warp < 2)) a.trace[(slot) * 64 + (idx)] = clock64(); } while (0)
 #else
 #define MLP_TRACE(slot, idx) do { } while (0)
+#define MLP_GT(idx) do { } while (0)
 #endif
 
 struct MlpArgs {
@@ -220,6 +227,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int NC = SPLIT ? a.HID / HC / NSPLIT : a.HID / HC;          // chunks of this CTA
   const int cbase = rank * NC;                                      // first hidden chunk of this CTA
   if (warp == 2) MLP_TRACE(12, 0);
+  MLP_GT(0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
@@ -242,6 +250,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   pdl_wait();
   pdl_launch();
   if (warp == 2) MLP_TRACE(12, 2);
+  MLP_GT(1);
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -569,6 +578,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 2) MLP_TRACE(12, 7);
+  MLP_GT(2);
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
