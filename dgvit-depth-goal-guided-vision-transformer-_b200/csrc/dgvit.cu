@@ -305,7 +305,8 @@ static void launch_ln_fwd(const float* X, const float* g, const float* b, A* Y, 
 // dxsum (optional): receives colsum over rows of the updated dX_io (a bias gradient, see layernorm_bwd_kernel)
 static void launch_ln_bwd(const float* dY, const float* X, const float* mean, const float* rstd,
                           const float* gamma, float* dX_io, bf16* dX_lp, float* dgamma, float* dbeta, float* dxsum,
-                          float* partial, int64_t T, int D, cudaStream_t st, ReduceList* defer = nullptr) {
+                          float* partial, int64_t T, int D, cudaStream_t st, ReduceList* defer = nullptr,
+                          const float* dX_row0 = nullptr, int Ntok = 1) {
   // 16 warps per block and at most two blocks per SM: 296 partial rows for the reduction instead of 592
   const int wpb = 16;
   int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 2);
@@ -313,7 +314,7 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
   if (defer && D % 4 == 0) partial = defer->alloc((size_t)nblocks * 3 * D); else defer = nullptr;
   const size_t smem = (size_t)wpb * 3 * D * sizeof(float);
   switch (D / 32) {
-#define LNB(V) case V: launch_k(layernorm_bwd_kernel<V>, nblocks, wpb * 32, smem, st, dY, X, mean, rstd, gamma, dX_io, dX_lp, partial, T); break;
+#define LNB(V) case V: launch_k(layernorm_bwd_kernel<V>, nblocks, wpb * 32, smem, st, dY, X, mean, rstd, gamma, dX_io, dX_lp, partial, T, dX_row0, Ntok); break;
     LNB(1) LNB(2) LNB(3) LNB(4) LNB(5) LNB(6) LNB(7) LNB(8)
 #undef LNB
     default: fail(DGVIT_ERR_ARG, "unsupported dim %d", D);
@@ -410,7 +411,7 @@ static void launch_patchify(const float* img, A* Pm, int B, const Dims& d, const
 // GoT.forward (vn/GoalFormer.py:156-171) given the goal token tok[B,D]; writes c.z.
 template <typename A>
 static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const float* img,
-                          const DropDev& drop, TrunkCtx<A>& c, cudaStream_t st, const GoalTok& gt) {
+                          const DropDev& drop, TrunkCtx<A>& c, cudaStream_t st, const GoalTok& gt, bool fuse_rms = false) {
   const dgvit_cfg& cfg = net.cfg;
   const float* P = net.params;
   // K1: patch embedding
@@ -508,10 +509,13 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
                               B_.Xm);
     }
   }
-  // c.Xout is compact [B, D] (token-0 rows of the last block)
-  launch_k(pool_rmsnorm_fwd_kernel, (unsigned)cdiv(d.B, 8), 256, 0, st, c.Xout, P + L.rms_g, c.z, d.B, 1, d.D,
-                                                                   sqrtf((float)d.D));
-  DG_LAUNCH_CHECK();
+  // c.Xout is compact [B, D] (token-0 rows of the last block); cls pooling + RMSNorm -> c.z, unless the caller's head
+  // kernel does it while staging its input (fuse_rms)
+  if (!fuse_rms) {
+    launch_k(pool_rmsnorm_fwd_kernel, (unsigned)cdiv(d.B, 8), 256, 0, st, c.Xout, P + L.rms_g, c.z, d.B, 1, d.D,
+                                                                     sqrtf((float)d.D));
+    DG_LAUNCH_CHECK();
+  }
 }
 
 // ------------------------------------------------------------------ trunk backward
@@ -598,10 +602,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
         DG_CUDA(cudaMemsetAsync(c.dO, 0, (size_t)d.T * d.inner * sizeof(A), st));
       linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.out_w), c.dO, d.B, d.D, d.inner, EPI_NONE, nullptr, 0, st, -1,
                             nullptr, ostride);
-      // expand the compact residual gradient to [T, D] (zero off token 0) for the LayerNorm-1 backward
-      const int64_t tot = d.T * d.D;
-      launch_k(scatter_row0_kernel, grid1d(tot), 256, 0, st, c.dXc, c.dX, tot, d.N, d.D);
-      DG_LAUNCH_CHECK();
+      // (the LayerNorm-1 backward below reads the compact residual gradient directly: zero off token 0)
     }
     if (!(last && launch_attention_row0<A>(B_.QKV, (A*)nullptr, (const A*)c.dO, c.dQKV, d, st)))
       launch_attention_bwd<A>(B_.QKV, B_.O, c.dO, c.dQKV, d, st);
@@ -609,7 +610,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     linear_bwd_x<A, A, float>(c.dQKV, WSel<A>::w(net, b.qkv_w), c.dXn, d.T, 3 * d.inner, d.D, EPI_NONE, nullptr, 0, st);
     // c.dX becomes dL/dX_a = gradient of the previous block's output: its column sums are that block's net.3.bias gradient
     launch_ln_bwd(c.dXn, B_.Xa, B_.mean1, B_.rstd1, P + b.ln1_w, c.dX, c.dXh, G + b.ln1_w, G + b.ln1_b,
-                  l > 0 ? G + L.block[l - 1].fc2_b : nullptr, c.partial, d.T, d.D, st, &rl);
+                  l > 0 ? G + L.block[l - 1].fc2_b : nullptr, c.partial, d.T, d.D, st, &rl, last ? c.dXc : nullptr, d.N);
     rl.launch(st);
   }
   // ---- embedding.  c.dX = dL/dX0 (post-dropout)
@@ -676,12 +677,12 @@ static void actor_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
   DG_REQUIRE(io.eps || io.drop.rng_state, "actor_forward: provide eps or drop.rng_state");
   const DropDev drop = make_drop(io.drop, d, io.sample_offset);
   const GoalTok gt{io.pstate, P + L.embed_w, P + L.embed_b, d.nps, 0};      // fc_embed, no activation (got_sac_network.py:224)
-  trunk_forward<A>(net, L, d, io.img, drop, c.t, st, gt);
-  {  // fc1 -> relu -> fc2 -> relu -> (mean_linear | log_std_linear), one launch
+  trunk_forward<A>(net, L, d, io.img, drop, c.t, st, gt, /*fuse_rms=*/true);
+  {  // cls pooling + RMSNorm -> fc1 -> relu -> fc2 -> relu -> (mean_linear | log_std_linear), one launch
     heads::FwdArgs h;
     memset(&h, 0, sizeof(h));
     h.nheads = 1; h.B = d.B; h.K1 = d.D; h.K2 = 0; h.H2 = 128; h.NOa = d.na; h.NOb = d.na;
-    h.x1 = c.t.z;
+    h.x1 = c.t.z; h.xraw = c.t.Xout; h.rms_g = P + L.rms_g; h.z_out = c.t.z;
     h.w[0] = heads::HeadW{P + L.fc1_w, P + L.fc1_b, P + L.fc2_w, P + L.fc2_b, P + L.mean_w, P + L.mean_b,
                           P + L.lstd_w, P + L.lstd_b, c.h1, c.h2, c.mean_raw, c.lstd_raw};
     heads::launch_fwd(h, st);
@@ -762,14 +763,15 @@ static void carve_critic(Carver& cv, const Dims& d, bool save, CriticCtx<A>& c) 
   c.dxb = cv.take<float>((int64_t)d.B * (d.D + d.na));
 }
 
-static void critic_heads_forward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const float* z,
+static void critic_heads_forward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, float* z,
                                  const float* action, float* xcat, float* h1a, float* h2a, float* h1b, float* h2b,
-                                 float* q1, float* q2, cudaStream_t st) {
+                                 float* q1, float* q2, cudaStream_t st, const float* xraw = nullptr) {
   const float* P = net.params;
   heads::FwdArgs h;
   memset(&h, 0, sizeof(h));
   h.nheads = 2; h.B = d.B; h.K1 = d.D; h.K2 = d.na; h.H2 = 32; h.NOa = d.na; h.NOb = 0;
   h.x1 = z; h.x2 = action; h.xcat = xcat;
+  if (xraw) { h.xraw = xraw; h.rms_g = P + L.rms_g; h.z_out = z; }   // cls pooling + RMSNorm while staging the input
   h.w[0] = heads::HeadW{P + L.fc1_w, P + L.fc1_b, P + L.fc2_w, P + L.fc2_b, P + L.fc3_w, P + L.fc3_b, nullptr, nullptr,
                         h1a, h2a, q1, nullptr};
   h.w[1] = heads::HeadW{P + L.fc11_w, P + L.fc11_b, P + L.fc21_w, P + L.fc21_b, P + L.fc31_w, P + L.fc31_b, nullptr,
@@ -784,8 +786,8 @@ static void critic_forward(const dgvit_net& net, const dgvit_layout& L, const Di
   DG_REQUIRE(io.img && io.pstate && io.action && io.q1 && io.q2, "critic_forward: null input/output");
   const DropDev drop = make_drop(io.drop, d, sample_offset);
   const GoalTok gt{io.pstate, P + L.embed_w, P + L.embed_b, d.nps, 1};      // relu(fc_embed) (got_sac_network.py:111)
-  trunk_forward<A>(net, L, d, io.img, drop, c.t, st, gt);
-  critic_heads_forward(net, L, d, c.t.z, io.action, c.xcat, c.h1a, c.h2a, c.h1b, c.h2b, io.q1, io.q2, st);
+  trunk_forward<A>(net, L, d, io.img, drop, c.t, st, gt, /*fuse_rms=*/true);
+  critic_heads_forward(net, L, d, c.t.z, io.action, c.xcat, c.h1a, c.h2a, c.h1b, c.h2b, io.q1, io.q2, st, c.t.Xout);
 }
 
 template <typename A>

@@ -27,6 +27,9 @@ struct FwdArgs {
   int nheads, B, K1, K2, H2, NOa, NOb;
   const float *x1, *x2;     // input = [x1 | x2] (x2 optional: the critic's action)
   float* xcat;              // optional: materialised [B, K1+K2] input (needed by the dW kernel when K2 > 0)
+  // optional fused cls pooling + RMSNorm (vn/GoalFormer.py:167-170,120-122): x1 = xraw / max(|xraw|, 1e-12) * sqrt(K1) * g,
+  // computed here from the trunk's token-0 rows and written to z_out (= the buffer x1 points to) for the backward
+  const float* xraw; const float* rms_g; float* z_out;
 };
 
 __host__ __device__ __forceinline__ int odd_pitch(int k) { return k | 1; }
@@ -85,8 +88,27 @@ __global__ void __launch_bounds__(FWD_THREADS) head_fwd_kernel(FwdArgs a) {
   const int j = tid & (H1 - 1), q = tid >> 7;
   for (int s0 = blockIdx.x * S; s0 < a.B; s0 += gridDim.x * S) {
     __syncthreads();
+    if (a.xraw) {              // RMSNorm of the token-0 rows: warp s normalises sample s0 + s
+      const int s = tid >> 5, lane = tid & 31, b = s0 + s;
+      if (s < S) {
+        float q = 0.f;
+        if (b < a.B) for (int d = lane; d < a.K1; d += 32) { const float x = a.xraw[(int64_t)b * a.K1 + d]; q = fmaf(x, x, q); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float sc = sqrtf((float)a.K1) / fmaxf(sqrtf(q), 1e-12f);
+        for (int d = lane; d < a.K1; d += 32) {
+          const float v = b < a.B ? a.xraw[(int64_t)b * a.K1 + d] * sc * a.rms_g[d] : 0.f;
+          xs[d * S + s] = v;
+          if (b < a.B && blockIdx.y == 0) {
+            a.z_out[(int64_t)b * a.K1 + d] = v;
+            if (a.xcat) a.xcat[(int64_t)b * K0 + d] = v;
+          }
+        }
+      }
+    }
     for (int i = tid; i < K0 * S; i += FWD_THREADS) {
       const int s = i / K0, k = i % K0, b = s0 + s;
+      if (a.xraw && k < a.K1) continue;
       float v = 0.f;
       if (b < a.B) v = k < a.K1 ? a.x1[(int64_t)b * a.K1 + k] : a.x2[(int64_t)b * a.K2 + (k - a.K1)];
       xs[k * S + s] = v;

@@ -196,7 +196,10 @@ template <int VPL>
 __global__ void __launch_bounds__(512) layernorm_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ X,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const float* __restrict__ gamma, float* __restrict__ dX_io,
-                                     bf16* __restrict__ dX_lp, float* __restrict__ part, int64_t T) {
+                                     bf16* __restrict__ dX_lp, float* __restrict__ part, int64_t T,
+                                     const float* __restrict__ dX_row0, int Ntok) {
+  // dX_row0 (optional, [T / Ntok, D]): the incoming residual gradient is zero except on token 0 of every sample, where it
+  // is this compact array (last transformer block); dX_io is then write-only.
   pdl_wait();
   pdl_launch();
   constexpr int D = 32 * VPL;
@@ -217,7 +220,9 @@ __global__ void __launch_bounds__(512) layernorm_bwd_kernel(const float* __restr
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         const int64_t e = row * D + lane + 32 * i;
-        xh[b][i] = ok ? X[e] : 0.f; dy[b][i] = ok ? dY[e] : 0.f; dxin[b][i] = ok ? dX_io[e] : 0.f;
+        xh[b][i] = ok ? X[e] : 0.f; dy[b][i] = ok ? dY[e] : 0.f;
+        if (dX_row0) dxin[b][i] = (ok && row % Ntok == 0) ? dX_row0[(row / Ntok) * D + lane + 32 * i] : 0.f;
+        else dxin[b][i] = ok ? dX_io[e] : 0.f;
       }
     }
 #pragma unroll
