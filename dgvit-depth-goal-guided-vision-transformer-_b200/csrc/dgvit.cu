@@ -207,6 +207,8 @@ struct TrunkCtx {
   A *dH, *dO, *dQKV, *dXp;
   bf16* dXh;  // bf16 copy of dX (operand of the tensor-core GEMMs); null in the fp32 path
   float* dXc; bf16* dXch;   // last block: compact [B, D] residual gradient of the token-0 rows
+  bf16 *dXh2, *dXch2;       // second bf16 copies (gradient after LayerNorm-2): lets the weight-gradient stream keep reading
+                            // the block's incoming gradient while the dX chain moves on
   size_t partial_floats, misc_floats;
   bool save;   // activations kept for a backward pass
   // residual-stream gradient in the operand dtype
@@ -247,7 +249,7 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
   }
   c.dX = nullptr; c.dXn = nullptr; c.dtok = nullptr; c.dz = nullptr; c.dg_rows = nullptr; c.partial = nullptr;
   c.dH = nullptr; c.dO = nullptr; c.dQKV = nullptr; c.dXp = nullptr; c.dXh = nullptr; c.partial_floats = 0; c.misc_floats = 0;
-  c.dXc = nullptr; c.dXch = nullptr;
+  c.dXc = nullptr; c.dXch = nullptr; c.dXh2 = nullptr; c.dXch2 = nullptr;
   if (save) {
     c.dX = cv.take<float>(d.T * d.D);
     c.dXn = cv.take<float>(d.T * d.D);
@@ -261,6 +263,8 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
     c.dXh = std::is_same<A, float>::value ? nullptr : cv.take<bf16>(d.T * d.D);
     c.dXc = cv.take<float>((int64_t)d.B * d.D);
     c.dXch = std::is_same<A, float>::value ? nullptr : cv.take<bf16>((int64_t)d.B * d.D);
+    c.dXh2 = std::is_same<A, float>::value ? nullptr : cv.take<bf16>(d.T * d.D);
+    c.dXch2 = std::is_same<A, float>::value ? nullptr : cv.take<bf16>((int64_t)d.B * d.D);
     int64_t mx = (int64_t)d.D * d.M;
     mx = std::max<int64_t>(mx, (int64_t)3 * d.inner * d.D);
     mx = std::max<int64_t>(mx, (int64_t)d.D * d.pd);
@@ -519,12 +523,39 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
 }
 
 // ------------------------------------------------------------------ trunk backward
+// Only the dX launches of a block are on the dependency chain to the next block; the weight-gradient launches (MLP dW,
+// dW_out, dW_qkv) and the block's multi-reduce feed nothing downstream.  In the bf16 path they are issued on a second
+// stream (event edges, capturable) so that the latency-bound links of the chain (LayerNorm backward, the short GEMMs)
+// run beside them instead of in series.  set_option "bwd_side" = 0 puts everything back on one stream.
+struct SideState { cudaStream_t s; cudaEvent_t now, dw, mr; };
+static bool g_side_enabled = true;
+static bool g_fork_enabled = true;
+static SideState& side_state() {
+  static SideState f;
+  static bool init = false;
+  if (!init) {
+    DG_CUDA(cudaStreamCreateWithFlags(&f.s, cudaStreamNonBlocking));
+    DG_CUDA(cudaEventCreateWithFlags(&f.now, cudaEventDisableTiming));
+    DG_CUDA(cudaEventCreateWithFlags(&f.dw, cudaEventDisableTiming));
+    DG_CUDA(cudaEventCreateWithFlags(&f.mr, cudaEventDisableTiming));
+    init = true;
+  }
+  return f;
+}
+
 // in: c.dz [B,D]; out: grads of every trunk parameter, c.dtok [B,D]
 template <typename A>
 static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const DropDev& drop,
                            TrunkCtx<A>& c, int relu_tok, cudaStream_t st) {
   const float* P = net.params;
   float* G = net.grads;
+  const bool side = g_side_enabled && g_fork_enabled && std::is_same<A, bf16>::value && c.dXh2 && !prof().on;
+  SideState* sd = side ? &side_state() : nullptr;
+  cudaStream_t ss = side ? sd->s : st;
+  auto side_after_main = [&]() {      // work issued on the side stream from here on sees everything main has issued so far
+    if (side) { DG_CUDA(cudaEventRecord(sd->now, st)); DG_CUDA(cudaStreamWaitEvent(ss, sd->now, 0)); }
+  };
+  bool have_mr = false;
   launch_k(pool_rmsnorm_bwd_kernel, d.B, 128, 0, st, c.Xout, P + L.rms_g, c.dz, c.dXc, c.dXch, c.dg_rows, d.B, 1, d.D,
                                                 sqrtf((float)d.D));
   DG_LAUNCH_CHECK();
@@ -551,8 +582,11 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     const bool last = (l == d.L - 1);
     const int64_t R = last ? d.B : d.T;
     float* dXr = last ? c.dXc : c.dX;                  // fp32 residual-stream gradient of these rows
-    bf16* dXr_lp = last ? c.dXch : c.dXh;
-    const A* dxop = last ? c.dxc_op() : c.dx_op();
+    const A* dxop = last ? c.dxc_op() : c.dx_op();     // operand copy of dL/dX_out
+    // operand copy of dL/dX_m (after the LayerNorm-2 backward): a second buffer when the dW stream is on
+    bf16* dXr_lp = side ? (last ? c.dXch2 : c.dXh2) : (last ? c.dXch : c.dXh);
+    const A* dxop_m = side ? (const A*)dXr_lp : dxop;
+    side_after_main();
     // every partial-sum reduction of this block is queued here and done by one launch at the end of the block
     ReduceList rl(c.partial, block_floats);
     // ---- MLP block.  dXr = dL/dX_out
@@ -568,7 +602,8 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
         ProfScope ps(PROF_GEMM_MLP, 8.0 * R * d.D * d.M, 0.0, st);
         // net.3.bias gradient = colsum(dL/dX_out): below the top block it falls out of the next block's LayerNorm-1 backward
         mlp::bwd(B_.Xn2, dxop, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), c.dXn, G + b.fc1_w,
-                 G + b.fc1_b, G + b.fc2_w, last ? G + b.fc2_b : nullptr, c.partial, R, d.M, st, &rl);
+                 G + b.fc1_b, G + b.fc2_w, last ? G + b.fc2_b : nullptr, c.partial, R, d.M, st, &rl, ss);
+        if (side) DG_CUDA(cudaEventRecord(sd->dw, ss));
       }
     }
 #else
@@ -587,31 +622,39 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
       linear_bwd_x<A, A, float>(c.dH, WSel<A>::w(net, b.fc1_w), c.dXn, R, d.M, d.D, EPI_NONE, nullptr, 0, st);
     }
     }
+    // the previous block's multi-reduce (side stream) must have read its partial sums before this block overwrites them
+    if (side && have_mr) DG_CUDA(cudaStreamWaitEvent(st, sd->mr, 0));
     // dXr becomes dL/dX_m, whose column sums are the to_out.0.bias gradient
     launch_ln_bwd(c.dXn, B_.Xm, B_.mean2, B_.rstd2, P + b.ln2_w, dXr, dXr_lp, G + b.ln2_w, G + b.ln2_b, G + b.out_b,
                   c.partial, R, d.D, st, &rl);
     // ---- attention block.  dXr = dL/dX_m
+    side_after_main();
     if (!last) {
-      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, nullptr, d.T, d.D, d.inner, c.partial, st, -1, -1, &rl);
-      linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.out_w), c.dO, d.T, d.D, d.inner, EPI_NONE, nullptr, 0, st);
+      linear_bwd_w<A, A>(dxop_m, B_.O, G + b.out_w, nullptr, d.T, d.D, d.inner, c.partial, ss, -1, -1, &rl);
+      linear_bwd_x<A, A, A>(dxop_m, WSel<A>::w(net, b.out_w), c.dO, d.T, d.D, d.inner, EPI_NONE, nullptr, 0, st);
     } else {
       const int64_t ostride = (int64_t)d.N * d.inner;
-      linear_bwd_w<A, A>(dxop, B_.O, G + b.out_w, nullptr, d.B, d.D, d.inner, c.partial, st, -1, ostride, &rl);
+      linear_bwd_w<A, A>(dxop_m, B_.O, G + b.out_w, nullptr, d.B, d.D, d.inner, c.partial, ss, -1, ostride, &rl);
       // dO is zero except on the token-0 rows (the single-query-row attention backward reads only those)
       if (!(d.dh == R0_DH && d.N <= R0_MAXN && (g_row0_mode & 2) && ((((uintptr_t)B_.QKV) | ((uintptr_t)c.dO) | ((uintptr_t)c.dQKV)) & 15) == 0))
         DG_CUDA(cudaMemsetAsync(c.dO, 0, (size_t)d.T * d.inner * sizeof(A), st));
-      linear_bwd_x<A, A, A>(dxop, WSel<A>::w(net, b.out_w), c.dO, d.B, d.D, d.inner, EPI_NONE, nullptr, 0, st, -1,
+      linear_bwd_x<A, A, A>(dxop_m, WSel<A>::w(net, b.out_w), c.dO, d.B, d.D, d.inner, EPI_NONE, nullptr, 0, st, -1,
                             nullptr, ostride);
       // (the LayerNorm-1 backward below reads the compact residual gradient directly: zero off token 0)
     }
     if (!(last && launch_attention_row0<A>(B_.QKV, (A*)nullptr, (const A*)c.dO, c.dQKV, d, st)))
       launch_attention_bwd<A>(B_.QKV, B_.O, c.dO, c.dQKV, d, st);
-    linear_bwd_w<A, A>(c.dQKV, B_.Xn1, G + b.qkv_w, nullptr, d.T, 3 * d.inner, d.D, c.partial, st, -1, -1, &rl);
+    side_after_main();
+    linear_bwd_w<A, A>(c.dQKV, B_.Xn1, G + b.qkv_w, nullptr, d.T, 3 * d.inner, d.D, c.partial, ss, -1, -1, &rl);
     linear_bwd_x<A, A, float>(c.dQKV, WSel<A>::w(net, b.qkv_w), c.dXn, d.T, 3 * d.inner, d.D, EPI_NONE, nullptr, 0, st);
+    // the MLP dW launch reads the incoming gradient copy that the next kernel overwrites
+    if (side) DG_CUDA(cudaStreamWaitEvent(st, sd->dw, 0));
     // c.dX becomes dL/dX_a = gradient of the previous block's output: its column sums are that block's net.3.bias gradient
     launch_ln_bwd(c.dXn, B_.Xa, B_.mean1, B_.rstd1, P + b.ln1_w, c.dX, c.dXh, G + b.ln1_w, G + b.ln1_b,
                   l > 0 ? G + L.block[l - 1].fc2_b : nullptr, c.partial, d.T, d.D, st, &rl, last ? c.dXc : nullptr, d.N);
-    rl.launch(st);
+    side_after_main();
+    rl.launch(ss);
+    if (side) { DG_CUDA(cudaEventRecord(sd->mr, ss)); have_mr = true; }
   }
   // ---- embedding.  c.dX = dL/dX0 (post-dropout)
   const int64_t tot = d.T * d.D;
@@ -632,6 +675,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
   linear_bwd_w<A, A>(c.dXp, c.Pm_ext ? c.Pm_ext : c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st, -1,
                      -1, &rl_misc);
   rl_misc.launch(st);
+  if (side && have_mr) DG_CUDA(cudaStreamWaitEvent(st, sd->mr, 0));     // join
 }
 
 // zero the gradient ranges the reference leaves as None (so the arena is fully defined)
@@ -901,7 +945,6 @@ struct ForkState {
   cudaStream_t aux[2];
   cudaEvent_t fork, join[2];
 };
-static bool g_fork_enabled = true;
 static ForkState& fork_state() {
   static ForkState f;
   static bool init = false;
@@ -1098,6 +1141,7 @@ int dgvit_set_option(const char* name, int value) {
   return guarded([&] {
     DG_REQUIRE(name != nullptr, "null option name");
     if (!strcmp(name, "fork_streams")) g_fork_enabled = value != 0;
+    else if (!strcmp(name, "bwd_side")) g_side_enabled = value != 0;
     else if (!strcmp(name, "pdl")) pdl_enabled() = value != 0;
     else if (!strcmp(name, "skip")) skip_mask() = value;
     else if (!strcmp(name, "attention_row0")) g_row0_mode = value;

@@ -957,7 +957,10 @@ static size_t bwd_partial_floats(int64_t M, int HID) {
 // dW1 / db1 / dW2 must be adjacent in that order (the parameter arena's order) so that one pass reduces all three.
 static void bwd(const bf16* x, const bf16* dy, const bf16* W1, const float* b1, const bf16* W2, float* dXn, float* dW1,
                 float* db1, float* dW2, float* db2, float* partial, int64_t M, int HID, cudaStream_t st,
-                ReduceList* defer = nullptr) {
+                ReduceList* defer = nullptr, cudaStream_t st_w = nullptr) {
+  // st_w: stream of the weight-gradient launch (it feeds nothing but the deferred reduction, so the caller may run it
+  // beside the dX chain); null = st
+  if (!st_w || !defer) st_w = st;
   if (defer) partial = defer->alloc(bwd_partial_floats(M, HID));
   DG_REQUIRE(db1 == dW1 + (int64_t)HID * 64 && dW2 == db1 + HID, "mlp::bwd: dW1 | db1 | dW2 must be contiguous");
   const int tiles = (int)cdiv(M, 128), NC = HID / HC;
@@ -985,7 +988,7 @@ static void bwd(const bf16* x, const bf16* dy, const bf16* W1, const float* b1, 
   else if (split) launch_k_cluster((mlp_bwd_tc_kernel<0, true>), tiles * f::NSPLIT, THREADS, b::SMEM_TOTAL, st, f::NSPLIT, tx, tdy, tw1, tw2, a);
   else launch_k(mlp_bwd_tc_kernel<0>, tiles, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
   DG_LAUNCH_CHECK();
-  if (!(skip_mask() & SKIP_MLP_BWD_W)) launch_k(mlp_bwd_tc_kernel<1>, NC * S, THREADS, b::SMEM_TOTAL, st, tx, tdy, tw1, tw2, a);
+  if (!(skip_mask() & SKIP_MLP_BWD_W)) launch_k(mlp_bwd_tc_kernel<1>, NC * S, THREADS, b::SMEM_TOTAL, st_w, tx, tdy, tw1, tw2, a);
   DG_LAUNCH_CHECK();
   if (defer) {       // the caller reduces these together with the block's other partial sums
     defer->add(partial, dW1, S, per_split, per_split);
