@@ -534,7 +534,8 @@ static SideState& side_state() {
   static SideState f;
   static bool init = false;
   if (!init) {
-    DG_CUDA(cudaStreamCreateWithFlags(&f.s, cudaStreamNonBlocking));
+    const char* pe = getenv("DGVIT_SIDE_PRIO");
+    DG_CUDA(cudaStreamCreateWithPriority(&f.s, cudaStreamNonBlocking, pe ? atoi(pe) : 0));
     DG_CUDA(cudaEventCreateWithFlags(&f.now, cudaEventDisableTiming));
     DG_CUDA(cudaEventCreateWithFlags(&f.dw, cudaEventDisableTiming));
     DG_CUDA(cudaEventCreateWithFlags(&f.mr, cudaEventDisableTiming));
@@ -543,13 +544,27 @@ static SideState& side_state() {
   return f;
 }
 
+template <typename A>
+static bool side_on(const TrunkCtx<A>& c) {
+  return g_side_enabled && g_fork_enabled && std::is_same<A, bf16>::value && c.dXh2 && !prof().on;
+}
+// stream for work that only the end of trunk_backward (its join) waits for; sees everything issued on st so far
+template <typename A>
+static cudaStream_t side_fork(const TrunkCtx<A>& c, cudaStream_t st) {
+  if (!side_on(c)) return st;
+  SideState& sd = side_state();
+  DG_CUDA(cudaEventRecord(sd.now, st));
+  DG_CUDA(cudaStreamWaitEvent(sd.s, sd.now, 0));
+  return sd.s;
+}
+
 // in: c.dz [B,D]; out: grads of every trunk parameter, c.dtok [B,D]
 template <typename A>
 static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const DropDev& drop,
                            TrunkCtx<A>& c, int relu_tok, cudaStream_t st) {
   const float* P = net.params;
   float* G = net.grads;
-  const bool side = g_side_enabled && g_fork_enabled && std::is_same<A, bf16>::value && c.dXh2 && !prof().on;
+  const bool side = side_on(c);
   SideState* sd = side ? &side_state() : nullptr;
   cudaStream_t ss = side ? sd->s : st;
   auto side_after_main = [&]() {      // work issued on the side stream from here on sees everything main has issued so far
@@ -773,7 +788,7 @@ static void actor_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     dw.add(c.dlstd, d.na, c.h2, G + L.lstd_w, G + L.lstd_b, d.na, 128);
     dw.add(c.dh2, 128, c.h1, G + L.fc2_w, G + L.fc2_b, 128, 128);
     dw.add(c.dh1, 128, c.t.z, G + L.fc1_w, G + L.fc1_b, 128, d.D);
-    dw.launch(st);
+    dw.launch(side_fork(c.t, st));      // joined at the end of trunk_backward
   }
   const DropDev drop = make_drop(io.drop, d, io.sample_offset);
   trunk_backward<A>(net, L, d, drop, c.t, /*relu_tok=*/0, st);
@@ -859,7 +874,7 @@ static void critic_backward(const dgvit_net& net, const dgvit_layout& L, const D
       dw.add(dq2, d.na, c.h2b, G + L.fc31_w, G + L.fc31_b, d.na, 32);
       dw.add(c.dh2b, 32, c.h1b, G + L.fc21_w, G + L.fc21_b, 32, 128);
       dw.add(c.dh1b, 128, c.xcat, G + L.fc11_w, G + L.fc11_b, 128, W);
-      dw.launch(st);
+      dw.launch(side_fork(c.t, st));    // joined at the end of trunk_backward
     }
   }
   const int W = d.D + d.na;
@@ -950,7 +965,8 @@ static ForkState& fork_state() {
   static bool init = false;
   if (!init) {
     for (int i = 0; i < 2; ++i) {
-      DG_CUDA(cudaStreamCreateWithFlags(&f.aux[i], cudaStreamNonBlocking));
+      const char* pe = getenv("DGVIT_AUX_PRIO");
+      DG_CUDA(cudaStreamCreateWithPriority(&f.aux[i], cudaStreamNonBlocking, pe ? atoi(pe) : 0));
       DG_CUDA(cudaEventCreateWithFlags(&f.join[i], cudaEventDisableTiming));
     }
     DG_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
