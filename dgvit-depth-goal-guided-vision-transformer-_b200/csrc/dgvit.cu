@@ -766,7 +766,7 @@ static void actor_backward(const dgvit_net& net, const dgvit_layout& L, const Di
                            cudaStream_t st) {
   const float* P = net.params;
   float* G = net.grads;
-  zero_unused_grads(net, L, st);
+  zero_unused_grads(net, L, side_fork(c.t, st));   // off the dependency chain; joined by trunk_backward
   SampleBwdArgs s;
   s.B = d.B; s.na = d.na;
   s.mean = c.mean_raw; s.lstd_raw = c.lstd_raw; s.eps = c.eps; s.scale = io.action_scale;
@@ -856,7 +856,7 @@ static void critic_backward(const dgvit_net& net, const dgvit_layout& L, const D
   const float* P = net.params;
   float* G = net.grads;
   (void)part_fallback;
-  if (param_grads) zero_unused_grads(net, L, st);
+  if (param_grads) zero_unused_grads(net, L, side_fork(c.t, st));   // off the dependency chain; joined by trunk_backward
   {
     heads::BwdArgs h;
     memset(&h, 0, sizeof(h));
@@ -958,7 +958,7 @@ static dgvit_drop sac_drop(const dgvit_sac& s, const dgvit_noise* nz, const uint
 // one CUDA graph) so that their many small, latency-bound kernels fill each other's gaps.
 struct ForkState {
   cudaStream_t aux[2];
-  cudaEvent_t fork, join[2];
+  cudaEvent_t fork, fork2, join[2];
 };
 static ForkState& fork_state() {
   static ForkState f;
@@ -970,6 +970,7 @@ static ForkState& fork_state() {
       DG_CUDA(cudaEventCreateWithFlags(&f.join[i], cudaEventDisableTiming));
     }
     DG_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
+    DG_CUDA(cudaEventCreateWithFlags(&f.fork2, cudaEventDisableTiming));
     init = true;
   }
   return f;
@@ -985,13 +986,15 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   ForkState f = f0;
   if (!g_fork_enabled) { f.aux[0] = st; f.aux[1] = st; }      // single-stream mode (per-kernel timing)
   // the five forward passes of an update see two distinct frame batches: patchify s and s' once, before the fork
-  launch_patchify<A>(b.obs, w.actor_s.t.Pm, da.B, da, s.actor.cfg, st);
+  // (s' on the caller's stream, s on the first forked stream; the second forked stream starts after the latter)
+  DG_CUDA(cudaEventRecord(f.fork, st));
+  DG_CUDA(cudaStreamWaitEvent(f.aux[0], f.fork, 0));
+  launch_patchify<A>(b.obs, w.actor_s.t.Pm, da.B, da, s.actor.cfg, f.aux[0]);
+  DG_CUDA(cudaEventRecord(f.fork2, f.aux[0]));
+  DG_CUDA(cudaStreamWaitEvent(f.aux[1], f.fork2, 0));
   launch_patchify<A>(b.next_obs, w.actor_tmp.t.Pm, d.B, d, s.actor.cfg, st);
   w.actor_s.t.Pm_ext = w.actor_s.t.Pm; w.critic_s.t.Pm_ext = w.actor_s.t.Pm;
   w.actor_tmp.t.Pm_ext = w.actor_tmp.t.Pm; w.critic_tmp.t.Pm_ext = w.actor_tmp.t.Pm;
-  DG_CUDA(cudaEventRecord(f.fork, st));
-  DG_CUDA(cudaStreamWaitEvent(f.aux[0], f.fork, 0));
-  DG_CUDA(cudaStreamWaitEvent(f.aux[1], f.fork, 0));
   // ---- stream 0 (caller's): a', log pi' = policy.sample(s') ; q_t = critic_target(s', a')   (DRL.py:388-393)
   dgvit_actor_io ai; memset(&ai, 0, sizeof(ai));
   ai.img = b.next_obs; ai.pstate = b.next_pobs; ai.eps = nz ? nz->eps_next : nullptr;
