@@ -307,13 +307,14 @@ static void launch_ln_fwd(const float* X, const float* g, const float* b, A* Y, 
   DG_LAUNCH_CHECK();
 }
 // dxsum (optional): receives colsum over rows of the updated dX_io (a bias gradient, see layernorm_bwd_kernel)
+static int g_lnb_wpb = 16, g_lnb_bps = 2;   // set_option "ln_bwd_warps", "ln_bwd_blocks_per_sm"
 static void launch_ln_bwd(const float* dY, const float* X, const float* mean, const float* rstd,
                           const float* gamma, float* dX_io, bf16* dX_lp, float* dgamma, float* dbeta, float* dxsum,
                           float* partial, int64_t T, int D, cudaStream_t st, ReduceList* defer = nullptr,
                           const float* dX_row0 = nullptr, int Ntok = 1) {
   // 16 warps per block and at most two blocks per SM: 296 partial rows for the reduction instead of 592
-  const int wpb = 16;
-  int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * 2);
+  const int wpb = g_lnb_wpb;
+  int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * g_lnb_bps);
   if (skip_mask() & SKIP_LN_BWD) return;
   if (defer && D % 4 == 0) partial = defer->alloc((size_t)nblocks * 3 * D); else defer = nullptr;
   const size_t smem = (size_t)wpb * 3 * D * sizeof(float);
@@ -1161,6 +1162,8 @@ int dgvit_set_option(const char* name, int value) {
     DG_REQUIRE(name != nullptr, "null option name");
     if (!strcmp(name, "fork_streams")) g_fork_enabled = value != 0;
     else if (!strcmp(name, "bwd_side")) g_side_enabled = value != 0;
+    else if (!strcmp(name, "ln_bwd_warps")) g_lnb_wpb = value >= 1 && value <= 16 ? value : 16;
+    else if (!strcmp(name, "ln_bwd_blocks_per_sm")) g_lnb_bps = value >= 1 && value <= 4 ? value : 2;
     else if (!strcmp(name, "pdl")) pdl_enabled() = value != 0;
     else if (!strcmp(name, "skip")) skip_mask() = value;
     else if (!strcmp(name, "attention_row0")) g_row0_mode = value;
