@@ -389,6 +389,10 @@ def run_ours(args):
                 back_to_back=dict(us_per_launch=burst_us, tflops=4.0 * rows * 64 * 2048 / burst_us / 1e6,
                                   frac=4.0 * rows * 64 * 2048 / burst_us / 1e6 / pk["tf_burst"], peak=pk["tf_burst"],
                                   what="20 graph-replayed launches between one event pair, %d token rows, burst bf16 peak" % rows),
+                limiter=dict(what="not the tensor pipe: the GELU epilogue needs one MUFU.TANH per hidden element and the SM "
+                                  "retires 16 per clock (profiles/r1_13_pipe_rates.md); floor = rows*2048/(148*16) clocks",
+                             floor_us=rows * 2048 / (148 * 16) / ((clocks or {}).get("sm_mhz") or 1965.0),
+                             at_sm_mhz=(clocks or {}).get("sm_mhz") or 1965.0),
                 algorithmic_flop_per_launch="4*rows*64*2048 + 2*rows*64*256 (8.72 + 0.55 GFLOP at 16640 token rows)",
                 launches_per_step=dom["launches_per_step"], kernel_ms_per_step=dom["ms_per_step"],
                 share_of_step=dom["ms_per_step"] / (ms / args.steps) if ms > 0 else None,
