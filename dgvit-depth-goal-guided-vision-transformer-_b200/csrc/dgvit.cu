@@ -559,6 +559,21 @@ static cudaStream_t side_fork(const TrunkCtx<A>& c, cudaStream_t st) {
   return sd.s;
 }
 
+// generic fork / join of the side stream for bookkeeping kernels that nothing on the caller's stream waits for
+static cudaStream_t lane_fork(cudaStream_t st) {
+  if (!(g_side_enabled && g_fork_enabled && !prof().on)) return st;
+  SideState& sd = side_state();
+  DG_CUDA(cudaEventRecord(sd.now, st));
+  DG_CUDA(cudaStreamWaitEvent(sd.s, sd.now, 0));
+  return sd.s;
+}
+static void lane_join(cudaStream_t lane, cudaStream_t st) {
+  if (lane == st) return;
+  SideState& sd = side_state();
+  DG_CUDA(cudaEventRecord(sd.mr, lane));
+  DG_CUDA(cudaStreamWaitEvent(st, sd.mr, 0));
+}
+
 // in: c.dz [B,D]; out: grads of every trunk parameter, c.dtok [B,D]
 template <typename A>
 static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const DropDev& drop,
@@ -1049,6 +1064,15 @@ static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   make_layout(s.critic.cfg, Lc);
   const bool shadow = s.precision == DGVIT_BF16;
   adam_step(s.critic, Lc, s.critic_opt, nullptr, 0.f, shadow, st);               // DRL.py:402
+  // soft update of the target (DRL.py:430-431): the critic does not change again in this update and nothing below reads
+  // the target, so it runs beside the policy half instead of at the end of the chain
+  cudaStream_t lane = st;
+  if (s.do_polyak) {
+    lane = lane_fork(st);
+    launch_k(polyak_kernel, 148 * 4, 256, 0, lane, s.critic_target.params, s.critic.params,
+                                           shadow ? (bf16*)s.critic_target.shadow : nullptr, s.tau, Lc.total);
+    DG_LAUNCH_CHECK();
+  }
   // the patch matrix of s was written by phase 1 (same workspace) into the saved actor context
   w.critic_tmp.t.Pm_ext = w.actor_s.t.Pm; w.actor_s.t.Pm_ext = w.actor_s.t.Pm; w.critic_s.t.Pm_ext = w.actor_s.t.Pm;
   // ---- q_pi = critic(s, pi) with the UPDATED critic (pi, log_pi come from phase 1)   (DRL.py:406-407)
@@ -1090,6 +1114,8 @@ static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
     DG_CUDA(cudaMemcpyAsync(out.debug + 4 * d.B * d.na, w.q1p, bn, cudaMemcpyDeviceToDevice, st));
     DG_CUDA(cudaMemcpyAsync(out.debug + 5 * d.B * d.na, w.logpi, (size_t)d.B * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
+  // the actor backward's own join has already ordered the side stream (and the soft update on it) before this point
+  if (lane != st) lane_join(lane, st);
 }
 
 template <typename A>
@@ -1098,22 +1124,20 @@ static void sac_phase3(const dgvit_sac& s, cudaStream_t st) {
   make_layout(s.actor.cfg, La);
   make_layout(s.critic.cfg, Lc);
   const bool shadow = s.precision == DGVIT_BF16;
+  // temperature step and RNG counter beside the actor's Adam pass
+  cudaStream_t lane = lane_fork(st);
   adam_step(s.actor, La, s.actor_opt, nullptr, 0.f, shadow, st);                 // DRL.py:413
   if (s.auto_alpha) {                                                            // DRL.py:416-423
-    launch_k(alpha_step_kernel, 1, 32, 0, st, s.log_alpha, s.alpha, s.alpha_m, s.alpha_v, s.alpha_step,
+    launch_k(alpha_step_kernel, 1, 32, 0, lane, s.log_alpha, s.alpha, s.alpha_m, s.alpha_v, s.alpha_step,
                                         s.actor.grads + La.alpha_grad_slot, s.lr_alpha, 0.9f, 0.999f,
                                         (float)(1.0 - 0.9), (float)(1.0 - 0.999), 1e-8f);
     DG_LAUNCH_CHECK();
   }
-  if (s.do_polyak) {                                                             // DRL.py:430-431
-    launch_k(polyak_kernel, 148 * 4, 256, 0, st, s.critic_target.params, s.critic.params,
-                                           shadow ? (bf16*)s.critic_target.shadow : nullptr, s.tau, Lc.total);
-    DG_LAUNCH_CHECK();
-  }
   if (s.rng_state) {
-    launch_k(rng_advance_kernel, 1, 32, 0, st, s.rng_state);
+    launch_k(rng_advance_kernel, 1, 32, 0, lane, s.rng_state);
     DG_LAUNCH_CHECK();
   }
+  lane_join(lane, st);
 }
 
 static void check_sac(const dgvit_sac& s, int B) {
