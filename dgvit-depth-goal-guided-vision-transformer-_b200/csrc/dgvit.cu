@@ -531,6 +531,8 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
 struct SideState { cudaStream_t s; cudaEvent_t now, dw, mr; };
 static bool g_side_enabled = true;
 static bool g_fork_enabled = true;
+static int g_actor_s_when = 1;      // set_option "actor_s_when": 0 = policy.sample(s) forward starts at the fork, 1 = after the
+                                    // policy.sample(s') forward, 2 = after the target critic forward (beside the critic backward)
 static SideState& side_state() {
   static SideState f;
   static bool init = false;
@@ -974,7 +976,7 @@ static dgvit_drop sac_drop(const dgvit_sac& s, const dgvit_noise* nz, const uint
 // one CUDA graph) so that their many small, latency-bound kernels fill each other's gaps.
 struct ForkState {
   cudaStream_t aux[2];
-  cudaEvent_t fork, fork2, join[2];
+  cudaEvent_t fork, fork2, fork3, join[2];
 };
 static ForkState& fork_state() {
   static ForkState f;
@@ -987,6 +989,7 @@ static ForkState& fork_state() {
     }
     DG_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
     DG_CUDA(cudaEventCreateWithFlags(&f.fork2, cudaEventDisableTiming));
+    DG_CUDA(cudaEventCreateWithFlags(&f.fork3, cudaEventDisableTiming));
     init = true;
   }
   return f;
@@ -1018,7 +1021,26 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   ai.drop = sac_drop(s, nz, nz ? nz->mask_a_next : nullptr, 1);
   ai.sample_offset = s.sample_offset;
   ai.mean = w.mean_tmp; ai.log_std = w.lstd_tmp; ai.action = w.a2; ai.log_prob = w.logp2;
+  // ---- stream 2: pi, log_pi = policy.sample(s)  (DRL.py:404; the actor is not touched before :413,
+  //      so this forward can run beside the whole critic update)
+  dgvit_actor_io ap; memset(&ap, 0, sizeof(ap));
+  ap.img = b.obs; ap.pstate = b.pobs; ap.eps = nz ? nz->eps_pi : nullptr;
+  ap.action_scale = s.action_scale; ap.action_bias = s.action_bias;
+  ap.drop = sac_drop(s, nz, nz ? nz->mask_a : nullptr, 4);
+  ap.sample_offset = s.sample_offset;
+  ap.mean = w.mean_pi; ap.log_std = w.lstd_pi; ap.action = w.pi; ap.log_prob = w.logpi; ap.mean_t = w.meant_pi;
+  auto launch_actor_s = [&](int when) {      // B rows (+ the imitation rows of learn_guidence)
+    if (when != g_actor_s_when) return;
+    if (when > 0 && f.aux[1] != st) {        // start it later: after this point of the caller's stream
+      DG_CUDA(cudaEventRecord(f.fork3, st));
+      DG_CUDA(cudaStreamWaitEvent(f.aux[1], f.fork3, 0));
+    }
+    actor_forward<A>(s.actor, La, da, ap, w.actor_s, f.aux[1]);
+    DG_CUDA(cudaEventRecord(f.join[1], f.aux[1]));
+  };
+  launch_actor_s(0);
   actor_forward<A>(s.actor, La, d, ai, w.actor_tmp, st);
+  launch_actor_s(1);
   dgvit_critic_io ci; memset(&ci, 0, sizeof(ci));
   ci.img = b.next_obs; ci.pstate = b.next_pobs; ci.action = w.a2;
   ci.drop = sac_drop(s, nz, nz ? nz->mask_ct : nullptr, 2);
@@ -1031,16 +1053,7 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   cs.q1 = w.q1; cs.q2 = w.q2;
   critic_forward<A>(s.critic, Lc, d, cs, s.sample_offset, w.critic_s, f.aux[0]);
   DG_CUDA(cudaEventRecord(f.join[0], f.aux[0]));
-  // ---- stream 2: pi, log_pi = policy.sample(s)  (DRL.py:404; the actor is not touched before :413,
-  //      so this forward can run beside the whole critic update)
-  dgvit_actor_io ap; memset(&ap, 0, sizeof(ap));
-  ap.img = b.obs; ap.pstate = b.pobs; ap.eps = nz ? nz->eps_pi : nullptr;
-  ap.action_scale = s.action_scale; ap.action_bias = s.action_bias;
-  ap.drop = sac_drop(s, nz, nz ? nz->mask_a : nullptr, 4);
-  ap.sample_offset = s.sample_offset;
-  ap.mean = w.mean_pi; ap.log_std = w.lstd_pi; ap.action = w.pi; ap.log_prob = w.logpi; ap.mean_t = w.meant_pi;
-  actor_forward<A>(s.actor, La, da, ap, w.actor_s, f.aux[1]);      // B rows (+ the imitation rows of learn_guidence)
-  DG_CUDA(cudaEventRecord(f.join[1], f.aux[1]));
+  launch_actor_s(2);
   // ---- losses + critic backward                                                 (DRL.py:396-401)
   DG_CUDA(cudaStreamWaitEvent(st, f.join[0], 0));
   launch_k(critic_loss_kernel, 1, 1024, 0, st, w.q1, w.q2, w.q1t, w.q2t, w.logp2, b.rew, s.alpha, s.gamma, d.B, d.na,
@@ -1186,6 +1199,7 @@ int dgvit_set_option(const char* name, int value) {
     DG_REQUIRE(name != nullptr, "null option name");
     if (!strcmp(name, "fork_streams")) g_fork_enabled = value != 0;
     else if (!strcmp(name, "bwd_side")) g_side_enabled = value != 0;
+    else if (!strcmp(name, "actor_s_when")) g_actor_s_when = value >= 0 && value <= 2 ? value : 0;
     else if (!strcmp(name, "ln_bwd_warps")) g_lnb_wpb = value >= 1 && value <= 16 ? value : 16;
     else if (!strcmp(name, "ln_bwd_blocks_per_sm")) g_lnb_bps = value >= 1 && value <= 4 ? value : 2;
     else if (!strcmp(name, "pdl")) pdl_enabled() = value != 0;
