@@ -339,7 +339,7 @@ def run_ours(args):
             ts.sort()
             act[name] = dict(p50_ms=ts[500] * 1e3, p99_ms=ts[990] * 1e3)
         act["calls"] = 1000
-        act["path"] = "SAC.choose_action: pinned host frame -> CUDA graph (H2D, actor forward, D2H) -> sync"
+        act["path"] = "SAC.choose_action: pinned host frame -> CUDA graph (kernels read the pinned frame and write the action to pinned host memory: zero-copy) -> sync"
     barrier()
 
     if rank != 0:
