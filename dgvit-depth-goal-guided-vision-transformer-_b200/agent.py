@@ -205,9 +205,13 @@ class SAC(object):
         self.target_policy = copy.deepcopy(self.policy)
         self._batch, self._idx = None, None
 
-    def _learn_cnn(self, batch: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None):
-        """vn/DRL.py:388-434 with the drop-in modules.  ``noise`` (tests): eps_next / eps_pi rsample draws and
-        mask_a_next / mask_a dropout keep-masks of the two actor passes."""
+    def _learn_cnn(self, batch: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None,
+                   extra: Optional[Dict[str, torch.Tensor]] = None):
+        """vn/DRL.py:388-434 (and :237-299 when ``extra`` is given) with the drop-in modules.  ``noise`` (tests): eps_next /
+        eps_pi rsample draws and mask_a_next / mask_a dropout keep-masks of the two actor passes (+ mask_x for the
+        imitation rows).  ``extra``: obs, pobs, target, weight of the ``learn_guidence`` imitation rows (expert rows, then
+        the rows with engage == 1): the reference's two extra ``policy.sample`` calls (:259-276) ride in one pass, and
+        ``weight`` carries guidence_weight / (n_expert * n_act) resp. engage_weight / (n_engaged * n_act)."""
         import torch.nn.functional as F
         view = lambda t: t.view(t.shape[0], *self.replay_buffer.obs_shape) if t.dim() == 2 else t
         s, s2 = view(batch["obs"]), view(batch["next_obs"])
@@ -234,6 +238,11 @@ class SAC(object):
         for p in self.critic.parameters():
             p.requires_grad_(True)
         policy_loss = ((self.alpha * log_pi) - torch.min(qf1_pi, qf2_pi)).mean()
+        if extra is not None:                                                                # :259-278
+            if noise:
+                self.policy.inject_noise(mask=nz.get("mask_x"), eps=nz.get("eps_x"))
+            _, _, predicted = self.policy.sample([view(extra["obs"]), extra["pobs"]])
+            policy_loss = policy_loss + (extra["weight"][:, None] * (predicted - extra["target"]) ** 2).sum()
         self.policy_optim.zero_grad()
         policy_loss.backward()
         self.policy_optim.step()
@@ -448,8 +457,6 @@ class SAC(object):
         for the critic / policy losses, plus the guidance (expert rows) and engage (rows with engage == 1)
         imitation losses on the actor's tanh-mean.  All imitation rows ride in the same actor pass as
         extra rows with per-row loss weights, so the update stays one fused call."""
-        if self._cnn_critic:
-            raise NotImplementedError("learn_guidence with the CNN critic: use critic_type='Transformer' or learn()")
         B = int(batch_size)
         rb, re = self.replay_buffer, (self.replay_buffer_expert if self.pre_buffer else None)
         Be = 0
@@ -485,6 +492,12 @@ class SAC(object):
             buf["target"][Be:n_extra].copy_(buf["act"][er])
             buf["weight"][Be:n_extra].fill_(self.engage_weight / (len(eng_rows) * self.action_dim * self.world))
         extra = None if n_extra == 0 else dict(target=buf["target"][:n_extra], weight=buf["weight"][:n_extra])
+        if self._cnn_critic:      # the reference's shipped default (vn/config.yaml:61): CNN critic, module path
+            if extra is not None:
+                extra.update(obs=buf["obs"][Bc:Bc + n_extra], pobs=buf["pobs"][Bc:Bc + n_extra])
+            q, p = self._learn_cnn({k: buf[k][:Bc] for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done")},
+                                   extra=extra)
+            return float(q), float(p)
         losses = self.update_from_batch({k: buf[k] for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done")},
                                         extra=extra).tolist()
         self.alpha = float(self._alpha.item()) if self.automatic_entropy_tuning else self.alpha

@@ -161,3 +161,77 @@ def test_sac_learn_with_cnn_critic_matches_reference_style_update():
     ag.replay_buffer.fill_synthetic(32)
     q, p = ag.learn(4)
     assert np.isfinite(q) and np.isfinite(p)
+
+
+@pytest.mark.gpu
+def test_sac_learn_guidence_with_cnn_critic():
+    """The reference's shipped configuration (vn/config.yaml:61 CNN critic + PRE_BUFFER): ``learn_guidence``
+    (vn/DRL.py:237-299) with the QNetwork critic -- the statements run with autograd on the oracle's functions, expert
+    rows and engaged rows through two separate ``policy.sample`` calls as in the reference; the drop-in runs them as one
+    pass over [expert rows | engaged rows] with per-row weights."""
+    import torch.nn.functional as F
+    from helpers import reference_init
+    from oracle.init_params import synthetic_noise
+    cfg = O.Cfg(dim=32, depth=2, heads=2)
+    B, Be = 4, 2                                   # agent rows, expert rows
+    ag = dg.SAC(2, 2, "GaussianTransformer", "CNN", False, False, True, 11, LR_C=1e-3, LR_A=1e-3, LR_ALPHA=1e-4,
+                BUFFER_SIZE=64, TAU=5e-3, POLICY_FREQ=1, GAMMA=0.99, ALPHA=0.2, block=2, head=2, l_f_size=32,
+                precision="fp32", buffer_size_expert=16)
+    pa, pc = reference_init("actor", cfg, 31), reference_qnet_init(32)
+    ag.policy.load_state_dict(pa); ag.critic.load_state_dict(pc); ag.critic_target.load_state_dict(pc)
+    ag._after_load()
+    ra = {k: v.clone().requires_grad_(True) for k, v in pa.items()}
+    rc = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    rt = {k: v.clone() for k, v in pc.items()}
+    opt_c, opt_a = torch.optim.Adam(list(rc.values()), lr=1e-3), torch.optim.Adam(list(ra.values()), lr=1e-3)
+    alpha, gw, ew = 0.2, ag.guidence_weight, ag.engage_weight
+    Bc = B + Be
+    batch, nz = synthetic_batch(cfg, Bc, 500), synthetic_noise(cfg, Bc, 600)
+    eng = torch.tensor([1, 3])                     # engaged agent rows
+    g = torch.Generator().manual_seed(7)
+    mask_g = (torch.rand(Be, cfg.n_tokens, cfg.dim, generator=g) >= 0.1).float()
+    mask_e = (torch.rand(len(eng), cfg.n_tokens, cfg.dim, generator=g) >= 0.1).float()
+    eps0 = torch.zeros(Be, 2), torch.zeros(len(eng), 2)
+    s, s2, ps, ps2, a, r = (batch[k] for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew"))
+    with torch.no_grad():
+        a2, lp2, _ = O.actor_sample(ra, s2, ps2, nz["eps_next"], cfg, nz["mask_a_next"])
+        q1t, q2t = O.qnet_forward(rt, s2, ps2, a2)
+        nq = r + 0.99 * (torch.min(q1t, q2t) - alpha * lp2)
+    q1, q2 = O.qnet_forward(rc, s, ps, a)
+    l1 = F.mse_loss(q1, nq)
+    lq = l1 + F.mse_loss(q2, nq)
+    opt_c.zero_grad(); lq.backward(); opt_c.step()
+    pi, lp, _ = O.actor_sample(ra, s, ps, nz["eps_pi"], cfg, nz["mask_a"])
+    q1p, q2p = O.qnet_forward(rc, s, ps, pi)
+    _, _, pred_g = O.actor_sample(ra, s[B:Bc], ps[B:Bc], eps0[0], cfg, mask_g)                   # :259-263
+    _, _, pred_e = O.actor_sample(ra, s[eng], ps[eng], eps0[1], cfg, mask_e)                     # :267-273
+    lpol = ((alpha * lp) - torch.min(q1p, q2p)).mean() + gw * F.mse_loss(pred_g, a[B:Bc]).mean() \
+        + ew * F.mse_loss(pred_e, a[eng]).mean()
+    opt_a.zero_grad(); lpol.backward(); opt_a.step()
+
+    gb = {k: v.cuda() for k, v in batch.items()}
+    n_g, n_e = Be * 2, len(eng) * 2
+    extra = dict(obs=torch.cat([s[B:Bc], s[eng]]).cuda(), pobs=torch.cat([ps[B:Bc], ps[eng]]).cuda(),
+                 target=torch.cat([a[B:Bc], a[eng]]).cuda(),
+                 weight=torch.cat([torch.full((Be,), gw / n_g), torch.full((len(eng),), ew / n_e)]).cuda())
+    nzg = {k: (v.cuda() if v is not None else None) for k, v in nz.items()}
+    nzg["mask_x"] = torch.cat([mask_g, mask_e]).cuda()
+    nzg["eps_x"] = torch.zeros(Be + len(eng), 2).cuda()
+    qg, pg = ag._learn_cnn(gb, nzg, extra=extra)
+    assert abs(float(qg) - float(l1)) < 1e-4 * max(1.0, abs(float(l1))), (float(qg), float(l1))
+    assert abs(float(pg) - float(lpol)) < 1e-4 * max(1.0, abs(float(lpol))), (float(pg), float(lpol))
+    for k, p in ag.critic.named_parameters():
+        assert float((p.detach().cpu() - rc[k].detach()).abs().max()) < 3e-5, ("critic", k)
+    for k, p in ag.policy.named_parameters():
+        d = (p.detach().cpu() - ra[k].detach()).abs()
+        assert float((d > 3e-5).float().mean()) < 5e-3, ("actor", k)
+
+    # the public entry point: agent + expert replay stores, engaged transitions
+    rs = np.random.RandomState(0)
+    for i in range(10):
+        f1, f2 = rs.rand(128, 160).astype(np.float32), rs.rand(128, 160).astype(np.float32)
+        ag.store_transition(f1, rs.rand(2) * 2 - 1, rs.rand(2), rs.rand(2), float(rs.randn()), f2, float(i % 3 == 0), None, 0)
+        ag.initialize_expert_buffer(f1, rs.rand(2) * 2 - 1, rs.rand(2), rs.rand(2), 1.0, f2, 0)
+    for _ in range(2):
+        q, p = ag.learn_guidence(False, 6)
+        assert np.isfinite(q) and np.isfinite(p)
