@@ -395,7 +395,11 @@ def run_ours(args):
                              at_sm_mhz=(clocks or {}).get("sm_mhz") or 1965.0),
                 algorithmic_flop_per_launch="4*rows*64*2048 + 2*rows*64*256 (8.72 + 0.55 GFLOP at 16640 token rows)",
                 launches_per_step=dom["launches_per_step"], kernel_ms_per_step=dom["ms_per_step"],
-                share_of_step=dom["ms_per_step"] / (ms / args.steps) if ms > 0 else None,
+                # share of the SERIALISED step (same single-stream eager pass the kernel was timed in: comparable with the
+                # ncu launch list in profiles/, which is serialised too); in the graph-replayed step kernels of different
+                # streams overlap, so kernel time / step time is not a share
+                share_of_step=dom["ms_per_step"] / eager_ms_per_step if eager_ms_per_step > 0 else None,
+                kernel_ms_over_graph_step_ms=dom["ms_per_step"] / (ms / args.steps) if ms > 0 else None,
                 eager_ms_per_step=eager_ms_per_step, peak_source=pk["src"] + " (sustained bf16 cuBLAS)",
                 other_kernels={k: v for k, v in prof.items() if k != "mlp_fused"})
     whole = dict(achieved_tflops=value * FLOP_PER_SAMPLE / 1e12, frac_of_peak=value * FLOP_PER_SAMPLE / 1e12 / pk["tf_sust"] / world)
