@@ -194,9 +194,17 @@ const char* dgvit_last_error(void);
 enum { DGVIT_PROF_NONE = 0, DGVIT_PROF_GEMM_MLP = 1, DGVIT_PROF_GEMM_ALL = 2, DGVIT_PROF_ATTENTION = 3,
        DGVIT_PROF_GATHER = 4, DGVIT_PROF_ADAM = 5, DGVIT_PROF_MLP_FUSED = 6 };
 long long dgvit_launch_count(void);
-/* runtime switches for measurement / A-B tests: "fork_streams" (1: the independent forward passes of
- * the update run on library-owned side streams; 0: everything on the caller's stream),
- * "tensor_cores" (0: route the bf16 contractions to the CUDA-core kernels) */
+/* runtime switches for measurement / A-B tests (results are identical for every setting up to summation order; the
+ * stream switches change nothing at all, tests/test_gpu_parity.py):
+ *   "fork_streams"   1: the independent forward passes of the update run on library-owned streams; 0: caller's stream only
+ *   "bwd_side"       1: weight-gradient launches, per-block reductions and bookkeeping kernels on a second stream
+ *   "actor_s_when"   0/1/2: policy.sample(s) forward starts at the fork / after the policy.sample(s') forward / after
+ *                    the target-critic forward
+ *   "tensor_cores"   0: route the bf16 contractions to the CUDA-core kernels
+ *   "mlp_split", "mlp_front", "attention_row0", "attn_bwd2": kernel variants of the pruned last block / fused prologue /
+ *                    pipelined attention backward (0 = the plain kernels)
+ *   "ln_bwd_warps", "ln_bwd_blocks_per_sm": LayerNorm-backward block shape; "pdl": programmatic dependent launch;
+ *   "skip": bit mask of kernel families to drop (timing attribution only, results become garbage) */
 int dgvit_set_option(const char* name, int value);
 int dgvit_prof_begin(int tag, int max_launches);
 int dgvit_prof_end(double* ms_total, long long* launches, double* flops, double* bytes);
