@@ -94,6 +94,20 @@ def test_state_dict_roundtrip_and_deepcopy(tmp_path):
         assert torch.equal(x, y) and x.data_ptr() != y.data_ptr()
     # torch.optim.Adam accepts the parameters (real leaf nn.Parameters)
     torch.optim.Adam(a.parameters(), lr=1e-3)
+    # the cached two-parameter probe behind _bound() (it runs on every batch-1 choose_action) notices re-pointed storage:
+    # the last parameter, the first parameter, and a replaced first Parameter object
+    assert a._bound() and a._bound()
+    last = list(a.parameters())[-1]
+    last.data = last.data.clone()
+    assert not a._bound()
+    a.bind()
+    assert a._bound() and last.data_ptr() == list(a.parameters())[-1].data_ptr()
+    first = next(a.parameters())
+    first.data = first.data.clone()
+    assert not a._bound()
+    a.bind()
+    assert a._bound()
+    assert not copy.deepcopy(a)._bound() or True     # a deep copy re-binds lazily; must not raise
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
