@@ -243,10 +243,13 @@ int dgvit_critic_backward(const dgvit_net* net, const dgvit_critic_io* io, const
 /* SAC.learn in three phases so that a data-parallel caller can all-reduce the gradient
  * arenas between them (vn/DRL.py:388-402 | :404-413 | :414-432):
  *   phase 1: TD target + critic forward/backward        -> critic.grads
- *   phase 2: critic Adam; actor forward; critic(s,pi); policy/alpha losses; backward
- *                                                      -> actor.grads (+ alpha grad slot)
- *   phase 3: actor Adam, alpha Adam, Polyak target update, RNG counter advance
- * dgvit_sac_update = phases 1-3 back to back (single GPU). */
+ *   phase 2: critic Adam (+ Polyak target update beside the rest of the phase); critic(s,pi) with the
+ *            policy sample of phase 1; policy/alpha losses; backward -> actor.grads (+ alpha grad slot)
+ *   phase 3: actor Adam, alpha Adam, RNG counter advance
+ * dgvit_sac_update = phases 1-3 back to back (single GPU).
+ * Stream contract: each call forks library-owned streams off `stream` with events (independent forward passes,
+ * weight-gradient launches, bookkeeping kernels) and joins every one of them back into `stream` before it returns, so
+ * the caller sees ordinary stream-ordered work and the call is capturable into one CUDA graph. */
 int dgvit_sac_phase1(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* nz,
                      const dgvit_sac_out* out, int B, void* workspace, size_t workspace_bytes,
                      void* stream);
