@@ -378,6 +378,43 @@ def run_ours(args):
     burst_us = b0_.elapsed_time(b1_) * 1e3 / 20
     del xs, rs_, outs
 
+    # ---------------- the HBM-bound kernels of the path against the measured copy bandwidth (north_star: gather and
+    # elementwise kernels "at a stated HBM-bandwidth fraction"): replay gather from the 2.46 GB store (random rows, > L2) and
+    # the depth pre-processing kernel on fresh 512x640 frames (vn/env_lab.py:420-434)
+    def hbm_time(fn, reps=10):
+        fn(0)
+        torch.cuda.synchronize(dev)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for i in range(reps):
+            fn(i + 1)
+        h1.record()
+        torch.cuda.synchronize(dev)
+        return h0.elapsed_time(h1) * 1e-3 / reps
+    hbm = {}
+    try:
+        frame_floats = ag.replay_buffer.obs.shape[1]
+        for gB in (B, 4096):
+            gidx = [torch.randint(0, args.replay - 1, (gB,), device=dev, dtype=torch.int64) for _ in range(11)]
+            z = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=dev)
+            gout = dict(obs=z(gB, frame_floats), next_obs=z(gB, frame_floats), pobs=z(gB, 2), next_pobs=z(gB, 2), act=z(gB, 2),
+                        rew=z(gB, 1), done=z(gB, 1))
+            t = hbm_time(lambda i: ag.replay_buffer.gather(gidx[i], gout))
+            by = gB * (4.0 * frame_floats * 4 + 9 * 4 * 2)          # two frames read + two written, plus the small fields
+            hbm["replay_gather_B%d" % gB] = dict(us=t * 1e6, GBps=by / t / 1e9, frac=by / t / 1e9 / pk["hbm"],
+                                                bytes_per_sample=by / gB)
+            del gout, gidx
+        nfr = 64
+        raws = [torch.rand(nfr, 512, 640, device=dev) * 10.0 for _ in range(3)]      # 3 x 84 MB: rotates past L2
+        drng = torch.tensor([SEED, 0], dtype=torch.int64, device=dev)
+        t = hbm_time(lambda i: dg.depth_augment(raws[i % 3], rng_state=drng))
+        by = nfr * 1392640.0                                         # bytes per frame (min/max pass + fused pass)
+        hbm["depth_augment_64x512x640"] = dict(us=t * 1e6, GBps=by / t / 1e9, frac=by / t / 1e9 / pk["hbm"],
+                                               bytes_per_frame=1392640)
+        del raws
+    except Exception as e:      # reporting only: never lose the bench line over it
+        hbm["error"] = repr(e)[:200]
+
     # ---------------- roofline of the dominant kernel (the MLP GEMM family), timed live above
     dom = prof["mlp_fused"]
     ach = dom["tflops"]
@@ -401,7 +438,8 @@ def run_ours(args):
                 share_of_step=dom["ms_per_step"] / eager_ms_per_step if eager_ms_per_step > 0 else None,
                 kernel_ms_over_graph_step_ms=dom["ms_per_step"] / (ms / args.steps) if ms > 0 else None,
                 eager_ms_per_step=eager_ms_per_step, peak_source=pk["src"] + " (sustained bf16 cuBLAS)",
-                other_kernels={k: v for k, v in prof.items() if k != "mlp_fused"})
+                other_kernels={k: v for k, v in prof.items() if k != "mlp_fused"},
+                hbm_kernels=dict(peak_GBps=pk["hbm"], peak_source=pk["src"] + " (device copy bandwidth)", **hbm))
     whole = dict(achieved_tflops=value * FLOP_PER_SAMPLE / 1e12, frac_of_peak=value * FLOP_PER_SAMPLE / 1e12 / pk["tf_sust"] / world)
 
     cpu = None
