@@ -148,8 +148,9 @@ def cpu_act_latency(calls: int = 60):
     return ts[len(ts) // 2] * 1e3
 
 
-def gpu_eager_rate(batch: int, dev):
-    """Informational: the same oracle (= the reference's ATen/cuBLAS library path, fp32 eager) on the GPU."""
+def gpu_eager_rate(batch: int, dev, autocast: bool = False):
+    """Informational: the same oracle (= the reference's ATen/cuBLAS library path, eager fp32, or eager under
+    torch.autocast(bfloat16): "the existing Blackwell path through libraries") on the GPU."""
     from oracle import dgvit_oracle as O
     from oracle.init_params import reference_sac_init, synthetic_batch, synthetic_noise
     cfg = O.Cfg(dim=PRESET["l_f_size"], depth=PRESET["block"], heads=PRESET["head"])
@@ -160,15 +161,17 @@ def gpu_eager_rate(batch: int, dev):
         orc = O.SACOracle({k: v.to(dev) for k, v in actor.items()}, {k: v.to(dev) for k, v in critic.items()}, cfg,
                           gamma=HP["GAMMA"], tau=HP["TAU"], alpha=HP["ALPHA"], policy_freq=HP["POLICY_FREQ"])
         orc.log_alpha = orc.log_alpha.to(dev)
-        for _ in range(3):
-            orc.learn(b, nz)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        n = 10
-        for _ in range(n):
-            orc.learn(b, nz)
-        torch.cuda.synchronize(dev)
-    return dict(value=batch * n / (time.perf_counter() - t0), unit=UNIT, what="oracle restatement in eager PyTorch fp32 on the same GPU")
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            for _ in range(3):
+                orc.learn(b, nz)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            n = 10
+            for _ in range(n):
+                orc.learn(b, nz)
+            torch.cuda.synchronize(dev)
+    return dict(value=batch * n / (time.perf_counter() - t0), unit=UNIT,
+                what="oracle restatement in eager PyTorch %s on the same GPU" % ("under torch.autocast(bfloat16)" if autocast else "fp32"))
 
 
 def run_reference(args):
@@ -240,6 +243,27 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
     barrier()
+    # the same step looped for >= 2 s (blocks of `steps` steps, median block): what the number looks like once the
+    # power governor has settled; the clocks are sampled through both regions
+    sustained = None
+    if not args.no_sustained:
+        blocks = []
+        t_end = time.perf_counter() + args.sustained_seconds
+        while time.perf_counter() < t_end or len(blocks) < 3:
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.steps):
+                ag.learn_async(B)
+            s1.record()
+            torch.cuda.synchronize(dev)
+            blocks.append(s0.elapsed_time(s1))
+        tb = torch.tensor([statistics.median(blocks)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        sustained = dict(value=B * world * args.steps / (float(tb.item()) / 1e3), unit=UNIT, blocks=len(blocks),
+                         steps_per_block=args.steps, seconds=sum(blocks) / 1e3,
+                         what="median block of the same step looped back to back for >= %.0f s" % args.sustained_seconds)
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel timing of the dominant kernel family + launch count: the same steps launched eagerly
     # (CUDA events around individual launches cannot be recorded inside a replayed graph)
@@ -250,7 +274,10 @@ def run_ours(args):
     n0 = lib.dgvit_launch_count()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
-    for tag_name, tag in (("mlp_fused", L.PROF_MLP_FUSED), ("gemm_all", L.PROF_GEMM_ALL), ("attention", L.PROF_ATTENTION)):
+    tags = (("mlp_fused", L.PROF_MLP_FUSED), ("gemm_all", L.PROF_GEMM_ALL), ("attention", L.PROF_ATTENTION),
+            ("adam_polyak", L.PROF_ADAM), ("layernorm_bwd", L.PROF_LN_BWD), ("embed_ln", L.PROF_EMBED),
+            ("patchify", L.PROF_PATCH), ("replay_gather", L.PROF_GATHER))
+    for tag_name, tag in tags:
         L.check(lib.dgvit_prof_begin(tag, psteps * 400), "prof_begin")
         for _ in range(psteps):
             ag.learn_async(B)
@@ -260,10 +287,14 @@ def run_ours(args):
         prof[tag_name] = dict(ms_per_step=pms.value / psteps, launches_per_step=pl.value / psteps,
                               tflops=(pfl.value / 1e12) / (pms.value / 1e3) if pms.value > 0 else 0.0,
                               flop_per_step=pfl.value / psteps)
+        if pby.value > 0:       # HBM-bound family: algorithmic bytes / event time around every launch
+            gbps = pby.value / 1e9 / (pms.value / 1e3) if pms.value > 0 else 0.0
+            prof[tag_name] = dict(us_per_launch=pms.value * 1e3 / max(pl.value, 1), launches_per_step=pl.value / psteps,
+                                  bytes_per_launch=pby.value / max(pl.value, 1), GBps=gbps, frac=gbps / pk["hbm"])
     p1.record()
     torch.cuda.synchronize(dev)
-    launches = (lib.dgvit_launch_count() - n0) * args.steps // (3 * psteps)
-    eager_ms_per_step = p0.elapsed_time(p1) / (3 * psteps)
+    launches = (lib.dgvit_launch_count() - n0) * args.steps // (len(tags) * psteps)
+    eager_ms_per_step = p0.elapsed_time(p1) / (len(tags) * psteps)
     L.check(lib.dgvit_set_option(b"fork_streams", 1), "set_option")
     ag.use_cuda_graph = graph_flag
     barrier()
@@ -272,7 +303,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = B * world * args.steps / (ms / 1e3)
-    losses = ag._losses.tolist()
+    losses = ag._loss_buffer().tolist()
 
     # ---------------- end to end: pinned HOST minibatches -> H2D -> update -> D2H losses
     f = ag.replay_buffer.obs.shape[1]
@@ -342,9 +373,12 @@ def run_ours(args):
         act["path"] = "SAC.choose_action: pinned host frame -> CUDA graph (kernels read the pinned frame and write the action to pinned host memory: zero-copy) -> sync"
     barrier()
 
+    dp_parity, c4, c5 = None, None, None
+    if not args.no_extras:
+        dp_parity, c4, c5 = run_extras(args, ag, dev, rank, world, dist, barrier)
+
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        teardown(ag, dist)
         return
 
     # the dominant kernel again, 20 launches back to back between ONE pair of events (no per-launch event gap; weights
@@ -445,15 +479,20 @@ def run_ours(args):
                 share_of_step=dom["ms_per_step"] / eager_ms_per_step if eager_ms_per_step > 0 else None,
                 kernel_ms_over_graph_step_ms=dom["ms_per_step"] / (ms / args.steps) if ms > 0 else None,
                 eager_ms_per_step=eager_ms_per_step, peak_source=pk["src"] + " (sustained bf16 cuBLAS)",
-                other_kernels={k: v for k, v in prof.items() if k != "mlp_fused"},
-                hbm_kernels=dict(peak_GBps=pk["hbm"], peak_source=pk["src"] + " (device copy bandwidth)", **hbm))
+                other_kernels={k: v for k, v in prof.items() if k in ("gemm_all", "attention")},
+                hbm_kernels=dict(peak_GBps=pk["hbm"], peak_source=pk["src"] + " (device copy bandwidth)",
+                                 in_step={k: v for k, v in prof.items() if k in ("adam_polyak", "layernorm_bwd", "embed_ln", "patchify", "replay_gather")},
+                                 in_step_how="CUDA events around every launch of the family inside the eager single-stream "
+                                             "replica of the timed step (B=%d; includes the per-launch event gap), "
+                                             "algorithmic bytes as stated in DESIGN.md §4" % B, **hbm))
     whole = dict(achieved_tflops=value * FLOP_PER_SAMPLE / 1e12, frac_of_peak=value * FLOP_PER_SAMPLE / 1e12 / pk["tf_sust"] / world)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, sample, _ = cpu_update_rate(12.0, B, 3, warmup=1)
         cpu = dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample, act_p50_ms=cpu_act_latency(),
-                   torch_eager_on_gpu=gpu_eager_rate(B, dev))
+                   torch_eager_on_gpu=gpu_eager_rate(B, dev),
+                   torch_eager_bf16_autocast_on_gpu=gpu_eager_rate(B, dev, autocast=True))
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -465,11 +504,138 @@ def run_ours(args):
                             l2="inputs gathered each step by random index from a %.2f GB device replay store (> 126 MB L2)"
                                % (ag.replay_buffer.obs.numel() * 4 / 1e9)),
                 roofline=roof, whole_step=whole, cpu_baseline=cpu,
+                value_sustained=sustained, dp_parity=dp_parity, c4=c4, c5=c5,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=16),
                 act_latency=act, gpu_launches=int(launches), clocks=clocks, losses=losses)
     print(json.dumps(line), flush=True)
-    if dist is not None:
+    teardown(ag, dist)
+
+
+def teardown(ag, dist):
+    """Captured graphs go before the communicator; a watchdog guarantees the process exits even if NCCL teardown stalls
+    (the JSON line is already out)."""
+    if dist is None:
+        return
+    threading.Timer(20.0, lambda: os._exit(0)).start()
+    try:
+        ag.close()
         dist.destroy_process_group()
+    finally:
+        os._exit(0)
+
+
+def run_extras(args, ag, dev, rank, world, dist, barrier):
+    """Records beside the headline (all ranks take part):
+       dp_parity  N > 1: one injected-noise fp32 update, data parallel over the N ranks, against a single-GPU replay of the
+                  same GLOBAL batch on rank 0 (gradient arenas after the all-reduce, losses);
+       c4         BASELINE config 4: global batch 4096 split N ways (strong scaling), samples/s and the all-reduce time;
+       c5         BASELINE config 5: depth pre-processing (raw 1024x1280 -> 256x320 states written into the replay store) +
+                  update of the wide / deep variant (D=128, 6 blocks, 6 heads, 257 tokens), global batch 4096 at N=8."""
+    import dgvit_b200 as dg
+    from dgvit_b200.parallel import shard_batch
+    out = [None, None, None]
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(t.item()) / steps
+
+    # ---- dp_parity
+    if world > 1:
+        try:
+            Bg = 8 * world
+            gen = torch.Generator().manual_seed(SEED + 21)            # same seed on every rank: the GLOBAL batch and noise
+            rnd = lambda *sh: torch.rand(*sh, generator=gen)
+            batch = dict(obs=rnd(Bg, 128 * 160), next_obs=rnd(Bg, 128 * 160), pobs=rnd(Bg, 2), next_pobs=rnd(Bg, 2),
+                         act=rnd(Bg, 2) * 2 - 1, rew=torch.randn(Bg, 1, generator=gen) * 20, done=torch.zeros(Bg, 1))
+            noise = {k: (rnd(Bg, 65, PRESET["l_f_size"]) > 0.1).float() for k in ("mask_a_next", "mask_ct", "mask_c", "mask_a", "mask_c_pi")}
+            noise["eps_next"], noise["eps_pi"] = torch.randn(Bg, 2, generator=gen), torch.randn(Bg, 2, generator=gen)
+            mk = lambda d: dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, False, SEED, BUFFER_SIZE=8,
+                                  precision="fp32", device=dev, distributed=d, **HP, **PRESET)
+            cu = lambda d: {k: (v.to(torch.uint8) if k.startswith("mask") else v.reshape(v.shape[0], -1) if k in ("obs", "next_obs") else v).to(dev).contiguous()
+                            for k, v in d.items() if v is not None}
+            a_dp = mk(True)
+            lb, ln = shard_batch(batch, world, rank), shard_batch(noise, world, rank)
+            l_dp = a_dp.update_from_batch(cu(lb), cu(ln), global_batch=Bg).clone()
+            torch.cuda.synchronize(dev)
+            if rank == 0:
+                a_1 = mk(False)
+                l_1 = a_1.update_from_batch(cu(batch), cu(noise), global_batch=Bg, sample_offset=0).clone()
+                torch.cuda.synchronize(dev)
+                rel = {}
+                for nm, m_dp, m_1 in (("critic_grads", a_dp.critic, a_1.critic), ("actor_grads", a_dp.policy, a_1.policy)):
+                    n_used = int(m_1.layout().alpha_grad_slot) if nm == "actor_grads" else m_1._garena.numel()
+                    g_dp, g_1 = m_dp._garena[:n_used], m_1._garena[:n_used]
+                    rel[nm] = float((g_dp - g_1).abs().max() / g_1.abs().max().clamp_min(1e-30))
+                rel["losses"] = float((l_dp - l_1).abs().max() / l_1.abs().max().clamp_min(1e-30))
+                out[0] = dict(max_abs=max(rel.values()), ok=bool(max(rel.values()) < 1e-4), detail=rel, global_batch=Bg,
+                              precision="fp32", what="DP(%d) update vs single-GPU update of the same global batch: max |diff| "
+                                                     "/ max |ref| of the all-reduced gradient arenas and of the losses" % world)
+                del a_1
+            del a_dp
+        except Exception as e:
+            out[0] = dict(ok=False, error=repr(e)[:300])
+        barrier()
+
+    # ---- c4: global 4096
+    try:
+        Bc = 4096 // world
+        ms4 = timed(lambda: ag.learn_async(Bc), min(args.steps, 10), 3)
+        rec = dict(global_batch=Bc * world, batch_per_gpu=Bc, ms_per_step=ms4, value=Bc * world / (ms4 / 1e3), unit=UNIT,
+                   scaling="strong", whole_step_frac_of_peak=Bc * world / (ms4 / 1e3) * FLOP_PER_SAMPLE / 1e12 / peaks()["tf_sust"] / world)
+        if world > 1:
+            def ar():
+                dist.all_reduce(ag.critic._garena)
+                dist.all_reduce(ag.policy._garena)
+            rec["allreduce_us_per_step"] = timed(ar, 20, 3) * 1e3
+            rec["allreduce_bytes"] = 4 * (ag.critic._garena.numel() + ag.policy._garena.numel())
+        out[1] = rec
+    except Exception as e:
+        out[1] = dict(error=repr(e)[:300])
+    barrier()
+
+    # ---- c5: depth pre-processing + wide / deep variant
+    try:
+        B5 = 4096 // world if world > 1 else 512
+        n_aug = 64
+        a5 = dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, False, SEED, BUFFER_SIZE=2048, precision="bf16",
+                    device=dev, distributed=world > 1, use_cuda_graph=True, image_size=(256, 320), block=6, head=6,
+                    l_f_size=128, **HP)
+        a5.replay_buffer.fill_synthetic(2048, seed=SEED + rank)
+        raws = [torch.rand(n_aug, 1024, 1280, device=dev) * 10.0 for _ in range(2)]
+        drng = torch.tensor([SEED, 0], dtype=torch.int64, device=dev)
+        cur = [0]
+
+        def step5():
+            r0 = (cur[0] * n_aug) % 1920
+            cur[0] += 1
+            dg.depth_augment(raws[cur[0] & 1], rng_state=drng, out=a5.replay_buffer.obs[r0:r0 + n_aug])   # states -> store rows
+            a5.learn_async(B5)
+        ms5 = timed(step5, 5, 3)
+        ms_aug = timed(lambda: dg.depth_augment(raws[0], rng_state=drng, out=a5.replay_buffer.obs[0:n_aug]), 5, 2)
+        trunk5 = 20_971_520 + 6 * (75_792_384 + 50_725_632 + 50_725_632 + 25_264_128 + 269_484_032)     # SURVEY §8d
+        out[2] = dict(batch_per_gpu=B5, global_batch=B5 * world, ms_per_step=ms5, value=B5 * world / (ms5 / 1e3), unit=UNIT,
+                      depth_frames_per_step=n_aug, depth_aug_frames_per_s=n_aug * world / (ms_aug / 1e3),
+                      model="D=128, 6 blocks, 6 heads, 257 tokens (256x320 frames), MLP 2048",
+                      whole_step_frac_of_peak=B5 / (ms5 / 1e3) * 9 * trunk5 / 1e12 / peaks()["tf_sust"],
+                      path="D=128 / 257 tokens: see DESIGN.md §4 for which kernels of this variant are tcgen05")
+        del a5, raws
+    except Exception as e:
+        out[2] = dict(error=repr(e)[:300])
+    barrier()
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -483,6 +649,9 @@ def main():
     ap.add_argument("--replay", type=int, default=30000, help="replay store transitions (vn/config.yaml:17)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the dp_parity / c4 / c5 records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -16,7 +16,8 @@ MAX_DEPTH = 16
 ACTOR, CRITIC = 0, 1
 FP32, BF16 = 0, 1
 DROP_NONE, DROP_MASK, DROP_RNG = 0, 1, 2
-PROF_NONE, PROF_GEMM_MLP, PROF_GEMM_ALL, PROF_ATTENTION, PROF_GATHER, PROF_ADAM, PROF_MLP_FUSED = range(7)
+(PROF_NONE, PROF_GEMM_MLP, PROF_GEMM_ALL, PROF_ATTENTION, PROF_GATHER, PROF_ADAM, PROF_MLP_FUSED, PROF_LN_BWD, PROF_EMBED,
+ PROF_PATCH) = range(10)
 
 c_f_p = C.c_void_p  # device pointers travel as integers
 
@@ -69,6 +70,10 @@ class ActorGrad(C.Structure):
 
 class CriticIO(C.Structure):
     _fields_ = [("img", c_f_p), ("pstate", c_f_p), ("action", c_f_p), ("drop", Drop), ("q1", c_f_p), ("q2", c_f_p)]
+
+
+class TrunkIO(C.Structure):
+    _fields_ = [("img", c_f_p), ("goal", c_f_p), ("drop", Drop), ("sample_offset", C.c_int32), ("z", c_f_p)]
 
 
 class Adam(C.Structure):
@@ -125,6 +130,10 @@ SYMBOLS = {
     "dgvit_refresh_shadow": (C.c_int, [P(Net), C.c_void_p]),
     "dgvit_actor_forward": (C.c_int, [P(Net), P(ActorIO), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dgvit_actor_backward": (C.c_int, [P(Net), P(ActorIO), P(ActorGrad), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_trunk_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
+    "dgvit_trunk_forward": (C.c_int, [P(Net), P(TrunkIO), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_trunk_backward": (C.c_int, [P(Net), P(TrunkIO), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                       C.c_void_p]),
     "dgvit_critic_forward": (C.c_int, [P(Net), P(CriticIO), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dgvit_critic_backward": (C.c_int, [P(Net), P(CriticIO), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -148,6 +157,9 @@ SYMBOLS = {
     "dgvit_polyak": (C.c_int, [P(Net), P(Net), C.c_float, C.c_void_p]),
     "dgvit_polyak_flat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "dgvit_replay_gather": (C.c_int, [P(Replay), C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
+    "dgvit_replay_record_floats": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    "dgvit_replay_append": (C.c_int, [P(Replay), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "dgvit_debug_drop_mask": (C.c_int, [P(Drop), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "dgvit_depth_scratch_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
     "dgvit_depth_augment": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_size_t, C.c_void_p]),

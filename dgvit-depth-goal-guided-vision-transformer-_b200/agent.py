@@ -26,14 +26,21 @@ class ReplayStore:
     """Device-resident ring store with the fields and ``next_of="obs"`` aliasing of the
     reference's cpprb buffer (vn/DRL.py:80-89).  Index *selection* stays on the host side of
     the boundary (the reference never updates priorities, so PER sampling is uniform);
-    the row gather is a bit-exact CUDA kernel (``dgvit_replay_gather``)."""
+    the row gather is a bit-exact CUDA kernel (``dgvit_replay_gather``) and transitions enter the
+    store through one packed host record + one scatter kernel (``dgvit_replay_append``).
+
+    Ring layout: ``cap = size + 1`` frame rows; transition at row ``i`` has its ``next_obs`` in row
+    ``(i + 1) % cap``.  ``head`` is the row the next transition's ``obs`` goes to; it always holds the
+    newest ``next_obs`` and is never a sampleable transition, so a stored transition can not be paired
+    with a frame of a later episode once the ring has wrapped (cpprb keeps that frame in a side cache)."""
+
+    STAGE_RECORDS = 64          # transitions per packed staging buffer
 
     def __init__(self, size: int, obs_shape=(128, 160), action_dim=2, pstate_dim=2, device="cuda", seed=0):
         self.size = int(size)
         self.obs_shape = tuple(obs_shape)
         self.device = torch.device(device)
         f = obs_shape[0] * obs_shape[1]
-        # one extra slot: next_obs of the newest transition lives at (idx+1) % (size+1) like cpprb's next_of
         self.cap = self.size + 1
         self.obs = torch.zeros(self.cap, f, dtype=torch.float32, device=self.device)
         self.pobs = torch.zeros(self.cap, pstate_dim, dtype=torch.float32, device=self.device)
@@ -47,25 +54,73 @@ class ReplayStore:
         self.head = 0
         self.action_dim, self.pstate_dim = action_dim, pstate_dim
         self._gen = torch.Generator().manual_seed(seed)
+        self._rec = int(L.lib().dgvit_replay_record_floats(f, pstate_dim, action_dim))
+        self._stage = None
+        self._stage_slot = 0
 
     def get_stored_size(self):
         return self.stored
 
+    def _struct(self) -> L.Replay:
+        return L.Replay(obs=self.obs.data_ptr(), size=self.cap, frame=self.obs.shape[1], pobs=self.pobs.data_ptr(),
+                        next_pobs=self.next_pobs.data_ptr(), act=self.act.data_ptr(), rew=self.rew.data_ptr(),
+                        done=self.done.data_ptr(), n_pstate=self.pstate_dim, n_act=self.action_dim)
+
+    # ---- write path (vn/DRL.py:449-477)
     def add(self, obs, act, pobs, next_pobs, rew, next_obs, engage=0.0, done=0.0):
-        i = self.head
-        j = (i + 1) % self.cap
-        dev = self.device
-        self.obs[i] = torch.as_tensor(np.asarray(obs, dtype=np.float32).reshape(-1)).to(dev)
-        self.obs[j] = torch.as_tensor(np.asarray(next_obs, dtype=np.float32).reshape(-1)).to(dev)
-        self.act[i] = torch.as_tensor(np.asarray(act, dtype=np.float32).reshape(-1)).to(dev)
-        self.pobs[i] = torch.as_tensor(np.asarray(pobs, dtype=np.float32).reshape(-1)).to(dev)
-        self.next_pobs[i] = torch.as_tensor(np.asarray(next_pobs, dtype=np.float32).reshape(-1)).to(dev)
-        self.rew[i] = float(rew)
-        self.done[i] = float(done)
-        self.engage[i] = float(engage)
-        self.engage_host[i] = float(engage)
-        self.head = j if j < self.size else 0
-        self.stored = min(self.stored + 1, self.size)
+        """One transition, or a batch when ``obs`` carries a leading transition axis (cpprb ``add`` accepts both;
+        ``initialize_expert_buffer`` is called with whole demonstration datasets, vn/main.py:264-266)."""
+        f = self.obs.shape[1]
+        o = np.asarray(obs, dtype=np.float32)
+        H, W = self.obs_shape
+        ok = (o.shape[-2:] == (H, W) and o.ndim in (2, 3)) or (o.shape[-3:] == (H, W, 1) and o.ndim in (3, 4)) or \
+             (o.shape[-1] == f and o.ndim in (1, 2))
+        if not ok:      # e.g. the 4-channel frame-stacked demonstrations of the legacy pipeline
+            raise ValueError(f"obs of shape {o.shape} is not [n,]{H}x{W}[x1] depth frames")
+        n = o.size // f
+        col = lambda v, w: np.broadcast_to(np.asarray(v, dtype=np.float32).reshape(-1, w) if np.ndim(v) else
+                                           np.full((1, w), float(v), np.float32), (n, w))
+        self.add_batch(o.reshape(n, f), np.asarray(next_obs, dtype=np.float32).reshape(n, f), col(pobs, self.pstate_dim),
+                       col(next_pobs, self.pstate_dim), col(act, self.action_dim), col(rew, 1), col(done, 1), col(engage, 1))
+
+    def add_batch(self, obs, next_obs, pobs, next_pobs, act, rew, done, engage):
+        """n transitions (2-D float32 arrays, oldest first) -> packed pinned records -> one H2D copy and one scatter
+        kernel per ``STAGE_RECORDS`` transitions."""
+        n, f, R = obs.shape[0], self.obs.shape[1], self._rec
+        if self._stage is None:
+            K = self.STAGE_RECORDS
+            self._stage = [dict(host=torch.zeros(K, R, dtype=torch.float32).pin_memory(),
+                                slots=torch.zeros(K, dtype=torch.int64).pin_memory(),
+                                dev=torch.zeros(K, R, dtype=torch.float32, device=self.device),
+                                dslots=torch.zeros(K, dtype=torch.int64, device=self.device),
+                                ev=torch.cuda.Event()) for _ in range(2)]
+        st = self._struct()
+        for a in range(0, n, self.STAGE_RECORDS):
+            b = min(n, a + self.STAGE_RECORDS)
+            k = b - a
+            sg = self._stage[self._stage_slot]
+            self._stage_slot ^= 1
+            sg["ev"].synchronize()                     # the copy that last read this pinned buffer has completed
+            rec = sg["host"].numpy()
+            rec[:k, :f] = obs[a:b]
+            rec[:k, f:2 * f] = next_obs[a:b]
+            c = 2 * f
+            for arr, w in ((pobs, self.pstate_dim), (next_pobs, self.pstate_dim), (act, self.action_dim), (rew, 1),
+                           (done, 1), (engage, 1)):
+                rec[:k, c:c + w] = arr[a:b]
+                c += w
+            slots = sg["slots"].numpy()
+            for i in range(k):
+                slots[i] = self.head
+                self.engage_host[self.head] = engage[a + i, 0]
+                self.head = (self.head + 1) % self.cap
+                self.stored = min(self.stored + 1, self.size)
+            stream = torch.cuda.current_stream(self.device)
+            sg["dev"][:k].copy_(sg["host"][:k], non_blocking=True)
+            sg["dslots"][:k].copy_(sg["slots"][:k], non_blocking=True)
+            sg["ev"].record(stream)
+            L.check(L.lib().dgvit_replay_append(C.byref(st), self.engage.data_ptr(), sg["dev"].data_ptr(),
+                                                sg["dslots"].data_ptr(), k, stream.cuda_stream), "replay_append")
 
     def fill_synthetic(self, n: int, seed: int = 3407):
         """Synthetic transitions written straight on the device."""
@@ -79,21 +134,43 @@ class ReplayStore:
         self.act[:n] = torch.rand(n, self.action_dim, device=self.device, generator=g) * 2 - 1
         self.rew[:n] = (torch.randn(n, 1, device=self.device, generator=g) * 20).clamp(-200, 500)
         self.done[:n] = (torch.rand(n, 1, device=self.device, generator=g) < 0.01).float()
-        self.stored, self.head = n, n % self.size
+        self.stored, self.head = n, n % self.cap
+
+    # ---- read path (vn/DRL.py:375-386)
+    def live_rows(self) -> np.ndarray:
+        """Store rows of the live transitions, oldest first."""
+        return (self.head - self.stored + np.arange(self.stored)) % self.cap
 
     def sample_indexes(self, batch_size: int) -> torch.Tensor:
-        return torch.randint(0, max(self.stored, 1), (batch_size,), generator=self._gen, dtype=torch.int64)
+        k = torch.randint(0, max(self.stored, 1), (batch_size,), generator=self._gen, dtype=torch.int64)
+        first = (self.head - self.stored) % self.cap
+        return k if first == 0 else (k + first) % self.cap
 
     def gather(self, idx: torch.Tensor, out: Dict[str, torch.Tensor]):
         """out: dict of preallocated device tensors obs,next_obs,pobs,next_pobs,act,rew,done."""
         B = idx.numel()
-        st = L.Replay(obs=self.obs.data_ptr(), size=self.cap, frame=self.obs.shape[1], pobs=self.pobs.data_ptr(),
-                      next_pobs=self.next_pobs.data_ptr(), act=self.act.data_ptr(), rew=self.rew.data_ptr(),
-                      done=self.done.data_ptr(), n_pstate=self.pstate_dim, n_act=self.action_dim)
+        st = self._struct()
         L.check(L.lib().dgvit_replay_gather(C.byref(st), idx.data_ptr(), B, out["obs"].data_ptr(),
                                             out["next_obs"].data_ptr(), out["pobs"].data_ptr(),
                                             out["next_pobs"].data_ptr(), out["act"].data_ptr(), out["rew"].data_ptr(),
                                             out["done"].data_ptr(), _stream(self.device)), "replay_gather")
+
+    # ---- on-disk format (vn/DRL.py:505-510 call cpprb's save_transitions / load_transitions; cpprb is absent here, so the
+    #      file is this store's own .npz: one array per field, oldest transition first)
+    def save_transitions(self, file: str):
+        rows = torch.as_tensor(self.live_rows(), device=self.device)
+        nxt = (rows + 1) % self.cap
+        cpu = lambda t: t.cpu().numpy()
+        np.savez(file if str(file).endswith(".npz") else str(file) + ".npz",
+                 obs=cpu(self.obs[rows]).reshape(-1, *self.obs_shape), next_obs=cpu(self.obs[nxt]).reshape(-1, *self.obs_shape),
+                 pobs=cpu(self.pobs[rows]), next_pobs=cpu(self.next_pobs[rows]), act=cpu(self.act[rows]),
+                 rew=cpu(self.rew[rows]), done=cpu(self.done[rows]), engage=cpu(self.engage[rows]))
+
+    def load_transitions(self, file: str):
+        d = np.load(file)
+        n = d["obs"].shape[0]
+        eng = d["engage"] if "engage" in d.files else np.zeros((n, 1), np.float32)
+        self.add(d["obs"], d["act"], d["pobs"], d["next_pobs"], d["rew"], d["next_obs"], engage=eng, done=d["done"])
 
 
 # --------------------------------------------------------------------------- agent
@@ -129,17 +206,21 @@ class SAC(object):
         self.lr_a, self.lr_c, self.lr_alpha = LR_A, LR_C, LR_ALPHA
         self.distributed = bool(distributed)
         self.use_cuda_graph = bool(use_cuda_graph)
+        self._graph_nccl = os.environ.get("DGVIT_GRAPH_NCCL", "0") == "1"
 
         torch.manual_seed(self.seed)
         torch.cuda.manual_seed(self.seed)
         np.random.seed(self.seed)
         set_seed(self.seed)
 
-        self.replay_buffer = ReplayStore(BUFFER_SIZE, image_size, action_dim, pstate_dim, self.device, self.seed)
+        # data-parallel ranks draw different minibatch indexes (same model seed, rank-offset sampler seed)
+        rk = self.rank if (self.distributed and torch.distributed.is_initialized()) else 0
+        self.replay_buffer = ReplayStore(BUFFER_SIZE, image_size, action_dim, pstate_dim, self.device,
+                                         self.seed + 7919 * rk)
         self.buffer_size_expert = buffer_size_expert + 1                    # vn/DRL.py:53
         self.guidence_weight, self.engage_weight, self.batch_expert = 1.0, 1.0, 0          # vn/DRL.py:51-52,54
         self.replay_buffer_expert = (ReplayStore(self.buffer_size_expert, image_size, action_dim, pstate_dim, self.device,
-                                                 self.seed + 1) if pre_buffer else None)    # vn/DRL.py:91-100
+                                                 self.seed + 1 + 7919 * rk) if pre_buffer else None)    # vn/DRL.py:91-100
         self._gbuf = {}
 
         if self._cnn_critic:
@@ -176,7 +257,6 @@ class SAC(object):
         self._losses = torch.zeros(4, **f32)
         self._ws = None
         self._batch = None
-        self._idx = None
         self._graphs = {}
         for m in (self.critic, self.critic_target, self.policy):
             m.refresh_shadow()
@@ -203,7 +283,7 @@ class SAC(object):
         self.log_alpha = torch.zeros(1, requires_grad=True, device=dev)                 # :138
         self.alpha_optim = torch.optim.Adam([self.log_alpha], lr=self.lr_alpha)         # :139
         self.target_policy = copy.deepcopy(self.policy)
-        self._batch, self._idx = None, None
+        self._batch = None
 
     def _learn_cnn(self, batch: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None,
                    extra: Optional[Dict[str, torch.Tensor]] = None):
@@ -291,12 +371,24 @@ class SAC(object):
         return self._ws
 
     def _batch_buffers(self, B: int) -> Dict[str, torch.Tensor]:
-        if self._batch is None or self._batch["obs"].shape[0] != B:
+        """Minibatch, index and pinned index-staging buffers of one batch size.  They are kept per batch size for the
+        life of the agent: a captured CUDA graph has their addresses baked in, so alternating batch sizes must find the
+        buffers their graphs were captured with."""
+        if self._batch is None:
+            self._batch = {}
+        ent = self._batch.get(B)
+        if ent is None:
             f = self.replay_buffer.obs.shape[1]
             z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
-            self._batch = dict(obs=z(B, f), next_obs=z(B, f), pobs=z(B, self.pstate_dim), next_pobs=z(B, self.pstate_dim),
-                               act=z(B, self.action_dim), rew=z(B, 1), done=z(B, 1))
-        return self._batch
+            ent = dict(obs=z(B, f), next_obs=z(B, f), pobs=z(B, self.pstate_dim), next_pobs=z(B, self.pstate_dim),
+                       act=z(B, self.action_dim), rew=z(B, 1), done=z(B, 1))
+            # ring of pinned staging buffers: the host may run several steps ahead of the GPU, and a slot is rewritten
+            # only after the H2D copy that last read it has completed
+            ent["_idx"] = torch.zeros(B, dtype=torch.int64, device=self.device)
+            ent["_ring"] = [(torch.zeros(B, dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            ent["_slot"] = 0
+            self._batch[B] = ent
+        return ent
 
     # ------------------------------------------------------------------ the update
     def update_from_batch(self, batch: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None,
@@ -326,7 +418,8 @@ class SAC(object):
                                                               "mask_a", "mask_c_pi")},
                          drop_mode=L.DROP_MASK if noise.get("mask_c") is not None else
                          (L.DROP_NONE if noise.get("no_dropout") else L.DROP_RNG))
-        out = L.SacOut(losses=self._losses.data_ptr(), debug=L.ptr(debug))
+        losses = self._loss_buffer()
+        out = L.SacOut(losses=losses.data_ptr(), debug=L.ptr(debug))
         lib = L.lib()
         nzp = C.byref(nz) if nz is not None else None
         keep = (s, bt, nz, out, ws, batch, noise, debug, extra)      # ctypes structs must outlive the calls
@@ -354,11 +447,27 @@ class SAC(object):
             phase(1)
             allreduce_sum_(self.critic._garena)
             phase(2)
-            allreduce_sum_(self.policy._garena)
+            allreduce_sum_(self.policy._garena)      # carries d(alpha_loss)/d(log_alpha) and the four loss sums in its tail
             phase(3)
-            allreduce_sum_(self._losses)
         self.itera += 1
+        return losses
+
+    def _loss_buffer(self) -> torch.Tensor:
+        """[qf1_loss, policy_loss, qf2_loss, alpha_loss].  Data parallel: four floats in the padded tail of the ACTOR
+        gradient arena (next to the alpha-gradient slot; Adam and the unused-gradient memsets skip that range), so the
+        actor's gradient all-reduce also sums the per-rank loss shares: no separate 16-byte collective."""
+        if self.distributed and self.world > 1:
+            self.policy.bind()
+            slot = int(self.policy.layout().alpha_grad_slot)
+            return self.policy._garena[slot + 1: slot + 5]
         return self._losses
+
+    def close(self):
+        """Drop captured CUDA graphs (call before ``torch.distributed.destroy_process_group``: a graph that holds
+        NCCL kernels must not outlive its communicator)."""
+        self._graphs = {}
+        if torch.cuda.is_available():
+            torch.cuda.synchronize(self.device)
 
     def learn(self, batch_size=64):
         """vn/DRL.py:373-437 — returns (qf1_loss, policy_loss) python floats (one D2H read)."""
@@ -378,19 +487,13 @@ class SAC(object):
         """Same update without the host read-back (losses stay on the device)."""
         B = int(batch_size)
         idx_host = self.replay_buffer.sample_indexes(B)
-        if self._idx is None or self._idx.numel() != B:
-            self._idx = torch.zeros(B, dtype=torch.int64, device=self.device)
-            # ring of pinned staging buffers: the host may run several steps ahead of the GPU, and a slot is rewritten only
-            # after the H2D copy that last read it has completed
-            self._idx_ring = [(torch.zeros(B, dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(4)]
-            self._idx_slot = 0
-        pin, ev = self._idx_ring[self._idx_slot]
-        self._idx_slot = (self._idx_slot + 1) % len(self._idx_ring)
+        batch = self._batch_buffers(B)
+        pin, ev = batch["_ring"][batch["_slot"]]
+        batch["_slot"] = (batch["_slot"] + 1) % len(batch["_ring"])
         ev.synchronize()
         pin.copy_(idx_host)
-        self._idx.copy_(pin, non_blocking=True)
+        batch["_idx"].copy_(pin, non_blocking=True)
         ev.record(torch.cuda.current_stream(self.device))
-        batch = self._batch_buffers(B)
         return self._run(("learn", B), batch, gather=True)
 
     def update_from_batch_graphed(self, batch: Dict[str, torch.Tensor], key) -> torch.Tensor:
@@ -416,41 +519,51 @@ class SAC(object):
         dp = self.distributed and self.world > 1
         if not self.use_cuda_graph:
             if gather:
-                self.replay_buffer.gather(self._idx, batch)
+                self.replay_buffer.gather(batch["_idx"], batch)
             return self.update_from_batch(batch)
-        key = key + (int(self.itera % self.policy_freq == 0),)
+        # a graph freezes every device pointer: re-bound arenas (.to(), load_state_dict(assign=True)) start new entries
+        key = key + (int(self.itera % self.policy_freq == 0), self.policy.net_struct().params,
+                     self.critic.net_struct().params, self.critic_target.net_struct().params)
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = "warm"
             if gather:
-                self.replay_buffer.gather(self._idx, batch)
+                self.replay_buffer.gather(batch["_idx"], batch)
             return self.update_from_batch(batch)
         if ent == "warm":
             torch.cuda.synchronize(self.device)
             phase = self.update_from_batch(batch, _phases=True)
             graphs = []
-            # (data parallel: one graph per phase.  Capturing the NCCL all-reduces into a single graph was measured at +0.3 %
-            # on 2 GPUs and made process teardown hang, so the collectives stay outside the graphs.)
-            for i, which in enumerate((1, 2, 3) if dp else (0,)):
+            # Data parallel: either one graph per phase with the NCCL all-reduces issued eagerly between them, or
+            # (DGVIT_GRAPH_NCCL=1) the collectives captured too, one graph per update; `close()` must then run before the
+            # process group is destroyed.
+            one = dp and self._graph_nccl
+            for i, which in enumerate((1, 2, 3) if (dp and not one) else (0,)):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self._capture_stream()):
                     if gather and i == 0:
-                        self.replay_buffer.gather(self._idx, batch)
-                    keep = phase(which)
+                        self.replay_buffer.gather(batch["_idx"], batch)
+                    if one:
+                        keep = phase(1)
+                        allreduce_sum_(self.critic._garena)
+                        phase(2)
+                        allreduce_sum_(self.policy._garena)
+                        phase(3)
+                    else:
+                        keep = phase(which)
                 graphs.append(g)
-            ent = self._graphs[key] = (graphs, keep)
+            ent = self._graphs[key] = (graphs, keep, self._loss_buffer())
         graphs = ent[0]
-        if dp:
+        if dp and len(graphs) == 3:
             graphs[0].replay()
             allreduce_sum_(self.critic._garena)
             graphs[1].replay()
             allreduce_sum_(self.policy._garena)
             graphs[2].replay()
-            allreduce_sum_(self._losses)
         else:
             graphs[0].replay()
         self.itera += 1
-        return self._losses
+        return ent[2]
 
     def learn_guidence(self, engage, batch_size=64):
         """vn/DRL.py:187-301 — the update the shipped config runs (PRE_BUFFER): agent + expert minibatch
@@ -507,6 +620,25 @@ class SAC(object):
         """vn/DRL.py:469-477."""
         self.replay_buffer_expert.add(obs=s, act=a_exp, pobs=ps, next_pobs=ps_, rew=r, next_obs=s_, done=d)
 
+    def load_demonstrations(self, files):
+        """vn/main.py:232-266: concatenate the demonstration episodes (``.npz`` written by vn/demonstration.py:237-245:
+        obs, act, goal, reward, next_obs, next_goal, done) and put them into the expert buffer in one batched append."""
+        keys = ("obs", "act", "goal", "reward", "next_obs", "next_goal", "done")
+        cols = {k: [] for k in keys}
+        for fn in files:
+            with np.load(fn) as d:
+                for k in keys:
+                    cols[k].append(np.array(d[k]))
+        c = {k: np.concatenate(v, axis=0) for k, v in cols.items()}
+        if self.replay_buffer_expert is None or self.replay_buffer_expert.size < c["obs"].shape[0]:
+            self.buffer_size_expert = c["obs"].shape[0] + 1
+            self.replay_buffer_expert = ReplayStore(self.buffer_size_expert, self.replay_buffer.obs_shape, self.action_dim,
+                                                    self.pstate_dim, self.device, self.seed + 1)
+            self.pre_buffer = True
+        self.initialize_expert_buffer(c["obs"], c["act"], c["goal"][:, :2], c["next_goal"][:, :2], c["reward"],
+                                      c["next_obs"], c["done"])
+        return c["obs"].shape[0]
+
     # ------------------------------------------------------------------ act
     def choose_action(self, istate, pstate, evaluate=False):
         """vn/DRL.py:170-185."""
@@ -517,6 +649,16 @@ class SAC(object):
         """vn/DRL.py:449-467."""
         self.replay_buffer.add(obs=s, act=a if a is not None else a_exp, pobs=ps, next_pobs=ps_, rew=r, next_obs=s_,
                                engage=engage, done=d)
+
+    def save_transition(self, output, timeend=0):
+        """vn/DRL.py:505-506."""
+        self.replay_buffer.save_transitions(file="{}/{}".format(output, timeend))
+
+    def load_transition(self, output):
+        """vn/DRL.py:508-510."""
+        if output is None:
+            return
+        self.replay_buffer.load_transitions("{}.npz".format(output))
 
     # ------------------------------------------------------------------ checkpoints (vn/DRL.py:480-503)
     def load_model(self, output):

@@ -735,10 +735,9 @@ static void fwd(const bf16* QKV, bf16* O, int B, int N, int H, cudaStream_t st) 
 #define DG_ATTN_F(NK_)                                                                                              \
     case NK_: {                                                                                                     \
       constexpr int smem = FwdSmem<NK_>::TOTAL;                                                                     \
-      static bool attr = false;                                                                                     \
-      if (!attr) {                                                                                                  \
+      static DevOnce attr;                                                                                     \
+      if (attr.first()) {                                                                                                  \
         DG_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<NK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
-        attr = true;                                                                                                \
       }                                                                                                             \
       launch_k(attn_fwd_tc_kernel<NK_>, grid, FWD_THREADS, smem, st, tkv, a);                                       \
     } break;
@@ -768,10 +767,9 @@ static void bwd(const bf16* QKV, const bf16* O, const bf16* dO, bf16* dQKV, int 
 #define DG_ATTN_B2(NK_)                                                                                                    \
       case NK_: {                                                                                                          \
         constexpr int smem2 = Bwd2Smem<NK_>::TOTAL;                                                                        \
-        static bool attr2 = false;                                                                                         \
-        if (!attr2) {                                                                                                      \
+        static DevOnce attr2;                                                                                         \
+        if (attr2.first()) {                                                                                                      \
           DG_CUDA(cudaFuncSetAttribute(attn_bwd2_tc_kernel<NK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));     \
-          attr2 = true;                                                                                                    \
         }                                                                                                                  \
         launch_k(attn_bwd2_tc_kernel<NK_>, grid, BWD2_THREADS, smem2, st, tkv, tdo2, a);                                   \
       } break;
@@ -784,10 +782,9 @@ static void bwd(const bf16* QKV, const bf16* O, const bf16* dO, bf16* dQKV, int 
   switch (a.KPAD / 16) {
 #define DG_ATTN_B(NK_)                                                                                              \
     case NK_: {                                                                                                     \
-      static bool attr = false;                                                                                     \
-      if (!attr) {                                                                                                  \
+      static DevOnce attr;                                                                                     \
+      if (attr.first()) {                                                                                                  \
         DG_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<NK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
-        attr = true;                                                                                                \
       }                                                                                                             \
       launch_k(attn_bwd_tc_kernel<NK_>, grid, BWD_THREADS, smem, st, tq, tkv, tdo, a);                              \
     } break;

@@ -119,7 +119,7 @@ inline Prof& prof() {
   return p;
 }
 enum { PROF_NONE = 0, PROF_GEMM_MLP = 1, PROF_GEMM_ALL = 2, PROF_ATTENTION = 3, PROF_GATHER = 4, PROF_ADAM = 5,
-       PROF_MLP_FUSED = 6 };
+       PROF_MLP_FUSED = 6, PROF_LN_BWD = 7, PROF_EMBED = 8, PROF_PATCH = 9 };
 struct ProfScope {
   bool active = false;
   cudaStream_t st;
@@ -158,6 +158,40 @@ static inline int guarded(F&& f) {
     return DGVIT_ERR_ARG;
   }
 }
+
+// ---------------------------------------------------------------- device plumbing
+// Function attributes, streams and events belong to ONE device: one-time initialisation is keyed by the current device.
+struct DevOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & 63;
+}
+// Every entry point runs on the device that owns its buffers, whatever device is current in the calling thread
+// (SAC(device="cuda:1") without torch.cuda.set_device): the guard switches to the device of `p` and back.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const void* p) {
+    if (!p) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return; }
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return;
+    cudaGetDevice(&prev);
+    if (at.device != prev) { cudaSetDevice(at.device); switched = true; }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 // ---------------------------------------------------------------- workspace carving
 struct Carver {

@@ -309,6 +309,7 @@ int dgvit_depth_scratch_bytes(int n, int H, int W, size_t* bytes) {
 int dgvit_depth_augment(const float* raw, const float* noise, const uint64_t* rng_state, int n, int H, int W,
                         float* out, void* scratch, size_t scratch_bytes, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(raw);
     DG_REQUIRE(raw && out && scratch && n >= 1, "null argument");
     DG_REQUIRE(noise || rng_state, "provide noise or rng_state");
     DG_REQUIRE(H % 4 == 0 && W % 4 == 0, "H and W must be multiples of 4");
@@ -328,10 +329,9 @@ int dgvit_depth_augment(const float* raw, const float* noise, const uint64_t* rn
     }
     launch_k(depth_minmax_kernel, dim3(MM_BLOCKS, n), 256, 0, st, raw, mm, (int64_t)H * W);
     DG_LAUNCH_CHECK();
-    static bool attr = false;
-    if (!attr) {
+    static DevOnce attr;
+    if (attr.first()) {
       DG_CUDA(cudaFuncSetAttribute(depth_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
-      attr = true;
     }
     (void)S1; (void)S2; (void)T1;
     launch_k(depth_fused_kernel, dim3((unsigned)cdiv(W / 4, TOW), (unsigned)cdiv(H / 4, TOH), n), 256, FUSED_SMEM, st, raw,

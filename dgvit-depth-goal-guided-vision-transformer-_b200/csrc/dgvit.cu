@@ -316,6 +316,8 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
   const int wpb = g_lnb_wpb;
   int nblocks = (int)std::min<int64_t>(cdiv(T, wpb), 148 * g_lnb_bps);
   if (skip_mask() & SKIP_LN_BWD) return;
+  // algorithmic bytes per row: dY, X, dX in / out (fp32) + the bf16 copy of dX + mean / rstd
+  ProfScope ps(PROF_LN_BWD, 0.0, (double)T * (D * (16.0 + (dX_lp ? 2.0 : 0.0)) + 8.0), st);
   if (defer && D % 4 == 0) partial = defer->alloc((size_t)nblocks * 3 * D); else defer = nullptr;
   const size_t smem = (size_t)wpb * 3 * D * sizeof(float);
   switch (D / 32) {
@@ -346,10 +348,9 @@ static void launch_attention_fwd(const A* QKV, A* O, const Dims& d, cudaStream_t
   const int threads = 256, nw = threads / 32;
   const size_t smem = ((size_t)d.N * (d.dh + 1) + (size_t)d.N * d.dh + (size_t)nw * d.N + (size_t)nw * d.dh) * sizeof(float);
   DG_REQUIRE(smem <= 227 * 1024, "attention_fwd: N=%d dh=%d needs %zu B smem", d.N, d.dh, smem);
-  static bool attr_done = false;  // attribute is per-function; set once per dtype instantiation
-  if (!attr_done) {
+  static DevOnce attr_done;  // attribute is per-function; set once per dtype instantiation
+  if (attr_done.first()) {
     DG_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
   }
   launch_k(attention_fwd_kernel<A>, d.B * d.H, threads, smem, st, QKV, O, d.N, d.H, d.dh, 1.0f / sqrtf((float)d.dh));
   DG_LAUNCH_CHECK();
@@ -368,11 +369,10 @@ static void launch_attention_bwd(const A* QKV, const A* O, const A* dO, A* dQKV,
   const bool qdo_smem = full <= 227 * 1024;
   const size_t smem = qdo_smem ? full : small;
   DG_REQUIRE(smem <= 227 * 1024, "attention_bwd: N=%d dh=%d needs %zu B smem (unsupported in this build)", d.N, d.dh, smem);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DevOnce attr_done;
+  if (attr_done.first()) {
     DG_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DG_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
   }
   const float scale = 1.0f / sqrtf((float)d.dh);
   if (qdo_smem) launch_k(attention_bwd_kernel<A, true>, d.B * d.H, threads, smem, st, QKV, O, dO, dQKV, d.N, d.H, d.dh, scale);
@@ -410,6 +410,7 @@ template <typename A>
 static void launch_patchify(const float* img, A* Pm, int B, const Dims& d, const dgvit_cfg& cfg, cudaStream_t st) {
   const int64_t total4 = (int64_t)B * d.P * d.pd / 4;
   DG_REQUIRE(cfg.patch_w % 4 == 0 && (((uintptr_t)img) & 15) == 0, "patchify: patch_w %% 4 and 16-byte aligned frames required");
+  ProfScope ps(PROF_PATCH, 0.0, (double)total4 * 4 * (4.0 + sizeof(A)), st);
   launch_k(patchify_kernel<A>, grid1d(total4), 256, 0, st, img, Pm, total4, cfg.img_h, cfg.img_w, cfg.patch_h, cfg.patch_w);
   DG_LAUNCH_CHECK();
 }
@@ -430,6 +431,8 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
       LayerBuf<A>& B0 = c.L[0];
       const int wpb = 8;
       const unsigned grid = (unsigned)cdiv(d.T, wpb);
+      // algorithmic bytes per token row: patch-embedding row in, residual stream out (fp32), LN output, mean / rstd
+      ProfScope ps(PROF_EMBED, 0.0, (double)d.T * (d.D * (8.0 + sizeof(A)) + 8.0), st);
       switch (d.D / 32) {
 #define EMB(V) case V: launch_k(embed_ln_kernel<A, V>, grid, wpb * 32, 0, st, gt, c.tok, (const float*)c.Xp, P + L.pos, B0.Xa, drop, \
                                 P + b0.ln1_w, P + b0.ln1_b, B0.Xn1, B0.mean1, B0.rstd1, d.T, d.N); break;
@@ -533,9 +536,12 @@ static bool g_side_enabled = true;
 static bool g_fork_enabled = true;
 static int g_actor_s_when = 1;      // set_option "actor_s_when": 0 = policy.sample(s) forward starts at the fork, 1 = after the
                                     // policy.sample(s') forward, 2 = after the target critic forward (beside the critic backward)
-static SideState& side_state() {
-  static SideState f;
-  static bool init = false;
+static SideState& side_state() {      // one set of streams / events per device
+  static SideState per_dev[64];
+  static bool inited[64] = {};
+  const int dev = current_device();
+  SideState& f = per_dev[dev];
+  bool& init = inited[dev];
   if (!init) {
     const char* pe = getenv("DGVIT_SIDE_PRIO");
     DG_CUDA(cudaStreamCreateWithPriority(&f.s, cudaStreamNonBlocking, pe ? atoi(pe) : 0));
@@ -926,8 +932,15 @@ static void adam_step(const dgvit_net& net, const dgvit_layout& L, const dgvit_a
   a.omb2 = (float)(1.0 - (double)o.beta2);
   a.n_skip = L.n_skip;
   for (int k = 0; k < 4; ++k) { a.skip_b[k] = L.skip_begin[k]; a.skip_e[k] = L.skip_end[k]; }
-  launch_k(adam_polyak_kernel, 148 * 4, 256, 0, st, a);
-  DG_LAUNCH_CHECK();
+  {  // algorithmic bytes: theta, m, v read + written, g read, bf16 shadow written (+ target read / written + its shadow)
+    int64_t used = L.total;
+    for (int k = 0; k < L.n_skip; ++k) used -= L.skip_end[k] - L.skip_begin[k];
+    const double per = 28.0 + (a.shadow ? 2.0 : 0.0);
+    const double tgt_b = a.tgt ? (double)L.total * (12.0 + (a.tgt_shadow ? 2.0 : 0.0)) : 0.0;
+    ProfScope ps(PROF_ADAM, 0.0, used * per + tgt_b, st);
+    launch_k(adam_polyak_kernel, 148 * 4, 256, 0, st, a);
+    DG_LAUNCH_CHECK();
+  }
 }
 
 // ------------------------------------------------------------------ SAC.learn
@@ -979,8 +992,11 @@ struct ForkState {
   cudaEvent_t fork, fork2, fork3, join[2];
 };
 static ForkState& fork_state() {
-  static ForkState f;
-  static bool init = false;
+  static ForkState per_dev[64];
+  static bool inited[64] = {};
+  const int dev = current_device();
+  ForkState& f = per_dev[dev];
+  bool& init = inited[dev];
   if (!init) {
     for (int i = 0; i < 2; ++i) {
       const char* pe = getenv("DGVIT_AUX_PRIO");
@@ -1284,6 +1300,7 @@ int dgvit_sac_workspace_bytes(const dgvit_cfg* acfg, int B, int n_extra, int pre
 
 int dgvit_refresh_shadow(const dgvit_net* net, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(net ? net->params : nullptr);
     DG_REQUIRE(net && net->params && net->shadow, "null argument");
     dgvit_layout L;
     make_layout(net->cfg, L);
@@ -1295,6 +1312,7 @@ int dgvit_refresh_shadow(const dgvit_net* net, void* stream) {
 int dgvit_actor_forward(const dgvit_net* net, const dgvit_actor_io* io, int B, int precision, int save,
                         void* ws, size_t ws_bytes, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(net ? net->params : nullptr);
     DG_REQUIRE(net && io && ws && B >= 1 && net->cfg.kind == DGVIT_ACTOR && net->params, "bad argument");
     dgvit_layout L;
     make_layout(net->cfg, L);
@@ -1314,6 +1332,7 @@ int dgvit_actor_forward(const dgvit_net* net, const dgvit_actor_io* io, int B, i
 int dgvit_actor_backward(const dgvit_net* net, const dgvit_actor_io* io, const dgvit_actor_grad* g, int B,
                          int precision, void* ws, size_t ws_bytes, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(net ? net->params : nullptr);
     DG_REQUIRE(net && io && g && ws && B >= 1 && net->cfg.kind == DGVIT_ACTOR && net->params && net->grads,
                "bad argument");
     dgvit_layout L;
@@ -1333,6 +1352,7 @@ int dgvit_actor_backward(const dgvit_net* net, const dgvit_actor_io* io, const d
 int dgvit_critic_forward(const dgvit_net* net, const dgvit_critic_io* io, int B, int precision, int save,
                          void* ws, size_t ws_bytes, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(net ? net->params : nullptr);
     DG_REQUIRE(net && io && ws && B >= 1 && net->cfg.kind == DGVIT_CRITIC && net->params, "bad argument");
     dgvit_layout L;
     make_layout(net->cfg, L);
@@ -1353,6 +1373,7 @@ int dgvit_critic_backward(const dgvit_net* net, const dgvit_critic_io* io, const
                           float* d_action, int param_grads, int B, int precision, void* ws, size_t ws_bytes,
                           void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(net ? net->params : nullptr);
     DG_REQUIRE(net && io && d_q1 && d_q2 && ws && B >= 1 && net->cfg.kind == DGVIT_CRITIC && net->params,
                "bad argument");
     if (param_grads) DG_REQUIRE(net->grads, "null grads");
@@ -1371,9 +1392,72 @@ int dgvit_critic_backward(const dgvit_net* net, const dgvit_critic_io* io, const
   });
 }
 
+// GoT.forward(img, goal) -> z (vn/GoalFormer.py:156-171) on its own: patch embedding, goal token prepended, position
+// embedding, dropout, the transformer blocks, token-0 pooling, RMSNorm.  `net` may be an actor or a critic arena (the
+// trunk sits at the same offsets in both).
+int dgvit_trunk_workspace_bytes(const dgvit_cfg* cfg, int B, int precision, int save, size_t* bytes) {
+  return guarded([&] {
+    DG_REQUIRE(cfg && bytes && B >= 1, "bad argument");
+    Dims d(*cfg, B);
+    Carver cv(nullptr, 0, true);
+    by_precision(precision, [&] { TrunkCtx<float> c; carve_trunk<float>(cv, d, save != 0, c); },
+                 [&] { TrunkCtx<bf16> c; carve_trunk<bf16>(cv, d, save != 0, c); });
+    *bytes = cv.off;
+  });
+}
+
+int dgvit_trunk_forward(const dgvit_net* net, const dgvit_trunk_io* io, int B, int precision, int save, void* ws,
+                        size_t ws_bytes, void* stream) {
+  return guarded([&] {
+    DeviceGuard dev_guard(net ? net->params : nullptr);
+    DG_REQUIRE(net && io && ws && B >= 1 && net->params && io->img && io->goal && io->z, "bad argument");
+    dgvit_layout L;
+    make_layout(net->cfg, L);
+    Dims d(net->cfg, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto run = [&](auto tag) {
+      using A = decltype(tag);
+      Carver cv(ws, ws_bytes);
+      TrunkCtx<A> c;
+      carve_trunk<A>(cv, d, save != 0, c);
+      const DropDev drop = make_drop(io->drop, d, io->sample_offset);
+      GoalTok gt{nullptr, nullptr, nullptr, 0, 0};
+      gt.direct = io->goal;
+      trunk_forward<A>(*net, L, d, io->img, drop, c, st, gt, /*fuse_rms=*/false);
+      DG_CUDA(cudaMemcpyAsync(io->z, c.z, (size_t)B * d.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    };
+    if (precision == DGVIT_BF16) DG_REQUIRE(net->shadow, "bf16 needs a shadow arena");
+    by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
+  });
+}
+
+int dgvit_trunk_backward(const dgvit_net* net, const dgvit_trunk_io* io, const float* d_z, float* d_goal, int B,
+                         int precision, void* ws, size_t ws_bytes, void* stream) {
+  return guarded([&] {
+    DeviceGuard dev_guard(net ? net->params : nullptr);
+    DG_REQUIRE(net && io && d_z && ws && B >= 1 && net->params && net->grads, "bad argument");
+    dgvit_layout L;
+    make_layout(net->cfg, L);
+    Dims d(net->cfg, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto run = [&](auto tag) {
+      using A = decltype(tag);
+      Carver cv(ws, ws_bytes);
+      TrunkCtx<A> c;
+      carve_trunk<A>(cv, d, true, c);
+      DG_CUDA(cudaMemcpyAsync(c.dz, d_z, (size_t)B * d.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      const DropDev drop = make_drop(io->drop, d, io->sample_offset);
+      trunk_backward<A>(*net, L, d, drop, c, /*relu_tok=*/0, st);
+      if (d_goal) DG_CUDA(cudaMemcpyAsync(d_goal, c.dtok, (size_t)B * d.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    };
+    by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
+  });
+}
+
 static int sac_run(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* nz, const dgvit_sac_out* out, int B,
                    void* ws, size_t ws_bytes, void* stream, int phases) {
   return guarded([&] {
+    DeviceGuard dev_guard(s ? s->actor.params : nullptr);
     DG_REQUIRE(s && ws, "null argument");
     check_sac(*s, B);
     if (phases & 3) {
@@ -1420,6 +1504,7 @@ int dgvit_gemm_bf16(int M, int N, int K, const void* A, int64_t a_sm, int64_t a_
                     int64_t b_sn, float* C, int64_t ldc, int splitk, float* partial, int use_tensor_cores,
                     void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(A);
     DG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
     GemmArgs g;
     g.M = M; g.N = N; g.K = K;
@@ -1442,6 +1527,7 @@ int dgvit_gemm_bf16(int M, int N, int K, const void* A, int64_t a_sm, int64_t a_
 int dgvit_linear_bf16(const void* x, const void* W, void* y, int64_t rows, int N, int K, int epilogue, const float* bias,
                       const void* aux, void* y2, int weight_is_kn, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(x);
     DG_REQUIRE(x && W && y && rows > 0 && N > 0 && K > 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     GemmArgs g;
@@ -1472,6 +1558,7 @@ int dgvit_mlp_bf16(const void* x, const void* W1, const float* b1, const void* W
                    float* out, const void* d_y, float* d_x, float* d_w, float* d_b2, float* partial, int64_t rows, int hid,
                    void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(x);
 #ifdef DGVIT_WITH_TC
     DG_REQUIRE(x && W1 && b1 && W2 && rows > 0 && hid > 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1495,6 +1582,7 @@ int dgvit_mlp_bf16(const void* x, const void* W1, const float* b1, const void* W
 int dgvit_attention_bf16(const void* qkv, void* o, const void* d_o, void* d_qkv, int B, int N, int H, int dim_head,
                          int use_tensor_cores, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(qkv);
     DG_REQUIRE(qkv && o && B >= 1 && N >= 1 && H >= 1, "bad argument");
     dgvit_cfg c;
     memset(&c, 0, sizeof(c));
@@ -1554,6 +1642,7 @@ int dgvit_qnet_forward(const float* params, const float* img, const float* pstat
                        int img_h, int img_w, int n_act, int n_pstate, int B, int precision, void* ws, size_t ws_bytes,
                        void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(params);
     DG_REQUIRE(params && img && pstate && action && q1 && q2 && ws, "qnet_forward: null argument");
     DG_REQUIRE((((uintptr_t)img) & 15) == 0 && (((uintptr_t)params) & 15) == 0, "qnet_forward: 16-byte alignment required");
     qnet_check(img_h, img_w, n_act, n_pstate, B);
@@ -1574,6 +1663,7 @@ int dgvit_qnet_backward(const float* params, float* grads, const float* img, con
                         const float* d_q2, float* d_action, int param_grads, int img_h, int img_w, int n_act, int n_pstate,
                         int B, int precision, void* ws, size_t ws_bytes, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(params);
     DG_REQUIRE(params && img && pstate && d_q1 && d_q2 && ws, "qnet_backward: null argument");
     DG_REQUIRE(!param_grads || grads, "qnet_backward: param_grads without a gradient arena");
     qnet_check(img_h, img_w, n_act, n_pstate, B);
@@ -1593,6 +1683,7 @@ int dgvit_qnet_backward(const float* params, float* grads, const float* img, con
 
 int dgvit_adam_step(const dgvit_net* net, const dgvit_adam* opt, const dgvit_net* tgt, float tau, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(net ? net->params : nullptr);
     DG_REQUIRE(net && opt && net->params && net->grads, "null argument");
     dgvit_layout L;
     make_layout(net->cfg, L);
@@ -1602,6 +1693,7 @@ int dgvit_adam_step(const dgvit_net* net, const dgvit_adam* opt, const dgvit_net
 
 int dgvit_polyak(const dgvit_net* target, const dgvit_net* source, float tau, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(target ? target->params : nullptr);
     DG_REQUIRE(target && source && target->params && source->params, "null argument");
     dgvit_layout L, Ls;
     make_layout(target->cfg, L);
@@ -1615,6 +1707,7 @@ int dgvit_polyak(const dgvit_net* target, const dgvit_net* source, float tau, vo
 
 int dgvit_polyak_flat(float* target, const float* source, int64_t n, float tau, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(target);
     DG_REQUIRE(target && source && n >= 0, "null argument");
     if (n == 0) return;
     launch_k(polyak_kernel, 148 * 4, 256, 0, (cudaStream_t)stream, target, source, (bf16*)nullptr, tau, n);
@@ -1625,27 +1718,72 @@ int dgvit_polyak_flat(float* target, const float* source, int64_t n, float tau, 
 int dgvit_replay_gather(const dgvit_replay* s, const int64_t* idx, int B, float* obs, float* next_obs, float* pobs,
                         float* next_pobs, float* act, float* rew, float* done, void* stream) {
   return guarded([&] {
+    DeviceGuard dev_guard(s ? s->obs : nullptr);
     DG_REQUIRE(s && idx && B >= 0 && s->obs && s->size > 0, "bad argument");
     DG_REQUIRE(s->frame % 4 == 0, "frame size must be a multiple of 4 floats");
     DG_REQUIRE(((uintptr_t)s->obs % 16) == 0 && ((uintptr_t)obs % 16) == 0 && ((uintptr_t)next_obs % 16) == 0,
                "frame buffers must be 16-byte aligned");
     if (B == 0) return;
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t frame4 = s->frame / 4;
-    // small batches: one float4 per thread (more CTAs in flight); large batches: 8 chunks per frame
-    const int chunks = (int)std::min<int64_t>(cdiv(frame4, 256), B <= 1024 ? 32 : 8);
-    dim3 grid((unsigned)chunks, (unsigned)B, 2);
-    launch_k(replay_gather_frames_kernel, grid, 256, 0, st, (const float4*)s->obs, idx, s->size, frame4, (float4*)obs,
-                                                      (float4*)next_obs);
-    DG_LAUNCH_CHECK();
-    SmallGather g;
+    GatherArgs g;
+    memset(&g, 0, sizeof(g));
+    g.store = (const float4*)s->obs; g.idx = idx; g.size = s->size; g.frame4 = s->frame / 4;
+    g.obs = (float4*)obs; g.next_obs = (float4*)next_obs;
     g.n = 5;
     g.src[0] = s->pobs; g.dst[0] = pobs; g.width[0] = s->n_pstate;
     g.src[1] = s->next_pobs; g.dst[1] = next_pobs; g.width[1] = s->n_pstate;
     g.src[2] = s->act; g.dst[2] = act; g.width[2] = s->n_act;
     g.src[3] = s->rew; g.dst[3] = rew; g.width[3] = 1;
     g.src[4] = s->done; g.dst[4] = done; g.width[4] = 1;
-    launch_k(replay_gather_small_kernel, (unsigned)cdiv(B, 128), 128, 0, st, g, idx, B);
+    DG_REQUIRE(2 * s->n_pstate + s->n_act + 2 <= 256, "too many scalar fields per transition");
+    // slices per frame: every thread moves GATHER_ILP float4 per pass; one pass per block at the shipped frame size
+    const int slices = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(g.frame4, 256 * GATHER_ILP), 64));
+    ProfScope ps(PROF_GATHER, 0.0, (double)B * (4.0 * s->frame * 4 + (2 * s->n_pstate + s->n_act + 2) * 8.0), st);
+    launch_k(replay_gather_kernel, dim3((unsigned)slices, (unsigned)B, 2), 256, 0, st, g);
+    DG_LAUNCH_CHECK();
+  });
+}
+
+int dgvit_replay_append(const dgvit_replay* s, float* engage_store, const float* records,
+                        const int64_t* slots, int n, void* stream) {
+  return guarded([&] {
+    DeviceGuard dev_guard(s ? s->obs : nullptr);
+    DG_REQUIRE(s && records && slots && n >= 0 && s->obs && s->size > 0, "bad argument");
+    DG_REQUIRE(s->frame % 4 == 0 && ((uintptr_t)s->obs % 16) == 0 && ((uintptr_t)records % 16) == 0,
+               "frames must be 16-byte aligned multiples of 4 floats");
+    if (n == 0) return;
+    AppendArgs a;
+    memset(&a, 0, sizeof(a));
+    a.store = (float4*)s->obs; a.size = s->size; a.frame4 = s->frame / 4;
+    a.fld[0] = (float*)s->pobs; a.width[0] = s->n_pstate;
+    a.fld[1] = (float*)s->next_pobs; a.width[1] = s->n_pstate;
+    a.fld[2] = (float*)s->act; a.width[2] = s->n_act;
+    a.fld[3] = (float*)s->rew; a.width[3] = 1;
+    a.fld[4] = (float*)s->done; a.width[4] = 1;
+    a.fld[5] = engage_store; a.width[5] = 1;
+    const int64_t scal = 2 * s->n_pstate + s->n_act + 3;
+    a.rec = records; a.rec_floats = (2 * s->frame + scal + 3) / 4 * 4;      // records are padded to 16 bytes
+    a.slot = slots;
+    const int slices = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(a.frame4, 1024), 16));
+    launch_k(replay_append_kernel, dim3((unsigned)slices, (unsigned)n, 2), 256, 0, (cudaStream_t)stream, a);
+    DG_LAUNCH_CHECK();
+  });
+}
+int64_t dgvit_replay_record_floats(int64_t frame, int n_pstate, int n_act) {
+  return (2 * frame + 2 * n_pstate + n_act + 3 + 3) / 4 * 4;
+}
+
+// the embedding-dropout keep decisions a trunk call with `drop` makes for B samples of N tokens x D features, as a
+// {0,1} mask [B, N, D] (tests: the in-kernel Philox stream must equal an injected DGVIT_DROP_MASK run)
+int dgvit_debug_drop_mask(const dgvit_drop* drop, int B, int N, int D, int sample_offset, uint8_t* out, void* stream) {
+  return guarded([&] {
+    DeviceGuard dev_guard(out);
+    DG_REQUIRE(drop && out && B >= 1 && N >= 1 && D >= 1, "bad argument");
+    DropDev r;
+    r.mode = drop->mode; r.p = drop->p; r.scale = 1.0f; r.mask = drop->keep_mask; r.rng = drop->rng_state;
+    r.stream_id = drop->stream_id; r.elem_offset = (int64_t)sample_offset * N * D;
+    const int64_t total = (int64_t)B * N * D;
+    launch_k(drop_mask_dump_kernel, grid1d(total), 256, 0, (cudaStream_t)stream, r, out, total);
     DG_LAUNCH_CHECK();
   });
 }

@@ -662,10 +662,9 @@ static int sm_count() {
 template <int BN, bool A_MN, bool B_MN, typename TC>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const TcArgs& a, cudaStream_t st) {
   using SL = SmemLayout<BN>;
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (attr.first()) {
     DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL));
-    attr = true;
   }
   const int tiles = (int)(cdiv(a.M, BM) * cdiv(a.N, BN) * a.splitk);
   const int grid = std::min(tiles, sm_count());

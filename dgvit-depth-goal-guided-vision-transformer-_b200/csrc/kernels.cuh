@@ -71,6 +71,7 @@ __global__ void embed_assemble_kernel(const float* __restrict__ tok, const float
 struct GoalTok {
   const float* ps; const float* W; const float* b;   // pstate [B,nps], fc_embed.weight [D,nps], .bias [D]
   int nps, relu;
+  const float* direct = nullptr;                     // GoT.forward(img, goal): the goal token itself [B,D] (ps / W / b unused)
 };
 template <typename A, int VPL>
 __global__ void embed_ln_kernel(GoalTok gt, float* __restrict__ tok, const float* __restrict__ Xp,
@@ -92,9 +93,13 @@ __global__ void embed_ln_kernel(GoalTok gt, float* __restrict__ tok, const float
     const int d = lane + 32 * i;
     float x;
     if (n == 0) {
-      x = gt.b[d];
-      for (int j = 0; j < gt.nps; ++j) x = fmaf(gt.W[d * gt.nps + j], gt.ps[b * gt.nps + j], x);
-      if (gt.relu) x = fmaxf(x, 0.f);
+      if (gt.direct) {
+        x = gt.direct[b * D + d];
+      } else {
+        x = gt.b[d];
+        for (int j = 0; j < gt.nps; ++j) x = fmaf(gt.W[d * gt.nps + j], gt.ps[b * gt.nps + j], x);
+        if (gt.relu) x = fmaxf(x, 0.f);
+      }
       tok[b * D + d] = x;
     } else {
       x = Xp[(b * (N - 1) + (n - 1)) * D + d];
@@ -156,6 +161,14 @@ __global__ void dpos_kernel(const float* __restrict__ dX0, float* __restrict__ p
     }
     part[((int64_t)s * N + n) * D + d] = acc;
   }
+}
+
+// the keep decisions of drop_factor as a {0,1} mask (dgvit_debug_drop_mask: tests)
+__global__ void drop_mask_dump_kernel(DropDev drop, uint8_t* __restrict__ out, int64_t total) {
+  pdl_wait();
+  pdl_launch();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = drop_factor(drop, i) != 0.0f ? 1 : 0;
 }
 
 // =====================================================================================
@@ -1056,42 +1069,89 @@ __global__ void rng_advance_kernel(uint64_t* rng) {
   pdl_launch(); if (threadIdx.x == 0 && blockIdx.x == 0) rng[1] += 1; }
 
 // =====================================================================================
-// Replay gather (cpprb sample(); vn/DRL.py:375-386): bit-exact 16-byte vectorised row copies.
-// grid = (chunks, B, 2): z=0 -> obs[idx], z=1 -> obs[(idx+1)%size]
+// Replay gather (cpprb sample(); vn/DRL.py:375-386): bit-exact 16-byte vectorised row copies, ONE launch.
+// grid = (slices, B, 2): z=0 -> obs[idx], z=1 -> obs[(idx+1)%size]; every thread keeps GATHER_ILP independent
+// 16-byte loads in flight (the copy is a pure latency x bandwidth problem).  The block (0, b, 0) also copies the
+// per-transition scalar fields of row b.  The field table is a __grid_constant__ parameter: indexed straight out of
+// the constant bank (a by-value copy indexed at run time lands in local memory).
 // =====================================================================================
-__global__ void replay_gather_frames_kernel(const float4* __restrict__ store, const int64_t* __restrict__ idx,
-                                            int64_t size, int64_t frame4, float4* __restrict__ obs,
-                                            float4* __restrict__ next_obs) {
+constexpr int GATHER_ILP = 4;
+struct GatherArgs {
+  const float4* store; const int64_t* idx; int64_t size, frame4;
+  float4* obs; float4* next_obs;
+  const float* src[5]; float* dst[5]; int width[5]; int n;
+};
+__global__ void __launch_bounds__(256) replay_gather_kernel(const __grid_constant__ GatherArgs a) {
   pdl_wait();
   pdl_launch();
   const int b = blockIdx.y;
-  int64_t r = idx[b];
-  float4* dst = obs;
-  if (blockIdx.z == 1) { r = (r + 1) % size; dst = next_obs; }
+  int64_t r = a.idx[b];
+  if (blockIdx.x == 0 && blockIdx.z == 0) {
+    // scalar fields: thread t copies element t of the concatenated fields (<= 16 floats per transition)
+    int t = threadIdx.x;
+    for (int k = 0; k < a.n; ++k) {
+      const int w = a.width[k];
+      if (t < w) { if (a.dst[k] && a.src[k]) a.dst[k][(int64_t)b * w + t] = a.src[k][r * w + t]; break; }
+      t -= w;
+    }
+  }
+  float4* dst = a.obs;
+  if (blockIdx.z == 1) { r = (r + 1) % a.size; dst = a.next_obs; }
   if (!dst) return;
-  const float4* src = store + r * frame4;
-  dst += (int64_t)b * frame4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < frame4;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + i));
-    dst[i] = v;
+  const float4* src = a.store + r * a.frame4;
+  dst += (int64_t)b * a.frame4;
+  const int64_t per = (int64_t)blockDim.x * GATHER_ILP;
+  for (int64_t base = (int64_t)blockIdx.x * per; base < a.frame4; base += (int64_t)gridDim.x * per) {
+    float4 v[GATHER_ILP];
+#pragma unroll
+    for (int u = 0; u < GATHER_ILP; ++u) {
+      const int64_t i = base + u * blockDim.x + threadIdx.x;
+      if (i < a.frame4)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(src + i));
+    }
+#pragma unroll
+    for (int u = 0; u < GATHER_ILP; ++u) {
+      const int64_t i = base + u * blockDim.x + threadIdx.x;
+      if (i < a.frame4) __stcs(dst + i, v[u]);
+    }
   }
 }
-struct SmallGather {
-  const float* src[5]; float* dst[5]; int width[5]; int n;
+
+// =====================================================================================
+// Replay append (store_transition / initialize_expert_buffer, vn/DRL.py:449-477): n packed transition records
+// [obs frame | next_obs frame | pobs | next_pobs | act | rew | done | engage] (floats; the record may live in pinned
+// host memory: zero-copy) scattered into the ring store in ONE launch: obs -> slot[i], next_obs -> (slot[i]+1) % size
+// (cpprb next_of="obs").  grid = (slices, n, 2).
+// =====================================================================================
+struct AppendArgs {
+  float4* store; int64_t size, frame4;
+  float* fld[6]; int width[6];              // pobs, next_pobs, act, rew, done, engage
+  const float* rec; int64_t rec_floats;     // record pitch
+  const int64_t* slot;                      // [n] (device or pinned host)
 };
-__global__ void replay_gather_small_kernel(SmallGather s, const int64_t* __restrict__ idx, int B) {
+__global__ void __launch_bounds__(256) replay_append_kernel(const __grid_constant__ AppendArgs a) {
   pdl_wait();
   pdl_launch();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int64_t r = idx[b];
-  for (int k = 0; k < s.n; ++k) {
-    if (!s.dst[k] || !s.src[k]) continue;
-    for (int j = 0; j < s.width[k]; ++j) s.dst[k][b * s.width[k] + j] = s.src[k][r * s.width[k] + j];
+  const int i = blockIdx.y;
+  const int64_t s = a.slot[i];
+  const float* rec = a.rec + (int64_t)i * a.rec_floats;
+  if (blockIdx.x == 0 && blockIdx.z == 0) {
+    int t = threadIdx.x;
+    const float* f = rec + 8 * a.frame4;
+    for (int k = 0; k < 6; ++k) {
+      const int w = a.width[k];
+      if (t < w) { if (a.fld[k]) a.fld[k][s * w + t] = f[t]; break; }
+      t -= w; f += w;
+    }
   }
+  const int64_t row = blockIdx.z == 0 ? s : (s + 1) % a.size;
+  // the next record of the same call overwrites that slot with its own obs (cpprb: the later add wins)
+  if (blockIdx.z == 1 && i + 1 < (int)gridDim.y && a.slot[i + 1] == row) return;
+  const float4* src = reinterpret_cast<const float4*>(rec) + (blockIdx.z == 0 ? 0 : a.frame4);
+  float4* dst = a.store + row * a.frame4;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.frame4; j += (int64_t)gridDim.x * blockDim.x)
+    dst[j] = src[j];
 }
 
 }  // namespace dgvit

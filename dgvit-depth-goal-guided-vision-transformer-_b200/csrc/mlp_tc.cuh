@@ -917,13 +917,12 @@ static void fwd(const bf16* x, const bf16* W1, const float* b1, const bf16* W2, 
   CUtensorMap tw1 = make_map(W1, 64, HID, 64, 64, 128);
   CUtensorMap tw2 = make_map(W2, HID, 64, HID, 64, 64);
   CUtensorMap two = front ? make_map(fr.Wo, 256, 64, 256, 64, 64) : tw1;
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (attr.first()) {
     DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
     DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
     DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL_FRONT));
     DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL_FRONT));
-    attr = true;
   }
   if (skip_mask() & SKIP_MLP_FWD) return;
   const int grid = (int)cdiv(M, 128);
@@ -976,12 +975,11 @@ static void bwd(const bf16* x, const bf16* dy, const bf16* W1, const float* b1, 
   CUtensorMap tdy = make_map(dy, 64, M, 64, 64, 128);
   CUtensorMap tw1 = make_map(W1, 64, HID, 64, 64, 128);
   CUtensorMap tw2 = make_map(W2, HID, 64, HID, 64, 64);
-  static bool attr = false;
-  if (!attr) {
+  static DevOnce attr;
+  if (attr.first()) {
     DG_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b::SMEM_TOTAL));
     DG_CUDA(cudaFuncSetAttribute((mlp_bwd_tc_kernel<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b::SMEM_TOTAL));
     DG_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b::SMEM_TOTAL));
-    attr = true;
   }
   const bool split = g_split_enabled && tiles * f::NSPLIT <= sm_count() && NC % f::NSPLIT == 0;
   if (skip_mask() & SKIP_MLP_BWD_X) {}

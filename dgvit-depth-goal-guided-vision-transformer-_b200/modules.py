@@ -53,7 +53,8 @@ def weights_init_(m):
 class _Patchify(nn.Module):
     """Placeholder for einops ``Rearrange('b (h p1) (w p2) -> b (h w) (p1 p2)')`` so that the
     patch Linear keeps the key ``to_patch_embedding.1`` (vn/GoalFormer.py:137-139).  The
-    rearrangement itself is folded into the patch-embedding kernel's addressing."""
+    rearrangement itself happens on the device inside the patch-embedding stage (``csrc/dgvit.cu``,
+    K1): no permuted copy of the frame is made on the Python side."""
 
     def __init__(self, p1, p2):
         super().__init__()
@@ -87,6 +88,10 @@ class Attention(nn.Module):
     def __init__(self, dim, heads=8, dim_head=64, dropout=0.0):
         super().__init__()
         inner_dim = dim_head * heads
+        if heads == 1 and dim_head == dim:
+            # the reference drops the output projection there (nn.Identity, vn/GoalFormer.py:55,67-70): another network
+            # (no to_out parameters, other state_dict keys, other RNG consumption at init) than the kernels implement
+            raise NotImplementedError("heads == 1 with dim_head == dim (no output projection) is not on the accelerated path")
         self.heads = heads
         self.scale = dim_head ** -0.5
         self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=False)
@@ -105,8 +110,9 @@ class Transformer(nn.Module):
 
 
 class GoT(nn.Module):
-    """Parameter container of the DGViT trunk (vn/GoalFormer.py:123-154).  The forward pass
-    is executed by the owning ``GoTPolicy`` / ``GoTQNetwork`` (one fused C call)."""
+    """The DGViT trunk (vn/GoalFormer.py:123-171).  Inside ``GoTPolicy`` / ``GoTQNetwork`` the owner runs it fused with
+    its heads (one C call); ``GoT.forward(img, goal)`` on its own goes through ``dgvit_trunk_forward`` on the owner's
+    arena (or a private arena for a stand-alone trunk)."""
 
     def __init__(self, *, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim, pool="cls",
                  channels=3, dim_head=64, dropout=0.0, emb_dropout=0.1):
@@ -137,8 +143,33 @@ class GoT(nn.Module):
         self.to_latent = nn.Identity()
         self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, num_classes))
 
+    def _set_owner(self, owner):
+        import weakref
+        object.__setattr__(self, "_owner_ref", weakref.ref(owner))
+
+    def _backend(self):
+        """The arena module that runs this trunk: the owning GoTPolicy / GoTQNetwork, else a private one."""
+        ref = self.__dict__.get("_owner_ref")
+        owner = ref() if ref is not None else None
+        if owner is None:
+            owner = self.__dict__.get("_standalone")
+            if owner is None:
+                owner = _StandaloneTrunk(self)
+                object.__setattr__(self, "_standalone", owner)      # not a registered sub-module (no cycle)
+        return owner
+
     def forward(self, img, goal):
-        raise NotImplementedError("call the owning GoTPolicy / GoTQNetwork; the trunk runs fused with its heads")
+        """vn/GoalFormer.py:156-171: img [B,H,W] + goal token [B,dim] -> z [B,dim] (``dgvit_trunk_forward``)."""
+        be = self._backend()
+        be.bind()
+        _require_cuda(be._arena)
+        img = be._check_img(img)
+        goal = goal.to(img.device, torch.float32)
+        if goal.dim() != 2 or goal.shape[0] != img.shape[0] or goal.shape[1] != self.dim:
+            raise ValueError(f"goal must be [B,{self.dim}], got {tuple(goal.shape)}")
+        ps_ = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in ps_) or goal.requires_grad)
+        return _TrunkFn.apply(be, self, need_grad, img, goal, *ps_)
 
 
 # --------------------------------------------------------------------------- arena binding
@@ -188,7 +219,7 @@ class _ArenaModule(nn.Module):
         raise NotImplementedError
 
     def _unused(self, name: str) -> bool:
-        return (name.endswith("cls_token") or ".mlp_head." in name or name.startswith("conv"))
+        return (name.endswith("cls_token") or "mlp_head." in name or name.startswith("conv"))
 
     # ---- binding
     def _bound(self) -> bool:
@@ -265,7 +296,7 @@ class _ArenaModule(nn.Module):
         keep-mask [B, N, D] of the embedding dropout, ``eps`` the rsample draw [B, n_act]."""
         self._noise_fifo.append(dict(mask=mask, eps=eps))
 
-    def _drop_struct(self, B: int, keep: List) -> Tuple[L.Drop, Optional[torch.Tensor]]:
+    def _drop_struct(self, B: int, keep: List, training: Optional[bool] = None) -> Tuple[L.Drop, Optional[torch.Tensor]]:
         dev = self._arena.device
         inj = self._noise_fifo.pop(0) if self._noise_fifo else None
         eps = None
@@ -280,9 +311,15 @@ class _ArenaModule(nn.Module):
             assert m.numel() == B * self.layout_tokens() * self._cfg.dim, "mask shape"
             keep.append(m)
             d.mode, d.keep_mask = L.DROP_MASK, m.data_ptr()
-        elif self.training and self.trans.emb_dropout > 0 and inj is None:
+        elif (self.training if training is None else training) and self.trans.emb_dropout > 0 and inj is None:
             d.mode = L.DROP_RNG
             self._rng_state[1] += 1          # host-ordered counter bump (plumbing, not arithmetic)
+            # The backward kernels regenerate the keep mask from {seed, counter}: bind the counter to THIS call (a
+            # snapshot kept alive with the saved workspace), so a later forward on the same module cannot change the mask
+            # an earlier, not yet back-propagated pass used (learn_guidence with the CNN critic: two samples, one backward).
+            call_state = self._rng_state.clone()
+            keep.append(call_state)
+            d.rng_state = call_state.data_ptr()
         return d, eps
 
     def layout_tokens(self) -> int:
@@ -304,6 +341,9 @@ class _ArenaModule(nn.Module):
         skip = {"_act_state": None, "_ws_cache": {}, "_noise_fifo": [], "_rng_state": None}
         for k, v in self.__dict__.items():
             new.__dict__[k] = skip[k] if k in skip else _copy.deepcopy(v, memo)
+        trunk = new._modules.get("trans")
+        if trunk is not None:
+            trunk._set_owner(new)          # the copied trunk runs on the copy's arena
         return new
 
     # nn.Module plumbing: .to()/.cuda()/.float() replace p.data -> arenas are re-bound lazily
@@ -332,6 +372,69 @@ def _require_cuda(t: torch.Tensor):
     if not t.is_cuda:
         raise RuntimeError("dgvit_b200 runs on CUDA (sm_100a) only; move the module with .to('cuda'). "
                            "There is no CPU fallback.")
+
+
+# --------------------------------------------------------------------------- trunk on its own
+class _TrunkFn(torch.autograd.Function):
+    """GoT.forward through ``dgvit_trunk_forward`` / ``dgvit_trunk_backward``."""
+
+    @staticmethod
+    def forward(ctx, be, got, need_grad, img, goal, *params):
+        B, dev = img.shape[0], img.device
+        keep: List = []
+        drop, _ = be._drop_struct(B, keep, training=got.training)
+        goal_c = goal.detach().contiguous()
+        z = torch.empty(B, got.dim, device=dev)
+        nbytes = C.c_size_t()
+        L.check(L.lib().dgvit_trunk_workspace_bytes(C.byref(be._cfg), B, be._precision_code(), int(need_grad),
+                                                    C.byref(nbytes)), "trunk_workspace_bytes")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        io = L.TrunkIO(img=img.data_ptr(), goal=goal_c.data_ptr(), drop=drop, sample_offset=0, z=z.data_ptr())
+        net = be.net_struct()
+        if be.precision == "bf16":
+            be.refresh_shadow()
+        L.check(L.lib().dgvit_trunk_forward(C.byref(net), C.byref(io), B, be._precision_code(), int(need_grad),
+                                            ws.data_ptr(), ws.numel(), _stream(dev)), "trunk_forward")
+        ctx.be, ctx.got, ctx.io, ctx.ws, ctx.B = be, got, io, ws, B
+        ctx.keep = (img, goal_c, z, keep)
+        ctx.needs = [p.requires_grad for p in params]
+        ctx.goal_grad = goal.requires_grad
+        return z
+
+    @staticmethod
+    def backward(ctx, d_z):
+        be, got, B = ctx.be, ctx.got, ctx.B
+        dev = ctx.keep[0].device
+        d_z = d_z.contiguous().float()
+        d_goal = torch.empty(B, got.dim, device=dev) if ctx.goal_grad else None
+        net = be.net_struct()
+        L.check(L.lib().dgvit_trunk_backward(C.byref(net), C.byref(ctx.io), d_z.data_ptr(), L.ptr(d_goal), B,
+                                             be._precision_code(), ctx.ws.data_ptr(), ctx.ws.numel(), _stream(dev)),
+                "trunk_backward")
+        offs = dict(_trunk_offsets(be.layout(), be._cfg.depth, pre=""))
+        grads = []
+        for (name, p), need in zip(got.named_parameters(), ctx.needs):
+            if not need or be._unused(name):
+                grads.append(None)
+            else:
+                grads.append(be._garena[offs[name]:offs[name] + p.numel()].view(p.shape).clone())
+        return (None, None, None, None, d_goal) + tuple(grads)
+
+
+class _StandaloneTrunk(_ArenaModule):
+    """Arena + C structs for a ``GoT`` used outside GoTPolicy / GoTQNetwork (an actor-kind layout whose head ranges
+    stay unused)."""
+
+    KIND = L.ACTOR
+
+    def __init__(self, got: "GoT"):
+        super().__init__()
+        self.trans = got
+        self._init_backend(2, 2, got.depth, got.heads, got.dim, image_size=got.image_size, patch_size=got.patch_size,
+                           mlp_dim=got.mlp_dim, dim_head=got.dim_head)
+
+    def _named_offsets(self):
+        return _trunk_offsets(self.layout(), self._cfg.depth)
 
 
 # --------------------------------------------------------------------------- actor
@@ -405,6 +508,7 @@ class GoTPolicy(_ArenaModule):
             self.action_scale = torch.FloatTensor((action_space.high - action_space.low) / 2.0)
             self.action_bias = torch.FloatTensor((action_space.high + action_space.low) / 2.0)
         self._init_backend(nb_actions, nb_pstate, block, head, l_f_size, image_size=image_size, mlp_dim=mlp_dim)
+        self.trans._set_owner(self)
 
     def _named_offsets(self):
         lay = self.layout()
@@ -582,6 +686,7 @@ class GoTQNetwork(_ArenaModule):
         self.fc31 = nn.Linear(32, nb_actions)
         self.apply(weights_init_)
         self._init_backend(nb_actions, nb_pstate, block, head, l_f_size, image_size=image_size, mlp_dim=mlp_dim)
+        self.trans._set_owner(self)
 
     def _named_offsets(self):
         lay = self.layout()

@@ -34,10 +34,12 @@ _scratch = {}
 
 
 def depth_augment(raw: torch.Tensor, noise: Optional[torch.Tensor] = None,
-                  rng_state: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  rng_state: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Depth normalise -> +N(0,50) -> clip -> 5x5 blur -> 11x11 centre-band blur -> 4x bilinear
     resize -> /255 (vn/env_lab.py:420-434,78-90,69-76,295-299).  raw [n,H,W] f32 on CUDA;
-    ``noise`` [n,H,W] f32 N(0,50) draws, or ``rng_state`` (int64[2] on device) to generate them."""
+    ``noise`` [n,H,W] f32 N(0,50) draws, or ``rng_state`` (int64[2] on device) to generate them.  ``out``: optional
+    contiguous f32 destination of n*(H/4)*(W/4) elements, e.g. consecutive rows of a ``ReplayStore`` (the states go
+    straight into the store, no intermediate copy)."""
     if not raw.is_cuda:
         raise RuntimeError("depth_augment runs on CUDA only (no CPU fallback)")
     if raw.dim() == 2:
@@ -57,7 +59,10 @@ def depth_augment(raw: torch.Tensor, noise: Optional[torch.Tensor] = None,
         sc = torch.empty(nb.value, dtype=torch.uint8, device=raw.device)
         _scratch.clear()
         _scratch[key] = sc
-    out = torch.empty(n, H // 4, W // 4, dtype=torch.float32, device=raw.device)
+    if out is None:
+        out = torch.empty(n, H // 4, W // 4, dtype=torch.float32, device=raw.device)
+    elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == n * (H // 4) * (W // 4)):
+        raise ValueError("out must be a contiguous CUDA float32 tensor of n*(H/4)*(W/4) elements")
     L.check(L.lib().dgvit_depth_augment(raw.data_ptr(), L.ptr(noise), L.ptr(rng_state), n, H, W, out.data_ptr(),
                                         sc.data_ptr(), sc.numel(), _stream(raw.device)), "depth_augment")
     return out

@@ -192,7 +192,8 @@ const char* dgvit_last_error(void);
  * CUDA-event timing of the launches of one kernel family (DGVIT_PROF_*), recorded on the
  * launching stream.  dgvit_prof_end synchronises on the recorded events. */
 enum { DGVIT_PROF_NONE = 0, DGVIT_PROF_GEMM_MLP = 1, DGVIT_PROF_GEMM_ALL = 2, DGVIT_PROF_ATTENTION = 3,
-       DGVIT_PROF_GATHER = 4, DGVIT_PROF_ADAM = 5, DGVIT_PROF_MLP_FUSED = 6 };
+       DGVIT_PROF_GATHER = 4, DGVIT_PROF_ADAM = 5, DGVIT_PROF_MLP_FUSED = 6, DGVIT_PROF_LN_BWD = 7,
+       DGVIT_PROF_EMBED = 8, DGVIT_PROF_PATCH = 9 };
 long long dgvit_launch_count(void);
 /* runtime switches for measurement / A-B tests (results are identical for every setting up to summation order; the
  * stream switches change nothing at all, tests/test_gpu_parity.py):
@@ -229,6 +230,23 @@ int dgvit_actor_forward(const dgvit_net* net, const dgvit_actor_io* io, int B, i
 int dgvit_actor_backward(const dgvit_net* net, const dgvit_actor_io* io,
                          const dgvit_actor_grad* g, int B, int precision, void* workspace,
                          size_t workspace_bytes, void* stream);
+
+/* ---- GoT.forward(img, goal) (vn/GoalFormer.py:156-171): the trunk on its own.  goal [B, dim] is the goal token
+ * (the caller's fc_embed output), z [B, dim] the pooled, RMS-normalised token 0.  `net` may be an actor or a critic
+ * arena (the trunk tensors sit at the same offsets).  backward: d_z [B, dim] -> the trunk ranges of net->grads
+ * (head ranges untouched) and d_goal [B, dim] (optional). */
+typedef struct dgvit_trunk_io {
+  const float* img;   /* [B, img_h, img_w] */
+  const float* goal;  /* [B, dim] */
+  dgvit_drop drop;
+  int32_t sample_offset;
+  float* z;           /* [B, dim] */
+} dgvit_trunk_io;
+int dgvit_trunk_workspace_bytes(const dgvit_cfg* cfg, int B, int precision, int save_for_backward, size_t* bytes);
+int dgvit_trunk_forward(const dgvit_net* net, const dgvit_trunk_io* io, int B, int precision, int save_for_backward,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int dgvit_trunk_backward(const dgvit_net* net, const dgvit_trunk_io* io, const float* d_z, float* d_goal, int B,
+                         int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* GoTQNetwork.forward — vn/got_sac_network.py:107-123 */
 int dgvit_critic_forward(const dgvit_net* net, const dgvit_critic_io* io, int B, int precision,
@@ -334,6 +352,20 @@ typedef struct dgvit_replay {
 int dgvit_replay_gather(const dgvit_replay* store, const int64_t* idx, int B, float* obs,
                         float* next_obs, float* pobs, float* next_pobs, float* act, float* rew,
                         float* done, void* stream);
+
+/* store_transition / initialize_expert_buffer (vn/DRL.py:449-477): n packed transition records
+ *   [obs frame | next_obs frame | pobs | next_pobs | act | rew | done | engage]  (floats, record pitch
+ *   dgvit_replay_record_floats(): padded to 16 bytes; device memory or pinned host memory read zero-copy)
+ * are scattered into the ring store by ONE kernel: obs -> row slots[i], next_obs -> row (slots[i]+1) % size (cpprb
+ * next_of="obs": when two records of one call target the same row the later one wins), scalar fields -> row slots[i].
+ * engage_store [size, 1]: the one field dgvit_replay does not carry (the gather never returns it); may be NULL. */
+int64_t dgvit_replay_record_floats(int64_t frame, int n_pstate, int n_act);
+int dgvit_replay_append(const dgvit_replay* store, float* engage_store, const float* records, const int64_t* slots,
+                        int n, void* stream);
+
+/* test hook: the embedding-dropout keep decisions ({0,1}, [B, N, D]) a trunk call with `drop` makes for samples
+ * sample_offset .. sample_offset+B-1 (DGVIT_DROP_RNG: the Philox stream the kernels evaluate in place) */
+int dgvit_debug_drop_mask(const dgvit_drop* drop, int B, int N, int D, int sample_offset, uint8_t* out, void* stream);
 
 /* depth normalise + noise + blur + resize — vn/env_lab.py:420-434,78-90,69-76,295-299.
  * raw [n, H, W] f32, noise [n, H, W] f32 (N(0,50) draws) or NULL (generated from rng),

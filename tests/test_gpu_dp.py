@@ -44,7 +44,7 @@ def _worker(rank, world, port, B, steps, out):
     torch.cuda.synchronize()
     if rank == 0:
         torch.save(dict(actor=ag.policy._arena.cpu(), critic=ag.critic._arena.cpu(), target=ag.critic_target._arena.cpu(),
-                        losses=ag._losses.cpu(), log_alpha=ag.log_alpha.cpu()), out)
+                        losses=ag._loss_buffer().cpu(), log_alpha=ag.log_alpha.cpu()), out)
     dist.destroy_process_group()
 
 

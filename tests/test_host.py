@@ -110,6 +110,32 @@ def test_state_dict_roundtrip_and_deepcopy(tmp_path):
     assert not copy.deepcopy(a)._bound() or True     # a deep copy re-binds lazily; must not raise
 
 
+def test_unsupported_reference_variants_fail_loudly():
+    """heads == 1 with dim_head == dim: the reference replaces the attention output projection by nn.Identity
+    (vn/GoalFormer.py:55,67-70) — another network than the kernels implement; building it must not silently succeed."""
+    with pytest.raises(NotImplementedError):
+        dg.GoTPolicy(2, 2, 2, 1, 64)
+    dg.GoTPolicy(2, 2, 2, 1, 32)            # heads == 1 with a projection (dim != dim_head) is fine
+    # a deep copy's trunk runs on the copy's arena, not on the original's
+    a = dg.GoTPolicy(2, 2, 1, 2, 32)
+    b = copy.deepcopy(a)
+    assert b.trans._backend() is b and a.trans._backend() is a
+    # the trunk of a stand-alone GoT gets a private arena whose layout follows the trunk's registration order
+    t = dg.GoT(image_size=(128, 160), patch_size=(16, 20), num_classes=2, dim=32, depth=2, heads=2, mlp_dim=2048, channels=1)
+    be = t._backend()
+    assert [n for n, _ in be._named_offsets()] == [n for n, _ in be.named_parameters()]
+    be.bind()
+    assert be._bound()
+
+
+def test_replay_record_layout():
+    """one packed transition record = obs frame | next_obs frame | pobs | next_pobs | act | rew | done | engage, padded to
+    16 bytes (dgvit_replay_append)"""
+    n = L.lib().dgvit_replay_record_floats(128 * 160, 2, 2)
+    assert n == 2 * 128 * 160 + 12 and n % 4 == 0
+    assert L.lib().dgvit_replay_record_floats(64, 3, 2) == (2 * 64 + 11 + 3) // 4 * 4
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     a = dg.GoTPolicy(2, 2, 2, 2, 32)
