@@ -390,15 +390,14 @@ def run_ours(args):
     rs_ = [torch.randn(rows, 64, device=dev, generator=gsrc) for _ in range(nset)]
     outs = [torch.empty(rows, 64, device=dev) for _ in range(nset)]
     W1 = (torch.randn(2048, 64, device=dev, generator=gsrc) * 0.125).bfloat16()
-    W2 = (torch.randn(64, 2048, device=dev, generator=gsrc) * 2048 ** -0.5).bfloat16()
+    W2 = (torch.randn(64, 2048, device=dev, generator=gsrc) * 2048 ** -0.5).half()       # f16 copy, as the update reads it
     b1, b2 = torch.randn(2048, device=dev, generator=gsrc) * 0.3, torch.randn(64, device=dev, generator=gsrc)
     def mlp_burst(n):
         st_ = torch.cuda.current_stream(dev).cuda_stream
         for i in range(n):
             j = i % nset
-            L.check(lib.dgvit_mlp_bf16(xs[j].data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
-                                       rs_[j].data_ptr(), outs[j].data_ptr(), None, None, None, None, None, rows, 2048, st_),
-                    "mlp_bf16")
+            L.check(lib.dgvit_mlp_fwd_f16w2(xs[j].data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                                            rs_[j].data_ptr(), outs[j].data_ptr(), rows, 2048, st_), "mlp_fwd_f16w2")
     mlp_burst(8)
     torch.cuda.synchronize(dev)
     gb = torch.cuda.CUDAGraph()           # replayed from a graph like the real step: no host launch cost between kernels

@@ -145,10 +145,12 @@ SYMBOLS = {
                                   C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "dgvit_linear_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "dgvit_attention_stats_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "dgvit_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                       C.c_int, C.c_void_p]),
+                                       C.c_int, C.c_void_p, C.c_void_p]),
     "dgvit_mlp_bf16": (C.c_int, [C.c_void_p] * 12 + [C.c_int64, C.c_int, C.c_void_p]),
     "dgvit_mlp_partial_floats": (C.c_int64, [C.c_int64, C.c_int]),
+    "dgvit_mlp_fwd_f16w2": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int, C.c_void_p]),
     "dgvit_qnet_param_layout": (C.c_int, [C.c_int, C.c_int, P(QnetLayout)]),
     "dgvit_qnet_workspace_bytes": (C.c_int, [C.c_int] * 6 + [P(C.c_size_t)]),
     "dgvit_qnet_forward": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -95,8 +95,10 @@ class ReplayStore:
                                 dslots=torch.zeros(K, dtype=torch.int64, device=self.device),
                                 ev=torch.cuda.Event()) for _ in range(2)]
         st = self._struct()
-        for a in range(0, n, self.STAGE_RECORDS):
-            b = min(n, a + self.STAGE_RECORDS)
+        # at most `size` records per launch: a longer run would wrap onto rows written by the same launch
+        step = min(self.STAGE_RECORDS, self.size)
+        for a in range(0, n, step):
+            b = min(n, a + step)
             k = b - a
             sg = self._stage[self._stage_slot]
             self._stage_slot ^= 1

@@ -37,9 +37,11 @@ inline void fail(int code, const char* fmt, ...) {
 #define DG_CUDA(call)                                                                          \
   do {                                                                                         \
     cudaError_t e__ = (call);                                                                  \
-    if (e__ != cudaSuccess)                                                                    \
+    if (e__ != cudaSuccess) {                                                                  \
+      cudaGetLastError(); /* do not leave it pending for a later, unrelated call */            \
       ::dgvit::fail(DGVIT_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,                 \
                     cudaGetErrorString(e__));                                                  \
+    }                                                                                          \
   } while (0)
 // every kernel launch of the library passes through here: error check + launch accounting
 // (bench.py reports the count as "gpu_launches")
@@ -84,7 +86,12 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  DG_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) {
+    cudaGetLastError();      // a refused launch must not linger as the "last error" of a later, unrelated call
+    fail(DGVIT_ERR_CUDA, "kernel launch refused (%s): grid (%u,%u,%u) block %u dynamic smem %zu", cudaGetErrorString(e), grid.x,
+         grid.y, grid.z, block.x, smem);
+  }
 }
 
 // same, as thread-block clusters of `cluster` CTAs along x
@@ -101,7 +108,12 @@ static inline void launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bl
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  DG_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    fail(DGVIT_ERR_CUDA, "cluster kernel launch refused (%s): grid (%u,%u,%u) block %u dynamic smem %zu cluster %d",
+         cudaGetErrorString(e), grid.x, grid.y, grid.z, block.x, smem, cluster);
+  }
 }
 
 // optional per-kernel timing of the launches tagged as the dominant kernel (bench.py roofline):

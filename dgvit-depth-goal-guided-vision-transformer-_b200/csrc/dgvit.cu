@@ -17,6 +17,7 @@
 #ifdef DGVIT_WITH_TC
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
+#include "attn_long_tc.cuh"
 #include "mlp_tc.cuh"
 #endif
 
@@ -99,6 +100,8 @@ template <> struct WSel<float> {
 template <> struct WSel<bf16> {
   static const bf16* w(const dgvit_net& n, int64_t off) { return (const bf16*)n.shadow + off; }
 };
+// f16 copy of a tensor: second half of the shadow arena (see store_shadows4)
+static const void* w_f16(const dgvit_net& n, const dgvit_layout& L, int64_t off) { return n.shadow + L.total + off; }
 
 // ------------------------------------------------------------------ GEMM dispatch
 // single-query-row attention in the last block (set_option "attention_row0": bit 0 forward, bit 1 backward).  Measured
@@ -196,6 +199,7 @@ template <typename A>
 struct LayerBuf {
   float *Xa, *Xm, *mean1, *rstd1, *mean2, *rstd2;
   A *Xn1, *QKV, *O, *Xn2, *Hpre, *Hact;
+  float* lse = nullptr;     // [B, H, N] softmax statistics of the long-sequence attention kernels (N > 128 only)
 };
 template <typename A>
 struct TrunkCtx {
@@ -205,6 +209,7 @@ struct TrunkCtx {
   // backward scratch (only when saved)
   float *dX, *dXn, *dtok, *dz, *dg_rows, *partial;
   A *dH, *dO, *dQKV, *dXp;
+  float* attn_delta = nullptr;   // [B, H, N] rowsum(dO o O) of the long-sequence attention backward (N > 128 only)
   bf16* dXh;  // bf16 copy of dX (operand of the tensor-core GEMMs); null in the fp32 path
   float* dXc; bf16* dXch;   // last block: compact [B, D] residual gradient of the token-0 rows
   bf16 *dXh2, *dXch2;       // second bf16 copies (gradient after LayerNorm-2): lets the weight-gradient stream keep reading
@@ -237,6 +242,7 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
     b.Xn1 = cv.take<A>(d.T * d.D);
     b.QKV = cv.take<A>(d.T * 3 * d.inner);
     b.O = cv.take<A>(d.T * d.inner);
+    b.lse = (d.N > 128 && !std::is_same<A, float>::value) ? cv.take<float>(d.T * d.H) : nullptr;
     b.Xn2 = cv.take<A>(d.T * d.D);
     b.Hpre = cv.take<A>(d.T * d.M);
     b.Hact = cv.take<A>(d.T * d.M);
@@ -249,7 +255,7 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
   }
   c.dX = nullptr; c.dXn = nullptr; c.dtok = nullptr; c.dz = nullptr; c.dg_rows = nullptr; c.partial = nullptr;
   c.dH = nullptr; c.dO = nullptr; c.dQKV = nullptr; c.dXp = nullptr; c.dXh = nullptr; c.partial_floats = 0; c.misc_floats = 0;
-  c.dXc = nullptr; c.dXch = nullptr; c.dXh2 = nullptr; c.dXch2 = nullptr;
+  c.dXc = nullptr; c.dXch = nullptr; c.dXh2 = nullptr; c.dXch2 = nullptr; c.attn_delta = nullptr;
   if (save) {
     c.dX = cv.take<float>(d.T * d.D);
     c.dXn = cv.take<float>(d.T * d.D);
@@ -259,6 +265,7 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
     c.dH = cv.take<A>(d.T * d.M);
     c.dO = cv.take<A>(d.T * d.inner);
     c.dQKV = cv.take<A>(d.T * 3 * d.inner);
+    c.attn_delta = (d.N > 128 && !std::is_same<A, float>::value) ? cv.take<float>(d.T * d.H) : nullptr;
     c.dXp = cv.take<A>((int64_t)d.B * d.P * d.D);
     c.dXh = std::is_same<A, float>::value ? nullptr : cv.take<bf16>(d.T * d.D);
     c.dXc = cv.take<float>((int64_t)d.B * d.D);
@@ -338,11 +345,13 @@ static void launch_ln_bwd(const float* dY, const float* X, const float* mean, co
 }
 
 template <typename A>
-static void launch_attention_fwd(const A* QKV, A* O, const Dims& d, cudaStream_t st) {
+static void launch_attention_fwd(const A* QKV, A* O, const Dims& d, cudaStream_t st, float* lse = nullptr) {
   ProfScope ps(PROF_ATTENTION, 4.0 * d.B * d.H * (double)d.N * d.N * d.dh, 0.0, st);
 #ifdef DGVIT_WITH_TC
   if constexpr (std::is_same<A, bf16>::value) {
     if (attn::eligible(d.N, d.dh, QKV, 3 * d.inner)) return attn::fwd(QKV, O, d.B, d.N, d.H, st);
+    // more than one 128-row tile (257 tokens at 2x resolution): key-chunked tcgen05 kernels (attn_long_tc.cuh)
+    if (lse && attnl::eligible(d.N, d.dh, QKV, 3 * d.inner)) return attnl::fwd(QKV, O, lse, d.B, d.N, d.H, st);
   }
 #endif
   const int threads = 256, nw = threads / 32;
@@ -356,11 +365,14 @@ static void launch_attention_fwd(const A* QKV, A* O, const Dims& d, cudaStream_t
   DG_LAUNCH_CHECK();
 }
 template <typename A>
-static void launch_attention_bwd(const A* QKV, const A* O, const A* dO, A* dQKV, const Dims& d, cudaStream_t st) {
+static void launch_attention_bwd(const A* QKV, const A* O, const A* dO, A* dQKV, const Dims& d, cudaStream_t st,
+                                 float* lse = nullptr, float* delta = nullptr) {
   ProfScope ps(PROF_ATTENTION, 10.0 * d.B * d.H * (double)d.N * d.N * d.dh, 0.0, st);
 #ifdef DGVIT_WITH_TC
   if constexpr (std::is_same<A, bf16>::value) {
     if (attn::eligible(d.N, d.dh, QKV, 3 * d.inner)) return attn::bwd(QKV, O, dO, dQKV, d.B, d.N, d.H, st);
+    if (lse && delta && attnl::eligible(d.N, d.dh, QKV, 3 * d.inner) && ((((uintptr_t)dO) | ((uintptr_t)dQKV) | ((uintptr_t)O)) & 15) == 0)
+      return attnl::bwd(QKV, O, dO, dQKV, lse, delta, d.B, d.N, d.H, st);
   }
 #endif
   const int threads = 256, nw = threads / 32;
@@ -453,7 +465,7 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
     ln1_done = false;
     linear_fwd<A, A, A>(B_.Xn1, WSel<A>::w(net, b.qkv_w), B_.QKV, d.T, 3 * d.inner, d.D, EPI_NONE, nullptr, st);
     // (last block: only the token-0 row of the attention output is ever read)
-    if (!(l == d.L - 1 && launch_attention_row0<A>(B_.QKV, B_.O, nullptr, nullptr, d, st))) launch_attention_fwd<A>(B_.QKV, B_.O, d, st);
+    if (!(l == d.L - 1 && launch_attention_row0<A>(B_.QKV, B_.O, nullptr, nullptr, d, st))) launch_attention_fwd<A>(B_.QKV, B_.O, d, st, B_.lse);
     // Only token 0 of the last block's output is consumed (x[:, 0], vn/GoalFormer.py:167): there the
     // out-projection, LayerNorm, MLP and residuals run on the B token-0 rows only (compact [B, D]
     // buffers).  Exact: the pruned rows never reach z, so outputs and every gradient are unchanged.
@@ -507,7 +519,7 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
         }
         ProfScope ps3(PROF_GEMM_ALL, front_done ? 2.0 * R * d.D * d.inner : 0.0, 0.0, st);
         mlp::fwd(B_.Xn2, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), P + b.fc2_b, B_.Xm, d.D, Xnext,
-                 d.D, R, d.M, st, ln, front_done ? fr : mlp::FrontFuse());
+                 d.D, R, d.M, st, ln, front_done ? fr : mlp::FrontFuse(), w_f16(net, L, b.fc2_w));
       }
 #endif
     } else {
@@ -595,6 +607,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     if (side) { DG_CUDA(cudaEventRecord(sd->now, st)); DG_CUDA(cudaStreamWaitEvent(ss, sd->now, 0)); }
   };
   bool have_mr = false;
+  bool have_dw = false;      // the MLP weight-gradient launch of the current block has been recorded on the side stream
   launch_k(pool_rmsnorm_bwd_kernel, d.B, 128, 0, st, c.Xout, P + L.rms_g, c.dz, c.dXc, c.dXch, c.dg_rows, d.B, 1, d.D,
                                                 sqrtf((float)d.D));
   DG_LAUNCH_CHECK();
@@ -642,7 +655,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
         // net.3.bias gradient = colsum(dL/dX_out): below the top block it falls out of the next block's LayerNorm-1 backward
         mlp::bwd(B_.Xn2, dxop, WSel<A>::w(net, b.fc1_w), P + b.fc1_b, WSel<A>::w(net, b.fc2_w), c.dXn, G + b.fc1_w,
                  G + b.fc1_b, G + b.fc2_w, last ? G + b.fc2_b : nullptr, c.partial, R, d.M, st, &rl, ss);
-        if (side) DG_CUDA(cudaEventRecord(sd->dw, ss));
+        if (side) { DG_CUDA(cudaEventRecord(sd->dw, ss)); have_dw = true; }
       }
     }
 #else
@@ -682,12 +695,14 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
       // (the LayerNorm-1 backward below reads the compact residual gradient directly: zero off token 0)
     }
     if (!(last && launch_attention_row0<A>(B_.QKV, (A*)nullptr, (const A*)c.dO, c.dQKV, d, st)))
-      launch_attention_bwd<A>(B_.QKV, B_.O, c.dO, c.dQKV, d, st);
+      launch_attention_bwd<A>(B_.QKV, B_.O, c.dO, c.dQKV, d, st, B_.lse, c.attn_delta);
     side_after_main();
     linear_bwd_w<A, A>(c.dQKV, B_.Xn1, G + b.qkv_w, nullptr, d.T, 3 * d.inner, d.D, c.partial, ss, -1, -1, &rl);
     linear_bwd_x<A, A, float>(c.dQKV, WSel<A>::w(net, b.qkv_w), c.dXn, d.T, 3 * d.inner, d.D, EPI_NONE, nullptr, 0, st);
     // the MLP dW launch reads the incoming gradient copy that the next kernel overwrites
-    if (side) DG_CUDA(cudaStreamWaitEvent(st, sd->dw, 0));
+    // (only when this block's fused-MLP weight gradient really went to the side stream: waiting on an event this capture
+    // never recorded is an error under CUDA-graph capture)
+    if (side && have_dw) { DG_CUDA(cudaStreamWaitEvent(st, sd->dw, 0)); have_dw = false; }
     // c.dX becomes dL/dX_a = gradient of the previous block's output: its column sums are that block's net.3.bias gradient
     launch_ln_bwd(c.dXn, B_.Xa, B_.mean1, B_.rstd1, P + b.ln1_w, c.dX, c.dXh, G + b.ln1_w, G + b.ln1_b,
                   l > 0 ? G + L.block[l - 1].fc2_b : nullptr, c.partial, d.T, d.D, st, &rl, last ? c.dXc : nullptr, d.N);
@@ -935,10 +950,10 @@ static void adam_step(const dgvit_net& net, const dgvit_layout& L, const dgvit_a
   {  // algorithmic bytes: theta, m, v read + written, g read, bf16 shadow written (+ target read / written + its shadow)
     int64_t used = L.total;
     for (int k = 0; k < L.n_skip; ++k) used -= L.skip_end[k] - L.skip_begin[k];
-    const double per = 28.0 + (a.shadow ? 2.0 : 0.0);
-    const double tgt_b = a.tgt ? (double)L.total * (12.0 + (a.tgt_shadow ? 2.0 : 0.0)) : 0.0;
+    const double per = 28.0 + (a.shadow ? 4.0 : 0.0);
+    const double tgt_b = a.tgt ? (double)L.total * (12.0 + (a.tgt_shadow ? 4.0 : 0.0)) : 0.0;
     ProfScope ps(PROF_ADAM, 0.0, used * per + tgt_b, st);
-    launch_k(adam_polyak_kernel, 148 * 4, 256, 0, st, a);
+    launch_k(adam_polyak_kernel, 148 * 8, 256, 0, st, a);
     DG_LAUNCH_CHECK();
   }
 }
@@ -1225,8 +1240,10 @@ int dgvit_set_option(const char* name, int value) {
     else if (!strcmp(name, "tensor_cores")) tc::g_tc_enabled = value != 0;
     else if (!strcmp(name, "debug_epilogue")) tc::g_debug = value;
     else if (!strcmp(name, "attn_bwd2")) attn::g_bwd2_enabled = value != 0;
+    else if (!strcmp(name, "attn_long")) attnl::g_enabled = value != 0;
     else if (!strcmp(name, "mlp_split")) mlp::g_split_enabled = value != 0;
     else if (!strcmp(name, "mlp_front")) mlp::g_front_enabled = value != 0;
+    else if (!strcmp(name, "mlp_h16")) mlp::g_h16_enabled = value != 0;
 #endif
     else fail(DGVIT_ERR_ARG, "unknown option %s", name);
   });
@@ -1579,8 +1596,25 @@ int dgvit_mlp_bf16(const void* x, const void* W1, const float* b1, const void* W
   });
 }
 
+int dgvit_mlp_fwd_f16w2(const void* x, const void* W1, const float* b1, const void* W2_f16, const float* b2, const float* resid,
+                        float* out, int64_t rows, int hid, void* stream) {
+  return guarded([&] {
+    DeviceGuard dev_guard(x);
+#ifdef DGVIT_WITH_TC
+    DG_REQUIRE(x && W1 && b1 && W2_f16 && b2 && resid && out && rows > 0 && hid > 0, "bad argument");
+    DG_REQUIRE(mlp::eligible(64, hid, rows, x, W1, W2_f16, resid, 64, out, 64), "mlp: shape not eligible for the fused kernel");
+    mlp::fwd((const bf16*)x, (const bf16*)W1, b1, nullptr, b2, resid, 64, out, 64, rows, hid, (cudaStream_t)stream, mlp::LnFuse(),
+             mlp::FrontFuse(), W2_f16);
+#else
+    fail(DGVIT_ERR_ARG, "built without the tensor-core kernels");
+#endif
+  });
+}
+
+int64_t dgvit_attention_stats_floats(int B, int N, int H) { return N > 128 ? (int64_t)2 * B * H * N : 0; }
+
 int dgvit_attention_bf16(const void* qkv, void* o, const void* d_o, void* d_qkv, int B, int N, int H, int dim_head,
-                         int use_tensor_cores, void* stream) {
+                         int use_tensor_cores, float* stats, void* stream) {
   return guarded([&] {
     DeviceGuard dev_guard(qkv);
     DG_REQUIRE(qkv && o && B >= 1 && N >= 1 && H >= 1, "bad argument");
@@ -1594,15 +1628,19 @@ int dgvit_attention_bf16(const void* qkv, void* o, const void* d_o, void* d_qkv,
 #ifdef DGVIT_WITH_TC
     const bool prev = tc::g_tc_enabled;
     tc::g_tc_enabled = use_tensor_cores != 0;
-    if (use_tensor_cores) DG_REQUIRE(attn::eligible(N, dim_head, qkv, 3 * d.inner), "attention: shape not eligible for the tensor-core kernel");
+    if (use_tensor_cores)
+      DG_REQUIRE(attn::eligible(N, dim_head, qkv, 3 * d.inner) || (stats && attnl::eligible(N, dim_head, qkv, 3 * d.inner)),
+                 "attention: shape not eligible for the tensor-core kernels (N > 128 needs the stats scratch)");
+    float* lse = stats;
+    float* delta = stats ? stats + (int64_t)B * H * N : nullptr;
 #else
     DG_REQUIRE(!use_tensor_cores, "built without the tensor-core kernels");
 #endif
     try {
-      if (!d_o) launch_attention_fwd<bf16>((const bf16*)qkv, (bf16*)o, d, st);
+      if (!d_o) launch_attention_fwd<bf16>((const bf16*)qkv, (bf16*)o, d, st, lse);
       else {
         DG_REQUIRE(d_qkv, "null d_qkv");
-        launch_attention_bwd<bf16>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, (bf16*)d_qkv, d, st);
+        launch_attention_bwd<bf16>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, (bf16*)d_qkv, d, st, lse, delta);
       }
     } catch (...) {
 #ifdef DGVIT_WITH_TC

@@ -2,6 +2,8 @@
 // RMSNorm pooling, tanh-Gaussian head, SAC losses, Adam/Polyak, replay gather).
 // Reference lines are cited per kernel; "vn/" = src/vis_nav/vis_nav/.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace dgvit {
@@ -1008,7 +1010,18 @@ __global__ void step_bump_kernel(int64_t* step) {
   pdl_wait();
   pdl_launch(); if (threadIdx.x == 0 && blockIdx.x == 0) ++(*step); }
 
-__global__ void adam_polyak_kernel(AdamArgs a) {
+// 16-bit shadows of a parameter arena: bf16 copy at shadow[0, n), f16 copy at shadow[n, 2n) (operands of the tensor-core
+// contractions; the f16 copy feeds the f16 x f16 second GEMM of the fused MLP forward).  Four elements per thread.
+__device__ __forceinline__ void store_shadows4(bf16* shadow, int64_t n, int64_t i, const float4& p) {
+  const __nv_bfloat162 b0 = __floats2bfloat162_rn(p.x, p.y), b1 = __floats2bfloat162_rn(p.z, p.w);
+  const __half2 h0 = __floats2half2_rn(p.x, p.y), h1 = __floats2half2_rn(p.z, p.w);
+  *reinterpret_cast<uint2*>(shadow + i) = make_uint2(*reinterpret_cast<const uint32_t*>(&b0), *reinterpret_cast<const uint32_t*>(&b1));
+  *reinterpret_cast<uint2*>(shadow + n + i) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+}
+
+// n is a multiple of 64 and every skip range starts / ends on a 64-float boundary (dgvit_param_layout), so a float4
+// never straddles a range
+__global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant__ AdamArgs a) {
   pdl_wait();
   pdl_launch();
   __shared__ float sh[2];
@@ -1021,47 +1034,66 @@ __global__ void adam_polyak_kernel(AdamArgs a) {
   }
   __syncthreads();
   const float step_size = sh[0], bc2s = sh[1];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t n4 = a.n >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q << 2;
     bool skip = false;
     for (int k = 0; k < a.n_skip; ++k) skip |= (i >= a.skip_b[k] && i < a.skip_e[k]);
-    float p = a.p[i];
+    float4 p = *reinterpret_cast<const float4*>(a.p + i);
     if (!skip) {
-      const float g = a.g[i];
-      float m = a.m[i], v = a.v[i];
-      m = m + a.omb1 * (g - m);                        // exp_avg.lerp_(grad, 1-beta1)
-      v = v * a.b2 + a.omb2 * g * g;                   // mul_(beta2).addcmul_(g,g,1-beta2)
-      const float denom = sqrtf(v) / bc2s + a.eps;
-      p = p - step_size * (m / denom);
-      a.m[i] = m; a.v[i] = v; a.p[i] = p;
+      const float4 g = *reinterpret_cast<const float4*>(a.g + i);
+      float4 m = *reinterpret_cast<const float4*>(a.m + i), v = *reinterpret_cast<const float4*>(a.v + i);
+#define DG_ADAM1(C_)                                                                                     \
+      m.C_ = m.C_ + a.omb1 * (g.C_ - m.C_);              /* exp_avg.lerp_(grad, 1-beta1) */                 \
+      v.C_ = v.C_ * a.b2 + a.omb2 * g.C_ * g.C_;         /* mul_(beta2).addcmul_(g,g,1-beta2) */            \
+      p.C_ = p.C_ - step_size * (m.C_ / (sqrtf(v.C_) / bc2s + a.eps));
+      DG_ADAM1(x) DG_ADAM1(y) DG_ADAM1(z) DG_ADAM1(w)
+#undef DG_ADAM1
+      *reinterpret_cast<float4*>(a.m + i) = m;
+      *reinterpret_cast<float4*>(a.v + i) = v;
+      *reinterpret_cast<float4*>(a.p + i) = p;
     }
-    if (a.shadow) a.shadow[i] = __float2bfloat16_rn(p);
+    if (a.shadow) store_shadows4(a.shadow, a.n, i, p);
     if (a.tgt) {
-      const float t = a.tgt[i] * (1.0f - a.tau) + p * a.tau;
-      a.tgt[i] = t;
-      if (a.tgt_shadow) a.tgt_shadow[i] = __float2bfloat16_rn(t);
+      float4 t = *reinterpret_cast<const float4*>(a.tgt + i);
+      t.x = t.x * (1.0f - a.tau) + p.x * a.tau; t.y = t.y * (1.0f - a.tau) + p.y * a.tau;
+      t.z = t.z * (1.0f - a.tau) + p.z * a.tau; t.w = t.w * (1.0f - a.tau) + p.w * a.tau;
+      *reinterpret_cast<float4*>(a.tgt + i) = t;
+      if (a.tgt_shadow) store_shadows4(a.tgt_shadow, a.n, i, t);
     }
   }
 }
 
-__global__ void polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, bf16* tgt_shadow,
-                              float tau, int64_t n) {
+__global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, bf16* tgt_shadow,
+                                                     float tau, int64_t n) {
   pdl_wait();
   pdl_launch();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const float t = (tau == 1.0f) ? src[i] : tgt[i] * (1.0f - tau) + src[i] * tau;
+  const int64_t n4 = n >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q << 2;
+    const float4 sv = *reinterpret_cast<const float4*>(src + i);
+    float4 t = sv;
+    if (tau != 1.0f) {
+      const float4 tv = *reinterpret_cast<const float4*>(tgt + i);
+      t.x = tv.x * (1.0f - tau) + sv.x * tau; t.y = tv.y * (1.0f - tau) + sv.y * tau;
+      t.z = tv.z * (1.0f - tau) + sv.z * tau; t.w = tv.w * (1.0f - tau) + sv.w * tau;
+    }
+    *reinterpret_cast<float4*>(tgt + i) = t;
+    if (tgt_shadow) store_shadows4(tgt_shadow, n, i, t);
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float t = (tau == 1.0f) ? src[i] : tgt[i] * (1.0f - tau) + src[i] * tau;      // tail (flat arenas of any length)
     tgt[i] = t;
-    if (tgt_shadow) tgt_shadow[i] = __float2bfloat16_rn(t);
+    if (tgt_shadow) { tgt_shadow[i] = __float2bfloat16_rn(t); reinterpret_cast<__half*>(tgt_shadow)[n + i] = __float2half_rn(t); }
   }
 }
 
-__global__ void shadow_refresh_kernel(const float* __restrict__ p, bf16* __restrict__ s, int64_t n) {
+__global__ void __launch_bounds__(256) shadow_refresh_kernel(const float* __restrict__ p, bf16* __restrict__ s, int64_t n) {
   pdl_wait();
   pdl_launch();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x)
-    s[i] = __float2bfloat16_rn(p[i]);
+  const int64_t n4 = n >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x)
+    store_shadows4(s, n, q << 2, *reinterpret_cast<const float4*>(p + (q << 2)));
 }
 
 __global__ void rng_advance_kernel(uint64_t* rng) {

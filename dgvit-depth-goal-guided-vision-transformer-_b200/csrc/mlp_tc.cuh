@@ -78,6 +78,14 @@ __device__ __forceinline__ __half2 gelu_h2(__half2 x) {
   const __half2 hx = __hmul2(x, hf);
   return __hfma2(hx, t, hx);
 }
+// the same function of xh = x / 2 (the forward epilogue forms xh = 0.5 acc + 0.5 b1 with ONE HFMA2, which also replaces
+// the separate 0.5 x product): gelu(x) = xh + xh tanh(xh (2a + 8b xh^2))  — 4 FMA-pipe instructions + 1 MUFU per pair
+__device__ __forceinline__ __half2 gelu_half_h2(__half2 xh) {
+  const __half2 A2 = __float2half2_rn(2.0f * GELU_A), B8 = __float2half2_rn(8.0f * GELU_B);
+  const __half2 s = __hmul2(xh, xh);
+  const __half2 t = h2_tanh(__hmul2(xh, __hfma2(s, B8, A2)));
+  return __hfma2(xh, t, xh);
+}
 // g = gelu(x), d = d gelu / dx of the same approximant
 __device__ __forceinline__ void gelu_grad_h2(__half2 x, __half2& g, __half2& d) {
   const __half2 A = __float2half2_rn(GELU_A), B = __float2half2_rn(GELU_B), hf = __float2half2_rn(0.5f);
@@ -114,9 +122,9 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 
 // fp32 bias -> f16 copy in shared memory (epilogue threads only), then a barrier among them
 template <int NWARPS = EPI_WARPS>
-__device__ __forceinline__ void stage_bias(const float* b, __half* dst, int n, int tid) {
+__device__ __forceinline__ void stage_bias(const float* b, __half* dst, int n, int tid, float scale = 1.0f) {
   for (int i = tid * 2; i < n; i += NWARPS * 32 * 2)
-    *reinterpret_cast<__half2*>(dst + i) = __floats2half2_rn(__ldg(b + i), __ldg(b + i + 1));
+    *reinterpret_cast<__half2*>(dst + i) = __floats2half2_rn(scale * __ldg(b + i), scale * __ldg(b + i + 1));
   epi_bar_sync<NWARPS>();
 }
 
@@ -198,7 +206,10 @@ struct MlpArgs {
 // SPLIT: few token tiles (the pruned last block, batch-1 act): a cluster of NSPLIT CTAs shares one tile, each taking
 // HID / NSPLIT hidden columns; the partial outputs meet in CTA 0 of the cluster through distributed shared memory.
 // FRONT: see MlpArgs.  tmX then maps the attention output o ([M rows, 256] bf16) and tmWo the out-projection weight.
-template <bool SPLIT, bool FRONT>
+// H16: the hidden activation tile and W2 are f16 (tmW2 maps the f16 copy of net.3.weight): the GELU result leaves the
+// epilogue as it is computed (f16x2) instead of being re-packed to bf16 (2 cvt + 1 F2FP per pair); kind::f16 takes either
+// format but not a mix, so GEMM2 runs f16 x f16 while GEMM1 and the prologue stay bf16 x bf16.
+template <bool SPLIT, bool FRONT, bool H16>
 __global__ void __launch_bounds__(f::FWD_THREADS, 1)
 mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmWo, const MlpArgs a) {
@@ -279,7 +290,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   } else if (warp == 1) {
     if (elect_one_sync()) {
       constexpr uint32_t idesc1 = make_idesc(128, HC, false, false);
-      constexpr uint32_t idesc2 = make_idesc(128, 64, false, false);
+      constexpr uint32_t idesc_front = make_idesc(128, 64, false, false);
+      constexpr uint32_t idesc2 = make_idesc_fmt(128, 64, false, false, H16 ? 0u : 1u, H16 ? 0u : 1u);
       const uint32_t sx = smem_u32(smem);
       auto gemm1 = [&](int c) {
         const int s = c % NST; const uint32_t ph = (c / NST) & 1;
@@ -302,7 +314,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int k = 0; k < 16; ++k) {
           const uint64_t od = make_smem_desc(sx + OFF_H + (k >> 2) * TILE16 + (k & 3) * 32, 16, 1024);
           const uint64_t wd = make_smem_desc(sx + OFF_WO + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024);
-          umma_bf16(tmem_base + T_Y, od, wd, idesc2, k > 0);
+          umma_bf16(tmem_base + T_Y, od, wd, idesc_front, k > 0);
         }
         umma_commit(front_done);
         mbar_wait(x_ready, 0);
@@ -345,7 +357,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int r = quad * 32 + lane;
     const int row0 = mt * 128 + quad * 32;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    stage_bias<FWD_EPI_WARPS>(a.b1, bias_s, a.HID, threadIdx.x - 64);
+    stage_bias<FWD_EPI_WARPS>(a.b1, bias_s, a.HID, threadIdx.x - 64, 0.5f);      // 0.5 b1: see gelu_half_h2
     if (warp == 2) MLP_TRACE(12, 3);
     if (FRONT) {
       static_assert(!FRONT || FWD_EPI_WARPS == 16, "front epilogue: 4 lane quadrants x 4 column groups");
@@ -440,9 +452,10 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           uint32_t ow[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            __half2 x = __floats2half2_rn(__uint_as_float(v[8 * i + 2 * j]), __uint_as_float(v[8 * i + 2 * j + 1]));
-            x = __hadd2(x, *reinterpret_cast<const __half2*>(&bw[j]));
-            ow[j] = h2_to_bf2_bits(gelu_h2(x));
+            const __half2 acc = __floats2half2_rn(__uint_as_float(v[8 * i + 2 * j]), __uint_as_float(v[8 * i + 2 * j + 1]));
+            const __half2 xh = __hfma2(acc, __float2half2_rn(0.5f), *reinterpret_cast<const __half2*>(&bw[j]));
+            const __half2 g = gelu_half_h2(xh);
+            ow[j] = H16 ? *reinterpret_cast<const uint32_t*>(&g) : h2_to_bf2_bits(g);
           }
           *reinterpret_cast<uint4*>(hb + sw128_off(r, hh * 4 + i)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
@@ -901,9 +914,13 @@ static bool front_eligible(int inner, const FrontFuse& fr) {
          ((((uintptr_t)fr.o) | ((uintptr_t)fr.Wo) | ((uintptr_t)fr.xa) | ((uintptr_t)fr.xm) | ((uintptr_t)fr.xn2)) & 15) == 0 &&
          fr.ldo % 8 == 0 && fr.ldxa % 4 == 0;
 }
+// W2h: f16 copy of W2 (null = bf16 W2 and a bf16 hidden tile)
+static bool g_h16_enabled = true;       // set_option "mlp_h16"
 static void fwd(const bf16* x, const bf16* W1, const float* b1, const bf16* W2, const float* b2, const float* resid,
                 int64_t ldr, float* out, int64_t ldc, int64_t M, int HID, cudaStream_t st, const LnFuse& ln = LnFuse(),
-                const FrontFuse& fr = FrontFuse()) {
+                const FrontFuse& fr = FrontFuse(), const void* W2h = nullptr) {
+  if (!g_h16_enabled || ((uintptr_t)W2h & 15)) W2h = nullptr;
+  const bool h16 = W2h != nullptr;
   MlpArgs a;
   memset(&a, 0, sizeof(a));
   a.trace = g_trace;
@@ -915,14 +932,16 @@ static void fwd(const bf16* x, const bf16* W1, const float* b1, const bf16* W2, 
   a.xn2 = fr.xn2; a.mean2 = fr.mean; a.rstd2 = fr.rstd;
   CUtensorMap tx = front ? make_map(fr.o, 256, M, fr.ldo, 64, 128) : make_map(x, 64, M, 64, 64, 128);
   CUtensorMap tw1 = make_map(W1, 64, HID, 64, 64, 128);
-  CUtensorMap tw2 = make_map(W2, HID, 64, HID, 64, 64);
+  CUtensorMap tw2 = make_map(h16 ? W2h : (const void*)W2, HID, 64, HID, 64, 64);      // (16-bit elements either way)
   CUtensorMap two = front ? make_map(fr.Wo, 256, 64, 256, 64, 64) : tw1;
   static DevOnce attr;
   if (attr.first()) {
-    DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
-    DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL));
-    DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL_FRONT));
-    DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, f::SMEM_TOTAL_FRONT));
+#define DG_MLP_ATTR(S_, F_, H_, B_) DG_CUDA(cudaFuncSetAttribute((mlp_fwd_tc_kernel<S_, F_, H_>), cudaFuncAttributeMaxDynamicSharedMemorySize, B_))
+    DG_MLP_ATTR(false, false, false, f::SMEM_TOTAL); DG_MLP_ATTR(true, false, false, f::SMEM_TOTAL);
+    DG_MLP_ATTR(false, true, false, f::SMEM_TOTAL_FRONT); DG_MLP_ATTR(true, true, false, f::SMEM_TOTAL_FRONT);
+    DG_MLP_ATTR(false, false, true, f::SMEM_TOTAL); DG_MLP_ATTR(true, false, true, f::SMEM_TOTAL);
+    DG_MLP_ATTR(false, true, true, f::SMEM_TOTAL_FRONT); DG_MLP_ATTR(true, true, true, f::SMEM_TOTAL_FRONT);
+#undef DG_MLP_ATTR
   }
   if (skip_mask() & SKIP_MLP_FWD) return;
   const int grid = (int)cdiv(M, 128);
@@ -930,13 +949,19 @@ static void fwd(const bf16* x, const bf16* W1, const float* b1, const bf16* W2, 
   // shares each tile's hidden columns
   const bool split = g_split_enabled && grid * f::NSPLIT <= sm_count() && (HID / HC) % f::NSPLIT == 0 && (HID / HC) / f::NSPLIT >= 1;
   const int smem = front ? f::SMEM_TOTAL_FRONT : f::SMEM_TOTAL;
+#define DG_MLP_GO(S_, F_, H_)                                                                                              \
+  do {                                                                                                                     \
+    if (S_) launch_k_cluster((mlp_fwd_tc_kernel<S_, F_, H_>), grid * f::NSPLIT, f::FWD_THREADS, smem, st, f::NSPLIT, tx, tw1, tw2, two, a); \
+    else launch_k((mlp_fwd_tc_kernel<S_, F_, H_>), grid, f::FWD_THREADS, smem, st, tx, tw1, tw2, two, a);                    \
+  } while (0)
   if (split) {
-    if (front) launch_k_cluster((mlp_fwd_tc_kernel<true, true>), grid * f::NSPLIT, f::FWD_THREADS, smem, st, f::NSPLIT, tx, tw1, tw2, two, a);
-    else launch_k_cluster((mlp_fwd_tc_kernel<true, false>), grid * f::NSPLIT, f::FWD_THREADS, smem, st, f::NSPLIT, tx, tw1, tw2, two, a);
+    if (front) { if (h16) DG_MLP_GO(true, true, true); else DG_MLP_GO(true, true, false); }
+    else { if (h16) DG_MLP_GO(true, false, true); else DG_MLP_GO(true, false, false); }
   } else {
-    if (front) launch_k((mlp_fwd_tc_kernel<false, true>), grid, f::FWD_THREADS, smem, st, tx, tw1, tw2, two, a);
-    else launch_k((mlp_fwd_tc_kernel<false, false>), grid, f::FWD_THREADS, smem, st, tx, tw1, tw2, two, a);
+    if (front) { if (h16) DG_MLP_GO(false, true, true); else DG_MLP_GO(false, true, false); }
+    else { if (h16) DG_MLP_GO(false, false, true); else DG_MLP_GO(false, false, false); }
   }
+#undef DG_MLP_GO
   DG_LAUNCH_CHECK();
 }
 

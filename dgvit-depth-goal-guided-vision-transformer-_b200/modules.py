@@ -258,7 +258,7 @@ class _ArenaModule(nn.Module):
         self._arena = arena
         self._bind_probe = None
         self._garena = torch.zeros_like(arena)
-        self._shadow = torch.zeros(lay.total, dtype=torch.bfloat16, device=dev)
+        self._shadow = torch.zeros(2 * lay.total, dtype=torch.bfloat16, device=dev)    # bf16 copy | f16 copy (bits)
         self._ws_cache = {}
         self._rng_state = None
         self._act_state = None

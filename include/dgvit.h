@@ -86,7 +86,9 @@ typedef struct dgvit_net {
   dgvit_cfg cfg;
   float* params;    /* fp32 master parameters */
   float* grads;     /* fp32 gradients (written, not accumulated, by *_backward) */
-  uint16_t* shadow; /* bf16 copy of params for DGVIT_BF16 (may be NULL for DGVIT_FP32) */
+  uint16_t* shadow; /* 16-bit operand copies of params for DGVIT_BF16, 2 * layout.total elements: bf16 copy in
+                       [0, total), f16 copy in [total, 2 total) (the f16 x f16 second GEMM of the fused MLP forward reads
+                       net.3.weight from it); may be NULL for DGVIT_FP32 */
 } dgvit_net;
 
 /* Stochastic inputs of one trunk call (vn/GoalFormer.py:163, emb dropout p=0.1). */
@@ -202,6 +204,8 @@ long long dgvit_launch_count(void);
  *   "actor_s_when"   0/1/2: policy.sample(s) forward starts at the fork / after the policy.sample(s') forward / after
  *                    the target-critic forward
  *   "tensor_cores"   0: route the bf16 contractions to the CUDA-core kernels
+ *   "mlp_h16"        0: bf16 hidden tile and bf16 W2 in the fused MLP forward (1: f16 tile + f16 copy of W2)
+ *   "attn_long"      0: sequences of more than 128 tokens go to the CUDA-core attention kernels
  *   "mlp_split", "mlp_front", "attention_row0", "attn_bwd2": kernel variants of the pruned last block / fused prologue /
  *                    pipelined attention backward (0 = the plain kernels)
  *   "ln_bwd_warps", "ln_bwd_blocks_per_sm": LayerNorm-backward block shape; "pdl": programmatic dependent launch;
@@ -219,7 +223,7 @@ int dgvit_workspace_bytes(const dgvit_cfg* cfg, int B, int precision, int save_f
 /* bytes of workspace dgvit_sac_* needs for a local batch of B */
 int dgvit_sac_workspace_bytes(const dgvit_cfg* actor_cfg, int B, int n_extra, int precision, size_t* bytes);
 
-/* refresh the bf16 shadow of a parameter arena (after load_state_dict etc.) */
+/* refresh both 16-bit shadows of a parameter arena (after load_state_dict etc.) */
 int dgvit_refresh_shadow(const dgvit_net* net, void* stream);
 
 /* GoTPolicy.forward/.sample — vn/got_sac_network.py:221-251 */
@@ -296,9 +300,12 @@ int dgvit_linear_bf16(const void* x, const void* W, void* y, int64_t rows, int N
 
 /* Attention.forward core (vn/GoalFormer.py:75-81) on bf16 QKV [B*N, 3*H*dim_head] (column =
  * which*inner + h*dim_head + d): forward when d_o == NULL (writes o [B*N, inner]), else backward
- * (reads o, d_o; writes d_qkv).  use_tensor_cores=1 -> tcgen05/TMEM kernel, 0 -> CUDA-core kernel. */
+ * (reads o, d_o; writes d_qkv).  use_tensor_cores=1 -> tcgen05/TMEM kernels, 0 -> CUDA-core kernel.
+ * stats: scratch of dgvit_attention_stats_floats(B, N, H) floats that the forward fills (softmax log-sum-exp) and the
+ * backward of the same inputs reads; needed for N > 128 (the key-chunked kernels), may be NULL otherwise. */
+int64_t dgvit_attention_stats_floats(int B, int N, int H);
 int dgvit_attention_bf16(const void* qkv, void* o, const void* d_o, void* d_qkv, int B, int N, int H,
-                         int dim_head, int use_tensor_cores, void* stream);
+                         int dim_head, int use_tensor_cores, float* stats, void* stream);
 
 /* FeedForward.forward + residual (vn/GoalFormer.py:39-50,104) on bf16 operands, fused tcgen05 kernels, D = 64:
  * forward  (d_y == NULL): out[rows,64] (fp32) = resid + W2 gelu(W1 x + b1) + b2, x [rows,64] bf16 (the LayerNorm output),
@@ -310,6 +317,9 @@ int dgvit_mlp_bf16(const void* x, const void* W1, const float* b1, const void* W
                    const float* resid, float* out, const void* d_y, float* d_x, float* d_w, float* d_b2,
                    float* partial, int64_t rows, int hid, void* stream);
 int64_t dgvit_mlp_partial_floats(int64_t rows, int hid);
+/* the forward as the update runs it: f16 hidden tile and an f16 copy of W2 (W2_f16 [64,hid]), W1 / x bf16 */
+int dgvit_mlp_fwd_f16w2(const void* x, const void* W1, const float* b1, const void* W2_f16, const float* b2,
+                        const float* resid, float* out, int64_t rows, int hid, void* stream);
 
 /* ---- CNN twin-Q critic `QNetwork` (vn/got_sac_network.py:125-170; the reference's shipped default critic_type,
  * vn/config.yaml:61, vn/DRL.py:118-121).  Parameters live in one flat fp32 arena in the reference's registration

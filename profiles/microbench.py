@@ -47,9 +47,9 @@ def attention(bwd):
     do = torch.randn(T, H * 64, device=dev).bfloat16()
     dq = torch.empty_like(qkv)
     def f():
-        L.check(lib.dgvit_attention_bf16(qkv.data_ptr(), o.data_ptr(), None, None, B, 65, H, 64, 1, st))
+        L.check(lib.dgvit_attention_bf16(qkv.data_ptr(), o.data_ptr(), None, None, B, 65, H, 64, 1, None, st))
     def b():
-        L.check(lib.dgvit_attention_bf16(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), dq.data_ptr(), B, 65, H, 64, 1, st))
+        L.check(lib.dgvit_attention_bf16(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), dq.data_ptr(), B, 65, H, 64, 1, None, st))
     f()
     return timeit(b if bwd else f)
 

@@ -43,8 +43,13 @@ def run(rows, hid=2048):
     def b():
         L.check(lib.dgvit_mlp_bf16(x.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), None, None, None, dy.data_ptr(),
                                    dx.data_ptr(), dw.data_ptr(), db2.data_ptr(), part.data_ptr(), rows, hid, st))
-    tf, tb = timeit(f), timeit(b)
+    W2h = W2.float().half()
+    def f16():
+        L.check(lib.dgvit_mlp_fwd_f16w2(x.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2h.data_ptr(), b2.data_ptr(), resid.data_ptr(),
+                                        out.data_ptr(), rows, hid, st))
+    tf, tb, tf16 = timeit(f), timeit(b), timeit(f16)
     fl = 4.0 * rows * 64 * hid
+    print(f"rows={rows:6d} hid={hid}: fwd (f16 hidden tile) {tf16:7.1f} us ({fl / tf16 / 1e6:6.1f} TFLOP/s)")
     print(f"rows={rows:6d} hid={hid}: fwd {tf:7.1f} us ({fl / tf / 1e6:6.1f} TFLOP/s)   bwd (dX + dW + 2 reduces) {tb:7.1f} us "
           f"({2 * fl / tb / 1e6:6.1f} TFLOP/s algorithmic)")
 

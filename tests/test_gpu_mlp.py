@@ -42,6 +42,13 @@ def test_fused_mlp_forward_backward(rows, hid):
     torch.cuda.synchronize()
     y_ref = out_ref - resid
     assert float(((out - resid) - y_ref).abs().max() / y_ref.abs().max()) < 1e-2
+    # the variant the update runs: f16 hidden tile x f16 copy of W2 (the f16 copy of a bf16 value is exact here: same W2)
+    out16 = torch.full((rows, 64), float("nan"), device="cuda")
+    W2h = W2.float().half()
+    L.check(L.lib().dgvit_mlp_fwd_f16w2(x.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2h.data_ptr(), b2.data_ptr(),
+                                        resid.data_ptr(), out16.data_ptr(), rows, hid, st), "mlp fwd f16w2")
+    torch.cuda.synchronize()
+    assert float(((out16 - resid) - y_ref).abs().max() / y_ref.abs().max()) < 1e-2
     n = L.lib().dgvit_mlp_partial_floats(rows, hid)
     assert n > 0
     partial = torch.empty(n, device="cuda")
