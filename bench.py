@@ -213,7 +213,19 @@ def run_ours(args):
         # NCCL writes its banner ("NCCL version ...") to stdout at NCCL_DEBUG=VERSION: stdout carries the JSON line only
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # ... and whatever NCCL still prints while the communicator comes up goes to stderr (fd-level: it is C code)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B = args.batch
     pk = peaks()
 
@@ -248,8 +260,12 @@ def run_ours(args):
     sustained = None
     if not args.no_sustained:
         blocks = []
-        t_end = time.perf_counter() + args.sustained_seconds
-        while time.perf_counter() < t_end or len(blocks) < 3:
+        # every rank runs the SAME number of blocks (the steps hold collectives): derived from the max-over-ranks time above
+        tm = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        nblocks = max(3, int(args.sustained_seconds * 1e3 / max(float(tm.item()), 1e-3)) + 1)
+        for _ in range(nblocks):
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
             for _ in range(args.steps):
