@@ -81,13 +81,19 @@ class Adam(C.Structure):
                 ("beta2", C.c_float), ("eps", C.c_float)]
 
 
+class Dp(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("multicast", c_f_p), ("peers", c_f_p), ("pads", c_f_p),
+                ("arena_off", C.c_int64 * 2), ("tail", c_f_p), ("reduced_out", c_f_p * 2), ("finished", c_f_p),
+                ("error_flag", c_f_p)]
+
+
 class Sac(C.Structure):
     _fields_ = [("actor", Net), ("critic", Net), ("critic_target", Net), ("actor_opt", Adam), ("critic_opt", Adam),
                 ("log_alpha", c_f_p), ("alpha", c_f_p), ("alpha_m", c_f_p), ("alpha_v", c_f_p), ("alpha_step", c_f_p),
                 ("lr_alpha", C.c_float), ("auto_alpha", C.c_int32), ("target_entropy", C.c_float),
                 ("gamma", C.c_float), ("tau", C.c_float), ("do_polyak", C.c_int32), ("precision", C.c_int32),
                 ("global_batch", C.c_int32), ("n_extra", C.c_int32), ("sample_offset", C.c_int32), ("rng_state", c_f_p),
-                ("action_scale", c_f_p), ("action_bias", c_f_p)]
+                ("action_scale", c_f_p), ("action_bias", c_f_p), ("dp", C.POINTER(Dp))]
 
 
 class Batch(C.Structure):

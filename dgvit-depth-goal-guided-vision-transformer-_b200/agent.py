@@ -253,6 +253,9 @@ class SAC(object):
             self._opt[name] = dict(m=torch.zeros(n, **f32), v=torch.zeros(n, **f32),
                                    step=torch.zeros(1, dtype=torch.int64, device=dev))
         self._rng = torch.tensor([self.seed, 0], dtype=torch.int64, device=dev)
+        self._dp = None
+        if self.distributed and self.world > 1 and os.environ.get("DGVIT_DP_FUSED", "1") == "1":
+            self._setup_fused_dp(keep_reduced=os.environ.get("DGVIT_DP_KEEP_REDUCED", "0") == "1")
         na = action_dim
         self._scale = self.policy.action_scale.to(dev, torch.float32).expand(na).contiguous()
         self._bias = self.policy.action_bias.to(dev, torch.float32).expand(na).contiguous()
@@ -339,6 +342,57 @@ class SAC(object):
         self.itera += 1
         return qf1_loss.detach(), policy_loss.detach()
 
+    # ------------------------------------------------------------------ data parallel without NCCL calls
+    def _setup_fused_dp(self, keep_reduced: bool = False):
+        """Both gradient arenas move into one symmetric-memory buffer ([critic | actor]); the Adam kernels then read the
+        rank-sum of the gradients themselves (NVLS multimem.ld_reduce, or peer loads) behind a flag barrier: the whole
+        data-parallel update is one C call / one CUDA graph (include/dgvit.h: dgvit_dp).  Falls back to the NCCL path
+        (all-reduce between the phases) when symmetric memory is not available."""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            dev = self.device
+            Lc, La = int(self.critic.layout().total), int(self.policy.layout().total)
+            buf = symm.empty(Lc + La, dtype=torch.float32, device=dev)
+            hdl = symm.rendezvous(buf, torch.distributed.group.WORLD.group_name)
+            buf.zero_()
+            mc = 0
+            try:
+                mc = int(hdl.multicast_ptr or 0)
+            except Exception:
+                mc = 0
+            if os.environ.get("DGVIT_DP_MULTICAST", "1") != "1":
+                mc = 0
+            i32 = dict(dtype=torch.int32, device=dev)
+            st = dict(buf=buf, hdl=hdl, Lc=Lc, La=La, tail=torch.zeros(64, device=dev), finished=torch.zeros(2, **i32),
+                      err=torch.zeros(1, **i32), multicast=mc,
+                      reduced=[torch.zeros(Lc, device=dev), torch.zeros(La, device=dev)] if keep_reduced else None)
+            st["struct"] = L.Dp(world=hdl.world_size, rank=hdl.rank, multicast=mc or None, peers=int(hdl.buffer_ptrs_dev),
+                                pads=int(hdl.signal_pad_ptrs_dev), arena_off=(C.c_int64 * 2)(0, Lc), tail=st["tail"].data_ptr(),
+                                reduced_out=(L.c_f_p * 2)(*( [t.data_ptr() for t in st["reduced"]] if keep_reduced else [None, None])),
+                                finished=st["finished"].data_ptr(), error_flag=st["err"].data_ptr())
+            torch.distributed.barrier()
+            self._dp = st
+            self._point_grads_at_symmetric_buffer()
+        except Exception as e:       # no symmetric memory on this system: NCCL all-reduce between the phases
+            import sys
+            print(f"dgvit_b200: fused data-parallel optimizer unavailable ({e!r}); using NCCL all-reduce", file=sys.stderr)
+            self._dp = None
+
+    def _point_grads_at_symmetric_buffer(self):
+        st = self._dp
+        for mod, a, b in ((self.critic, 0, st["Lc"]), (self.policy, st["Lc"], st["Lc"] + st["La"])):
+            mod.bind()
+            if mod._garena.data_ptr() != st["buf"].data_ptr() + 4 * a:
+                mod._garena = st["buf"][a:b]
+
+    def reduced_gradients(self):
+        """(critic, actor) gradient arenas summed over the ranks as the last update saw them."""
+        if self._dp is not None:
+            if self._dp["reduced"] is None:
+                raise RuntimeError("construct the fused data-parallel state with keep_reduced=True to read reduced gradients")
+            return self._dp["reduced"][0], self._dp["reduced"][1]
+        return self.critic._garena, self.policy._garena
+
     # ------------------------------------------------------------------ plumbing
     @property
     def world(self):
@@ -353,7 +407,10 @@ class SAC(object):
             o = self._opt[name]
             return L.Adam(m=o["m"].data_ptr(), v=o["v"].data_ptr(), step=o["step"].data_ptr(), lr=lr, beta1=0.9,
                           beta2=0.999, eps=1e-8)
-        return L.Sac(actor=self.policy.net_struct(), critic=self.critic.net_struct(),
+        if self._dp is not None:
+            self._point_grads_at_symmetric_buffer()
+        return L.Sac(dp=C.pointer(self._dp["struct"]) if self._dp is not None else None,
+                     actor=self.policy.net_struct(), critic=self.critic.net_struct(),
                      critic_target=self.critic_target.net_struct(), actor_opt=adam("actor", self.lr_a),
                      critic_opt=adam("critic", self.lr_c), log_alpha=self.log_alpha.data_ptr(),
                      alpha=self._alpha.data_ptr(), alpha_m=self._alpha_m.data_ptr(), alpha_v=self._alpha_v.data_ptr(),
@@ -421,7 +478,7 @@ class SAC(object):
                          drop_mode=L.DROP_MASK if noise.get("mask_c") is not None else
                          (L.DROP_NONE if noise.get("no_dropout") else L.DROP_RNG))
         losses = self._loss_buffer()
-        out = L.SacOut(losses=losses.data_ptr(), debug=L.ptr(debug))
+        out = L.SacOut(losses=self._loss_out().data_ptr(), debug=L.ptr(debug))
         lib = L.lib()
         nzp = C.byref(nz) if nz is not None else None
         keep = (s, bt, nz, out, ws, batch, noise, debug, extra)      # ctypes structs must outlive the calls
@@ -443,8 +500,8 @@ class SAC(object):
 
         if _phases is not None:          # caller (graph capture of the data-parallel path) drives the phases itself
             return phase
-        if not self.distributed or self.world == 1:
-            phase(0)
+        if not self.distributed or self.world == 1 or self._dp is not None:
+            phase(0)        # (fused data parallel: the Adam kernels all-reduce the gradients themselves)
         else:
             phase(1)
             allreduce_sum_(self.critic._garena)
@@ -458,7 +515,15 @@ class SAC(object):
         """[qf1_loss, policy_loss, qf2_loss, alpha_loss].  Data parallel: four floats in the padded tail of the ACTOR
         gradient arena (next to the alpha-gradient slot; Adam and the unused-gradient memsets skip that range), so the
         actor's gradient all-reduce also sums the per-rank loss shares: no separate 16-byte collective."""
+        if self._dp is not None:
+            return self._dp["tail"][1:5]          # written by the actor's fused all-reduce + Adam pass
+        return self._loss_out()
+
+    def _loss_out(self) -> torch.Tensor:
+        """Where the loss kernels write their per-rank shares."""
         if self.distributed and self.world > 1:
+            if self._dp is not None:
+                self._point_grads_at_symmetric_buffer()
             self.policy.bind()
             slot = int(self.policy.layout().alpha_grad_slot)
             return self.policy._garena[slot + 1: slot + 5]
@@ -518,7 +583,7 @@ class SAC(object):
         graph; per-step state (Adam step counts, alpha, RNG counter, sampled indexes) lives in device
         memory.  Single GPU: one graph for gather + update.  Data parallel: one graph per phase with the
         two NCCL gradient all-reduces issued between them."""
-        dp = self.distributed and self.world > 1
+        dp = self.distributed and self.world > 1 and self._dp is None
         if not self.use_cuda_graph:
             if gather:
                 self.replay_buffer.gather(batch["_idx"], batch)

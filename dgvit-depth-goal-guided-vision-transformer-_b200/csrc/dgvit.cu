@@ -930,8 +930,28 @@ static void critic_backward(const dgvit_net& net, const dgvit_layout& L, const D
 }
 
 // ------------------------------------------------------------------ optimizer
+// data-parallel arguments of one network's fused all-reduce + Adam pass (which: 0 critic, 1 actor); dp == null: off
+static DpDev make_dp(const dgvit_dp* dp, int which, const dgvit_layout& L) {
+  DpDev d;
+  memset(&d, 0, sizeof(d));
+  if (!dp) return d;
+  d.world = dp->world; d.rank = dp->rank; d.which = which;
+  d.arena_off = dp->arena_off[which];
+  d.mc = dp->multicast ? dp->multicast + d.arena_off : nullptr;
+  d.peers = dp->peers; d.pads = dp->pads;
+  d.error_flag = dp->error_flag;
+  d.reduced_out = dp->reduced_out[which];
+  if (which == 1) { d.tail_out = dp->tail; d.tail_begin = L.alpha_grad_slot; d.tail_n = DGVIT_ALIGN_FLOATS; }
+  return d;
+}
+static void dp_wait_done(const dgvit_dp* dp, int which, const dgvit_layout& L, const int64_t* step, cudaStream_t st) {
+  if (!dp) return;
+  launch_k(dp_wait_done_kernel, 1, 32, 0, st, make_dp(dp, which, L), step);
+  DG_LAUNCH_CHECK();
+}
+
 static void adam_step(const dgvit_net& net, const dgvit_layout& L, const dgvit_adam& o, const dgvit_net* tgt,
-                      float tau, bool want_shadow, cudaStream_t st) {
+                      float tau, bool want_shadow, cudaStream_t st, const dgvit_dp* dp = nullptr, int which = 0) {
   DG_REQUIRE(o.m && o.v && o.step, "adam: null state");
   launch_k(step_bump_kernel, 1, 32, 0, st, o.step);
   DG_LAUNCH_CHECK();
@@ -953,7 +973,13 @@ static void adam_step(const dgvit_net& net, const dgvit_layout& L, const dgvit_a
     const double per = 28.0 + (a.shadow ? 4.0 : 0.0);
     const double tgt_b = a.tgt ? (double)L.total * (12.0 + (a.tgt_shadow ? 4.0 : 0.0)) : 0.0;
     ProfScope ps(PROF_ADAM, 0.0, used * per + tgt_b, st);
-    launch_k(adam_polyak_kernel, 148 * 8, 256, 0, st, a);
+    if (dp) {
+      DG_REQUIRE(dp->world >= 2 && dp->rank >= 0 && dp->rank < dp->world && dp->peers && dp->pads && dp->finished && dp->tail,
+                 "dgvit_dp: incomplete");
+      launch_k(adam_polyak_kernel<true>, 148 * 8, 256, 0, st, a, make_dp(dp, which, L), dp->finished + which);
+    } else {
+      launch_k(adam_polyak_kernel<false>, 148 * 8, 256, 0, st, a, DpDev(), (unsigned int*)nullptr);
+    }
     DG_LAUNCH_CHECK();
   }
 }
@@ -1090,6 +1116,7 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   launch_k(critic_loss_kernel, 1, 1024, 0, st, w.q1, w.q2, w.q1t, w.q2t, w.logp2, b.rew, s.alpha, s.gamma, d.B, d.na,
                                          s.global_batch, w.nq, w.dq1, w.dq2, out.losses);
   DG_LAUNCH_CHECK();
+  dp_wait_done(s.dp, 0, Lc, s.critic_opt.step, st);      // (data parallel) peers have read the previous critic gradients
   critic_backward<A>(s.critic, Lc, d, cs, s.sample_offset, w.dq1, w.dq2, nullptr, true, w.critic_s, nullptr, st);
   if (out.debug) {
     const size_t bn = (size_t)d.B * d.na * sizeof(float);
@@ -1107,7 +1134,7 @@ static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   make_layout(s.actor.cfg, La);
   make_layout(s.critic.cfg, Lc);
   const bool shadow = s.precision == DGVIT_BF16;
-  adam_step(s.critic, Lc, s.critic_opt, nullptr, 0.f, shadow, st);               // DRL.py:402
+  adam_step(s.critic, Lc, s.critic_opt, nullptr, 0.f, shadow, st, s.dp, 0);      // DRL.py:402 (+ gradient all-reduce when s.dp)
   // soft update of the target (DRL.py:430-431): the critic does not change again in this update and nothing below reads
   // the target, so it runs beside the policy half instead of at the end of the chain
   cudaStream_t lane = st;
@@ -1140,6 +1167,7 @@ static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
                      w.actor_s.t.partial, st);
   dgvit_actor_grad ag; memset(&ag, 0, sizeof(ag));
   ag.d_action = w.dpi;
+  dp_wait_done(s.dp, 1, La, s.actor_opt.step, st);
   if (da.B == d.B) {
     actor_backward<A>(s.actor, La, d, ai, ag, s.alpha, 1.0f / (float)s.global_batch, w.actor_s, st);
   } else {
@@ -1170,10 +1198,11 @@ static void sac_phase3(const dgvit_sac& s, cudaStream_t st) {
   const bool shadow = s.precision == DGVIT_BF16;
   // temperature step and RNG counter beside the actor's Adam pass
   cudaStream_t lane = lane_fork(st);
-  adam_step(s.actor, La, s.actor_opt, nullptr, 0.f, shadow, st);                 // DRL.py:413
+  adam_step(s.actor, La, s.actor_opt, nullptr, 0.f, shadow, st, s.dp, 1);        // DRL.py:413
+  if (s.dp) { lane_join(lane, st); lane = st; }       // the temperature step needs the REDUCED alpha gradient the pass above wrote
   if (s.auto_alpha) {                                                            // DRL.py:416-423
     launch_k(alpha_step_kernel, 1, 32, 0, lane, s.log_alpha, s.alpha, s.alpha_m, s.alpha_v, s.alpha_step,
-                                        s.actor.grads + La.alpha_grad_slot, s.lr_alpha, 0.9f, 0.999f,
+                                        s.dp ? s.dp->tail : s.actor.grads + La.alpha_grad_slot, s.lr_alpha, 0.9f, 0.999f,
                                         (float)(1.0 - 0.9), (float)(1.0 - 0.999), 1e-8f);
     DG_LAUNCH_CHECK();
   }

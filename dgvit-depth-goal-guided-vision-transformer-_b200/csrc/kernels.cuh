@@ -1019,9 +1019,75 @@ __device__ __forceinline__ void store_shadows4(bf16* shadow, int64_t n, int64_t 
   *reinterpret_cast<uint2*>(shadow + n + i) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
 }
 
+// ---- data parallel: gradient all-reduce fused into the optimizer pass (no NCCL call, no extra launch) -----------------
+// Every rank's gradient arena lives in symmetric memory (torch.distributed._symmetric_memory): the kernel first runs a
+// flag barrier over NVLink (each rank stores the Adam step number into its slot of every peer's signal pad and waits until
+// all slots of its own pad show that number: all gradients of this step are written), then reads the SUM over ranks of
+// every gradient element — one multimem.ld_reduce per 16 bytes, reduced inside the NVSwitch (NVLS), or, without multicast
+// support, one peer load per rank in fixed rank order — and applies Adam.  All ranks read the same sums, so the replicas
+// stay identical.  When a rank has read everything it raises its "done" slot on every peer; the next backward pass waits
+// for those slots (dp_wait_done_kernel) before it overwrites the gradients.
+struct DpDev {
+  int world, rank;
+  const float* mc;                  // multicast address of this arena (null: peer loads)
+  const float* const* peers;        // [world] this arena on every rank (device array of device pointers)
+  int64_t arena_off;                // float offset of this arena inside the symmetric buffer (peers[] point at the buffer)
+  uint32_t* const* pads;            // [world] signal pads (uint32 words); slots: [which][0: ready, 1: done][rank]
+  int which;                        // 0 critic, 1 actor
+  float* tail_out; int64_t tail_begin, tail_n;   // reduced copy of a skipped range Adam does not touch (alpha gradient + loss sums)
+  float* reduced_out;               // optional: the reduced gradients (tests)
+  int* error_flag;                  // set when a flag wait times out
+};
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t* dp_slot(const DpDev& dp, int on_rank, int kind, int of_rank) {
+  return dp.pads[on_rank] + ((dp.which * 2 + kind) * dp.world + of_rank);
+}
+// all `world` slots of kind `kind` on this rank's pad have reached `epoch` (bounded spin: a dead peer must not hang the GPU)
+__device__ __forceinline__ void dp_wait_all(const DpDev& dp, int kind, uint32_t epoch) {
+  const long long t0 = clock64();
+  for (int p = 0; p < dp.world; ++p) {
+    const uint32_t* slot = dp_slot(dp, dp.rank, kind, p);
+    while ((int32_t)(ld_acquire_sys(slot) - epoch) < 0) {
+      if (clock64() - t0 > 6000000000ll) { if (dp.error_flag) *dp.error_flag = 1; return; }
+      __nanosleep(64);
+    }
+  }
+}
+__device__ __forceinline__ float4 dp_reduced4(const DpDev& dp, int64_t i) {
+  float4 g;
+  if (dp.mc) {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(dp.mc + i) : "memory");
+  } else {
+    g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < dp.world; ++p) {
+      float4 v;
+      asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(dp.peers[p] + dp.arena_off + i) : "memory");
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+  }
+  return g;
+}
+// the next writer of a gradient arena waits until every peer has finished reading the previous step's gradients
+__global__ void dp_wait_done_kernel(const __grid_constant__ DpDev dp, const int64_t* step) {
+  pdl_wait();
+  pdl_launch();
+  if (threadIdx.x == 0) dp_wait_all(dp, 1, (uint32_t)(*step));
+}
+
 // n is a multiple of 64 and every skip range starts / ends on a 64-float boundary (dgvit_param_layout), so a float4
 // never straddles a range
-__global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant__ AdamArgs a) {
+template <bool DP>
+__global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant__ AdamArgs a, const __grid_constant__ DpDev dp,
+                                                          unsigned int* finished) {
   pdl_wait();
   pdl_launch();
   __shared__ float sh[2];
@@ -1031,6 +1097,14 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
     const double bc2 = 1.0 - pow((double)a.b2, t);
     sh[0] = (float)((double)a.lr / bc1);
     sh[1] = (float)sqrt(bc2);
+    if (DP) {
+      const uint32_t epoch = (uint32_t)(*a.step);
+      if (blockIdx.x == 0) {                 // this rank's gradients are complete (stream order): tell every peer
+        __threadfence_system();
+        for (int p = 0; p < dp.world; ++p) st_release_sys(dp_slot(dp, p, 0, dp.rank), epoch);
+      }
+      dp_wait_all(dp, 0, epoch);
+    }
   }
   __syncthreads();
   const float step_size = sh[0], bc2s = sh[1];
@@ -1040,8 +1114,11 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
     bool skip = false;
     for (int k = 0; k < a.n_skip; ++k) skip |= (i >= a.skip_b[k] && i < a.skip_e[k]);
     float4 p = *reinterpret_cast<const float4*>(a.p + i);
+    if (DP && skip && i >= dp.tail_begin && i < dp.tail_begin + dp.tail_n)
+      *reinterpret_cast<float4*>(dp.tail_out + (i - dp.tail_begin)) = dp_reduced4(dp, i);
     if (!skip) {
-      const float4 g = *reinterpret_cast<const float4*>(a.g + i);
+      const float4 g = DP ? dp_reduced4(dp, i) : *reinterpret_cast<const float4*>(a.g + i);
+      if (DP && dp.reduced_out) *reinterpret_cast<float4*>(dp.reduced_out + i) = g;
       float4 m = *reinterpret_cast<const float4*>(a.m + i), v = *reinterpret_cast<const float4*>(a.v + i);
 #define DG_ADAM1(C_)                                                                                     \
       m.C_ = m.C_ + a.omb1 * (g.C_ - m.C_);              /* exp_avg.lerp_(grad, 1-beta1) */                 \
@@ -1060,6 +1137,18 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
       t.z = t.z * (1.0f - a.tau) + p.z * a.tau; t.w = t.w * (1.0f - a.tau) + p.w * a.tau;
       *reinterpret_cast<float4*>(a.tgt + i) = t;
       if (a.tgt_shadow) store_shadows4(a.tgt_shadow, a.n, i, t);
+    }
+  }
+  if (DP) {     // the last block to finish reading raises this rank's "done" slot on every peer
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int done = atomicAdd(finished, 1u);
+      if (done == gridDim.x - 1) {
+        *finished = 0;
+        const uint32_t epoch = (uint32_t)(*a.step);
+        for (int p = 0; p < dp.world; ++p) st_release_sys(dp_slot(dp, p, 1, dp.rank), epoch);
+      }
     }
   }
 }

@@ -145,6 +145,24 @@ typedef struct dgvit_adam {
   float lr, beta1, beta2, eps;
 } dgvit_adam;
 
+/* Data parallel without NCCL calls: the gradient all-reduce is fused into the optimizer pass.  Both gradient arenas live
+ * in ONE symmetric-memory buffer per rank ([critic grads | actor grads], e.g. torch.distributed._symmetric_memory): the
+ * Adam kernel of a network runs a flag barrier over the ranks' signal pads, reads the rank-sum of every gradient element
+ * (multimem.ld_reduce through the NVSwitch when `multicast` != NULL, else peer loads in rank order) and updates the
+ * replica; dgvit_sac_update is then the whole data-parallel step (one call, one CUDA graph).  All pointers are device
+ * pointers of THIS rank's address space. */
+typedef struct dgvit_dp {
+  int32_t world, rank;
+  const float* multicast;         /* multicast address of the symmetric buffer, or NULL */
+  const float* const* peers;      /* [world] the symmetric buffer on every rank (device array) */
+  uint32_t* const* pads;          /* [world] signal pads, >= 4 * world uint32 each, zero-initialised (device array) */
+  int64_t arena_off[2];           /* float offset of the critic / actor gradient arena inside the buffer */
+  float* tail;                    /* [64] local: reduced alpha-gradient slot and loss sums (actor arena tail) */
+  float* reduced_out[2];          /* optional [layout.total] each: the reduced gradients (tests), else NULL */
+  unsigned int* finished;         /* [2] local zero-initialised counters */
+  int32_t* error_flag;            /* local: set to 1 when a peer did not show up within ~3 s */
+} dgvit_dp;
+
 typedef struct dgvit_sac {
   dgvit_net actor, critic, critic_target;
   dgvit_adam actor_opt, critic_opt;
@@ -159,6 +177,7 @@ typedef struct dgvit_sac {
   int32_t sample_offset;  /* this rank's first sample inside the global batch */
   uint64_t* rng_state;    /* device {seed, counter}; counter advanced once per update */
   const float* action_scale; const float* action_bias;
+  const dgvit_dp* dp;     /* NULL: single GPU, or gradients all-reduced by the caller between the phases */
 } dgvit_sac;
 
 typedef struct dgvit_batch {   /* one replay minibatch, already on the device */
