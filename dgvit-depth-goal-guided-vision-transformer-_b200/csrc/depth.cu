@@ -21,10 +21,11 @@ __global__ void depth_minmax_kernel(const float* __restrict__ raw, float* __rest
   const int f = blockIdx.y;
   const float* src = raw + (int64_t)f * hw;
   float mn = INFINITY, mx = -INFINITY;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = src[i];
-    mn = fminf(mn, v);
-    mx = fmaxf(mx, v);
+  const int64_t hw4 = hw >> 2;          // (H and W are multiples of 4, frames 16-byte aligned)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+    mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
   }
   __shared__ float smn[32], smx[32];
 #pragma unroll
@@ -154,6 +155,44 @@ __global__ void depth_resize_kernel(const float* __restrict__ S2, const float* _
   }
 }
 
+// Four N(0,1) draws of the aligned pixel group gi4 = gi >> 2: ONE Philox4x32 call and two Box-Muller pairs (the per-pixel
+// normal_at() above evaluates the same numbers; it recomputes the call for each of the 4 pixels)
+__device__ __forceinline__ float4 normal4_at(const uint64_t* rng, int64_t gi4) {
+  uint32_t r[4];
+  philox4x32(rng[0], (uint64_t)gi4, 0x6465707468000000ull | (rng[1] & 0xffffffffu), r);
+  const float rad0 = sqrtf(-2.0f * __logf(u01(r[0]))), rad1 = sqrtf(-2.0f * __logf(u01(r[2])));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u01(r[1]), &s0, &c0);
+  __sincosf(6.283185307179586f * u01(r[3]), &s1, &c1);
+  return make_float4(rad0 * c0, rad0 * s0, rad1 * c1, rad1 * s1);
+}
+__device__ __forceinline__ float noisy1(float raw, float nz, double scale, double shift) {
+  const float nrm = (float)((double)raw * scale + shift);          // cv2.normalize(NORM_MINMAX, 0..255) ...
+  const float u8 = (float)(int)fminf(fmaxf(nrm, 0.f), 255.f);      // ... .astype(uint8) (truncation)
+  return fminf(fmaxf(u8 + nz, 0.f), 255.f);
+}
+// the noisy image A at the aligned 4-pixel group starting at column x4 of row gy (x4 may lie outside the image: every
+// pixel is then taken at its BORDER_REFLECT_101 mirror, noise included: the blur mirrors the NOISY image)
+__device__ __forceinline__ float4 noisy_group(const float* __restrict__ raw, const float* __restrict__ noise, const uint64_t* rng,
+                                              int64_t fbase, int gy, int x4, int W, double scale, double shift) {
+  const int64_t rb = fbase + (int64_t)gy * W;
+  if (x4 >= 0 && x4 + 3 < W) {
+    const float4 rv = *reinterpret_cast<const float4*>(raw + rb + x4);
+    float4 nz;
+    if (noise) nz = *reinterpret_cast<const float4*>(noise + rb + x4);
+    else { nz = normal4_at(rng, (rb + x4) >> 2); nz.x *= 50.f; nz.y *= 50.f; nz.z *= 50.f; nz.w *= 50.f; }
+    return make_float4(noisy1(rv.x, nz.x, scale, shift), noisy1(rv.y, nz.y, scale, shift), noisy1(rv.z, nz.z, scale, shift),
+                       noisy1(rv.w, nz.w, scale, shift));
+  }
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t gi = rb + reflect101(x4 + k, W);
+    o[k] = noisy1(raw[gi], noise ? noise[gi] : 50.0f * normal_at(rng, gi), scale, shift);
+  }
+  return make_float4(o[0], o[1], o[2], o[3]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fused pass: noise + 5x5 blur + centre-band 11x11 blur + 4x bilinear resize + /255 in one kernel.
 // One CTA = an 8 x 32 tile of OUTPUT pixels (32 x 128 input pixels + halo) staged in shared memory:
@@ -167,7 +206,9 @@ constexpr int TOH = 8, TOW = 32;                 // output tile
 constexpr int CORE_R = TOH * 4 - 2, CORE_C = TOW * 4 - 2;   // span of sampled rows / cols (30, 126)
 constexpr int A_R = CORE_R + 14, A_C = CORE_C + 14;         // 44 x 140 (halo 7)
 constexpr int S_R = CORE_R + 10, S_C = CORE_C + 10;         // 40 x 136 (halo 5)
-constexpr int A_P = A_C + 1, S_P = S_C + 1;                 // padded pitches
+constexpr int A_P = 148, S_P = S_C + 1;                     // pitches: A rows hold aligned float4 groups (144 columns at most)
+static_assert(A_P % 4 == 0 && A_P >= A_C + 4, "A pitch");
+constexpr int H_P = TOW + 1;                                // fast path: horizontal 6-tap results [rows][TOW]
 constexpr int FUSED_SMEM = (A_R * A_P + A_R * S_P) * 4 + 32;   // S2 reuses A, T1 reuses Bh
 
 __global__ void __launch_bounds__(256) depth_fused_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
@@ -184,16 +225,22 @@ __global__ void __launch_bounds__(256) depth_fused_kernel(const float* __restric
   const int f = blockIdx.z, oy0 = blockIdx.y * TOH, ox0 = blockIdx.x * TOW;
   const int oh = H / 4, ow = W / 4;
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    float mn = INFINITY, mx = -INFINITY;
-    for (int b = 0; b < MM_BLOCKS; ++b) {
-      mn = fminf(mn, mmpart[((int64_t)f * MM_BLOCKS + b) * 2]);
-      mx = fmaxf(mx, mmpart[((int64_t)f * MM_BLOCKS + b) * 2 + 1]);
+  if (tid < 32) {        // frame min / max from the 64 partials: one warp, two partials per lane
+    static_assert(MM_BLOCKS == 64, "two partials per lane");
+    const float2 p0 = *reinterpret_cast<const float2*>(mmpart + ((int64_t)f * MM_BLOCKS + tid) * 2);
+    const float2 p1 = *reinterpret_cast<const float2*>(mmpart + ((int64_t)f * MM_BLOCKS + 32 + tid) * 2);
+    float mn = fminf(p0.x, p1.x), mx = fmaxf(p0.y, p1.y);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    const double rg = (double)mx - (double)mn;
-    const double s = rg > 2.220446049250313e-16 ? 255.0 / rg : 0.0;
-    sc[0] = s;
-    sc[1] = 0.0 - (double)mn * s;
+    if (tid == 0) {
+      const double rg = (double)mx - (double)mn;
+      const double s = rg > 2.220446049250313e-16 ? 255.0 / rg : 0.0;
+      sc[0] = s;
+      sc[1] = 0.0 - (double)mn * s;
+    }
   }
   const int ys0 = oy0 * 4 + 1, xs0 = ox0 * 4 + 1;           // first sampled row / col of the tile
   const int y2 = y1 + bh;
@@ -205,43 +252,97 @@ __global__ void __launch_bounds__(256) depth_fused_kernel(const float* __restric
   const double scale = sc[0], shift = sc[1];
   const float k5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
   const int64_t fbase = (int64_t)f * H * W;
-  {  // stage A: warp per window row, lanes over columns; all loads of a row issued before any use
-    const int lane = tid & 31, wrp = tid >> 5;
-    for (int r = wrp; r < ar; r += 8) {
-      const int gy = reflect101(ys0 - hs - 2 + r, H);
-      const int64_t rb = fbase + (int64_t)gy * W;
-      float rv[5], nv[5];
-      int gxs[5];
+  // stage A: one thread = one aligned group of 4 pixels (16-byte loads of raw / noise, one Philox call per group).
+  // Column c of the window sits at A[r][c + ax] where ax = (window start) - (aligned start) in [0, 4).
+  const int wx0 = xs0 - hs - 2;                                  // first window column (frame coordinates, may be < 0)
+  const int xa = (wx0 >= 0 ? wx0 : wx0 - 3) / 4 * 4;             // aligned down
+  const int ax = wx0 - xa;
+  const int ng = (ax + ac + 3) / 4;                              // groups per row
+  {
+    // all 16-byte loads of a thread's groups are issued before any of them is used (the stage is a chain of HBM
+    // latencies otherwise: 4 resident CTAs per SM hold one load per thread in flight)
+    constexpr int U = 2;
+    const int total = ar * ng;
+    for (int base = tid; base < total; base += 256 * U) {
+      float4 rv[U], nv[U];
+      int rr[U], gg[U], gys[U];
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int c = lane + 32 * k;
-        gxs[k] = reflect101(xs0 - hs - 2 + min(c, ac - 1), W);
-        rv[k] = raw[rb + gxs[k]];
-        nv[k] = noise ? noise[rb + gxs[k]] : 0.f;
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * 256;
+        rr[u] = band ? i / 36 : i / 34;                      // ng = 36 (band window) or 34: constant divisors
+        gg[u] = i - rr[u] * ng;
+        gys[u] = reflect101(ys0 - hs - 2 + min(rr[u], ar - 1), H);
+        const int x4 = xa + 4 * gg[u];
+        rv[u] = nv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total && x4 >= 0 && x4 + 3 < W) {
+          const int64_t gi = fbase + (int64_t)gys[u] * W + x4;
+          rv[u] = *reinterpret_cast<const float4*>(raw + gi);
+          if (noise) nv[u] = *reinterpret_cast<const float4*>(noise + gi);
+        }
       }
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int c = lane + 32 * k;
-        if (c < ac) {
-          const float nrm = (float)((double)rv[k] * scale + shift);
-          const float u8 = (float)(int)fminf(fmaxf(nrm, 0.f), 255.f);
-          const float nz = noise ? nv[k] : 50.0f * normal_at(rng, rb + gxs[k]);
-          A[r * A_P + c] = fminf(fmaxf(u8 + nz, 0.f), 255.f);
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * 256;
+        if (i >= total) continue;
+        const int x4 = xa + 4 * gg[u];
+        float4 o;
+        if (x4 >= 0 && x4 + 3 < W) {
+          float4 nz = nv[u];
+          if (!noise) {
+            nz = normal4_at(rng, (fbase + (int64_t)gys[u] * W + x4) >> 2);
+            nz.x *= 50.f; nz.y *= 50.f; nz.z *= 50.f; nz.w *= 50.f;
+          }
+          o = make_float4(noisy1(rv[u].x, nz.x, scale, shift), noisy1(rv[u].y, nz.y, scale, shift),
+                          noisy1(rv[u].z, nz.z, scale, shift), noisy1(rv[u].w, nz.w, scale, shift));
+        } else {
+          o = noisy_group(raw, noise, rng, fbase, gys[u], x4, W, scale, shift);      // image border: mirrored pixel by pixel
         }
+        *reinterpret_cast<float4*>(A + rr[u] * A_P + 4 * gg[u]) = o;
       }
     }
   }
   __syncthreads();
-  for (int i = tid; i < ar * scn; i += blockDim.x) {          // horizontal 5-tap
-    const int r = i / scn, c = i % scn;
+  if (!band) {
+    // Fast path (no sampled row in the centre band: 80 % of the tiles).  cv2.resize by 4 averages the GaussianBlur(5,5)
+    // image at rows / columns 4o+1, 4o+2: the composite is ONE separable 6-tap filter with stride 4,
+    //   w6 = ([1 4 6 4 1 0] + [0 1 4 6 4 1]) / 32 = [1 5 10 10 5 1] / 32   over pixels 4o-1 .. 4o+4,
+    // so only 1/4 of the blurred image is ever formed: horizontal pass at the TOW output columns of every window row
+    // (three conflict-free 16-byte shared loads per result), vertical pass at the TOH output rows.
+    const float w6[6] = {1.f / 32, 5.f / 32, 10.f / 32, 10.f / 32, 5.f / 32, 1.f / 32};
+    float* Hh = Bh;                                              // [ar][H_P]
+    for (int i = tid; i < ar * TOW; i += blockDim.x) {
+      const int r = i / TOW, j = i % TOW;
+      // window column of pixel 4(ox0+j)-1 is 4j (hs = 0: the window starts at 4 ox0 - 1), i.e. A column 4j + ax
+      const float* row = A + r * A_P + 4 * j + ax;               // ax = 3 here (wx0 = 4 ox0 - 1): row + 1 is 16-byte aligned
+      const float a0 = row[0];
+      const float4 m = *reinterpret_cast<const float4*>(row + 1);
+      const float a5 = row[5];
+      Hh[r * H_P + j] = w6[0] * a0 + w6[1] * m.x + w6[2] * m.y + w6[3] * m.z + w6[4] * m.w + w6[5] * a5;
+    }
+    __syncthreads();
+    const int oy = oy0 + tid / TOW, ox = ox0 + tid % TOW;
+    if (oy < oh && ox < ow) {
+      const float* col = Hh + (tid / TOW) * 4 * H_P + tid % TOW;
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) acc = fmaf(w6[t], col[t * H_P], acc);
+      out[((int64_t)f * oh + oy) * ow + ox] = acc / 255.0f;
+    }
+    return;
+  }
+  // band tiles: A columns are addressed through the alignment offset from here on
+  A += ax;
+  // (band tiles: hs = 5, so ar = A_R, sr = S_R, scn = S_C are compile-time constants: no run-time divisions below)
+  for (int i = tid; i < A_R * S_C; i += 256) {                 // horizontal 5-tap
+    const int r = i / S_C, c = i % S_C;
     float s = 0.f;
 #pragma unroll
     for (int t = 0; t < 5; ++t) s = fmaf(k5[t], A[r * A_P + c + t], s);
     Bh[r * S_P + c] = s;
   }
   __syncthreads();
-  for (int i = tid; i < sr * scn; i += blockDim.x) {          // vertical 5-tap -> GaussianBlur(5,5)
-    const int r = i / scn, c = i % scn;
+  for (int i = tid; i < S_R * S_C; i += 256) {                 // vertical 5-tap -> GaussianBlur(5,5)
+    const int r = i / S_C, c = i % S_C;
     float s = 0.f;
 #pragma unroll
     for (int t = 0; t < 5; ++t) s = fmaf(k5[t], Bh[(r + t) * S_P + c], s);
@@ -249,7 +350,7 @@ __global__ void __launch_bounds__(256) depth_fused_kernel(const float* __restric
   }
   __syncthreads();
   if (band) {                                                  // horizontal 11-tap at the sampled columns
-    for (int i = tid; i < sr * 2 * TOW; i += blockDim.x) {
+    for (int i = tid; i < S_R * 2 * TOW; i += 256) {
       const int r = i / (2 * TOW), j = i % (2 * TOW);
       const int c = (j >> 1) * 4 + (j & 1);                    // sampled col relative to xs0
       float s = 0.f;
@@ -274,7 +375,9 @@ __global__ void __launch_bounds__(256) depth_fused_kernel(const float* __restric
             v = 0.f;
 #pragma unroll
             for (int t = 0; t < 11; ++t) {
-              const int yy = y1 + reflect101(y - y1 + t - 5, bh);          // reflect inside the band
+              int yb = y - y1 + t - 5;                                       // reflect inside the band (one fold: bh > 5)
+              yb = bh > 5 ? (yb < 0 ? -yb : (yb >= bh ? 2 * (bh - 1) - yb : yb)) : reflect101(yb, bh);
+              const int yy = y1 + yb;
               v = fmaf(kk.k[t], T1[(yy - (ys0 - hs)) * 2 * TOW + j], v);
             }
           } else {
@@ -313,6 +416,7 @@ int dgvit_depth_augment(const float* raw, const float* noise, const uint64_t* rn
     DG_REQUIRE(raw && out && scratch && n >= 1, "null argument");
     DG_REQUIRE(noise || rng_state, "provide noise or rng_state");
     DG_REQUIRE(H % 4 == 0 && W % 4 == 0, "H and W must be multiples of 4");
+    DG_REQUIRE((((uintptr_t)raw) & 15) == 0 && (((uintptr_t)noise) & 15) == 0, "raw / noise must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     Carver cv(scratch, scratch_bytes);
     float* mm = cv.take<float>((size_t)n * MM_BLOCKS * 2);
