@@ -19,6 +19,7 @@
 #include "attn_tc.cuh"
 #include "attn_long_tc.cuh"
 #include "mlp_tc.cuh"
+#include "patch_tc.cuh"
 #endif
 
 namespace dgvit {
@@ -433,7 +434,25 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
   const dgvit_cfg& cfg = net.cfg;
   const float* P = net.params;
   // K1: patch embedding
-  if (!(skip_mask() & SKIP_EMBED)) {
+  bool embedded = false;
+#ifdef DGVIT_WITH_TC
+  if constexpr (std::is_same<A, bf16>::value) {
+    // im2col-free: frame -> swizzled smem A tiles -> tcgen05 -> bias + goal token + pos + dropout + LayerNorm-1, one launch
+    if (!(skip_mask() & SKIP_EMBED) && patch::eligible(cfg, img, WSel<A>::w(net, L.patch_w), c.L[0].Xn1)) {
+      const dgvit_block_layout& b0 = L.block[0];
+      LayerBuf<A>& B0 = c.L[0];
+      patch::PatchArgs pa;
+      pa.img = img; pa.n_tok = (int64_t)d.B * d.P; pa.P = d.P; pa.N = d.N;
+      pa.bias = P + L.patch_b; pa.pos = P + L.pos; pa.gt = gt; pa.tok = c.tok; pa.drop = drop;
+      pa.X0 = B0.Xa; pa.Y = (bf16*)B0.Xn1; pa.gamma = P + b0.ln1_w; pa.beta = P + b0.ln1_b; pa.mean = B0.mean1; pa.rstd = B0.rstd1;
+      ProfScope ps(PROF_EMBED, 2.0 * d.B * d.P * d.pd * d.D, (double)d.B * (cfg.img_h * cfg.img_w * 4.0 + d.N * (d.D * 6.0 + 8.0)), st);
+      ProfScope ps2(PROF_GEMM_ALL, 2.0 * d.B * d.P * d.pd * d.D, 0.0, st);
+      patch::fwd(cfg, pa, (const bf16*)WSel<A>::w(net, L.patch_w), st);
+      embedded = true;
+    }
+  }
+#endif
+  if (!embedded && !(skip_mask() & SKIP_EMBED)) {
     if (!c.Pm_ext) launch_patchify<A>(img, c.Pm, d.B, d, cfg, st);
     linear_fwd<A, A, float>(c.Pm_ext ? c.Pm_ext : c.Pm, WSel<A>::w(net, L.patch_w), c.Xp, (int64_t)d.B * d.P, d.D, d.pd, EPI_BIAS,
                             P + L.patch_b, st);
@@ -597,7 +616,7 @@ static void lane_join(cudaStream_t lane, cudaStream_t st) {
 // in: c.dz [B,D]; out: grads of every trunk parameter, c.dtok [B,D]
 template <typename A>
 static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const DropDev& drop,
-                           TrunkCtx<A>& c, int relu_tok, cudaStream_t st) {
+                           TrunkCtx<A>& c, int relu_tok, cudaStream_t st, const float* img) {
   const float* P = net.params;
   float* G = net.grads;
   const bool side = side_on(c);
@@ -726,6 +745,16 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
       DG_LAUNCH_CHECK();
     }
   }
+  // patch-weight gradient dW = dXp^T Pm: the im2col-free forward never wrote the patch matrix, so unless the caller made
+  // one for these frames (the update does, once per frame batch) it is formed here
+#ifdef DGVIT_WITH_TC
+  if constexpr (std::is_same<A, bf16>::value) {
+    if (!c.Pm_ext && patch::eligible(net.cfg, img, WSel<A>::w(net, L.patch_w), c.L[0].Xn1)) {
+      DG_REQUIRE(img != nullptr, "trunk_backward: frames needed to rebuild the patch matrix");
+      launch_patchify<A>(img, c.Pm, d.B, d, net.cfg, st);
+    }
+  }
+#endif
   linear_bwd_w<A, A>(c.dXp, c.Pm_ext ? c.Pm_ext : c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st, -1,
                      -1, &rl_misc);
   rl_misc.launch(st);
@@ -830,7 +859,7 @@ static void actor_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     dw.launch(side_fork(c.t, st));      // joined at the end of trunk_backward
   }
   const DropDev drop = make_drop(io.drop, d, io.sample_offset);
-  trunk_backward<A>(net, L, d, drop, c.t, /*relu_tok=*/0, st);
+  trunk_backward<A>(net, L, d, drop, c.t, /*relu_tok=*/0, st, io.img);
   {  // fc_embed: dW[D,nps] = dtok^T pstate ; db = colsum(dtok)
     heads::DwList dw(d.B);
     dw.add(c.t.dtok, d.D, io.pstate, G + L.embed_w, G + L.embed_b, d.D, d.nps);
@@ -922,7 +951,7 @@ static void critic_backward(const dgvit_net& net, const dgvit_layout& L, const D
   DG_LAUNCH_CHECK();
   if (param_grads) {
     const DropDev drop = make_drop(io.drop, d, sample_offset);
-    trunk_backward<A>(net, L, d, drop, c.t, /*relu_tok=*/1, st);
+    trunk_backward<A>(net, L, d, drop, c.t, /*relu_tok=*/1, st, io.img);
     heads::DwList dw(d.B);
     dw.add(c.t.dtok, d.D, io.pstate, G + L.embed_w, G + L.embed_b, d.D, d.nps);
     dw.launch(st);
@@ -1068,7 +1097,13 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   launch_patchify<A>(b.obs, w.actor_s.t.Pm, da.B, da, s.actor.cfg, f.aux[0]);
   DG_CUDA(cudaEventRecord(f.fork2, f.aux[0]));
   DG_CUDA(cudaStreamWaitEvent(f.aux[1], f.fork2, 0));
-  launch_patchify<A>(b.next_obs, w.actor_tmp.t.Pm, d.B, d, s.actor.cfg, st);
+  bool fused_embed = false;     // im2col-free forward: s' needs no patch matrix at all, s only for the two patch-weight gradients
+#ifdef DGVIT_WITH_TC
+  if constexpr (std::is_same<A, bf16>::value)
+    fused_embed = patch::eligible(s.actor.cfg, b.next_obs, WSel<A>::w(s.actor, La.patch_w), w.actor_tmp.t.L[0].Xn1) &&
+                  patch::eligible(s.actor.cfg, b.obs, WSel<A>::w(s.critic, Lc.patch_w), w.actor_s.t.L[0].Xn1);
+#endif
+  if (!fused_embed) launch_patchify<A>(b.next_obs, w.actor_tmp.t.Pm, d.B, d, s.actor.cfg, st);
   w.actor_s.t.Pm_ext = w.actor_s.t.Pm; w.critic_s.t.Pm_ext = w.actor_s.t.Pm;
   w.actor_tmp.t.Pm_ext = w.actor_tmp.t.Pm; w.critic_tmp.t.Pm_ext = w.actor_tmp.t.Pm;
   // ---- stream 0 (caller's): a', log pi' = policy.sample(s') ; q_t = critic_target(s', a')   (DRL.py:388-393)
@@ -1270,6 +1305,7 @@ int dgvit_set_option(const char* name, int value) {
     else if (!strcmp(name, "debug_epilogue")) tc::g_debug = value;
     else if (!strcmp(name, "attn_bwd2")) attn::g_bwd2_enabled = value != 0;
     else if (!strcmp(name, "attn_long")) attnl::g_enabled = value != 0;
+    else if (!strcmp(name, "patch_fused")) patch::g_enabled = value != 0;
     else if (!strcmp(name, "mlp_split")) mlp::g_split_enabled = value != 0;
     else if (!strcmp(name, "mlp_front")) mlp::g_front_enabled = value != 0;
     else if (!strcmp(name, "mlp_h16")) mlp::g_h16_enabled = value != 0;
@@ -1493,7 +1529,7 @@ int dgvit_trunk_backward(const dgvit_net* net, const dgvit_trunk_io* io, const f
       carve_trunk<A>(cv, d, true, c);
       DG_CUDA(cudaMemcpyAsync(c.dz, d_z, (size_t)B * d.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
       const DropDev drop = make_drop(io->drop, d, io->sample_offset);
-      trunk_backward<A>(*net, L, d, drop, c, /*relu_tok=*/0, st);
+      trunk_backward<A>(*net, L, d, drop, c, /*relu_tok=*/0, st, io->img);
       if (d_goal) DG_CUDA(cudaMemcpyAsync(d_goal, c.dtok, (size_t)B * d.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     };
     by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
