@@ -38,7 +38,7 @@ F_A, F_C = 190_371_072, 190_371_328
 FLOP_PER_SAMPLE = 4 * F_A + 5 * F_C
 # dram__bytes_read.sum + dram__bytes_write.sum of one mlp_fwd_tc_kernel launch (16640 rows, no pre-activation
 # store) from the `ncu --set full` capture summarised in profiles/ (None until captured)
-NCU_TRAFFIC_BYTES = 13400000  # profiles/r1_15_final_launches.md (mlp_fwd_tc_kernel<0,1>, 16640 rows: 13.4 MB read + written per launch)
+NCU_TRAFFIC_BYTES = 34_890_000  # profiles/r2_02_mlp_fwd_ncu.md (mlp_fwd_tc_kernel<0,1,1>, 16640 rows: 13.39 MB read + 21.5 MB written per launch)
 
 
 def peaks():
@@ -291,7 +291,7 @@ def run_ours(args):
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
     tags = (("mlp_fused", L.PROF_MLP_FUSED), ("gemm_all", L.PROF_GEMM_ALL), ("attention", L.PROF_ATTENTION),
-            ("adam_polyak", L.PROF_ADAM), ("layernorm_bwd", L.PROF_LN_BWD), ("embed_ln", L.PROF_EMBED),
+            ("adam_polyak", L.PROF_ADAM), ("layernorm_bwd", L.PROF_LN_BWD), ("patch_embed", L.PROF_EMBED),
             ("patchify", L.PROF_PATCH), ("replay_gather", L.PROF_GATHER))
     for tag_name, tag in tags:
         L.check(lib.dgvit_prof_begin(tag, psteps * 400), "prof_begin")
@@ -476,14 +476,15 @@ def run_ours(args):
     ach = dom["tflops"]
     roof = dict(bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s", frac=ach / pk["tf_sust"],
                 traffic=NCU_TRAFFIC_BYTES,
-                kernel="mlp::mlp_fwd_tc_kernel (out-projection + LayerNorm-2 prologue, fused fc1 + GELU + fc2 + residual, next LayerNorm-1; tcgen05/TMEM)",
+                kernel="mlp::mlp_fwd_tc_kernel (out-projection + LayerNorm-2 prologue, fused fc1 + GELU + fc2 (f16 hidden tile) + residual, next LayerNorm-1; tcgen05/TMEM)",
                 how="CUDA events around every launch of the kernel in an eager single-stream replica of the timed steps "
-                    "(includes the per-launch event gap; ncu reports the same 27-28 us per cold launch)",
+                    "(includes the per-launch event gap; ncu reports 34-35 us per cold launch incl. the prologue)",
                 back_to_back=dict(us_per_launch=burst_us, tflops=4.0 * rows * 64 * 2048 / burst_us / 1e6,
                                   frac=4.0 * rows * 64 * 2048 / burst_us / 1e6 / pk["tf_burst"], peak=pk["tf_burst"],
                                   what="20 graph-replayed launches between one event pair, %d token rows, burst bf16 peak" % rows),
-                limiter=dict(what="not the tensor pipe: the GELU epilogue needs one MUFU.TANH per hidden element and the SM "
-                                  "retires 16 per clock (profiles/r1_13_pipe_rates.md); floor = rows*2048/(148*16) clocks",
+                limiter=dict(what="stall-bound (ncu, profiles/r2_02_mlp_fwd_ncu.md: XU 30 %, FMA 21 %, tensor 16 % of peak; long-scoreboard "
+                                  "and barrier waits with 4.5 warps per scheduler); the MUFU.TANH floor below (one per hidden element, "
+                                  "16 per clock per SM) is the next hard limit: floor = rows*2048/(148*16) clocks",
                              floor_us=rows * 2048 / (148 * 16) / ((clocks or {}).get("sm_mhz") or 1965.0),
                              at_sm_mhz=(clocks or {}).get("sm_mhz") or 1965.0),
                 algorithmic_flop_per_launch="4*rows*64*2048 + 2*rows*64*256 (8.72 + 0.55 GFLOP at 16640 token rows)",
@@ -496,7 +497,7 @@ def run_ours(args):
                 eager_ms_per_step=eager_ms_per_step, peak_source=pk["src"] + " (sustained bf16 cuBLAS)",
                 other_kernels={k: v for k, v in prof.items() if k in ("gemm_all", "attention")},
                 hbm_kernels=dict(peak_GBps=pk["hbm"], peak_source=pk["src"] + " (device copy bandwidth)",
-                                 in_step={k: v for k, v in prof.items() if k in ("adam_polyak", "layernorm_bwd", "embed_ln", "patchify", "replay_gather")},
+                                 in_step={k: v for k, v in prof.items() if k in ("adam_polyak", "layernorm_bwd", "patch_embed", "patchify", "replay_gather")},
                                  in_step_how="CUDA events around every launch of the family inside the eager single-stream "
                                              "replica of the timed step (B=%d; includes the per-launch event gap), "
                                              "algorithmic bytes as stated in DESIGN.md §4" % B, **hbm))
