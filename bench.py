@@ -303,7 +303,9 @@ def run_ours(args):
         prof[tag_name] = dict(ms_per_step=pms.value / psteps, launches_per_step=pl.value / psteps,
                               tflops=(pfl.value / 1e12) / (pms.value / 1e3) if pms.value > 0 else 0.0,
                               flop_per_step=pfl.value / psteps)
-        if pby.value > 0:       # HBM-bound family: algorithmic bytes / event time around every launch
+        if pl.value == 0 and tag_name in ("patchify",):
+            prof.pop(tag_name, None)      # (the bf16 update has no patch matrix: nothing to report)
+        elif pby.value > 0:       # HBM-bound family: algorithmic bytes / event time around every launch
             gbps = pby.value / 1e9 / (pms.value / 1e3) if pms.value > 0 else 0.0
             prof[tag_name] = dict(us_per_launch=pms.value * 1e3 / max(pl.value, 1), launches_per_step=pl.value / psteps,
                                   bytes_per_launch=pby.value / max(pl.value, 1), GBps=gbps, frac=gbps / pk["hbm"])

@@ -184,6 +184,16 @@ static void linear_bwd_w(const TA* dy, const TB* x, float* dW, float* db, int64_
   }
 }
 
+// db[N] = colsum(dy[R, N]) through the deferred reduction (fixed summation order)
+template <typename TA>
+static void bias_grad_colsum(const TA* dy, int64_t ldy, float* db, int64_t R, int N, ReduceList& rl, cudaStream_t st) {
+  const int S = (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 128);   // row ranges per column block
+  float* partial = rl.alloc((size_t)S * N);
+  launch_k(colsum_partial_kernel<TA>, dim3((unsigned)cdiv(N, 256), (unsigned)S), 128, 0, st, dy, ldy, partial, R, N, cdiv(R, S));
+  DG_LAUNCH_CHECK();
+  rl.add(partial, db, S, N, N);
+}
+
 static unsigned grid1d(int64_t n, int bs = 256) {
   int64_t g = cdiv(n, bs);
   if (g > 148 * 16) g = 148 * 16;
@@ -281,7 +291,7 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
     // one block's worth of queued reductions (split-K dW of qkv / out / both MLP matrices + LayerNorm partials)
     const int64_t per_block = (int64_t)32 * (4 * d.inner * d.D + 2 * d.D * d.M) + (int64_t)8 * d.D * 148 * 4 + 4 * d.M + 4096;
     // + the reductions outside the blocks (rms gain, pos embedding, patch dW split-K + bias)
-    c.misc_floats = (size_t)(64 * d.D + (int64_t)32 * d.N * d.D + (int64_t)32 * d.D * d.pd + 128 * d.D + 1024);
+    c.misc_floats = (size_t)(64 * d.D + (int64_t)32 * d.N * d.D + (int64_t)80 * d.D * d.pd + 256 * d.D + 1024);
     c.partial_floats = (size_t)std::max<int64_t>(mx * 32, per_block) + c.misc_floats;
     c.partial = cv.take<float>(c.partial_floats);
   }
@@ -745,18 +755,26 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
       DG_LAUNCH_CHECK();
     }
   }
-  // patch-weight gradient dW = dXp^T Pm: the im2col-free forward never wrote the patch matrix, so unless the caller made
-  // one for these frames (the update does, once per frame batch) it is formed here
+  // patch-weight gradient dW = dXp^T patches.  bf16 path: no patch matrix exists (the forward is im2col-free); the
+  // weight-gradient kernel rebuilds the frame tiles in shared memory as its MN-major operand (patch_tc.cuh)
+  bool patch_dw_done = false;
 #ifdef DGVIT_WITH_TC
   if constexpr (std::is_same<A, bf16>::value) {
-    if (!c.Pm_ext && patch::eligible(net.cfg, img, WSel<A>::w(net, L.patch_w), c.L[0].Xn1)) {
+    if (img && patch::g_dw_enabled && patch::eligible(net.cfg, img, WSel<A>::w(net, L.patch_w), c.L[0].Xn1) && ((((uintptr_t)c.dXp) & 15) == 0)) {
+      const int64_t n_tok = (int64_t)d.B * d.P;
+      ProfScope ps_all(PROF_GEMM_ALL, 2.0 * n_tok * d.D * d.pd, 0.0, st);
+      patch::bwd_w(net.cfg, img, (const bf16*)c.dXp, n_tok, G + L.patch_w, rl_misc, st);
+      bias_grad_colsum<A>(c.dXp, d.D, G + L.patch_b, n_tok, d.D, rl_misc, st);
+      patch_dw_done = true;
+    } else if (!c.Pm_ext && patch::eligible(net.cfg, img, WSel<A>::w(net, L.patch_w), c.L[0].Xn1)) {
       DG_REQUIRE(img != nullptr, "trunk_backward: frames needed to rebuild the patch matrix");
       launch_patchify<A>(img, c.Pm, d.B, d, net.cfg, st);
     }
   }
 #endif
-  linear_bwd_w<A, A>(c.dXp, c.Pm_ext ? c.Pm_ext : c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st, -1,
-                     -1, &rl_misc);
+  if (!patch_dw_done)
+    linear_bwd_w<A, A>(c.dXp, c.Pm_ext ? c.Pm_ext : c.Pm, G + L.patch_w, G + L.patch_b, (int64_t)d.B * d.P, d.D, d.pd, c.partial, st, -1,
+                       -1, &rl_misc);
   rl_misc.launch(st);
   if (side && have_mr) DG_CUDA(cudaStreamWaitEvent(st, sd->mr, 0));     // join
 }
@@ -1094,15 +1112,16 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   // (s' on the caller's stream, s on the first forked stream; the second forked stream starts after the latter)
   DG_CUDA(cudaEventRecord(f.fork, st));
   DG_CUDA(cudaStreamWaitEvent(f.aux[0], f.fork, 0));
-  launch_patchify<A>(b.obs, w.actor_s.t.Pm, da.B, da, s.actor.cfg, f.aux[0]);
-  DG_CUDA(cudaEventRecord(f.fork2, f.aux[0]));
-  DG_CUDA(cudaStreamWaitEvent(f.aux[1], f.fork2, 0));
-  bool fused_embed = false;     // im2col-free forward: s' needs no patch matrix at all, s only for the two patch-weight gradients
+  bool fused_embed = false;     // im2col-free patch embedding and patch-weight gradient: no patch matrix at all
 #ifdef DGVIT_WITH_TC
   if constexpr (std::is_same<A, bf16>::value)
-    fused_embed = patch::eligible(s.actor.cfg, b.next_obs, WSel<A>::w(s.actor, La.patch_w), w.actor_tmp.t.L[0].Xn1) &&
+    fused_embed = patch::g_dw_enabled &&
+                  patch::eligible(s.actor.cfg, b.next_obs, WSel<A>::w(s.actor, La.patch_w), w.actor_tmp.t.L[0].Xn1) &&
                   patch::eligible(s.actor.cfg, b.obs, WSel<A>::w(s.critic, Lc.patch_w), w.actor_s.t.L[0].Xn1);
 #endif
+  if (!fused_embed) launch_patchify<A>(b.obs, w.actor_s.t.Pm, da.B, da, s.actor.cfg, f.aux[0]);
+  DG_CUDA(cudaEventRecord(f.fork2, f.aux[0]));
+  DG_CUDA(cudaStreamWaitEvent(f.aux[1], f.fork2, 0));
   if (!fused_embed) launch_patchify<A>(b.next_obs, w.actor_tmp.t.Pm, d.B, d, s.actor.cfg, st);
   w.actor_s.t.Pm_ext = w.actor_s.t.Pm; w.critic_s.t.Pm_ext = w.actor_s.t.Pm;
   w.actor_tmp.t.Pm_ext = w.actor_tmp.t.Pm; w.critic_tmp.t.Pm_ext = w.actor_tmp.t.Pm;
@@ -1306,6 +1325,7 @@ int dgvit_set_option(const char* name, int value) {
     else if (!strcmp(name, "attn_bwd2")) attn::g_bwd2_enabled = value != 0;
     else if (!strcmp(name, "attn_long")) attnl::g_enabled = value != 0;
     else if (!strcmp(name, "patch_fused")) patch::g_enabled = value != 0;
+    else if (!strcmp(name, "patch_dw")) patch::g_dw_enabled = value != 0;
     else if (!strcmp(name, "mlp_split")) mlp::g_split_enabled = value != 0;
     else if (!strcmp(name, "mlp_front")) mlp::g_front_enabled = value != 0;
     else if (!strcmp(name, "mlp_h16")) mlp::g_h16_enabled = value != 0;

@@ -52,9 +52,10 @@ def weights_init_(m):
 # --------------------------------------------------------------------------- containers
 class _Patchify(nn.Module):
     """Placeholder for einops ``Rearrange('b (h p1) (w p2) -> b (h w) (p1 p2)')`` so that the
-    patch Linear keeps the key ``to_patch_embedding.1`` (vn/GoalFormer.py:137-139).  The
-    rearrangement itself happens on the device inside the patch-embedding stage (``csrc/dgvit.cu``,
-    K1): no permuted copy of the frame is made on the Python side."""
+    patch Linear keeps the key ``to_patch_embedding.1`` (vn/GoalFormer.py:137-139).  In the bf16 path the
+    rearrangement is the shared-memory address of the patch-embedding kernels (``csrc/patch_tc.cuh``: frame rows ->
+    swizzled UMMA tiles, forward and weight gradient; no patch matrix in HBM); the fp32 parity path materialises the
+    patch matrix with ``patchify_kernel``."""
 
     def __init__(self, p1, p2):
         super().__init__()
