@@ -363,18 +363,24 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       static_assert(!FRONT || FWD_EPI_WARPS == 16, "front epilogue: 4 lane quadrants x 4 column groups");
       // x_m = o W_out^T + b_out + x_a (fp32) ; LayerNorm-2 -> bf16 tile that is the A operand of every GEMM1.
       // x_m also stays in shared memory (over the dead W_out tile) as the residual of the output stage.
+      // residual row and bias are fetched BEFORE the wait for the out-projection accumulator: their global-load latency
+      // runs under the TMA of the attention-output tile and the 16 MMAs instead of after them
+      const int row = row0 + lane;
+      const bool ok = row < a.M;
+      float4 rr4[4], bb4[4];
+      if (ok) {
+        const float* R = a.xa + (int64_t)row * a.ldxa + grp * 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { rr4[i] = reinterpret_cast<const float4*>(R)[i]; bb4[i] = __ldg(reinterpret_cast<const float4*>(a.ob + grp * 16) + i); }
+      }
       mbar_wait(front_done, 0);
       tc_fence_after();
       float y[16];
       tmem_ld16(tmem_base + T_Y + grp * 16 + lane_off, y);
-      const int row = row0 + lane;
-      const bool ok = row < a.M;
       if (ok) {
-        const float* R = a.xa + (int64_t)row * a.ldxa + grp * 16;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 r4 = reinterpret_cast<const float4*>(R)[i];
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ob + grp * 16) + i);
+          const float4 r4 = rr4[i], b4 = bb4[i];
           y[4 * i] += b4.x + r4.x; y[4 * i + 1] += b4.y + r4.y; y[4 * i + 2] += b4.z + r4.z; y[4 * i + 3] += b4.w + r4.w;
         }
       } else {
