@@ -60,7 +60,7 @@ class ActorIO(C.Structure):
     _fields_ = [("img", c_f_p), ("pstate", c_f_p), ("eps", c_f_p), ("action_scale", c_f_p),
                 ("action_bias", c_f_p), ("drop", Drop), ("sample_offset", C.c_int32),
                 ("mean", c_f_p), ("log_std", c_f_p), ("action", c_f_p), ("log_prob", c_f_p),
-                ("mean_t", c_f_p), ("eps_out", c_f_p)]
+                ("mean_t", c_f_p), ("eps_out", c_f_p), ("advance_rng", C.c_int32)]
 
 
 class ActorGrad(C.Structure):

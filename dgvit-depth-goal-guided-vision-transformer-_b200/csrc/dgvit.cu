@@ -840,6 +840,7 @@ static void actor_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
   s.sample_offset = io.sample_offset;
   s.mean_out = io.mean; s.log_std = io.log_std; s.action = io.action; s.log_prob = io.log_prob; s.mean_t = io.mean_t;
   s.eps_out = c.eps;
+  s.rng_bump = (io.advance_rng && io.drop.rng_state && d.B <= 128) ? const_cast<uint64_t*>(io.drop.rng_state) : nullptr;
   launch_k(actor_sample_kernel, (unsigned)cdiv(d.B, 128), 128, 0, st, s);
   DG_LAUNCH_CHECK();
   if (io.eps_out)

@@ -761,6 +761,7 @@ struct SampleArgs {
   int64_t sample_offset;
   float *mean_out, *log_std, *action, *log_prob, *mean_t, *eps_out;
   int B, na;
+  uint64_t* rng_bump;     // non-null: advance the RNG counter once this (last) kernel of the call has made its draws
 };
 __global__ void actor_sample_kernel(SampleArgs a) {
   pdl_wait();
@@ -795,6 +796,11 @@ __global__ void actor_sample_kernel(SampleArgs a) {
     lp -= logf(sc * (1.0f - y * y) + 1e-6f);
   }
   if (a.log_prob) a.log_prob[b] = lp;
+  // (single-block launches only — the batch-1 act loop: every draw of this call has been made when thread 0 gets here)
+  if (a.rng_bump && blockIdx.x == 0 && gridDim.x == 1) {
+    __syncthreads();
+    if (threadIdx.x == 0) a.rng_bump[1] += 1;
+  }
 }
 
 struct SampleBwdArgs {

@@ -554,10 +554,22 @@ class GoTPolicy(_ArenaModule):
             st = self._build_act_graph(key)
         st["img_np"][...] = istate.reshape(1, c.img_h, c.img_w)
         st["ps_np"][...] = np.asarray(pstate, dtype=np.float32).reshape(1, c.n_pstate)
+        self._sync_shadow(st)
         st["graph"].replay()
         st["done"].record()
         st["done"].synchronize()
         return (st["mean_t_np"] if evaluate else st["action_np"])[0].copy()
+
+    def _sync_shadow(self, st):
+        """The 16-bit operand copies follow the fp32 arena: the library's own optimizer kernels keep them current; a torch-side
+        in-place write (torch.optim step, load_state_dict, ...) bumps the arena's version counter and is caught here — outside
+        the replayed graph, so the control loop does not pay a 1.4 M-element pass per action."""
+        if self.precision != "bf16":
+            return
+        v = self._arena._version
+        if st.get("shadow_version") != v:
+            self.refresh_shadow()
+            st["shadow_version"] = v
 
     def _build_act_graph(self, key):
         c = self._cfg
@@ -587,22 +599,21 @@ class GoTPolicy(_ArenaModule):
         io = L.ActorIO(img=src("img"), pstate=src("ps"), eps=None, action_scale=st["scale"].data_ptr(),
                        action_bias=st["bias"].data_ptr(), drop=drop, sample_offset=0, mean=st["mean"].data_ptr(),
                        log_std=st["log_std"].data_ptr(), action=src("action"), log_prob=st["log_prob"].data_ptr(),
-                       mean_t=src("mean_t"), eps_out=None)
+                       mean_t=src("mean_t"), eps_out=None, advance_rng=1)     # fresh rsample / dropout stream per call
         net = self.net_struct()
+        st["shadow_version"] = -1
 
         def run():
             if not zc:
                 st["img"].copy_(st["img_host"], non_blocking=True)
                 st["ps"].copy_(st["ps_host"], non_blocking=True)
-            self._rng_state[1] += 1            # fresh rsample / dropout stream per call
-            if self.precision == "bf16":
-                self.refresh_shadow()
             L.check(L.lib().dgvit_actor_forward(C.byref(net), C.byref(io), 1, self._precision_code(), 0,
                                                 st["ws"].data_ptr(), st["ws"].numel(), _stream(dev)), "actor_forward")
             if not zc:
                 st["action_host"].copy_(st["action"], non_blocking=True)
                 st["mean_t_host"].copy_(st["mean_t"], non_blocking=True)
 
+        self._sync_shadow(st)
         run()                                   # eager warm-up (lazy kernel attributes, tensor-map entry point)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()

@@ -116,6 +116,8 @@ typedef struct dgvit_actor_io {
   float* log_prob; /* [B, 1] */
   float* mean_t;   /* [B, n_act]  tanh(mean)*scale+bias */
   float* eps_out;  /* [B, n_act]  the eps actually used (needed by backward) */
+  int32_t advance_rng; /* 1 (B <= 128 only): the call's last kernel advances the counter of drop.rng_state once all its
+                          draws are made — the batch-1 act loop replays one graph and needs a fresh stream per call */
 } dgvit_actor_io;
 
 typedef struct dgvit_actor_grad {
