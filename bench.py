@@ -391,9 +391,11 @@ def run_ours(args):
         act["path"] = "SAC.choose_action: pinned host frame -> CUDA graph (kernels read the pinned frame and write the action to pinned host memory: zero-copy) -> sync"
     barrier()
 
-    dp_parity, c4, c5 = None, None, None
+    dp_parity, c4, c5, next_rows = None, None, None, None
     if not args.no_extras:
         dp_parity, c4, c5 = run_extras(args, ag, dev, rank, world, dist, barrier)
+        if world == 1:
+            next_rows = run_next_rows(dev)
 
     if rank != 0:
         teardown(ag, dist)
@@ -522,7 +524,7 @@ def run_ours(args):
                             l2="inputs gathered each step by random index from a %.2f GB device replay store (> 126 MB L2)"
                                % (ag.replay_buffer.obs.numel() * 4 / 1e9)),
                 roofline=roof, whole_step=whole, cpu_baseline=cpu,
-                value_sustained=sustained, dp_parity=dp_parity, c4=c4, c5=c5,
+                value_sustained=sustained, dp_parity=dp_parity, c4=c4, c5=c5, next_rows=next_rows,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=16),
                 act_latency=act, gpu_launches=int(launches), clocks=clocks, losses=losses)
     print(json.dumps(line), flush=True)
@@ -540,6 +542,56 @@ def teardown(ag, dist):
         dist.destroy_process_group()
     finally:
         os._exit(0)
+
+
+def run_next_rows(dev):
+    """SURVEY §8f "next" rows, measured through the agent API on one GPU (informational; B = 256, bf16):
+       f1  SAC.learn with the CNN twin-Q critic (the reference's shipped default critic_type), module path;
+       f2  SAC.learn_guidence (agent + expert minibatch, guidance / engage imitation rows in the same fused update);
+       f4  replay write path: store_transition one at a time (control loop) and a batched append (demonstration ingest)."""
+    import numpy as np
+    import dgvit_b200 as dg
+    out = {}
+
+    def rate(fn, n, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize(dev)
+        return n / (time.perf_counter() - t0)
+    try:
+        a1 = dg.SAC(2, 2, "GaussianTransformer", "CNN", False, False, False, SEED, BUFFER_SIZE=4096, precision="bf16", device=dev,
+                    **HP, **PRESET)
+        a1.replay_buffer.fill_synthetic(4096, seed=SEED)
+        out["f1_cnn_critic_learn"] = dict(value=256 * rate(lambda: a1.learn(256), 10), unit=UNIT,
+                                          what="SAC.learn(256), QNetwork critic + DGViT actor, autograd-glued module path")
+        del a1
+    except Exception as e:
+        out["f1_cnn_critic_learn"] = dict(error=repr(e)[:200])
+    try:
+        a2 = dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, True, SEED, BUFFER_SIZE=4096, buffer_size_expert=2048,
+                    precision="bf16", device=dev, **HP, **PRESET)
+        a2.replay_buffer.fill_synthetic(4096, seed=SEED)
+        a2.replay_buffer.engage_host[:4096:7] = 1.0
+        a2.replay_buffer_expert.fill_synthetic(2048, seed=SEED + 1)
+        out["f2_learn_guidence"] = dict(value=256 * rate(lambda: a2.learn_guidence(False, 256), 10), unit=UNIT,
+                                        what="SAC.learn_guidence(batch 256 + expert share + guidance / engage rows), one fused update per call")
+        rs = np.random.RandomState(0)
+        s0, s1 = rs.rand(128, 160, 1).astype(np.float32), rs.rand(128, 160, 1).astype(np.float32)
+        one = lambda: a2.store_transition(s0, np.zeros(2, np.float32), np.zeros(2, np.float32), np.zeros(2, np.float32), 0.5, s1, 0.0, None, 0)
+        obs = rs.rand(512, 128, 160).astype(np.float32)
+        many = lambda: a2.replay_buffer.add(obs, np.zeros((512, 2), np.float32), np.zeros((512, 2), np.float32),
+                                            np.zeros((512, 2), np.float32), np.zeros(512, np.float32), obs)
+        out["f4_store_transition"] = dict(single_per_s=rate(one, 200), batched_per_s=512 * rate(many, 5, warm=1), unit="transitions/s",
+                                          what="packed pinned record -> H2D -> one scatter kernel; host-side packing included")
+        del a2
+    except Exception as e:
+        out["f2_f4"] = dict(error=repr(e)[:200])
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_extras(args, ag, dev, rank, world, dist, barrier):
