@@ -27,7 +27,10 @@ using attn::tmem_ld16_nowait;
 using attn::tmem_ld_wait;
 
 constexpr int MAX_TILES = 3;                 // key / query tiles of 128 rows (N <= 384)
-constexpr int THREADS = 64 + 128;            // TMA warp, MMA warp, one softmax warpgroup (thread = row of the tile)
+constexpr int SW = 8;                        // softmax warps: two threads per row of the tile, each owning every other
+                                             // 64-column block of the scores (one warpgroup = one warp per scheduler)
+constexpr int THREADS = 64 + SW * 32;        // TMA warp, MMA warp, softmax warps
+__device__ __forceinline__ void sm_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SW * 32) : "memory"); }
 
 struct LongArgs {
   int B, N, H, KP, NT;       // KP = N rounded up to 16 (key columns multiplied), NT = ceil(N / 128)
@@ -44,7 +47,8 @@ struct LongArgs {
 namespace f {
 constexpr int OFF_K = 0, OFF_V = MAX_TILES * TILE, OFF_Q = 2 * MAX_TILES * TILE;   // Q: ring of 2 tiles
 constexpr int OFF_P = OFF_Q + 2 * TILE;                                             // 2 chunk buffers x 2 tiles
-constexpr int OFF_BAR = OFF_P + 4 * TILE;
+constexpr int OFF_X = OFF_P + 4 * TILE;      // [2][128][2] floats: row max / row sum halves of the two threads of a row
+constexpr int OFF_BAR = OFF_X + 2048;
 constexpr int TOTAL = OFF_BAR + 256 + 1024;
 static_assert(TOTAL <= 232448, "smem budget");
 constexpr uint32_t T_O = 448;               // S: columns [0, KP) ; O: [448, 512)
@@ -64,8 +68,9 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const LongArgs a
   uint64_t* p_ready = s_full + 1;      // [2] (4 warps)
   uint64_t* p_free = p_ready + 2;      // [2]
   uint64_t* o_full = p_free + 2;       // 1
-  uint64_t* t_free = o_full + 1;       // 1 (4 warps): S / O accumulators drained
-  uint32_t* tmem_slot = (uint32_t*)(t_free + 1);
+  uint64_t* s_free = o_full + 1;       // 1 (4 warps): S accumulator read for the last time (end of softmax pass 2)
+  uint64_t* o_free = s_free + 1;       // 1 (4 warps): O accumulator drained
+  uint32_t* tmem_slot = (uint32_t*)(o_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inner = a.H * DH;
@@ -74,8 +79,8 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const LongArgs a
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&p_free[i], 1); }
-    mbar_init(s_full, 1); mbar_init(o_full, 1); mbar_init(t_free, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&p_ready[i], SW); mbar_init(&p_free[i], 1); }
+    mbar_init(s_full, 1); mbar_init(o_full, 1); mbar_init(s_free, SW); mbar_init(o_free, SW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -115,7 +120,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const LongArgs a
         for (int t = 0; t < a.NT; ++t, ++qn, ++tn) {
           const int s = qn & 1;
           mbar_wait(&q_full[s], (qn >> 1) & 1);
-          mbar_wait(t_free, (tn & 1) ^ 1);
+          mbar_wait(s_free, (tn & 1) ^ 1);        // S of the next query tile is formed while the threads still store O
           tc_fence_after();
           const uint64_t qd = make_smem_desc(smem_u32(smem + OFF_Q + s * TILE), 16, 1024);
           for (int c = 0; c < NC; ++c) {
@@ -132,6 +137,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const LongArgs a
             const int pb = c & 1;
             const int ks = min(128, a.KP - 128 * c) / 16;
             mbar_wait(&p_ready[pb], pn[pb] & 1);
+            if (c == 0) mbar_wait(o_free, (tn & 1) ^ 1);    // the previous tile's O has been read
             tc_fence_after();
             for (int k = 0; k < ks; ++k) {
               const uint64_t pd = make_smem_desc(sp + pb * 2 * TILE + (k >> 2) * TILE + (k & 3) * 32, 16, 1024);
@@ -147,11 +153,14 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const LongArgs a
       }
     }
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3, hh = (warp - 2) >> 2;       // TMEM lane quadrant ; which 64-column blocks of a row
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const float sl2 = a.scale * 1.44269504088896f;
+    float* xmax = reinterpret_cast<float*>(smem + OFF_X);
+    float* xsum = xmax + 256;
     uint32_t tn = 0, pn[2] = {0, 0};
+    const int nkb = a.KP / 16;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int b = it / a.H, h = it % a.H;
       for (int t = 0; t < a.NT; ++t, ++tn) {
@@ -160,29 +169,35 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const LongArgs a
         mbar_wait(s_full, tn & 1);
         tc_fence_after();
         const uint32_t ts = tmem_base + lane_off;
-        // pass 1: row maximum over the N real key columns
+        // pass 1: row maximum over the N real key columns (this thread: the 64-column blocks hh, hh + 2, ...)
         float mx = -INFINITY;
-        for (int kb = 0; kb < a.KP / 16; kb += 2) {
-          uint32_t s0[16], s1[16];
-          tmem_ld16_nowait(ts + 16 * kb, s0);
-          if (kb + 1 < a.KP / 16) tmem_ld16_nowait(ts + 16 * (kb + 1), s1);
+        for (int k4 = hh * 4; k4 < nkb; k4 += 8) {
+          uint32_t s0[16], s1[16], s2[16], s3[16];
+          tmem_ld16_nowait(ts + 16 * k4, s0);
+          if (k4 + 1 < nkb) tmem_ld16_nowait(ts + 16 * (k4 + 1), s1);
+          if (k4 + 2 < nkb) tmem_ld16_nowait(ts + 16 * (k4 + 2), s2);
+          if (k4 + 3 < nkb) tmem_ld16_nowait(ts + 16 * (k4 + 3), s3);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) if (16 * kb + i < a.N) mx = fmaxf(mx, __uint_as_float(s0[i]));
-          if (kb + 1 < a.KP / 16) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) if (16 * (kb + 1) + i < a.N) mx = fmaxf(mx, __uint_as_float(s1[i]));
+          for (int i = 0; i < 16; ++i) {
+            if (16 * k4 + i < a.N) mx = fmaxf(mx, __uint_as_float(s0[i]));
+            if (k4 + 1 < nkb && 16 * (k4 + 1) + i < a.N) mx = fmaxf(mx, __uint_as_float(s1[i]));
+            if (k4 + 2 < nkb && 16 * (k4 + 2) + i < a.N) mx = fmaxf(mx, __uint_as_float(s2[i]));
+            if (k4 + 3 < nkb && 16 * (k4 + 3) + i < a.N) mx = fmaxf(mx, __uint_as_float(s3[i]));
           }
         }
+        xmax[r * 2 + hh] = mx;
+        sm_bar();
+        mx = fmaxf(xmax[r * 2], xmax[r * 2 + 1]);
         const float mb = mx * sl2;
         float sum = 0.f;
-        // pass 2: P chunk by chunk
+        // pass 2: P chunk by chunk (this thread: 64 of the chunk's 128 columns)
         for (int c = 0; c < NC; ++c) {
           const int pb = c & 1;
           const int nb = min(128, a.KP - 128 * c) / 16;
           uint8_t* P = smem + OFF_P + pb * 2 * TILE;
           mbar_wait(&p_free[pb], (pn[pb] & 1) ^ 1);        // the MMAs that read this buffer two chunks ago have retired
-          for (int kb = 0; kb < nb; ++kb) {
+          for (int kb = hh * 4; kb < min(nb, hh * 4 + 4); ++kb) {
             uint32_t sr[16];
             tmem_ld16_nowait(ts + 128 * c + 16 * kb, sr);
             tmem_ld_wait();
@@ -205,27 +220,33 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const LongArgs a
           if (lane == 0) mbar_arrive(&p_ready[pb]);
           ++pn[pb];
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);              // S has been read for the last time
+        xsum[r * 2 + hh] = sum;
+        sm_bar();
+        sum = xsum[r * 2] + xsum[r * 2 + 1];
         mbar_wait(o_full, tn & 1);
         tc_fence_after();
         const float inv = valid ? 1.0f / sum : 0.f;
-        uint32_t orr[4][16];
+        uint32_t orr[2][16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(ts + T_O + 16 * c, orr[c]);
+        for (int c = 0; c < 2; ++c) tmem_ld16_nowait(ts + T_O + hh * 32 + 16 * c, orr[c]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(t_free);              // S and O are in registers: the next query tile may start
+        if (lane == 0) mbar_arrive(o_free);              // O is in registers: the next tile's P V products may start
         if (valid) {
-          bf16* dst = a.O + ((int64_t)b * a.N + row) * inner + h * DH;
+          bf16* dst = a.O + ((int64_t)b * a.N + row) * inner + h * DH + hh * 32;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             uint32_t w[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) w[i] = pack2(__uint_as_float(orr[c][2 * i]) * inv, __uint_as_float(orr[c][2 * i + 1]) * inv);
             reinterpret_cast<uint4*>(dst + 16 * c)[0] = make_uint4(w[0], w[1], w[2], w[3]);
             reinterpret_cast<uint4*>(dst + 16 * c)[1] = make_uint4(w[4], w[5], w[6], w[7]);
           }
-          if (a.lse) a.lse[((int64_t)b * a.H + h) * a.N + row] = mb + log2f(sum);
+          if (hh == 0 && a.lse) a.lse[((int64_t)b * a.H + h) * a.N + row] = mb + log2f(sum);
         }
       }
     }
@@ -270,8 +291,8 @@ attn_bwd_dq_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmdO);
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1); mbar_init(qdo_full, 1); mbar_init(qdo_empty, 1);
-    mbar_init(sdp_full, 1); mbar_init(sdp_free, 4); mbar_init(dq_full, 1); mbar_init(dq_free, 4);
-    for (int i = 0; i < 2; ++i) { mbar_init(&ds_ready[i], 4); mbar_init(&ds_free[i], 1); }
+    mbar_init(sdp_full, 1); mbar_init(sdp_free, SW); mbar_init(dq_full, 1); mbar_init(dq_free, SW);
+    for (int i = 0; i < 2; ++i) { mbar_init(&ds_ready[i], SW); mbar_init(&ds_free[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -324,7 +345,6 @@ attn_bwd_dq_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         mbar_wait(kv_full, kvn & 1);
         for (int t = 0; t < a.NT; ++t, ++tn) {
           mbar_wait(qdo_full, tn & 1);
-          mbar_wait(dq_free, (tn & 1) ^ 1);
           tc_fence_after();
           issue_sdp(0);
           for (int c = 0; c < NC; ++c) {
@@ -332,6 +352,7 @@ attn_bwd_dq_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             const int db = c & 1;
             const int ks = min(128, a.KP - 128 * c) / 16;
             mbar_wait(&ds_ready[db], dn[db] & 1);
+            if (c == 0) mbar_wait(dq_free, (tn & 1) ^ 1);      // the previous tile's dQ has been read
             tc_fence_after();
             for (int k = 0; k < ks; ++k) {       // dQ[128 x 64] += dS_c[:, 16k..] K_c[16k.., :]
               const uint64_t ad = make_smem_desc(sds + db * 2 * TILE + (k >> 2) * TILE + (k & 3) * 32, 16, 1024);
@@ -348,7 +369,7 @@ attn_bwd_dq_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       }
     }
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3, hh = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const float sl2 = a.scale * 1.44269504088896f;
@@ -375,22 +396,28 @@ attn_bwd_dq_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           }
           const int64_t si = ((int64_t)b * a.H + h) * a.N + row;
           lse = a.lse[si];
-          a.delta[si] = delta;
+          if (hh == 0) a.delta[si] = delta;
         }
         const uint32_t ts = tmem_base + lane_off;
         for (int c = 0; c < NC; ++c, ++cn) {
           const int db = c & 1;
           const int nb = min(128, a.KP - 128 * c) / 16;
+          const int kb0 = hh * 4, kb1 = min(nb, hh * 4 + 4);      // this thread's 64 columns of the chunk
           uint8_t* dS = smem + OFF_DS + db * 2 * TILE;
           mbar_wait(sdp_full, cn & 1);
           tc_fence_after();
           mbar_wait(&ds_free[db], (dn[db] & 1) ^ 1);
-          for (int kb = 0; kb < nb; ++kb) {
+          if (kb0 >= kb1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sdp_free);
+          }
+          for (int kb = kb0; kb < kb1; ++kb) {
             uint32_t sr[16], dpr[16];
             tmem_ld16_nowait(ts + T_S + 16 * kb, sr);
             tmem_ld16_nowait(ts + T_DP + 16 * kb, dpr);
             tmem_ld_wait();
-            if (kb == nb - 1) {
+            if (kb == kb1 - 1) {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(sdp_free);           // S_c / dP_c are in registers: chunk c+1 may overwrite them
@@ -415,17 +442,17 @@ attn_bwd_dq_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         }
         mbar_wait(dq_full, tn & 1);
         tc_fence_after();
-        uint32_t orr[4][16];
+        uint32_t orr[2][16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(ts + T_DQ + 16 * c, orr[c]);
+        for (int c = 0; c < 2; ++c) tmem_ld16_nowait(ts + T_DQ + hh * 32 + 16 * c, orr[c]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_free);
         if (valid) {
-          bf16* dst = a.dQKV + ((int64_t)b * a.N + row) * (3 * inner) + h * DH;
+          bf16* dst = a.dQKV + ((int64_t)b * a.N + row) * (3 * inner) + h * DH + hh * 32;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             uint32_t u[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) u[i] = pack2(__uint_as_float(orr[c][2 * i]), __uint_as_float(orr[c][2 * i + 1]));
@@ -477,8 +504,8 @@ attn_bwd_dkdv_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmdO);
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(sdp_free, 4); mbar_init(pds_ready, 4); mbar_init(pds_free, 1);
-    mbar_init(out_full, 1); mbar_init(out_free, 4);
+    mbar_init(sdp_full, 1); mbar_init(sdp_free, SW); mbar_init(pds_ready, SW); mbar_init(pds_free, 1);
+    mbar_init(out_full, 1); mbar_init(out_free, SW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -520,7 +547,6 @@ attn_bwd_dkdv_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
         const int nk = min(128, a.KP - 128 * kt);
         const uint32_t idesc_s = make_idesc(128, nk, false, false);
         mbar_wait(kv_full, kvn & 1);
-        mbar_wait(out_free, (on & 1) ^ 1);
         auto issue_sdp = [&](uint32_t qi) {                // S = Q_t K^T ; dP = dO_t V^T  (query tile in ring stage qi & 1)
           const int s = qi & 1;
           mbar_wait(&qdo_full[s], (qi >> 1) & 1);
@@ -540,6 +566,7 @@ attn_bwd_dkdv_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
           if (t + 1 < a.NT) issue_sdp(qn + 1);
           const int s = qn & 1;
           mbar_wait(pds_ready, pn & 1);
+          if (t == 0) mbar_wait(out_free, (on & 1) ^ 1);       // the previous item's dK / dV have been read
           tc_fence_after();
           const uint32_t sq = smem_u32(smem + OFF_QDO + s * 2 * TILE), sdo = sq + TILE;
 #pragma unroll
@@ -557,7 +584,7 @@ attn_bwd_dkdv_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       }
     }
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3, hh = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const float sl2 = a.scale * 1.44269504088896f;
@@ -568,6 +595,7 @@ attn_bwd_dkdv_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       const int kt = it % a.NT, bh = it / a.NT;
       const int b = bh / a.H, h = bh % a.H;
       const int nb = min(128, a.KP - 128 * kt) / 16;
+      const int kb0 = hh * 4, kb1 = min(nb, hh * 4 + 4);     // this thread's 64 key columns of the tile
       const uint32_t ts = tmem_base + lane_off;
       for (int t = 0; t < a.NT; ++t, ++sn, ++pn) {
         const int row = t * 128 + r;                       // query row of this thread
@@ -581,12 +609,17 @@ attn_bwd_dkdv_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
         mbar_wait(sdp_full, sn & 1);
         tc_fence_after();
         mbar_wait(pds_free, (pn & 1) ^ 1);                 // the MMAs of the previous query tile have consumed the P / dS tiles
-        for (int kb = 0; kb < nb; ++kb) {
+        if (kb0 >= kb1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdp_free);
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
           uint32_t sr[16], dpr[16];
           tmem_ld16_nowait(ts + T_S + 16 * kb, sr);
           tmem_ld16_nowait(ts + T_DP + 16 * kb, dpr);
           tmem_ld_wait();
-          if (kb == nb - 1) {
+          if (kb == kb1 - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(sdp_free);
@@ -612,31 +645,26 @@ attn_bwd_dkdv_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
         __syncwarp();
         if (lane == 0) mbar_arrive(pds_ready);
       }
-      // dK / dV rows of key (kt * 128 + r)
+      // dK (threads hh = 0) / dV (hh = 1) row of key (kt * 128 + r)
       mbar_wait(out_full, on & 1);
       tc_fence_after();
       const int key = kt * 128 + r;
-      bf16* dst = a.dQKV + ((int64_t)b * a.N + key) * (3 * inner) + inner + h * DH;
-#pragma unroll 1
-      for (int w = 0; w < 2; ++w) {          // dK, dV
-        uint32_t orr[4][16];
+      bf16* dst = a.dQKV + ((int64_t)b * a.N + key) * (3 * inner) + (1 + hh) * inner + h * DH;
+      uint32_t orr[4][16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld16_nowait(ts + T_DK + w * 64 + 16 * c, orr[c]);
-        tmem_ld_wait();
-        if (w == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(out_free);
-        }
-        if (key < a.N) {
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(ts + T_DK + hh * 64 + 16 * c, orr[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_free);
+      if (key < a.N) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t u[8];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t u[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) u[i] = pack2(__uint_as_float(orr[c][2 * i]), __uint_as_float(orr[c][2 * i + 1]));
-            reinterpret_cast<uint4*>(dst + w * inner + 16 * c)[0] = make_uint4(u[0], u[1], u[2], u[3]);
-            reinterpret_cast<uint4*>(dst + w * inner + 16 * c)[1] = make_uint4(u[4], u[5], u[6], u[7]);
-          }
+          for (int i = 0; i < 8; ++i) u[i] = pack2(__uint_as_float(orr[c][2 * i]), __uint_as_float(orr[c][2 * i + 1]));
+          reinterpret_cast<uint4*>(dst + 16 * c)[0] = make_uint4(u[0], u[1], u[2], u[3]);
+          reinterpret_cast<uint4*>(dst + 16 * c)[1] = make_uint4(u[4], u[5], u[6], u[7]);
         }
       }
     }

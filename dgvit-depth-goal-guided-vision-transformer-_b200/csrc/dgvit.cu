@@ -131,8 +131,9 @@ static void gemm(const GemmArgs& g, cudaStream_t st) {
 template <typename TA, typename TB, typename TC>
 static void linear_fwd(const TA* x, const TB* W, TC* y, int64_t R, int N, int K, int epi, const float* bias,
                        cudaStream_t st, const float* resid = nullptr, void* C2 = nullptr, int64_t ldc = -1,
-                       int64_t ldx = -1, int64_t ldr = -1) {
+                       int64_t ldx = -1, int64_t ldr = -1, int skip_pre = 0) {
   GemmArgs g;
+  g.skip_pre = skip_pre;
   g.M = (int)R; g.N = N; g.K = K;
   g.A = x; g.a_sm = ldx < 0 ? K : ldx; g.a_sk = 1;
   g.B = W; g.b_sk = 1; g.b_sn = K;
@@ -552,8 +553,9 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
       }
 #endif
     } else {
+      // (forward passes without a backward do not keep the pre-activation: half of the hidden-activation traffic)
       linear_fwd<A, A, A>(B_.Xn2, WSel<A>::w(net, b.fc1_w), B_.Hpre, R, d.M, d.D, EPI_BIAS_GELU2, P + b.fc1_b, st,
-                          nullptr, B_.Hact);
+                          nullptr, B_.Hact, -1, -1, -1, c.save ? 0 : 1);
       linear_fwd<A, A, float>(B_.Hact, WSel<A>::w(net, b.fc2_w), Xnext, R, d.D, d.M, EPI_BIAS_RESID, P + b.fc2_b, st,
                               B_.Xm);
     }

@@ -29,6 +29,7 @@ struct GemmArgs {
   void* C = nullptr;
   int64_t ldc = 0;
   int epi = EPI_NONE;
+  int skip_pre = 0;           // EPI_BIAS_GELU2: do not store the pre-activation C (forward passes nobody differentiates)
   const float* bias = nullptr;
   const float* resid = nullptr;
   int64_t ldr = 0;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
           stf((TC*)g.C2 + (int64_t)m * g.ldc + n, gelu_f(x));
         } break;
       }
-      stf(C + (int64_t)m * g.ldc + n, v);
+      if (!(g.epi == EPI_BIAS_GELU2 && g.skip_pre)) stf(C + (int64_t)m * g.ldc + n, v);
     }
   }
 }

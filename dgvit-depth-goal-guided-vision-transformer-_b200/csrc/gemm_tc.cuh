@@ -164,6 +164,7 @@ struct TcArgs {
   int trans_out;        // store C^T (element (m,n) at C[n*ldc + m])
   int epi;
   int tma_store;        // bf16 output without epilogue math leaves through TMA tile stores (tmC)
+  int skip_pre;         // EPI_BIAS_GELU2: the pre-activation output is not wanted
   void* C; void* C2; int64_t ldc;
   const float* bias; const float* resid; int64_t ldr;
   const void* aux; int64_t ldaux;
@@ -508,7 +509,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             break;
           case EPI_BIAS_GELU2:
             // first output: the pre-activation (saved for backward); then GELU in place
-            if (staged) {
+            if (g.skip_pre) {
+            } else if (staged) {
               if constexpr (std::is_same<TC, bf16>::value) stage_store(v, (bf16*)g.C, col);
             } else if (row_ok) {
               store_row32<TC>((TC*)g.C + (int64_t)row * g.ldc + col, v, nvalid);
@@ -736,7 +738,7 @@ static bool gemm_tc_try(const GemmArgs& g0, cudaStream_t st) {
     TcArgs a;
     a.debug = g_debug;
     a.M = g.M; a.N = g.N; a.K = g.K;
-    a.splitk = g.splitk; a.trans_out = trans_out; a.epi = g.epi;
+    a.splitk = g.splitk; a.trans_out = trans_out; a.epi = g.epi; a.skip_pre = g.skip_pre;
     a.C = g.C; a.C2 = g.C2; a.ldc = g.ldc; a.bias = g.bias; a.resid = g.resid; a.ldr = g.ldr;
     a.aux = g.aux; a.ldaux = g.ldaux; a.partial = g.partial;
     a.ln_gamma = g.ln_gamma; a.ln_beta = g.ln_beta; a.ln_out = (bf16*)g.ln_out; a.ln_mean = g.ln_mean; a.ln_rstd = g.ln_rstd;
