@@ -10,13 +10,19 @@ HDRS  := $(wildcard $(CSRC)/*.cuh) include/dgvit.h
 
 all: $(LIB)
 
-$(LIB): $(SRCS) $(HDRS)
-	$(NVCC) $(FLAGS) $(EXTRA) -DDGVIT_WITH_TC -shared -o $@ $(SRCS)
+OBJS  := $(PKG)/csrc/.obj/dgvit.o $(PKG)/csrc/.obj/depth.o
+
+$(PKG)/csrc/.obj/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(PKG)/csrc/.obj
+	$(NVCC) $(FLAGS) $(EXTRA) -DDGVIT_WITH_TC -c -o $@ $<
+
+$(LIB): $(OBJS)
+	$(NVCC) $(FLAGS) -shared -o $@ $(OBJS)
 
 # instrumented build for profiles/mlp_trace.py (never loaded by the package)
 trace: $(SRCS) $(HDRS)
 	$(NVCC) $(FLAGS) -DDGVIT_WITH_TC -DDGVIT_MLP_TRACE -shared -o $(PKG)/libdgvit_trace.so $(SRCS)
 
 clean:
-	rm -f $(LIB)
+	rm -rf $(LIB) $(PKG)/csrc/.obj
 .PHONY: all clean trace

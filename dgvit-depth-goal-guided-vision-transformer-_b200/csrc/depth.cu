@@ -22,10 +22,19 @@ __global__ void depth_minmax_kernel(const float* __restrict__ raw, float* __rest
   const float* src = raw + (int64_t)f * hw;
   float mn = INFINITY, mx = -INFINITY;
   const int64_t hw4 = hw >> 2;          // (H and W are multiples of 4, frames 16-byte aligned)
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(src)[i];
-    mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
-    mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw4; i += 4 * stride) {      // four loads in flight
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = i + u * stride;
+      v[u] = reinterpret_cast<const float4*>(src)[j < hw4 ? j : i];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      mn = fminf(fminf(mn, v[u].x), fminf(v[u].y, fminf(v[u].z, v[u].w)));
+      mx = fmaxf(fmaxf(mx, v[u].x), fmaxf(v[u].y, fmaxf(v[u].z, v[u].w)));
+    }
   }
   __shared__ float smn[32], smx[32];
 #pragma unroll
@@ -42,153 +51,105 @@ __global__ void depth_minmax_kernel(const float* __restrict__ raw, float* __rest
   }
 }
 
+// uniform in (0,1] from the top 23 bits, by bit assembly (no integer -> float conversion instruction)
+__device__ __forceinline__ float u01d(uint32_t x) { return 2.0f - __uint_as_float((x >> 9) | 0x3f800000u); }
+
 // N(0,1) draw of pixel gi: one Philox4x32 call serves the 4 pixels of an aligned group (two Box-Muller pairs)
 __device__ __forceinline__ float normal_at(const uint64_t* rng, int64_t gi) {
   uint32_t r[4];
   philox4x32(rng[0], (uint64_t)(gi >> 2), 0x6465707468000000ull | (rng[1] & 0xffffffffu), r);
   const int q = (int)(gi & 3);
-  const float rad = sqrtf(-2.0f * __logf(u01(r[q & 2])));
+  const float rad = sqrtf(-2.0f * __logf(u01d(r[q & 2])));
   float sn, cs;
-  __sincosf(6.283185307179586f * u01(r[(q & 2) + 1]), &sn, &cs);
+  __sincosf(6.283185307179586f * u01d(r[(q & 2) + 1]), &sn, &cs);
   return rad * ((q & 1) ? sn : cs);
 }
-__device__ __forceinline__ float noisy_px(const float* __restrict__ raw, const float* __restrict__ noise,
-                                          const uint64_t* rng, int64_t gi, double scale, double shift) {
-  // cv2.normalize(NORM_MINMAX, 0..255) then .astype(uint8) (truncation)
-  const float nrm = (float)((double)raw[gi] * scale + shift);
-  const float u8 = (float)(int)fminf(fmaxf(nrm, 0.f), 255.f);
-  const float nz = noise ? noise[gi] : 50.0f * normal_at(rng, gi);
-  return fminf(fmaxf(u8 + nz, 0.f), 255.f);
-}
-
-// pass 1: noisy image + horizontal 5-tap [1 4 6 4 1]/16, BORDER_REFLECT_101
-__global__ void depth_noise_hblur_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
-                                         const uint64_t* rng, const float* __restrict__ mmpart,
-                                         float* __restrict__ S1, int H, int W) {
-  pdl_wait();
-  pdl_launch();
-  const int f = blockIdx.z, y = blockIdx.y;
-  __shared__ double sc[2];
-  if (threadIdx.x == 0) {
-    float mn = INFINITY, mx = -INFINITY;
-    for (int b = 0; b < MM_BLOCKS; ++b) {
-      mn = fminf(mn, mmpart[((int64_t)f * MM_BLOCKS + b) * 2]);
-      mx = fmaxf(mx, mmpart[((int64_t)f * MM_BLOCKS + b) * 2 + 1]);
-    }
-    const double rng_ = (double)mx - (double)mn;
-    const double s = rng_ > 2.220446049250313e-16 ? 255.0 / rng_ : 0.0;
-    sc[0] = s;
-    sc[1] = 0.0 - (double)mn * s;
-  }
-  __syncthreads();
-  const double scale = sc[0], shift = sc[1];
-  const int64_t rowbase = ((int64_t)f * H + y) * W;
-  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
-    const float k[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
-    float s = 0.f;
-#pragma unroll
-    for (int t = 0; t < 5; ++t)
-      s = fmaf(k[t], noisy_px(raw, noise, rng, rowbase + reflect101(x + t - 2, W), scale, shift), s);
-    S1[rowbase + x] = s;
-  }
-}
-
-// pass 2: vertical 5-tap
-__global__ void depth_vblur5_kernel(const float* __restrict__ S1, float* __restrict__ S2, int H, int W) {
-  pdl_wait();
-  pdl_launch();
-  const int f = blockIdx.z, y = blockIdx.y;
-  const float k[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
-  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
-    float s = 0.f;
-#pragma unroll
-    for (int t = 0; t < 5; ++t) s = fmaf(k[t], S1[((int64_t)f * H + reflect101(y + t - 2, H)) * W + x], s);
-    S2[((int64_t)f * H + y) * W + x] = s;
-  }
-}
-
 struct K11 { float k[11]; };
-
-// pass 3: horizontal 11-tap on the centre band rows (reflect in x)
-__global__ void depth_band_hblur_kernel(const float* __restrict__ S2, float* __restrict__ T1, K11 kk, int H, int W,
-                                        int y1, int bh) {
-  pdl_wait();
-  pdl_launch();
-  const int f = blockIdx.z, r = blockIdx.y;
-  const float* src = S2 + ((int64_t)f * H + y1 + r) * W;
-  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
-    float s = 0.f;
-#pragma unroll
-    for (int t = 0; t < 11; ++t) s = fmaf(kk.k[t], src[reflect101(x + t - 5, W)], s);
-    T1[((int64_t)f * bh + r) * W + x] = s;
-  }
-}
-
-// pass 4: band vertical 11-tap (reflect inside the band) + bilinear downsample by `fac` + /255
-__global__ void depth_resize_kernel(const float* __restrict__ S2, const float* __restrict__ T1, K11 kk,
-                                    float* __restrict__ out, int H, int W, int y1, int bh, int fac) {
-  pdl_wait();
-  pdl_launch();
-  const int f = blockIdx.z, oy = blockIdx.y;
-  const int oh = H / fac, ow = W / fac, o = fac / 2 - 1;
-  for (int ox = blockIdx.x * blockDim.x + threadIdx.x; ox < ow; ox += gridDim.x * blockDim.x) {
-    float acc = 0.f;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const int y = oy * fac + o + dy;
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int x = ox * fac + o + dx;
-        float v;
-        if (y >= y1 && y < y1 + bh) {
-          v = 0.f;
-#pragma unroll
-          for (int t = 0; t < 11; ++t)
-            v = fmaf(kk.k[t], T1[((int64_t)f * bh + reflect101(y - y1 + t - 5, bh)) * W + x], v);
-        } else {
-          v = S2[((int64_t)f * H + y) * W + x];
-        }
-        acc += 0.25f * v;
-      }
-    }
-    out[((int64_t)f * oh + oy) * ow + ox] = acc / 255.0f;
-  }
-}
 
 // Four N(0,1) draws of the aligned pixel group gi4 = gi >> 2: ONE Philox4x32 call and two Box-Muller pairs (the per-pixel
 // normal_at() above evaluates the same numbers; it recomputes the call for each of the 4 pixels)
 __device__ __forceinline__ float4 normal4_at(const uint64_t* rng, int64_t gi4) {
   uint32_t r[4];
   philox4x32(rng[0], (uint64_t)gi4, 0x6465707468000000ull | (rng[1] & 0xffffffffu), r);
-  const float rad0 = sqrtf(-2.0f * __logf(u01(r[0]))), rad1 = sqrtf(-2.0f * __logf(u01(r[2])));
+  const float rad0 = sqrtf(-2.0f * __logf(u01d(r[0]))), rad1 = sqrtf(-2.0f * __logf(u01d(r[2])));
   float s0, c0, s1, c1;
-  __sincosf(6.283185307179586f * u01(r[1]), &s0, &c0);
-  __sincosf(6.283185307179586f * u01(r[3]), &s1, &c1);
+  __sincosf(6.283185307179586f * u01d(r[1]), &s0, &c0);
+  __sincosf(6.283185307179586f * u01d(r[3]), &s1, &c1);
   return make_float4(rad0 * c0, rad0 * s0, rad1 * c1, rad1 * s1);
 }
-__device__ __forceinline__ float noisy1(float raw, float nz, double scale, double shift) {
-  const float nrm = (float)((double)raw * scale + shift);          // cv2.normalize(NORM_MINMAX, 0..255) ...
-  const float u8 = (float)(int)fminf(fmaxf(nrm, 0.f), 255.f);      // ... .astype(uint8) (truncation)
-  return fminf(fmaxf(u8 + nz, 0.f), 255.f);
+// per-frame normalisation: cv2.normalize(NORM_MINMAX, 0..255) computes dst = src * scale + shift in double
+struct Norm { double scale, shift; float mn, sf; };
+__device__ __noinline__ float u8_exact(float raw, double scale, double shift) {      // (a real call: must not be if-converted)
+  const float nrm = (float)((double)raw * scale + shift);
+  return (float)(int)fminf(fmaxf(nrm, 0.f), 255.f);
+}
+__device__ __forceinline__ float noisy1(float raw, float nz, const Norm& nm) {
+  // u8 = trunc((float)(raw * scale + shift)) as the reference forms it (.astype(uint8)).  Fast path in float, without a
+  // single conversion instruction: (raw - min) * scale is within 5e-5 of the double result and lies in [0, 255.0001] because
+  // min / max come from the same frame; trunc by a round-toward-zero add of 2^23.  Whenever that value is within 1e-4 of an
+  // integer (2e-4 of the pixels; also NaN / out-of-range input) the exact double path decides.
+  const float f = (raw - nm.mn) * nm.sf;
+  float t = __fadd_rz(f, 8388608.f) - 8388608.f;
+  if (!(fabsf((f - t) - 0.5f) <= 0.4999f)) t = u8_exact(raw, nm.scale, nm.shift);
+  return fminf(fmaxf(t + nz, 0.f), 255.f);
+}
+// four pixels at once: one (rare) branch per group instead of one per pixel
+__device__ __noinline__ float4 u8_exact4(float4 rv, double scale, double shift) {
+  float4 t;
+  t.x = u8_exact(rv.x, scale, shift); t.y = u8_exact(rv.y, scale, shift);
+  t.z = u8_exact(rv.z, scale, shift); t.w = u8_exact(rv.w, scale, shift);
+  return t;
+}
+// packed fp32 pairs (sm_100 FADD2 / FMUL2: one issue slot for two lanes of arithmetic; these kernels are issue-bound)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b) { f32x2 r; asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+__device__ __forceinline__ float4 noisy4(const float4& rv, const float4& nz, const Norm& nm) {
+  const f32x2 mn2 = pk2(nm.mn, nm.mn), sf2 = pk2(nm.sf, nm.sf), big = pk2(8388608.f, 8388608.f), half = pk2(0.5f, 0.5f);
+  const f32x2 f01 = mul2(sub2(pk2(rv.x, rv.y), mn2), sf2), f23 = mul2(sub2(pk2(rv.z, rv.w), mn2), sf2);
+  const f32x2 t01 = sub2(add2_rz(f01, big), big), t23 = sub2(add2_rz(f23, big), big);      // trunc (0 <= f < 2^23)
+  float d0, d1, d2, d3;
+  unpk2(sub2(sub2(f01, t01), half), d0, d1);
+  unpk2(sub2(sub2(f23, t23), half), d2, d3);
+  const float c = 0.4999f;
+  const bool ok = (fabsf(d0) <= c) & (fabsf(d1) <= c) & (fabsf(d2) <= c) & (fabsf(d3) <= c);
+  float4 o;
+  if (ok) {
+    unpk2(add2(t01, pk2(nz.x, nz.y)), o.x, o.y);
+    unpk2(add2(t23, pk2(nz.z, nz.w)), o.z, o.w);
+  } else {
+    const float4 t = u8_exact4(rv, nm.scale, nm.shift);
+    o = make_float4(t.x + nz.x, t.y + nz.y, t.z + nz.z, t.w + nz.w);
+  }
+  return make_float4(fminf(fmaxf(o.x, 0.f), 255.f), fminf(fmaxf(o.y, 0.f), 255.f), fminf(fmaxf(o.z, 0.f), 255.f),
+                     fminf(fmaxf(o.w, 0.f), 255.f));
 }
 // the noisy image A at the aligned 4-pixel group starting at column x4 of row gy (x4 may lie outside the image: every
 // pixel is then taken at its BORDER_REFLECT_101 mirror, noise included: the blur mirrors the NOISY image)
 __device__ __forceinline__ float4 noisy_group(const float* __restrict__ raw, const float* __restrict__ noise, const uint64_t* rng,
-                                              int64_t fbase, int gy, int x4, int W, double scale, double shift) {
+                                              int64_t fbase, int gy, int x4, int W, const Norm& nm) {
   const int64_t rb = fbase + (int64_t)gy * W;
   if (x4 >= 0 && x4 + 3 < W) {
     const float4 rv = *reinterpret_cast<const float4*>(raw + rb + x4);
     float4 nz;
     if (noise) nz = *reinterpret_cast<const float4*>(noise + rb + x4);
     else { nz = normal4_at(rng, (rb + x4) >> 2); nz.x *= 50.f; nz.y *= 50.f; nz.z *= 50.f; nz.w *= 50.f; }
-    return make_float4(noisy1(rv.x, nz.x, scale, shift), noisy1(rv.y, nz.y, scale, shift), noisy1(rv.z, nz.z, scale, shift),
-                       noisy1(rv.w, nz.w, scale, shift));
+    return noisy4(rv, nz, nm);
   }
   float o[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int64_t gi = rb + reflect101(x4 + k, W);
-    o[k] = noisy1(raw[gi], noise ? noise[gi] : 50.0f * normal_at(rng, gi), scale, shift);
+    o[k] = noisy1(raw[gi], noise ? noise[gi] : 50.0f * normal_at(rng, gi), nm);
   }
   return make_float4(o[0], o[1], o[2], o[3]);
 }
@@ -211,45 +172,21 @@ static_assert(A_P % 4 == 0 && A_P >= A_C + 4, "A pitch");
 constexpr int H_P = TOW + 1;                                // fast path: horizontal 6-tap results [rows][TOW]
 constexpr int FUSED_SMEM = (A_R * A_P + A_R * S_P) * 4 + 32;   // S2 reuses A, T1 reuses Bh
 
-__global__ void __launch_bounds__(256) depth_fused_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
-                                                          const uint64_t* rng, const float* __restrict__ mmpart,
-                                                          K11 kk, float* __restrict__ out, int H, int W, int y1, int bh) {
-  pdl_wait();
-  pdl_launch();
-  extern __shared__ __align__(16) float smf[];
+__device__ __forceinline__ void depth_tile(const float* __restrict__ raw, const float* __restrict__ noise, const uint64_t* rng,
+                                           const K11& kk, float* __restrict__ out, int H, int W, int y1, int bh, int f, int oy0,
+                                           int ox0, int oy_end, const Norm& nm, float* smf) {
   float* A = smf;                       // [A_R][A_P]
   float* Bh = A + A_R * A_P;            // [A_R][S_P]
   float* S2 = A;                        // [S_R][S_P]     (A is dead once Bh exists)
   float* T1 = Bh;                       // [S_R][2*TOW]   (Bh is dead once S2 exists)
-  double* sc = reinterpret_cast<double*>(Bh + A_R * S_P);
-  const int f = blockIdx.z, oy0 = blockIdx.y * TOH, ox0 = blockIdx.x * TOW;
-  const int oh = H / 4, ow = W / 4;
+  const int ohf = H / 4, oh = min(ohf, oy_end), ow = W / 4;      // rows [.., oy_end) belong to this launch's tile rows
   const int tid = threadIdx.x;
-  if (tid < 32) {        // frame min / max from the 64 partials: one warp, two partials per lane
-    static_assert(MM_BLOCKS == 64, "two partials per lane");
-    const float2 p0 = *reinterpret_cast<const float2*>(mmpart + ((int64_t)f * MM_BLOCKS + tid) * 2);
-    const float2 p1 = *reinterpret_cast<const float2*>(mmpart + ((int64_t)f * MM_BLOCKS + 32 + tid) * 2);
-    float mn = fminf(p0.x, p1.x), mx = fmaxf(p0.y, p1.y);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    if (tid == 0) {
-      const double rg = (double)mx - (double)mn;
-      const double s = rg > 2.220446049250313e-16 ? 255.0 / rg : 0.0;
-      sc[0] = s;
-      sc[1] = 0.0 - (double)mn * s;
-    }
-  }
   const int ys0 = oy0 * 4 + 1, xs0 = ox0 * 4 + 1;           // first sampled row / col of the tile
   const int y2 = y1 + bh;
   const bool band = (ys0 + CORE_R - 1 >= y1) && (ys0 < y2);  // some sampled row lies in the centre band
   const int hs = band ? 5 : 0;                                // halo of S2, A needs hs + 2
   const int ar = CORE_R + 2 * (hs + 2), ac = CORE_C + 2 * (hs + 2);
   const int sr = CORE_R + 2 * hs, scn = CORE_C + 2 * hs;
-  __syncthreads();
-  const double scale = sc[0], shift = sc[1];
   const float k5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
   const int64_t fbase = (int64_t)f * H * W;
   // stage A: one thread = one aligned group of 4 pixels (16-byte loads of raw / noise, one Philox call per group).
@@ -292,10 +229,9 @@ __global__ void __launch_bounds__(256) depth_fused_kernel(const float* __restric
             nz = normal4_at(rng, (fbase + (int64_t)gys[u] * W + x4) >> 2);
             nz.x *= 50.f; nz.y *= 50.f; nz.z *= 50.f; nz.w *= 50.f;
           }
-          o = make_float4(noisy1(rv[u].x, nz.x, scale, shift), noisy1(rv[u].y, nz.y, scale, shift),
-                          noisy1(rv[u].z, nz.z, scale, shift), noisy1(rv[u].w, nz.w, scale, shift));
+          o = noisy4(rv[u], nz, nm);
         } else {
-          o = noisy_group(raw, noise, rng, fbase, gys[u], x4, W, scale, shift);      // image border: mirrored pixel by pixel
+          o = noisy_group(raw, noise, rng, fbase, gys[u], x4, W, nm);      // image border: mirrored pixel by pixel
         }
         *reinterpret_cast<float4*>(A + rr[u] * A_P + 4 * gg[u]) = o;
       }
@@ -326,7 +262,7 @@ __global__ void __launch_bounds__(256) depth_fused_kernel(const float* __restric
       float acc = 0.f;
 #pragma unroll
       for (int t = 0; t < 6; ++t) acc = fmaf(w6[t], col[t * H_P], acc);
-      out[((int64_t)f * oh + oy) * ow + ox] = acc / 255.0f;
+      out[((int64_t)f * ohf + oy) * ow + ox] = acc / 255.0f;
     }
     return;
   }
@@ -386,25 +322,373 @@ __global__ void __launch_bounds__(256) depth_fused_kernel(const float* __restric
           acc += 0.25f * v;
         }
       }
-      out[((int64_t)f * oh + oy) * ow + ox] = acc / 255.0f;
+      out[((int64_t)f * ohf + oy) * ow + ox] = acc / 255.0f;
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Streaming role (every output row with no sample in the centre band: ~80 % of a frame).  Off the band the result is the
+// separable stride-4 filter w6 = [1 5 10 10 5 1]/32 over pixels 4o-1 .. 4o+4 of the noisy image in both directions
+// (GaussianBlur(5,5) sampled at 4o+1, 4o+2 and averaged = cv2.resize by 4), so nothing needs shared memory:
+//   lane = one aligned 4-pixel group (one 16-byte load of raw, one of noise / one Philox call per row), its left and right
+//   neighbour pixels arrive by shuffle from the adjacent lanes: lanes 1..30 of a warp own output columns, lanes 0 and 31
+//   only carry the neighbours' pixels (column -1 mirrors to 1, column W to W-2: both inside the lane's own group);
+//   the warp walks down a strip of STRIP output rows, 4 input rows per step; each lane's 16-byte pieces of the next two
+//   steps are in flight as cp.async copies into the lane's own slots of a small shared-memory ring (no registers held
+//   across the wait, no barrier: a lane reads back only what it copied); rows 4o+3, 4o+4 serve outputs o and o+1.
+// Every pixel of the strip is read and turned into a noisy value once (+ 2 halo rows per strip and 2 of 32 lanes).
+constexpr int SEG = 30;
+#ifndef STREAM_BPS
+#define STREAM_BPS 3
+#endif
+
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+#ifndef DRING
+#define DRING 2
+#endif
+constexpr int RING = DRING;                                        // steps (4 rows each) in flight per warp
+template <bool NOISE> constexpr int stream_smem() { return 8 * RING * 4 * (NOISE ? 2 : 1) * 32 * 16; }   // 8 warps per block
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool NOISE>
+__device__ __forceinline__ void depth_stream(const float* __restrict__ raw, const float* __restrict__ noise, const uint64_t* rng,
+                                             float* __restrict__ out, int H, int W, int f, int oy0, int oy1, int seg,
+                                             const Norm& nm, float4* ring) {
+  const int lane = threadIdx.x & 31;
+  const int ow = W >> 2, ohf = H >> 2;
+  const int g = seg * SEG - 1 + lane;                   // this lane's pixel group = its output column
+  const bool writer = lane >= 1 && lane <= SEG && g < ow;
+  const int gc = min(max(g, 0), ow - 1);                // (lanes outside the row load a valid group; their values are not used)
+  const int64_t fbase = (int64_t)f * H * W;
+  const float w0 = 1.f / 32, w1 = 5.f / 32, w2 = 10.f / 32;
+  constexpr int ARR = NOISE ? 2 : 1;
+  auto row_of = [&](int y) { return y < 0 ? -y : (y >= H ? 2 * (H - 1) - y : y); };      // BORDER_REFLECT_101 (one fold)
+  const float* rbase = raw + fbase + 4 * gc;
+  const float* nbase = NOISE ? noise + fbase + 4 * gc : nullptr;
+  auto slot = [&](int step, int t, int arr) { return ring + (((step % RING) * 4 + t) * ARR + arr) * 32 + lane; };
+  // every lane copies its own 16 bytes and reads back only those: the copies need no barrier, only wait_group
+  auto issue = [&](int step, int nsteps) {
+    if (step < nsteps) {
+      const int y = 4 * (oy0 + step) - 1;
+      if (y >= 0 && y + 3 < H) {                         // (warp-uniform) rows y .. y+3 are consecutive: one offset, three adds
+        const float* rp = rbase + (int64_t)y * W;
+        const float* np = nbase + (int64_t)y * W;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          cp_async16(slot(step, t, 0), rp + t * W);
+          if (NOISE) cp_async16(slot(step, t, 1), np + t * W);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int off = row_of(y + t) * W;           // (a frame has < 2^31 pixels; the last step uses two of its rows)
+          cp_async16(slot(step, t, 0), rbase + off);
+          if (NOISE) cp_async16(slot(step, t, 1), nbase + off);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  auto hrow = [&](int step, int t, int y) {
+    const float4 rv = *slot(step, t, 0);
+    float4 nz;
+    if (NOISE) {
+      nz = *slot(step, t, 1);
+    } else {
+      nz = normal4_at(rng, (fbase + (int64_t)row_of(y) * W + 4 * gc) >> 2);
+      nz.x *= 50.f; nz.y *= 50.f; nz.z *= 50.f; nz.w *= 50.f;
+    }
+    const float4 a = noisy4(rv, nz, nm);
+    float left = __shfl_up_sync(0xffffffffu, a.w, 1), right = __shfl_down_sync(0xffffffffu, a.x, 1);
+    if (g == 0) left = a.y;
+    if (g == ow - 1) right = a.z;
+    return w0 * (left + right) + w1 * (a.x + a.w) + w2 * (a.y + a.z);
+  };
+  const int n_out = oy1 - oy0, nsteps = n_out + 1;
+#pragma unroll
+  for (int i = 0; i < RING - 1; ++i) issue(i, nsteps);
+  float carry = 0.f;
+  for (int i = 0; i < nsteps; ++i) {
+    issue(i + RING - 1, nsteps);
+    cp_async_wait<RING - 1>();                           // step i has landed
+    const int y = 4 * (oy0 + i) - 1;
+    const float h0 = hrow(i, 0, y), h1 = hrow(i, 1, y + 1);
+    if (i >= 1 && writer) out[((int64_t)f * ohf + oy0 + i - 1) * ow + g] = (carry + w1 * h0 + w0 * h1) / 255.0f;
+    if (i < n_out) {
+      const float h2 = hrow(i, 2, y + 2), h3 = hrow(i, 3, y + 3);
+      carry = w0 * h0 + w1 * h1 + w2 * (h2 + h3);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Band role (output rows with a sample in the centre band).  Same register streaming, one warp per (frame, 28-column
+// segment) walking down ALL rows the band needs.  Horizontally everything the band does is one composite filter per
+// output column: c16 = k5 * (k11 at column 4o+1  +  k11 at column 4o+2)/2 over pixels 4o-6 .. 4o+9 (own group, the two
+// neighbours, half of the next two: 12 shuffles); image-border columns mirror exactly because every filter is symmetric
+// (lanes outside the row hold the mirrored pixels).  Vertically: 5-tap sliding window in registers -> the blurred row goes
+// into this lane's private shared-memory column; the 11-tap with BORDER_REFLECT_101 INSIDE the band reads that column
+// back.  An output row with one sample outside the band takes that sample from the plain w6 path (two registers).
+constexpr int BSEG = 28;
+#ifndef BAND_BPS
+#define BAND_BPS 3
+#endif
+struct BandGeo {
+  int H, W, y1, bh, first, last, segs;      // output rows first..last touch the band
+  int64_t items;                            // n * segs
+};
+struct StreamGeo {
+  int H, W, ob0, ob1, strip, strips_lo, strips, segs;   // output rows [ob0, ob1) are not streamed
+  int64_t items;
+};
+
+__device__ __forceinline__ void frame_scale(const float* __restrict__ mmpart, int f, int lane, Norm& nm) {
+  static_assert(MM_BLOCKS == 64, "two partials per lane");
+  const float2 p0 = *reinterpret_cast<const float2*>(mmpart + ((int64_t)f * MM_BLOCKS + lane) * 2);
+  const float2 p1 = *reinterpret_cast<const float2*>(mmpart + ((int64_t)f * MM_BLOCKS + 32 + lane) * 2);
+  float mn = fminf(p0.x, p1.x), mx = fmaxf(p0.y, p1.y);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  const double rg = (double)mx - (double)mn;
+  nm.scale = rg > 2.220446049250313e-16 ? 255.0 / rg : 0.0;
+  nm.shift = 0.0 - (double)mn * nm.scale;
+  nm.mn = mn;
+  nm.sf = (float)nm.scale;
+}
+
+template <bool NOISE>
+__global__ void __launch_bounds__(256, BAND_BPS) depth_band_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
+                                                            const uint64_t* rng, const float* __restrict__ mmpart,
+                                                            const __grid_constant__ K11 kk, float* __restrict__ out,
+                                                            const __grid_constant__ BandGeo gm) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ __align__(16) float smf[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f = blockIdx.x / gm.segs, seg = blockIdx.x % gm.segs;
+  Norm nm;
+  frame_scale(mmpart, f, lane, nm);
+  const int H = gm.H, W = gm.W, y1 = gm.y1, bh = gm.bh, y2 = y1 + bh;
+  const int ow = W >> 2, ohf = H >> 2;
+  const int g = seg * BSEG - 2 + lane, x4 = 4 * g;
+  const bool inimg = x4 >= 0 && x4 + 3 < W;
+  const bool writer = lane >= 2 && lane < 2 + BSEG && g < ow;
+  // mirrored lanes (W >= 16): group g < 0 is (group -g).x, (group -g-1).w,.z,.y; group g >= ow is (group 2ow-g-1).z,.y,.x,
+  // (group 2ow-g-2).w; both source groups sit in this warp (lane = group - seg * BSEG + 2)
+  const int vmode = g < 0 ? 1 : (g >= ow && g <= ow + 1 ? 2 : 0);
+  const int srcA = (vmode == 1 ? -g : 2 * ow - g - 1) - seg * BSEG + 2, srcB = srcA - 1;
+  const bool border = seg == 0 || (seg + 1) * BSEG + 2 > ow;          // (warp-uniform) some lane of this warp is mirrored
+  const int x4c = min(max(x4, 0), W - 4);
+  const int64_t fbase = (int64_t)f * H * W;
+  const float k5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+  float c16[16];
+  {
+    float h12[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) h12[j] = 0.5f * ((j < 11 ? kk.k[j] : 0.f) + (j >= 1 ? kk.k[j - 1] : 0.f));
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      float a = 0.f;
+#pragma unroll
+      for (int t = 0; t < 5; ++t)
+        if (m - t >= 0 && m - t < 12) a = fmaf(k5[t], h12[m - t], a);
+      c16[m] = a;
+    }
+  }
+  const float w0 = 1.f / 32, w1 = 5.f / 32, w2 = 10.f / 32;
+  // blurred rows to form: the band itself plus the (at most one each side) sampled row just outside it
+  const int ylo = 4 * gm.first + 1, yhi = 4 * gm.last + 2;
+  const int sa = min(y1, ylo), sb = max(y2 - 1, yhi);
+  const int ra = sa - 2, rb = sb + 2, nrows = rb - ra + 1;           // noisy rows (y1 - 3 .. y2 + 2 at most)
+  float* ah16 = smf + lane;                                          // [nrows][32]  horizontal c16 of noisy row ra + i
+  float* s2 = ah16 + (size_t)nrows * 32;                             // [bh][32]     blurred band row y1 + i
+  float* ah6 = s2 + (size_t)bh * 32;                                 // [10][32]     horizontal w6 of rows y1-3..y1+1, y2-2..y2+2
+  // ---- phase 1: warp w takes the noisy rows ra + w, ra + w + 8, ...; four rows' loads in flight
+  for (int r0 = ra + warp; r0 <= rb; r0 += 32) {
+    float4 rv[4], nv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      rv[u] = nv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int r = r0 + 8 * u;
+      if (r <= rb && inimg) {
+        const int64_t gi = fbase + (int64_t)((r < 0 || r >= H) ? reflect101(r, H) : r) * W + x4;
+        rv[u] = ld_stream4(raw + gi);
+        if (NOISE) nv[u] = ld_stream4(noise + gi);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + 8 * u;
+      if (r > rb) break;                                             // (warp-uniform)
+      const int rr = (r < 0 || r >= H) ? reflect101(r, H) : r;
+      float4 nz = nv[u];
+      if (!NOISE) {
+        nz = normal4_at(rng, (fbase + (int64_t)rr * W + x4c) >> 2);
+        nz.x *= 50.f; nz.y *= 50.f; nz.z *= 50.f; nz.w *= 50.f;
+      }
+      float4 a = noisy4(rv[u], nz, nm);                              // (lanes outside the row: replaced below)
+      const unsigned FULL = 0xffffffffu;
+      if (border) {
+        // lanes left / right of the image hold the BORDER_REFLECT_101 mirror of the noisy row: pixel -p is pixel p,
+        // pixel W-1+p is pixel W-1-p; both sit in the in-image lanes next to them
+        const float Ax = __shfl_sync(FULL, a.x, srcA), Ay = __shfl_sync(FULL, a.y, srcA), Az = __shfl_sync(FULL, a.z, srcA);
+        const float Bw = __shfl_sync(FULL, a.w, srcB), Bz = __shfl_sync(FULL, a.z, srcB), By = __shfl_sync(FULL, a.y, srcB);
+        if (vmode == 1) a = make_float4(Ax, Bw, Bz, By);
+        else if (vmode == 2) a = make_float4(Az, Ay, Ax, Bw);
+      }
+      const float m2z = __shfl_up_sync(FULL, a.z, 2), m2w = __shfl_up_sync(FULL, a.w, 2);
+      const float m1x = __shfl_up_sync(FULL, a.x, 1), m1y = __shfl_up_sync(FULL, a.y, 1);
+      const float m1z = __shfl_up_sync(FULL, a.z, 1), m1w = __shfl_up_sync(FULL, a.w, 1);
+      const float p1x = __shfl_down_sync(FULL, a.x, 1), p1y = __shfl_down_sync(FULL, a.y, 1);
+      const float p1z = __shfl_down_sync(FULL, a.z, 1), p1w = __shfl_down_sync(FULL, a.w, 1);
+      const float p2x = __shfl_down_sync(FULL, a.x, 2), p2y = __shfl_down_sync(FULL, a.y, 2);
+      float h16 = c16[0] * m2z, h16b = c16[1] * m2w;                 // two chains
+      h16 = fmaf(c16[2], m1x, h16); h16b = fmaf(c16[3], m1y, h16b);
+      h16 = fmaf(c16[4], m1z, h16); h16b = fmaf(c16[5], m1w, h16b);
+      h16 = fmaf(c16[6], a.x, h16); h16b = fmaf(c16[7], a.y, h16b);
+      h16 = fmaf(c16[8], a.z, h16); h16b = fmaf(c16[9], a.w, h16b);
+      h16 = fmaf(c16[10], p1x, h16); h16b = fmaf(c16[11], p1y, h16b);
+      h16 = fmaf(c16[12], p1z, h16); h16b = fmaf(c16[13], p1w, h16b);
+      h16 = fmaf(c16[14], p2x, h16); h16b = fmaf(c16[15], p2y, h16b);
+      ah16[(r - ra) * 32] = h16 + h16b;
+      const float h6 = w0 * (m1w + p1x) + w1 * (a.x + a.w) + w2 * (a.y + a.z);
+      if (r >= y1 - 3 && r <= y1 + 1) ah6[(r - (y1 - 3)) * 32] = h6;
+      if (r >= y2 - 2 && r <= y2 + 2) ah6[(5 + r - (y2 - 2)) * 32] = h6;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: vertical 5-tap -> the GaussianBlur(5,5) rows of the band (already filtered horizontally for the samples)
+  for (int q = y1 + warp; q < y2; q += 8) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) sacc = fmaf(k5[t], ah16[(q - 2 + t - ra) * 32], sacc);
+    s2[(q - y1) * 32] = sacc;
+  }
+  float s6_lo = 0.f, s6_hi = 0.f;       // plain-path samples at rows y1 - 1 and y2 (read only when an output row straddles the edge)
+  if (ylo < y1) {
+#pragma unroll
+    for (int t = 0; t < 5; ++t) s6_lo = fmaf(k5[t], ah6[t * 32], s6_lo);
+  }
+  if (yhi >= y2) {
+#pragma unroll
+    for (int t = 0; t < 5; ++t) s6_hi = fmaf(k5[t], ah6[(5 + t) * 32], s6_hi);
+  }
+  __syncthreads();
+  // ---- phase 3: 11-tap down the band column (BORDER_REFLECT_101 inside the band), 2 x 2 average
+  if (!writer) return;
+  for (int oy = gm.first + warp; oy <= gm.last; oy += 8) {
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int y = 4 * oy + 1 + dy;
+      float v;
+      if (y >= y1 && y < y2) {
+        v = 0.f;
+        const int yb0 = y - y1 - 5;
+        if (yb0 >= 0 && yb0 + 10 < bh) {
+#pragma unroll
+          for (int t = 0; t < 11; ++t) v = fmaf(kk.k[t], s2[(yb0 + t) * 32], v);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 11; ++t) v = fmaf(kk.k[t], s2[reflect101(yb0 + t, bh) * 32], v);     // reflect inside the band
+        }
+      } else {
+        v = y < y1 ? s6_lo : s6_hi;
+      }
+      acc += 0.5f * v;
+    }
+    out[((int64_t)f * ohf + oy) * ow + g] = acc / 255.0f;
+  }
+}
+
+// streaming role over the rows outside [ob0, ob1): one (frame, strip, 30-column segment) per warp
+template <bool NOISE>
+__global__ void __launch_bounds__(256, STREAM_BPS) depth_stream_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
+                                                           const uint64_t* rng, const float* __restrict__ mmpart,
+                                                           float* __restrict__ out, const __grid_constant__ StreamGeo gm) {
+  pdl_wait();
+  pdl_launch();
+  const int64_t item = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (item >= gm.items) return;
+  const int f = (int)(item / ((int64_t)gm.strips * gm.segs));
+  Norm nm;
+  frame_scale(mmpart, f, threadIdx.x & 31, nm);
+  const int seg = (int)(item % gm.segs);
+  const int sidx = (int)((item / gm.segs) % gm.strips);
+  int oy0, oy1;
+  if (sidx < gm.strips_lo) { oy0 = sidx * gm.strip; oy1 = min(oy0 + gm.strip, gm.ob0); }
+  else { oy0 = gm.ob1 + (sidx - gm.strips_lo) * gm.strip; oy1 = min(oy0 + gm.strip, gm.H / 4); }
+  extern __shared__ __align__(16) float4 ring4[];
+  depth_stream<NOISE>(raw, noise, rng, out, gm.H, gm.W, f, oy0, oy1, seg, nm,
+                      ring4 + (threadIdx.x >> 5) * (RING * 4 * (NOISE ? 2 : 1) * 32));
+}
+
+// every row through the shared-memory tiles (dgvit_set_option("depth_strip", 0), and frames whose band column does not fit
+// into shared memory): the first fused version, kept as the cross-check of the two streaming roles
+__global__ void __launch_bounds__(256) depth_tile_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
+                                                         const uint64_t* rng, const float* __restrict__ mmpart,
+                                                         const __grid_constant__ K11 kk, float* __restrict__ out, int H, int W,
+                                                         int y1, int bh) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ __align__(16) float smf[];
+  __shared__ Norm snm;
+  const int f = blockIdx.z;
+  if (threadIdx.x < 32) {
+    Norm nm;
+    frame_scale(mmpart, f, threadIdx.x, nm);
+    if (threadIdx.x == 0) snm = nm;
+  }
+  __syncthreads();
+  const Norm nm = snm;
+  depth_tile(raw, noise, rng, kk, out, H, W, y1, bh, f, blockIdx.y * TOH, blockIdx.x * TOW, H / 4, nm, smf);
 }
 
 }  // namespace dgvit
 
 using namespace dgvit;
 
+namespace {
+struct DepthSide { cudaStream_t s; cudaEvent_t fork, join; };
+DepthSide& depth_side() {       // one second stream per device (fork / join by events: capturable)
+  static DepthSide per_dev[64];
+  static bool inited[64] = {};
+  const int dev = current_device();
+  if (!inited[dev]) {
+    DG_CUDA(cudaStreamCreateWithFlags(&per_dev[dev].s, cudaStreamNonBlocking));
+    DG_CUDA(cudaEventCreateWithFlags(&per_dev[dev].fork, cudaEventDisableTiming));
+    DG_CUDA(cudaEventCreateWithFlags(&per_dev[dev].join, cudaEventDisableTiming));
+    inited[dev] = true;
+  }
+  return per_dev[dev];
+}
+}  // namespace
+
 extern "C" {
+
+int g_depth_skip = 0;           // debug (profiles/depth_bench.py): 1 = no band kernel, 2 = no streaming kernel, 4 = no min/max pass
+int g_depth_strip = -1;         // dgvit_set_option("depth_strip"): output rows per streaming strip; < 0 = chosen per call, 0 = every row through the tiles
 
 int dgvit_depth_scratch_bytes(int n, int H, int W, size_t* bytes) {
   return guarded([&] {
     DG_REQUIRE(bytes && n >= 1 && H >= 8 && W >= 8, "bad argument");
     Carver cv(nullptr, 0, true);
     cv.take<float>((size_t)n * MM_BLOCKS * 2);
-    cv.take<float>((size_t)n * H * W);
-    cv.take<float>((size_t)n * H * W);
-    cv.take<float>((size_t)n * (H / 5) * W);
     *bytes = cv.off;
   });
 }
@@ -415,15 +699,11 @@ int dgvit_depth_augment(const float* raw, const float* noise, const uint64_t* rn
     DeviceGuard dev_guard(raw);
     DG_REQUIRE(raw && out && scratch && n >= 1, "null argument");
     DG_REQUIRE(noise || rng_state, "provide noise or rng_state");
-    DG_REQUIRE(H % 4 == 0 && W % 4 == 0, "H and W must be multiples of 4");
+    DG_REQUIRE(H >= 8 && W >= 8 && H % 4 == 0 && W % 4 == 0, "H and W must be multiples of 4 (>= 8)");
     DG_REQUIRE((((uintptr_t)raw) & 15) == 0 && (((uintptr_t)noise) & 15) == 0, "raw / noise must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     Carver cv(scratch, scratch_bytes);
     float* mm = cv.take<float>((size_t)n * MM_BLOCKS * 2);
-    float* S1 = cv.take<float>((size_t)n * H * W);
-    float* S2 = cv.take<float>((size_t)n * H * W);
-    const int bh = H / 5, y1 = H / 2 - bh / 2;   // get_center_band, env_lab.py:33-39
-    float* T1 = cv.take<float>((size_t)n * bh * W);
     K11 kk;
     {  // cv2.getGaussianKernel(11, sigma<=0): sigma = 0.3*((11-1)*0.5-1)+0.8 = 2.0
       const double sigma = 0.3 * ((11 - 1) * 0.5 - 1) + 0.8;
@@ -431,16 +711,77 @@ int dgvit_depth_augment(const float* raw, const float* noise, const uint64_t* rn
       for (int i = 0; i < 11; ++i) { const double x = i - 5.0; k[i] = exp(-(x * x) / (2 * sigma * sigma)); sum += k[i]; }
       for (int i = 0; i < 11; ++i) kk.k[i] = (float)(k[i] / sum);
     }
-    launch_k(depth_minmax_kernel, dim3(MM_BLOCKS, n), 256, 0, st, raw, mm, (int64_t)H * W);
-    DG_LAUNCH_CHECK();
+    if (!(g_depth_skip & 4)) {
+      launch_k(depth_minmax_kernel, dim3(MM_BLOCKS, n), 256, 0, st, raw, mm, (int64_t)H * W);
+      DG_LAUNCH_CHECK();
+    }
+    const int bh = H / 5, y1 = H / 2 - bh / 2, y2 = y1 + bh;     // get_center_band, env_lab.py:33-39
+    const int oh = H / 4, ow = W / 4;
+    // output row oy samples rows 4oy+1, 4oy+2: it touches the band when one of them lies in [y1, y2)
+    int first = y1 - 2 <= 0 ? 0 : (y1 - 2 + 3) / 4, last = std::min(oh - 1, (y2 - 2) / 4);
+    if (bh < 1 || last < first) { first = 0; last = -1; }
+    const size_t band_smem = (size_t)(2 * bh + 16) * 32 * sizeof(float);     // ah16 [<= bh + 6] + s2 [bh] + ah6 [10] rows of 32
     static DevOnce attr;
     if (attr.first()) {
-      DG_CUDA(cudaFuncSetAttribute(depth_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
+      DG_CUDA(cudaFuncSetAttribute(depth_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
+      DG_CUDA(cudaFuncSetAttribute(depth_band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      DG_CUDA(cudaFuncSetAttribute(depth_band_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      DG_CUDA(cudaFuncSetAttribute(depth_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_smem<true>()));
+      DG_CUDA(cudaFuncSetAttribute(depth_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_smem<false>()));
     }
-    (void)S1; (void)S2; (void)T1;
-    launch_k(depth_fused_kernel, dim3((unsigned)cdiv(W / 4, TOW), (unsigned)cdiv(H / 4, TOH), n), 256, FUSED_SMEM, st, raw,
-             noise, rng_state, mm, kk, out, H, W, y1, bh);
-    DG_LAUNCH_CHECK();
+    if (g_depth_strip == 0 || band_smem > 200 * 1024 || W < 16) {
+      launch_k(depth_tile_kernel, dim3((unsigned)cdiv(ow, TOW), (unsigned)cdiv(oh, TOH), n), 256, FUSED_SMEM, st, raw, noise,
+               rng_state, (const float*)mm, kk, out, H, W, y1, bh);
+      DG_LAUNCH_CHECK();
+      return;
+    }
+    // the band rows (a few long-running warps) on a second stream beside the streamed rows
+    DepthSide& sd = depth_side();
+    const bool have_band = last >= first;
+    if (have_band && !(g_depth_skip & 1)) {
+      BandGeo bg;
+      bg.H = H; bg.W = W; bg.y1 = y1; bg.bh = bh; bg.first = first; bg.last = last;
+      bg.segs = (int)cdiv(ow, BSEG);
+      bg.items = (int64_t)n * bg.segs;
+      DG_CUDA(cudaEventRecord(sd.fork, st));
+      DG_CUDA(cudaStreamWaitEvent(sd.s, sd.fork, 0));
+      const dim3 grid((unsigned)bg.items);
+      if (noise) launch_k(depth_band_kernel<true>, grid, 256, band_smem, sd.s, raw, noise, rng_state, (const float*)mm, kk, out, bg);
+      else launch_k(depth_band_kernel<false>, grid, 256, band_smem, sd.s, raw, noise, rng_state, (const float*)mm, kk, out, bg);
+      DG_LAUNCH_CHECK();
+      DG_CUDA(cudaEventRecord(sd.join, sd.s));
+    }
+    StreamGeo gm;
+    gm.H = H; gm.W = W;
+    gm.ob0 = have_band ? first : 0;
+    gm.ob1 = have_band ? last + 1 : 0;
+    gm.segs = (int)cdiv(ow, SEG);
+    auto n_strips = [&](int strip) { return cdiv(gm.ob0, strip) + cdiv(oh - gm.ob1, strip); };
+    int strip = g_depth_strip;
+    if (strip < 0) {
+      // strip height against wave quantisation: a warp's time grows with its rows (4 per output row + 2 halo + start-up), the
+      // launch takes whole waves of 148 SMs x STREAM_BPS blocks x 8 warps
+      const int64_t capacity = 148 * STREAM_BPS * 8;
+      const int rows_max = std::max(gm.ob0, oh - gm.ob1);
+      double best = 1e300;
+      for (int cand = 3; cand <= 32; ++cand) {
+        const int64_t items = (int64_t)n * gm.segs * n_strips(cand);
+        const double cost = (double)cdiv(items, capacity) * (4.0 * std::min(cand, std::max(rows_max, 1)) + 6.0);
+        if (cost < best) { best = cost; strip = cand; }
+      }
+    }
+    gm.strip = std::max(1, std::min(strip, 64));
+    gm.strips_lo = (int)cdiv(gm.ob0, gm.strip);
+    gm.strips = (int)n_strips(gm.strip);
+    gm.items = (int64_t)n * gm.strips * gm.segs;
+    if (gm.items > 0 && !(g_depth_skip & 2)) {
+      const int64_t blocks = cdiv(gm.items, 8);
+      DG_REQUIRE(blocks < (int64_t)1 << 31, "too many frames for one launch");
+      if (noise) launch_k(depth_stream_kernel<true>, dim3((unsigned)blocks), 256, stream_smem<true>(), st, raw, noise, rng_state, (const float*)mm, out, gm);
+      else launch_k(depth_stream_kernel<false>, dim3((unsigned)blocks), 256, stream_smem<false>(), st, raw, noise, rng_state, (const float*)mm, out, gm);
+      DG_LAUNCH_CHECK();
+    }
+    if (have_band && !(g_depth_skip & 1)) DG_CUDA(cudaStreamWaitEvent(st, sd.join, 0));
   });
 }
 

@@ -1306,6 +1306,8 @@ static void by_precision(int precision, F32&& f32, BF&& bf) {
 // =====================================================================================
 using namespace dgvit;
 
+extern "C" int g_depth_strip, g_depth_skip;      // depth.cu
+
 extern "C" {
 
 int dgvit_version(void) { return 100; }
@@ -1322,6 +1324,8 @@ int dgvit_set_option(const char* name, int value) {
     else if (!strcmp(name, "pdl")) pdl_enabled() = value != 0;
     else if (!strcmp(name, "skip")) skip_mask() = value;
     else if (!strcmp(name, "attention_row0")) g_row0_mode = value;
+    else if (!strcmp(name, "depth_strip")) g_depth_strip = value;
+    else if (!strcmp(name, "depth_skip")) g_depth_skip = value;
 #ifdef DGVIT_WITH_TC
     else if (!strcmp(name, "tensor_cores")) tc::g_tc_enabled = value != 0;
     else if (!strcmp(name, "debug_epilogue")) tc::g_debug = value;

@@ -51,13 +51,14 @@ def depth_augment(raw: torch.Tensor, noise: Optional[torch.Tensor] = None,
     elif rng_state is None:
         rng_state = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, int(torch.randint(0, 2**31, (1,)))],
                                  dtype=torch.int64, device=raw.device)
-    nb = C.c_size_t()
-    L.check(L.lib().dgvit_depth_scratch_bytes(n, H, W, C.byref(nb)), "depth_scratch_bytes")
-    key = (raw.device, nb.value)
+    key = (raw.device, n, H, W)
     sc = _scratch.get(key)
     if sc is None:
+        nb = C.c_size_t()
+        L.check(L.lib().dgvit_depth_scratch_bytes(n, H, W, C.byref(nb)), "depth_scratch_bytes")
         sc = torch.empty(nb.value, dtype=torch.uint8, device=raw.device)
-        _scratch.clear()
+        if len(_scratch) > 16:
+            _scratch.clear()
         _scratch[key] = sc
     if out is None:
         out = torch.empty(n, H // 4, W // 4, dtype=torch.float32, device=raw.device)

@@ -447,3 +447,25 @@ def test_device_argument_without_set_device():
     assert np.isfinite(q) and np.isfinite(p)
     a = ag.choose_action(np.random.rand(128, 160, 1).astype(np.float32), np.array([0.3, 0.1], np.float32), True)
     assert a.shape == (2,)
+
+
+@pytest.mark.gpu
+def test_depth_streaming_rows_equal_tile_rows():
+    """The rows off the centre band leave through the register-streaming role of the depth kernel, the band rows through the
+    shared-memory tiles; with `depth_strip` = 0 every row takes the tile path.  Same pixels, same Philox draws: the two agree
+    to rounding, for given and for drawn noise, on frame sizes whose width is / is not a multiple of the 30-column segments."""
+    from dgvit_b200 import _lib as L
+    rng = torch.tensor([77, 3], dtype=torch.int64, device="cuda")
+    try:
+        for (n, H, W) in ((3, 512, 640), (2, 64, 80), (1, 256, 320), (2, 40, 136), (1, 8, 8), (1, 1024, 1280)):
+            raw = (torch.rand(n, H, W, generator=torch.Generator().manual_seed(H + W)) * 6 + 1).cuda()
+            noise = torch.randn(n, H, W, generator=torch.Generator().manual_seed(W)).cuda() * 50
+            outs = {}
+            for strip in (0, -1, 8, 5, 64):
+                L.check(L.lib().dgvit_set_option(b"depth_strip", strip), "set_option")
+                outs[strip] = (dg.depth_augment(raw, noise).clone(), dg.depth_augment(raw, None, rng).clone())
+            for strip in (-1, 8, 5, 64):
+                for k in range(2):
+                    assert float((outs[strip][k] - outs[0][k]).abs().max()) < 2e-6, (n, H, W, strip, k)
+    finally:
+        L.check(L.lib().dgvit_set_option(b"depth_strip", -1), "set_option")
