@@ -589,10 +589,14 @@ def run_next_rows(dev):
         return n / (time.perf_counter() - t0)
     try:
         a1 = dg.SAC(2, 2, "GaussianTransformer", "CNN", False, False, False, SEED, BUFFER_SIZE=4096, precision="bf16", device=dev,
-                    **HP, **PRESET)
+                    use_cuda_graph=True, **HP, **PRESET)
         a1.replay_buffer.fill_synthetic(4096, seed=SEED)
-        out["f1_cnn_critic_learn"] = dict(value=256 * rate(lambda: a1.learn(256), 10), unit=UNIT,
-                                          what="SAC.learn(256), QNetwork critic + DGViT actor, autograd-glued module path")
+        r_sync = rate(lambda: a1.learn(256), 10)
+        r_async = rate(lambda: a1.learn_async(256), 20)
+        out["f1_cnn_critic_learn"] = dict(value=256 * r_async, with_loss_readback=256 * r_sync, unit=UNIT,
+                                          what="SAC.learn_async(256) / SAC.learn(256): QNetwork critic + DGViT actor, replay gather + "
+                                               "the whole update in one C call (dgvit_sac_update, critic kind DGVIT_QNET), CUDA graph")
+        a1.close()
         del a1
     except Exception as e:
         out["f1_cnn_critic_learn"] = dict(error=repr(e)[:200])

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DGVIT_LIB") or os.path.join(_HERE, "libdgvit.so")
 
 MAX_DEPTH = 16
-ACTOR, CRITIC = 0, 1
+ACTOR, CRITIC, QNET = 0, 1, 2
 FP32, BF16 = 0, 1
 DROP_NONE, DROP_MASK, DROP_RNG = 0, 1, 2
 (PROF_NONE, PROF_GEMM_MLP, PROF_GEMM_ALL, PROF_ATTENTION, PROF_GATHER, PROF_ADAM, PROF_MLP_FUSED, PROF_LN_BWD, PROF_EMBED,
@@ -133,6 +133,7 @@ SYMBOLS = {
     "dgvit_param_layout": (C.c_int, [P(Cfg), P(Layout)]),
     "dgvit_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
     "dgvit_sac_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
+    "dgvit_sac_qnet_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
     "dgvit_refresh_shadow": (C.c_int, [P(Net), C.c_void_p]),
     "dgvit_actor_forward": (C.c_int, [P(Net), P(ActorIO), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dgvit_actor_backward": (C.c_int, [P(Net), P(ActorIO), P(ActorGrad), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -225,13 +225,14 @@ class SAC(object):
                                                  self.seed + 1 + 7919 * rk) if pre_buffer else None)    # vn/DRL.py:91-100
         self._gbuf = {}
 
-        if self._cnn_critic:
-            self._init_cnn_critic(action_dim, pstate_dim, block, head, l_f_size, image_size, mlp_dim, ALPHA)
-            return
         # construction order == reference (critic, critic_target, policy): same seed -> same weights
         kw = dict(image_size=image_size, mlp_dim=mlp_dim)
-        self.critic = GoTQNetwork(action_dim, pstate_dim, block, head, l_f_size, **kw).to(self.device)
-        self.critic_target = GoTQNetwork(action_dim, pstate_dim, block, head, l_f_size, **kw).to(self.device)
+        if self._cnn_critic:      # vn/DRL.py:118-121 (the shipped default, vn/config.yaml:61): CNN twin-Q critic
+            self.critic = QNetwork(action_dim, pstate_dim, image_size=image_size).to(self.device)
+            self.critic_target = QNetwork(action_dim, pstate_dim, image_size=image_size).to(self.device)
+        else:
+            self.critic = GoTQNetwork(action_dim, pstate_dim, block, head, l_f_size, **kw).to(self.device)
+            self.critic_target = GoTQNetwork(action_dim, pstate_dim, block, head, l_f_size, **kw).to(self.device)
         self.target_entropy = -float(action_dim)
         self.policy = GoTPolicy(action_dim, pstate_dim, block, head, l_f_size, **kw).to(self.device)
         for m in (self.critic, self.critic_target, self.policy):
@@ -264,83 +265,39 @@ class SAC(object):
         self._batch = None
         self._graphs = {}
         for m in (self.critic, self.critic_target, self.policy):
-            m.refresh_shadow()
+            if hasattr(m, "refresh_shadow"):
+                m.refresh_shadow()
 
     # ------------------------------------------------------------------ CNN critic (vn/DRL.py:118-121)
-    def _init_cnn_critic(self, action_dim, pstate_dim, block, head, l_f_size, image_size, mlp_dim, ALPHA):
-        """critic_type != "Transformer": the reference's wiring (vn/DRL.py:118-150) on top of the drop-in modules —
-        ``QNetwork`` critic + target, DGViT actor, three ``torch.optim.Adam``.  The update is the reference's
-        ``learn`` statement by statement with autograd as the glue between the library's forward / backward calls
-        (the single-call fused update exists for the Transformer critic only)."""
-        if self.distributed:
-            raise NotImplementedError("data-parallel updates are implemented for critic_type='Transformer'")
-        dev = self.device
-        self.critic = QNetwork(action_dim, pstate_dim, image_size=image_size).to(dev)
-        self.critic_target = QNetwork(action_dim, pstate_dim, image_size=image_size).to(dev)
-        self.target_entropy = -float(action_dim)
-        self.policy = GoTPolicy(action_dim, pstate_dim, block, head, l_f_size, image_size=image_size, mlp_dim=mlp_dim).to(dev)
-        for m in (self.critic, self.critic_target, self.policy):
-            m.precision = self.precision
-            m.bind()
-        hard_update(self.critic_target, self.critic)                                   # vn/DRL.py:123
-        self.critic_optim = torch.optim.Adam(self.critic.parameters(), lr=self.lr_c)    # :113
-        self.policy_optim = torch.optim.Adam(self.policy.parameters(), lr=self.lr_a)    # :150
-        self.log_alpha = torch.zeros(1, requires_grad=True, device=dev)                 # :138
-        self.alpha_optim = torch.optim.Adam([self.log_alpha], lr=self.lr_alpha)         # :139
-        self.target_policy = copy.deepcopy(self.policy)
-        self._batch = None
-
     def _learn_cnn(self, batch: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None,
                    extra: Optional[Dict[str, torch.Tensor]] = None):
-        """vn/DRL.py:388-434 (and :237-299 when ``extra`` is given) with the drop-in modules.  ``noise`` (tests): eps_next /
-        eps_pi rsample draws and mask_a_next / mask_a dropout keep-masks of the two actor passes (+ mask_x for the
-        imitation rows).  ``extra``: obs, pobs, target, weight of the ``learn_guidence`` imitation rows (expert rows, then
-        the rows with engage == 1): the reference's two extra ``policy.sample`` calls (:259-276) ride in one pass, and
-        ``weight`` carries guidence_weight / (n_expert * n_act) resp. engage_weight / (n_engaged * n_act)."""
-        import torch.nn.functional as F
-        view = lambda t: t.view(t.shape[0], *self.replay_buffer.obs_shape) if t.dim() == 2 else t
-        s, s2 = view(batch["obs"]), view(batch["next_obs"])
-        ps, ps2, a, r = batch["pobs"], batch["next_pobs"], batch["act"], batch["rew"]
-        nz = noise or {}
-        with torch.no_grad():
-            if noise:
-                self.policy.inject_noise(mask=nz.get("mask_a_next"), eps=nz.get("eps_next"))
-            a2, logp2, _ = self.policy.sample([s2, ps2])
-            q1t, q2t = self.critic_target([s2, ps2, a2])
-            next_q = r + self.gamma * (torch.min(q1t, q2t) - self.alpha * logp2)
-        qf1, qf2 = self.critic([s, ps, a])
-        qf1_loss = F.mse_loss(qf1, next_q)
-        qf_loss = qf1_loss + F.mse_loss(qf2, next_q)
-        self.critic_optim.zero_grad()
-        qf_loss.backward()
-        self.critic_optim.step()
-        if noise:
-            self.policy.inject_noise(mask=nz.get("mask_a"), eps=nz.get("eps_pi"))
-        pi, log_pi, _ = self.policy.sample([s, ps])
-        for p in self.critic.parameters():          # the reference discards these gradients at the next zero_grad
-            p.requires_grad_(False)
-        qf1_pi, qf2_pi = self.critic([s, ps, pi])
-        for p in self.critic.parameters():
-            p.requires_grad_(True)
-        policy_loss = ((self.alpha * log_pi) - torch.min(qf1_pi, qf2_pi)).mean()
-        if extra is not None:                                                                # :259-278
-            if noise:
-                self.policy.inject_noise(mask=nz.get("mask_x"), eps=nz.get("eps_x"))
-            _, _, predicted = self.policy.sample([view(extra["obs"]), extra["pobs"]])
-            policy_loss = policy_loss + (extra["weight"][:, None] * (predicted - extra["target"]) ** 2).sum()
-        self.policy_optim.zero_grad()
-        policy_loss.backward()
-        self.policy_optim.step()
-        if self.automatic_entropy_tuning:
-            alpha_loss = -(self.log_alpha * (log_pi + self.target_entropy).detach()).mean()
-            self.alpha_optim.zero_grad()
-            alpha_loss.backward()
-            self.alpha_optim.step()
-            self.alpha = self.log_alpha.exp().detach()
-        if self.itera % self.policy_freq == 0:
-            soft_update(self.critic_target, self.critic, self.tau)
-        self.itera += 1
-        return qf1_loss.detach(), policy_loss.detach()
+        """critic_type != "Transformer": vn/DRL.py:388-434 (and :237-299 when ``extra`` is given) with the ``QNetwork``
+        critic, through the same single C call as the Transformer critic (``dgvit_sac_update`` with cfg.kind ==
+        DGVIT_QNET for the critic slots).  ``noise`` (tests): eps_next / eps_pi rsample draws and mask_a_next / mask_a
+        keep-masks of the two actor passes (+ eps_x / mask_x for the imitation rows; the CNN critic has no dropout).
+        ``extra``: obs, pobs, target, weight of the ``learn_guidence`` imitation rows."""
+        view = lambda t: t.reshape(t.shape[0], -1)
+        b = {k: view(batch[k]) for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew")}
+        if "done" in batch:
+            b["done"] = batch["done"]
+        nz = None
+        if noise is not None:
+            nz = {k: noise.get(k) for k in ("eps_next", "eps_pi", "mask_a_next", "mask_a")}
+            nz["mask_c"] = nz["mask_a"]        # (selects the injected-mask mode; the CNN critic itself draws nothing)
+        ex = None
+        if extra is not None:
+            b["obs"] = torch.cat([b["obs"], view(extra["obs"])])
+            b["pobs"] = torch.cat([b["pobs"], extra["pobs"]])
+            ex = dict(target=extra["target"], weight=extra["weight"])
+            if nz is not None:
+                nz["eps_pi"] = torch.cat([nz["eps_pi"], noise["eps_x"]])
+                nz["mask_a"] = nz["mask_c"] = torch.cat([nz["mask_a"], noise["mask_x"]])
+        if nz is not None:
+            nz = {k: (v.to(torch.uint8) if k.startswith("mask") else v).contiguous() for k, v in nz.items()}
+        b = {k: v.contiguous() for k, v in b.items()}
+        losses = self.update_from_batch(b, nz, extra=ex).tolist()
+        self.alpha = float(self._alpha.item()) if self.automatic_entropy_tuning else self.alpha
+        return losses[0], losses[1]
 
     # ------------------------------------------------------------------ data parallel without NCCL calls
     def _setup_fused_dp(self, keep_reduced: bool = False):
@@ -424,7 +381,8 @@ class SAC(object):
     def _workspace(self, B: int, n_extra: int = 0) -> torch.Tensor:
         n = C.c_size_t()
         prec = {"fp32": L.FP32, "bf16": L.BF16}[self.precision]
-        L.check(L.lib().dgvit_sac_workspace_bytes(C.byref(self.policy._cfg), B, n_extra, prec, C.byref(n)), "sac_workspace")
+        query = L.lib().dgvit_sac_qnet_workspace_bytes if self._cnn_critic else L.lib().dgvit_sac_workspace_bytes
+        L.check(query(C.byref(self.policy._cfg), B, n_extra, prec, C.byref(n)), "sac_workspace")
         if self._ws is None or self._ws.numel() < n.value:
             self._ws = torch.empty(n.value, dtype=torch.uint8, device=self.device)
         return self._ws
@@ -538,13 +496,6 @@ class SAC(object):
 
     def learn(self, batch_size=64):
         """vn/DRL.py:373-437 — returns (qf1_loss, policy_loss) python floats (one D2H read)."""
-        if self._cnn_critic:
-            B = int(batch_size)
-            idx = self.replay_buffer.sample_indexes(B).to(self.device)
-            batch = self._batch_buffers(B)
-            self.replay_buffer.gather(idx, batch)
-            q, p = self._learn_cnn(batch)
-            return float(q), float(p)
         losses = self.learn_async(batch_size)
         l = losses.tolist()
         self.alpha = float(self._alpha.item()) if self.automatic_entropy_tuning else self.alpha
@@ -672,12 +623,6 @@ class SAC(object):
             buf["target"][Be:n_extra].copy_(buf["act"][er])
             buf["weight"][Be:n_extra].fill_(self.engage_weight / (len(eng_rows) * self.action_dim * self.world))
         extra = None if n_extra == 0 else dict(target=buf["target"][:n_extra], weight=buf["weight"][:n_extra])
-        if self._cnn_critic:      # the reference's shipped default (vn/config.yaml:61): CNN critic, module path
-            if extra is not None:
-                extra.update(obs=buf["obs"][Bc:Bc + n_extra], pobs=buf["pobs"][Bc:Bc + n_extra])
-            q, p = self._learn_cnn({k: buf[k][:Bc] for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done")},
-                                   extra=extra)
-            return float(q), float(p)
         losses = self.update_from_batch({k: buf[k] for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done")},
                                         extra=extra).tolist()
         self.alpha = float(self._alpha.item()) if self.automatic_entropy_tuning else self.alpha

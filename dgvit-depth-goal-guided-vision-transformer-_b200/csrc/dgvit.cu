@@ -1249,9 +1249,8 @@ static void sac_phase2(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
 
 template <typename A>
 static void sac_phase3(const dgvit_sac& s, cudaStream_t st) {
-  dgvit_layout La, Lc;
+  dgvit_layout La;
   make_layout(s.actor.cfg, La);
-  make_layout(s.critic.cfg, Lc);
   const bool shadow = s.precision == DGVIT_BF16;
   // temperature step and RNG counter beside the actor's Adam pass
   cudaStream_t lane = lane_fork(st);
@@ -1270,17 +1269,157 @@ static void sac_phase3(const dgvit_sac& s, cudaStream_t st) {
   lane_join(lane, st);
 }
 
+// ------------------------------------------------------------------ SAC.learn with the CNN twin-Q critic
+// critic_type != "Transformer" (vn/DRL.py:118-121, the shipped default vn/config.yaml:61): the critic and its target are
+// QNetwork arenas (dgvit_qnet_layout), cfg.kind == DGVIT_QNET.  Same statements, same three phases and the same loss /
+// Adam / Polyak kernels as the Transformer-critic update; only the critic passes differ (qnet.cuh, no dropout).
+template <typename A>
+struct SacQWs {
+  ActorCtx<A> actor_s;      // saved: policy.sample(s)
+  ActorCtx<A> actor_tmp;    // unsaved: policy.sample(s')
+  qnet::Ws<A> cq;           // critic(s, a) forward + backward, then critic(s, pi) forward + d/d pi
+  qnet::Ws<A> ct;           // critic_target(s', a')
+  float *a2, *logp2, *mean_tmp, *lstd_tmp, *q1t, *q2t, *q1, *q2, *dq1, *dq2, *nq;
+  float *pi, *logpi, *mean_pi, *lstd_pi, *q1p, *q2p, *dpi, *meant_pi, *dlogp, *dmeant;
+};
+template <typename A>
+static void carve_sac_qnet(Carver& cv, const Dims& d, const Dims& da, const qnet::Geo& g, SacQWs<A>& w) {
+  carve_actor<A>(cv, da, true, w.actor_s);
+  carve_actor<A>(cv, d, false, w.actor_tmp);
+  qnet::carve(cv, g, w.cq);
+  qnet::carve(cv, g, w.ct);
+  const int64_t bn = (int64_t)d.B * d.na, an = (int64_t)da.B * d.na;
+  w.a2 = cv.take<float>(bn); w.logp2 = cv.take<float>(d.B);
+  w.mean_tmp = cv.take<float>(bn); w.lstd_tmp = cv.take<float>(bn);
+  w.q1t = cv.take<float>(bn); w.q2t = cv.take<float>(bn);
+  w.q1 = cv.take<float>(bn); w.q2 = cv.take<float>(bn);
+  w.dq1 = cv.take<float>(bn); w.dq2 = cv.take<float>(bn); w.nq = cv.take<float>(bn);
+  w.pi = cv.take<float>(an); w.logpi = cv.take<float>(da.B);
+  w.mean_pi = cv.take<float>(an); w.lstd_pi = cv.take<float>(an);
+  w.q1p = cv.take<float>(bn); w.q2p = cv.take<float>(bn); w.dpi = cv.take<float>(an);
+  w.meant_pi = cv.take<float>(an); w.dlogp = cv.take<float>(da.B); w.dmeant = cv.take<float>(an);
+}
+// the flat QNetwork arena seen by adam_step / the data-parallel exchange: one range, nothing skipped, no 16-bit shadows
+static dgvit_layout qnet_flat_layout(const dgvit_qnet_layout& Lq) {
+  dgvit_layout L;
+  memset(&L, 0, sizeof(L));
+  L.total = Lq.total;
+  return L;
+}
+
+template <typename A>
+static void sac_qnet_run(const dgvit_sac& s, const dgvit_batch* bp, const dgvit_noise* nz, const dgvit_sac_out* outp,
+                         const Dims& d, const Dims& da, const qnet::Geo& g, SacQWs<A>& w, cudaStream_t st, int phases) {
+  dgvit_layout La;
+  make_layout(s.actor.cfg, La);
+  dgvit_qnet_layout Lq;
+  qnet::make_layout(g.na, g.nps, Lq);
+  const dgvit_layout Lc = qnet_flat_layout(Lq);
+  const bool shadow = s.precision == DGVIT_BF16;
+  dgvit_actor_io ap; memset(&ap, 0, sizeof(ap));       // pi, log_pi = policy.sample(s): B rows (+ the imitation rows)
+  if (phases & 3) {
+    ap.img = bp->obs; ap.pstate = bp->pobs; ap.eps = nz ? nz->eps_pi : nullptr;
+    ap.action_scale = s.action_scale; ap.action_bias = s.action_bias;
+    ap.drop = sac_drop(s, nz, nz ? nz->mask_a : nullptr, 4);
+    ap.sample_offset = s.sample_offset;
+    ap.mean = w.mean_pi; ap.log_std = w.lstd_pi; ap.action = w.pi; ap.log_prob = w.logpi; ap.mean_t = w.meant_pi;
+  }
+  if (phases & 1) {
+    const dgvit_batch& b = *bp;
+    const dgvit_sac_out& out = *outp;
+    ForkState f = fork_state();
+    if (!g_fork_enabled) { f.aux[0] = st; f.aux[1] = st; }
+    DG_CUDA(cudaEventRecord(f.fork, st));
+    DG_CUDA(cudaStreamWaitEvent(f.aux[0], f.fork, 0));
+    DG_CUDA(cudaStreamWaitEvent(f.aux[1], f.fork, 0));
+    // ---- forked stream 0: critic(s, a)                                                (DRL.py:395)
+    qnet::forward<A>(s.critic.params, Lq, g, b.obs, b.pobs, b.act, w.q1, w.q2, w.cq, f.aux[0]);
+    DG_CUDA(cudaEventRecord(f.join[0], f.aux[0]));
+    // ---- forked stream 1: policy.sample(s) (the actor is not touched before DRL.py:413)
+    actor_forward<A>(s.actor, La, da, ap, w.actor_s, f.aux[1]);
+    DG_CUDA(cudaEventRecord(f.join[1], f.aux[1]));
+    // ---- caller's stream: a', log pi' = policy.sample(s') ; q_t = critic_target(s', a')   (DRL.py:388-393)
+    dgvit_actor_io ai; memset(&ai, 0, sizeof(ai));
+    ai.img = b.next_obs; ai.pstate = b.next_pobs; ai.eps = nz ? nz->eps_next : nullptr;
+    ai.action_scale = s.action_scale; ai.action_bias = s.action_bias;
+    ai.drop = sac_drop(s, nz, nz ? nz->mask_a_next : nullptr, 1);
+    ai.sample_offset = s.sample_offset;
+    ai.mean = w.mean_tmp; ai.log_std = w.lstd_tmp; ai.action = w.a2; ai.log_prob = w.logp2;
+    actor_forward<A>(s.actor, La, d, ai, w.actor_tmp, st);
+    qnet::forward<A>(s.critic_target.params, Lq, g, b.next_obs, b.next_pobs, w.a2, w.q1t, w.q2t, w.ct, st);
+    // ---- losses + critic backward                                                     (DRL.py:396-401)
+    DG_CUDA(cudaStreamWaitEvent(st, f.join[0], 0));
+    launch_k(critic_loss_kernel, 1, 1024, 0, st, w.q1, w.q2, w.q1t, w.q2t, w.logp2, b.rew, s.alpha, s.gamma, d.B, d.na,
+             s.global_batch, w.nq, w.dq1, w.dq2, out.losses);
+    DG_LAUNCH_CHECK();
+    dp_wait_done(s.dp, 0, Lc, s.critic_opt.step, st);
+    qnet::backward<A>(s.critic.params, s.critic.grads, Lq, g, b.obs, b.pobs, w.dq1, w.dq2, nullptr, true, w.cq, st);
+    if (out.debug) {
+      const size_t bn = (size_t)d.B * d.na * sizeof(float);
+      DG_CUDA(cudaMemcpyAsync(out.debug, w.nq, bn, cudaMemcpyDeviceToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(out.debug + d.B * d.na, w.q1, bn, cudaMemcpyDeviceToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(out.debug + 2 * d.B * d.na, w.q2, bn, cudaMemcpyDeviceToDevice, st));
+    }
+    DG_CUDA(cudaStreamWaitEvent(st, f.join[1], 0));
+  }
+  if (phases & 2) {
+    const dgvit_batch& b = *bp;
+    const dgvit_sac_out& out = *outp;
+    dgvit_net cnet = s.critic;
+    cnet.shadow = nullptr;
+    adam_step(cnet, Lc, s.critic_opt, nullptr, 0.f, false, st, s.dp, 0);                  // DRL.py:402
+    cudaStream_t lane = st;
+    if (s.do_polyak) {                                                                    // DRL.py:430-431, beside the policy half
+      lane = lane_fork(st);
+      launch_k(polyak_kernel, 148 * 4, 256, 0, lane, s.critic_target.params, (const float*)s.critic.params, (bf16*)nullptr, s.tau,
+               Lc.total);
+      DG_LAUNCH_CHECK();
+    }
+    // ---- q_pi = critic(s, pi) with the UPDATED critic                                 (DRL.py:406-407)
+    qnet::forward<A>(s.critic.params, Lq, g, b.obs, b.pobs, w.pi, w.q1p, w.q2p, w.cq, st);
+    launch_k(policy_loss_kernel, 1, 1024, 0, st, w.q1p, w.q2p, w.logpi, s.alpha, s.log_alpha, s.target_entropy, d.B, d.na,
+             s.global_batch, w.dq1, w.dq2, out.losses, s.actor.grads + La.alpha_grad_slot);
+    DG_LAUNCH_CHECK();
+    // d policy_loss / d pi through the critic heads only (its parameter gradients are discarded, DRL.py:399)
+    qnet::backward<A>(s.critic.params, nullptr, Lq, g, b.obs, b.pobs, w.dq1, w.dq2, w.dpi, false, w.cq, st);
+    dgvit_actor_grad ag; memset(&ag, 0, sizeof(ag));
+    ag.d_action = w.dpi;
+    dp_wait_done(s.dp, 1, La, s.actor_opt.step, st);
+    if (da.B == d.B) {
+      actor_backward<A>(s.actor, La, d, ap, ag, s.alpha, 1.0f / (float)s.global_batch, w.actor_s, st);
+    } else {
+      DG_REQUIRE(b.extra_target && b.extra_weight, "n_extra > 0 needs extra_target / extra_weight");
+      launch_k(imitation_grad_kernel, 1, 1024, 0, st, (const float*)w.meant_pi, b.extra_target, b.extra_weight, (const float*)s.alpha,
+               1.0f / (float)s.global_batch, d.B, da.B, d.na, w.dpi, w.dlogp, w.dmeant, out.losses);
+      DG_LAUNCH_CHECK();
+      ag.d_log_prob = w.dlogp;
+      ag.d_mean_t = w.dmeant;
+      actor_backward<A>(s.actor, La, da, ap, ag, nullptr, 0.f, w.actor_s, st);
+    }
+    if (out.debug) {
+      const size_t bn = (size_t)d.B * d.na * sizeof(float);
+      DG_CUDA(cudaMemcpyAsync(out.debug + 3 * d.B * d.na, w.pi, bn, cudaMemcpyDeviceToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(out.debug + 4 * d.B * d.na, w.q1p, bn, cudaMemcpyDeviceToDevice, st));
+      DG_CUDA(cudaMemcpyAsync(out.debug + 5 * d.B * d.na, w.logpi, (size_t)d.B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (lane != st) lane_join(lane, st);
+  }
+  if (phases & 4) sac_phase3<A>(s, st);        // actor Adam, temperature, RNG counter: nothing critic-specific
+  (void)shadow;
+}
+
 static void check_sac(const dgvit_sac& s, int B) {
   DG_REQUIRE(B >= 1, "B must be >= 1");
-  DG_REQUIRE(s.actor.cfg.kind == DGVIT_ACTOR && s.critic.cfg.kind == DGVIT_CRITIC &&
-             s.critic_target.cfg.kind == DGVIT_CRITIC, "sac: wrong network kinds");
+  DG_REQUIRE(s.actor.cfg.kind == DGVIT_ACTOR && (s.critic.cfg.kind == DGVIT_CRITIC || s.critic.cfg.kind == DGVIT_QNET) &&
+             s.critic_target.cfg.kind == s.critic.cfg.kind, "sac: wrong network kinds");
   DG_REQUIRE(s.actor.params && s.actor.grads && s.critic.params && s.critic.grads && s.critic_target.params,
              "sac: null arena");
   DG_REQUIRE(s.alpha && s.log_alpha, "sac: null alpha");
   DG_REQUIRE(s.global_batch >= B, "sac: global_batch < B");
   DG_REQUIRE(s.action_scale && s.action_bias, "sac: null action scale/bias");
   if (s.precision == DGVIT_BF16)
-    DG_REQUIRE(s.actor.shadow && s.critic.shadow && s.critic_target.shadow, "sac: bf16 needs shadow arenas");
+    DG_REQUIRE(s.actor.shadow && (s.critic.cfg.kind == DGVIT_QNET || (s.critic.shadow && s.critic_target.shadow)),
+               "sac: bf16 needs shadow arenas");
 }
 
 template <typename A>
@@ -1404,6 +1543,19 @@ int dgvit_sac_workspace_bytes(const dgvit_cfg* acfg, int B, int n_extra, int pre
     DG_REQUIRE(acfg && bytes && B >= 1 && n_extra >= 0, "bad argument");
     by_precision(precision, [&] { *bytes = sac_ws_bytes<float>(*acfg, B, n_extra); },
                  [&] { *bytes = sac_ws_bytes<bf16>(*acfg, B, n_extra); });
+  });
+}
+
+int dgvit_sac_qnet_workspace_bytes(const dgvit_cfg* acfg, int B, int n_extra, int precision, size_t* bytes) {
+  return guarded([&] {
+    DG_REQUIRE(acfg && bytes && B >= 1 && n_extra >= 0, "bad argument");
+    Dims d(*acfg, B), da(*acfg, B + n_extra);
+    qnet::Geo g(B, acfg->img_h, acfg->img_w, acfg->n_act, acfg->n_pstate);
+    DG_REQUIRE(g.H3 >= 1 && g.W3 >= 1, "qnet: image too small");
+    Carver cv(nullptr, 0, true);
+    by_precision(precision, [&] { SacQWs<float> w; carve_sac_qnet<float>(cv, d, da, g, w); },
+                 [&] { SacQWs<bf16> w; carve_sac_qnet<bf16>(cv, d, da, g, w); });
+    *bytes = cv.off;
   });
 }
 
@@ -1563,6 +1715,7 @@ int dgvit_trunk_backward(const dgvit_net* net, const dgvit_trunk_io* io, const f
   });
 }
 
+static void qnet_check(int img_h, int img_w, int n_act, int n_pstate, int B);
 static int sac_run(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* nz, const dgvit_sac_out* out, int B,
                    void* ws, size_t ws_bytes, void* stream, int phases) {
   return guarded([&] {
@@ -1572,14 +1725,32 @@ static int sac_run(const dgvit_sac* s, const dgvit_batch* b, const dgvit_noise* 
     if (phases & 3) {
       DG_REQUIRE(b && out && out->losses, "null batch/out");
       DG_REQUIRE(b->obs && b->next_obs && b->pobs && b->next_pobs && b->act && b->rew, "null batch tensor");
-      if (nz && nz->drop_mode == DGVIT_DROP_MASK)
-        DG_REQUIRE(nz->mask_a_next && nz->mask_ct && nz->mask_c && nz->mask_a && nz->mask_c_pi, "null mask");
+      if (nz && nz->drop_mode == DGVIT_DROP_MASK) {
+        DG_REQUIRE(nz->mask_a_next && nz->mask_a, "null mask");
+        if (s->critic.cfg.kind != DGVIT_QNET) DG_REQUIRE(nz->mask_ct && nz->mask_c && nz->mask_c_pi, "null mask");
+      }
       if (!nz || !nz->eps_next || !nz->eps_pi || nz->drop_mode == DGVIT_DROP_RNG)
         DG_REQUIRE(s->rng_state, "rng_state required when noise is not injected");
     }
     DG_REQUIRE(s->n_extra >= 0, "n_extra < 0");
     Dims d(s->actor.cfg, B), da(s->actor.cfg, B + s->n_extra);
     cudaStream_t st = (cudaStream_t)stream;
+    if (s->critic.cfg.kind == DGVIT_QNET) {       // CNN twin-Q critic (vn/DRL.py:118-121)
+      const dgvit_cfg& cc = s->critic.cfg;
+      DG_REQUIRE(cc.img_h == s->actor.cfg.img_h && cc.img_w == s->actor.cfg.img_w && cc.n_act == s->actor.cfg.n_act &&
+                 cc.n_pstate == s->actor.cfg.n_pstate, "sac: actor / critic disagree on the input shapes");
+      qnet_check(cc.img_h, cc.img_w, cc.n_act, cc.n_pstate, B);
+      qnet::Geo g(B, cc.img_h, cc.img_w, cc.n_act, cc.n_pstate);
+      auto runq = [&](auto tag) {
+        using A = decltype(tag);
+        Carver cv(ws, ws_bytes);
+        SacQWs<A> w;
+        carve_sac_qnet<A>(cv, d, da, g, w);
+        sac_qnet_run<A>(*s, b, nz, out, d, da, g, w, st, phases);
+      };
+      by_precision(s->precision, [&] { runq(float()); }, [&] { runq(bf16()); });
+      return;
+    }
     auto run = [&](auto tag) {
       using A = decltype(tag);
       Carver cv(ws, ws_bytes);

@@ -830,6 +830,13 @@ class QNetwork(nn.Module):
         self._arena, self._garena, self._ws_cache = arena, torch.zeros_like(arena), {}
         return self
 
+    def net_struct(self) -> L.Net:
+        """The critic / critic_target slot of ``dgvit_sac`` (cfg.kind == DGVIT_QNET: only the input shapes are read)."""
+        self.bind()
+        cfg = L.Cfg(kind=L.QNET, img_h=self.image_size[0], img_w=self.image_size[1], n_act=self.nb_actions,
+                    n_pstate=self.nb_pstate)
+        return L.Net(cfg=cfg, params=self._arena.data_ptr(), grads=self._garena.data_ptr(), shadow=None)
+
     def _precision_code(self) -> int:
         return {"fp32": L.FP32, "bf16": L.BF16}[self.precision]
 

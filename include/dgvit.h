@@ -31,7 +31,9 @@ extern "C" {
 #define DGVIT_MAX_DEPTH 16
 #define DGVIT_ALIGN_FLOATS 64 /* every tensor starts on a 256-byte boundary inside an arena */
 
-enum { DGVIT_ACTOR = 0, DGVIT_CRITIC = 1 };
+enum { DGVIT_ACTOR = 0, DGVIT_CRITIC = 1,
+       DGVIT_QNET = 2 /* CNN twin-Q critic `QNetwork` inside dgvit_sac: params / grads are dgvit_qnet_layout arenas, only
+                         img_h, img_w, n_act, n_pstate of the cfg are read, no shadow */ };
 enum { DGVIT_FP32 = 0, DGVIT_BF16 = 1 };                 /* arithmetic of the contractions */
 enum { DGVIT_DROP_NONE = 0, DGVIT_DROP_MASK = 1, DGVIT_DROP_RNG = 2 };
 
@@ -45,7 +47,7 @@ enum {
 /* Shapes of one network: GoTPolicy(nb_actions, nb_pstate, block, head, l_f_size)
  * vn/got_sac_network.py:173-185 / GoTQNetwork(...) :76-88; GoT(...) vn/GoalFormer.py:124. */
 typedef struct dgvit_cfg {
-  int32_t kind;     /* DGVIT_ACTOR | DGVIT_CRITIC */
+  int32_t kind;     /* DGVIT_ACTOR | DGVIT_CRITIC (| DGVIT_QNET, dgvit_sac.critic / critic_target only) */
   int32_t img_h, img_w, patch_h, patch_w; /* 128,160,16,20 */
   int32_t dim;      /* l_f_size */
   int32_t depth;    /* block */
@@ -243,6 +245,10 @@ int dgvit_workspace_bytes(const dgvit_cfg* cfg, int B, int precision, int save_f
                           size_t* bytes);
 /* bytes of workspace dgvit_sac_* needs for a local batch of B */
 int dgvit_sac_workspace_bytes(const dgvit_cfg* actor_cfg, int B, int n_extra, int precision, size_t* bytes);
+/* the same when dgvit_sac.critic / critic_target are the CNN twin-Q critic (cfg.kind == DGVIT_QNET): the reference's shipped
+ * default critic_type (vn/config.yaml:61, vn/DRL.py:118-121).  dgvit_sac_update / _phase1-3 then run vn/DRL.py:388-434 with
+ * QNetwork passes (vn/got_sac_network.py:125-170) in place of the GoT critic's; critic_opt spans the QNetwork arena. */
+int dgvit_sac_qnet_workspace_bytes(const dgvit_cfg* actor_cfg, int B, int n_extra, int precision, size_t* bytes);
 
 /* refresh both 16-bit shadows of a parameter arena (after load_state_dict etc.) */
 int dgvit_refresh_shadow(const dgvit_net* net, void* stream);

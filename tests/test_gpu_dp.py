@@ -12,9 +12,9 @@ from helpers import O, SEED, synthetic_batch, synthetic_noise
 pytestmark = pytest.mark.gpu
 
 
-def _agent(cfg, distributed, device):
+def _agent(cfg, distributed, device, critic="Transformer"):
     import dgvit_b200 as dg
-    return dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, False, SEED, LR_C=1e-3, LR_A=1e-3,
+    return dg.SAC(2, 2, "GaussianTransformer", critic, False, False, False, SEED, LR_C=1e-3, LR_A=1e-3,
                   LR_ALPHA=1e-4, BUFFER_SIZE=16, TAU=5e-4, POLICY_FREQ=1, GAMMA=0.999, ALPHA=1.0, block=cfg.depth,
                   head=cfg.heads, l_f_size=cfg.dim, precision="fp32", device=device, distributed=distributed)
 
@@ -28,14 +28,14 @@ def _cuda(d, B):
     return out
 
 
-def _worker(rank, world, port, B, steps, out):
+def _worker(rank, world, port, B, steps, out, critic="Transformer"):
     import torch.distributed as dist
     from dgvit_b200.parallel import shard_batch
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     cfg = O.Cfg(dim=32, depth=2, heads=2)
-    ag = _agent(cfg, True, f"cuda:{rank}")
+    ag = _agent(cfg, True, f"cuda:{rank}", critic)
     for s in range(steps):
         batch, noise = synthetic_batch(cfg, B, 100 + s), synthetic_noise(cfg, B, 200 + s)
         lb, ln = shard_batch(batch, world, rank), shard_batch(noise, world, rank)
@@ -49,16 +49,17 @@ def _worker(rank, world, port, B, steps, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_dp2_equals_single_gpu(tmp_path):
+@pytest.mark.parametrize("critic", ["Transformer", "CNN"])
+def test_dp2_equals_single_gpu(tmp_path, critic):
     B, steps = 8, 2
     out = str(tmp_path / "dp.pt")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, B, steps, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, B, steps, out, critic), nprocs=2, join=True)
     got = torch.load(out)
     cfg = O.Cfg(dim=32, depth=2, heads=2)
-    ag = _agent(cfg, False, "cuda:0")
+    ag = _agent(cfg, False, "cuda:0", critic)
     for s in range(steps):
         batch, noise = synthetic_batch(cfg, B, 100 + s), synthetic_noise(cfg, B, 200 + s)
         ag.update_from_batch(_cuda(batch, B), _cuda(noise, B))

@@ -235,3 +235,58 @@ def test_sac_learn_guidence_with_cnn_critic():
     for _ in range(2):
         q, p = ag.learn_guidence(False, 6)
         assert np.isfinite(q) and np.isfinite(p)
+
+
+def _cnn_agent(seed, precision, **kw):
+    return dg.SAC(2, 2, "GaussianTransformer", "CNN", False, False, False, seed, LR_C=1e-3, LR_A=1e-3, LR_ALPHA=1e-4,
+                  BUFFER_SIZE=256, TAU=5e-3, POLICY_FREQ=1, GAMMA=0.99, ALPHA=0.2, block=4, head=4, l_f_size=64,
+                  precision=precision, **kw)
+
+
+@pytest.mark.gpu
+def test_cnn_critic_update_bf16_tracks_fp32_at_the_shipped_preset():
+    """The single-call update with the CNN critic at the shipped preset (D=64, 4 blocks, 4 heads), B=64: the bf16 path
+    (tcgen05 convolution GEMMs, fused MLP) against the fp32 path of the same library on the same batch and injected noise
+    (the fp32 path is the one checked against the oracle above): TD target, Q, actions, losses, critic gradients."""
+    from oracle.init_params import synthetic_noise
+    cfg = O.Cfg()
+    B = 64
+    batch, nz = synthetic_batch(cfg, B, 700), synthetic_noise(cfg, B, 701)
+    gb = {k: v.reshape(B, -1).cuda().contiguous() for k, v in batch.items()}
+    noise = {k: nz[k].cuda() for k in ("eps_next", "eps_pi", "mask_a_next", "mask_a")}
+    noise = {k: (v.to(torch.uint8) if k.startswith("mask") else v).contiguous() for k, v in noise.items()}
+    noise["mask_c"] = noise["mask_a"]
+    res = {}
+    for prec in ("fp32", "bf16"):
+        ag = _cnn_agent(5, prec)
+        dbg = torch.zeros(B * 11, device="cuda")
+        losses = ag.update_from_batch(gb, noise, debug=dbg).tolist()
+        res[prec] = (losses, dbg.cpu(), ag.critic._garena.detach().cpu().clone(), ag.policy._garena.detach().cpu().clone())
+    (lf, df, gcf, gaf), (lb, db, gcb, gab) = res["fp32"], res["bf16"]
+    n2 = B * 2
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+    assert rel(db[:n2], df[:n2]) < 2e-2            # TD target
+    assert rel(db[n2:2 * n2], df[n2:2 * n2]) < 2e-2    # Q1(s, a)
+    assert rel(db[3 * n2:4 * n2], df[3 * n2:4 * n2]) < 2e-2    # pi
+    assert abs(lb[0] - lf[0]) <= 3e-2 * abs(lf[0]) and abs(lb[1] - lf[1]) <= 3e-2 * max(1.0, abs(lf[1])), (lb, lf)
+    cos = lambda a, b: float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30))
+    assert cos(gcb, gcf) > 0.99 and 0.95 < float(gcb.norm() / gcf.norm()) < 1.05
+    assert cos(gab, gaf) > 0.97
+
+
+@pytest.mark.gpu
+def test_cnn_critic_graph_replay_equals_eager():
+    """``learn_async`` with the CNN critic: eager, captured and replayed updates of one agent follow the same trajectory as an
+    agent that never uses a graph (same seed: same sampled indexes, same in-kernel Philox streams)."""
+    out = {}
+    for graph in (False, True):
+        ag = _cnn_agent(9, "fp32", use_cuda_graph=graph)
+        ag.replay_buffer.fill_synthetic(200, seed=3)
+        ls = [ag.learn_async(8).clone() for _ in range(5)]
+        torch.cuda.synchronize()
+        out[graph] = (torch.stack(ls).cpu(), ag.critic._arena.detach().cpu().clone(), ag.policy._arena.detach().cpu().clone(),
+                      ag.critic_target._arena.detach().cpu().clone())
+        ag.close()
+    for a, b in zip(out[False], out[True]):
+        assert torch.isfinite(a).all()
+        assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(a.abs().max()))
