@@ -170,11 +170,15 @@ static void linear_bwd_w(const TA* dy, const TB* x, float* dW, float* db, int64_
   g.splitk = pick_splitk(R); g.partial = partial;
   gemm<TA, TB, float>(g, st);
   if (db) {
-    const int S = (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 128);   // row ranges per column block
+    // long, narrow dy (the CNN critic's convolutions): whole-row warps, many row ranges
+    const bool tall = R >= 32768 && N % 2 == 0 && N <= 512 && 256 % (N / 2) == 0 && ldy % 2 == 0 && ((((uintptr_t)dy) & 7) == 0);
+    const int S = tall ? (int)std::min<int64_t>(R / 256, 148 * 4)
+                       : (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 128);   // row ranges per column block
     const int64_t rpb = cdiv(R, S);
     dim3 grid((unsigned)cdiv(N, 256), (unsigned)S);
     if (defer) partial = defer->alloc((size_t)S * N);      // the GEMM's partials may still be queued
-    launch_k(colsum_partial_kernel<TA>, grid, 128, 0, st, dy, ldy, partial, R, N, rpb);
+    if (tall) launch_k(colsum_tall_kernel<TA>, (unsigned)S, 256, 0, st, dy, ldy, partial, R, N, rpb);
+    else launch_k(colsum_partial_kernel<TA>, grid, 128, 0, st, dy, ldy, partial, R, N, rpb);
     DG_LAUNCH_CHECK();
     if (defer && N % 4 == 0) {
       defer->add(partial, db, S, N, N);

@@ -350,6 +350,37 @@ __global__ void colsum_partial_kernel(const T_* __restrict__ A, int64_t lda, flo
   }
 }
 
+// The same for long, narrow matrices (the CNN critic's conv bias gradients: 274k rows x 64 columns): with one thread per
+// column pair the launch above has 32 active threads per block.  Here a block covers N/2 column pairs x (256 / (N/2)) row
+// lanes (a warp reads one or more whole rows), four rows in flight per thread, row lanes summed through shared memory
+// in a fixed order.  N even, N/2 a divisor of 256.
+template <typename T_>
+__global__ void __launch_bounds__(256) colsum_tall_kernel(const T_* __restrict__ A, int64_t lda, float* __restrict__ part,
+                                                          int64_t rows, int N, int64_t rows_per_block) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float2 sm[256];
+  const int cp = N / 2, nrl = 256 / cp;
+  const int c = threadIdx.x % cp, rl = threadIdx.x / cp;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+  int64_t r = r0 + rl;
+  for (; r + 3 * nrl < r1; r += 4 * nrl) {
+    const float2 x0 = ld2(A + r * lda + 2 * c), x1 = ld2(A + (r + nrl) * lda + 2 * c);
+    const float2 x2 = ld2(A + (r + 2 * nrl) * lda + 2 * c), x3 = ld2(A + (r + 3 * nrl) * lda + 2 * c);
+    s0.x += x0.x; s0.y += x0.y; s1.x += x1.x; s1.y += x1.y; s2.x += x2.x; s2.y += x2.y; s3.x += x3.x; s3.y += x3.y;
+  }
+  for (; r < r1; r += nrl) { const float2 x = ld2(A + r * lda + 2 * c); s0.x += x.x; s0.y += x.y; }
+  sm[threadIdx.x] = make_float2((s0.x + s1.x) + (s2.x + s3.x), (s0.y + s1.y) + (s2.y + s3.y));
+  __syncthreads();
+  if (rl == 0) {
+    float2 t = sm[c];
+    for (int k = 1; k < nrl; ++k) { const float2 v = sm[k * cp + c]; t.x += v.x; t.y += v.y; }
+    part[(int64_t)blockIdx.x * N + 2 * c] = t.x;
+    part[(int64_t)blockIdx.x * N + 2 * c + 1] = t.y;
+  }
+}
+
 // =====================================================================================
 // Last-block attention.  Only token 0 of the last block's output is consumed (x[:, 0], vn/GoalFormer.py:167), so
 // there the attention needs a single query row per (sample, head): o0 = softmax(q0 K^T * dh^-0.5) V.  K and V

@@ -101,52 +101,107 @@ template <> __device__ __forceinline__ float4 ld4<bf16>(const bf16* p) {
                      __uint_as_float(u.y & 0xffff0000u));
 }
 
-// patch matrix: col[(b,oy,ox)][tap*C + c] = A[b, 2oy+ky, 2ox+kx, c].  Work item = (row, tap, 4 channels).
+// patch matrix: col[(b,oy,ox)][tap*C + c] = A[b, 2oy+ky, 2ox+kx, c].  Work item = 8 consecutive elements of col (one 16-byte
+// store in the bf16 path): consecutive threads write consecutive pieces of a col row and read consecutive channel groups
+// of one input pixel (and, for C = 16, of the next tap's pixel, which is the next pixel of the frame): both sides are
+// coalesced.  Four items per thread are loaded before the first is stored.
+template <typename T> __device__ __forceinline__ void st8(T* p, const float4& a, const float4& b);
+template <> __device__ __forceinline__ void st8<float>(float* p, const float4& a, const float4& b) {
+  reinterpret_cast<float4*>(p)[0] = a; reinterpret_cast<float4*>(p)[1] = b;
+}
+template <> __device__ __forceinline__ void st8<bf16>(bf16* p, const float4& a, const float4& b) {
+  const __nv_bfloat162 v0 = __floats2bfloat162_rn(a.x, a.y), v1 = __floats2bfloat162_rn(a.z, a.w);
+  const __nv_bfloat162 v2 = __floats2bfloat162_rn(b.x, b.y), v3 = __floats2bfloat162_rn(b.z, b.w);
+  uint4 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&v0); u.y = *reinterpret_cast<const uint32_t*>(&v1);
+  u.z = *reinterpret_cast<const uint32_t*>(&v2); u.w = *reinterpret_cast<const uint32_t*>(&v3);
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
 template <typename T>
-__global__ void im2col_kernel(const float* __restrict__ A, T* __restrict__ col, int64_t items, int Hi, int Wi, int Ho, int Wo,
-                              int C) {
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ A, T* __restrict__ col, int64_t items, int Hi, int Wi,
+                                                     int Ho, int Wo, int C) {
   pdl_wait();
   pdl_launch();
-  const int C4 = C / 4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    const int tap = (int)((i / C4) % TAPS);
-    const int64_t r = i / ((int64_t)C4 * TAPS);
-    const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho);
-    const int64_t b = r / ((int64_t)Wo * Ho);
-    const int ky = tap / KS, kx = tap % KS;
-    const float4 v = *reinterpret_cast<const float4*>(A + ((b * Hi + oy * ST + ky) * Wi + ox * ST + kx) * C + c4 * 4);
-    st4<T>(col + r * ((int64_t)TAPS * C) + tap * C + c4 * 4, v);
+  const int C8 = C / 8;
+  const int per_row = TAPS * C8;
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < items; i0 += U * stride) {
+    float4 va[U], vb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < items) {
+        const int64_t r = i / per_row;
+        const int q = (int)(i - r * per_row);
+        const int tap = q / C8, c8 = q - tap * C8;
+        const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho);
+        const int64_t bimg = r / ((int64_t)Wo * Ho);
+        const int ky = tap / KS, kx = tap - ky * KS;
+        const float4* src = reinterpret_cast<const float4*>(A + ((bimg * Hi + oy * ST + ky) * Wi + ox * ST + kx) * C + c8 * 8);
+        va[u] = __ldg(src); vb[u] = __ldg(src + 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < items) st8<T>(col + i * 8, va[u], vb[u]);
+    }
   }
 }
 
-// dA[b,iy,ix,c] = relu'(A) * sum over the (<= 3x3) output pixels whose window covers (iy,ix) of dcol[(b,oy,ox)][tap*C+c]
+// dA[b,iy,ix,c] = relu'(A) * sum over the (<= 3x3) output pixels whose window covers (iy,ix) of dcol[(b,oy,ox)][tap*C+c].
+// Work item = (input pixel, 8 channels): 16-byte loads of dcol in the bf16 path, all (<= 9) of them issued before the sum.
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float4& a, float4& b);
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float4& a, float4& b) {
+  a = reinterpret_cast<const float4*>(p)[0]; b = reinterpret_cast<const float4*>(p)[1];
+}
+template <> __device__ __forceinline__ void ld8<bf16>(const bf16* p, float4& a, float4& b) {
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+  a = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                  __uint_as_float(u.y & 0xffff0000u));
+  b = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u), __uint_as_float(u.w << 16),
+                  __uint_as_float(u.w & 0xffff0000u));
+}
 template <typename T, typename TO>
-__global__ void col2im_kernel(const T* __restrict__ dcol, const float* __restrict__ A, TO* __restrict__ dA, int64_t items,
-                              int Hi, int Wi, int Ho, int Wo, int C) {
+__global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ dcol, const float* __restrict__ A, TO* __restrict__ dA,
+                                                     int64_t items, int Hi, int Wi, int Ho, int Wo, int C) {
   pdl_wait();
   pdl_launch();
-  const int C4 = C / 4;
+  const int C8 = C / 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    const int64_t pix = i / C4;
+    const int c8 = (int)(i % C8);
+    const int64_t pix = i / C8;
     const int ix = (int)(pix % Wi), iy = (int)((pix / Wi) % Hi);
     const int64_t b = pix / ((int64_t)Wi * Hi);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int ky = iy & 1; ky < KS; ky += 2) {
-      const int oy = (iy - ky) / 2;
-      if (iy - ky < 0 || oy >= Ho) continue;
-      for (int kx = ix & 1; kx < KS; kx += 2) {
-        const int ox = (ix - kx) / 2;
-        if (ix - kx < 0 || ox >= Wo) continue;
-        const float4 v = ld4<T>(dcol + ((b * Ho + oy) * Wo + ox) * ((int64_t)TAPS * C) + (ky * KS + kx) * C + c4 * 4);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    float4 va[9], vb[9];
+    int n = 0;
+#pragma unroll
+    for (int jy = 0; jy < 3; ++jy) {
+      const int ky = (iy & 1) + 2 * jy, oy = (iy - ky) / 2;
+      const bool oky = ky < KS && iy - ky >= 0 && oy < Ho;
+#pragma unroll
+      for (int jx = 0; jx < 3; ++jx) {
+        const int kx = (ix & 1) + 2 * jx, ox = (ix - kx) / 2;
+        va[n] = vb[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (oky && kx < KS && ix - kx >= 0 && ox < Wo)
+          ld8<T>(dcol + ((b * Ho + oy) * Wo + ox) * ((int64_t)TAPS * C) + (ky * KS + kx) * C + c8 * 8, va[n], vb[n]);
+        ++n;
       }
     }
-    const float4 a = *reinterpret_cast<const float4*>(A + pix * C + c4 * 4);
-    acc.x = a.x > 0.f ? acc.x : 0.f; acc.y = a.y > 0.f ? acc.y : 0.f;
-    acc.z = a.z > 0.f ? acc.z : 0.f; acc.w = a.w > 0.f ? acc.w : 0.f;
-    st4<TO>(dA + pix * C + c4 * 4, acc);
+    float4 s0 = va[0], s1 = vb[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) {
+      s0.x += va[k].x; s0.y += va[k].y; s0.z += va[k].z; s0.w += va[k].w;
+      s1.x += vb[k].x; s1.y += vb[k].y; s1.z += vb[k].z; s1.w += vb[k].w;
+    }
+    const float4 a0 = *reinterpret_cast<const float4*>(A + pix * C + c8 * 8), a1 = *reinterpret_cast<const float4*>(A + pix * C + c8 * 8 + 4);
+    s0.x = a0.x > 0.f ? s0.x : 0.f; s0.y = a0.y > 0.f ? s0.y : 0.f; s0.z = a0.z > 0.f ? s0.z : 0.f; s0.w = a0.w > 0.f ? s0.w : 0.f;
+    s1.x = a1.x > 0.f ? s1.x : 0.f; s1.y = a1.y > 0.f ? s1.y : 0.f; s1.z = a1.z > 0.f ? s1.z : 0.f; s1.w = a1.w > 0.f ? s1.w : 0.f;
+    st4<TO>(dA + pix * C + c8 * 8, s0);
+    st4<TO>(dA + pix * C + c8 * 8 + 4, s1);
   }
 }
 
@@ -239,45 +294,62 @@ __global__ void split_kernel(const float* __restrict__ dxa, const float* __restr
 }
 
 // conv1 weight / bias gradient: part[block][c*25 + tap] = sum over this block's output pixels of dY1[p][c] * x[p, tap],
-// part[block][400 + c] = sum dY1[p][c].  400 threads = (c, tap); pixels staged 64 at a time in shared memory.
-constexpr int C1W_PIX = 64, C1W_THREADS = C1 * TAPS;
+// part[block][400 + c] = sum dY1[p][c].  128 pixels are staged per round; each of the 4 warps takes 32 of them with
+// lane = tap (lane 25 multiplies by 1: the bias sums) and all 16 channels in registers, so a pixel costs one shared load of
+// x and four broadcast 16-byte loads of dY1 for 16 FMAs per lane (the first version had one accumulator per thread and two
+// shared loads per FMA: 370 us at B = 256).
+constexpr int C1W_PIX = 128, C1W_THREADS = 128, C1W_N = C1 * TAPS + C1;
 __global__ void __launch_bounds__(C1W_THREADS) conv1_bwd_w_kernel(const float* __restrict__ dY1, const float* __restrict__ x,
                                                                  float* __restrict__ part, int64_t R1, int64_t pix_per_block,
                                                                  int H0, int W0, int H1, int W1) {
   pdl_wait();
   pdl_launch();
-  __shared__ float dys[C1W_PIX][C1 + 1];
-  __shared__ float xs[C1W_PIX][TAPS + 2];
-  const int tid = threadIdx.x, c = tid / TAPS, tap = tid % TAPS;
+  __shared__ __align__(16) float dys[C1W_PIX][C1];
+  __shared__ float xs[C1W_PIX][TAPS];
+  __shared__ float red[4][C1W_N];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t p0 = (int64_t)blockIdx.x * pix_per_block, p1 = min(R1, p0 + pix_per_block);
-  float acc = 0.f, accb = 0.f;
+  float acc[C1];
+#pragma unroll
+  for (int c = 0; c < C1; ++c) acc[c] = 0.f;
   for (int64_t q0 = p0; q0 < p1; q0 += C1W_PIX) {
     __syncthreads();
-    for (int i = tid; i < C1W_PIX * C1; i += C1W_THREADS) {
-      const int64_t p = q0 + i / C1;
-      dys[i / C1][i % C1] = p < p1 ? dY1[p * C1 + i % C1] : 0.f;
+    for (int i = tid; i < C1W_PIX * (C1 / 4); i += C1W_THREADS) {
+      const int64_t p = q0 + i / (C1 / 4);
+      reinterpret_cast<float4*>(&dys[0][0])[i] =
+          p < p1 ? __ldg(reinterpret_cast<const float4*>(dY1 + p * C1) + i % (C1 / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int i = tid; i < C1W_PIX * TAPS; i += C1W_THREADS) {
-      const int64_t p = q0 + i / TAPS;
+      const int s = i / TAPS, t = i - s * TAPS;
+      const int64_t p = q0 + s;
       float v = 0.f;
       if (p < p1) {
-        const int t = i % TAPS, ox = (int)(p % W1), oy = (int)((p / W1) % H1);
+        const int ox = (int)(p % W1), oy = (int)((p / W1) % H1);
         const int64_t bi = p / ((int64_t)W1 * H1);
         v = __ldg(x + (bi * H0 + oy * ST + t / KS) * W0 + ox * ST + t % KS);
       }
-      xs[i / TAPS][i % TAPS] = v;
+      xs[s][t] = v;
     }
     __syncthreads();
-#pragma unroll 8
-    for (int s = 0; s < C1W_PIX; ++s) {
-      const float d = dys[s][c];
-      acc = fmaf(d, xs[s][tap], acc);
-      accb += d;
+#pragma unroll 4
+    for (int s = warp * 32; s < warp * 32 + 32; ++s) {
+      const float xv = lane < TAPS ? xs[s][lane] : 1.0f;
+      const float4* d = reinterpret_cast<const float4*>(&dys[s][0]);
+#pragma unroll
+      for (int c4 = 0; c4 < C1 / 4; ++c4) {
+        const float4 v = d[c4];
+        acc[4 * c4] = fmaf(v.x, xv, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(v.y, xv, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(v.z, xv, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(v.w, xv, acc[4 * c4 + 3]);
+      }
     }
   }
-  float* P = part + (int64_t)blockIdx.x * (C1 * TAPS + C1);
-  P[c * TAPS + tap] = acc;
-  if (tap == 0) P[C1 * TAPS + c] = accb;
+  if (lane <= TAPS) {
+#pragma unroll
+    for (int c = 0; c < C1; ++c) red[warp][lane < TAPS ? c * TAPS + lane : C1 * TAPS + c] = acc[c];
+  }
+  __syncthreads();
+  float* P = part + (int64_t)blockIdx.x * C1W_N;
+  for (int j = tid; j < C1W_N; j += C1W_THREADS) P[j] = (red[0][j] + red[1][j]) + (red[2][j] + red[3][j]);
 }
 
 // out_a[j] (j < split) / out_b[j - split] = sum over nb partial rows of part[k][j], k ascending
@@ -304,7 +376,7 @@ struct Ws {
   float *A1, *A2, *A3, *pooled, *xcat, *h1a, *h2a, *h1b, *h2b;
   T *col2, *col3, *Wp2, *Wp3;
   // backward
-  float *dxa, *dxb, *dx, *demb, *dh1a, *dh2a, *dh1b, *dh2b, *dY1, *dWp, *partial;
+  float *dxa, *dxb, *dx, *demb, *dh1a, *dh2a, *dh1b, *dh2b, *dY1, *dWp, *dWp2, *partial;
   T *dY3, *dY2, *dcol;
   size_t partial_floats;
 };
@@ -328,10 +400,13 @@ static void carve(Carver& cv, const Geo& g, Ws<T>& w) {
   w.dh1b = cv.take<float>((int64_t)g.B * 128); w.dh2b = cv.take<float>((int64_t)g.B * 32);
   w.dY1 = cv.take<float>(g.R1 * C1);
   w.dWp = cv.take<float>((int64_t)C3 * TAPS * C2);
+  w.dWp2 = cv.take<float>((int64_t)C2 * TAPS * C1);
   w.dY3 = cv.take<T>(g.R3 * C3);
   w.dY2 = cv.take<T>(g.R2 * C2);
   w.dcol = cv.take<T>(std::max(g.R3 * (int64_t)(TAPS * C2), g.R2 * (int64_t)(TAPS * C1)));
-  w.partial_floats = (size_t)32 * C3 * TAPS * C2;                       // split-K partials of the largest dW
+  // split-K partials of both dW GEMMs, column-sum partials of the bias gradients, conv1's per-block partials: all reduced
+  // by ONE deferred launch at the end of the backward
+  w.partial_floats = (size_t)32 * C3 * TAPS * C2 + (size_t)32 * C2 * TAPS * C1 + ((size_t)1 << 21);
   w.partial = cv.take<float>(w.partial_floats);
 }
 
@@ -351,8 +426,8 @@ static void forward(const float* P, const dgvit_qnet_layout& L, const Geo& g, co
     const int64_t n = (int64_t)C2 * TAPS * C1;
     launch_k(wperm_kernel<T>, (unsigned)cdiv(n, 256), 256, 0, st, P + L.conv_w[1], w.Wp2, n, C1);
     DG_LAUNCH_CHECK();
-    const int64_t items = g.R2 * TAPS * (C1 / 4);
-    launch_k(im2col_kernel<T>, gs(items), 256, 0, st, (const float*)w.A1, w.col2, items, g.H1, g.W1, g.H2, g.W2, C1);
+    const int64_t items = g.R2 * TAPS * (C1 / 8);
+    launch_k(im2col_kernel<T>, gs(cdiv(items, 4)), 256, 0, st, (const float*)w.A1, w.col2, items, g.H1, g.W1, g.H2, g.W2, C1);
     DG_LAUNCH_CHECK();
     linear_fwd<T, T, float>(w.col2, w.Wp2, w.A2, g.R2, C2, TAPS * C1, EPI_BIAS_RELU, P + L.conv_b[1], st);
   }
@@ -361,8 +436,8 @@ static void forward(const float* P, const dgvit_qnet_layout& L, const Geo& g, co
     const int64_t n = (int64_t)C3 * TAPS * C2;
     launch_k(wperm_kernel<T>, (unsigned)cdiv(n, 256), 256, 0, st, P + L.conv_w[2], w.Wp3, n, C2);
     DG_LAUNCH_CHECK();
-    const int64_t items = g.R3 * TAPS * (C2 / 4);
-    launch_k(im2col_kernel<T>, gs(items), 256, 0, st, (const float*)w.A2, w.col3, items, g.H2, g.W2, g.H3, g.W3, C2);
+    const int64_t items = g.R3 * TAPS * (C2 / 8);
+    launch_k(im2col_kernel<T>, gs(cdiv(items, 4)), 256, 0, st, (const float*)w.A2, w.col3, items, g.H2, g.W2, g.H3, g.W3, C2);
     DG_LAUNCH_CHECK();
     linear_fwd<T, T, float>(w.col3, w.Wp3, w.A3, g.R3, C3, TAPS * C2, EPI_BIAS_RELU, P + L.conv_b[2], st);
   }
@@ -382,14 +457,11 @@ static void forward(const float* P, const dgvit_qnet_layout& L, const Geo& g, co
   heads::launch_fwd(h, st);
 }
 
-// conv layer backward through the patch matrix: dW (tap-permuted, then restored), db, and (optionally) dcol
+// conv layer weight gradient through the patch matrix: dWp (tap-permuted; split-K partials queued on `rl`) and db
 template <typename T>
-static void conv_bwd_w(const T* dY, const T* col, float* dW, float* db, int64_t R, int Cout, int Cin, Ws<T>& w, cudaStream_t st) {
-  const int K = TAPS * Cin;
-  linear_bwd_w<T, T>(dY, col, w.dWp, db, R, Cout, K, w.partial, st);
-  const int64_t n = (int64_t)Cout * K;
-  launch_k(wperm_back_kernel, (unsigned)cdiv(n, 256), 256, 0, st, (const float*)w.dWp, dW, n, Cin);
-  DG_LAUNCH_CHECK();
+static void conv_bwd_w(const T* dY, const T* col, float* dWp, float* db, int64_t R, int Cout, int Cin, ReduceList& rl,
+                       cudaStream_t st) {
+  linear_bwd_w<T, T>(dY, col, dWp, db, R, Cout, TAPS * Cin, nullptr, st, -1, -1, &rl);
 }
 
 template <typename T>
@@ -418,38 +490,43 @@ static void backward(const float* P, float* G, const dgvit_qnet_layout& L, const
     dw.add(w.demb, EMB, pstate, G + L.embed_w, G + L.embed_b, EMB, g.nps);
     dw.launch(st);
   }
+  ReduceList rl(w.partial, w.partial_floats);
   // conv3
   {
     const int64_t items = g.R3 * (C3 / 4);
     launch_k(avgpool_bwd_kernel<T>, gs(items), 256, 0, st, (const float*)w.dx, g.K0, (const float*)w.A3, w.dY3, items, g.H3 * g.W3);
     DG_LAUNCH_CHECK();
-    conv_bwd_w<T>(w.dY3, w.col3, G + L.conv_w[2], G + L.conv_b[2], g.R3, C3, C2, w, st);
+    conv_bwd_w<T>(w.dY3, w.col3, w.dWp, G + L.conv_b[2], g.R3, C3, C2, rl, st);
     linear_bwd_x<T, T, T>(w.dY3, w.Wp3, w.dcol, g.R3, C3, TAPS * C2, EPI_NONE, nullptr, 0, st);
-    const int64_t it2 = g.R2 * (C2 / 4);
+    const int64_t it2 = g.R2 * (C2 / 8);
     launch_k(col2im_kernel<T, T>, gs(it2), 256, 0, st, (const T*)w.dcol, (const float*)w.A2, w.dY2, it2, g.H2, g.W2, g.H3, g.W3, C2);
     DG_LAUNCH_CHECK();
   }
   // conv2
   {
-    conv_bwd_w<T>(w.dY2, w.col2, G + L.conv_w[1], G + L.conv_b[1], g.R2, C2, C1, w, st);
+    conv_bwd_w<T>(w.dY2, w.col2, w.dWp2, G + L.conv_b[1], g.R2, C2, C1, rl, st);
     linear_bwd_x<T, T, T>(w.dY2, w.Wp2, w.dcol, g.R2, C2, TAPS * C1, EPI_NONE, nullptr, 0, st);
-    const int64_t it1 = g.R1 * (C1 / 4);
+    const int64_t it1 = g.R1 * (C1 / 8);
     launch_k(col2im_kernel<T, float>, gs(it1), 256, 0, st, (const T*)w.dcol, (const float*)w.A1, w.dY1, it1, g.H1, g.W1, g.H2, g.W2, C1);
     DG_LAUNCH_CHECK();
   }
   // conv1
   {
-    const int nblocks = (int)std::min<int64_t>(148 * 4, cdiv(g.R1, C1W_PIX));
+    const int nblocks = (int)std::min<int64_t>(148 * 8, cdiv(g.R1, C1W_PIX));
     const int64_t ppb = cdiv(cdiv(g.R1, nblocks), C1W_PIX) * C1W_PIX;
     const int nb = (int)cdiv(g.R1, ppb);
-    const int64_t n = C1 * TAPS + C1;
-    DG_REQUIRE((size_t)nb * n <= w.partial_floats, "qnet: partial buffer too small");
-    launch_k(conv1_bwd_w_kernel, nb, C1W_THREADS, 0, st, (const float*)w.dY1, img, w.partial, g.R1, ppb, g.H0, g.W0, g.H1, g.W1);
+    float* part = rl.alloc((size_t)nb * C1W_N);
+    launch_k(conv1_bwd_w_kernel, nb, C1W_THREADS, 0, st, (const float*)w.dY1, img, part, g.R1, ppb, g.H0, g.W0, g.H1, g.W1);
     DG_LAUNCH_CHECK();
-    // conv1.weight (400) and conv1.bias (16) are adjacent only up to the arena alignment: two reductions
-    DG_REQUIRE(L.conv_b[0] - L.conv_w[0] >= C1 * TAPS, "qnet layout");
-    launch_k(reduce_cols_kernel, (unsigned)cdiv(n, 128), 128, 0, st, (const float*)w.partial, G + L.conv_w[0], G + L.conv_b[0],
-             nb, (int)n, C1 * TAPS);
+    rl.add(part, G + L.conv_w[0], nb, C1 * TAPS, C1W_N);
+    rl.add(part + C1 * TAPS, G + L.conv_b[0], nb, C1, C1W_N);
+  }
+  rl.launch(st);       // every split-K / column-sum / per-block partial of this backward, one launch, fixed summation order
+  {
+    const int64_t n3 = (int64_t)C3 * TAPS * C2, n2 = (int64_t)C2 * TAPS * C1;
+    launch_k(wperm_back_kernel, (unsigned)cdiv(n3, 256), 256, 0, st, (const float*)w.dWp, G + L.conv_w[2], n3, C2);
+    DG_LAUNCH_CHECK();
+    launch_k(wperm_back_kernel, (unsigned)cdiv(n2, 256), 256, 0, st, (const float*)w.dWp2, G + L.conv_w[1], n2, C1);
     DG_LAUNCH_CHECK();
   }
 }

@@ -42,8 +42,18 @@ for prec in ("bf16", "fp32"):
     tf, tb = timeit(fwd), timeit(fwdbwd)
     print(f"QNetwork B={B} {prec}: forward {tf:8.1f} us ({B * FLOP / tf / 1e6:6.1f} TFLOP/s algorithmic), "
           f"forward+backward {tb:8.1f} us ({3 * B * FLOP / tb / 1e6:6.1f} TFLOP/s)")
-ag = dg.SAC(2, 2, "GaussianTransformer", "CNN", False, False, False, 3407, BUFFER_SIZE=4096, block=4, head=4, l_f_size=64,
-            precision="bf16")
-ag.replay_buffer.fill_synthetic(4096)
-t = timeit(lambda: ag.learn(B), iters=5)
-print(f"SAC.learn critic_type='CNN' (module path, autograd glue) B={B}: {t / 1e3:.2f} ms/update = {B / t * 1e6:.0f} samples/s")
+for graph in (False, True):
+    ag = dg.SAC(2, 2, "GaussianTransformer", "CNN", False, False, False, 3407, BUFFER_SIZE=4096, block=4, head=4, l_f_size=64,
+                precision="bf16", use_cuda_graph=graph)
+    ag.replay_buffer.fill_synthetic(4096)
+    for _ in range(4):
+        ag.learn_async(B)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ag.learn_async(B)
+    e1.record(); torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e3 / 20
+    print(f"SAC.learn_async critic_type='CNN' (dgvit_sac_update, graph={graph}) B={B}: {t / 1e3:.2f} ms/update = {B / t * 1e6:.0f} samples/s")
+    ag.close()
