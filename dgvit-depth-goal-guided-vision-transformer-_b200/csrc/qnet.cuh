@@ -53,8 +53,10 @@ static void make_layout(int na, int nps, dgvit_qnet_layout& L) {
 
 // ------------------------------------------------------------------ kernels
 // conv1 + ReLU: x [B,H0,W0] -> A1 [B,H1,W1,16].  Thread = output pixel, 16 channel accumulators.
+template <typename T> __device__ __forceinline__ void st4(T* p, float4 v);
+template <typename TO>
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ b, float* __restrict__ out, int64_t R1,
+                                                        const float* __restrict__ b, TO* __restrict__ out, int64_t R1,
                                                         int H0, int W0, int H1, int W1) {
   pdl_wait();
   pdl_launch();
@@ -63,10 +65,9 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
   for (int i = threadIdx.x; i < TAPS * C1; i += blockDim.x) ws[i % TAPS][i / TAPS] = w[i];   // w is [c][tap]
   if (threadIdx.x < C1) bs[threadIdx.x] = b[threadIdx.x];
   __syncthreads();
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < R1; p += (int64_t)gridDim.x * blockDim.x) {
-    const int ox = (int)(p % W1), oy = (int)((p / W1) % H1);
-    const int64_t bi = p / ((int64_t)W1 * H1);
-    const float* xp = x + (bi * H0 + (int64_t)oy * ST) * W0 + ox * ST;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < (unsigned)R1; p += gridDim.x * blockDim.x) {
+    const unsigned pr = p / W1, ox = p - pr * W1, bi = pr / H1, oy = pr - bi * H1;      // (R1 < 2^31: checked by the host)
+    const float* xp = x + ((size_t)bi * H0 + oy * ST) * W0 + ox * ST;
     float acc[C1];
 #pragma unroll
     for (int c = 0; c < C1; ++c) acc[c] = bs[c];
@@ -78,10 +79,10 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
 #pragma unroll
         for (int c = 0; c < C1; ++c) acc[c] = fmaf(ws[ky * KS + kx][c], v, acc[c]);
       }
-    float4* o = reinterpret_cast<float4*>(out + p * C1);
+    TO* o = out + (size_t)p * C1;
 #pragma unroll
     for (int c = 0; c < C1; c += 4)
-      o[c / 4] = make_float4(fmaxf(acc[c], 0.f), fmaxf(acc[c + 1], 0.f), fmaxf(acc[c + 2], 0.f), fmaxf(acc[c + 3], 0.f));
+      st4<TO>(o + c, make_float4(fmaxf(acc[c], 0.f), fmaxf(acc[c + 1], 0.f), fmaxf(acc[c + 2], 0.f), fmaxf(acc[c + 3], 0.f)));
   }
 }
 
@@ -101,107 +102,83 @@ template <> __device__ __forceinline__ float4 ld4<bf16>(const bf16* p) {
                      __uint_as_float(u.y & 0xffff0000u));
 }
 
-// patch matrix: col[(b,oy,ox)][tap*C + c] = A[b, 2oy+ky, 2ox+kx, c].  Work item = 8 consecutive elements of col (one 16-byte
-// store in the bf16 path): consecutive threads write consecutive pieces of a col row and read consecutive channel groups
+// patch matrix: col[(b,oy,ox)][tap*C + c] = A[b, 2oy+ky, 2ox+kx, c], both in the operand dtype (the activations A1 / A2 are
+// kept in it: the GEMM would round them to it anyway).  Work item = 8 consecutive elements of col (one 16-byte copy in the
+// bf16 path): consecutive threads write consecutive pieces of a col row and read consecutive channel groups
 // of one input pixel (and, for C = 16, of the next tap's pixel, which is the next pixel of the frame): both sides are
 // coalesced.  Four items per thread are loaded before the first is stored.
-template <typename T> __device__ __forceinline__ void st8(T* p, const float4& a, const float4& b);
-template <> __device__ __forceinline__ void st8<float>(float* p, const float4& a, const float4& b) {
-  reinterpret_cast<float4*>(p)[0] = a; reinterpret_cast<float4*>(p)[1] = b;
+template <typename T> struct Vec8;                       // 8 consecutive elements in registers
+template <> struct Vec8<float> { float4 a, b; };
+template <> struct Vec8<bf16> { uint4 a; };
+__device__ __forceinline__ void ld_vec8(const float* p, Vec8<float>& v) {
+  v.a = __ldg(reinterpret_cast<const float4*>(p)); v.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
 }
-template <> __device__ __forceinline__ void st8<bf16>(bf16* p, const float4& a, const float4& b) {
-  const __nv_bfloat162 v0 = __floats2bfloat162_rn(a.x, a.y), v1 = __floats2bfloat162_rn(a.z, a.w);
-  const __nv_bfloat162 v2 = __floats2bfloat162_rn(b.x, b.y), v3 = __floats2bfloat162_rn(b.z, b.w);
-  uint4 u;
-  u.x = *reinterpret_cast<const uint32_t*>(&v0); u.y = *reinterpret_cast<const uint32_t*>(&v1);
-  u.z = *reinterpret_cast<const uint32_t*>(&v2); u.w = *reinterpret_cast<const uint32_t*>(&v3);
-  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+__device__ __forceinline__ void ld_vec8(const bf16* p, Vec8<bf16>& v) { v.a = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void st_vec8(float* p, const Vec8<float>& v) {
+  reinterpret_cast<float4*>(p)[0] = v.a; reinterpret_cast<float4*>(p)[1] = v.b;
+}
+__device__ __forceinline__ void st_vec8(bf16* p, const Vec8<bf16>& v) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.a.x), "r"(v.a.y), "r"(v.a.z), "r"(v.a.w) : "memory");
 }
 template <typename T>
-__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ A, T* __restrict__ col, int64_t items, int Hi, int Wi,
+__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ A, T* __restrict__ col, int64_t items, int Hi, int Wi,
                                                      int Ho, int Wo, int C) {
   pdl_wait();
   pdl_launch();
-  const int C8 = C / 8;
-  const int per_row = TAPS * C8;
+  const unsigned C8 = C / 8;
+  const unsigned per_row = TAPS * C8;
   constexpr int U = 4;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < items; i0 += U * stride) {
-    float4 va[U], vb[U];
+  // (32-bit index arithmetic: the host checks items < 2^31; 64-bit divisions cost more than the copy itself)
+  const unsigned n_items = (unsigned)items, stride = gridDim.x * blockDim.x;
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_items; i0 += U * stride) {
+    Vec8<T> v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + u * stride;
-      va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < items) {
-        const int64_t r = i / per_row;
-        const int q = (int)(i - r * per_row);
-        const int tap = q / C8, c8 = q - tap * C8;
-        const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho);
-        const int64_t bimg = r / ((int64_t)Wo * Ho);
-        const int ky = tap / KS, kx = tap - ky * KS;
-        const float4* src = reinterpret_cast<const float4*>(A + ((bimg * Hi + oy * ST + ky) * Wi + ox * ST + kx) * C + c8 * 8);
-        va[u] = __ldg(src); vb[u] = __ldg(src + 1);
+      const unsigned i = i0 + u * stride;
+      if (i < n_items) {
+        const unsigned r = i / per_row, q = i - r * per_row;
+        const unsigned tap = q / C8, c8 = q - tap * C8;
+        const unsigned rr = r / Wo, ox = r - rr * Wo;
+        const unsigned bimg = rr / Ho, oy = rr - bimg * Ho;
+        const unsigned ky = tap / KS, kx = tap - ky * KS;
+        ld_vec8(A + ((size_t)(bimg * Hi + oy * ST + ky) * Wi + ox * ST + kx) * C + c8 * 8, v[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + u * stride;
-      if (i < items) st8<T>(col + i * 8, va[u], vb[u]);
+      const unsigned i = i0 + u * stride;
+      if (i < n_items) st_vec8(col + (size_t)i * 8, v[u]);
     }
   }
 }
 
-// dA[b,iy,ix,c] = relu'(A) * sum over the (<= 3x3) output pixels whose window covers (iy,ix) of dcol[(b,oy,ox)][tap*C+c].
-// Work item = (input pixel, 8 channels): 16-byte loads of dcol in the bf16 path, all (<= 9) of them issued before the sum.
-template <typename T> __device__ __forceinline__ void ld8(const T* p, float4& a, float4& b);
-template <> __device__ __forceinline__ void ld8<float>(const float* p, float4& a, float4& b) {
-  a = reinterpret_cast<const float4*>(p)[0]; b = reinterpret_cast<const float4*>(p)[1];
-}
-template <> __device__ __forceinline__ void ld8<bf16>(const bf16* p, float4& a, float4& b) {
-  uint4 u;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
-  a = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
-                  __uint_as_float(u.y & 0xffff0000u));
-  b = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u), __uint_as_float(u.w << 16),
-                  __uint_as_float(u.w & 0xffff0000u));
-}
+// dA[b,iy,ix,c] = relu'(A) * sum over the (<= 3x3) output pixels whose window covers (iy,ix) of dcol[(b,oy,ox)][tap*C+c]
+// (work item = (input pixel, 4 channels); an 8-channel / 16-byte-load version measured slower: 162 vs 96 us)
 template <typename T, typename TO>
-__global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ dcol, const float* __restrict__ A, TO* __restrict__ dA,
-                                                     int64_t items, int Hi, int Wi, int Ho, int Wo, int C) {
+__global__ void col2im_kernel(const T* __restrict__ dcol, const T* __restrict__ A, TO* __restrict__ dA, int64_t items,
+                              int Hi, int Wi, int Ho, int Wo, int C) {
   pdl_wait();
   pdl_launch();
-  const int C8 = C / 8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    const int64_t pix = i / C8;
-    const int ix = (int)(pix % Wi), iy = (int)((pix / Wi) % Hi);
-    const int64_t b = pix / ((int64_t)Wi * Hi);
-    float4 va[9], vb[9];
-    int n = 0;
-#pragma unroll
-    for (int jy = 0; jy < 3; ++jy) {
-      const int ky = (iy & 1) + 2 * jy, oy = (iy - ky) / 2;
-      const bool oky = ky < KS && iy - ky >= 0 && oy < Ho;
-#pragma unroll
-      for (int jx = 0; jx < 3; ++jx) {
-        const int kx = (ix & 1) + 2 * jx, ox = (ix - kx) / 2;
-        va[n] = vb[n] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (oky && kx < KS && ix - kx >= 0 && ox < Wo)
-          ld8<T>(dcol + ((b * Ho + oy) * Wo + ox) * ((int64_t)TAPS * C) + (ky * KS + kx) * C + c8 * 8, va[n], vb[n]);
-        ++n;
+  const unsigned C4 = C / 4, n_items = (unsigned)items;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const unsigned pix = i / C4, c4 = i - pix * C4;
+    const unsigned pr = pix / Wi, ix = pix - pr * Wi;
+    const unsigned b = pr / Hi, iy = pr - b * Hi;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ky = iy & 1; ky < KS; ky += 2) {
+      const int oy = ((int)iy - ky) / 2;
+      if ((int)iy - ky < 0 || oy >= Ho) continue;
+      for (int kx = ix & 1; kx < KS; kx += 2) {
+        const int ox = ((int)ix - kx) / 2;
+        if ((int)ix - kx < 0 || ox >= Wo) continue;
+        const float4 v = ld4<T>(dcol + ((size_t)(b * Ho + oy) * Wo + ox) * ((size_t)TAPS * C) + (ky * KS + kx) * C + c4 * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
     }
-    float4 s0 = va[0], s1 = vb[0];
-#pragma unroll
-    for (int k = 1; k < 9; ++k) {
-      s0.x += va[k].x; s0.y += va[k].y; s0.z += va[k].z; s0.w += va[k].w;
-      s1.x += vb[k].x; s1.y += vb[k].y; s1.z += vb[k].z; s1.w += vb[k].w;
-    }
-    const float4 a0 = *reinterpret_cast<const float4*>(A + pix * C + c8 * 8), a1 = *reinterpret_cast<const float4*>(A + pix * C + c8 * 8 + 4);
-    s0.x = a0.x > 0.f ? s0.x : 0.f; s0.y = a0.y > 0.f ? s0.y : 0.f; s0.z = a0.z > 0.f ? s0.z : 0.f; s0.w = a0.w > 0.f ? s0.w : 0.f;
-    s1.x = a1.x > 0.f ? s1.x : 0.f; s1.y = a1.y > 0.f ? s1.y : 0.f; s1.z = a1.z > 0.f ? s1.z : 0.f; s1.w = a1.w > 0.f ? s1.w : 0.f;
-    st4<TO>(dA + pix * C + c8 * 8, s0);
-    st4<TO>(dA + pix * C + c8 * 8 + 4, s1);
+    const float4 a = ld4<T>(A + (size_t)pix * C + c4 * 4);
+    acc.x = a.x > 0.f ? acc.x : 0.f; acc.y = a.y > 0.f ? acc.y : 0.f;
+    acc.z = a.z > 0.f ? acc.z : 0.f; acc.w = a.w > 0.f ? acc.w : 0.f;
+    st4<TO>(dA + (size_t)pix * C + c4 * 4, acc);
   }
 }
 
@@ -247,13 +224,11 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dx, int ldx, const 
   pdl_wait();
   pdl_launch();
   const float inv = 1.0f / (float)HW;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % (C3 / 4));
-    const int64_t r = i / (C3 / 4);
-    const int64_t b = r / HW;
-    const float4 a = *reinterpret_cast<const float4*>(A3 + r * C3 + c4 * 4);
-    const float* d = dx + b * ldx + c4 * 4;
-    st4<T>(dY3 + r * C3 + c4 * 4, make_float4(a.x > 0.f ? d[0] * inv : 0.f, a.y > 0.f ? d[1] * inv : 0.f,
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)items; i += gridDim.x * blockDim.x) {
+    const unsigned c4 = i % (C3 / 4), r = i / (C3 / 4), b = r / HW;
+    const float4 a = *reinterpret_cast<const float4*>(A3 + (size_t)r * C3 + c4 * 4);
+    const float* d = dx + (size_t)b * ldx + c4 * 4;
+    st4<T>(dY3 + (size_t)r * C3 + c4 * 4, make_float4(a.x > 0.f ? d[0] * inv : 0.f, a.y > 0.f ? d[1] * inv : 0.f,
                                               a.z > 0.f ? d[2] * inv : 0.f, a.w > 0.f ? d[3] * inv : 0.f));
   }
 }
@@ -319,16 +294,18 @@ __global__ void __launch_bounds__(C1W_THREADS) conv1_bwd_w_kernel(const float* _
       reinterpret_cast<float4*>(&dys[0][0])[i] =
           p < p1 ? __ldg(reinterpret_cast<const float4*>(dY1 + p * C1) + i % (C1 / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int i = tid; i < C1W_PIX * TAPS; i += C1W_THREADS) {
-      const int s = i / TAPS, t = i - s * TAPS;
-      const int64_t p = q0 + s;
-      float v = 0.f;
+    {                                                    // thread = staged pixel: its coordinates once, then the 25 taps
+      static_assert(C1W_PIX == C1W_THREADS, "one staged pixel per thread");
+      const int64_t p = q0 + tid;
       if (p < p1) {
-        const int ox = (int)(p % W1), oy = (int)((p / W1) % H1);
-        const int64_t bi = p / ((int64_t)W1 * H1);
-        v = __ldg(x + (bi * H0 + oy * ST + t / KS) * W0 + ox * ST + t % KS);
+        const unsigned pu = (unsigned)p, pr = pu / W1, ox = pu - pr * W1, bi = pr / H1, oy = pr - bi * H1;
+        const float* src = x + ((size_t)bi * H0 + oy * ST) * W0 + ox * ST;
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) xs[tid][t] = __ldg(src + (t / KS) * W0 + t % KS);
+      } else {
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) xs[tid][t] = 0.f;
       }
-      xs[s][t] = v;
     }
     __syncthreads();
 #pragma unroll 4
@@ -373,7 +350,8 @@ __global__ void reduce_cols_kernel(const float* __restrict__ part, float* __rest
 // ------------------------------------------------------------------ workspace
 template <typename T>
 struct Ws {
-  float *A1, *A2, *A3, *pooled, *xcat, *h1a, *h2a, *h1b, *h2b;
+  T *A1, *A2;                // activations of conv1 / conv2 in the operand dtype, channels-last
+  float *A3, *pooled, *xcat, *h1a, *h2a, *h1b, *h2b;
   T *col2, *col3, *Wp2, *Wp3;
   // backward
   float *dxa, *dxb, *dx, *demb, *dh1a, *dh2a, *dh1b, *dh2b, *dY1, *dWp, *dWp2, *partial;
@@ -382,8 +360,8 @@ struct Ws {
 };
 template <typename T>
 static void carve(Carver& cv, const Geo& g, Ws<T>& w) {
-  w.A1 = cv.take<float>(g.R1 * C1);
-  w.A2 = cv.take<float>(g.R2 * C2);
+  w.A1 = cv.take<T>(g.R1 * C1);
+  w.A2 = cv.take<T>(g.R2 * C2);
   w.A3 = cv.take<float>(g.R3 * C3);
   w.pooled = cv.take<float>((int64_t)g.B * C3);
   w.xcat = cv.take<float>((int64_t)g.B * g.K0);
@@ -419,7 +397,9 @@ static unsigned gs(int64_t n, int bs = 256) {
 template <typename T>
 static void forward(const float* P, const dgvit_qnet_layout& L, const Geo& g, const float* img, const float* pstate,
                     const float* action, float* q1, float* q2, Ws<T>& w, cudaStream_t st) {
-  launch_k(conv1_fwd_kernel, gs(g.R1), 256, 0, st, img, P + L.conv_w[0], P + L.conv_b[0], w.A1, g.R1, g.H0, g.W0, g.H1, g.W1);
+  DG_REQUIRE(g.R1 * C1 < ((int64_t)1 << 31) && g.R2 * TAPS * C1 < ((int64_t)1 << 31) && g.R3 * TAPS * C2 < ((int64_t)1 << 31),
+             "qnet: batch too large for the 32-bit index arithmetic of the patch-matrix kernels (B <= ~5000 at 128x160)");
+  launch_k(conv1_fwd_kernel<T>, gs(g.R1), 256, 0, st, img, P + L.conv_w[0], P + L.conv_b[0], w.A1, g.R1, g.H0, g.W0, g.H1, g.W1);
   DG_LAUNCH_CHECK();
   // conv2
   {
@@ -427,9 +407,9 @@ static void forward(const float* P, const dgvit_qnet_layout& L, const Geo& g, co
     launch_k(wperm_kernel<T>, (unsigned)cdiv(n, 256), 256, 0, st, P + L.conv_w[1], w.Wp2, n, C1);
     DG_LAUNCH_CHECK();
     const int64_t items = g.R2 * TAPS * (C1 / 8);
-    launch_k(im2col_kernel<T>, gs(cdiv(items, 4)), 256, 0, st, (const float*)w.A1, w.col2, items, g.H1, g.W1, g.H2, g.W2, C1);
+    launch_k(im2col_kernel<T>, gs(cdiv(items, 4)), 256, 0, st, (const T*)w.A1, w.col2, items, g.H1, g.W1, g.H2, g.W2, C1);
     DG_LAUNCH_CHECK();
-    linear_fwd<T, T, float>(w.col2, w.Wp2, w.A2, g.R2, C2, TAPS * C1, EPI_BIAS_RELU, P + L.conv_b[1], st);
+    linear_fwd<T, T, T>(w.col2, w.Wp2, w.A2, g.R2, C2, TAPS * C1, EPI_BIAS_RELU, P + L.conv_b[1], st);
   }
   // conv3
   {
@@ -437,7 +417,7 @@ static void forward(const float* P, const dgvit_qnet_layout& L, const Geo& g, co
     launch_k(wperm_kernel<T>, (unsigned)cdiv(n, 256), 256, 0, st, P + L.conv_w[2], w.Wp3, n, C2);
     DG_LAUNCH_CHECK();
     const int64_t items = g.R3 * TAPS * (C2 / 8);
-    launch_k(im2col_kernel<T>, gs(cdiv(items, 4)), 256, 0, st, (const float*)w.A2, w.col3, items, g.H2, g.W2, g.H3, g.W3, C2);
+    launch_k(im2col_kernel<T>, gs(cdiv(items, 4)), 256, 0, st, (const T*)w.A2, w.col3, items, g.H2, g.W2, g.H3, g.W3, C2);
     DG_LAUNCH_CHECK();
     linear_fwd<T, T, float>(w.col3, w.Wp3, w.A3, g.R3, C3, TAPS * C2, EPI_BIAS_RELU, P + L.conv_b[2], st);
   }
@@ -498,16 +478,16 @@ static void backward(const float* P, float* G, const dgvit_qnet_layout& L, const
     DG_LAUNCH_CHECK();
     conv_bwd_w<T>(w.dY3, w.col3, w.dWp, G + L.conv_b[2], g.R3, C3, C2, rl, st);
     linear_bwd_x<T, T, T>(w.dY3, w.Wp3, w.dcol, g.R3, C3, TAPS * C2, EPI_NONE, nullptr, 0, st);
-    const int64_t it2 = g.R2 * (C2 / 8);
-    launch_k(col2im_kernel<T, T>, gs(it2), 256, 0, st, (const T*)w.dcol, (const float*)w.A2, w.dY2, it2, g.H2, g.W2, g.H3, g.W3, C2);
+    const int64_t it2 = g.R2 * (C2 / 4);
+    launch_k(col2im_kernel<T, T>, gs(it2), 256, 0, st, (const T*)w.dcol, (const T*)w.A2, w.dY2, it2, g.H2, g.W2, g.H3, g.W3, C2);
     DG_LAUNCH_CHECK();
   }
   // conv2
   {
     conv_bwd_w<T>(w.dY2, w.col2, w.dWp2, G + L.conv_b[1], g.R2, C2, C1, rl, st);
     linear_bwd_x<T, T, T>(w.dY2, w.Wp2, w.dcol, g.R2, C2, TAPS * C1, EPI_NONE, nullptr, 0, st);
-    const int64_t it1 = g.R1 * (C1 / 8);
-    launch_k(col2im_kernel<T, float>, gs(it1), 256, 0, st, (const T*)w.dcol, (const float*)w.A1, w.dY1, it1, g.H1, g.W1, g.H2, g.W2, C1);
+    const int64_t it1 = g.R1 * (C1 / 4);
+    launch_k(col2im_kernel<T, float>, gs(it1), 256, 0, st, (const T*)w.dcol, (const T*)w.A1, w.dY1, it1, g.H1, g.W1, g.H2, g.W2, C1);
     DG_LAUNCH_CHECK();
   }
   // conv1
