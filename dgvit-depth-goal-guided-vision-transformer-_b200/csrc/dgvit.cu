@@ -747,7 +747,7 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
   }
   // ---- embedding.  c.dX = dL/dX0 (post-dropout)
   const int64_t tot = d.T * d.D;
-  launch_k(embed_bwd_kernel<A>, grid1d(tot), 256, 0, st, c.dX, c.tok, c.dXp, c.dtok, drop, tot, d.N, d.D, relu_tok);
+  launch_k(embed_bwd_kernel<A>, grid1d(tot / 4), 256, 0, st, c.dX, c.tok, c.dXp, c.dtok, drop, tot, d.N, d.D, relu_tok);
   DG_LAUNCH_CHECK();
   {
     const int S = std::max(1, std::min(32, d.B / 8));

@@ -131,17 +131,34 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dX0, const float* __r
                                  int N, int D, int relu) {
   pdl_wait();
   pdl_launch();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int d = (int)(i % D);
-    const int64_t bn = i / D;
-    const int n = (int)(bn % N);
-    const int64_t b = bn / N;
-    const float g = dX0[i] * drop_factor(drop, i);
-    if (n == 0) {
-      dtok[b * D + d] = (relu && !(tok[b * D + d] > 0.f)) ? 0.f : g;
+  // one thread = 4 consecutive features of one token (D % 4 == 0): one 16-byte load, one Philox call; 32-bit index
+  // arithmetic when the tensor allows it (two 64-bit divisions per element cost more than the copy)
+  const int64_t total4 = total >> 2;
+  const int D4 = D >> 2;
+  for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (int64_t)gridDim.x * blockDim.x) {
+    int d4, n;
+    int64_t b;
+    if (total4 < ((int64_t)1 << 31)) {
+      const unsigned u = (unsigned)i4, bn = u / D4, bb = bn / N;
+      d4 = u - bn * D4; n = bn - bb * N; b = bb;
     } else {
-      stf(dXp + (b * (N - 1) + (n - 1)) * D + d, g);
+      d4 = (int)(i4 % D4);
+      const int64_t bn = i4 / D4;
+      n = (int)(bn % N); b = bn / N;
+    }
+    const float4 f = drop_factor4(drop, i4 * 4);
+    float4 g = reinterpret_cast<const float4*>(dX0)[i4];
+    g.x *= f.x; g.y *= f.y; g.z *= f.z; g.w *= f.w;
+    if (n == 0) {
+      float* o = dtok + b * D + 4 * d4;
+      if (relu) {
+        const float4 t = *reinterpret_cast<const float4*>(tok + b * D + 4 * d4);
+        g.x = t.x > 0.f ? g.x : 0.f; g.y = t.y > 0.f ? g.y : 0.f; g.z = t.z > 0.f ? g.z : 0.f; g.w = t.w > 0.f ? g.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(o) = g;
+    } else {
+      A* o = dXp + (b * (N - 1) + (n - 1)) * D + 4 * d4;
+      stf(o, g.x); stf(o + 1, g.y); stf(o + 2, g.z); stf(o + 3, g.w);
     }
   }
 }
@@ -770,11 +787,18 @@ __global__ void scatter_row0_kernel(const float* __restrict__ dXc, float* __rest
                                     int D) {
   pdl_wait();
   pdl_launch();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int d = (int)(i % D);
-    const int64_t bn = i / D;
-    dX[i] = (bn % N == 0) ? dXc[(bn / N) * D + d] : 0.f;
+  // one thread = 4 consecutive features (D % 4 == 0)
+  const int64_t total4 = total >> 2;
+  const int D4 = D >> 2;
+  for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (int64_t)gridDim.x * blockDim.x) {
+    int64_t bn;
+    int d4;
+    if (total4 < ((int64_t)1 << 31)) { const unsigned u = (unsigned)i4, q = u / D4; d4 = u - q * D4; bn = q; }
+    else { d4 = (int)(i4 % D4); bn = i4 / D4; }
+    const bool row0 = total4 < ((int64_t)1 << 31) ? ((unsigned)bn % (unsigned)N == 0) : (bn % N == 0);
+    const int64_t b = total4 < ((int64_t)1 << 31) ? (int64_t)((unsigned)bn / (unsigned)N) : bn / N;
+    reinterpret_cast<float4*>(dX)[i4] =
+        row0 ? *reinterpret_cast<const float4*>(dXc + b * D + 4 * d4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 

@@ -42,20 +42,6 @@ struct PatchArgs {
   float* mean; float* rstd;
 };
 
-// dropout factors of 4 consecutive elements starting at the 4-aligned element index i (one Philox call in RNG mode)
-__device__ __forceinline__ float4 drop_factor4(const DropDev& d, int64_t i) {
-  if (d.mode == DGVIT_DROP_NONE) return make_float4(1.f, 1.f, 1.f, 1.f);
-  if (d.mode == DGVIT_DROP_MASK) {
-    const uchar4 m = *reinterpret_cast<const uchar4*>(d.mask + i);
-    return make_float4(m.x ? d.scale : 0.f, m.y ? d.scale : 0.f, m.z ? d.scale : 0.f, m.w ? d.scale : 0.f);
-  }
-  uint32_t o[4];
-  const uint64_t gi = (uint64_t)(i + d.elem_offset);        // elem_offset is a multiple of N * D, hence of 4
-  philox4x32(d.rng[0], gi >> 2, ((uint64_t)d.stream_id << 32) | (d.rng[1] & 0xffffffffu), o);
-  return make_float4(u01(o[0]) > d.p ? d.scale : 0.f, u01(o[1]) > d.p ? d.scale : 0.f, u01(o[2]) > d.p ? d.scale : 0.f,
-                     u01(o[3]) > d.p ? d.scale : 0.f);
-}
-
 // frame -> 128B-swizzled K-major tiles [128 tokens][320] (five [128][64] k-blocks at `tiles`) for the 128 patch tokens
 // starting at t0.  The tokens are 128 / GW patch rows = 16 * 128 / GW pixel rows of GW * 20 pixels, contiguous in memory
 // (frames back to back).  One thread-item = 4 consecutive pixels of one patch row = 4 consecutive k; eight 16-byte loads in
