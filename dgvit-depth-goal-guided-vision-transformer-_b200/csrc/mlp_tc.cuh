@@ -439,12 +439,17 @@ mlp_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if ((ew & 7) == 0) MLP_TRACE(1, c);
       tc_fence_after();
       uint8_t* hb = smem + OFF_H + ab * H_BYTES + half * 16384;
+      // the second 32 columns are requested while the first 32 are being turned into GELU values: one TMEM round trip per
+      // chunk on the critical path instead of two
+      uint32_t vv[2][32];
+      tmem_ld32_nowait(tmem_base + ab * HC + half * 64 + lane_off, vv[0]);
+      tmem_wait_ld();
+      tmem_ld32_nowait(tmem_base + ab * HC + half * 64 + 32 + lane_off, vv[1]);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[32];
-        tmem_ld32_nowait(tmem_base + ab * HC + half * 64 + hh * 32 + lane_off, v);
-        tmem_wait_ld();
+        uint32_t (&v)[32] = vv[hh];
         if (hh == 1) {
+          tmem_wait_ld();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_free[ab]);      // TMEM chunk drained: GEMM1(c+2) may start
