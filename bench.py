@@ -601,6 +601,21 @@ def run_next_rows(dev):
     except Exception as e:
         out["f1_cnn_critic_learn"] = dict(error=repr(e)[:200])
     try:
+        pol = dg.GoTPolicy(2, 2, PRESET["block"], PRESET["head"], PRESET["l_f_size"]).to(dev)
+        pol.precision = "bf16"
+        g3 = torch.Generator(device=dev).manual_seed(SEED)
+        rec = {}
+        for bb in (32, 256):          # (32 = batch_size of vn/attention_imitating.py:96)
+            img, goal = torch.rand(bb, 128, 160, device=dev, generator=g3), torch.rand(bb, 2, device=dev, generator=g3)
+            act = torch.rand(bb, 2, device=dev, generator=g3) * 2 - 1
+            rec["B%d" % bb] = bb * rate(lambda: pol.bc_step(img, goal, act), 20)
+        out["f3_bc_step"] = dict(value=rec["B256"], at_batch_32=rec["B32"], unit=UNIT,
+                                 what="GoTPolicy.bc_step: policy.sample -> RMSE -> backward -> clip_grad_norm_ -> Adam in one C call "
+                                      "(dgvit_bc_step), eager calls, no host sync")
+        del pol
+    except Exception as e:
+        out["f3_bc_step"] = dict(error=repr(e)[:200])
+    try:
         a2 = dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, True, SEED, BUFFER_SIZE=4096, buffer_size_expert=2048,
                     precision="bf16", device=dev, **HP, **PRESET)
         a2.replay_buffer.fill_synthetic(4096, seed=SEED)

@@ -63,6 +63,12 @@ class ActorIO(C.Structure):
                 ("mean_t", c_f_p), ("eps_out", c_f_p), ("advance_rng", C.c_int32)]
 
 
+class BcIO(C.Structure):
+    _fields_ = [("img", c_f_p), ("pstate", c_f_p), ("target", c_f_p), ("eps", c_f_p), ("action_scale", c_f_p),
+                ("action_bias", c_f_p), ("drop", Drop), ("sample_offset", C.c_int32), ("advance_rng", C.c_int32),
+                ("max_action", C.c_float), ("max_norm", C.c_float), ("loss", c_f_p), ("grad_norm", c_f_p)]
+
+
 class ActorGrad(C.Structure):
     _fields_ = [("d_mean", c_f_p), ("d_log_std", c_f_p), ("d_action", c_f_p), ("d_log_prob", c_f_p),
                 ("d_mean_t", c_f_p), ("d_log_prob_const", C.c_float)]
@@ -137,6 +143,8 @@ SYMBOLS = {
     "dgvit_refresh_shadow": (C.c_int, [P(Net), C.c_void_p]),
     "dgvit_actor_forward": (C.c_int, [P(Net), P(ActorIO), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dgvit_actor_backward": (C.c_int, [P(Net), P(ActorIO), P(ActorGrad), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dgvit_bc_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, P(C.c_size_t)]),
+    "dgvit_bc_step": (C.c_int, [P(Net), P(Adam), P(BcIO), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dgvit_trunk_workspace_bytes": (C.c_int, [P(Cfg), C.c_int, C.c_int, C.c_int, P(C.c_size_t)]),
     "dgvit_trunk_forward": (C.c_int, [P(Net), P(TrunkIO), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dgvit_trunk_backward": (C.c_int, [P(Net), P(TrunkIO), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,

@@ -1004,23 +1004,30 @@ static void dp_wait_done(const dgvit_dp* dp, int which, const dgvit_layout& L, c
   DG_LAUNCH_CHECK();
 }
 
-static void adam_step(const dgvit_net& net, const dgvit_layout& L, const dgvit_adam& o, const dgvit_net* tgt,
-                      float tau, bool want_shadow, cudaStream_t st, const dgvit_dp* dp = nullptr, int which = 0) {
-  DG_REQUIRE(o.m && o.v && o.step, "adam: null state");
-  launch_k(step_bump_kernel, 1, 32, 0, st, o.step);
-  DG_LAUNCH_CHECK();
-  AdamArgs a;
+static void fill_adam_args(AdamArgs& a, const dgvit_net& net, const dgvit_layout& L, const dgvit_adam& o) {
+  memset(&a, 0, sizeof(a));
   a.p = net.params; a.g = net.grads; a.m = o.m; a.v = o.v;
-  a.shadow = (want_shadow && net.shadow) ? (bf16*)net.shadow : nullptr;
-  a.tgt = tgt ? tgt->params : nullptr;
-  a.tgt_shadow = (tgt && want_shadow && tgt->shadow) ? (bf16*)tgt->shadow : nullptr;
-  a.tau = tau;
   a.n = L.total; a.step = o.step;
   a.lr = o.lr; a.b1 = o.beta1; a.b2 = o.beta2; a.eps = o.eps;
   a.omb1 = (float)(1.0 - (double)o.beta1);
   a.omb2 = (float)(1.0 - (double)o.beta2);
   a.n_skip = L.n_skip;
   for (int k = 0; k < 4; ++k) { a.skip_b[k] = L.skip_begin[k]; a.skip_e[k] = L.skip_end[k]; }
+}
+
+static void adam_step(const dgvit_net& net, const dgvit_layout& L, const dgvit_adam& o, const dgvit_net* tgt,
+                      float tau, bool want_shadow, cudaStream_t st, const dgvit_dp* dp = nullptr, int which = 0,
+                      const float* gscale = nullptr) {
+  DG_REQUIRE(o.m && o.v && o.step, "adam: null state");
+  launch_k(step_bump_kernel, 1, 32, 0, st, o.step);
+  DG_LAUNCH_CHECK();
+  AdamArgs a;
+  fill_adam_args(a, net, L, o);
+  a.gscale = gscale;
+  a.shadow = (want_shadow && net.shadow) ? (bf16*)net.shadow : nullptr;
+  a.tgt = tgt ? tgt->params : nullptr;
+  a.tgt_shadow = (tgt && want_shadow && tgt->shadow) ? (bf16*)tgt->shadow : nullptr;
+  a.tau = tau;
   {  // algorithmic bytes: theta, m, v read + written, g read, bf16 shadow written (+ target read / written + its shadow)
     int64_t used = L.total;
     for (int k = 0; k < L.n_skip; ++k) used -= L.skip_end[k] - L.skip_begin[k];
@@ -1435,6 +1442,20 @@ static size_t sac_ws_bytes(const dgvit_cfg& acfg, int B, int n_extra) {
   return cv.off;
 }
 
+// behaviour-cloning step workspace (dgvit_bc_step)
+template <typename A>
+struct BcWs {
+  ActorCtx<A> actor;
+  float *mean, *lstd, *action, *logp, *mean_t, *d_mean_t, *part, *scale;
+};
+template <typename A>
+static void carve_bc(Carver& cv, const Dims& d, BcWs<A>& w) {
+  carve_actor<A>(cv, d, true, w.actor);
+  const int64_t bn = (int64_t)d.B * d.na;
+  w.mean = cv.take<float>(bn); w.lstd = cv.take<float>(bn); w.action = cv.take<float>(bn); w.logp = cv.take<float>(d.B);
+  w.mean_t = cv.take<float>(bn); w.d_mean_t = cv.take<float>(bn);
+  w.part = cv.take<float>(GN_BLOCKS); w.scale = cv.take<float>(4);
+}
 template <typename F32, typename BF>
 static void by_precision(int precision, F32&& f32, BF&& bf) {
   if (precision == DGVIT_FP32) f32();
@@ -1609,6 +1630,62 @@ int dgvit_actor_backward(const dgvit_net* net, const dgvit_actor_io* io, const d
       ActorCtx<A> c;
       carve_actor<A>(cv, d, true, c);
       actor_backward<A>(*net, L, d, *io, *g, nullptr, 0.f, c, (cudaStream_t)stream);
+    };
+    by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
+  });
+}
+
+// ---- behaviour-cloning step (vn/attention_imitating.py:48-67): one call = policy.sample -> RMSE on the clipped tanh-mean
+//      -> backward -> clip_grad_norm_ -> Adam
+int dgvit_bc_workspace_bytes(const dgvit_cfg* cfg, int B, int precision, size_t* bytes) {
+  return guarded([&] {
+    DG_REQUIRE(cfg && bytes && B >= 1 && cfg->kind == DGVIT_ACTOR, "bad argument");
+    Dims d(*cfg, B);
+    Carver cv(nullptr, 0, true);
+    by_precision(precision, [&] { BcWs<float> w; carve_bc<float>(cv, d, w); }, [&] { BcWs<bf16> w; carve_bc<bf16>(cv, d, w); });
+    *bytes = cv.off;
+  });
+}
+int dgvit_bc_step(const dgvit_net* net, const dgvit_adam* opt, const dgvit_bc_io* io, int B, int precision, void* ws,
+                  size_t ws_bytes, void* stream) {
+  return guarded([&] {
+    DeviceGuard dev_guard(net ? net->params : nullptr);
+    DG_REQUIRE(net && opt && io && ws && B >= 1 && net->cfg.kind == DGVIT_ACTOR && net->params && net->grads, "bad argument");
+    DG_REQUIRE(io->img && io->pstate && io->target && io->action_scale && io->action_bias && io->loss, "bc_step: null input");
+    DG_REQUIRE(io->max_action > 0.f && io->max_norm > 0.f, "bc_step: max_action and max_norm must be positive");
+    if (precision == DGVIT_BF16) DG_REQUIRE(net->shadow, "bc_step: bf16 needs the shadow arena");
+    dgvit_layout L;
+    make_layout(net->cfg, L);
+    Dims d(net->cfg, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto run = [&](auto tag) {
+      using A = decltype(tag);
+      Carver cv(ws, ws_bytes);
+      BcWs<A> w;
+      carve_bc<A>(cv, d, w);
+      dgvit_actor_io ai; memset(&ai, 0, sizeof(ai));
+      ai.img = io->img; ai.pstate = io->pstate; ai.eps = io->eps;
+      ai.action_scale = io->action_scale; ai.action_bias = io->action_bias;
+      ai.drop = io->drop; ai.sample_offset = io->sample_offset;
+      ai.mean = w.mean; ai.log_std = w.lstd; ai.action = w.action; ai.log_prob = w.logp; ai.mean_t = w.mean_t;
+      actor_forward<A>(*net, L, d, ai, w.actor, st);                                         // :56
+      const int n = d.B * d.na;
+      launch_k(bc_loss_kernel, 1, 1024, 0, st, (const float*)w.mean_t, io->target, n, io->max_action, w.d_mean_t, io->loss);   // :58-60
+      DG_LAUNCH_CHECK();
+      dgvit_actor_grad ag; memset(&ag, 0, sizeof(ag));
+      ag.d_mean_t = w.d_mean_t;
+      actor_backward<A>(*net, L, d, ai, ag, nullptr, 0.f, w.actor, st);                        // :61
+      AdamArgs a;
+      fill_adam_args(a, *net, L, *opt);
+      launch_k(sumsq_partial_kernel, GN_BLOCKS, 256, 0, st, a, w.part);                        // :62 clip_grad_norm_
+      DG_LAUNCH_CHECK();
+      launch_k(clip_scale_kernel, 1, 32, 0, st, (const float*)w.part, GN_BLOCKS, io->max_norm, w.scale, io->grad_norm);
+      DG_LAUNCH_CHECK();
+      adam_step(*net, L, *opt, nullptr, 0.f, precision == DGVIT_BF16, st, nullptr, 0, w.scale);   // :63
+      if (io->advance_rng && io->drop.rng_state) {
+        launch_k(rng_advance_kernel, 1, 32, 0, st, const_cast<uint64_t*>(io->drop.rng_state));
+        DG_LAUNCH_CHECK();
+      }
     };
     by_precision(precision, [&] { run(float()); }, [&] { run(bf16()); });
   });

@@ -1066,6 +1066,7 @@ struct AdamArgs {
   float lr, b1, b2, eps;
   float omb1, omb2;                          // (float)(1 - beta) computed in double like torch
   int n_skip; int64_t skip_b[4], skip_e[4];
+  const float* gscale;                       // optional device scalar multiplied into every gradient (clip_grad_norm_)
 };
 __global__ void step_bump_kernel(int64_t* step) {
   pdl_wait();
@@ -1169,6 +1170,7 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
   }
   __syncthreads();
   const float step_size = sh[0], bc2s = sh[1];
+  const float gs = a.gscale ? __ldg(a.gscale) : 1.0f;
   const int64_t n4 = a.n >> 2;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = q << 2;
@@ -1178,7 +1180,8 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
     if (DP && skip && i >= dp.tail_begin && i < dp.tail_begin + dp.tail_n)
       *reinterpret_cast<float4*>(dp.tail_out + (i - dp.tail_begin)) = dp_reduced4(dp, i);
     if (!skip) {
-      const float4 g = DP ? dp_reduced4(dp, i) : *reinterpret_cast<const float4*>(a.g + i);
+      float4 g = DP ? dp_reduced4(dp, i) : *reinterpret_cast<const float4*>(a.g + i);
+      if (a.gscale) { g.x *= gs; g.y *= gs; g.z *= gs; g.w *= gs; }
       if (DP && dp.reduced_out) *reinterpret_cast<float4*>(dp.reduced_out + i) = g;
       float4 m = *reinterpret_cast<const float4*>(a.m + i), v = *reinterpret_cast<const float4*>(a.v + i);
 #define DG_ADAM1(C_)                                                                                     \
@@ -1211,6 +1214,83 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
         for (int p = 0; p < dp.world; ++p) st_release_sys(dp_slot(dp, p, 1, dp.rank), epoch);
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------ behaviour-cloning step (vn/attention_imitating.py:58-64)
+// loss = sqrt(mean((clip(tanh-mean, -max_action, max_action) - action)^2)) over B * na elements; d_mean_t = dloss / d tanh-mean.
+// One block (B * na is a few hundred); fixed summation order.
+__global__ void __launch_bounds__(1024) bc_loss_kernel(const float* __restrict__ mean_t, const float* __restrict__ target, int n,
+                                                       float max_action, float* __restrict__ d_mean_t, float* __restrict__ loss) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = fminf(fmaxf(mean_t[i], -max_action), max_action) - target[i];
+    s = fmaf(d, d, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) sh[0] = sqrtf(t / (float)n);
+  }
+  __syncthreads();
+  const float l = sh[0];
+  if (threadIdx.x == 0) *loss = l;
+  const float inv = l > 0.f ? 1.0f / ((float)n * l) : 0.f;      // d sqrt(mean d^2) / d x = d / (n * loss)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float m = mean_t[i];
+    d_mean_t[i] = (m >= -max_action && m <= max_action) ? (m - target[i]) * inv : 0.f;      // clip passes the gradient inside its range
+  }
+}
+// torch.nn.utils.clip_grad_norm_: total_norm = ||g||_2 over every parameter that has a gradient (the ranges Adam skips have
+// none); gradients are multiplied by min(1, max_norm / (total_norm + 1e-6)).  Two launches, fixed summation order:
+// per-block sums of squares, then one block -> *scale (read by the Adam pass), *norm.
+constexpr int GN_BLOCKS = 148 * 2;
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const __grid_constant__ AdamArgs a, float* __restrict__ part) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float sh[8];
+  float s0 = 0.f, s1 = 0.f;
+  const int64_t n4 = a.n >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q << 2;
+    bool skip = false;
+    for (int k = 0; k < a.n_skip; ++k) skip |= (i >= a.skip_b[k] && i < a.skip_e[k]);
+    if (skip) continue;
+    const float4 g = *reinterpret_cast<const float4*>(a.g + i);
+    s0 = fmaf(g.x, g.x, fmaf(g.y, g.y, s0));
+    s1 = fmaf(g.z, g.z, fmaf(g.w, g.w, s1));
+  }
+  float s = s0 + s1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(32) clip_scale_kernel(const float* __restrict__ part, int nb, float max_norm, float* __restrict__ scale,
+                                                        float* __restrict__ norm) {
+  pdl_wait();
+  pdl_launch();
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 32) s += (double)part[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) {
+    const float total = (float)sqrt(s);
+    *scale = fminf(max_norm / (total + 1e-6f), 1.0f);
+    if (norm) *norm = total;
   }
 }
 

@@ -339,7 +339,7 @@ class _ArenaModule(nn.Module):
         cls = self.__class__
         new = cls.__new__(cls)
         memo[id(self)] = new
-        skip = {"_act_state": None, "_ws_cache": {}, "_noise_fifo": [], "_rng_state": None}
+        skip = {"_act_state": None, "_ws_cache": {}, "_noise_fifo": [], "_rng_state": None, "_bc": None}
         for k, v in self.__dict__.items():
             new.__dict__[k] = skip[k] if k in skip else _copy.deepcopy(v, memo)
         trunk = new._modules.get("trans")
@@ -536,6 +536,53 @@ class GoTPolicy(_ArenaModule):
     def sample(self, inp):
         _, _, action, log_prob, mean_t = self._run(inp)
         return action, log_prob, mean_t
+
+    def bc_step(self, istate, pstate, action, lr=1e-3, max_action=1.0, max_norm=10.0) -> torch.Tensor:
+        """One behaviour-cloning step of the reference's imitation script (vn/attention_imitating.py:48-67) in ONE library
+        call: ``policy.sample`` -> ``sqrt(mean((mean.clip(-max_action, max_action) - action) ** 2))`` -> backward ->
+        ``clip_grad_norm_(parameters, max_norm)`` -> ``Adam(lr).step()``.  The Adam moments live with the module (created on
+        the first call, ``bc_reset()`` drops them).  Returns the loss as a device tensor (no host sync); the total gradient
+        norm before clipping is kept in ``self._bc["grad_norm"]``."""
+        self.bind()
+        _require_cuda(self._arena)
+        dev = self._arena.device
+        img = self._check_img(istate)
+        ps = pstate.to(dev, torch.float32).contiguous()
+        tgt = action.to(dev, torch.float32).contiguous()
+        B = img.shape[0]
+        st = getattr(self, "_bc", None)
+        if st is None or st["arena"] != self._arena.data_ptr():
+            n = self.layout().total
+            f32 = dict(dtype=torch.float32, device=dev)
+            st = self._bc = dict(arena=self._arena.data_ptr(), m=torch.zeros(n, **f32), v=torch.zeros(n, **f32),
+                                 step=torch.zeros(1, dtype=torch.int64, device=dev), loss=torch.zeros(1, **f32),
+                                 grad_norm=torch.zeros(1, **f32), ws=None,
+                                 scale=self.action_scale.to(dev, torch.float32).expand(self._cfg.n_act).contiguous(),
+                                 bias=self.action_bias.to(dev, torch.float32).expand(self._cfg.n_act).contiguous())
+        nb = C.c_size_t()
+        L.check(L.lib().dgvit_bc_workspace_bytes(C.byref(self._cfg), B, self._precision_code(), C.byref(nb)), "bc_workspace_bytes")
+        if st["ws"] is None or st["ws"].numel() < nb.value:
+            st["ws"] = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        keep: List = []
+        drop, eps = self._drop_struct(B, keep, training=True)
+        if self.precision == "bf16":
+            self._sync_shadow(st)
+        net = self.net_struct()
+        opt = L.Adam(m=st["m"].data_ptr(), v=st["v"].data_ptr(), step=st["step"].data_ptr(), lr=float(lr), beta1=0.9, beta2=0.999,
+                     eps=1e-8)
+        io = L.BcIO(img=img.data_ptr(), pstate=ps.data_ptr(), target=tgt.data_ptr(), eps=L.ptr(eps),
+                    action_scale=st["scale"].data_ptr(), action_bias=st["bias"].data_ptr(), drop=drop, sample_offset=0,
+                    advance_rng=0, max_action=float(max_action), max_norm=float(max_norm), loss=st["loss"].data_ptr(),
+                    grad_norm=st["grad_norm"].data_ptr())
+        L.check(L.lib().dgvit_bc_step(C.byref(net), C.byref(opt), C.byref(io), B, self._precision_code(), st["ws"].data_ptr(),
+                                      st["ws"].numel(), _stream(dev)), "bc_step")
+        st["keep"] = (keep, img, ps, tgt, eps)       # inputs stay alive until the next step has been queued behind this one
+        if self.precision == "bf16":
+            st["shadow_version"] = self._arena._version      # (the step's Adam pass refreshed the 16-bit copies itself)
+        return st["loss"]
+
+    def bc_reset(self):
+        self._bc = None
 
     def choose_action(self, istate, pstate, evaluate=False):
         """numpy (H,W,1) frame + (2,) goal -> numpy action (vn/got_sac_network.py:205-220).

@@ -149,6 +149,28 @@ typedef struct dgvit_adam {
   float lr, beta1, beta2, eps;
 } dgvit_adam;
 
+/* ---- behaviour-cloning step on the actor (vn/attention_imitating.py:48-67), SURVEY.md section 8 row f3 ------------------------
+ * One call = policy.sample([img, pstate]) -> loss = sqrt(mean((clip(tanh-mean, +-max_action) - target)^2)) -> backward ->
+ * torch.nn.utils.clip_grad_norm_(parameters, max_norm) -> Adam.step (opt; parameters the loss does not reach -- cls_token,
+ * mlp_head.*, log_std_linear -- keep zero moments and do not move, like `grad is None` in the reference). */
+typedef struct dgvit_bc_io {
+  const float* img;      /* [B, img_h, img_w] */
+  const float* pstate;   /* [B, n_pstate] */
+  const float* target;   /* [B, n_act] demonstrated actions */
+  const float* eps;      /* [B, n_act] rsample draws or NULL (the sampled action does not enter the loss) */
+  const float* action_scale; const float* action_bias;   /* [n_act] */
+  dgvit_drop drop;
+  int32_t sample_offset;
+  int32_t advance_rng;   /* 1: advance the counter of drop.rng_state after the step */
+  float max_action;      /* clip range of the predicted mean (1.0 in the reference) */
+  float max_norm;        /* clip_grad_norm_ threshold (10 in the reference) */
+  float* loss;           /* device [1] */
+  float* grad_norm;      /* device [1] total gradient norm before clipping, or NULL */
+} dgvit_bc_io;
+int dgvit_bc_workspace_bytes(const dgvit_cfg* actor_cfg, int B, int precision, size_t* bytes);
+int dgvit_bc_step(const dgvit_net* actor, const dgvit_adam* opt, const dgvit_bc_io* io, int B, int precision,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* Data parallel without NCCL calls: the gradient all-reduce is fused into the optimizer pass.  Both gradient arenas live
  * in ONE symmetric-memory buffer per rank ([critic grads | actor grads], e.g. torch.distributed._symmetric_memory): the
  * Adam kernel of a network runs a flag barrier over the ranks' signal pads, reads the rank-sum of every gradient element

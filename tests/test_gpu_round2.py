@@ -469,3 +469,42 @@ def test_depth_streaming_rows_equal_tile_rows():
                     assert float((outs[strip][k] - outs[0][k]).abs().max()) < 2e-6, (n, H, W, strip, k)
     finally:
         L.check(L.lib().dgvit_set_option(b"depth_strip", -1), "set_option")
+
+
+@pytest.mark.gpu
+def test_behaviour_cloning_step_single_call():
+    """SURVEY §8 f3, vn/attention_imitating.py:48-67 as ONE library call (`GoTPolicy.bc_step` -> `dgvit_bc_step`): policy.sample
+    -> RMSE on the clipped tanh-mean -> backward -> clip_grad_norm_ -> Adam.  Three fp32 steps against the same statements run
+    with autograd on the oracle's parameters; the third step uses a tiny max_norm so the clip is active (scale << 1)."""
+    from helpers import reference_init
+    cfg = O.Cfg(dim=32, depth=2, heads=2)
+    B = 6
+    pa = reference_init("actor", cfg, 71)
+    a = _mk("actor", cfg, pa)
+    ref = {k: v.clone().requires_grad_(True) for k, v in pa.items()}
+    ropt = torch.optim.Adam(list(ref.values()), lr=1e-3)
+    for s, max_norm in enumerate((10.0, 10.0, 1e-2)):
+        batch, nz = synthetic_batch(cfg, B, 80 + s), synthetic_noise(cfg, B, 90 + s)
+        img, goal, act = batch["obs"], batch["pobs"], batch["act"]
+        _, _, mean = O.actor_sample(ref, img, goal, nz["eps_pi"], cfg, nz["mask_a"])
+        rloss = torch.sqrt(torch.pow(mean.clip(-1, 1) - act, 2).mean())
+        ropt.zero_grad()
+        rloss.backward()
+        rnorm = torch.nn.utils.clip_grad_norm_([p for p in ref.values() if p.grad is not None], max_norm)
+        ropt.step()
+        a.inject_noise(mask=nz["mask_a"], eps=nz["eps_pi"])
+        loss = a.bc_step(img.cuda(), goal.cuda(), act.cuda(), lr=1e-3, max_action=1.0, max_norm=max_norm)
+        assert abs(float(loss) - float(rloss)) < 1e-4 * max(1.0, abs(float(rloss))), (s, float(loss), float(rloss))
+        assert abs(float(a._bc["grad_norm"]) - float(rnorm)) < 2e-4 * max(1.0, float(rnorm)), (s, float(a._bc["grad_norm"]), float(rnorm))
+        for k, p in a.named_parameters():
+            d = (p.detach().cpu() - ref[k].detach()).abs()
+            assert float((d > 2e-5 * (s + 1)).float().mean()) < 5e-3, (s, k, float(d.max()))
+    # parameters the loss does not reach did not move (grad is None in the reference)
+    for k in ("log_std_linear.weight", "log_std_linear.bias"):
+        assert torch.equal(dict(a.named_parameters())[k].detach().cpu(), pa[k])
+    # bf16 path: the in-kernel noise, twenty steps on one batch: the imitation loss goes down
+    b = _mk("actor", cfg, pa)
+    b.precision = "bf16"
+    img, goal, act = (batch[k].cuda() for k in ("obs", "pobs", "act"))
+    ls = [float(b.bc_step(img, goal, act, lr=1e-3)) for _ in range(20)]
+    assert np.isfinite(ls).all() and np.mean(ls[-3:]) < 0.8 * np.mean(ls[:3]), ls
