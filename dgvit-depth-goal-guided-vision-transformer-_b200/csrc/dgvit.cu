@@ -414,6 +414,9 @@ static bool launch_attention_row0(const A* QKV, A* O, const A* dO, A* dQKV, cons
   if (d.dh != R0_DH || d.N > R0_MAXN || !(g_row0_mode & (dO ? 2 : 1))) return false;
   if ((((uintptr_t)QKV) & 15) || (dO && ((((uintptr_t)dO) | ((uintptr_t)dQKV)) & 15))) return false;
   const int items = d.B * d.H;
+  // a handful of (sample, head) items (batch-1 act: 4) is one under-filled block walking 65 keys serially: 15 us against 6 us
+  // for the tensor-core kernel on the whole (tiny) tile
+  if (!dO && items < 32 && std::is_same<A, bf16>::value) return false;
   const float scale = 1.0f / sqrtf((float)d.dh);
   if (!dO) launch_k(attention_row0_fwd_kernel<A>, (unsigned)cdiv(items, 4), 128, 0, st, QKV, O, items, d.N, d.H, scale);
   else launch_k(attention_row0_bwd_kernel<A>, (unsigned)cdiv(items, 4), 128, 0, st, QKV, dO, dQKV, items, d.N, d.H, scale);
