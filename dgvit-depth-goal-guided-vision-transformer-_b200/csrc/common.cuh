@@ -75,6 +75,50 @@ inline bool& pdl_enabled() {
   static bool e = true;
   return e;
 }
+// Programmatic dependent launch and the non-coherent load path.  A kernel launched with the programmatic attribute starts
+// its life while the kernel before it in the stream is still running (it blocks in griddepcontrol.wait before touching data).
+// `ld.global.nc` / __ldg promise "read-only for the lifetime of the kernel", which that early start breaks for anything the
+// previous kernel writes.  Two rules follow: (1) buffers produced by the launch right before (partial sums, frames just
+// gathered, activations, the clip factor of the optimizer) are read with coherent loads (__ldcg or plain), never __ldg;
+// (2) parameters (biases, LayerNorm gains, position embedding) stay on the __ldg path, so the kernel right after a kernel
+// that REWRITES parameters (Adam, Polyak, shadow refresh) -- and the first launch of every C call on each stream, whose
+// predecessor belongs to the caller -- is an ordinary, fully serialised launch.
+struct NoPdlOnce {
+  cudaStream_t strict[8];      // streams whose next launch must be an ordinary one
+  int n_strict = 0;
+  unsigned epoch = 0;          // bumped at every C entry point
+  cudaStream_t seen[16];
+  unsigned seen_epoch[16];
+  int n_seen = 0;
+  void mark_strict(cudaStream_t st) {
+    for (int i = 0; i < n_strict; ++i)
+      if (strict[i] == st) return;
+    if (n_strict < 8) strict[n_strict++] = st;
+    else strict[0] = st;
+  }
+  bool take(cudaStream_t st) {
+    bool hit = false;
+    for (int i = 0; i < n_strict; ++i)
+      if (strict[i] == st) { strict[i] = strict[--n_strict]; hit = true; break; }
+    int k = -1;
+    for (int i = 0; i < n_seen; ++i)
+      if (seen[i] == st) { k = i; break; }
+    if (k < 0) {
+      k = n_seen < 16 ? n_seen++ : 0;
+      seen[k] = st; seen_epoch[k] = epoch - 1;
+    }
+    if (seen_epoch[k] != epoch) { seen_epoch[k] = epoch; hit = true; }      // first launch of this C call on this stream
+    return hit;
+  }
+};
+inline NoPdlOnce& no_pdl_once() {
+  static thread_local NoPdlOnce r;
+  return r;
+}
+static inline bool pdl_for_launch(cudaStream_t st) {
+  const bool strict = no_pdl_once().take(st);          // (always consumed)
+  return pdl_enabled() && !strict;
+}
 template <typename... KArgs, typename... Args>
 static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                             Args&&... args) {
@@ -85,7 +129,7 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_for_launch(st) ? 1 : 0;
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
   if (e != cudaSuccess) {
     cudaGetLastError();      // a refused launch must not linger as the "last error" of a later, unrelated call
@@ -107,7 +151,7 @@ static inline void launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bl
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = pdl_for_launch(st) ? 2 : 1;
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -158,6 +202,7 @@ struct ProfScope {
 template <typename F>
 static inline int guarded(F&& f) {
   try {
+    ++no_pdl_once().epoch;           // the first launch of a call on each stream is fully serialised behind whatever the caller queued
     f();
     return DGVIT_OK;
   } catch (const Fail& e) {

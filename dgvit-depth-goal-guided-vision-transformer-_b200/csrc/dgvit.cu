@@ -584,6 +584,7 @@ static void trunk_forward(const dgvit_net& net, const dgvit_layout& L, const Dim
 struct SideState { cudaStream_t s; cudaEvent_t now, dw, mr; };
 static bool g_side_enabled = true;
 static bool g_fork_enabled = true;
+static int g_target_fork = 1;       // set_option "target_fork": critic_target's trunk on its own stream beside policy.sample(s')
 static int g_actor_s_when = 1;      // set_option "actor_s_when": 0 = policy.sample(s) forward starts at the fork, 1 = after the
                                     // policy.sample(s') forward, 2 = after the target critic forward (beside the critic backward)
 static SideState& side_state() {      // one set of streams / events per device
@@ -700,6 +701,11 @@ static void trunk_backward(const dgvit_net& net, const dgvit_layout& L, const Di
     fused = false;
 #endif
     if (!fused) {
+      // These weight-gradient GEMMs put their split-K / column-sum partials at the START of c.partial, from the main stream,
+      // right now: the previous block's multi-reduce (side stream) reads its queued partial sums from the same place and must
+      // be done first.  (Found as run-to-run different LayerNorm / bias gradients of the block above whenever D != 64 --
+      // this path -- ran with the side stream on: profiles/race_where.py.)
+      if (side && have_mr) { DG_CUDA(cudaStreamWaitEvent(st, sd->mr, 0)); have_mr = false; }
       GemmArgs g;
       g.M = (int)R; g.N = d.M; g.K = d.D;
       g.A = dxop; g.a_sm = d.D; g.a_sk = 1;
@@ -936,12 +942,20 @@ static void critic_heads_forward(const dgvit_net& net, const dgvit_layout& L, co
 
 template <typename A>
 static void critic_forward(const dgvit_net& net, const dgvit_layout& L, const Dims& d, const dgvit_critic_io& io,
-                           int64_t sample_offset, CriticCtx<A>& c, cudaStream_t st) {
+                           int64_t sample_offset, CriticCtx<A>& c, cudaStream_t st, cudaStream_t trunk_st = nullptr,
+                           cudaEvent_t trunk_done = nullptr) {
   const float* P = net.params;
   DG_REQUIRE(io.img && io.pstate && io.action && io.q1 && io.q2, "critic_forward: null input/output");
   const DropDev drop = make_drop(io.drop, d, sample_offset);
   const GoalTok gt{io.pstate, P + L.embed_w, P + L.embed_b, d.nps, 1};      // relu(fc_embed) (got_sac_network.py:111)
-  trunk_forward<A>(net, L, d, io.img, drop, c.t, st, gt, /*fuse_rms=*/true);
+  // the action enters at the heads only: the trunk may run on another stream, beside whatever produces the action
+  if (trunk_st && trunk_st != st) {
+    trunk_forward<A>(net, L, d, io.img, drop, c.t, trunk_st, gt, /*fuse_rms=*/true);
+    DG_CUDA(cudaEventRecord(trunk_done, trunk_st));
+    DG_CUDA(cudaStreamWaitEvent(st, trunk_done, 0));
+  } else {
+    trunk_forward<A>(net, L, d, io.img, drop, c.t, st, gt, /*fuse_rms=*/true);
+  }
   critic_heads_forward(net, L, d, c.t.z, io.action, c.xcat, c.h1a, c.h2a, c.h1b, c.h2b, io.q1, io.q2, st, c.t.Xout);
 }
 
@@ -1045,6 +1059,8 @@ static void adam_step(const dgvit_net& net, const dgvit_layout& L, const dgvit_a
       launch_k(adam_polyak_kernel<false>, 148 * 8, 256, 0, st, a, DpDev(), (unsigned int*)nullptr);
     }
     DG_LAUNCH_CHECK();
+    no_pdl_once().mark_strict(st);      // the next kernel on this stream may read the parameters just rewritten (bias / LayerNorm /
+                                        // position loads go through the non-coherent path): it must not start before this one ends
   }
 }
 
@@ -1093,8 +1109,8 @@ static dgvit_drop sac_drop(const dgvit_sac& s, const dgvit_noise* nz, const uint
 // policy.sample(s).  They are issued on three streams (fork/join with events: capturable into
 // one CUDA graph) so that their many small, latency-bound kernels fill each other's gaps.
 struct ForkState {
-  cudaStream_t aux[2];
-  cudaEvent_t fork, fork2, fork3, join[2];
+  cudaStream_t aux[3];
+  cudaEvent_t fork, fork2, fork3, fork4, join[3];
 };
 static ForkState& fork_state() {
   static ForkState per_dev[64];
@@ -1103,7 +1119,7 @@ static ForkState& fork_state() {
   ForkState& f = per_dev[dev];
   bool& init = inited[dev];
   if (!init) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       const char* pe = getenv("DGVIT_AUX_PRIO");
       DG_CUDA(cudaStreamCreateWithPriority(&f.aux[i], cudaStreamNonBlocking, pe ? atoi(pe) : 0));
       DG_CUDA(cudaEventCreateWithFlags(&f.join[i], cudaEventDisableTiming));
@@ -1111,6 +1127,7 @@ static ForkState& fork_state() {
     DG_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
     DG_CUDA(cudaEventCreateWithFlags(&f.fork2, cudaEventDisableTiming));
     DG_CUDA(cudaEventCreateWithFlags(&f.fork3, cudaEventDisableTiming));
+    DG_CUDA(cudaEventCreateWithFlags(&f.fork4, cudaEventDisableTiming));
     init = true;
   }
   return f;
@@ -1124,7 +1141,7 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
   make_layout(s.critic.cfg, Lc);
   ForkState& f0 = fork_state();
   ForkState f = f0;
-  if (!g_fork_enabled) { f.aux[0] = st; f.aux[1] = st; }      // single-stream mode (per-kernel timing)
+  if (!g_fork_enabled) { f.aux[0] = st; f.aux[1] = st; f.aux[2] = st; }      // single-stream mode (per-kernel timing)
   // the five forward passes of an update see two distinct frame batches: patchify s and s' once, before the fork
   // (s' on the caller's stream, s on the first forked stream; the second forked stream starts after the latter)
   DG_CUDA(cudaEventRecord(f.fork, st));
@@ -1167,13 +1184,18 @@ static void sac_phase1(const dgvit_sac& s, const dgvit_batch& b, const dgvit_noi
     DG_CUDA(cudaEventRecord(f.join[1], f.aux[1]));
   };
   launch_actor_s(0);
+  if (g_target_fork && f.aux[2] != st) {     // critic_target's trunk starts here (after the patch matrix of s', if there is one)
+    DG_CUDA(cudaEventRecord(f.fork4, st));
+    DG_CUDA(cudaStreamWaitEvent(f.aux[2], f.fork4, 0));
+  }
   actor_forward<A>(s.actor, La, d, ai, w.actor_tmp, st);
   launch_actor_s(1);
   dgvit_critic_io ci; memset(&ci, 0, sizeof(ci));
   ci.img = b.next_obs; ci.pstate = b.next_pobs; ci.action = w.a2;
   ci.drop = sac_drop(s, nz, nz ? nz->mask_ct : nullptr, 2);
   ci.q1 = w.q1t; ci.q2 = w.q2t;
-  critic_forward<A>(s.critic_target, Lc, d, ci, s.sample_offset, w.critic_tmp, st);
+  // (its trunk does not need a': with "target_fork" it starts at the fork on a stream of its own, the heads follow policy.sample(s'))
+  critic_forward<A>(s.critic_target, Lc, d, ci, s.sample_offset, w.critic_tmp, st, g_target_fork ? f.aux[2] : nullptr, f.join[2]);
   // ---- stream 1: critic(s, a)                                                   (DRL.py:395)
   dgvit_critic_io cs; memset(&cs, 0, sizeof(cs));
   cs.img = b.obs; cs.pstate = b.pobs; cs.action = b.act;
@@ -1486,6 +1508,7 @@ int dgvit_set_option(const char* name, int value) {
     if (!strcmp(name, "fork_streams")) g_fork_enabled = value != 0;
     else if (!strcmp(name, "bwd_side")) g_side_enabled = value != 0;
     else if (!strcmp(name, "actor_s_when")) g_actor_s_when = value >= 0 && value <= 2 ? value : 0;
+    else if (!strcmp(name, "target_fork")) g_target_fork = value != 0;
     else if (!strcmp(name, "ln_bwd_warps")) g_lnb_wpb = value >= 1 && value <= 16 ? value : 16;
     else if (!strcmp(name, "ln_bwd_blocks_per_sm")) g_lnb_bps = value >= 1 && value <= 4 ? value : 2;
     else if (!strcmp(name, "pdl")) pdl_enabled() = value != 0;

@@ -167,12 +167,12 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, float*
     for (; k + 8 <= S; k += 8) {
       float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(partial + (int64_t)(k + u) * n + i));
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)(k + u) * n + i));
 #pragma unroll
       for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
     }
     for (; k < S; ++k) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (int64_t)k * n + i));
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)k * n + i));
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     *reinterpret_cast<float4*>(out + i) = s;
@@ -190,6 +190,9 @@ static inline unsigned reduce_grid(int64_t n) { return (unsigned)cdiv(cdiv(n, 4)
 // transformer block produces five to ten of them (split-K weight gradients, LayerNorm parameter / bias partials);
 // each is a few microseconds of pure latency as its own kernel.  Block = 16 warps x 128 consecutive floats of one
 // job: warp w sums the partial rows k = w, w+16, ..., the 16 warp sums are added in a fixed order.
+// (the partial sums are produced by the launches right before these kernels and their buffers are reused from block to block:
+//  they must not be read through the non-coherent path, whose contract -- read-only for the kernel's lifetime -- a
+//  programmatically launched kernel breaks: its lifetime starts while the producer still runs.  __ldcg = L2, coherent.)
 struct ReduceJob {
   const float* part; float* out;
   int S, n; int64_t stride; int blk0;
@@ -213,15 +216,15 @@ __global__ void __launch_bounds__(MR_WARPS * 32) multi_reduce_kernel(ReduceJobs 
     const float* p = j.part + e;
     int k = w;
     for (; k + 3 * MR_WARPS < j.S; k += 4 * MR_WARPS) {
-      const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + (int64_t)k * j.stride));
-      const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(k + MR_WARPS) * j.stride));
-      const float4 v2 = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(k + 2 * MR_WARPS) * j.stride));
-      const float4 v3 = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(k + 3 * MR_WARPS) * j.stride));
+      const float4 v0 = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)k * j.stride));
+      const float4 v1 = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)(k + MR_WARPS) * j.stride));
+      const float4 v2 = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)(k + 2 * MR_WARPS) * j.stride));
+      const float4 v3 = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)(k + 3 * MR_WARPS) * j.stride));
       s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y);
       s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
     }
     for (; k < j.S; k += MR_WARPS) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p + (int64_t)k * j.stride));
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)k * j.stride));
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
   }

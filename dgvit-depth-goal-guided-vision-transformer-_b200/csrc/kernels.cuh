@@ -1170,7 +1170,7 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
   }
   __syncthreads();
   const float step_size = sh[0], bc2s = sh[1];
-  const float gs = a.gscale ? __ldg(a.gscale) : 1.0f;
+  const float gs = a.gscale ? __ldcg(a.gscale) : 1.0f;       // written by the launch right before this one
   const int64_t n4 = a.n >> 2;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = q << 2;

@@ -59,7 +59,7 @@ __device__ __forceinline__ void frames_to_tiles(uint8_t* tiles, const float* img
       const int i = base + u * THREADS;
       const int yy = i / ROW4, q = i % ROW4;
       const int r = (yy / PH) * GW + (4 * q) / PW;
-      v[u] = (i < ITEMS && t0 + r < n_tok) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[u] = (i < ITEMS && t0 + r < n_tok) ? __ldcg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);      // (frames: written by the gather right before)
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {

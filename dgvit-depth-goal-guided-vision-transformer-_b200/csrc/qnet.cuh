@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
     for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
       for (int kx = 0; kx < KS; ++kx) {
-        const float v = __ldg(xp + ky * W0 + kx);
+        const float v = xp[ky * W0 + kx];        // (frames may come from the launch right before: no non-coherent loads)
 #pragma unroll
         for (int c = 0; c < C1; ++c) acc[c] = fmaf(ws[ky * KS + kx][c], v, acc[c]);
       }
@@ -111,9 +111,9 @@ template <typename T> struct Vec8;                       // 8 consecutive elemen
 template <> struct Vec8<float> { float4 a, b; };
 template <> struct Vec8<bf16> { uint4 a; };
 __device__ __forceinline__ void ld_vec8(const float* p, Vec8<float>& v) {
-  v.a = __ldg(reinterpret_cast<const float4*>(p)); v.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v.a = reinterpret_cast<const float4*>(p)[0]; v.b = reinterpret_cast<const float4*>(p)[1];
 }
-__device__ __forceinline__ void ld_vec8(const bf16* p, Vec8<bf16>& v) { v.a = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void ld_vec8(const bf16* p, Vec8<bf16>& v) { v.a = *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void st_vec8(float* p, const Vec8<float>& v) {
   reinterpret_cast<float4*>(p)[0] = v.a; reinterpret_cast<float4*>(p)[1] = v.b;
 }
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(C1W_THREADS) conv1_bwd_w_kernel(const float* _
     for (int i = tid; i < C1W_PIX * (C1 / 4); i += C1W_THREADS) {
       const int64_t p = q0 + i / (C1 / 4);
       reinterpret_cast<float4*>(&dys[0][0])[i] =
-          p < p1 ? __ldg(reinterpret_cast<const float4*>(dY1 + p * C1) + i % (C1 / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          p < p1 ? reinterpret_cast<const float4*>(dY1 + p * C1)[i % (C1 / 4)] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     {                                                    // thread = staged pixel: its coordinates once, then the 25 taps
       static_assert(C1W_PIX == C1W_THREADS, "one staged pixel per thread");
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(C1W_THREADS) conv1_bwd_w_kernel(const float* _
         const unsigned pu = (unsigned)p, pr = pu / W1, ox = pu - pr * W1, bi = pr / H1, oy = pr - bi * H1;
         const float* src = x + ((size_t)bi * H0 + oy * ST) * W0 + ox * ST;
 #pragma unroll
-        for (int t = 0; t < TAPS; ++t) xs[tid][t] = __ldg(src + (t / KS) * W0 + t % KS);
+        for (int t = 0; t < TAPS; ++t) xs[tid][t] = src[(t / KS) * W0 + t % KS];
       } else {
 #pragma unroll
         for (int t = 0; t < TAPS; ++t) xs[tid][t] = 0.f;

@@ -508,3 +508,27 @@ def test_behaviour_cloning_step_single_call():
     img, goal, act = (batch[k].cuda() for k in ("obs", "pobs", "act"))
     ls = [float(b.bc_step(img, goal, act, lr=1e-3)) for _ in range(20)]
     assert np.isfinite(ls).all() and np.mean(ls[-3:]) < 0.8 * np.mean(ls[:3]), ls
+
+
+@pytest.mark.gpu
+def test_update_is_run_to_run_deterministic_with_unfused_mlp():
+    """Regression: with D != 64 the MLP backward runs as separate GEMMs whose split-K partials live at the start of the
+    partial-sum workspace; they used to be written from the main stream while the previous block's deferred reduction (side
+    stream) could still be reading its queued partial sums from the same place -> LayerNorm / bias gradients of the block
+    above changed from run to run whenever another forward pass shifted the timing (`actor_s_when` = 2 made it 8 runs in 12).
+    Same seed, same batches: the eager multi-stream update must reproduce bit for bit."""
+    def run():
+        ag = dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, False, 11, BUFFER_SIZE=300, TAU=5e-4,
+                    POLICY_FREQ=1, GAMMA=0.999, ALPHA=1.0, block=2, head=2, l_f_size=32, precision="bf16")
+        ag.replay_buffer.fill_synthetic(300, seed=3)
+        for B in (64, 64, 128, 64, 128, 128, 64):
+            ag.learn_async(B)
+        torch.cuda.synchronize()
+        return torch.cat([ag.policy._arena.flatten(), ag.critic._arena.flatten(), ag._loss_buffer().flatten()]).clone()
+    try:
+        L.check(L.lib().dgvit_set_option(b"actor_s_when", 2), "set_option")
+        ref = run()
+        for _ in range(6):
+            assert torch.equal(run(), ref)
+    finally:
+        L.check(L.lib().dgvit_set_option(b"actor_s_when", 1), "set_option")
