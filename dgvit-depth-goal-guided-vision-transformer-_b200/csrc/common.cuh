@@ -77,12 +77,12 @@ inline bool& pdl_enabled() {
 }
 // Programmatic dependent launch and the non-coherent load path.  A kernel launched with the programmatic attribute starts
 // its life while the kernel before it in the stream is still running (it blocks in griddepcontrol.wait before touching data).
-// `ld.global.nc` / __ldg promise "read-only for the lifetime of the kernel", which that early start breaks for anything the
-// previous kernel writes.  Two rules follow: (1) buffers produced by the launch right before (partial sums, frames just
-// gathered, activations, the clip factor of the optimizer) are read with coherent loads (__ldcg or plain), never __ldg;
-// (2) parameters (biases, LayerNorm gains, position embedding) stay on the __ldg path, so the kernel right after a kernel
-// that REWRITES parameters (Adam, Polyak, shadow refresh) -- and the first launch of every C call on each stream, whose
-// predecessor belongs to the caller -- is an ordinary, fully serialised launch.
+// `ld.global.nc` / __ldg promise "read-only for the lifetime of the kernel", which that early start formally breaks for
+// anything the previous kernel writes.  No wrong value was ever traced to it (the compiler emits LDG.CONSTANT for most
+// `const __restrict__` loads anyway and the update is bit-reproducible), but as a precaution: (1) the reductions read the
+// partial sums of the launch right before them with __ldcg; (2) the launch right after a kernel that REWRITES parameters
+// (Adam) -- and the first launch of every C call on each stream, whose predecessor belongs to the caller -- is an ordinary,
+// fully serialised launch.
 struct NoPdlOnce {
   cudaStream_t strict[8];      // streams whose next launch must be an ordinary one
   int n_strict = 0;

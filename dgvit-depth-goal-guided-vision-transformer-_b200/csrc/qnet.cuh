@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
     for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
       for (int kx = 0; kx < KS; ++kx) {
-        const float v = xp[ky * W0 + kx];        // (frames may come from the launch right before: no non-coherent loads)
+        const float v = __ldg(xp + ky * W0 + kx);   // (the frames are not written inside the update)
 #pragma unroll
         for (int c = 0; c < C1; ++c) acc[c] = fmaf(ws[ky * KS + kx][c], v, acc[c]);
       }
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(C1W_THREADS) conv1_bwd_w_kernel(const float* _
         const unsigned pu = (unsigned)p, pr = pu / W1, ox = pu - pr * W1, bi = pr / H1, oy = pr - bi * H1;
         const float* src = x + ((size_t)bi * H0 + oy * ST) * W0 + ox * ST;
 #pragma unroll
-        for (int t = 0; t < TAPS; ++t) xs[tid][t] = src[(t / KS) * W0 + t % KS];
+        for (int t = 0; t < TAPS; ++t) xs[tid][t] = __ldg(src + (t / KS) * W0 + t % KS);
       } else {
 #pragma unroll
         for (int t = 0; t < TAPS; ++t) xs[tid][t] = 0.f;
