@@ -192,9 +192,13 @@ static void linear_bwd_w(const TA* dy, const TB* x, float* dW, float* db, int64_
 // db[N] = colsum(dy[R, N]) through the deferred reduction (fixed summation order)
 template <typename TA>
 static void bias_grad_colsum(const TA* dy, int64_t ldy, float* db, int64_t R, int N, ReduceList& rl, cudaStream_t st) {
-  const int S = (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 128);   // row ranges per column block
+  // narrow dy (N = 64: the patch-embedding bias): whole-row warps instead of 32 active threads per block
+  const bool tall = R >= 4096 && N % 2 == 0 && N <= 512 && 256 % (N / 2) == 0 && ldy % 2 == 0 && ((((uintptr_t)dy) & 7) == 0);
+  const int S = tall ? (int)std::min<int64_t>(R / 128, 148 * 2)
+                     : (int)std::min<int64_t>(std::max<int64_t>(R / 64, 1), 128);   // row ranges per column block
   float* partial = rl.alloc((size_t)S * N);
-  launch_k(colsum_partial_kernel<TA>, dim3((unsigned)cdiv(N, 256), (unsigned)S), 128, 0, st, dy, ldy, partial, R, N, cdiv(R, S));
+  if (tall) launch_k(colsum_tall_kernel<TA>, (unsigned)S, 256, 0, st, dy, ldy, partial, R, N, cdiv(R, S));
+  else launch_k(colsum_partial_kernel<TA>, dim3((unsigned)cdiv(N, 256), (unsigned)S), 128, 0, st, dy, ldy, partial, R, N, cdiv(R, S));
   DG_LAUNCH_CHECK();
   rl.add(partial, db, S, N, N);
 }
@@ -296,7 +300,7 @@ static void carve_trunk(Carver& cv, const Dims& d, bool save, TrunkCtx<A>& c) {
     // one block's worth of queued reductions (split-K dW of qkv / out / both MLP matrices + LayerNorm partials)
     const int64_t per_block = (int64_t)32 * (4 * d.inner * d.D + 2 * d.D * d.M) + (int64_t)8 * d.D * 148 * 4 + 4 * d.M + 4096;
     // + the reductions outside the blocks (rms gain, pos embedding, patch dW split-K + bias)
-    c.misc_floats = (size_t)(64 * d.D + (int64_t)32 * d.N * d.D + (int64_t)80 * d.D * d.pd + 256 * d.D + 1024);
+    c.misc_floats = (size_t)(64 * d.D + (int64_t)32 * d.N * d.D + (int64_t)80 * d.D * d.pd + 320 * d.D + 1024);
     c.partial_floats = (size_t)std::max<int64_t>(mx * 32, per_block) + c.misc_floats;
     c.partial = cv.take<float>(c.partial_floats);
   }

@@ -202,6 +202,12 @@ struct ReduceJobs {
   int njobs;
 };
 constexpr int MR_WARPS = 16;
+constexpr int MR_WIDE_S = 32;            // jobs with at most this many partial rows run in "wide" mode
+// Two shapes of job.  Tall (S > 32 rows of a few hundred floats: LayerNorm / bias partials, one row per producer block):
+// block = 16 warps x 128 consecutive floats, warp w sums rows w, w+16, ..., the 16 warp sums are added in a fixed order.
+// Wide (S <= 32 rows of up to a quarter million floats: split-K weight gradients): with 9 rows only 9 of those 16 warps had
+// a single load to do; there each thread owns one float4 column of 2048 per block and sums all S rows itself, eight loads
+// in flight (round 2: 13.9 -> ~5 us per launch in the ncu list).
 __global__ void __launch_bounds__(MR_WARPS * 32) multi_reduce_kernel(ReduceJobs a) {
   pdl_wait();
   pdl_launch();
@@ -209,6 +215,26 @@ __global__ void __launch_bounds__(MR_WARPS * 32) multi_reduce_kernel(ReduceJobs 
   int ji = 0;
   while (ji + 1 < a.njobs && (int)blockIdx.x >= a.job[ji + 1].blk0) ++ji;
   const ReduceJob& j = a.job[ji];
+  if (j.S <= MR_WIDE_S) {
+    const int64_t e = ((int64_t)((int)blockIdx.x - j.blk0) * (MR_WARPS * 32) + threadIdx.x) * 4;
+    if (e >= j.n) return;
+    const float* p = j.part + e;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = 0;
+    for (; k + 8 <= j.S; k += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)(k + u) * j.stride));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; k < j.S; ++k) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)k * j.stride));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(j.out + e) = s;
+    return;
+  }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t e = ((int64_t)((int)blockIdx.x - j.blk0) * 32 + lane) * 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -254,7 +280,7 @@ struct ReduceList {
                "multi_reduce: job table full or unaligned job");
     ReduceJob& j = a.job[a.njobs++];
     j.part = part; j.out = out; j.S = S; j.n = (int)n; j.stride = stride; j.blk0 = blocks;
-    blocks += (int)cdiv(n, 128);
+    blocks += (int)cdiv(n, S <= MR_WIDE_S ? MR_WARPS * 32 * 4 : 128);
   }
   void launch(cudaStream_t st) {
     if (a.njobs && !(skip_mask() & SKIP_REDUCE)) {
