@@ -571,7 +571,8 @@ def teardown(ag, dist):
 
 def run_next_rows(dev):
     """SURVEY §8f "next" rows, measured through the agent API on one GPU (informational; B = 256, bf16):
-       f1  SAC.learn with the CNN twin-Q critic (the reference's shipped default critic_type), module path;
+       f1  SAC.learn with the CNN twin-Q critic (the reference's shipped default critic_type): the same single-call update;
+       f3  the behaviour-cloning step as one C call (GoTPolicy.bc_step);
        f2  SAC.learn_guidence (agent + expert minibatch, guidance / engage imitation rows in the same fused update);
        f4  replay write path: store_transition one at a time (control loop) and a batched append (demonstration ingest)."""
     import numpy as np
