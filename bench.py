@@ -618,12 +618,14 @@ def run_next_rows(dev):
         out["f3_bc_step"] = dict(error=repr(e)[:200])
     try:
         a2 = dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, True, SEED, BUFFER_SIZE=4096, buffer_size_expert=2048,
-                    precision="bf16", device=dev, **HP, **PRESET)
+                    precision="bf16", device=dev, use_cuda_graph=True, **HP, **PRESET)
         a2.replay_buffer.fill_synthetic(4096, seed=SEED)
         a2.replay_buffer.engage_host[:4096:7] = 1.0
         a2.replay_buffer_expert.fill_synthetic(2048, seed=SEED + 1)
-        out["f2_learn_guidence"] = dict(value=256 * rate(lambda: a2.learn_guidence(False, 256), 10), unit=UNIT,
-                                        what="SAC.learn_guidence(batch 256 + expert share + guidance / engage rows), one fused update per call")
+        out["f2_learn_guidence"] = dict(value=256 * rate(lambda: a2.learn_guidence(False, 256), 20, warm=8), unit=UNIT,
+                                        what="SAC.learn_guidence(256): agent + expert minibatch, guidance / engage imitation rows (engage rows "
+                                             "padded to a multiple of 32 with weight 0), assembly + one fused update per call, CUDA graph, "
+                                             "losses read back every call")
         rs = np.random.RandomState(0)
         s0, s1 = rs.rand(128, 160, 1).astype(np.float32), rs.rand(128, 160, 1).astype(np.float32)
         one = lambda: a2.store_transition(s0, np.zeros(2, np.float32), np.zeros(2, np.float32), np.zeros(2, np.float32), 0.5, s1, 0.0, None, 0)

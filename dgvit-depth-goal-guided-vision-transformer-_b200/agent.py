@@ -528,29 +528,32 @@ class SAC(object):
             self._cap_stream = torch.cuda.Stream(device=self.device, priority=prio)
         return self._cap_stream
 
-    def _run(self, key, batch, gather: bool) -> torch.Tensor:
+    def _run(self, key, batch, gather, extra=None) -> torch.Tensor:
         """Eager on the first call with a key (warms lazily initialised state), captured on the second,
         replayed afterwards.  Every launch, tensor map and device pointer of the update is frozen in the
         graph; per-step state (Adam step counts, alpha, RNG counter, sampled indexes) lives in device
         memory.  Single GPU: one graph for gather + update.  Data parallel: one graph per phase with the
-        two NCCL gradient all-reduces issued between them."""
+        two NCCL gradient all-reduces issued between them.  ``gather``: True = the replay gather of ``learn``, a callable =
+        the minibatch assembly of ``learn_guidence`` (gathers + row copies); either is part of the graph."""
         dp = self.distributed and self.world > 1 and self._dp is None
+        if gather is True:
+            pre = lambda: self.replay_buffer.gather(batch["_idx"], batch)
+        else:
+            pre = gather if callable(gather) else (lambda: None)
         if not self.use_cuda_graph:
-            if gather:
-                self.replay_buffer.gather(batch["_idx"], batch)
-            return self.update_from_batch(batch)
+            pre()
+            return self.update_from_batch(batch, extra=extra)
         # a graph freezes every device pointer: re-bound arenas (.to(), load_state_dict(assign=True)) start new entries
         key = key + (int(self.itera % self.policy_freq == 0), self.policy.net_struct().params,
                      self.critic.net_struct().params, self.critic_target.net_struct().params)
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = "warm"
-            if gather:
-                self.replay_buffer.gather(batch["_idx"], batch)
-            return self.update_from_batch(batch)
+            pre()
+            return self.update_from_batch(batch, extra=extra)
         if ent == "warm":
             torch.cuda.synchronize(self.device)
-            phase = self.update_from_batch(batch, _phases=True)
+            phase = self.update_from_batch(batch, _phases=True, extra=extra)
             graphs = []
             # Data parallel: either one graph per phase with the NCCL all-reduces issued eagerly between them, or
             # (DGVIT_GRAPH_NCCL=1) the collectives captured too, one graph per update; `close()` must then run before the
@@ -559,8 +562,8 @@ class SAC(object):
             for i, which in enumerate((1, 2, 3) if (dp and not one) else (0,)):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self._capture_stream()):
-                    if gather and i == 0:
-                        self.replay_buffer.gather(batch["_idx"], batch)
+                    if i == 0:
+                        pre()
                     if one:
                         keep = phase(1)
                         allreduce_sum_(self.critic._garena)
@@ -595,6 +598,8 @@ class SAC(object):
             Be = int(min(np.floor(re.get_stored_size() / rb.get_stored_size() * B), B))      # :193-196
         idx_a = rb.sample_indexes(B)
         eng_rows = np.nonzero(rb.engage_host[idx_a.numpy()] == 1)[0]                         # :266
+        if self.use_cuda_graph:
+            return self._learn_guidence_graphed(B, Be, idx_a, eng_rows)
         Bc, n_extra = B + Be, Be + len(eng_rows)
         f = rb.obs.shape[1]
         dev = self.device
@@ -625,6 +630,80 @@ class SAC(object):
         extra = None if n_extra == 0 else dict(target=buf["target"][:n_extra], weight=buf["weight"][:n_extra])
         losses = self.update_from_batch({k: buf[k] for k in ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done")},
                                         extra=extra).tolist()
+        self.alpha = float(self._alpha.item()) if self.automatic_entropy_tuning else self.alpha
+        return losses[0], losses[1]
+
+    def _learn_guidence_graphed(self, B: int, Be: int, idx_a: torch.Tensor, eng_rows: np.ndarray):
+        """``learn_guidence`` replayed from a CUDA graph.  The number of engaged rows changes from call to call; a graph
+        needs fixed shapes, so the engage rows are padded to the next multiple of 32 with rows of weight 0 (a zero-weight
+        imitation row contributes exact zeros to the loss and to every gradient).  One graph per (B, Be, padded count):
+        sampled indexes, engaged-row indexes and the per-row weights arrive through pinned staging buffers; the two
+        gathers, the row copies and the update are graph nodes."""
+        rb, re = self.replay_buffer, self.replay_buffer_expert
+        dev = self.device
+        n_e = len(eng_rows)
+        n_pad = 0 if n_e == 0 else min(B, (n_e + 31) // 32 * 32)
+        Bc, n_extra = B + Be, Be + n_pad
+        key = ("guidence", B, Be, n_pad)
+        st = self._gbuf.get(key)
+        if st is None:
+            f = rb.obs.shape[1]
+            z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+            i64 = lambda n: torch.zeros(max(n, 1), dtype=torch.int64, device=dev)
+            st = dict(obs=z(Bc + n_extra, f), next_obs=z(Bc, f), pobs=z(Bc + n_extra, self.pstate_dim),
+                      next_pobs=z(Bc, self.pstate_dim), act=z(Bc, self.action_dim), rew=z(Bc, 1), done=z(Bc, 1),
+                      target=z(max(n_extra, 1), self.action_dim), weight=z(max(n_extra, 1)),
+                      idx_a=i64(B), idx_e=i64(Be), er=i64(n_pad),
+                      ring=[dict(idx_a=torch.zeros(B, dtype=torch.int64).pin_memory(),
+                                 idx_e=torch.zeros(max(Be, 1), dtype=torch.int64).pin_memory(),
+                                 er=torch.zeros(max(n_pad, 1), dtype=torch.int64).pin_memory(),
+                                 weight=torch.zeros(max(n_extra, 1)).pin_memory(), ev=torch.cuda.Event()) for _ in range(4)],
+                      slot=0)
+            self._gbuf[key] = st
+            # Be follows the fill ratio of the two stores and the padded count the data: keep the eight most recent shapes
+            gk = [k for k in self._gbuf if isinstance(k, tuple) and k and k[0] == "guidence"]
+            for old_key in gk[:-8]:
+                torch.cuda.synchronize(dev)
+                del self._gbuf[old_key]
+                for gkey in [k for k in self._graphs if k[:len(old_key)] == old_key]:
+                    del self._graphs[gkey]
+        pin = st["ring"][st["slot"]]
+        st["slot"] = (st["slot"] + 1) % len(st["ring"])
+        pin["ev"].synchronize()                      # the copies that last read this staging slot have completed
+        pin["idx_a"].copy_(idx_a)
+        if Be > 0:
+            pin["idx_e"][:Be].copy_(re.sample_indexes(Be))
+        w = pin["weight"]
+        w.zero_()
+        if Be > 0:
+            w[:Be] = self.guidence_weight / (Be * self.action_dim * self.world)
+        if n_e > 0:
+            pin["er"].zero_()
+            pin["er"][:n_e].copy_(torch.from_numpy(np.ascontiguousarray(eng_rows, dtype=np.int64)))
+            w[Be:Be + n_e] = self.engage_weight / (n_e * self.action_dim * self.world)
+        st["idx_a"].copy_(pin["idx_a"], non_blocking=True)
+        if Be > 0:
+            st["idx_e"][:Be].copy_(pin["idx_e"][:Be], non_blocking=True)
+        if n_pad > 0:
+            st["er"][:n_pad].copy_(pin["er"][:n_pad], non_blocking=True)
+        st["weight"].copy_(pin["weight"], non_blocking=True)
+        pin["ev"].record(torch.cuda.current_stream(dev))
+        fields = ("obs", "next_obs", "pobs", "next_pobs", "act", "rew", "done")
+
+        def assemble():
+            rb.gather(st["idx_a"], {k: st[k][0:B] for k in fields})
+            if Be > 0:
+                re.gather(st["idx_e"][:Be], {k: st[k][B:Bc] for k in fields})
+                st["obs"][Bc:Bc + Be].copy_(st["obs"][B:Bc])            # guidance rows = the expert minibatch again, :259-263
+                st["pobs"][Bc:Bc + Be].copy_(st["pobs"][B:Bc])
+                st["target"][:Be].copy_(st["act"][B:Bc])
+            if n_pad > 0:                                                # engaged rows, :267-273 (padding rows: row 0, weight 0)
+                torch.index_select(st["obs"][:Bc], 0, st["er"][:n_pad], out=st["obs"][Bc + Be:])
+                torch.index_select(st["pobs"][:Bc], 0, st["er"][:n_pad], out=st["pobs"][Bc + Be:])
+                torch.index_select(st["act"][:Bc], 0, st["er"][:n_pad], out=st["target"][Be:n_extra])
+
+        extra = None if n_extra == 0 else dict(target=st["target"][:n_extra], weight=st["weight"][:n_extra])
+        losses = self._run(key, {k: st[k] for k in fields}, assemble, extra=extra).tolist()
         self.alpha = float(self._alpha.item()) if self.automatic_entropy_tuning else self.alpha
         return losses[0], losses[1]
 

@@ -532,3 +532,28 @@ def test_update_is_run_to_run_deterministic_with_unfused_mlp():
             assert torch.equal(run(), ref)
     finally:
         L.check(L.lib().dgvit_set_option(b"actor_s_when", 1), "set_option")
+
+
+@pytest.mark.gpu
+def test_learn_guidence_graph_replay_matches_eager():
+    """``learn_guidence`` (vn/DRL.py:187-301) from a CUDA graph: the engaged rows are padded to a multiple of 32 with rows of
+    weight 0; same seeds -> same sampled rows, so the graph-replayed agent must follow the eager agent (fp32: the padding rows
+    add exact zeros; only the split points of the reductions move with the row count)."""
+    def run(graph):
+        ag = dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, True, 5, LR_C=1e-3, LR_A=1e-3, LR_ALPHA=1e-4,
+                    BUFFER_SIZE=128, TAU=5e-3, POLICY_FREQ=1, GAMMA=0.99, ALPHA=0.2, block=2, head=2, l_f_size=32,
+                    precision="fp32", buffer_size_expert=64, use_cuda_graph=graph)
+        rs = np.random.RandomState(0)
+        for i in range(60):
+            f1, f2 = rs.rand(128, 160).astype(np.float32), rs.rand(128, 160).astype(np.float32)
+            ag.store_transition(f1, rs.rand(2) * 2 - 1, rs.rand(2), rs.rand(2), float(rs.randn()), f2, float(i % 3 == 0), None, 0)
+            if i < 40:
+                ag.initialize_expert_buffer(f1, rs.rand(2) * 2 - 1, rs.rand(2), rs.rand(2), 1.0, f2, 0)
+        out = [ag.learn_guidence(False, 16) for _ in range(6)]
+        torch.cuda.synchronize()
+        return np.array(out), ag.policy._arena.detach().cpu().clone(), ag.critic._arena.detach().cpu().clone()
+    (lg, pg, cg), (le, pe, ce) = run(True), run(False)
+    assert np.isfinite(lg).all() and np.allclose(lg, le, rtol=2e-4, atol=1e-5), (lg, le)
+    for a, b in ((pg, pe), (cg, ce)):
+        d = (a - b).abs()
+        assert float((d > 5e-5).float().mean()) < 5e-3 and float(d.max()) < 5e-3, float(d.max())
