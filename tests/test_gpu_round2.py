@@ -535,12 +535,13 @@ def test_update_is_run_to_run_deterministic_with_unfused_mlp():
 
 
 @pytest.mark.gpu
-def test_learn_guidence_graph_replay_matches_eager():
+@pytest.mark.parametrize("critic", ["Transformer", "CNN"])
+def test_learn_guidence_graph_replay_matches_eager(critic):
     """``learn_guidence`` (vn/DRL.py:187-301) from a CUDA graph: the engaged rows are padded to a multiple of 32 with rows of
     weight 0; same seeds -> same sampled rows, so the graph-replayed agent must follow the eager agent (fp32: the padding rows
     add exact zeros; only the split points of the reductions move with the row count)."""
     def run(graph):
-        ag = dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, True, 5, LR_C=1e-3, LR_A=1e-3, LR_ALPHA=1e-4,
+        ag = dg.SAC(2, 2, "GaussianTransformer", critic, False, False, True, 5, LR_C=1e-3, LR_A=1e-3, LR_ALPHA=1e-4,
                     BUFFER_SIZE=128, TAU=5e-3, POLICY_FREQ=1, GAMMA=0.99, ALPHA=0.2, block=2, head=2, l_f_size=32,
                     precision="fp32", buffer_size_expert=64, use_cuda_graph=graph)
         rs = np.random.RandomState(0)
