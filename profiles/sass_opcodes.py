@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "dgvit-depth-goal-guided-vision-transformer-_b200", "libdgvit.so")
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 names = subprocess.run(["c++filt"], input="\n".join(re.findall(r"Function : (\S+)", sass)), capture_output=True, text=True).stdout.split("\n")
-COLS = ["UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "MULTIMEM", "MUFU.TANH", "MUFU.EX2", "FADD2", "LDGSTS", "HMMA"]
+COLS = ["UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "LDGMC", "MUFU.TANH", "MUFU.EX2", "FADD2", "LDGSTS", "HMMA"]
 rows, cur, i = [], None, -1
 for line in sass.split("\n"):
     m = re.search(r"Function : (\S+)", line)
@@ -23,7 +23,7 @@ for line in sass.split("\n"):
                 cur[c] += 1
 print("# SASS opcode summary of libdgvit.so (round 2, final code)\n")
 print("`cuobjdump -sass libdgvit.so`, counted per kernel (sm_100a; `profiles/sass_opcodes.py`). `UTCHMMA` = `tcgen05.mma kind::f16`, `LDTM` = `tcgen05.ld`, "
-      "`UTMALDG` / `UTMASTG` = TMA tile\nload / store (`cp.async.bulk.tensor`), `UTCBAR` = `tcgen05.commit`, `SYNCS` = mbarrier ops, `MULTIMEM` = "
+      "`UTMALDG` / `UTMASTG` = TMA tile\nload / store (`cp.async.bulk.tensor`), `UTCBAR` = `tcgen05.commit`, `SYNCS` = mbarrier ops, `LDGMC` = "
       "`multimem.ld_reduce` (NVLS), `FADD2` = packed fp32 pairs,\n`LDGSTS` = `cp.async`. There is no `HMMA` (legacy `mma.sync`) in any kernel of the library.\n")
 print("| kernel | " + " | ".join(COLS) + " |")
 print("|---|" + "---:|" * len(COLS))
