@@ -145,3 +145,52 @@ def test_no_cpu_fallback():
         dg.SAC(2, 2, "GaussianTransformer", "Transformer", False, False, False, 0)
     with pytest.raises(RuntimeError, match="CUDA"):
         dg.depth_augment(torch.zeros(8, 8))
+
+
+def test_depth_streaming_formulation_equals_the_staged_pipeline():
+    """The identities csrc/depth.cu's streaming kernels rest on, checked in numpy against the oracle's staged pipeline
+    (normalise -> +noise -> GaussianBlur(5,5) -> 11x11 on the centre band -> resize by 4 -> /255):
+      * off the band: resize(blur5(A)) is ONE separable stride-4 filter w6 = [1 5 10 10 5 1] / 32 over pixels 4o-1 .. 4o+4 of the
+        noisy image A, image borders by BORDER_REFLECT_101;
+      * in the band: horizontally ONE 16-tap composite c16 = k5 * (k11 at column 4o+1 + k11 at column 4o+2) / 2 over pixels
+        4o-6 .. 4o+9; vertically 5-tap, then the 11-tap with BORDER_REFLECT_101 INSIDE the band, sample rows 4o+1, 4o+2; an output
+        row with one sample outside the band takes that sample from the w6 path."""
+    from oracle.dgvit_oracle import gaussian_kernel
+    rs = np.random.RandomState(5)
+    for (H, W) in ((64, 80), (120, 96), (40, 136)):
+        raw = (rs.rand(H, W) * 7 + 0.5).astype(np.float32)
+        noise = rs.normal(0, 50, (H, W)).astype(np.float32)
+        want = O.depth_augment(raw, noise.astype(np.float64), out_hw=(H // 4, W // 4))
+        mn, mx = float(raw.min()), float(raw.max())
+        scale = 255.0 / (mx - mn)
+        u8 = np.trunc((raw.astype(np.float64) * scale - mn * scale).astype(np.float32).clip(0, 255))
+        A = np.clip(u8.astype(np.float64) + noise.astype(np.float64), 0, 255)
+        refl = lambda i, n: np.where(i < 0, -i, np.where(i >= n, 2 * (n - 1) - i, i))
+        k5, k11 = np.array([1, 4, 6, 4, 1]) / 16.0, gaussian_kernel(11).astype(np.float64).reshape(-1)
+        w6 = np.array([1, 5, 10, 10, 5, 1]) / 32.0
+        h12 = 0.5 * (np.append(k11, 0) + np.append(0, k11))
+        c16 = np.convolve(k5, h12)
+        oh, ow = H // 4, W // 4
+        cols6 = refl(4 * np.arange(ow)[:, None] - 1 + np.arange(6)[None, :], W)              # [ow, 6]
+        cols16 = refl(4 * np.arange(ow)[:, None] - 6 + np.arange(16)[None, :], W)            # [ow, 16]
+        Ah6 = (A[:, cols6] * w6).sum(-1)                                                      # [H, ow]
+        Ah16 = (A[:, cols16] * c16).sum(-1)
+        bh = H // 5
+        y1 = H // 2 - bh // 2
+        y2 = y1 + bh
+        blur5_rows = lambda M, q: sum(k5[t] * M[refl(q + t - 2, H)] for t in range(5))       # vertical 5-tap at row q
+        out = np.zeros((oh, ow))
+        for oy in range(oh):
+            acc = 0.0
+            for y in (4 * oy + 1, 4 * oy + 2):
+                if y1 <= y < y2:
+                    acc = acc + 0.5 * sum(k11[t] * blur5_rows(Ah16, y1 + int(refl(np.array(y - y1 + t - 5), bh))) for t in range(11))
+                else:
+                    acc = acc + 0.5 * blur5_rows(Ah6, y)
+            out[oy] = acc / 255.0
+        assert np.abs(out - want).max() < 1e-9, (H, W, float(np.abs(out - want).max()))
+        # off the band the vertical direction collapses to the same w6: rows 4o-1 .. 4o+4
+        for oy in range(oh):
+            if not (y1 <= 4 * oy + 2 and 4 * oy + 1 < y2):
+                rows = refl(4 * oy - 1 + np.arange(6), H)
+                assert np.abs((Ah6[rows] * w6[:, None]).sum(0) / 255.0 - want[oy]).max() < 1e-9
