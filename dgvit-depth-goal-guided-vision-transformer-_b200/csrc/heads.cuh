@@ -61,8 +61,6 @@ __device__ __forceinline__ void stage_matrix(float* dst, int pitch, const float*
 // q-th quarter of the contraction for all S samples (weights conflict-free through the odd row pitch, inputs
 // broadcast as float4); the four quarters are summed in a fixed order through shared memory.
 __global__ void __launch_bounds__(FWD_THREADS) head_fwd_kernel(FwdArgs a) {
-  pdl_wait();
-  pdl_launch();
   extern __shared__ __align__(16) float sm[];
   const HeadW& w = a.w[blockIdx.y];
   const int K0 = a.K1 + a.K2, H2 = a.H2, NO = a.NOa + a.NOb;
@@ -85,6 +83,11 @@ __global__ void __launch_bounds__(FWD_THREADS) head_fwd_kernel(FwdArgs a) {
   for (int i = tid; i < H1; i += FWD_THREADS) b1s[i] = w.b1[i];
   for (int i = tid; i < H2; i += FWD_THREADS) b2s[i] = w.b2[i];
   for (int i = tid; i < NO; i += FWD_THREADS) b3s[i] = i < a.NOa ? w.b3a[i] : w.b3b[i - a.NOa];
+  // Everything above reads PARAMETERS only: under programmatic dependent launch it runs while the trunk's last kernel is
+  // still finishing (the weight staging is most of this kernel's latency).  The launch right after a kernel that rewrites
+  // parameters is never programmatic (common.cuh), so the weights are final here.  Activations only after the wait.
+  pdl_wait();
+  pdl_launch();
   const int j = tid & (H1 - 1), q = tid >> 7;
   for (int s0 = blockIdx.x * S; s0 < a.B; s0 += gridDim.x * S) {
     __syncthreads();
@@ -181,8 +184,6 @@ struct BwdArgs {
 };
 
 __global__ void __launch_bounds__(BWD_THREADS) head_bwd_dx_kernel(BwdArgs a) {
-  pdl_wait();
-  pdl_launch();
   extern __shared__ __align__(16) float sm[];
   const BwdHead& h = a.h[blockIdx.y];
   const int K0 = a.K0, H2 = a.H2, NO = a.NOa + a.NOb;
@@ -197,6 +198,8 @@ __global__ void __launch_bounds__(BWD_THREADS) head_bwd_dx_kernel(BwdArgs a) {
   stage_matrix(W2s, H1, h.W2, H2, H1, tid, BWD_THREADS);
   stage_matrix(W3s, H2, h.W3a, a.NOa, H2, tid, BWD_THREADS);
   if (a.NOb) stage_matrix(W3s + a.NOa * H2, H2, h.W3b, a.NOb, H2, tid, BWD_THREADS);
+  pdl_wait();            // (parameters staged before the wait, as in the forward)
+  pdl_launch();
   for (int s0 = blockIdx.x * S; s0 < a.B; s0 += gridDim.x * S) {
     __syncthreads();
     if (tid < NO * S) {
